@@ -186,9 +186,12 @@ def random_codes(rng, n, gc):
 
 
 def make_genomes(seed: int, tax: Taxonomy, genome_len: int, share_frac: float = 0.10, mut: float = 0.02,
-                 gc_range=(0.3, 0.7)) -> dict:
+                 gc_range=(0.3, 0.7), conserved_rank: str | None = None, conserved_len: int = 0,
+                 conserved_mut: float = 0.002) -> dict:
     """tid -> uint8 code array.  ``share_frac`` of each genome is copied (with ``mut`` substitutions)
-    from the previous genome under the same parent, creating multi-tid k-mers."""
+    from the previous genome under the same parent, creating multi-tid k-mers.
+    With ``conserved_rank`` every node of that rank also plants one ``conserved_len`` segment into all
+    genomes below it, which yields long taxid lists (tens of tids) for the k-mers inside it."""
     rng = rng_for(seed)
     genomes = {}
     last_by_parent = {}
@@ -209,6 +212,16 @@ def make_genomes(seed: int, tax: Taxonomy, genome_len: int, share_frac: float = 
             g[dst0:dst0 + n] = seg
         genomes[tid] = g
         last_by_parent[par] = tid
+    if conserved_rank and conserved_len:
+        for node in [t for t in tax.tids() if tax.rank[t] == conserved_rank]:
+            seg0 = random_codes(rng, conserved_len, rng.uniform(*gc_range))
+            for tid in tax.leaves:
+                if node in tax.path_to_root(tid) and len(genomes[tid]) >= conserved_len:
+                    seg = seg0.copy()
+                    flip = rng.random(conserved_len) < conserved_mut
+                    seg[flip] = (seg[flip] + rng.integers(1, 4, size=int(flip.sum()))) % 4
+                    d0 = int(rng.integers(0, len(genomes[tid]) - conserved_len + 1))
+                    genomes[tid][d0:d0 + conserved_len] = seg
     return genomes
 
 

@@ -1,0 +1,68 @@
+"""Shared fixture scenarios for the parity tests and for tests/golden/make_golden.py.
+
+A scenario = seeded taxonomy + genomes + reads + null models written to a work directory.  The DB
+itself is built by the caller: here in the build container through the unmodified reference chain
+(oracle/refchain.py), on the GPU box from the committed golden table dump.
+"""
+from __future__ import annotations
+
+import os
+
+from lmat_b200 import fixtures as fx
+
+K = 20
+
+SCENARIOS = {
+    # name: (tax seed, n_leaves, genome_len, share, conserved_rank, conserved_len, n_reads, read_len)
+    "small": dict(seed=7, n_leaves=24, genome_len=4000, share=0.3, cons_rank=None, cons_len=0, n_reads=400, read_len=150),
+    "lists": dict(seed=17, n_leaves=90, genome_len=3000, share=0.4, cons_rank="order", cons_len=500, n_reads=600, read_len=150),
+    "mixed": dict(seed=27, n_leaves=40, genome_len=5000, share=0.3, cons_rank="family", cons_len=300, n_reads=500, read_len=120),
+}
+
+# option sets applied to read_label (reference flags) / to the oracle and product (field names)
+OPTION_SETS = {
+    "run_rl": dict(null=True, min_kmer=30, hbias=0.0, sdiff=1.0, min_score=0.0, prn_all=True),
+    "nonull": dict(null=False, min_kmer=30, hbias=0.0, sdiff=1.0, min_score=0.0, prn_all=True),
+    "defaults": dict(null=True, min_kmer=35, hbias=3.0, sdiff=1.0, min_score=0.0, prn_all=False),
+    "tight": dict(null=True, min_kmer=30, hbias=1.5, sdiff=0.25, min_score=0.5, prn_all=True),
+    "permissive": dict(null=True, min_kmer=30, hbias=0.0, sdiff=1.0, min_score=0.0, prn_all=True, permissive=True),
+    "prune3": dict(null=True, min_kmer=30, hbias=0.0, sdiff=1.0, min_score=0.0, prn_all=True, prune=3),
+    "nophix_hide": dict(null=True, min_kmer=30, hbias=0.0, sdiff=2.0, min_score=0.0, prn_all=False, phix_off=True, hide_read=True),
+    "quirk": dict(null=True, min_kmer=30, hbias=0.0, sdiff=1.0, min_score=0.0, prn_all=True, min_fnd=40),
+    "plasmid": dict(null=False, min_kmer=30, hbias=0.0, sdiff=1.0, min_score=0.0, prn_all=True, plasmids=True),
+}
+
+
+def build_inputs(name: str, workdir: str) -> dict:
+    """Write every text input of a scenario; returns paths + in-memory objects."""
+    sc = SCENARIOS[name]
+    os.makedirs(workdir, exist_ok=True)
+    tax = fx.make_taxonomy(sc["seed"], sc["n_leaves"], specials=True)
+    paths = fx.write_taxonomy_files(tax, workdir)
+    genomes = fx.make_genomes(sc["seed"] + 1, tax, sc["genome_len"], share_frac=sc["share"],
+                              conserved_rank=sc["cons_rank"], conserved_len=sc["cons_len"])
+    paths["genomes"] = os.path.join(workdir, "genomes.fa")
+    fx.write_kpc_fasta(paths["genomes"], genomes)
+    hdrs, seqs = fx.simulate_reads(sc["seed"] + 2, genomes, sc["n_reads"], sc["read_len"], n_rate=0.003,
+                                   lower_frac=0.1, len_jitter=40)
+    # hand-made edge cases: too short, exactly k, all N, GC-only (bin_sel = 10), period-25 repeat
+    # (the silent-NoMatch quirk of SURVEY.md 2.2.7), a read with no header
+    g0 = fx.codes_to_str(next(iter(genomes.values())))
+    extra = [("short", "ACGTACGTAC"), ("exact_k", g0[100:120]), ("all_n", "N" * 60),
+             ("gc_only", "GC" * 40), ("period25", (g0[200:225] * 4)[:80]), ("", g0[300:420]),
+             ("lower_n", g0[500:560].lower() + "n" + g0[561:640].lower())]
+    for h, s in extra:
+        hdrs.append(h)
+        seqs.append(s)
+    paths["reads"] = os.path.join(workdir, "reads.fa")
+    fx.write_fasta(paths["reads"], hdrs, seqs)
+    paths["reads_wrapped"] = os.path.join(workdir, "reads_wrapped.fa")
+    fx.write_fasta(paths["reads_wrapped"], hdrs, seqs, wrap=60)
+    paths["reads_fq"] = os.path.join(workdir, "reads.fq")
+    fx.write_fastq(paths["reads_fq"], [h or "nohdr" for h in hdrs], seqs)
+    paths["null_lst"] = fx.write_null_models(sc["seed"] + 3, tax, workdir)
+    paths["plasmids"] = os.path.join(workdir, "plasmids.txt")
+    with open(paths["plasmids"], "w") as f:
+        f.write(f"{tax.leaves[0]}\n{tax.leaves[3]}\n")
+    paths["workdir"] = workdir
+    return dict(paths=paths, tax=tax, genomes=genomes, hdrs=hdrs, seqs=seqs)
