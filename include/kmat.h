@@ -1,0 +1,198 @@
+/* kmat.h -- C ABI of libkmat, a B200-native (sm_100a) implementation of LMAT's read_label hot path.
+ *
+ * Drop-in boundary.  The reference (LivGen/LMAT v1.2.4_2018a) has no FFI layer; the seam this ABI
+ * replaces is the in-process call
+ *     proc_line(tax_tree, len, read, k, INDEXDB<DBTID_T>* table, ofs, threshold, sopt, max_count, ...)
+ *                                                                       (src/read_label.cpp:1211-1212, call site :1746)
+ * and, beneath it, the duck-typed table contract
+ *     bool begin_(u64 kmer, u16& count, u32& offset, u8& page);  void next(u32&, u8&, tid_T&);
+ *     char get_kmer_length();  size_t size();                (src/kmerdb/SortedDb.hpp:188,366,433,438)
+ * Each entry point below names the reference interface it stands in for.  Plain C types only: the
+ * caller owns every host buffer, the library owns all device memory, every call returns 0 or a
+ * negative KMAT_ERR_* (no exit(), no exceptions).  There is NO CPU fallback: calls that need the GPU
+ * fail with KMAT_ERR_NO_DEVICE / KMAT_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef KMAT_H
+#define KMAT_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMAT_ABI_VERSION 1
+
+enum {
+    KMAT_OK = 0,
+    KMAT_ERR_ARG = -1,         /* bad argument                                                      */
+    KMAT_ERR_NO_DEVICE = -2,   /* no CUDA device / driver                                           */
+    KMAT_ERR_CUDA = -3,        /* a CUDA call failed (see kmat_last_error)                          */
+    KMAT_ERR_NOMEM = -4,
+    KMAT_ERR_IO = -5,          /* file missing / unreadable (reference: cerr + return -1)           */
+    KMAT_ERR_FORMAT = -6,      /* malformed input file / DB image                                   */
+    KMAT_ERR_UNSUPPORTED = -7, /* valid for the reference but outside what this build handles       */
+    KMAT_ERR_BAD_TAXID = -8,   /* stored id missing from the -f map: reference asserts (TaxNodeStat.hpp:140-144,235-238) */
+    KMAT_ERR_TREE = -9,        /* taxonomy is not a forest (missing parent / cycle): reference exits or hangs (TaxTree.hpp:73-77) */
+    KMAT_ERR_OVERFLOW = -10    /* caller-provided output buffer too small; required size is reported */
+};
+
+/* ---- opaque handles ------------------------------------------------------------------------- */
+typedef struct kmat_table kmat_table;   /* host-side logical table: ascending k-mers + CSR lists of stored ids     */
+typedef struct kmat_db kmat_db;         /* device-resident bucketised hash table (one per device / shard)          */
+typedef struct kmat_inputs kmat_inputs; /* parsed run-time text inputs (-c -e -w -f -m -r -n)                       */
+typedef struct kmat_ctx kmat_ctx;       /* device-resident taxonomy + null models + options, bound to one kmat_db  */
+
+const char *kmat_strerror(int code);
+const char *kmat_last_error(void);      /* thread-local detail of the last failure */
+int kmat_abi_version(void);
+int kmat_device_count(void);            /* 0 when no usable GPU (never an error) */
+
+/* ---- table ingest (host) ---------------------------------------------------------------------
+ * Replaces: `perm(&taxtable,..); mopen(db,"r",0)` + the SortedDb members reached through begin_/next
+ * (read_label.cpp:1481-1489; layout SortedDb.hpp:143-148,453-481).  A reference-side binding passes
+ * the three arrays of its mapped SortedDb object. */
+int kmat_table_from_sorteddb(const uint64_t *top_tier_block, uint64_t tt_block_count, int bits_per_2nd,
+                             const void *kmer_table /* 8-byte kmer_record[] */, uint64_t n_records,
+                             const char *storage_space, uint64_t storage_bytes,
+                             int kmer_length, int tid_bytes /* sizeof(DBTID_T): 2 or 4 */, kmat_table **out);
+/* From a logical dump: kmers strictly ascending, offs[n+1], ids = stored ids (as next() would yield them). */
+int kmat_table_from_arrays(const uint64_t *kmers, const uint64_t *offs, const uint32_t *ids, uint64_t n_kmers,
+                           int kmer_length, int tid_bytes, kmat_table **out);
+/* Open a DB file: a flat ".kmat" image written by kmat_table_save, or the KMPERM01 heap image that
+ * oracle/_ref/make_db_table writes (real perm-je heaps: parity unpinned, KMAT_ERR_FORMAT). */
+int kmat_table_open(const char *path, int tid_bytes, kmat_table **out);
+int kmat_table_save(const kmat_table *, const char *path);
+uint64_t kmat_table_size(const kmat_table *);        /* SortedDb::size()            (SortedDb.hpp:438) */
+int kmat_table_kmer_length(const kmat_table *);      /* SortedDb::get_kmer_length() (SortedDb.hpp:433) */
+int kmat_table_tid_bytes(const kmat_table *);
+/* Borrowed views for inspection (valid until kmat_table_free). */
+int kmat_table_view(const kmat_table *, const uint64_t **kmers, const uint64_t **offs, const uint32_t **ids,
+                    uint64_t *n_ids);
+void kmat_table_free(kmat_table *);
+
+/* ---- device table ---------------------------------------------------------------------------- */
+/* Build the HBM hash table on `device`.  shard_count > 1 keeps only k-mers whose
+ * kmat_shard_of(kmer) == shard_index (DB-sharded mode, SURVEY.md 8(e) mode B). */
+int kmat_db_upload(const kmat_table *, int device, int shard_index, int shard_count, kmat_db **out);
+/* Same, from DEVICE arrays already resident on `device` (used to build very large synthetic tables
+ * without a host round trip): payload[i] = stored id for singletons, or (1u<<31 | pool offset in
+ * 4-byte words) for lists; pool = the list pool ([count][ids...] records). */
+int kmat_db_build_device(int device, int kmer_length, int tid_bytes, uint64_t n_kmers,
+                         const uint64_t *d_kmers, const uint32_t *d_payload,
+                         const uint32_t *d_pool, uint64_t pool_words, uint32_t n_stored_ids, kmat_db **out);
+uint32_t kmat_shard_of(uint64_t kmer, int kmer_length, int shard_count);
+uint64_t kmat_db_size(const kmat_db *);
+uint64_t kmat_db_bytes(const kmat_db *);             /* device bytes held */
+int kmat_db_kmer_length(const kmat_db *);
+int kmat_db_device(const kmat_db *);
+void kmat_db_free(kmat_db *);
+
+/* K2 parity hook.  Replaces TaxNodeStat::begin(kmer) + next() loop with no pruning
+ * (TaxNodeStat.hpp:41-58,208-256).  Host buffers; hit_off has n+1 entries; ids receives the stored
+ * ids of every hit in list order.  On KMAT_ERR_OVERFLOW *n_ids is the capacity needed. */
+int kmat_lookup_batch(const kmat_db *, const uint64_t *kmers, uint32_t n, uint64_t *hit_off, uint32_t *ids,
+                      uint64_t ids_cap, uint64_t *n_ids);
+
+/* K1 parity hook.  Replaces the rolling encoder of retrieve_kmer_labels (read_label.cpp:978-1017,
+ * 1205-1206) for a batch of reads.  kmers/flags are indexed by base offset (offs[r] + p for k-mer
+ * start position p; the k-1 tail slots of each read are unused): flags 0 = no valid k-mer, 1 = valid
+ * first occurrence, 2 = valid duplicate.  valid_kmers[r], bin_sel[r] per read. */
+int kmat_encode_batch(const kmat_db *, const char *bases, const uint64_t *offs, uint32_t n_reads,
+                      uint64_t *kmers, uint8_t *flags, int32_t *valid_kmers, int32_t *bin_sel);
+
+/* ---- run-time inputs --------------------------------------------------------------------------
+ * Replaces the loaders in read_label main(): TaxTree ctor (-c, TaxTree.hpp:24-57), depth map (-e,
+ * :1573-1582), gRank_table (-w, :1560-1567), conv_map (-f, :1585-1602), tid_rank_map (-m, :1543-1559),
+ * loadLowNumPlasmids (-r, :499-510), loadRandHits (-n, :512-678; lmat_dir = $LMAT_DIR).  Any path may
+ * be NULL (option absent). */
+int kmat_inputs_load(const char *tree, const char *depth, const char *rank, const char *conv16, const char *numrank,
+                     const char *plasmids, const char *null_list, const char *lmat_dir, kmat_inputs **out);
+void kmat_inputs_free(kmat_inputs *);
+
+typedef struct {
+    int32_t min_kmer;      /* -j, default 35 (run_rl.sh passes 30)        read_label.cpp:1337,1364 */
+    int32_t min_fnd_kmer;  /* -z, default 1                                :1337,1367 */
+    float sdiff;           /* -b, ScoreOptions::_diff_thresh, default 1.0  :488,1388  */
+    float hbias;           /* -l, ScoreOptions::_diff_thresh2, default 3.0 :488,1391  */
+    float min_score;       /* -x, default 0 (host tallies only)            :1336,1373 */
+    int32_t max_count;     /* -g, default 65535 = uint16_t(~0)             :1346,1422 */
+    int32_t permissive;    /* -s                                           :1382      */
+    int32_t phix_screen;   /* default 1; -h clears                         :41,1355   */
+    int32_t want_lineage;  /* also return the valid_cand list (printed on MultiMatch without -p, :917-927) */
+} kmat_opts;
+void kmat_opts_default(kmat_opts *);
+
+int kmat_ctx_create(const kmat_db *, const kmat_inputs *, const kmat_opts *, kmat_ctx **out);
+int kmat_ctx_set_opts(kmat_ctx *, const kmat_opts *);
+void kmat_ctx_destroy(kmat_ctx *);
+
+/* ---- per-read results ------------------------------------------------------------------------- */
+enum { KMAT_DIRECT = 0, KMAT_MULTI = 1, KMAT_PARTIAL = 2, KMAT_NOMATCH = 3, KMAT_LCA_ERROR = 4 }; /* match_t, read_label.cpp:202 */
+enum {
+    KMAT_ST_SHORT_LEN = 0,   /* len < k: "-1 -1 -1\t-1 -1\t<len> <k> ReadTooShort"              :1217-1218 */
+    KMAT_ST_SHORT_VALID = 1, /* valid_kmers < -j: "... <valid> <min_kmer> ReadTooShort"          :1232-1233 */
+    KMAT_ST_NODBHITS = 2,    /* no taxid: "-1 -1 <valid>\t-1 -1\t<len> <k> NoDbHits"             :1270-1271 */
+    KMAT_ST_SILENT = 3,      /* construct_labels early NoMatch: NOTHING is written, tallied NoDbHits :727-733,1248-1253 */
+    KMAT_ST_PHIX = 4,        /* PhiX / artificial-sequence bypass                                 :841-848  */
+    KMAT_ST_LABELED = 5,     /* normal line                                                        :894-937  */
+    KMAT_ST_ERROR = 6        /* this read could not be processed; see err */
+};
+typedef struct { uint32_t tid; float score; } kmat_pair;
+typedef struct {
+    int32_t status;          /* KMAT_ST_*                                                    */
+    int32_t n1, n2;          /* the two integers of the ReadTooShort / NoDbHits lines        */
+    int32_t valid_kmers;     /* retrieve_kmer_labels().first                                  */
+    int32_t cand_kmer_cnt;   /* construct_labels: positions with label_vec[pos].first >= 0    */
+    int32_t match;           /* KMAT_DIRECT ...                                               */
+    uint32_t tid;            /* best_guess.first                                              */
+    float score;             /* best_guess.second                                             */
+    float log_avg, stdev;    /* first two numbers of the normal line                          */
+    uint32_t n_cand;         /* rank_label after sort(TCmp), ascending (printed descending)   */
+    uint32_t n_lin;          /* valid_cand list (only when opts.want_lineage)                 */
+    uint64_t cand_off;       /* offsets into the cands / lineage output arrays                */
+    uint64_t lin_off;
+    int32_t bin_sel;         /* GC bin                                                         */
+    int32_t err;             /* KMAT_ERR_* for status == KMAT_ST_ERROR, else 0                */
+} kmat_read_result;
+
+/* THE hot path.  Replaces one proc_line() call per read (read_label.cpp:1211-1279) for a batch:
+ * bases = concatenated reads (any bytes; non-ACGT resets the k-mer run), offs[n+1] byte offsets.
+ * Host buffers in, host buffers out; device work runs on an internal stream and the call returns
+ * when the results are in `out`.  cands/lineage may be NULL (then n_cand/n_lin are still reported);
+ * on KMAT_ERR_OVERFLOW *n_cands / *n_lineage hold the capacities needed and `out` is valid. */
+int kmat_label_batch(kmat_ctx *, const char *bases, const uint64_t *offs, uint32_t n_reads, kmat_read_result *out,
+                     kmat_pair *cands, uint64_t cands_cap, uint64_t *n_cands,
+                     kmat_pair *lineage, uint64_t lineage_cap, uint64_t *n_lineage);
+
+/* Device-resident variant used for kernel-only timing and multi-batch pipelines: inputs already in
+ * HBM (d_bases, d_offs on the ctx's device); results stay on the device (d_out) unless NULL.
+ * max_read_len bounds the longest read of the batch (sizes the per-warp dedup sets).
+ * stream = a cudaStream_t cast to void* (NULL = the ctx's own stream); does not synchronise. */
+int kmat_label_batch_device(kmat_ctx *, const char *d_bases, const uint64_t *d_offs, uint32_t n_reads,
+                            uint64_t total_bases, uint32_t max_read_len, kmat_read_result *d_out, void *stream);
+int kmat_ctx_sync(kmat_ctx *);
+/* Statistics of the last batch (device counters read back): unique k-mer lookups issued, hits, list
+ * hits, total list ids, and the algorithmic table bytes of SURVEY.md 8(d). */
+typedef struct {
+    uint64_t lookups, hits, list_hits, list_ids, probe_extra_buckets, algorithmic_bytes;
+    uint64_t reads_fast, reads_slow, reads_error;
+} kmat_batch_stats;
+int kmat_ctx_last_stats(kmat_ctx *, kmat_batch_stats *);
+/* Kernel launches issued by this library since load (bench.py's gpu_launches). */
+uint64_t kmat_launch_count(void);
+
+/* Text after "hdr\tread\t" exactly as the reference writes it (read_label.cpp:1218,1233,1271,
+ * 844-848,894-937; floats via ostream<<float == "%g").  prn_all = -p.  Returns bytes written
+ * (0 for KMAT_ST_SILENT: the reference writes nothing, not even '\n') or <0 if cap is too small. */
+int kmat_format_tail(const kmat_read_result *, const kmat_pair *cands, const kmat_pair *lineage, int prn_all,
+                     char *buf, size_t cap);
+
+/* Random-access HBM roofline probe: uniform random `access_bytes`-wide loads
+ * (8, 16 or 32) over a `span_bytes` device allocation; returns achieved gathers/s. */
+int kmat_gather_bench(int device, uint64_t span_bytes, int access_bytes, uint64_t n_gathers, int iters,
+                      double *gathers_per_s, double *sector_gbps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,327 @@
+"""ctypes binding of libkmat's C ABI (include/kmat.h) -- the host-side mirror used by tests and bench.py.
+
+Nothing here computes: every method is a thin call through the C ABI into the CUDA library.  If the
+shared library is missing it is built in-tree with nvcc (lmat_b200.build); if no GPU is present the
+compute calls raise KmatError (KMAT_ERR_NO_DEVICE) -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+ST_NAMES = ["SHORT_LEN", "SHORT_VALID", "NODBHITS", "SILENT", "PHIX", "LABELED", "ERROR"]
+MATCH_NAMES = ["DirectMatch", "MultiMatch", "PartialMultiMatch", "NoMatch", "LCA_ERROR"]
+
+RESULT_DTYPE = np.dtype([("status", "<i4"), ("n1", "<i4"), ("n2", "<i4"), ("valid_kmers", "<i4"),
+                         ("cand_kmer_cnt", "<i4"), ("match", "<i4"), ("tid", "<u4"), ("score", "<f4"),
+                         ("log_avg", "<f4"), ("stdev", "<f4"), ("n_cand", "<u4"), ("n_lin", "<u4"),
+                         ("cand_off", "<u8"), ("lin_off", "<u8"), ("bin_sel", "<i4"), ("err", "<i4")])
+PAIR_DTYPE = np.dtype([("tid", "<u4"), ("score", "<f4")])
+
+
+class Opts(C.Structure):
+    _fields_ = [("min_kmer", C.c_int32), ("min_fnd_kmer", C.c_int32), ("sdiff", C.c_float), ("hbias", C.c_float),
+                ("min_score", C.c_float), ("max_count", C.c_int32), ("permissive", C.c_int32),
+                ("phix_screen", C.c_int32), ("want_lineage", C.c_int32)]
+
+
+class BatchStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("lookups", "hits", "list_hits", "list_ids", "probe_extra_buckets",
+                                           "algorithmic_bytes", "reads_fast", "reads_slow", "reads_error")]
+
+
+class KmatError(RuntimeError):
+    def __init__(self, code, detail):
+        super().__init__(f"libkmat error {code}: {detail}")
+        self.code = code
+
+
+EXPORTS = [
+    "kmat_strerror", "kmat_last_error", "kmat_abi_version", "kmat_device_count", "kmat_table_from_sorteddb",
+    "kmat_table_from_arrays", "kmat_table_open", "kmat_table_save", "kmat_table_size", "kmat_table_kmer_length",
+    "kmat_table_tid_bytes", "kmat_table_view", "kmat_table_free", "kmat_db_upload", "kmat_db_build_device",
+    "kmat_shard_of", "kmat_db_size", "kmat_db_bytes", "kmat_db_kmer_length", "kmat_db_device", "kmat_db_free",
+    "kmat_lookup_batch", "kmat_encode_batch", "kmat_inputs_load", "kmat_inputs_free", "kmat_opts_default",
+    "kmat_ctx_create", "kmat_ctx_set_opts", "kmat_ctx_destroy", "kmat_label_batch", "kmat_label_batch_device",
+    "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench",
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build_lib()
+    L = C.CDLL(path)
+    vp, u64p = C.c_void_p, C.c_void_p
+    L.kmat_strerror.restype = C.c_char_p
+    L.kmat_strerror.argtypes = [C.c_int]
+    L.kmat_last_error.restype = C.c_char_p
+    L.kmat_table_from_sorteddb.argtypes = [vp, C.c_uint64, C.c_int, vp, C.c_uint64, vp, C.c_uint64, C.c_int, C.c_int, C.POINTER(vp)]
+    L.kmat_table_from_arrays.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, C.POINTER(vp)]
+    L.kmat_table_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.kmat_table_save.argtypes = [vp, C.c_char_p]
+    L.kmat_table_size.restype = C.c_uint64
+    L.kmat_table_size.argtypes = [vp]
+    L.kmat_table_kmer_length.argtypes = [vp]
+    L.kmat_table_tid_bytes.argtypes = [vp]
+    L.kmat_table_view.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.kmat_table_free.argtypes = [vp]
+    L.kmat_db_upload.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.kmat_db_build_device.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, vp, vp, vp, C.c_uint64, C.c_uint32, C.POINTER(vp)]
+    L.kmat_shard_of.restype = C.c_uint32
+    L.kmat_shard_of.argtypes = [C.c_uint64, C.c_int, C.c_int]
+    L.kmat_db_size.restype = C.c_uint64
+    L.kmat_db_size.argtypes = [vp]
+    L.kmat_db_bytes.restype = C.c_uint64
+    L.kmat_db_bytes.argtypes = [vp]
+    L.kmat_db_kmer_length.argtypes = [vp]
+    L.kmat_db_device.argtypes = [vp]
+    L.kmat_db_free.argtypes = [vp]
+    L.kmat_lookup_batch.argtypes = [vp, vp, C.c_uint32, vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.kmat_encode_batch.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, vp, vp]
+    L.kmat_inputs_load.argtypes = [C.c_char_p] * 8 + [C.POINTER(vp)]
+    L.kmat_inputs_free.argtypes = [vp]
+    L.kmat_opts_default.argtypes = [C.POINTER(Opts)]
+    L.kmat_ctx_create.argtypes = [vp, vp, C.POINTER(Opts), C.POINTER(vp)]
+    L.kmat_ctx_set_opts.argtypes = [vp, C.POINTER(Opts)]
+    L.kmat_ctx_destroy.argtypes = [vp]
+    L.kmat_label_batch.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, C.POINTER(C.c_uint64), vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.kmat_label_batch_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, vp, vp]
+    L.kmat_ctx_sync.argtypes = [vp]
+    L.kmat_ctx_last_stats.argtypes = [vp, C.POINTER(BatchStats)]
+    L.kmat_launch_count.restype = C.c_uint64
+    L.kmat_format_tail.argtypes = [vp, vp, vp, C.c_int, C.c_char_p, C.c_size_t]
+    L.kmat_gather_bench.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc < 0:
+        L = lib()
+        raise KmatError(rc, f"{L.kmat_strerror(rc).decode()}: {L.kmat_last_error().decode(errors='replace')}")
+    return rc
+
+
+def device_count() -> int:
+    return lib().kmat_device_count()
+
+
+def _b(s):
+    return None if s is None else os.fsencode(s)
+
+
+class Table:
+    """Host logical table (SortedDb contents flattened)."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @classmethod
+    def from_arrays(cls, kmers, offs, ids, kmer_len=20, tid_bytes=2):
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        h = C.c_void_p()
+        _check(lib().kmat_table_from_arrays(kmers.ctypes.data, offs.ctypes.data, ids.ctypes.data, len(kmers), kmer_len, tid_bytes, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_sorteddb(cls, top_tier, kmer_table, storage, kmer_len=20, tid_bytes=2):
+        """top_tier: uint64 array; kmer_table: raw bytes of kmer_record[]; storage: raw bytes (reference layout)."""
+        h = C.c_void_p()
+        bits = 13 if kmer_len == 20 else 9
+        _check(lib().kmat_table_from_sorteddb(top_tier.ctypes.data, len(top_tier), bits, kmer_table.ctypes.data, len(kmer_table) // 8,
+                                              storage.ctypes.data, len(storage), kmer_len, tid_bytes, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def open(cls, path, tid_bytes=2):
+        h = C.c_void_p()
+        _check(lib().kmat_table_open(_b(path), tid_bytes, C.byref(h)))
+        return cls(h)
+
+    def save(self, path):
+        _check(lib().kmat_table_save(self.h, _b(path)))
+
+    @property
+    def size(self):
+        return lib().kmat_table_size(self.h)
+
+    @property
+    def kmer_length(self):
+        return lib().kmat_table_kmer_length(self.h)
+
+    def arrays(self):
+        k, o, i = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n_ids = C.c_uint64()
+        _check(lib().kmat_table_view(self.h, C.byref(k), C.byref(o), C.byref(i), C.byref(n_ids)))
+        n = self.size
+        kmers = np.ctypeslib.as_array(C.cast(k, C.POINTER(C.c_uint64)), shape=(max(n, 1),))[:n].copy()
+        offs = np.ctypeslib.as_array(C.cast(o, C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
+        ids = np.ctypeslib.as_array(C.cast(i, C.POINTER(C.c_uint32)), shape=(max(n_ids.value, 1),))[:n_ids.value].copy()
+        return kmers, offs, ids
+
+    def __del__(self):
+        try:
+            lib().kmat_table_free(self.h)
+        except Exception:
+            pass
+
+
+class Db:
+    """Device-resident hash table."""
+
+    def __init__(self, handle, keep=None):
+        self.h = handle
+        self._keep = keep
+
+    @classmethod
+    def upload(cls, table: Table, device=0, shard_index=0, shard_count=1):
+        h = C.c_void_p()
+        _check(lib().kmat_db_upload(table.h, device, shard_index, shard_count, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def build_device(cls, device, kmer_len, tid_bytes, n, d_kmers_ptr, d_payload_ptr, d_pool_ptr, pool_words, n_stored_ids=0):
+        h = C.c_void_p()
+        _check(lib().kmat_db_build_device(device, kmer_len, tid_bytes, n, d_kmers_ptr, d_payload_ptr, d_pool_ptr, pool_words, n_stored_ids, C.byref(h)))
+        return cls(h)
+
+    @property
+    def size(self):
+        return lib().kmat_db_size(self.h)
+
+    @property
+    def bytes(self):
+        return lib().kmat_db_bytes(self.h)
+
+    @property
+    def kmer_length(self):
+        return lib().kmat_db_kmer_length(self.h)
+
+    def lookup(self, kmers):
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+        offs = np.zeros(len(kmers) + 1, dtype=np.uint64)
+        n_ids = C.c_uint64()
+        cap = max(1024, 4 * len(kmers))
+        while True:
+            ids = np.zeros(cap, dtype=np.uint32)
+            rc = lib().kmat_lookup_batch(self.h, kmers.ctypes.data, len(kmers), offs.ctypes.data, ids.ctypes.data, cap, C.byref(n_ids))
+            if rc == -10:
+                cap = int(n_ids.value)
+                continue
+            _check(rc)
+            return offs, ids[:n_ids.value]
+
+    def encode(self, seqs):
+        blob, offs = pack_reads(seqs)
+        total = int(offs[-1])
+        kmers = np.zeros(total + 1, dtype=np.uint64)
+        flags = np.zeros(total + 1, dtype=np.uint8)
+        valid = np.zeros(len(seqs), dtype=np.int32)
+        bins = np.zeros(len(seqs), dtype=np.int32)
+        _check(lib().kmat_encode_batch(self.h, blob, offs.ctypes.data, len(seqs), kmers.ctypes.data, flags.ctypes.data, valid.ctypes.data, bins.ctypes.data))
+        return kmers, flags, valid, bins, offs
+
+    def __del__(self):
+        try:
+            lib().kmat_db_free(self.h)
+        except Exception:
+            pass
+
+
+class Inputs:
+    def __init__(self, tree=None, depth=None, rank=None, map16=None, numrank=None, plasmids=None, null_lst=None, lmat_dir=None):
+        self.h = C.c_void_p()
+        _check(lib().kmat_inputs_load(_b(tree), _b(depth), _b(rank), _b(map16), _b(numrank), _b(plasmids), _b(null_lst), _b(lmat_dir), C.byref(self.h)))
+
+    def __del__(self):
+        try:
+            lib().kmat_inputs_free(self.h)
+        except Exception:
+            pass
+
+
+def pack_reads(seqs):
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    offs = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        offs[1:] = np.cumsum([len(b) for b in bs])
+    return b"".join(bs), offs
+
+
+def default_opts(**kw) -> Opts:
+    o = Opts()
+    lib().kmat_opts_default(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+class Ctx:
+    def __init__(self, db: Db, inputs: Inputs, opts: Opts | None = None):
+        self.db, self.inputs = db, inputs
+        self.opts = opts or default_opts()
+        self.h = C.c_void_p()
+        _check(lib().kmat_ctx_create(db.h, inputs.h, C.byref(self.opts), C.byref(self.h)))
+
+    def set_opts(self, **kw):
+        for k, v in kw.items():
+            setattr(self.opts, k, v)
+        _check(lib().kmat_ctx_set_opts(self.h, C.byref(self.opts)))
+
+    def label(self, seqs=None, blob=None, offs=None):
+        """Label a batch through kmat_label_batch (host buffers in, host buffers out)."""
+        if seqs is not None:
+            blob, offs = pack_reads(seqs)
+        n = len(offs) - 1
+        res = np.zeros(n, dtype=RESULT_DTYPE)
+        cap = max(4096, 32 * n)
+        n_c, n_l = C.c_uint64(), C.c_uint64()
+        while True:
+            cands = np.zeros(cap, dtype=PAIR_DTYPE)
+            lin = np.zeros(cap if self.opts.want_lineage else 1, dtype=PAIR_DTYPE)
+            ptr = blob if isinstance(blob, (bytes, bytearray)) else blob.ctypes.data
+            rc = lib().kmat_label_batch(self.h, ptr, offs.ctypes.data, n, res.ctypes.data, cands.ctypes.data, len(cands), C.byref(n_c),
+                                        lin.ctypes.data if self.opts.want_lineage else None, len(lin), C.byref(n_l))
+            if rc == -10:
+                cap = int(max(n_c.value, n_l.value)) + 16
+                continue
+            _check(rc)
+            return res, cands[:n_c.value], lin[:n_l.value]
+
+    def tails(self, res, cands, lin, prn_all=True):
+        out = []
+        buf = C.create_string_buffer(1 << 20)
+        cp = cands.ctypes.data if len(cands) else None
+        lp = lin.ctypes.data if len(lin) else None
+        for i in range(len(res)):
+            n = lib().kmat_format_tail(res[i:i + 1].ctypes.data, cp, lp, int(prn_all), buf, len(buf))
+            _check(n)
+            out.append(buf.raw[:n].decode())
+        return out
+
+    def stats(self) -> BatchStats:
+        s = BatchStats()
+        _check(lib().kmat_ctx_last_stats(self.h, C.byref(s)))
+        return s
+
+    def __del__(self):
+        try:
+            lib().kmat_ctx_destroy(self.h)
+        except Exception:
+            pass
+
+
+def gather_bench(device=0, span_bytes=1 << 30, access_bytes=8, n_gathers=1 << 28, iters=5):
+    g, s = C.c_double(), C.c_double()
+    _check(lib().kmat_gather_bench(device, span_bytes, access_bytes, n_gathers, iters, C.byref(g), C.byref(s)))
+    return g.value, s.value

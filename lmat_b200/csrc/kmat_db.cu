@@ -1,0 +1,546 @@
+// kmat_db.cu -- the HBM-resident k-mer table: build (insertion kernel), the K1 (encode) and K2 (probe)
+// kernels, their parity hooks, and the random-gather roofline probe.
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "kmat_device.cuh"
+#include "kmat_priv.h"
+
+std::atomic<unsigned long long> g_km_launches{0};
+extern "C" uint64_t kmat_launch_count(void) { return g_km_launches.load(); }
+
+extern "C" int kmat_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------------------------
+static int km_choose_bucket_bits(uint64_t n, int kmer_bits) {
+    int b = 4;
+    while (((uint64_t)1 << b) * 2 < n) b++;           // load <= 2 keys per 4-slot bucket
+    if (b < kmer_bits - KM_REM_BITS) b = kmer_bits - KM_REM_BITS;
+    if (b > kmer_bits) b = kmer_bits;
+    return b;
+}
+
+extern "C" uint32_t kmat_shard_of(uint64_t kmer, int kmer_length, int shard_count) {
+    if (shard_count <= 1) return 0;
+    // hash prefix of the canonical k-mer (a raw k-mer prefix would be skewed); a different
+    // odd multiplier than km_mix so that shard and bucket are independent
+    uint64_t x = kmer * 0xA24BAED4963EE407ull;
+    x ^= x >> 29;
+    x *= 0x9FB21C651E98DF25ull;
+    x ^= x >> 32;
+    (void)kmer_length;
+    return (uint32_t)((x >> 11) % (uint64_t)shard_count);
+}
+
+// ---------------------------------------------------------------------------------------------
+// build
+// ---------------------------------------------------------------------------------------------
+__global__ void km_insert_kernel(const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ payload, uint64_t n,
+                                 unsigned long long *slots, uint64_t bucket_mask, int kmer_bits, int rem_bits, int *fail) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t x = km_mix(kmers[i], kmer_bits);
+        const uint64_t home = x >> rem_bits, rem = x & ((1ull << rem_bits) - 1);
+        const uint32_t pl = payload[i];
+        const uint64_t base = (1ull << 63) | ((uint64_t)((pl >> 31) & 1) << 62) | (rem << 32) | (pl & 0x7FFFFFFFu);
+        bool done = false;
+        for (int d = 0; d <= KM_MAX_DISP && !done; d++) {
+            unsigned long long *b = slots + ((home + d) & bucket_mask) * KM_SLOTS_PER_BUCKET;
+            const unsigned long long v = base | ((uint64_t)d << 60);
+            for (int s = 0; s < KM_SLOTS_PER_BUCKET && !done; s++) {
+                if (b[s] == 0ull && atomicCAS(b + s, 0ull, v) == 0ull) done = true;
+            }
+        }
+        if (!done) atomicExch(fail, 1);
+    }
+}
+__global__ void km_prefix_bits_kernel(const uint64_t *__restrict__ kmers, uint64_t n, uint32_t *bits, int shift) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t p = kmers[i] >> shift;
+        atomicOr(bits + (p >> 5), 1u << (p & 31));
+    }
+}
+
+static int km_db_alloc_and_insert(kmat_db *db, const uint64_t *d_kmers, const uint32_t *d_payload, uint64_t n) {
+    const int kmer_bits = 2 * db->kmer_len;
+    for (int b = km_choose_bucket_bits(n, kmer_bits);; b++) {
+        if (b > kmer_bits) { kmat_set_error("hash table build failed: displacement limit at maximum size"); return KMAT_ERR_UNSUPPORTED; }
+        db->geom.kmer_bits = kmer_bits; db->geom.bucket_bits = b; db->geom.rem_bits = kmer_bits - b;
+        db->n_buckets = 1ull << b;
+        const size_t bytes = db->n_buckets * KM_SLOTS_PER_BUCKET * sizeof(uint64_t);
+        KM_CUDA(cudaMalloc((void **)&db->d_slots, bytes));
+        KM_CUDA(cudaMemset(db->d_slots, 0, bytes));
+        int *d_fail;
+        KM_CUDA(cudaMalloc((void **)&d_fail, sizeof(int)));
+        KM_CUDA(cudaMemset(d_fail, 0, sizeof(int)));
+        if (n) {
+            const int threads = 256;
+            const int blocks = (int)std::min<uint64_t>((n + threads - 1) / threads, 148ull * 16);
+            km_insert_kernel<<<blocks, threads>>>(d_kmers, d_payload, n, (unsigned long long *)db->d_slots, db->n_buckets - 1,
+                                                  kmer_bits, db->geom.rem_bits, d_fail);
+            g_km_launches++;
+            KM_CUDA(cudaGetLastError());
+        }
+        int fail = 0;
+        KM_CUDA(cudaMemcpy(&fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost));
+        cudaFree(d_fail);
+        if (!fail) break;
+        cudaFree(db->d_slots); db->d_slots = nullptr;       // a key was displaced > KM_MAX_DISP buckets: double the table
+    }
+    // bitmap of the reference's non-empty top-tier prefixes: only used to count "prefix miss" lookups exactly
+    // for the algorithmic-bytes statistic; 2^27 bits = 16 MiB
+    db->prefix_shift = db->kmer_len == 18 ? 9 : 13;
+    const uint64_t nprefix = (kmer_bits - db->prefix_shift) >= 40 ? 0 : (1ull << (kmer_bits - db->prefix_shift));
+    if (nprefix && nprefix <= (1ull << 32)) {
+        const size_t words = (size_t)((nprefix + 31) / 32);
+        KM_CUDA(cudaMalloc((void **)&db->d_prefix_bits, words * 4));
+        KM_CUDA(cudaMemset(db->d_prefix_bits, 0, words * 4));
+        if (n) {
+            km_prefix_bits_kernel<<<(int)std::min<uint64_t>((n + 255) / 256, 148ull * 16), 256>>>(d_kmers, n, db->d_prefix_bits, db->prefix_shift);
+            g_km_launches++;
+            KM_CUDA(cudaGetLastError());
+        }
+        db->prefix_bytes = words * 4;
+    }
+    KM_CUDA(cudaDeviceSynchronize());
+    db->n_kmers = n;
+    return KMAT_OK;
+}
+
+KmDbDev km_db_dev(const kmat_db *db) {
+    KmDbDev d;
+    d.slots = db->d_slots; d.bucket_mask = db->n_buckets - 1; d.kmer_bits = db->geom.kmer_bits; d.rem_bits = db->geom.rem_bits;
+    d.kmer_len = db->kmer_len; d.tid_bytes = db->tid_bytes; d.pool = db->d_pool; d.prefix_bits = db->d_prefix_bits;
+    d.prefix_shift = db->prefix_shift;
+    return d;
+}
+
+extern "C" int kmat_db_build_device(int device, int kmer_len, int tid_bytes, uint64_t n, const uint64_t *d_kmers,
+                                    const uint32_t *d_payload, const uint32_t *d_pool, uint64_t pool_words, uint32_t n_stored_ids,
+                                    kmat_db **out) {
+    if (!out || (tid_bytes != 2 && tid_bytes != 4) || kmer_len < 8 || kmer_len > 28) { kmat_set_error("kmat_db_build_device: bad argument"); return KMAT_ERR_ARG; }
+    if (kmat_device_count() <= device) { kmat_set_error("CUDA device %d not available", device); return KMAT_ERR_NO_DEVICE; }
+    if (pool_words >= (1ull << 31)) { kmat_set_error("list pool of %llu words exceeds the 31-bit offset range", (unsigned long long)pool_words); return KMAT_ERR_UNSUPPORTED; }
+    KM_CUDA(cudaSetDevice(device));
+    kmat_db *db = new kmat_db();
+    db->device = device; db->kmer_len = kmer_len; db->tid_bytes = tid_bytes; db->n_sid = tid_bytes == 2 ? 65536u : n_stored_ids;
+    db->pool_words = pool_words;
+    if (pool_words) {
+        KM_CUDA(cudaMalloc((void **)&db->d_pool, pool_words * 4));
+        KM_CUDA(cudaMemcpy(db->d_pool, d_pool, pool_words * 4, cudaMemcpyDeviceToDevice));
+    }
+    int rc = km_db_alloc_and_insert(db, d_kmers, d_payload, n);
+    if (rc != KMAT_OK) { kmat_db_free(db); return rc; }
+    *out = db;
+    return KMAT_OK;
+}
+
+// Host table -> device.  List pool record: 16-bit ids: [u16 count][u16 id]*count ; 32-bit ids: [u32 count][u32 id]*count,
+// padded to 4 bytes; a record of <= 32 bytes never straddles a 32-byte sector, so a list fetch is one sector.
+extern "C" int kmat_db_upload(const kmat_table *t, int device, int shard_index, int shard_count, kmat_db **out) {
+    if (!t || !out || shard_count < 1 || shard_index < 0 || shard_index >= shard_count) { kmat_set_error("kmat_db_upload: bad argument"); return KMAT_ERR_ARG; }
+    if (kmat_device_count() <= device) { kmat_set_error("CUDA device %d not available", device); return KMAT_ERR_NO_DEVICE; }
+    if (t->kmer_len < 8 || t->kmer_len > 28) { kmat_set_error("k-mer length %d unsupported", t->kmer_len); return KMAT_ERR_UNSUPPORTED; }
+    std::vector<uint64_t> kmers; std::vector<uint32_t> payload, pool;
+    std::vector<uint32_t> stored;      // 32-bit DBs: distinct stored tids, ascending; lists hold indices into it
+    if (t->tid_bytes == 4) {
+        stored.assign(t->ids, t->ids + t->n_ids);
+        std::sort(stored.begin(), stored.end());
+        stored.erase(std::unique(stored.begin(), stored.end()), stored.end());
+    }
+    auto sid_of = [&](uint32_t id) -> uint32_t {
+        if (t->tid_bytes == 2) return id & 0xFFFF;
+        return (uint32_t)(std::lower_bound(stored.begin(), stored.end(), id) - stored.begin());
+    };
+    kmers.reserve(t->n_kmers / shard_count + 16); payload.reserve(t->n_kmers / shard_count + 16);
+    for (uint64_t i = 0; i < t->n_kmers; i++) {
+        if (shard_count > 1 && (int)kmat_shard_of(t->kmers[i], t->kmer_len, shard_count) != shard_index) continue;
+        const uint64_t a = t->offs[i], c = t->offs[i + 1] - a;
+        if (c == 0) continue;                         // cannot occur in a SortedDb (every record has >= 1 tid)
+        if (c >= 32768) { kmat_set_error("taxid list of %llu entries: counts >= 32768 turn label_vec[pos].first negative in the reference (int16_t, read_label.cpp:49); unsupported", (unsigned long long)c); return KMAT_ERR_UNSUPPORTED; }
+        kmers.push_back(t->kmers[i]);
+        if (c == 1) { payload.push_back(sid_of(t->ids[a])); continue; }
+        size_t words = t->tid_bytes == 2 ? (2 + 2 * c + 3) / 4 : 1 + c;
+        size_t at = pool.size();
+        if (words <= 8 && (at % 8) + words > 8) at = (at + 7) & ~(size_t)7;      // keep short records inside one sector
+        if (at + words >= (1ull << 31)) { kmat_set_error("list pool exceeds the 31-bit offset range"); return KMAT_ERR_UNSUPPORTED; }
+        pool.resize(at + words, 0);
+        if (t->tid_bytes == 2) {
+            uint16_t *p = (uint16_t *)(pool.data() + at);
+            p[0] = (uint16_t)c;
+            for (uint64_t j = 0; j < c; j++) p[1 + j] = (uint16_t)t->ids[a + j];
+        } else {
+            pool[at] = (uint32_t)c;
+            for (uint64_t j = 0; j < c; j++) pool[at + 1 + j] = sid_of(t->ids[a + j]);
+        }
+        payload.push_back(0x80000000u | (uint32_t)at);
+    }
+    KM_CUDA(cudaSetDevice(device));
+    uint64_t *d_k = nullptr; uint32_t *d_p = nullptr, *d_pool = nullptr;
+    const uint64_t n = kmers.size();
+    if (n) {
+        KM_CUDA(cudaMalloc((void **)&d_k, n * 8)); KM_CUDA(cudaMalloc((void **)&d_p, n * 4));
+        KM_CUDA(cudaMemcpy(d_k, kmers.data(), n * 8, cudaMemcpyHostToDevice));
+        KM_CUDA(cudaMemcpy(d_p, payload.data(), n * 4, cudaMemcpyHostToDevice));
+    }
+    if (!pool.empty()) {
+        KM_CUDA(cudaMalloc((void **)&d_pool, pool.size() * 4));
+        KM_CUDA(cudaMemcpy(d_pool, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice));
+    }
+    int rc = kmat_db_build_device(device, t->kmer_len, t->tid_bytes, n, d_k, d_p, d_pool, pool.size(), (uint32_t)stored.size(), out);
+    cudaFree(d_k); cudaFree(d_p); cudaFree(d_pool);
+    if (rc == KMAT_OK) (*out)->stored_tids = stored;
+    return rc;
+}
+
+extern "C" uint64_t kmat_db_size(const kmat_db *db) { return db ? db->n_kmers : 0; }
+extern "C" uint64_t kmat_db_bytes(const kmat_db *db) { return db ? db->n_buckets * 32 + db->pool_words * 4 + db->prefix_bytes : 0; }
+extern "C" int kmat_db_kmer_length(const kmat_db *db) { return db ? db->kmer_len : 0; }
+extern "C" int kmat_db_device(const kmat_db *db) { return db ? db->device : -1; }
+extern "C" void kmat_db_free(kmat_db *db) {
+    if (!db) return;
+    cudaSetDevice(db->device);
+    cudaFree(db->d_slots); cudaFree(db->d_pool); cudaFree(db->d_prefix_bits);
+    delete db;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 parity hook: thread per k-mer
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t km_list_count(const KmDbDev &db, uint32_t off) {
+    return db.tid_bytes == 2 ? (uint32_t)(*(const uint16_t *)(db.pool + off)) : db.pool[off];
+}
+__device__ __forceinline__ uint32_t km_list_id(const KmDbDev &db, uint32_t off, uint32_t j) {
+    return db.tid_bytes == 2 ? (uint32_t)((const uint16_t *)(db.pool + off))[1 + j] : db.pool[off + 1 + j];
+}
+__global__ void km_lookup_count_kernel(KmDbDev db, const uint64_t *__restrict__ kmers, uint32_t n, uint32_t *hit, uint64_t *cnt) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t extra;
+    const uint32_t h = km_probe(db, kmers[i], extra);
+    hit[i] = h;
+    cnt[i] = h == KM_HIT_MISS ? 0 : (h & KM_HIT_LIST) ? km_list_count(db, h & 0x7FFFFFFFu) : 1;
+}
+__global__ void km_lookup_fill_kernel(KmDbDev db, const uint32_t *__restrict__ hit, const uint64_t *__restrict__ off, uint32_t n,
+                                      uint32_t *ids, uint64_t cap) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t h = hit[i];
+    if (h == KM_HIT_MISS) return;
+    const uint64_t o = off[i];
+    if (h & KM_HIT_LIST) {
+        const uint32_t lo = h & 0x7FFFFFFFu, c = km_list_count(db, lo);
+        for (uint32_t j = 0; j < c; j++) if (o + j < cap) ids[o + j] = km_list_id(db, lo, j);
+    } else if (o < cap) ids[o] = h;
+}
+
+extern "C" int kmat_lookup_batch(const kmat_db *db, const uint64_t *kmers, uint32_t n, uint64_t *hit_off, uint32_t *ids,
+                                 uint64_t ids_cap, uint64_t *n_ids) {
+    if (!db || (n && (!kmers || !hit_off))) { kmat_set_error("kmat_lookup_batch: bad argument"); return KMAT_ERR_ARG; }
+    KM_CUDA(cudaSetDevice(db->device));
+    hit_off[0] = 0;
+    if (n_ids) *n_ids = 0;
+    if (!n) return KMAT_OK;
+    uint64_t *d_k, *d_cnt, *d_off; uint32_t *d_hit, *d_ids = nullptr;
+    KM_CUDA(cudaMalloc((void **)&d_k, (size_t)n * 8)); KM_CUDA(cudaMalloc((void **)&d_cnt, (size_t)(n + 1) * 8));
+    KM_CUDA(cudaMalloc((void **)&d_off, (size_t)(n + 1) * 8)); KM_CUDA(cudaMalloc((void **)&d_hit, (size_t)n * 4));
+    KM_CUDA(cudaMemcpy(d_k, kmers, (size_t)n * 8, cudaMemcpyHostToDevice));
+    KM_CUDA(cudaMemset(d_cnt, 0, (size_t)(n + 1) * 8));
+    KmDbDev dd = km_db_dev(db);
+    km_lookup_count_kernel<<<(n + 255) / 256, 256>>>(dd, d_k, n, d_hit, d_cnt);
+    g_km_launches++;
+    void *tmp = nullptr; size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_cnt, d_off, n + 1);
+    KM_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_cnt, d_off, n + 1);
+    g_km_launches++;
+    KM_CUDA(cudaMemcpy(hit_off, d_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost));
+    const uint64_t total = hit_off[n];
+    if (n_ids) *n_ids = total;
+    int rc = KMAT_OK;
+    if (total > ids_cap || (total && !ids)) rc = KMAT_ERR_OVERFLOW;
+    else if (total) {
+        KM_CUDA(cudaMalloc((void **)&d_ids, total * 4));
+        km_lookup_fill_kernel<<<(n + 255) / 256, 256>>>(dd, d_hit, d_off, n, d_ids, total);
+        g_km_launches++;
+        KM_CUDA(cudaMemcpy(ids, d_ids, total * 4, cudaMemcpyDeviceToHost));
+        if (db->tid_bytes == 4) for (uint64_t i = 0; i < total; i++) ids[i] = db->stored_tids[ids[i]];   // dense id -> stored tid
+    }
+    cudaFree(d_k); cudaFree(d_cnt); cudaFree(d_off); cudaFree(d_hit); cudaFree(d_ids); cudaFree(tmp);
+    KM_CUDA(cudaGetLastError());
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 + K2: encode, dedup, probe.  One warp per read, streaming over 32-base chunks.
+//
+// Restates the rolling encoder of retrieve_kmer_labels (read_label.cpp:943-950, 978-1017): 2-bit MSB-first
+// packing, canonical = min(forward, reverse complement), any non-ACGT byte resets the run, the first
+// occurrence of a canonical k-mer in the read wins (no_dups, :1010,1017), and the GC bookkeeping of
+// :994-1008 / :1205-1206 (bases of every run of >= k valid bases are counted once).
+// ---------------------------------------------------------------------------------------------
+#define KM_DEDUP_SLOTS 512          // per-warp shared-memory set; reads with more k-mer positions use a global one
+#define KM_PROBE_WARPS 8
+
+struct KmProbeParams {
+    KmDbDev db;
+    const char *bases; const uint64_t *offs; uint32_t n_reads;
+    uint32_t *hit;                 // per base offset (k-mer start position p of read r -> hit[offs[r] + p])
+    int2 *hdr;                     // per read: {valid_kmers, bin_sel}
+    uint64_t *out_kmers; uint8_t *out_flags;    // optional (encode parity hook)
+    unsigned long long *long_sets; uint32_t long_slots;   // global dedup sets for long reads: one per warp in the grid
+    KmStatsDev *stats;             // optional
+    int do_probe;
+};
+
+__device__ __forceinline__ int km_code(unsigned char ch) {
+    // ENCODE macro, read_label.cpp:943-950: a/A 0, c/C 1, g/G 2, t/T 3, anything else resets
+    switch (ch) {
+        case 'a': case 'A': return 0;
+        case 'c': case 'C': return 1;
+        case 'g': case 'G': return 2;
+        case 't': case 'T': return 3;
+        default: return -1;
+    }
+}
+__device__ __forceinline__ uint64_t km_revcomp(uint64_t fwd, int kmer_bits) {
+    uint64_t x = ~fwd << (64 - kmer_bits);            // complement; k-mer now left-aligned
+    x = __brevll(x);                                   // reverses base order and the two bits inside each base
+    return ((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull);
+}
+
+__global__ void __launch_bounds__(KM_PROBE_WARPS * 32) km_encode_probe_kernel(KmProbeParams P) {
+    __shared__ unsigned long long s_set[KM_PROBE_WARPS][KM_DEDUP_SLOTS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t warp_global = blockIdx.x * KM_PROBE_WARPS + wib, n_warps = gridDim.x * KM_PROBE_WARPS;
+    const int k = P.db.kmer_len, kmer_bits = P.db.kmer_bits;
+    const uint64_t kmask = (1ull << kmer_bits) - 1;
+    const int ebits = 64 - kmer_bits;                   // epoch tag above the k-mer: stale entries read as empty
+    const uint32_t emax = (ebits >= 31 ? 0x7FFFFFFFu : ((1u << ebits) - 1));
+    unsigned long long *sset = s_set[wib];
+    for (int i = lane; i < KM_DEDUP_SLOTS; i += 32) sset[i] = 0;
+    unsigned long long *lset = P.long_sets ? P.long_sets + (size_t)warp_global * P.long_slots : nullptr;
+    uint32_t epoch_s = 0, epoch_l = emax;               // the long set is cleared on first use
+    unsigned long long st_lookups = 0, st_hits = 0, st_lists = 0, st_extra = 0, st_pmiss = 0;
+    __syncwarp();
+
+    for (uint32_t r = warp_global; r < P.n_reads; r += n_warps) {
+        const uint64_t off = P.offs[r];
+        const int len = (int)(P.offs[r + 1] - off);
+        const int np = len - k + 1;
+        // pick the dedup set
+        unsigned long long *set; uint32_t smask; uint32_t epoch;
+        if (np <= KM_DEDUP_SLOTS / 2 || !lset) {
+            if (++epoch_s > emax) { for (int i = lane; i < KM_DEDUP_SLOTS; i += 32) sset[i] = 0; epoch_s = 1; __syncwarp(); }
+            set = sset; smask = KM_DEDUP_SLOTS - 1; epoch = epoch_s;
+        } else {
+            if (++epoch_l > emax) { for (uint32_t i = lane; i < P.long_slots; i += 32) lset[i] = 0; epoch_l = 1; __syncwarp(); }
+            set = lset; smask = P.long_slots - 1; epoch = epoch_l;
+        }
+        const unsigned long long etag = ebits >= 64 ? 0ull : ((unsigned long long)epoch << kmer_bits);
+        uint64_t prev = 0;             // packed previous 32 bases
+        uint32_t pinv = 0xFFFFFFFFu;   // invalid-base mask of the previous chunk (before the read: all invalid)
+        uint32_t pgc = 0;
+        int valid = 0, vgc = 0, vtot = 0;
+        const int nchunks = (len + 31) >> 5;
+        for (int c = 0; c < nchunks; c++) {
+            const int j = (c << 5) + lane;                                   // base index handled by this lane
+            const int code = j < len ? km_code((unsigned char)P.bases[off + j]) : -1;
+            const uint32_t cinv = __ballot_sync(KM_FULL, code < 0);
+            const uint32_t cgc = __ballot_sync(KM_FULL, code == 1 || code == 2);
+            const uint32_t cc = code < 0 ? 0u : (uint32_t)code;
+            const uint32_t hi = __reduce_or_sync(KM_FULL, lane < 16 ? cc << (30 - 2 * lane) : 0u);
+            const uint32_t lo = __reduce_or_sync(KM_FULL, lane >= 16 ? cc << (62 - 2 * lane) : 0u);
+            const uint64_t cur = ((uint64_t)hi << 32) | lo;
+            // k-mer ENDING at base j (start position p = j - k + 1)
+            const int s = 62 - 2 * lane;
+            const uint64_t fwd = ((cur >> s) | (s ? (prev << (64 - s)) : 0ull)) & kmask;
+            const uint64_t inv64 = ((uint64_t)cinv << 32) | pinv, gc64 = ((uint64_t)cgc << 32) | pgc;
+            const uint64_t wmask = (1ull << k) - 1;
+            const int wsh = 32 + lane - k + 1;                               // >= 0 because k <= 32
+            const bool ok = ((inv64 >> wsh) & wmask) == 0;                   // no invalid base in [p, j]
+            const bool ok_prev = wsh > 0 && ((inv64 >> (wsh - 1)) & wmask) == 0;   // the window ending at j-1
+            const int p = j - k + 1;
+            uint64_t canon = 0; bool first = false;
+            if (ok) {
+                const uint64_t rc = km_revcomp(fwd, kmer_bits);
+                canon = fwd < rc ? fwd : rc;                                   // read_label.cpp:1009
+            }
+            // GC bookkeeping (:994-1008): a run's first k-mer adds its k bases, each further k-mer adds one
+            const int add_tot = ok ? (ok_prev ? 1 : k) : 0;
+            const int add_gc = ok ? (ok_prev ? (int)((cgc >> lane) & 1) : __popcll((gc64 >> wsh) & wmask)) : 0;
+            valid += ok; vtot += add_tot; vgc += add_gc;
+            // dedup: lower position wins.  Chunks are visited in order; inside a chunk the lowest lane of each
+            // equal-k-mer group is the leader and inserts.
+            const uint32_t okmask = __ballot_sync(KM_FULL, ok);
+            if (ok) {
+                const uint32_t grp = __match_any_sync(okmask, canon);
+                const int leader = __ffs(grp) - 1;
+                bool fresh = false;
+                if (lane == leader) {
+                    const unsigned long long key = etag | canon;
+                    uint32_t h = (uint32_t)((canon * 0x9E3779B97F4A7C15ull) >> 40) & smask;
+                    for (;;) {
+                        const unsigned long long cur_e = ((volatile unsigned long long *)set)[h];   // L1-bypassing: lanes CAS the same set
+                        if (cur_e == key) break;                                               // seen earlier in this read
+                        const bool stale = ebits < 64 ? ((cur_e >> kmer_bits) != epoch) : (cur_e == 0);
+                        if (stale) {
+                            const unsigned long long old = atomicCAS(set + h, cur_e, key);
+                            if (old == cur_e) { fresh = true; break; }
+                            if (old == key) break;
+                            continue;                                                          // someone else took it: re-read
+                        }
+                        h = (h + 1) & smask;
+                    }
+                }
+                fresh = __shfl_sync(grp, fresh, leader);
+                first = fresh && lane == leader;
+            }
+            uint32_t hw = KM_HIT_INVALID;
+            if (first) {
+                hw = KM_HIT_MISS;
+                if (P.do_probe) {
+                    uint32_t extra;
+                    hw = km_probe(P.db, canon, extra);
+                    if (P.stats) {
+                        st_lookups++; st_extra += extra;
+                        if (hw != KM_HIT_MISS) { st_hits++; if (hw & KM_HIT_LIST) st_lists++; }
+                        else if (P.db.prefix_bits) {
+                            const uint64_t pf = canon >> P.db.prefix_shift;
+                            if (!((P.db.prefix_bits[pf >> 5] >> (pf & 31)) & 1)) st_pmiss++;
+                        }
+                    }
+                }
+            }
+            if (p >= 0 && j < len) {
+                P.hit[off + p] = hw;
+                if (P.out_kmers) { P.out_kmers[off + p] = ok ? canon : 0; P.out_flags[off + p] = ok ? (first ? 1 : 2) : 0; }
+            }
+            prev = cur; pinv = cinv; pgc = cgc;
+        }
+        valid = km_warp_sum(valid); vgc = km_warp_sum(vgc); vtot = km_warp_sum(vtot);
+        if (lane == 0) {
+            // gc_pcnt = ((float)vgc / (float)vtot) * 100.0 [double] -> float; bin = gc_pcnt / 10   (:1205-1206)
+            const float frac = __fdiv_rn((float)vgc, (float)vtot);
+            const float gc_pcnt = __double2float_rn(__dmul_rn((double)frac, 100.0));
+            const float q = __fdiv_rn(gc_pcnt, 10.0f);
+            P.hdr[r] = make_int2(valid, vtot > 0 ? (int)q : 0);
+        }
+    }
+    if (P.stats) {
+        st_lookups = km_warp_sum((int)st_lookups); st_hits = km_warp_sum((int)st_hits); st_lists = km_warp_sum((int)st_lists);
+        st_extra = km_warp_sum((int)st_extra); st_pmiss = km_warp_sum((int)st_pmiss);
+        if (lane == 0) {
+            atomicAdd(&P.stats->lookups, st_lookups); atomicAdd(&P.stats->hits, st_hits); atomicAdd(&P.stats->list_hits, st_lists);
+            atomicAdd(&P.stats->extra_buckets, st_extra); atomicAdd(&P.stats->prefix_miss, st_pmiss);
+        }
+    }
+}
+
+int km_launch_encode_probe(const kmat_db *db, const char *d_bases, const uint64_t *d_offs, uint32_t n_reads, uint32_t *d_hit,
+                           int2 *d_hdr, uint64_t *d_kmers, uint8_t *d_flags, unsigned long long *d_long_sets, uint32_t long_slots,
+                           int grid, KmStatsDev *d_stats, int do_probe, cudaStream_t stream) {
+    KmProbeParams P;
+    P.db = km_db_dev(db); P.bases = d_bases; P.offs = d_offs; P.n_reads = n_reads; P.hit = d_hit; P.hdr = d_hdr;
+    P.out_kmers = d_kmers; P.out_flags = d_flags; P.long_sets = d_long_sets; P.long_slots = long_slots; P.stats = d_stats;
+    P.do_probe = do_probe;
+    km_encode_probe_kernel<<<grid, KM_PROBE_WARPS * 32, 0, stream>>>(P);
+    g_km_launches++;
+    KM_CUDA(cudaGetLastError());
+    return KMAT_OK;
+}
+
+int km_probe_grid(uint32_t n_reads) {
+    // persistent-style grid: 148 SMs x resident CTAs (8 warps, 32 KB smem -> 6 CTAs/SM by smem, 8 by threads)
+    const uint32_t want = (n_reads + KM_PROBE_WARPS - 1) / KM_PROBE_WARPS;
+    return (int)std::max<uint32_t>(1, std::min<uint32_t>(want, 148u * 6));
+}
+
+extern "C" int kmat_encode_batch(const kmat_db *db, const char *bases, const uint64_t *offs, uint32_t n_reads, uint64_t *kmers,
+                                 uint8_t *flags, int32_t *valid_kmers, int32_t *bin_sel) {
+    if (!db || !offs || (n_reads && !bases)) { kmat_set_error("kmat_encode_batch: bad argument"); return KMAT_ERR_ARG; }
+    KM_CUDA(cudaSetDevice(db->device));
+    if (!n_reads) return KMAT_OK;
+    const uint64_t total = offs[n_reads];
+    uint32_t max_np = 0;
+    for (uint32_t r = 0; r < n_reads; r++) max_np = std::max<uint32_t>(max_np, (uint32_t)(offs[r + 1] - offs[r]));
+    char *d_b; uint64_t *d_o, *d_k; uint32_t *d_hit; int2 *d_hdr; uint8_t *d_f; unsigned long long *d_long = nullptr;
+    KM_CUDA(cudaMalloc((void **)&d_b, total + 1)); KM_CUDA(cudaMalloc((void **)&d_o, (size_t)(n_reads + 1) * 8));
+    KM_CUDA(cudaMalloc((void **)&d_k, (total + 1) * 8)); KM_CUDA(cudaMalloc((void **)&d_hit, (total + 1) * 4));
+    KM_CUDA(cudaMalloc((void **)&d_hdr, (size_t)n_reads * sizeof(int2))); KM_CUDA(cudaMalloc((void **)&d_f, total + 1));
+    KM_CUDA(cudaMemcpy(d_b, bases, total, cudaMemcpyHostToDevice));
+    KM_CUDA(cudaMemcpy(d_o, offs, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice));
+    KM_CUDA(cudaMemset(d_k, 0, (total + 1) * 8)); KM_CUDA(cudaMemset(d_f, 0, total + 1));
+    const int grid = km_probe_grid(n_reads);
+    uint32_t long_slots = 0;
+    if (max_np > KM_DEDUP_SLOTS / 2) {
+        long_slots = 1024; while (long_slots < 2 * max_np) long_slots <<= 1;
+        KM_CUDA(cudaMalloc((void **)&d_long, (size_t)grid * KM_PROBE_WARPS * long_slots * 8));
+    }
+    int rc = km_launch_encode_probe(db, d_b, d_o, n_reads, d_hit, d_hdr, d_k, d_f, d_long, long_slots, grid, nullptr, 0, 0);
+    if (rc == KMAT_OK) {
+        std::vector<int2> hdr(n_reads);
+        KM_CUDA(cudaMemcpy(hdr.data(), d_hdr, (size_t)n_reads * sizeof(int2), cudaMemcpyDeviceToHost));
+        if (kmers) KM_CUDA(cudaMemcpy(kmers, d_k, total * 8, cudaMemcpyDeviceToHost));
+        if (flags) KM_CUDA(cudaMemcpy(flags, d_f, total, cudaMemcpyDeviceToHost));
+        for (uint32_t r = 0; r < n_reads; r++) { if (valid_kmers) valid_kmers[r] = hdr[r].x; if (bin_sel) bin_sel[r] = hdr[r].y; }
+    }
+    cudaFree(d_b); cudaFree(d_o); cudaFree(d_k); cudaFree(d_hit); cudaFree(d_hdr); cudaFree(d_f); cudaFree(d_long);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// random-gather roofline probe: uniform random aligned loads over a large span
+// ---------------------------------------------------------------------------------------------
+template <int BYTES>
+__global__ void km_gather_kernel(const uint8_t *__restrict__ base, uint64_t n_units, uint64_t n_gathers, uint64_t seed, unsigned long long *sink) {
+    unsigned long long acc = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_gathers; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t x = (i + seed) * 0x9E3779B97F4A7C15ull;
+        x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32;
+        const uint64_t u = (uint64_t)(((unsigned __int128)x * n_units) >> 64);
+        const uint8_t *p = base + u * 32;                     // one access per 32-byte sector
+        if (BYTES == 8) acc += *(const unsigned long long *)p;
+        else if (BYTES == 16) { const ulonglong2 v = *(const ulonglong2 *)p; acc += v.x ^ v.y; }
+        else { uint64_t a, b, c, d; km_load_bucket((const uint64_t *)p, a, b, c, d); acc += a ^ b ^ c ^ d; }
+    }
+    if (acc == 0x123456789abcdefull) *sink = acc;
+}
+extern "C" int kmat_gather_bench(int device, uint64_t span_bytes, int access_bytes, uint64_t n_gathers, int iters,
+                                 double *gathers_per_s, double *sector_gbps) {
+    if (kmat_device_count() <= device) { kmat_set_error("CUDA device %d not available", device); return KMAT_ERR_NO_DEVICE; }
+    if (access_bytes != 8 && access_bytes != 16 && access_bytes != 32) return KMAT_ERR_ARG;
+    KM_CUDA(cudaSetDevice(device));
+    uint8_t *buf; unsigned long long *sink;
+    KM_CUDA(cudaMalloc((void **)&buf, span_bytes)); KM_CUDA(cudaMalloc((void **)&sink, 8));
+    KM_CUDA(cudaMemset(buf, 1, span_bytes));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const uint64_t n_units = span_bytes / 32;
+    float best = 1e30f;
+    for (int it = 0; it < iters + 1; it++) {
+        cudaEventRecord(e0);
+        const int blocks = 148 * 16, threads = 256;
+        if (access_bytes == 8) km_gather_kernel<8><<<blocks, threads>>>(buf, n_units, n_gathers, 977 * it, sink);
+        else if (access_bytes == 16) km_gather_kernel<16><<<blocks, threads>>>(buf, n_units, n_gathers, 977 * it, sink);
+        else km_gather_kernel<32><<<blocks, threads>>>(buf, n_units, n_gathers, 977 * it, sink);
+        g_km_launches++;
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (it > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf); cudaFree(sink);
+    KM_CUDA(cudaGetLastError());
+    if (gathers_per_s) *gathers_per_s = (double)n_gathers / (best * 1e-3);
+    if (sector_gbps) *sector_gbps = (double)n_gathers * 32.0 / (best * 1e-3) / 1e9;
+    return KMAT_OK;
+}

@@ -1,0 +1,105 @@
+// kmat_device.cuh -- device-side structures and small helpers shared by the kernels.
+#ifndef KMAT_DEVICE_CUH
+#define KMAT_DEVICE_CUH
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kmat_internal.h"
+
+#define KM_FULL 0xffffffffu
+
+// hit word written by the probe kernel for every k-mer start position of a read
+#define KM_HIT_INVALID 0xFFFFFFFFu   // no valid k-mer starts here, or it duplicates an earlier one (label_vec[pos].first = -1)
+#define KM_HIT_MISS 0xFFFFFFFEu      // valid first occurrence, not in the table (first = 0, empty set)
+#define KM_HIT_LIST 0x80000000u      // bit 31: payload is a list-pool offset (4-byte words); else a stored id
+
+struct KmDbDev {
+    const uint64_t *slots;        // n_buckets * 4
+    uint64_t bucket_mask;
+    int kmer_bits, rem_bits, kmer_len, tid_bytes;
+    const uint32_t *pool;         // list pool, 4-byte words
+    const uint32_t *prefix_bits;  // bitmap over the reference's top-tier prefixes (stats only), may be null
+    int prefix_shift;             // BITS_PER_2ND of the reference layout (13 for k=20, 9 for k=18)
+};
+
+struct KmStatsDev {
+    unsigned long long lookups, hits, list_hits, list_ids, extra_buckets, prefix_miss, list_sectors;
+    unsigned long long reads_fast, reads_slow, reads_error;
+};
+
+// 256-bit load of one bucket (one 32-byte sector): LDG.E.256 on sm_100a
+__device__ __forceinline__ void km_load_bucket(const uint64_t *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+
+// Probe: returns the hit word.  extra = number of additional buckets visited (linear probing past a full bucket).
+__device__ __forceinline__ uint32_t km_probe(const KmDbDev &db, uint64_t kmer, uint32_t &extra) {
+    const uint64_t x = km_mix(kmer, db.kmer_bits);
+    const uint64_t home = x >> db.rem_bits;
+    const uint64_t rem = x & ((1ull << db.rem_bits) - 1);
+    extra = 0;
+#pragma unroll 1
+    for (int d = 0; d <= KM_MAX_DISP; d++) {
+        uint64_t s0, s1, s2, s3;
+        km_load_bucket(db.slots + ((home + d) & db.bucket_mask) * KM_SLOTS_PER_BUCKET, s0, s1, s2, s3);
+        const uint64_t want = (1ull << 63) | ((uint64_t)d << 60) | (rem << 32);
+        const uint64_t keymask = ~((1ull << 62) | 0xFFFFFFFFull);
+        uint64_t hit = 0;
+        if ((s0 & keymask) == want) hit = s0;
+        if ((s1 & keymask) == want) hit = s1;
+        if ((s2 & keymask) == want) hit = s2;
+        if ((s3 & keymask) == want) hit = s3;
+        if (hit) return (uint32_t)hit | (((hit >> 62) & 1) ? KM_HIT_LIST : 0u);
+        if (!(s0 && s1 && s2 && s3)) return KM_HIT_MISS;   // a free slot: the key cannot have been displaced further
+        extra++;
+    }
+    return KM_HIT_MISS;
+}
+
+__device__ __forceinline__ int km_warp_sum(int v) { return __reduce_add_sync(KM_FULL, v); }
+__device__ __forceinline__ unsigned long long km_warp_or64(unsigned long long v) {
+    unsigned lo = __reduce_or_sync(KM_FULL, (unsigned)v), hi = __reduce_or_sync(KM_FULL, (unsigned)(v >> 32));
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// glibc >= 2.27 logf (sysdeps/ieee754/flt-32/e_logf.c), evaluated in double exactly like the host libm;
+// the reference scores with std::log(float) (read_label.cpp:688).  Exhaustively identical to the host
+// logf for every positive finite float (tests/test_logf_stdsort.py checks the C twin of this routine).
+__device__ __forceinline__ float km_logf(float x) {
+    const double T[16][2] = {
+        {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
+        {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},
+        {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},
+        {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},
+        {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0},
+        {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},
+        {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
+        {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+    const double Ln2 = 0x1.62e42fefa39efp-1;
+    const double A0 = -0x1.00ea348b88334p-2, A1 = 0x1.5575b0be00b6ap-2, A2 = -0x1.ffffef20a4123p-2;
+    uint32_t ix = __float_as_uint(x);
+    if (ix == 0x3f800000u) return 0.0f;
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+        if (ix * 2 == 0) return __uint_as_float(0xff800000u);            // -inf
+        if (ix == 0x7f800000u) return x;
+        if ((ix & 0x80000000u) || ix * 2 >= 0xff000000u) return __uint_as_float(0x7fc00000u);
+        ix = __float_as_uint(__fmul_rn(x, 8388608.0f));
+        ix -= 23u << 23;
+    }
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (int)((tmp >> 19) & 15);
+    const int k = (int)tmp >> 23;
+    const uint32_t iz = ix - (tmp & 0xff800000u);
+    const double invc = T[i][0], logc = T[i][1];
+    const double z = (double)__uint_as_float(iz);
+    const double r = __dadd_rn(__dmul_rn(z, invc), -1.0);
+    const double y0 = __dadd_rn(logc, __dmul_rn((double)k, Ln2));
+    const double r2 = __dmul_rn(r, r);
+    double y = __dadd_rn(__dmul_rn(A1, r), A2);
+    y = __dadd_rn(__dmul_rn(A0, r2), y);
+    y = __dadd_rn(__dmul_rn(y, r2), __dadd_rn(y0, r));
+    return __double2float_rn(y);
+}
+
+#endif

@@ -1,0 +1,98 @@
+"""CPU: the C-ABI library loads, exports every symbol include/kmat.h declares, and its host-side
+pieces (table ingest, input parsers, formatter) behave -- no compute calls, no GPU needed."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from lmat_b200 import api
+from oracle import oracle_py as op
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "kmat.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(kmat_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = api.lib()
+    names = declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/kmat.h but not exported by libkmat.so"
+    assert set(names) == set(api.EXPORTS)
+    assert L.kmat_abi_version() == 1
+
+
+def test_compute_call_without_gpu_fails_loudly():
+    if api.device_count() > 0:
+        pytest.skip("a GPU is present")
+    t = api.Table.from_arrays(np.array([5, 9], dtype=np.uint64), np.array([0, 1, 2], dtype=np.uint64), np.array([3, 4], dtype=np.uint32))
+    with pytest.raises(api.KmatError) as e:
+        api.Db.upload(t)
+    assert e.value.code == -2          # KMAT_ERR_NO_DEVICE: there is no CPU fallback
+
+
+def test_table_from_sorteddb_layout_roundtrip(golden_small):
+    """Walk the reference's SortedDb memory layout (rebuilt by oracle_py.SortedDbArrays from the golden
+    dump) through kmat_table_from_sorteddb and get the dump back."""
+    g = golden_small
+    sd = op.SortedDbArrays(g.kmers, g.offs, g.ids, g.kmer_len, g.tid_bytes)
+    t = api.Table.from_sorteddb(sd.top_tier, sd.kmer_table, sd.storage, g.kmer_len, g.tid_bytes)
+    k, o, i = t.arrays()
+    assert t.size == len(g.kmers) and t.kmer_length == 20
+    assert np.array_equal(k, g.kmers) and np.array_equal(o, g.offs) and np.array_equal(i, g.ids)
+
+
+def test_flat_image_save_open(golden_small, tmp_path):
+    g = golden_small
+    t = api.Table.from_arrays(g.kmers, g.offs, g.ids, g.kmer_len, g.tid_bytes)
+    p = str(tmp_path / "t.kmat")
+    t.save(p)
+    t2 = api.Table.open(p)
+    k, o, i = t2.arrays()
+    assert np.array_equal(k, g.kmers) and np.array_equal(o, g.offs) and np.array_equal(i, g.ids)
+    with pytest.raises(api.KmatError):
+        api.Table.open(str(tmp_path / "missing.db"))
+    bad = tmp_path / "bad.db"
+    bad.write_bytes(b"x" * 200)
+    with pytest.raises(api.KmatError) as e:
+        api.Table.open(str(bad))
+    assert e.value.code == -6
+
+
+def test_table_rejects_unsorted():
+    with pytest.raises(api.KmatError):
+        api.Table.from_arrays(np.array([9, 5], dtype=np.uint64), np.array([0, 1, 2], dtype=np.uint64), np.array([3, 4], dtype=np.uint32))
+
+
+def test_inputs_parse_and_bad_tree(golden_small, tmp_path):
+    P = golden_small.paths
+    api.Inputs(tree=P["tree"], depth=P["depth"], rank=P["rank"], map16=P["map16"], numrank=P["numrank"], plasmids=P["plasmids"],
+               null_lst=P["null_lst"], lmat_dir=golden_small.workdir)
+    with pytest.raises(api.KmatError) as e:
+        api.Inputs(tree=str(tmp_path / "nope.tree"))
+    assert e.value.code == -5
+
+
+def test_format_tail_matches_oracle_formatter(golden_small):
+    """The product's line formatter and the oracle's agree on every result the oracle produces."""
+    from conftest import oracle_for
+    g = golden_small
+    for opts, prn in (("run_rl", True), ("defaults", False)):
+        orc = oracle_for(g, opts)
+        hdrs, seqs = op.read_fasta_like_reference(g.paths["reads"])
+        res, cands, lin = orc.label(seqs)
+        want = orc.tails(res)
+        r2 = np.zeros(len(res), dtype=api.RESULT_DTYPE)
+        for f in api.RESULT_DTYPE.names:
+            r2[f] = res[f]
+        buf = C.create_string_buffer(1 << 20)
+        for i in range(len(res)):
+            n = api.lib().kmat_format_tail(r2[i:i + 1].ctypes.data, cands.ctypes.data if len(cands) else None,
+                                           lin.ctypes.data if len(lin) else None, int(prn), buf, len(buf))
+            assert n >= 0 and buf.raw[:n].decode() == want[i]

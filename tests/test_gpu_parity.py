@@ -1,0 +1,119 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle and the committed
+reference outputs.  Bit-exact bar: k-mer encoding, table hits and taxid lists, and the per-read output
+lines byte for byte (float scores included -- the device reproduces the reference's float operation
+order and glibc's logf; no tolerance is needed or used)."""
+import numpy as np
+import pytest
+
+import scenarios as S
+from conftest import oracle_for
+from lmat_b200 import api
+from lmat_b200 import fixtures as fx
+from oracle import oracle_py as op
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dbs(golden_small, golden_lists):
+    out = {}
+    for g in (golden_small, golden_lists):
+        t = api.Table.from_arrays(g.kmers, g.offs, g.ids, g.kmer_len, g.tid_bytes)
+        out[g.name] = api.Db.upload(t)
+    return out
+
+
+def make_ctx(g, db, opts_name):
+    o = S.OPTION_SETS[opts_name]
+    P = g.paths
+    inp = api.Inputs(tree=P["tree"], depth=P["depth"], rank=P["rank"], map16=P["map16"],
+                     numrank=P["numrank"] if o.get("prune") else None, plasmids=P["plasmids"] if o.get("plasmids") else None,
+                     null_lst=P["null_lst"] if o["null"] else None, lmat_dir=g.workdir)
+    opts = api.default_opts(min_kmer=o["min_kmer"], hbias=o["hbias"], sdiff=o["sdiff"], min_score=o["min_score"],
+                            permissive=int(bool(o.get("permissive"))), phix_screen=0 if o.get("phix_off") else 1,
+                            min_fnd_kmer=o.get("min_fnd", 1), max_count=o.get("prune", 65535), want_lineage=0 if o["prn_all"] else 1)
+    return api.Ctx(db, inp, opts)
+
+
+@pytest.mark.parametrize("scen", ["golden_small", "golden_lists"])
+def test_lookup_matches_oracle_and_table(scen, request, dbs):
+    g = request.getfixturevalue(scen)
+    db = dbs[g.name]
+    assert db.size == len(g.kmers)
+    rng = np.random.default_rng(3)
+    q = np.concatenate([g.kmers, rng.integers(0, 1 << 40, 50000, dtype=np.uint64), g.kmers[::7] ^ np.uint64(1)])
+    offs, ids = db.lookup(q)
+    sd = op.SortedDbArrays(g.kmers, g.offs, g.ids, g.kmer_len, g.tid_bytes)
+    o_offs, o_ids = op.Oracle(cdb=sd.cdb(), keep=sd).lookup(q)
+    assert np.array_equal(offs, o_offs) and np.array_equal(ids, o_ids)
+    # every k-mer of the table is found with exactly its list, in list order
+    n = len(g.kmers)
+    assert np.array_equal(offs[:n + 1], g.offs) and np.array_equal(ids[:int(g.offs[-1])], g.ids)
+
+
+def test_encode_matches_oracle(golden_small, dbs):
+    g = golden_small
+    hdrs, seqs = op.read_fasta_like_reference(g.paths["reads"])
+    seqs = seqs + ["", "A", "ACGT" * 100, "N" * 50, "acgtnACGT" * 30, "GC" * 40, fx.codes_to_str(np.arange(700) % 4)]
+    kmers, flags, valid, bins, offs = dbs[g.name].encode(seqs)
+    for r, s in enumerate(seqs):
+        v, b, km, fl = op.encode_read(s, 20)
+        o = int(offs[r])
+        n = max(len(s) - 19, 0)
+        assert valid[r] == v, (r, s[:30])
+        assert np.array_equal(flags[o:o + n], fl), r
+        assert np.array_equal(kmers[o:o + n][fl > 0], km[fl > 0]), r
+        if v > 0:
+            assert bins[r] == b, r
+
+
+@pytest.mark.parametrize("scen", ["golden_small", "golden_lists"])
+@pytest.mark.parametrize("opts", [k for k in S.OPTION_SETS if k != "permissive"])
+def test_labels_match_reference_golden(scen, opts, request, dbs):
+    """kmat_label_batch -> kmat_format_tail reproduces the reference read_label .out byte for byte."""
+    g = request.getfixturevalue(scen)
+    o = S.OPTION_SETS[opts]
+    ctx = make_ctx(g, dbs[g.name], opts)
+    hdrs, seqs = op.read_fasta_like_reference(g.paths["reads"])
+    res, cands, lin = ctx.label(seqs)
+    assert (res["status"] != 6).all(), f"{(res['status'] == 6).sum()} reads hit an unsupported path"
+    mine = op.assemble_lines(hdrs, seqs, ctx.tails(res, cands, lin, prn_all=o["prn_all"]), prn_read=not o.get("hide_read"))
+    want = g.golden_out(opts)
+    if mine != want:
+        a, b = mine.split("\n"), want.split("\n")
+        bad = [i for i, (x, y) in enumerate(zip(a, b)) if x != y]
+        raise AssertionError(f"{len(bad)} lines differ; first: {a[bad[0]][-200:]!r} vs {b[bad[0]][-200:]!r}")
+
+
+def test_labels_match_oracle_fields(golden_lists, dbs):
+    """Field-level comparison with the oracle (status, counts, tid, score bits, candidate arrays)."""
+    g = golden_lists
+    ctx = make_ctx(g, dbs[g.name], "run_rl")
+    orc = oracle_for(g, "run_rl")
+    hdrs, seqs = op.read_fasta_like_reference(g.paths["reads"])
+    res, cands, lin = ctx.label(seqs)
+    ores, ocands, olin = orc.label(seqs)
+    for f in ("status", "n1", "n2", "valid_kmers", "cand_kmer_cnt", "match", "tid", "n_cand"):
+        sel = slice(None) if f in ("status", "valid_kmers") else (ores["status"] >= 2)
+        assert np.array_equal(res[f][sel], ores[f][sel]), f
+    lab = ores["status"] >= 4
+    for f in ("score", "log_avg", "stdev"):
+        assert np.array_equal(res[f][lab].view(np.uint32), ores[f][lab].view(np.uint32)), f
+    for i in np.nonzero(ores["status"] == 5)[0]:
+        a = cands[int(res["cand_off"][i]):int(res["cand_off"][i]) + int(res["n_cand"][i])]
+        b = ocands[int(ores["cand_off"][i]):int(ores["cand_off"][i]) + int(ores["n_cand"][i])]
+        assert np.array_equal(a["tid"], b["tid"]) and np.array_equal(a["score"].view(np.uint32), b["score"].view(np.uint32)), i
+
+
+def test_batch_split_invariance(golden_small, dbs):
+    """Size-independent property: labels do not depend on how reads are batched."""
+    g = golden_small
+    ctx = make_ctx(g, dbs[g.name], "run_rl")
+    hdrs, seqs = op.read_fasta_like_reference(g.paths["reads"])
+    res, cands, lin = ctx.label(seqs)
+    whole = ctx.tails(res, cands, lin)
+    parts = []
+    for a in range(0, len(seqs), 37):
+        r, c, l = ctx.label(seqs[a:a + 37])
+        parts += ctx.tails(r, c, l)
+    assert parts == whole
