@@ -46,37 +46,38 @@ struct KmScoreParams {
 struct KmRl { float score; uint32_t idx; };          // rank_label element: candidate index + (bias-adjusted) score
 
 struct __align__(16) KmWarpB {
-    // candidate hash: nid -> slot
+    // candidate hash: nid -> slot; h_idx[slot] = candidate id (dense, in insertion order)
     uint32_t h_nid[KB_HSLOTS], h_seq[KB_HSLOTS], h_leaf[KB_HSLOTS];
     uint8_t h_idx[KB_HSLOTS];
-    // candidates in taxid_lst order
+    // candidates, indexed by candidate id.  order[f] = id of the f-th entry of the reference's taxid_lst.
     uint32_t c_nid[KB_CMAX], c_tid[KB_CMAX], c_meta[KB_CMAX], c_spec[KB_CMAX], c_tin[KB_CMAX], c_tout[KB_CMAX], c_poff[KB_CMAX], c_plen[KB_CMAX];
     uint32_t c_leaf[KB_CMAX], c_first[KB_CMAX], c_hits[KB_CMAX];
     unsigned long long c_anc[KB_CMAX];
     float c_rp[KB_CMAX], c_score[KB_CMAX];
-    uint8_t c_cls[KB_CMAX], c_qual[KB_CMAX], c_hasrow[KB_CMAX], cl[KB_CMAX];
-    // per-position member lists
-    uint8_t pool[KB_POOL];
-    uint16_t pos_off[KB_PMAX];
-    uint8_t pos_n[KB_PMAX];
-    uint32_t lst[32][KB_LFAST];
-    uint16_t dep[32][KB_LFAST];
-    // serial phase
-    KmRl rl[KB_CMAX];
-    uint32_t l_tid[KB_LIN], l_tin[KB_LIN], l_tout[KB_LIN];
-    float l_score[KB_LIN];
-    uint16_t l_depth[KB_LIN];
-    uint8_t l_nogood[KB_LIN], l_perm[KB_LIN];
+    uint8_t c_cls[KB_CMAX], c_qual[KB_CMAX], c_slot[KB_CMAX], order[KB_CMAX];
+    // per position: bit set of the candidate ids kept there (label_vec[pos].second before the post-pass)
+    unsigned long long posmask[KB_PMAX];
+    union {
+        struct { uint32_t lst[32][KB_LFAST]; uint16_t dep[32][KB_LFAST]; } pl;      // position loop: per-lane list scratch
+        struct {                                                                  // serial phase
+            KmRl rl[KB_CMAX];
+            uint32_t l_tid[KB_LIN], l_tin[KB_LIN], l_tout[KB_LIN];
+            float l_score[KB_LIN];
+            uint16_t l_depth[KB_LIN];
+            uint8_t l_nogood[KB_LIN], l_perm[KB_LIN];
+        } sp;
+    } u;
     float track_val[64];
     uint8_t track_has[64];
-    uint32_t pool_cursor, n_used;
+    uint32_t n_used;
 };
 
 // ---------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t kb_hash(uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; return x & (KB_HSLOTS - 1); }
-// insert-or-find; returns slot or -1 when the table would exceed KB_CMAX distinct keys
+// insert-or-find; returns slot or -1 when the table would exceed KB_CMAX distinct keys.  The inserting lane
+// assigns the dense candidate id; other lanes may read h_idx[slot] only after a __syncwarp.
 __device__ int kb_cand_insert(KmWarpB &S, uint32_t nid) {
     uint32_t h = kb_hash(nid);
     for (int step = 0; step < KB_HSLOTS; step++) {
@@ -85,7 +86,12 @@ __device__ int kb_cand_insert(KmWarpB &S, uint32_t nid) {
         if (cur == KMAT_NONE) {
             if (((volatile uint32_t *)&S.n_used)[0] >= KB_CMAX) return -1;
             const uint32_t old = atomicCAS(&S.h_nid[h], KMAT_NONE, nid);
-            if (old == KMAT_NONE) { if (atomicAdd(&S.n_used, 1u) >= KB_CMAX) return -1; return (int)h; }
+            if (old == KMAT_NONE) {
+                const uint32_t id = atomicAdd(&S.n_used, 1u);
+                if (id >= KB_CMAX) return -1;
+                S.h_idx[h] = (uint8_t)id; S.c_slot[id] = (uint8_t)h;
+                return (int)h;
+            }
             if (old == nid) return (int)h;
         }
         h = (h + 1) & (KB_HSLOTS - 1);
@@ -151,7 +157,7 @@ struct KbRankLess {       // MyPair::operator< (SortedDb.hpp:133-135): by rank n
 __device__ int kb_big_list(const KmCtxDev &C, uint32_t hw, uint2 *scratch, int *first_out) {
     const uint32_t lo = hw & 0x7FFFFFFFu;
     int count = (int)kb_list_count(C.db, lo);
-    if (count > KB_BIGCAP / 2) return -KMAT_ERR_UNSUPPORTED * 1000;
+    if (count > KB_BIGCAP / 2) return -2;
     uint2 *seq = scratch;                  // ids in next() order
     uint2 *heap = scratch + KB_BIGCAP / 2;
     int n = 0;
@@ -228,22 +234,28 @@ struct KbTCmp {           // TCmp, read_label.cpp:475-485: |a-b| < 0.001 (double
 };
 struct KbLinDepthDesc {   // CmpDepth over lineage entries (:159-167), sorting a permutation
     const KmWarpB *S;
-    __device__ bool operator()(const uint8_t &a, const uint8_t &b) const { return (int)S->l_depth[a] > (int)S->l_depth[b]; }
+    __device__ bool operator()(const uint8_t &a, const uint8_t &b) const { return (int)S->u.sp.l_depth[a] > (int)S->u.sp.l_depth[b]; }
 };
 
-__device__ void kb_serial_phase(const KmScoreParams &P, KmWarpB &S, int C, bool useRandMod, bool hasHuman, kmat_read_result &res) {
+__device__ void kb_serial_phase(const KmScoreParams &P, KmWarpB &S, int C, bool hasHuman, kmat_read_result &res) {
     const KmCtxDev &X = P.C;
+    KmRl *rl = S.u.sp.rl;
+    uint32_t *l_tid = S.u.sp.l_tid, *l_tin = S.u.sp.l_tin, *l_tout = S.u.sp.l_tout;
+    float *l_score = S.u.sp.l_score;
+    uint16_t *l_depth = S.u.sp.l_depth;
+    uint8_t *l_nogood = S.u.sp.l_nogood, *l_perm = S.u.sp.l_perm;
     // ---- :807-837 sums in taxid_lst order
     bool fndPhiX = false;
     float log_sum = 0.0f, pos_log_sum = 0.0f, top_score = 0.0f, phiXscore = 0.0f;
     unsigned sig_hits = 0, pos_sig_hits = 0;
-    for (int i = 0; i < C; i++) {
+    for (int f = 0; f < C; f++) {
+        const int i = S.order[f];
         const float lo = S.c_score[i];
         log_sum = __fadd_rn(log_sum, lo);
         sig_hits++;
         if (lo > 0) { pos_sig_hits++; pos_log_sum = __fadd_rn(pos_log_sum, lo); }
         if (X.opt.phix_screen && (S.c_meta[i] & KM_META_PHIX)) { phiXscore = lo; fndPhiX = true; }
-        if (i == 0 || lo > top_score) top_score = lo;
+        if (f == 0 || lo > top_score) top_score = lo;
     }
     res.n_cand = 0; res.n_lin = 0; res.cand_off = 0; res.lin_off = 0;
     if (X.opt.phix_screen && phiXscore >= top_score && fndPhiX) {           // :841-848
@@ -255,46 +267,47 @@ __device__ void kb_serial_phase(const KmScoreParams &P, KmWarpB &S, int C, bool 
     if (pos_sig_hits > min_pos_examples) { use_sig_hits = pos_sig_hits; log_avg = __fdiv_rn(pos_log_sum, (float)pos_sig_hits); }
     else { use_sig_hits = sig_hits; log_avg = sig_hits > 0 ? __fdiv_rn(log_sum, (float)sig_hits) : 0.0f; }
     float log_std = 0.0f;
-    for (int i = 0; i < C; i++) {                                            // :865-880
-        const float sc = S.c_score[i];
+    for (int f = 0; f < C; f++) {                                            // :865-880
+        const float sc = S.c_score[S.order[f]];
         if (sc > 0 && pos_sig_hits > min_pos_examples) { const float v = __fsub_rn(log_avg, sc); log_std = __fadd_rn(log_std, __fmul_rn(v, v)); }
         if (pos_sig_hits <= min_pos_examples) { const float v = __fsub_rn(log_avg, sc); log_std = __fadd_rn(log_std, __fmul_rn(v, v)); }
     }
     const float stdev1 = use_sig_hits > 1 ? __fsqrt_rn(__fdiv_rn(log_std, (float)(use_sig_hits - 1))) : 0.0f;   // :881
     res.status = KMAT_ST_LABELED; res.log_avg = log_avg; res.stdev = stdev1;
-    // rank_label = (tid, score [+ hbias*stdev for human tids]) then sort(TCmp)   :882-893
-    for (int i = 0; i < C; i++) {
+    // rank_label = (tid, score [+ hbias*stdev for human tids]) in taxid_lst order, then sort(TCmp)   :882-893
+    for (int f = 0; f < C; f++) {
+        const int i = S.order[f];
         float sc = S.c_score[i];
         if (hasHuman && (S.c_meta[i] & KM_META_HUMAN)) sc = __fadd_rn(sc, __fmul_rn(X.opt.hbias, stdev1));
-        S.rl[i].score = sc; S.rl[i].idx = (uint32_t)i;
+        rl[f].score = sc; rl[f].idx = (uint32_t)i;
     }
     KbTCmp tcmp{&S};
-    kmstd::sort(S.rl, C, tcmp);
+    kmstd::sort(rl, C, tcmp);
     const float diff_thresh = __fmul_rn(stdev1, X.opt.sdiff);                // :895
     // ---- findReadLabelVer2
     int nlin = 0;
     auto lin_push_cand = [&](int ci, float score) {
         if (nlin >= KB_LIN) return false;
-        S.l_tid[nlin] = S.c_tid[ci]; S.l_tin[nlin] = S.c_tin[ci]; S.l_tout[nlin] = S.c_tout[ci]; S.l_score[nlin] = score;
-        S.l_depth[nlin] = (uint16_t)(S.c_meta[ci] & KM_META_DEPTH_MASK); S.l_nogood[nlin] = 0;
+        l_tid[nlin] = S.c_tid[ci]; l_tin[nlin] = S.c_tin[ci]; l_tout[nlin] = S.c_tout[ci]; l_score[nlin] = score;
+        l_depth[nlin] = (uint16_t)(S.c_meta[ci] & KM_META_DEPTH_MASK); l_nogood[nlin] = 0;
         nlin++;
         return true;
     };
     bool plasmidTopHit = false; int savePlasmid = -1;
     unsigned lowest_depth = 0, highest_depth = 0;
-    int lowest = -1, highest = -1; float lowest_score = 0, highest_score = 0;
+    int lowest = -1, highest = -1; float lowest_score = 0;
     int lidx = -1; bool linDone = false, lin_overflow = false;
     for (int i = C - 1; i >= 0; --i) {                                        // :295-325
-        const int ci = (int)S.rl[i].idx; const float sc = S.rl[i].score;
+        const int ci = (int)rl[i].idx; const float sc = rl[i].score;
         const unsigned cdepth = S.c_meta[ci] & KM_META_DEPTH_MASK;
         if (sc >= top_score && (S.c_meta[ci] & KM_META_PLASMID)) { plasmidTopHit = true; savePlasmid = ci; }
         bool added = false;
         if (!linDone) {                                                       // addToCandLineage :225-262
             bool addNode = true;
             for (int q = 0; q < nlin; q++) {
-                const unsigned chk = S.l_depth[q];
-                if (chk > cdepth && !kb_is_anc(S.c_tin[ci], S.c_tout[ci], S.l_tin[q])) { addNode = false; break; }
-                else if (chk < cdepth && !kb_is_anc(S.l_tin[q], S.l_tout[q], S.c_tin[ci])) { addNode = false; break; }
+                const unsigned chk = l_depth[q];
+                if (chk > cdepth && !kb_is_anc(S.c_tin[ci], S.c_tout[ci], l_tin[q])) { addNode = false; break; }
+                else if (chk < cdepth && !kb_is_anc(l_tin[q], l_tout[q], S.c_tin[ci])) { addNode = false; break; }
                 else if (chk == cdepth) { addNode = false; break; }
             }
             if (addNode) { if (!lin_push_cand(ci, sc)) lin_overflow = true; added = true; }
@@ -302,47 +315,44 @@ __device__ void kb_serial_phase(const KmScoreParams &P, KmWarpB &S, int C, bool 
         if (!linDone && !added) { lidx = i; linDone = true; }
         else if (!linDone) {
             if (cdepth > lowest_depth || i == C - 1) { lowest = ci; lowest_score = sc; lowest_depth = cdepth; }
-            if (cdepth < highest_depth || i == C - 1) { highest = ci; highest_score = sc; highest_depth = cdepth; }
+            if (cdepth < highest_depth || i == C - 1) { highest = ci; highest_depth = cdepth; }
         }
         if (linDone && sc < top_score) break;
     }
-    (void)highest_score;
-    const int n_chain = nlin;
-    int add_lo = nlin, add_hi = nlin;                                         // add_set = lineage entries [add_lo, add_hi)
+    const int add_lo = nlin; int add_hi = nlin;                               // add_set = lineage entries [add_lo, add_hi)
     if (highest_depth != 0 && highest >= 0) {                                 // :327-343
         const uint32_t poff = S.c_poff[highest], plen = S.c_plen[highest];
         for (uint32_t q = 0; q < plen; q++) {
             const uint32_t a = X.paths[poff + q];
             if (nlin >= KB_LIN) { lin_overflow = true; break; }
             const int slot = kb_cand_find(S, a);
-            if (slot >= 0) { lin_push_cand((int)S.h_idx[slot], S.c_score[S.h_idx[slot]]); }   // all_cand_set holds the un-biased score
+            if (slot >= 0) lin_push_cand((int)S.h_idx[slot], S.c_score[S.h_idx[slot]]);      // all_cand_set holds the un-biased score
             else {
                 const KmNodeA na = kb_nodeA(X, a); const KmNodeB nb = kb_nodeB(X, a);
-                S.l_tid[nlin] = na.tid; S.l_tin[nlin] = nb.tin; S.l_tout[nlin] = nb.tout; S.l_score[nlin] = -10000.0f;
-                S.l_depth[nlin] = (uint16_t)(na.meta & KM_META_DEPTH_MASK); S.l_nogood[nlin] = 0;
+                l_tid[nlin] = na.tid; l_tin[nlin] = nb.tin; l_tout[nlin] = nb.tout; l_score[nlin] = -10000.0f;
+                l_depth[nlin] = (uint16_t)(na.meta & KM_META_DEPTH_MASK); l_nogood[nlin] = 0;
                 nlin++;
             }
         }
         add_hi = nlin;
     }
-    (void)n_chain;
     if (lin_overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; return; }
-    for (int q = 0; q < nlin; q++) S.l_perm[q] = (uint8_t)q;
+    for (int q = 0; q < nlin; q++) l_perm[q] = (uint8_t)q;
     KbLinDepthDesc ldd{&S};
-    kmstd::sort(S.l_perm, nlin, ldd);                                         // cand_lin_vec sorted by depth desc :350-351
+    kmstd::sort(l_perm, nlin, ldd);                                           // cand_lin_vec sorted by depth desc :350-351
     bool any_nogood = false;
     for (int i = lidx; i >= 0; --i) {                                         // :355-362
-        const int ci = (int)S.rl[i].idx; const float sc = S.rl[i].score;
+        const int ci = (int)rl[i].idx; const float sc = rl[i].score;
         bool in_add = false;
-        for (int q = add_lo; q < add_hi && !in_add; q++) in_add = S.l_tid[q] == S.c_tid[ci];
+        for (int q = add_lo; q < add_hi && !in_add; q++) in_add = l_tid[q] == S.c_tid[ci];
         if (in_add) continue;
         bool keep_going = true;                                               // cmpCompLineage :264-282
         for (int z = 0; z < nlin; z++) {
-            const int q = S.l_perm[z];
-            if (kb_is_anc(S.l_tin[q], S.l_tout[q], S.c_tin[ci])) break;
-            const float dlt = __fsub_rn(S.l_score[q], sc);
-            if (S.l_score[q] != -10000.0f && dlt > diff_thresh) { keep_going = false; break; }
-            if (dlt <= diff_thresh) { S.l_nogood[q] = 1; any_nogood = true; }
+            const int q = l_perm[z];
+            if (kb_is_anc(l_tin[q], l_tout[q], S.c_tin[ci])) break;
+            const float dlt = __fsub_rn(l_score[q], sc);
+            if (l_score[q] != -10000.0f && dlt > diff_thresh) { keep_going = false; break; }
+            if (dlt <= diff_thresh) { l_nogood[q] = 1; any_nogood = true; }
         }
         if (!keep_going) break;
     }
@@ -355,19 +365,19 @@ __device__ void kb_serial_phase(const KmScoreParams &P, KmWarpB &S, int C, bool 
     } else {                                                                  // :369-409
         float max_val = -10000.0f; int root = -1;
         for (int z = 0; z < nlin; z++) {
-            const int q = S.l_perm[z];
-            max_val = S.l_score[q] < max_val ? max_val : S.l_score[q];       // std::max(cand, max_val)
+            const int q = l_perm[z];
+            max_val = l_score[q] < max_val ? max_val : l_score[q];           // std::max(cand, max_val)
             bool ng = false;                                                  // no_good is a set of taxids
-            for (int y = 0; y < nlin && !ng; y++) ng = S.l_nogood[y] && S.l_tid[y] == S.l_tid[q];
+            for (int y = 0; y < nlin && !ng; y++) ng = l_nogood[y] && l_tid[y] == l_tid[q];
             if (!ng) { root = q; break; }
         }
         if (root < 0) { call_tid = 0; call_score = -1.0f; match = KMAT_LCA_ERROR; }
         else {
             match = KMAT_MULTI;
             bool in_all = false;
-            for (int c2 = 0; c2 < C && !in_all; c2++) in_all = S.c_tid[c2] == S.l_tid[root];
-            if (in_all && max_val < S.l_score[root]) { match = KMAT_PARTIAL; max_val = S.l_score[root]; }   // :400-406 (unreachable in practice)
-            call_tid = S.l_tid[root]; call_score = max_val; call_tin = S.l_tin[root]; call_tout = S.l_tout[root]; call_has_node = true;
+            for (int c2 = 0; c2 < C && !in_all; c2++) in_all = S.c_tid[c2] == l_tid[root];
+            if (in_all && max_val < l_score[root]) { match = KMAT_PARTIAL; max_val = l_score[root]; }   // :400-406 (unreachable in practice)
+            call_tid = l_tid[root]; call_score = max_val; call_tin = l_tin[root]; call_tout = l_tout[root]; call_has_node = true;
         }
     }
     if (plasmidTopHit && call_has_node && kb_is_anc(call_tin, call_tout, S.c_tin[savePlasmid])) call_tid = S.c_tid[savePlasmid];   // :410-416
@@ -378,12 +388,12 @@ __device__ void kb_serial_phase(const KmScoreParams &P, KmWarpB &S, int C, bool 
     res.n_cand = (uint32_t)C;
     const unsigned long long co = atomicAdd(P.cand_cursor, (unsigned long long)C);
     res.cand_off = co;
-    if (P.cands && co + C <= P.cand_cap) for (int i = 0; i < C; i++) P.cands[co + i] = kmat_pair{S.c_tid[S.rl[i].idx], S.rl[i].score};
+    if (P.cands && co + C <= P.cand_cap) for (int i = 0; i < C; i++) P.cands[co + i] = kmat_pair{S.c_tid[rl[i].idx], rl[i].score};
     if (X.opt.want_lineage) {
         res.n_lin = (uint32_t)nlin;
         const unsigned long long lo2 = atomicAdd(P.lin_cursor, (unsigned long long)nlin);
         res.lin_off = lo2;
-        if (P.lin && lo2 + nlin <= P.lin_cap) for (int q = 0; q < nlin; q++) P.lin[lo2 + q] = kmat_pair{S.l_tid[q], S.l_score[q]};
+        if (P.lin && lo2 + nlin <= P.lin_cap) for (int q = 0; q < nlin; q++) P.lin[lo2 + q] = kmat_pair{l_tid[q], l_score[q]};
     }
 }
 
@@ -416,7 +426,7 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P
         if (done) { if (lane == 0) P.out[r] = res; continue; }
 
         for (int i = lane; i < KB_HSLOTS; i += 32) { S.h_nid[i] = KMAT_NONE; S.h_seq[i] = 0xFFFFFFFFu; S.h_leaf[i] = 0; }
-        if (lane == 0) { S.pool_cursor = 0; S.n_used = 0; }
+        if (lane == 0) S.n_used = 0;
         __syncwarp();
         int cand_cnt = 0, fnd_cnt = 0, err = 0;
         bool overflow = false;
@@ -424,8 +434,8 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P
         for (int p0 = 0; p0 < np; p0 += 32) {
             const int p = p0 + lane;
             const uint32_t hw = p < np ? P.hit[off + p] : KM_HIT_INVALID;
-            uint32_t *L = S.lst[lane];
-            uint16_t *D = S.dep[lane];
+            uint32_t *L = S.u.pl.lst[lane];
+            uint16_t *D = S.u.pl.dep[lane];
             int m = 0;
             bool bigl = false;
             if (hw != KM_HIT_INVALID) {
@@ -459,9 +469,26 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P
                             L[q] = nid; D[q] = dpt;
                             n++;
                         }
-                        m = kb_leaf_filter(X, L, n);
+                        m = err ? 0 : kb_leaf_filter(X, L, n);
                     }
                 }
+            }
+            // insert the kept members (taxid_lst / leaf_track bookkeeping, :1111-1122); L[j] becomes the hash slot
+            if (m > 0) {
+                fnd_cnt++;
+                for (int j = 0; j < m; j++) {
+                    const int slot = kb_cand_insert(S, L[j]);
+                    if (slot < 0) { overflow = true; m = 0; break; }
+                    atomicMin(&S.h_seq[slot], ((uint32_t)p << 16) | (uint32_t)j);   // first appearance in taxid_lst order
+                    atomicAdd(&S.h_leaf[slot], 1u);                                 // leaf_track
+                    L[j] = (uint32_t)slot;
+                }
+            }
+            __syncwarp();                                                     // candidate ids of this chunk's inserts are visible
+            if (p < np) {
+                unsigned long long mask = 0;
+                for (int j = 0; j < m; j++) mask |= 1ull << S.h_idx[L[j]];
+                S.posmask[p] = mask;
             }
             // long lists / run-time pruning: one lane at a time through the per-warp global scratch
             uint32_t bigmask = __ballot_sync(KM_FULL, bigl);
@@ -472,41 +499,20 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P
                     int first = 0;
                     const int mm = kb_big_list(X, hw, big, &first);
                     if (mm == -1) err = KMAT_ERR_BAD_TAXID;
-                    else if (mm < 0 || mm > 255) overflow = true;
+                    else if (mm < 0) overflow = true;
                     else if (mm > 0) {
-                        if (first < 0) overflow = true;     // count >= 32768 is rejected at table build; defensive
-                        const uint32_t base = atomicAdd(&S.pool_cursor, (uint32_t)mm);
-                        if (base + mm > KB_POOL) overflow = true;
-                        else {
-                            for (int j = 0; j < mm; j++) {
-                                const int slot = kb_cand_insert(S, big[j].x);
-                                if (slot < 0) { overflow = true; break; }
-                                atomicMin(&S.h_seq[slot], ((uint32_t)p << 16) | (uint32_t)j);
-                                atomicAdd(&S.h_leaf[slot], 1u);
-                                S.pool[base + j] = (uint8_t)slot;
-                            }
-                            S.pos_off[p] = (uint16_t)base; S.pos_n[p] = (uint8_t)mm; fnd_cnt++;
+                        unsigned long long mask = 0;
+                        for (int j = 0; j < mm; j++) {
+                            const int slot = kb_cand_insert(S, big[j].x);
+                            if (slot < 0) { overflow = true; break; }
+                            atomicMin(&S.h_seq[slot], ((uint32_t)p << 16) | (uint32_t)min(j, 0xFFFF));
+                            atomicAdd(&S.h_leaf[slot], 1u);
+                            mask |= 1ull << ((volatile uint8_t *)S.h_idx)[slot];   // inserted by this lane now, or before the last __syncwarp
                         }
-                    } else S.pos_n[p] = 0;
+                        S.posmask[p] = mask; fnd_cnt++;
+                    }
                 }
                 __syncwarp();
-            }
-            if (!bigl && p < np) {
-                if (m > 0) {
-                    fnd_cnt++;
-                    const uint32_t base = atomicAdd(&S.pool_cursor, (uint32_t)m);
-                    if (base + m > KB_POOL) { overflow = true; S.pos_n[p] = 0; }
-                    else {
-                        for (int j = 0; j < m; j++) {
-                            const int slot = kb_cand_insert(S, L[j]);
-                            if (slot < 0) { overflow = true; break; }
-                            atomicMin(&S.h_seq[slot], ((uint32_t)p << 16) | (uint32_t)j);   // first appearance in taxid_lst order
-                            atomicAdd(&S.h_leaf[slot], 1u);                                 // leaf_track (:1112-1116)
-                            S.pool[base + j] = (uint8_t)slot;
-                        }
-                        S.pos_off[p] = (uint16_t)base; S.pos_n[p] = (uint8_t)m;
-                    }
-                } else S.pos_n[p] = 0;
             }
         }
         __syncwarp();
@@ -515,33 +521,25 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P
         overflow = __any_sync(KM_FULL, overflow);
         if (err) { res.status = KMAT_ST_ERROR; res.err = -err; if (lane == 0) P.out[r] = res; st_err++; continue; }
         if (overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; if (lane == 0) P.out[r] = res; st_err++; continue; }
-        // ---- candidates in first-appearance order (taxid_lst)
-        int C1 = 0;
-        for (int g = 0; g < KB_HSLOTS / 32; g++) {
-            const int s = g * 32 + lane;
-            const bool occ = S.h_nid[s] != KMAT_NONE;
-            const uint32_t mk = __ballot_sync(KM_FULL, occ);
-            if (occ) S.cl[C1 + __popc(mk & lt_mask)] = (uint8_t)s;
-            C1 += __popc(mk);
-        }
-        __syncwarp();
+        const int C1 = (int)S.n_used;
         if (C1 == 0) {                                                       // taxid_lst.empty() -> NoDbHits (:1270-1271)
             res.status = KMAT_ST_NODBHITS; res.n1 = len; res.n2 = k;
             if (lane == 0) P.out[r] = res;
             st_fast++;
             continue;
         }
+        // ---- taxid_lst order of the first C1 candidates = order of first appearance (position, then list order)
         for (int i = lane; i < C1; i += 32) {
-            const int s = S.cl[i];
+            const int s = S.c_slot[i];
             const uint32_t q = S.h_seq[s];
             int rank = 0;
-            for (int j = 0; j < C1; j++) rank += S.h_seq[S.cl[j]] < q;
-            S.h_idx[s] = (uint8_t)rank;
+            for (int j = 0; j < C1; j++) rank += S.h_seq[S.c_slot[j]] < q;
+            S.order[rank] = (uint8_t)i;
             const uint32_t nid = S.h_nid[s];
             const KmNodeA na = kb_nodeA(X, nid); const KmNodeB nb = kb_nodeB(X, nid);
-            S.c_nid[rank] = nid; S.c_tid[rank] = na.tid; S.c_meta[rank] = na.meta; S.c_spec[rank] = na.species_anc;
-            S.c_tin[rank] = nb.tin; S.c_tout[rank] = nb.tout; S.c_poff[rank] = nb.path_off; S.c_plen[rank] = nb.path_len;
-            S.c_leaf[rank] = S.h_leaf[s]; S.c_first[rank] = q >> 16; S.c_anc[rank] = 0ull;
+            S.c_nid[i] = nid; S.c_tid[i] = na.tid; S.c_meta[i] = na.meta; S.c_spec[i] = na.species_anc;
+            S.c_tin[i] = nb.tin; S.c_tout[i] = nb.tout; S.c_poff[i] = nb.path_off; S.c_plen[i] = nb.path_len;
+            S.c_leaf[i] = S.h_leaf[s]; S.c_first[i] = q >> 16; S.c_anc[i] = 0ull;
         }
         __syncwarp();
         // ---- representative strain per species (:1143-1177) -> which members get their lineage added
@@ -563,7 +561,8 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P
             S.c_qual[i] = qual;
         }
         __syncwarp();
-        // ---- lineage expansion (:1178-1203): qualifying members in (first position, taxid) order
+        // ---- lineage expansion (:1178-1203): qualifying members in (first position, taxid) order; the ancestors
+        //      appended to taxid_lst get the next candidate ids, so for them id == taxid_lst index
         int C = C1;
         {
             unsigned long long key0 = ~0ull, key1 = ~0ull;
@@ -580,37 +579,38 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P
                 ci = __shfl_sync(KM_FULL, ci, src);
                 const uint32_t poff = S.c_poff[ci], plen = S.c_plen[ci];
                 unsigned long long anc = 0;
-                for (uint32_t c0 = 0; c0 < plen && !overflow; c0 += 32) {
+                for (uint32_t c0 = 0; c0 < plen; c0 += 32) {
                     const uint32_t a = c0 + lane < plen ? X.paths[poff + c0 + lane] : KMAT_NONE;
                     int slot = a != KMAT_NONE ? kb_cand_find(S, a) : -1;
                     const bool isnew = a != KMAT_NONE && slot < 0;
                     const uint32_t nm = __ballot_sync(KM_FULL, isnew);
                     const int nnew = __popc(nm);
                     if (C + nnew > KB_CMAX) { overflow = true; break; }
+                    // claim ids C.. in path order (nearest ancestor first) = the order the reference appends them
+                    if (lane == 0) S.n_used = (uint32_t)(C + nnew);
                     if (isnew) {
                         const int idx = C + __popc(nm & lt_mask);
-                        slot = kb_cand_insert(S, a);
-                        if (slot < 0) overflow = true;
-                        else {
-                            S.h_idx[slot] = (uint8_t)idx;
-                            const KmNodeA na = kb_nodeA(X, a); const KmNodeB nb = kb_nodeB(X, a);
-                            S.c_nid[idx] = a; S.c_tid[idx] = na.tid; S.c_meta[idx] = na.meta; S.c_spec[idx] = na.species_anc;
-                            S.c_tin[idx] = nb.tin; S.c_tout[idx] = nb.tout; S.c_poff[idx] = nb.path_off; S.c_plen[idx] = nb.path_len;
-                            S.c_leaf[idx] = 0; S.c_first[idx] = 0; S.c_anc[idx] = 0ull; S.c_qual[idx] = 0;
+                        uint32_t h = kb_hash(a);
+                        for (;;) {                                            // distinct new keys: plain CAS insert
+                            if (atomicCAS(&S.h_nid[h], KMAT_NONE, a) == KMAT_NONE) break;
+                            h = (h + 1) & (KB_HSLOTS - 1);
                         }
+                        slot = (int)h;
+                        S.h_idx[h] = (uint8_t)idx; S.c_slot[idx] = (uint8_t)h; S.order[idx] = (uint8_t)idx;
+                        const KmNodeA na = kb_nodeA(X, a); const KmNodeB nb = kb_nodeB(X, a);
+                        S.c_nid[idx] = a; S.c_tid[idx] = na.tid; S.c_meta[idx] = na.meta; S.c_spec[idx] = na.species_anc;
+                        S.c_tin[idx] = nb.tin; S.c_tout[idx] = nb.tout; S.c_poff[idx] = nb.path_off; S.c_plen[idx] = nb.path_len;
+                        S.c_leaf[idx] = 0; S.c_first[idx] = 0; S.c_anc[idx] = 0ull; S.c_qual[idx] = 0;
                     }
                     C += nnew;
                     __syncwarp();
-                    overflow = __any_sync(KM_FULL, overflow);
-                    if (overflow) break;
                     anc |= km_warp_or64(a != KMAT_NONE ? (1ull << S.h_idx[slot]) : 0ull);
                 }
+                if (overflow) break;
                 if (lane == 0) S.c_anc[ci] = anc;
                 __syncwarp();
-                if (overflow) break;
             }
         }
-        overflow = __any_sync(KM_FULL, overflow);
         if (overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; if (lane == 0) P.out[r] = res; st_err++; continue; }
         // ---- hits per candidate = number of positions whose (expanded) set holds it (:748-759)
         {
@@ -619,11 +619,11 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P
                 const int p = p0 + lane;
                 unsigned long long mask = 0;
                 if (p < np) {
-                    const int n = S.pos_n[p];
-                    const int b = S.pos_off[p];
-                    for (int j = 0; j < n; j++) {
-                        const int idx = S.h_idx[S.pool[b + j]];
-                        mask |= 1ull << idx;
+                    unsigned long long mm = S.posmask[p];
+                    mask = mm;
+                    while (mm) {
+                        const int idx = __ffsll((long long)mm) - 1;
+                        mm &= mm - 1;
                         if (S.c_qual[idx]) mask |= S.c_anc[idx];
                     }
                 }
@@ -651,17 +651,17 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P
         bool hasHuman = false, bad_model = false;
         for (int i = lane; i < C; i += 32) {
             hasHuman |= (S.c_meta[i] & KM_META_HUMAN) != 0;
-            float rp = 0.1f; uint8_t cls = 0, hasrow = 0;
+            float rp = 0.1f; uint8_t cls = 0;
             if (useRandMod) {
                 const int32_t row = X.mrow[(size_t)model * X.n_nodes + S.c_nid[i]];
                 if (row >= 0) {
                     // val_vec[bin_sel]: bin_sel == nbins (GC 100 %) reads past the vector in the reference (:770); 0 here
                     const float val = hd.y >= 0 && hd.y < X.nbins ? X.cut[(size_t)row * X.nbins + hd.y] : 0.0f;
                     rp = __double2float_rn(__dadd_rn((double)val, 0.0001));         // :771
-                    cls = X.cls[row]; hasrow = 1;
+                    cls = X.cls[row];
                 } else { rp = 1.0f; bad_model = true; }                              // :773-778: the reference asserts here
             }
-            S.c_rp[i] = rp; S.c_cls[i] = cls; S.c_hasrow[i] = hasrow;
+            S.c_rp[i] = rp; S.c_cls[i] = cls;
         }
         hasHuman = __any_sync(KM_FULL, hasHuman);
         bad_model = __any_sync(KM_FULL, bad_model);
@@ -669,7 +669,8 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P
         __syncwarp();
         if (useRandMod && lane == 0) {                                               // track[] class maxima, order dependent (:776-800)
             for (int c = 0; c < X.n_classes; c++) S.track_has[c] = 0;
-            for (int i = 0; i < C; i++) {
+            for (int f = 0; f < C; f++) {
+                const int i = S.order[f];
                 const int cid = S.c_cls[i];
                 const float rp = S.c_rp[i];
                 if (!S.track_has[cid]) { S.track_has[cid] = 1; S.track_val[cid] = rp; }
@@ -692,7 +693,7 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P
             S.c_score[i] = sc;
         }
         __syncwarp();
-        if (lane == 0) { kb_serial_phase(P, S, C, useRandMod, hasHuman, res); P.out[r] = res; }
+        if (lane == 0) { kb_serial_phase(P, S, C, hasHuman, res); P.out[r] = res; }
         __syncwarp();
         st_fast++;
     }
