@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- reads/s and k-mer lookups/s of the read_label hot path on synthetic 150 bp reads, k = 20.
+
+Workload (BASELINE.json configs[1]): a synthetic table built from G random genomes of
+L bp (defaults 2,000 x 500 kbp ~ 1e9 distinct 20-mers, 10 % of each genome shared with a sibling) through
+the C ABI (kmat_db_build_device), replicated per GPU; R = 10 M Illumina-like 150 bp reads per GPU.
+
+A step = one pass of the hot path (encode -> probe -> candidate sets -> scoring/LCA) over the R reads.
+  value : whole-job reads/s with the reads already resident in HBM (kmat_label_batch_device), CUDA events on
+          the launching stream, K steps after W warm-ups, barrier + synchronize on both sides, max over ranks
+  e2e   : the same metric through kmat_label_batch with HOST buffers (H2D of the reads and D2H of the results
+          inside the timed region)
+  roofline : the encode+probe kernel (the table-bound one): algorithmic table bytes of SURVEY.md 8(d)
+          (1 sector for a prefix miss, 2 for any other lookup, + ceil((2+2n)/32) per fetched list) / its
+          CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs and the random-gather rate measured here
+  cpu_baseline : the UNMODIFIED reference read_label (oracle/_ref, all host threads) on a bounded sample of the
+          same workload (a sub-table of the first genomes, reads drawn from them); rank 0, N = 1 only
+`--impl reference` prints the reference arm's line instead (same metric/config, CPU only).
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reads_per_s"
+UNIT = "reads/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="kmat", choices=["kmat", "reference"])
+    ap.add_argument("--genomes", type=int, default=2000)
+    ap.add_argument("--genome-len", type=int, default=500000)
+    ap.add_argument("--reads", type=int, default=10_000_000)
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--cpu-genomes", type=int, default=24, help="genomes in the CPU-baseline sub-table")
+    ap.add_argument("--cpu-reads", type=int, default=200_000, help="reads in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"C2-replicated: {a.genomes} random genomes x {a.genome_len} bp (10% sibling-shared, 2% mutated), k=20, "
+            f"16-bit ids; {a.reads} x {a.read_len} bp reads/GPU (90% genomic, 10% novel, 0.1%-2% subst, 0.05% N)")
+
+
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, streaming copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# -------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the unmodified reference read_label on a bounded sample
+# -------------------------------------------------------------------------------------------------
+def build_cpu_sample(a, workdir, device):
+    """Sub-table of the first `cpu_genomes` genomes written as a tax_histo file and built into a reference DB by
+    oracle/_ref/make_db_table; reads drawn from those genomes with the workload's read model."""
+    import numpy as np
+    import torch
+    from lmat_b200 import fixtures as fx
+    from lmat_b200 import synth
+    from oracle import refchain as rc
+    G = min(a.cpu_genomes, a.genomes)
+    tax, m16, anc_tid, anc_sid = synth.make_taxonomy_c2(20240, a.genomes)
+    paths = fx.write_taxonomy_files(tax, workdir)
+    null_lst = synth.write_null_models_for(tax, workdir)
+    dev = device
+    codes = synth.make_genomes_gpu(20240, tax, a.genomes, a.genome_len, dev)[:G].contiguous() if dev != "cpu" else \
+        synth.make_genomes_gpu(20240, tax, G, a.genome_len, dev)
+    tbl = synth.build_table_gpu(codes, anc_sid[:G])
+    sid2tid = np.zeros(65536, dtype=np.uint32)
+    for t, s in m16.items():
+        sid2tid[s] = t
+    kmers, offs, tids, _ = synth.table_to_host(tbl, sid2tid)
+    th = os.path.join(workdir, "cpu_sample.th.bin")
+    synth.write_tax_histo_fast(th, 20, kmers, offs, tids)
+    size_gib = int(2 + (len(kmers) * 8 + len(tids) * 8) / (1 << 30) * 1.3) + 1
+    db = None
+    kind = "port"
+    if rc.have_ref("make_db_table") and rc.have_ref("read_label"):
+        db = rc.make_db_table([th], os.path.join(workdir, "cpu_sample.db"), 20, size_gib, workdir, map16=paths["map16"])
+        kind = "reference"
+    reads = synth.make_reads_gpu(20241, codes, a.cpu_reads, a.read_len).cpu().numpy()
+    fa = os.path.join(workdir, "cpu_sample.fa")
+    with open(fa, "wb") as f:
+        for i in range(reads.shape[0]):
+            f.write(b">r%d\n" % i)
+            f.write(reads[i].tobytes())
+            f.write(b"\n")
+    return dict(db=db, kind=kind, paths=paths, null_lst=null_lst, fasta=fa, n_reads=int(reads.shape[0]), n_kmers=int(len(kmers)),
+                table=(kmers, offs, tids), reads=reads, genomes=G)
+
+
+def run_cpu_sample(sample, workdir, threads):
+    """One timed run of the reference on the sample.  Returns (reads/s from its own 'Total query time', wall s)."""
+    from oracle import refchain as rc
+    if sample["kind"] == "reference":
+        P = sample["paths"]
+        t0 = time.time()
+        out, qt = rc.read_label(sample["db"], sample["fasta"], os.path.join(workdir, "cpu_rl_"), P["depth"], P["tree"], threads=threads,
+                                map16=P["map16"], rank=P["rank"], names=P["names"], null_lst=sample["null_lst"], lmat_dir=workdir,
+                                min_kmer=30, hbias=0, sdiff=1.0, prn_all=True)
+        wall = time.time() - t0
+        return sample["n_reads"] / qt, wall
+    # port: the plain-C oracle restatement, single thread
+    import numpy as np
+    from oracle import oracle_py as op
+    kmers, offs, tids = sample["table"]
+    from lmat_b200 import fixtures as fx
+    m16 = {}
+    for ln in open(sample["paths"]["map16"]):
+        t, s = ln.split()
+        m16[int(t)] = int(s)
+    ids = np.array([m16[int(t)] for t in tids], dtype=np.uint32)
+    sd = op.SortedDbArrays(kmers, offs, ids)
+    orc = op.Oracle(cdb=sd.cdb(), keep=sd)
+    P = sample["paths"]
+    orc.set_opts(min_kmer=30, hbias=0.0, sdiff=1.0, prn_all=1)
+    orc.load_files(tree=P["tree"], depth=P["depth"], rank=P["rank"], map16=P["map16"], null_lst=sample["null_lst"], lmat_dir=workdir)
+    n = min(sample["n_reads"], 20000)
+    seqs = [sample["reads"][i].tobytes() for i in range(n)]
+    t0 = time.time()
+    orc.label(seqs)
+    dt = time.time() - t0
+    return n / dt, dt
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    workdir = tempfile.mkdtemp(prefix="kmat_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+        if dev == "cpu":
+            a.cpu_genomes = min(a.cpu_genomes, 8)
+        sample = build_cpu_sample(a, workdir, dev)
+        threads = os.cpu_count() or 1
+        vals, walls = [], []
+        for i in range(a.warmup + a.steps):
+            v, w = run_cpu_sample(sample, workdir, threads)
+            if i >= a.warmup:
+                vals.append(v)
+                walls.append(w)
+        value = sum(vals) / len(vals)
+        cores = threads if sample["kind"] == "reference" else 1
+        desc = (f"{sample['n_reads']} x {a.read_len} bp reads vs a {sample['n_kmers']}-k-mer sub-table (first {sample['genomes']} of "
+                f"{a.genomes} genomes) per step; reference read_label -t {cores}, its own 'Total query time'")
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1e3 * sample["n_reads"] / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64/f32", "data": "synthetic", "config": {"workload": workload_name(a), "sample": desc},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": sample["kind"], "sample": desc},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "kmer_lookups_per_s": value * (a.read_len - 19), "wall_s_per_step": sum(walls) / len(walls), "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+    finally:
+        shutil.rmtree(workdir, ignore_errors=True)
+
+
+# -------------------------------------------------------------------------------------------------
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        reference_arm(a)
+        return
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lmat_b200 import api
+    from lmat_b200 import fixtures as fx
+    from lmat_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- libkmat has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    launches0 = api.lib().kmat_launch_count()
+
+    workdir = tempfile.mkdtemp(prefix=f"kmat_bench_{rank}_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        t_setup = time.time()
+        tax, m16, anc_tid, anc_sid = synth.make_taxonomy_c2(20240, a.genomes)
+        paths = fx.write_taxonomy_files(tax, workdir)
+        null_lst = synth.write_null_models_for(tax, workdir)
+        codes = synth.make_genomes_gpu(20240, tax, a.genomes, a.genome_len, dev)
+        tbl = synth.build_table_gpu(codes, anc_sid)
+        n_kmers, n_lists = tbl.n, int((~tbl.single).sum().item())
+        db = synth.upload_table(tbl, local)
+        del tbl
+        torch.cuda.empty_cache()
+        inputs = api.Inputs(tree=paths["tree"], depth=paths["depth"], rank=paths["rank"], map16=paths["map16"], null_lst=null_lst, lmat_dir=workdir)
+        # options of bin/run_rl.sh:243: -j 30 -l 0 -b 1.0 -x 0 -p, null models on
+        ctx = api.Ctx(db, inputs, api.default_opts(min_kmer=30, hbias=0.0, sdiff=1.0, min_score=0.0, want_lineage=0))
+        reads = synth.make_reads_gpu(20241 + rank, codes, a.reads, a.read_len)           # weak scaling: every rank its own R reads
+        del codes
+        torch.cuda.empty_cache()
+        n, L = reads.shape
+        d_offs = (torch.arange(n + 1, device=dev, dtype=torch.int64) * L).contiguous()
+        total = n * L
+        setup_s = time.time() - t_setup
+
+        stream = torch.cuda.current_stream().cuda_stream
+
+        def step():
+            ctx.label_device(reads.data_ptr(), d_offs.data_ptr(), n, total, L, None, stream)
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        for _ in range(a.warmup):
+            step()
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        probe_ms, score_ms = [], []
+        barrier()
+        e0.record()
+        for _ in range(a.steps):
+            step()
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+        # per-kernel durations (CUDA events on the same stream), one extra untimed step each
+        for _ in range(3):
+            step()
+            p, s = ctx.kernel_ms()
+            probe_ms.append(p)
+            score_ms.append(s)
+        torch.cuda.synchronize()
+        st = ctx.stats()
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item()) / a.steps
+        value = world * n / (ms_step * 1e-3)
+        lookups_per_read = st.lookups / n
+
+        # ---- e2e through the host-buffer API
+        e2e = None
+        if not a.no_e2e:
+            h_reads = torch.empty((n, L), dtype=torch.uint8, pin_memory=True)
+            h_reads.copy_(reads)
+            h_offs = (np.arange(n + 1, dtype=np.uint64) * L)
+            res = np.zeros(n, dtype=api.RESULT_DTYPE)
+            cands = np.zeros(max(1, 40 * n), dtype=api.PAIR_DTYPE)
+            import ctypes as C
+            n_c = C.c_uint64()
+
+            def e2e_step():
+                rc = api.lib().kmat_label_batch(ctx.h, h_reads.data_ptr(), h_offs.ctypes.data, n, res.ctypes.data, cands.ctypes.data, len(cands),
+                                                C.byref(n_c), None, 0, None)
+                if rc < 0:
+                    raise api.KmatError(rc, api.lib().kmat_last_error().decode())
+            e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(max(1, min(a.steps, 3))):
+                e2e_step()
+            barrier()
+            dt = (time.perf_counter() - t0) / max(1, min(a.steps, 3))
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e = {"value": world * n / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(total + 8 * (n + 1)),
+                   "d2h_bytes_per_step": int(n * api.RESULT_DTYPE.itemsize + n_c.value * 8)}
+            del h_reads
+
+        if rank == 0:
+            hbm_peak, peak_src = measured_peaks()
+            gather_gps, gather_gbps = api.gather_bench(local, 16 << 30, 8, 1 << 29, 10)
+            pm = sorted(probe_ms)[len(probe_ms) // 2]
+            sm_ = sorted(score_ms)[len(score_ms) // 2]
+            achieved = st.algorithmic_bytes / (pm * 1e-3) / 1e9
+            errs = st.reads_error
+            line = {
+                "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/f32", "data": "synthetic",
+                "config": {"workload": workload_name(a), "db_kmers": int(n_kmers), "db_lists": n_lists, "db_bytes": int(db.bytes),
+                           "reads_per_gpu": n, "read_len": L, "k": 20, "options": "run_rl.sh:243 (-j 30 -l 0 -b 1 -p, null models on)",
+                           "l2_policy": "inputs larger than L2 (reads 1.5 GB, table >> 126 MB); no flush needed",
+                           "parallelism": f"read-sharded x{world}, table replicated, no data-path collective"},
+                "kmer_lookups_per_s": value * lookups_per_read, "lookups_per_read": lookups_per_read,
+                "hit_rate": st.hits / max(1, st.lookups), "reads_error": int(errs),
+                "kernels_ms": {"encode_probe": pm, "score": sm_},
+                "roofline": {"bound": "hbm", "kernel": "km_encode_probe_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                             "random_access_peak": gather_gbps, "frac_random_access": achieved / gather_gbps,
+                             "random_access_how": "uniform random 8-byte loads, one per 32-byte sector, over 16 GiB, best of 10 (kmat_gather_bench)",
+                             "algorithmic_bytes_per_lookup": st.algorithmic_bytes / max(1, st.lookups)},
+                "e2e": e2e, "gpu_launches": int(api.lib().kmat_launch_count() - launches0), "clocks": clocks, "setup_s": setup_s,
+            }
+            if world == 1 and not a.no_cpu_baseline:
+                try:
+                    sample = build_cpu_sample(a, workdir, dev)
+                    threads = os.cpu_count() or 1
+                    v, w = run_cpu_sample(sample, workdir, threads)
+                    cores = threads if sample["kind"] == "reference" else 1
+                    line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": sample["kind"],
+                                            "sample": f"{sample['n_reads']} reads vs a {sample['n_kmers']}-k-mer sub-table (first {sample['genomes']} genomes); "
+                                                      f"read_label -t {cores} 'Total query time'; wall {w:.1f} s"}
+                except Exception as ex:          # the baseline must never take the GPU number down with it
+                    line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)[:200]}
+            print(json.dumps(line), flush=True)
+    finally:
+        shutil.rmtree(workdir, ignore_errors=True)
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

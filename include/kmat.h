@@ -178,6 +178,11 @@ typedef struct {
     uint64_t reads_fast, reads_slow, reads_error;
 } kmat_batch_stats;
 int kmat_ctx_last_stats(kmat_ctx *, kmat_batch_stats *);
+/* Turn the statistics counters on (default) or off for subsequent batches. */
+int kmat_ctx_set_stats(kmat_ctx *, int enable);
+/* Device time of the two kernels of the last batch (CUDA events on the launching stream): the
+ * encode+probe kernel (K1+K2) and the scoring kernel (K3+K4).  Synchronises on the batch. */
+int kmat_ctx_last_kernel_ms(kmat_ctx *, float *probe_ms, float *score_ms);
 /* Kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t kmat_launch_count(void);
 

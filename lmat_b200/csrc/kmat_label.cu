@@ -736,6 +736,7 @@ struct kmat_ctx {
     kmat_read_result *h_out = nullptr;
     int score_grid = 0;
     size_t score_smem = 0;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // around the probe and the scoring kernel of the last batch
 };
 
 template <typename T>
@@ -762,6 +763,7 @@ extern "C" int kmat_ctx_create(const kmat_db *db, const kmat_inputs *in, const k
     UP(d_model_of_cand, model_of_cand); UP(d_mrow, mrow); UP(d_cut, cut); UP(d_cls, cls);
 #undef UP
     KM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; i++) KM_CUDA(cudaEventCreate(&c->ev[i]));
     KM_CUDA(cudaMalloc((void **)&c->d_cursors, 16));
     KM_CUDA(cudaMalloc((void **)&c->d_stats, sizeof(KmStatsDev)));
     c->score_smem = sizeof(KmWarpB) * KB_WARPS;
@@ -792,6 +794,7 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
     cudaFree(c->d_cands); cudaFree(c->d_lin); cudaFree(c->d_cursors); cudaFree(c->d_big); cudaFree(c->d_long_sets); cudaFree(c->d_stats);
     cudaFreeHost(c->h_bases); cudaFreeHost(c->h_offs); cudaFreeHost(c->h_out);
     if (c->stream) cudaStreamDestroy(c->stream);
+    for (int i = 0; i < 3; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
 }
 
@@ -852,9 +855,11 @@ static int km_run_device(kmat_ctx *c, const char *d_bases, const uint64_t *d_off
     if (c->opt.want_lineage && !c->d_lin) { if ((rc = km_grow(&c->d_lin, &c->cap_lin, (uint64_t)n_reads * 24 + 4096)) != KMAT_OK) return rc; }
     KM_CUDA(cudaMemsetAsync(c->d_cursors, 0, 16, st));
     if (c->collect_stats) KM_CUDA(cudaMemsetAsync(c->d_stats, 0, sizeof(KmStatsDev), st));
+    KM_CUDA(cudaEventRecord(c->ev[0], st));
     rc = km_launch_encode_probe(c->db, d_bases, d_offs, n_reads, c->d_hit, c->d_hdr, nullptr, nullptr, c->d_long_sets, c->long_slots,
                                 pgrid, c->collect_stats ? c->d_stats : nullptr, 1, st);
     if (rc != KMAT_OK) return rc;
+    KM_CUDA(cudaEventRecord(c->ev[1], st));
     KmScoreParams P;
     P.C = km_ctx_dev(c);
     P.offs = d_offs; P.n_reads = n_reads; P.hit = c->d_hit; P.hdr = c->d_hdr; P.out = d_out;
@@ -865,6 +870,7 @@ static int km_run_device(kmat_ctx *c, const char *d_bases, const uint64_t *d_off
     km_score_kernel<<<grid, KB_WARPS * 32, c->score_smem, st>>>(P);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
+    KM_CUDA(cudaEventRecord(c->ev[2], st));
     return KMAT_OK;
 }
 
@@ -878,6 +884,22 @@ extern "C" int kmat_label_batch_device(kmat_ctx *c, const char *d_bases, const u
     if (rc != KMAT_OK) return rc;
     if (!d_out) d_out = c->d_out;
     return km_run_device(c, d_bases, d_offs, n_reads, total_bases, max_read_len, d_out, st);
+}
+extern "C" int kmat_ctx_last_kernel_ms(kmat_ctx *c, float *probe_ms, float *score_ms) {
+    if (!c) return KMAT_ERR_ARG;
+    KM_CUDA(cudaSetDevice(c->device));
+    KM_CUDA(cudaEventSynchronize(c->ev[2]));
+    float a = 0, b = 0;
+    KM_CUDA(cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
+    KM_CUDA(cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
+    if (probe_ms) *probe_ms = a;
+    if (score_ms) *score_ms = b;
+    return KMAT_OK;
+}
+extern "C" int kmat_ctx_set_stats(kmat_ctx *c, int enable) {
+    if (!c) return KMAT_ERR_ARG;
+    c->collect_stats = enable ? 1 : 0;
+    return KMAT_OK;
 }
 extern "C" int kmat_ctx_sync(kmat_ctx *c) {
     if (!c) return KMAT_ERR_ARG;
