@@ -264,7 +264,12 @@ def main():
         total = n * L
         setup_s = time.time() - t_setup
 
-        stream = torch.cuda.current_stream().cuda_stream
+        # a non-default torch stream: its handle is passed to the library, so the kernels and the CUDA events
+        # below are on the same stream (handle 0 would mean "the ctx's own stream" to the C ABI)
+        tstream = torch.cuda.Stream()
+        torch.cuda.synchronize()
+        torch.cuda.set_stream(tstream)
+        stream = tstream.cuda_stream
 
         def step():
             ctx.label_device(reads.data_ptr(), d_offs.data_ptr(), n, total, L, None, stream)
