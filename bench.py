@@ -285,7 +285,7 @@ def main():
         sampler = ClockSampler(local)
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        probe_ms, score_ms = [], []
+        probe_ms, cand_ms, score_ms = [], [], []
         barrier()
         e0.record()
         for _ in range(a.steps):
@@ -297,8 +297,9 @@ def main():
         # per-kernel durations (CUDA events on the same stream), one extra untimed step each
         for _ in range(3):
             step()
-            p, s = ctx.kernel_ms()
+            p, c_, s = ctx.kernel_ms()
             probe_ms.append(p)
+            cand_ms.append(c_)
             score_ms.append(s)
         torch.cuda.synchronize()
         st = ctx.stats()
@@ -344,6 +345,7 @@ def main():
             gather_gps, gather_gbps = api.gather_bench(local, 16 << 30, 8, 1 << 29, 10)
             pm = sorted(probe_ms)[len(probe_ms) // 2]
             sm_ = sorted(score_ms)[len(score_ms) // 2]
+            cm_ = sorted(cand_ms)[len(cand_ms) // 2]
             achieved = st.algorithmic_bytes / (pm * 1e-3) / 1e9
             errs = st.reads_error
             line = {
@@ -355,7 +357,7 @@ def main():
                            "parallelism": f"read-sharded x{world}, table replicated, no data-path collective"},
                 "kmer_lookups_per_s": value * lookups_per_read, "lookups_per_read": lookups_per_read,
                 "hit_rate": st.hits / max(1, st.lookups), "reads_error": int(errs),
-                "kernels_ms": {"encode_probe": pm, "score": sm_},
+                "kernels_ms": {"encode_probe": pm, "candidates": cm_, "score": sm_},
                 "roofline": {"bound": "hbm", "kernel": "km_encode_probe_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                              "random_access_peak": gather_gbps, "frac_random_access": achieved / gather_gbps,

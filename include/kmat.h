@@ -180,9 +180,10 @@ typedef struct {
 int kmat_ctx_last_stats(kmat_ctx *, kmat_batch_stats *);
 /* Turn the statistics counters on (default) or off for subsequent batches. */
 int kmat_ctx_set_stats(kmat_ctx *, int enable);
-/* Device time of the two kernels of the last batch (CUDA events on the launching stream): the
- * encode+probe kernel (K1+K2) and the scoring kernel (K3+K4).  Synchronises on the batch. */
-int kmat_ctx_last_kernel_ms(kmat_ctx *, float *probe_ms, float *score_ms);
+/* Device time of the three kernels of the last batch (CUDA events on the launching stream): the
+ * encode+probe kernel (K1+K2), the candidate-set kernel (K3) and the scoring/LCA kernel (K4).
+ * Synchronises on the batch. */
+int kmat_ctx_last_kernel_ms(kmat_ctx *, float *probe_ms, float *cand_ms, float *score_ms);
 /* Kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t kmat_launch_count(void);
 
@@ -196,6 +197,10 @@ int kmat_format_tail(const kmat_read_result *, const kmat_pair *cands, const kma
  * (8, 16 or 32) over a `span_bytes` device allocation; returns achieved gathers/s. */
 int kmat_gather_bench(int device, uint64_t span_bytes, int access_bytes, uint64_t n_gathers, int iters,
                       double *gathers_per_s, double *sector_gbps);
+
+/* cudaLimitMaxL2FetchGranularity hint (32 / 64 / 128) on `device`; bytes <= 0 only queries.  Returns the
+ * granularity in effect, or a negative error. */
+int kmat_set_l2_fetch_granularity(int device, int bytes);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,7 @@ EXPORTS = [
     "kmat_lookup_batch", "kmat_encode_batch", "kmat_inputs_load", "kmat_inputs_free", "kmat_opts_default",
     "kmat_ctx_create", "kmat_ctx_set_opts", "kmat_ctx_destroy", "kmat_label_batch", "kmat_label_batch_device",
     "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench",
+    "kmat_set_l2_fetch_granularity",
 ]
 
 _lib = None
@@ -97,10 +98,11 @@ def lib():
     L.kmat_ctx_sync.argtypes = [vp]
     L.kmat_ctx_last_stats.argtypes = [vp, C.POINTER(BatchStats)]
     L.kmat_ctx_set_stats.argtypes = [vp, C.c_int]
-    L.kmat_ctx_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.kmat_ctx_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.kmat_launch_count.restype = C.c_uint64
     L.kmat_format_tail.argtypes = [vp, vp, vp, C.c_int, C.c_char_p, C.c_size_t]
     L.kmat_gather_bench.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.kmat_set_l2_fetch_granularity.argtypes = [C.c_int, C.c_int]
     _lib = L
     return L
 
@@ -316,9 +318,9 @@ class Ctx:
         _check(lib().kmat_label_batch_device(self.h, d_bases_ptr, d_offs_ptr, n_reads, total_bases, max_read_len, d_out_ptr, stream))
 
     def kernel_ms(self):
-        a, b = C.c_float(), C.c_float()
-        _check(lib().kmat_ctx_last_kernel_ms(self.h, C.byref(a), C.byref(b)))
-        return a.value, b.value
+        a, b, d = C.c_float(), C.c_float(), C.c_float()
+        _check(lib().kmat_ctx_last_kernel_ms(self.h, C.byref(a), C.byref(b), C.byref(d)))
+        return a.value, b.value, d.value
 
     def set_stats(self, enable):
         _check(lib().kmat_ctx_set_stats(self.h, int(enable)))

@@ -502,7 +502,9 @@ extern "C" int kmat_encode_batch(const kmat_db *db, const char *bases, const uin
 // ---------------------------------------------------------------------------------------------
 // random-gather roofline probe: uniform random aligned loads over a large span
 // ---------------------------------------------------------------------------------------------
-template <int BYTES>
+// access modes of the probe: 8 / 16 / 32 = plain loads of that width (32 = the table's LDG.256); the 1xx modes are
+// 8-byte loads with different cache operators, used to find out what a random access costs in DRAM traffic
+template <int MODE>
 __global__ void km_gather_kernel(const uint8_t *__restrict__ base, uint64_t n_units, uint64_t n_gathers, uint64_t seed, unsigned long long *sink) {
     unsigned long long acc = 0;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_gathers; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -510,16 +512,25 @@ __global__ void km_gather_kernel(const uint8_t *__restrict__ base, uint64_t n_un
         x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32;
         const uint64_t u = (uint64_t)(((unsigned __int128)x * n_units) >> 64);
         const uint8_t *p = base + u * 32;                     // one access per 32-byte sector
-        if (BYTES == 8) acc += *(const unsigned long long *)p;
-        else if (BYTES == 16) { const ulonglong2 v = *(const ulonglong2 *)p; acc += v.x ^ v.y; }
-        else { uint64_t a, b, c, d; km_load_bucket((const uint64_t *)p, a, b, c, d); acc += a ^ b ^ c ^ d; }
+        unsigned long long v = 0;
+        if (MODE == 8) v = *(const unsigned long long *)p;
+        else if (MODE == 16) { const ulonglong2 w = *(const ulonglong2 *)p; v = w.x ^ w.y; }
+        else if (MODE == 32) { uint64_t a, b, c, d; km_load_bucket((const uint64_t *)p, a, b, c, d); v = a ^ b ^ c ^ d; }
+        else if (MODE == 101) asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
+        else if (MODE == 102) asm volatile("ld.global.cv.u64 %0, [%1];" : "=l"(v) : "l"(p));
+        else if (MODE == 103) asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+        else if (MODE == 104) asm volatile("ld.global.cs.u64 %0, [%1];" : "=l"(v) : "l"(p));
+        else if (MODE == 105) asm volatile("ld.global.L1::no_allocate.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(p));
+        else if (MODE == 106) asm volatile("ld.global.lu.u64 %0, [%1];" : "=l"(v) : "l"(p));
+        acc += v;
     }
     if (acc == 0x123456789abcdefull) *sink = acc;
 }
 extern "C" int kmat_gather_bench(int device, uint64_t span_bytes, int access_bytes, uint64_t n_gathers, int iters,
                                  double *gathers_per_s, double *sector_gbps) {
     if (kmat_device_count() <= device) { kmat_set_error("CUDA device %d not available", device); return KMAT_ERR_NO_DEVICE; }
-    if (access_bytes != 8 && access_bytes != 16 && access_bytes != 32) return KMAT_ERR_ARG;
+    const int mode = access_bytes;
+    if (mode != 8 && mode != 16 && mode != 32 && !(mode >= 101 && mode <= 106)) return KMAT_ERR_ARG;
     KM_CUDA(cudaSetDevice(device));
     uint8_t *buf; unsigned long long *sink;
     KM_CUDA(cudaMalloc((void **)&buf, span_bytes)); KM_CUDA(cudaMalloc((void **)&sink, 8));
@@ -530,9 +541,9 @@ extern "C" int kmat_gather_bench(int device, uint64_t span_bytes, int access_byt
     for (int it = 0; it < iters + 1; it++) {
         cudaEventRecord(e0);
         const int blocks = 148 * 16, threads = 256;
-        if (access_bytes == 8) km_gather_kernel<8><<<blocks, threads>>>(buf, n_units, n_gathers, 977 * it, sink);
-        else if (access_bytes == 16) km_gather_kernel<16><<<blocks, threads>>>(buf, n_units, n_gathers, 977 * it, sink);
-        else km_gather_kernel<32><<<blocks, threads>>>(buf, n_units, n_gathers, 977 * it, sink);
+#define KM_G(M) case M: km_gather_kernel<M><<<blocks, threads>>>(buf, n_units, n_gathers, 977 * it, sink); break;
+        switch (mode) { KM_G(8) KM_G(16) KM_G(32) KM_G(101) KM_G(102) KM_G(103) KM_G(104) KM_G(105) KM_G(106) }
+#undef KM_G
         g_km_launches++;
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -543,4 +554,15 @@ extern "C" int kmat_gather_bench(int device, uint64_t span_bytes, int access_byt
     if (gathers_per_s) *gathers_per_s = (double)n_gathers / (best * 1e-3);
     if (sector_gbps) *sector_gbps = (double)n_gathers * 32.0 / (best * 1e-3) / 1e9;
     return KMAT_OK;
+}
+
+// cudaLimitMaxL2FetchGranularity hint (32, 64 or 128 bytes) for the current device: random 32-byte probes do not
+// benefit from wider DRAM fetches.  Returns the value in effect afterwards (or a negative error).
+extern "C" int kmat_set_l2_fetch_granularity(int device, int bytes) {
+    if (kmat_device_count() <= device) return KMAT_ERR_NO_DEVICE;
+    KM_CUDA(cudaSetDevice(device));
+    if (bytes > 0) { cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes); if (e != cudaSuccess) cudaGetLastError(); }
+    size_t v = 0;
+    KM_CUDA(cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity));
+    return (int)v;
 }

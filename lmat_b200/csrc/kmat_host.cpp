@@ -489,6 +489,14 @@ int kmat_build_host_ctx(const kmat_inputs &in, int tid_bytes, const std::vector<
         out.sid2nid.resize(stored_tids.size());
         for (size_t i = 0; i < stored_tids.size(); i++) out.sid2nid[i] = nid_of(stored_tids[i]);
     }
+    // fold isHuman / dropped-tid flags into the stored-id table (bit 31 / bit 30; nid in the low 30 bits)
+    if (N >= (1u << 30)) { kmat_set_error("taxonomy too large"); return KMAT_ERR_UNSUPPORTED; }
+    for (auto &e : out.sid2nid) {
+        if (e == KMAT_NONE) continue;
+        const uint32_t meta = out.nodeA[e].meta;
+        e |= (meta & KM_META_HUMAN) ? 0x80000000u : 0u;
+        e |= (meta & KM_META_DROP) ? 0x40000000u : 0u;
+    }
     // ---- pruning ranks (-m)
     if (in.has_prune) {
         out.prune_rank.assign(N, 0);

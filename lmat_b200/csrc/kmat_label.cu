@@ -14,14 +14,21 @@
 #include "kmat_priv.h"
 #include "kmat_std_emul.cuh"
 
-#define KB_WARPS 4
+#define KB_WARPS 8         // warps per CTA of the candidate kernel
 #define KB_PMAX 320        // k-mer positions per read handled by the shared-memory path
-#define KB_POOL 768        // member entries per read
 #define KB_CMAX 64         // candidate taxids per read (one 64-bit mask)
 #define KB_HSLOTS 128
 #define KB_LFAST 16        // list length sorted in place per lane (libstdc++ uses plain insertion sort up to 16)
 #define KB_LIN 128         // lineage entries in findReadLabelVer2
 #define KB_BIGCAP 8192     // per-warp global scratch for longer lists / run-time pruning
+#define KS_THREADS 128     // threads per CTA of the scoring kernel (one read per thread)
+#define KMAT_ST_PENDING 7  // internal: candidates built, scoring still to run
+
+// stored id -> node: low 30 bits nid, bit 31 = isHuman, bit 30 = dropped tid (flags folded in so that the common
+// singleton hit needs no node-record load)
+#define KB_SID_HUMAN 0x80000000u
+#define KB_SID_DROP 0x40000000u
+#define KB_SID_NIDMASK 0x3FFFFFFFu
 
 struct KmCtxDev {
     KmDbDev db;
@@ -50,25 +57,14 @@ struct __align__(16) KmWarpB {
     uint32_t h_nid[KB_HSLOTS], h_seq[KB_HSLOTS], h_leaf[KB_HSLOTS];
     uint8_t h_idx[KB_HSLOTS];
     // candidates, indexed by candidate id.  order[f] = id of the f-th entry of the reference's taxid_lst.
-    uint32_t c_nid[KB_CMAX], c_tid[KB_CMAX], c_meta[KB_CMAX], c_spec[KB_CMAX], c_tin[KB_CMAX], c_tout[KB_CMAX], c_poff[KB_CMAX], c_plen[KB_CMAX];
+    uint32_t c_nid[KB_CMAX], c_tid[KB_CMAX], c_meta[KB_CMAX], c_spec[KB_CMAX], c_poff[KB_CMAX], c_plen[KB_CMAX];
     uint32_t c_leaf[KB_CMAX], c_first[KB_CMAX], c_hits[KB_CMAX];
     unsigned long long c_anc[KB_CMAX];
-    float c_rp[KB_CMAX], c_score[KB_CMAX];
-    uint8_t c_cls[KB_CMAX], c_qual[KB_CMAX], c_slot[KB_CMAX], order[KB_CMAX];
+    uint8_t c_qual[KB_CMAX], c_slot[KB_CMAX], order[KB_CMAX];
     // per position: bit set of the candidate ids kept there (label_vec[pos].second before the post-pass)
     unsigned long long posmask[KB_PMAX];
-    union {
-        struct { uint32_t lst[32][KB_LFAST]; uint16_t dep[32][KB_LFAST]; } pl;      // position loop: per-lane list scratch
-        struct {                                                                  // serial phase
-            KmRl rl[KB_CMAX];
-            uint32_t l_tid[KB_LIN], l_tin[KB_LIN], l_tout[KB_LIN];
-            float l_score[KB_LIN];
-            uint16_t l_depth[KB_LIN];
-            uint8_t l_nogood[KB_LIN], l_perm[KB_LIN];
-        } sp;
-    } u;
-    float track_val[64];
-    uint8_t track_has[64];
+    uint32_t lst[32][KB_LFAST];          // position loop: per-lane list scratch
+    uint16_t dep[32][KB_LFAST];
     uint32_t n_used;
 };
 
@@ -133,12 +129,14 @@ __device__ __forceinline__ uint32_t kb_list_id(const KmDbDev &db, uint32_t off, 
 // Leaf filter (read_label.cpp:1103-1134): ids sorted by depth descending; keep an id unless it is a strict
 // ancestor of an id kept before it.  In place; returns the number kept.
 __device__ int kb_leaf_filter(const KmCtxDev &C, uint32_t *ids, int n) {
-    int m = 0;
-    for (int i = 0; i < n; i++) {
+    if (n <= 1) return n;
+    int m = 1;                                   // the deepest id is always kept
+    uint32_t first_tin = kb_nodeB(C, ids[0]).tin;
+    for (int i = 1; i < n; i++) {
         const uint32_t t = ids[i];
         const KmNodeB tb = kb_nodeB(C, t);
-        bool anc = false;
-        for (int j = 0; j < m && !anc; j++) anc = kb_is_anc(tb.tin, tb.tout, kb_nodeB(C, ids[j]).tin);
+        bool anc = kb_is_anc(tb.tin, tb.tout, first_tin);
+        for (int j = 1; j < m && !anc; j++) anc = kb_is_anc(tb.tin, tb.tout, kb_nodeB(C, ids[j]).tin);
         if (!anc) ids[m++] = t;
     }
     return m;
@@ -153,8 +151,8 @@ struct KbRankLess {       // MyPair::operator< (SortedDb.hpp:133-135): by rank n
 
 // Long list / run-time pruning path, one lane, per-warp global scratch.  Restates TaxNodeStat::begin + next
 // (TaxNodeStat.hpp:60-256) followed by the filters of read_label.cpp:1031-1074.  Returns kept member count
-// (members left in scratch[0..m).x) or <0 on error; *first_out = label_vec[pos].first.
-__device__ int kb_big_list(const KmCtxDev &C, uint32_t hw, uint2 *scratch, int *first_out) {
+// (members left in scratch[0..m).x) or <0 on error (-1 bad taxid, -2 list too long for the scratch).
+__device__ int kb_big_list(const KmCtxDev &C, uint32_t hw, uint2 *scratch) {
     const uint32_t lo = hw & 0x7FFFFFFFu;
     int count = (int)kb_list_count(C.db, lo);
     if (count > KB_BIGCAP / 2) return -2;
@@ -166,15 +164,16 @@ __device__ int kb_big_list(const KmCtxDev &C, uint32_t hw, uint2 *scratch, int *
         if (!C.prune_rank) {               // p_map.size() == 0: count forced to 1, next() reads the first stored id (:78-81)
             count = 1;
             const uint32_t sid = kb_list_id(C.db, lo, 0);
-            const uint32_t nid = sid < C.n_sid ? C.sid2nid[sid] : KMAT_NONE;
-            if (nid == KMAT_NONE) return -1;
-            seq[n++] = make_uint2(nid, 0);
+            const uint32_t e = sid < C.n_sid ? C.sid2nid[sid] : KMAT_NONE;
+            if (e == KMAT_NONE) return -1;
+            seq[n++] = make_uint2(e & KB_SID_NIDMASK, 0);
         } else {                           // :118-201
             int hn = 0;
             for (int i = 0; i < count; i++) {
                 const uint32_t sid = kb_list_id(C.db, lo, i);
-                const uint32_t nid = sid < C.n_sid ? C.sid2nid[sid] : KMAT_NONE;
-                if (nid == KMAT_NONE) return -1;
+                const uint32_t e = sid < C.n_sid ? C.sid2nid[sid] : KMAT_NONE;
+                if (e == KMAT_NONE) return -1;
+                const uint32_t nid = e & KB_SID_NIDMASK;
                 kmstd::pq_push(heap, hn, make_uint2(nid, C.prune_rank[nid]), KbRankLess());
             }
             int newcount = count;
@@ -190,9 +189,9 @@ __device__ int kb_big_list(const KmCtxDev &C, uint32_t hw, uint2 *scratch, int *
     } else {
         for (int i = 0; i < count; i++) {
             const uint32_t sid = kb_list_id(C.db, lo, i);
-            const uint32_t nid = sid < C.n_sid ? C.sid2nid[sid] : KMAT_NONE;
-            if (nid == KMAT_NONE) return -1;
-            seq[n++] = make_uint2(nid, 0);
+            const uint32_t e = sid < C.n_sid ? C.sid2nid[sid] : KMAT_NONE;
+            if (e == KMAT_NONE) return -1;
+            seq[n++] = make_uint2(e & KB_SID_NIDMASK, 0);
         }
     }
     // human collapse, dropped ids, depth lookup (read_label.cpp:1031-1066)
@@ -208,7 +207,6 @@ __device__ int kb_big_list(const KmCtxDev &C, uint32_t hw, uint2 *scratch, int *
         if (meta & KM_META_DROP) continue;
         seq[w++] = make_uint2(nid, meta & KM_META_DEPTH_MASK);
     }
-    *first_out = w > 0 ? (int)(int16_t)(uint16_t)(count <= 0 ? 1 : count) : 0;
     kmstd::sort(seq, w, KbDepthDesc());                                  // :1073-1074
     // leaf filter
     int m = 0;
@@ -223,184 +221,11 @@ __device__ int kb_big_list(const KmCtxDev &C, uint32_t hw, uint2 *scratch, int *
 }
 
 // ---------------------------------------------------------------------------------------------
-// serial phase (lane 0): construct_labels from the score sums on (:803-941) and findReadLabelVer2 (:284-419)
+// K3: candidate sets.  One warp per read.  Restates the list handling and the post-pass of retrieve_kmer_labels
+// (read_label.cpp:1031-1204) and the per-taxid position counts of construct_labels (:748-759).  Leaves, per
+// read, the candidates in taxid_lst order as (nid, hits) pairs in the cands buffer for the scoring kernel.
 // ---------------------------------------------------------------------------------------------
-struct KbTCmp {           // TCmp, read_label.cpp:475-485: |a-b| < 0.001 (double compare) -> shallower first, else by score
-    const KmWarpB *S;
-    __device__ bool operator()(const KmRl &a, const KmRl &b) const {
-        if ((double)fabsf(__fsub_rn(a.score, b.score)) < 0.001) return (int)(S->c_meta[a.idx] & KM_META_DEPTH_MASK) < (int)(S->c_meta[b.idx] & KM_META_DEPTH_MASK);
-        return a.score < b.score;
-    }
-};
-struct KbLinDepthDesc {   // CmpDepth over lineage entries (:159-167), sorting a permutation
-    const KmWarpB *S;
-    __device__ bool operator()(const uint8_t &a, const uint8_t &b) const { return (int)S->u.sp.l_depth[a] > (int)S->u.sp.l_depth[b]; }
-};
-
-__device__ void kb_serial_phase(const KmScoreParams &P, KmWarpB &S, int C, bool hasHuman, kmat_read_result &res) {
-    const KmCtxDev &X = P.C;
-    KmRl *rl = S.u.sp.rl;
-    uint32_t *l_tid = S.u.sp.l_tid, *l_tin = S.u.sp.l_tin, *l_tout = S.u.sp.l_tout;
-    float *l_score = S.u.sp.l_score;
-    uint16_t *l_depth = S.u.sp.l_depth;
-    uint8_t *l_nogood = S.u.sp.l_nogood, *l_perm = S.u.sp.l_perm;
-    // ---- :807-837 sums in taxid_lst order
-    bool fndPhiX = false;
-    float log_sum = 0.0f, pos_log_sum = 0.0f, top_score = 0.0f, phiXscore = 0.0f;
-    unsigned sig_hits = 0, pos_sig_hits = 0;
-    for (int f = 0; f < C; f++) {
-        const int i = S.order[f];
-        const float lo = S.c_score[i];
-        log_sum = __fadd_rn(log_sum, lo);
-        sig_hits++;
-        if (lo > 0) { pos_sig_hits++; pos_log_sum = __fadd_rn(pos_log_sum, lo); }
-        if (X.opt.phix_screen && (S.c_meta[i] & KM_META_PHIX)) { phiXscore = lo; fndPhiX = true; }
-        if (f == 0 || lo > top_score) top_score = lo;
-    }
-    res.n_cand = 0; res.n_lin = 0; res.cand_off = 0; res.lin_off = 0;
-    if (X.opt.phix_screen && phiXscore >= top_score && fndPhiX) {           // :841-848
-        res.status = KMAT_ST_PHIX; res.match = KMAT_DIRECT; res.tid = 32630u; res.score = phiXscore;
-        return;
-    }
-    float log_avg; unsigned use_sig_hits;
-    const unsigned min_pos_examples = 3;
-    if (pos_sig_hits > min_pos_examples) { use_sig_hits = pos_sig_hits; log_avg = __fdiv_rn(pos_log_sum, (float)pos_sig_hits); }
-    else { use_sig_hits = sig_hits; log_avg = sig_hits > 0 ? __fdiv_rn(log_sum, (float)sig_hits) : 0.0f; }
-    float log_std = 0.0f;
-    for (int f = 0; f < C; f++) {                                            // :865-880
-        const float sc = S.c_score[S.order[f]];
-        if (sc > 0 && pos_sig_hits > min_pos_examples) { const float v = __fsub_rn(log_avg, sc); log_std = __fadd_rn(log_std, __fmul_rn(v, v)); }
-        if (pos_sig_hits <= min_pos_examples) { const float v = __fsub_rn(log_avg, sc); log_std = __fadd_rn(log_std, __fmul_rn(v, v)); }
-    }
-    const float stdev1 = use_sig_hits > 1 ? __fsqrt_rn(__fdiv_rn(log_std, (float)(use_sig_hits - 1))) : 0.0f;   // :881
-    res.status = KMAT_ST_LABELED; res.log_avg = log_avg; res.stdev = stdev1;
-    // rank_label = (tid, score [+ hbias*stdev for human tids]) in taxid_lst order, then sort(TCmp)   :882-893
-    for (int f = 0; f < C; f++) {
-        const int i = S.order[f];
-        float sc = S.c_score[i];
-        if (hasHuman && (S.c_meta[i] & KM_META_HUMAN)) sc = __fadd_rn(sc, __fmul_rn(X.opt.hbias, stdev1));
-        rl[f].score = sc; rl[f].idx = (uint32_t)i;
-    }
-    KbTCmp tcmp{&S};
-    kmstd::sort(rl, C, tcmp);
-    const float diff_thresh = __fmul_rn(stdev1, X.opt.sdiff);                // :895
-    // ---- findReadLabelVer2
-    int nlin = 0;
-    auto lin_push_cand = [&](int ci, float score) {
-        if (nlin >= KB_LIN) return false;
-        l_tid[nlin] = S.c_tid[ci]; l_tin[nlin] = S.c_tin[ci]; l_tout[nlin] = S.c_tout[ci]; l_score[nlin] = score;
-        l_depth[nlin] = (uint16_t)(S.c_meta[ci] & KM_META_DEPTH_MASK); l_nogood[nlin] = 0;
-        nlin++;
-        return true;
-    };
-    bool plasmidTopHit = false; int savePlasmid = -1;
-    unsigned lowest_depth = 0, highest_depth = 0;
-    int lowest = -1, highest = -1; float lowest_score = 0;
-    int lidx = -1; bool linDone = false, lin_overflow = false;
-    for (int i = C - 1; i >= 0; --i) {                                        // :295-325
-        const int ci = (int)rl[i].idx; const float sc = rl[i].score;
-        const unsigned cdepth = S.c_meta[ci] & KM_META_DEPTH_MASK;
-        if (sc >= top_score && (S.c_meta[ci] & KM_META_PLASMID)) { plasmidTopHit = true; savePlasmid = ci; }
-        bool added = false;
-        if (!linDone) {                                                       // addToCandLineage :225-262
-            bool addNode = true;
-            for (int q = 0; q < nlin; q++) {
-                const unsigned chk = l_depth[q];
-                if (chk > cdepth && !kb_is_anc(S.c_tin[ci], S.c_tout[ci], l_tin[q])) { addNode = false; break; }
-                else if (chk < cdepth && !kb_is_anc(l_tin[q], l_tout[q], S.c_tin[ci])) { addNode = false; break; }
-                else if (chk == cdepth) { addNode = false; break; }
-            }
-            if (addNode) { if (!lin_push_cand(ci, sc)) lin_overflow = true; added = true; }
-        }
-        if (!linDone && !added) { lidx = i; linDone = true; }
-        else if (!linDone) {
-            if (cdepth > lowest_depth || i == C - 1) { lowest = ci; lowest_score = sc; lowest_depth = cdepth; }
-            if (cdepth < highest_depth || i == C - 1) { highest = ci; highest_depth = cdepth; }
-        }
-        if (linDone && sc < top_score) break;
-    }
-    const int add_lo = nlin; int add_hi = nlin;                               // add_set = lineage entries [add_lo, add_hi)
-    if (highest_depth != 0 && highest >= 0) {                                 // :327-343
-        const uint32_t poff = S.c_poff[highest], plen = S.c_plen[highest];
-        for (uint32_t q = 0; q < plen; q++) {
-            const uint32_t a = X.paths[poff + q];
-            if (nlin >= KB_LIN) { lin_overflow = true; break; }
-            const int slot = kb_cand_find(S, a);
-            if (slot >= 0) lin_push_cand((int)S.h_idx[slot], S.c_score[S.h_idx[slot]]);      // all_cand_set holds the un-biased score
-            else {
-                const KmNodeA na = kb_nodeA(X, a); const KmNodeB nb = kb_nodeB(X, a);
-                l_tid[nlin] = na.tid; l_tin[nlin] = nb.tin; l_tout[nlin] = nb.tout; l_score[nlin] = -10000.0f;
-                l_depth[nlin] = (uint16_t)(na.meta & KM_META_DEPTH_MASK); l_nogood[nlin] = 0;
-                nlin++;
-            }
-        }
-        add_hi = nlin;
-    }
-    if (lin_overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; return; }
-    for (int q = 0; q < nlin; q++) l_perm[q] = (uint8_t)q;
-    KbLinDepthDesc ldd{&S};
-    kmstd::sort(l_perm, nlin, ldd);                                           // cand_lin_vec sorted by depth desc :350-351
-    bool any_nogood = false;
-    for (int i = lidx; i >= 0; --i) {                                         // :355-362
-        const int ci = (int)rl[i].idx; const float sc = rl[i].score;
-        bool in_add = false;
-        for (int q = add_lo; q < add_hi && !in_add; q++) in_add = l_tid[q] == S.c_tid[ci];
-        if (in_add) continue;
-        bool keep_going = true;                                               // cmpCompLineage :264-282
-        for (int z = 0; z < nlin; z++) {
-            const int q = l_perm[z];
-            if (kb_is_anc(l_tin[q], l_tout[q], S.c_tin[ci])) break;
-            const float dlt = __fsub_rn(l_score[q], sc);
-            if (l_score[q] != -10000.0f && dlt > diff_thresh) { keep_going = false; break; }
-            if (dlt <= diff_thresh) { l_nogood[q] = 1; any_nogood = true; }
-        }
-        if (!keep_going) break;
-    }
-    uint32_t call_tid = 0; float call_score = 0; int match = KMAT_NOMATCH;
-    uint32_t call_tin = 0, call_tout = 0; bool call_has_node = false;
-    if (nlin == 0 && !any_nogood) match = KMAT_NOMATCH;
-    else if (nlin != 0 && !any_nogood) {                                      // :366-368
-        call_tid = S.c_tid[lowest]; call_score = lowest_score; match = KMAT_DIRECT;
-        call_tin = S.c_tin[lowest]; call_tout = S.c_tout[lowest]; call_has_node = true;
-    } else {                                                                  // :369-409
-        float max_val = -10000.0f; int root = -1;
-        for (int z = 0; z < nlin; z++) {
-            const int q = l_perm[z];
-            max_val = l_score[q] < max_val ? max_val : l_score[q];           // std::max(cand, max_val)
-            bool ng = false;                                                  // no_good is a set of taxids
-            for (int y = 0; y < nlin && !ng; y++) ng = l_nogood[y] && l_tid[y] == l_tid[q];
-            if (!ng) { root = q; break; }
-        }
-        if (root < 0) { call_tid = 0; call_score = -1.0f; match = KMAT_LCA_ERROR; }
-        else {
-            match = KMAT_MULTI;
-            bool in_all = false;
-            for (int c2 = 0; c2 < C && !in_all; c2++) in_all = S.c_tid[c2] == l_tid[root];
-            if (in_all && max_val < l_score[root]) { match = KMAT_PARTIAL; max_val = l_score[root]; }   // :400-406 (unreachable in practice)
-            call_tid = l_tid[root]; call_score = max_val; call_tin = l_tin[root]; call_tout = l_tout[root]; call_has_node = true;
-        }
-    }
-    if (plasmidTopHit && call_has_node && kb_is_anc(call_tin, call_tout, S.c_tin[savePlasmid])) call_tid = S.c_tid[savePlasmid];   // :410-416
-    res.match = match;
-    if (match == KMAT_DIRECT || match == KMAT_MULTI || match == KMAT_PARTIAL) { res.tid = call_tid; res.score = call_score; }
-    else { res.tid = 0; res.score = 0; }                                      // best_guess stays (0,0), :839
-    // ---- outputs: sorted rank_label, lineage
-    res.n_cand = (uint32_t)C;
-    const unsigned long long co = atomicAdd(P.cand_cursor, (unsigned long long)C);
-    res.cand_off = co;
-    if (P.cands && co + C <= P.cand_cap) for (int i = 0; i < C; i++) P.cands[co + i] = kmat_pair{S.c_tid[rl[i].idx], rl[i].score};
-    if (X.opt.want_lineage) {
-        res.n_lin = (uint32_t)nlin;
-        const unsigned long long lo2 = atomicAdd(P.lin_cursor, (unsigned long long)nlin);
-        res.lin_off = lo2;
-        if (P.lin && lo2 + nlin <= P.lin_cap) for (int q = 0; q < nlin; q++) P.lin[lo2 + q] = kmat_pair{l_tid[q], l_score[q]};
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// the scoring kernel
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P) {
+__global__ void __launch_bounds__(KB_WARPS * 32) km_cand_kernel(KmScoreParams P) {
     extern __shared__ __align__(16) unsigned char kb_smem[];
     KmWarpB &S = reinterpret_cast<KmWarpB *>(kb_smem)[threadIdx.x >> 5];
     const KmCtxDev &X = P.C;
@@ -434,53 +259,79 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P
         for (int p0 = 0; p0 < np; p0 += 32) {
             const int p = p0 + lane;
             const uint32_t hw = p < np ? P.hit[off + p] : KM_HIT_INVALID;
-            uint32_t *L = S.u.pl.lst[lane];
-            uint16_t *D = S.u.pl.dep[lane];
+            uint32_t *L = S.lst[lane];
+            uint16_t *D = S.dep[lane];
             int m = 0;
             bool bigl = false;
+            uint32_t single = KMAT_NONE;                                      // the kept member when there is exactly one
             if (hw != KM_HIT_INVALID) {
                 cand_cnt++;                                                   // label_vec[pos].first >= 0 (:1015, :702)
                 if (hw != KM_HIT_MISS) {
-                    int n_raw = 1;
-                    const uint32_t lo = hw & 0x7FFFFFFFu;
-                    if (hw & KM_HIT_LIST) {
-                        n_raw = (int)kb_list_count(X.db, lo);
+                    if (!(hw & KM_HIT_LIST)) {
+                        // singleton: one stored id.  16->32 conversion, human collapse, dropped tids (:1031-1038)
+                        const uint32_t e = hw < X.n_sid ? X.sid2nid[hw] : KMAT_NONE;
+                        if (e == KMAT_NONE) err = KMAT_ERR_BAD_TAXID;          // "bad taxid" assert (TaxNodeStat.hpp:235-238)
+                        else if (!(e & KB_SID_DROP)) { single = (e & KB_SID_HUMAN) ? X.nid_human : (e & KB_SID_NIDMASK); m = 1; }
+                    } else {
+                        const uint32_t lo = hw & 0x7FFFFFFFu;
+                        const int n_raw = (int)kb_list_count(X.db, lo);
                         st_list_ids += n_raw;
                         st_list_sectors += (2 + n_raw * X.db.tid_bytes + 31) / 32;
                         if (n_raw > KB_LFAST || n_raw > X.opt.max_count) bigl = true;
-                    }
-                    if (!bigl) {
-                        bool seenHuman = false;
-                        int n = 0;
-                        for (int j = 0; j < n_raw; j++) {
-                            const uint32_t sid = (hw & KM_HIT_LIST) ? kb_list_id(X.db, lo, j) : hw;
-                            uint32_t nid = sid < X.n_sid ? X.sid2nid[sid] : KMAT_NONE;
-                            if (nid == KMAT_NONE) { err = KMAT_ERR_BAD_TAXID; break; }              // "bad taxid" assert (TaxNodeStat.hpp:235-238)
-                            uint32_t meta = kb_nodeA(X, nid).meta;
-                            if (meta & KM_META_HUMAN) {                                             // :1033-1037
-                                if (seenHuman) continue;
-                                nid = X.nid_human; meta = kb_nodeA(X, nid).meta; seenHuman = true;
+                        else {
+                            bool seenHuman = false;
+                            int n = 0;
+                            for (int j = 0; j < n_raw; j++) {
+                                const uint32_t sid = kb_list_id(X.db, lo, j);
+                                const uint32_t e = sid < X.n_sid ? X.sid2nid[sid] : KMAT_NONE;
+                                if (e == KMAT_NONE) { err = KMAT_ERR_BAD_TAXID; break; }
+                                if (e & KB_SID_DROP) continue;                                       // :1038
+                                uint32_t nid = e & KB_SID_NIDMASK;
+                                if (e & KB_SID_HUMAN) {                                               // :1033-1037
+                                    if (seenHuman) continue;
+                                    nid = X.nid_human; seenHuman = true;
+                                }
+                                // insertion into depth-descending order == std::sort's insertion sort for n <= 16 (stable)
+                                const uint16_t dpt = (uint16_t)(kb_nodeA(X, nid).meta & KM_META_DEPTH_MASK);
+                                int q = n;
+                                while (q > 0 && D[q - 1] < dpt) { L[q] = L[q - 1]; D[q] = D[q - 1]; q--; }
+                                L[q] = nid; D[q] = dpt;
+                                n++;
                             }
-                            if (meta & KM_META_DROP) continue;                                      // :1038
-                            // insertion into depth-descending order == std::sort's insertion sort for n <= 16 (stable)
-                            const uint16_t dpt = (uint16_t)(meta & KM_META_DEPTH_MASK);
-                            int q = n;
-                            while (q > 0 && D[q - 1] < dpt) { L[q] = L[q - 1]; D[q] = D[q - 1]; q--; }
-                            L[q] = nid; D[q] = dpt;
-                            n++;
+                            m = err ? 0 : kb_leaf_filter(X, L, n);
+                            if (m == 1) single = L[0];
                         }
-                        m = err ? 0 : kb_leaf_filter(X, L, n);
                     }
                 }
             }
-            // insert the kept members (taxid_lst / leaf_track bookkeeping, :1111-1122); L[j] becomes the hash slot
-            if (m > 0) {
+            // insert the kept members (taxid_lst / leaf_track bookkeeping, :1111-1122)
+            // (a) positions with exactly one member: lanes holding the same taxid elect a leader
+            {
+                const uint32_t smask = __ballot_sync(KM_FULL, m == 1);
+                if (m == 1) {
+                    const uint32_t grp = __match_any_sync(smask, single);
+                    const int leader = __ffs(grp) - 1;
+                    int slot = 0;
+                    if (lane == leader) {
+                        slot = kb_cand_insert(S, single);
+                        if (slot >= 0) {
+                            atomicMin(&S.h_seq[slot], (uint32_t)p << 16);             // first appearance: lowest position of the group
+                            atomicAdd(&S.h_leaf[slot], (uint32_t)__popc(grp));        // leaf_track
+                        }
+                    }
+                    slot = __shfl_sync(grp, slot, leader);
+                    if (slot < 0) { overflow = true; m = 0; } else L[0] = (uint32_t)slot;
+                    fnd_cnt++;
+                }
+            }
+            // (b) positions with several members
+            if (m > 1) {
                 fnd_cnt++;
                 for (int j = 0; j < m; j++) {
                     const int slot = kb_cand_insert(S, L[j]);
                     if (slot < 0) { overflow = true; m = 0; break; }
                     atomicMin(&S.h_seq[slot], ((uint32_t)p << 16) | (uint32_t)j);   // first appearance in taxid_lst order
-                    atomicAdd(&S.h_leaf[slot], 1u);                                 // leaf_track
+                    atomicAdd(&S.h_leaf[slot], 1u);
                     L[j] = (uint32_t)slot;
                 }
             }
@@ -490,14 +341,13 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P
                 for (int j = 0; j < m; j++) mask |= 1ull << S.h_idx[L[j]];
                 S.posmask[p] = mask;
             }
-            // long lists / run-time pruning: one lane at a time through the per-warp global scratch
+            // (c) long lists / run-time pruning: one lane at a time through the per-warp global scratch
             uint32_t bigmask = __ballot_sync(KM_FULL, bigl);
             while (bigmask) {
                 const int src = __ffs(bigmask) - 1;
                 bigmask &= bigmask - 1;
                 if (lane == src) {
-                    int first = 0;
-                    const int mm = kb_big_list(X, hw, big, &first);
+                    const int mm = kb_big_list(X, hw, big);
                     if (mm == -1) err = KMAT_ERR_BAD_TAXID;
                     else if (mm < 0) overflow = true;
                     else if (mm > 0) {
@@ -528,6 +378,14 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P
             st_fast++;
             continue;
         }
+        const uint16_t cand16 = (uint16_t)cand_cnt;
+        res.cand_kmer_cnt = cand16;
+        if (fnd_cnt < X.opt.min_fnd_kmer || (int)cand16 < X.opt.min_kmer) {       // construct_labels :727-733: silent NoMatch
+            res.status = KMAT_ST_SILENT; res.match = KMAT_NOMATCH; res.tid = 0; res.score = -1.0f;
+            if (lane == 0) P.out[r] = res;
+            st_fast++;
+            continue;
+        }
         // ---- taxid_lst order of the first C1 candidates = order of first appearance (position, then list order)
         for (int i = lane; i < C1; i += 32) {
             const int s = S.c_slot[i];
@@ -538,9 +396,10 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P
             const uint32_t nid = S.h_nid[s];
             const KmNodeA na = kb_nodeA(X, nid); const KmNodeB nb = kb_nodeB(X, nid);
             S.c_nid[i] = nid; S.c_tid[i] = na.tid; S.c_meta[i] = na.meta; S.c_spec[i] = na.species_anc;
-            S.c_tin[i] = nb.tin; S.c_tout[i] = nb.tout; S.c_poff[i] = nb.path_off; S.c_plen[i] = nb.path_len;
+            S.c_poff[i] = nb.path_off; S.c_plen[i] = nb.path_len;
             S.c_leaf[i] = S.h_leaf[s]; S.c_first[i] = q >> 16; S.c_anc[i] = 0ull;
         }
+        for (int i = lane; i < KB_CMAX; i += 32) S.c_hits[i] = 0;
         __syncwarp();
         // ---- representative strain per species (:1143-1177) -> which members get their lineage added
         for (int i = lane; i < C1; i += 32) {
@@ -597,10 +456,7 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P
                         }
                         slot = (int)h;
                         S.h_idx[h] = (uint8_t)idx; S.c_slot[idx] = (uint8_t)h; S.order[idx] = (uint8_t)idx;
-                        const KmNodeA na = kb_nodeA(X, a); const KmNodeB nb = kb_nodeB(X, a);
-                        S.c_nid[idx] = a; S.c_tid[idx] = na.tid; S.c_meta[idx] = na.meta; S.c_spec[idx] = na.species_anc;
-                        S.c_tin[idx] = nb.tin; S.c_tout[idx] = nb.tout; S.c_poff[idx] = nb.path_off; S.c_plen[idx] = nb.path_len;
-                        S.c_leaf[idx] = 0; S.c_first[idx] = 0; S.c_anc[idx] = 0ull; S.c_qual[idx] = 0;
+                        S.c_nid[idx] = a; S.c_anc[idx] = 0ull; S.c_qual[idx] = 0;
                     }
                     C += nnew;
                     __syncwarp();
@@ -612,89 +468,46 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P
             }
         }
         if (overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; if (lane == 0) P.out[r] = res; st_err++; continue; }
-        // ---- hits per candidate = number of positions whose (expanded) set holds it (:748-759)
-        {
-            uint32_t acc0 = 0, acc1 = 0;
-            for (int p0 = 0; p0 < np; p0 += 32) {
-                const int p = p0 + lane;
-                unsigned long long mask = 0;
-                if (p < np) {
-                    unsigned long long mm = S.posmask[p];
-                    mask = mm;
-                    while (mm) {
-                        const int idx = __ffsll((long long)mm) - 1;
-                        mm &= mm - 1;
-                        if (S.c_qual[idx]) mask |= S.c_anc[idx];
+        // ---- hits per candidate = number of positions whose (expanded) set holds it (:748-759).  Positions of a
+        //      chunk with the same set are counted once by a leader lane.
+        for (int p0 = 0; p0 < np; p0 += 32) {
+            const int p = p0 + lane;
+            unsigned long long mask = 0;
+            if (p < np) {
+                unsigned long long mm = S.posmask[p];
+                mask = mm;
+                while (mm) {
+                    const int idx = __ffsll((long long)mm) - 1;
+                    mm &= mm - 1;
+                    if (S.c_qual[idx]) mask |= S.c_anc[idx];
+                }
+            }
+            const uint32_t act = __ballot_sync(KM_FULL, mask != 0);
+            if (mask != 0) {
+                const uint32_t grp = __match_any_sync(act, mask);
+                if (lane == __ffs(grp) - 1) {
+                    const uint32_t cnt = (uint32_t)__popc(grp);
+                    while (mask) {
+                        const int idx = __ffsll((long long)mask) - 1;
+                        mask &= mask - 1;
+                        atomicAdd(&S.c_hits[idx], cnt);
                     }
                 }
-                if (!__any_sync(KM_FULL, mask != 0)) continue;
-                for (int c = 0; c < C; c++) {
-                    const uint32_t bal = __ballot_sync(KM_FULL, (mask >> c) & 1);
-                    if ((c & 31) == lane) { if (c < 32) acc0 += __popc(bal); else acc1 += __popc(bal); }
-                }
             }
-            if (lane < C) S.c_hits[lane] = acc0;
-            if (lane + 32 < C) S.c_hits[lane + 32] = acc1;
         }
         __syncwarp();
-        // ---- construct_labels (:692-941)
-        const uint16_t cand16 = (uint16_t)cand_cnt;
-        res.cand_kmer_cnt = cand16;
-        if (fnd_cnt < X.opt.min_fnd_kmer || (int)cand16 < X.opt.min_kmer) {       // :727-733: silent NoMatch
-            res.status = KMAT_ST_SILENT; res.match = KMAT_NOMATCH; res.tid = 0; res.score = -1.0f;
-            if (lane == 0) P.out[r] = res;
-            st_fast++;
-            continue;
-        }
-        const int model = X.n_models ? (int)X.model_of_cand[cand16] : -1;
-        const bool useRandMod = model >= 0;
-        bool hasHuman = false, bad_model = false;
-        for (int i = lane; i < C; i += 32) {
-            hasHuman |= (S.c_meta[i] & KM_META_HUMAN) != 0;
-            float rp = 0.1f; uint8_t cls = 0;
-            if (useRandMod) {
-                const int32_t row = X.mrow[(size_t)model * X.n_nodes + S.c_nid[i]];
-                if (row >= 0) {
-                    // val_vec[bin_sel]: bin_sel == nbins (GC 100 %) reads past the vector in the reference (:770); 0 here
-                    const float val = hd.y >= 0 && hd.y < X.nbins ? X.cut[(size_t)row * X.nbins + hd.y] : 0.0f;
-                    rp = __double2float_rn(__dadd_rn((double)val, 0.0001));         // :771
-                    cls = X.cls[row];
-                } else { rp = 1.0f; bad_model = true; }                              // :773-778: the reference asserts here
-            }
-            S.c_rp[i] = rp; S.c_cls[i] = cls;
-        }
-        hasHuman = __any_sync(KM_FULL, hasHuman);
-        bad_model = __any_sync(KM_FULL, bad_model);
-        if (bad_model) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_FORMAT; if (lane == 0) P.out[r] = res; st_err++; continue; }
-        __syncwarp();
-        if (useRandMod && lane == 0) {                                               // track[] class maxima, order dependent (:776-800)
-            for (int c = 0; c < X.n_classes; c++) S.track_has[c] = 0;
-            for (int f = 0; f < C; f++) {
+        // ---- hand over to the scoring kernel: (nid, hits) in taxid_lst order
+        unsigned long long co = 0;
+        if (lane == 0) co = atomicAdd(P.cand_cursor, (unsigned long long)C);
+        co = __shfl_sync(KM_FULL, co, 0);
+        res.status = KMAT_ST_PENDING; res.n_cand = (uint32_t)C; res.cand_off = co;
+        if (P.cands && co + C <= P.cand_cap) {
+            for (int f = lane; f < C; f += 32) {
                 const int i = S.order[f];
-                const int cid = S.c_cls[i];
-                const float rp = S.c_rp[i];
-                if (!S.track_has[cid]) { S.track_has[cid] = 1; S.track_val[cid] = rp; }
-                else S.track_val[cid] = rp < S.track_val[cid] ? S.track_val[cid] : rp;       // std::max(random_prob, track[cval])
-                for (int ti = (int)X.class_ranknum[cid] - 1; ti >= 0; ti--) {
-                    if (!S.track_has[ti]) { S.track_has[ti] = 1; S.track_val[ti] = 0.0f; }   // operator[] default-inserts 0
-                    S.track_val[cid] = S.track_val[cid] < S.track_val[ti] ? S.track_val[ti] : S.track_val[cid];
-                }
+                P.cands[co + f] = kmat_pair{S.c_nid[i], __uint_as_float(S.c_hits[i])};
             }
-        }
-        __syncwarp();
-        for (int i = lane; i < C; i += 32) {                                         // :807-820
-            const float label_prob = __fdiv_rn((float)S.c_hits[i], (float)cand16);  // :761
-            float sc = label_prob;
-            if (useRandMod) {
-                const float random_prob = S.track_val[S.c_cls[i]];
-                const float denom = random_prob <= 0 ? 0.00001f : random_prob;       // :687
-                sc = km_logf(__fdiv_rn(label_prob, denom));                          // :688
-            }
-            S.c_score[i] = sc;
-        }
-        __syncwarp();
-        if (lane == 0) { kb_serial_phase(P, S, C, hasHuman, res); P.out[r] = res; }
-        __syncwarp();
+        } else { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_OVERFLOW; }       // candidate buffer too small: the host re-runs with the size asked for
+        if (lane == 0) P.out[r] = res;
         st_fast++;
     }
     if (P.stats && lane == 0) {
@@ -704,6 +517,234 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_score_kernel(KmScoreParams P
         st_list_ids = (unsigned long long)km_warp_sum((int)st_list_ids); st_list_sectors = (unsigned long long)km_warp_sum((int)st_list_sectors);
         if (lane == 0) { atomicAdd(&P.stats->list_ids, st_list_ids); atomicAdd(&P.stats->list_sectors, st_list_sectors); }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: scoring and LCA.  One THREAD per read (the arithmetic is order dependent and cannot be spread over
+// lanes; running 32 reads per warp keeps the lanes busy instead).  Restates construct_labels from the null-model
+// lookup on (read_label.cpp:735-941) and findReadLabelVer2 (:284-419) in the reference's float operation order.
+// ---------------------------------------------------------------------------------------------
+struct KsLocal {
+    uint32_t nid[KB_CMAX], tid[KB_CMAX], tin[KB_CMAX], tout[KB_CMAX];
+    float score[KB_CMAX], rp[KB_CMAX];
+    uint16_t depth[KB_CMAX];
+    uint8_t flags[KB_CMAX], cls[KB_CMAX];        // flags: 1 human, 2 phix, 4 plasmid
+    KmRl rl[KB_CMAX];
+    uint32_t l_tid[KB_LIN], l_tin[KB_LIN], l_tout[KB_LIN];
+    float l_score[KB_LIN];
+    uint16_t l_depth[KB_LIN];
+    uint8_t l_nogood[KB_LIN], l_perm[KB_LIN];
+    float track_val[64];
+    uint8_t track_has[64];
+};
+struct KsTCmp {           // TCmp, read_label.cpp:475-485: |a-b| < 0.001 (double compare) -> shallower first, else by score
+    const uint16_t *depth;
+    __device__ bool operator()(const KmRl &a, const KmRl &b) const {
+        if ((double)fabsf(__fsub_rn(a.score, b.score)) < 0.001) return (int)depth[a.idx] < (int)depth[b.idx];
+        return a.score < b.score;
+    }
+};
+struct KsLinDepthDesc {   // CmpDepth over lineage entries (:159-167), sorting a permutation
+    const uint16_t *l_depth;
+    __device__ bool operator()(const uint8_t &a, const uint8_t &b) const { return (int)l_depth[a] > (int)l_depth[b]; }
+};
+
+__global__ void __launch_bounds__(KS_THREADS) km_score_kernel(KmScoreParams P) {
+    const uint32_t r = blockIdx.x * KS_THREADS + threadIdx.x;
+    if (r >= P.n_reads) return;
+    kmat_read_result res = P.out[r];
+    if (res.status != KMAT_ST_PENDING) return;
+    const KmCtxDev &X = P.C;
+    KsLocal T;
+    const int C = (int)res.n_cand;
+    const unsigned long long co = res.cand_off;
+    const uint16_t cand16 = (uint16_t)res.cand_kmer_cnt;
+    const int bin = res.bin_sel;
+    const int model = X.n_models ? (int)X.model_of_cand[cand16] : -1;          // getReadLen(cand_kmer_cnt) -> model (:736-742)
+    const bool useRandMod = model >= 0;
+    bool hasHuman = false, bad_model = false;
+    // ---- :748-802 per-taxid hit fraction, null-model cut-off, class maxima (order dependent)
+    if (useRandMod) for (int c = 0; c < X.n_classes; c++) T.track_has[c] = 0;
+    for (int f = 0; f < C; f++) {
+        const kmat_pair e = P.cands[co + f];
+        const uint32_t nid = e.tid, hits = __float_as_uint(e.score);
+        const KmNodeA na = kb_nodeA(X, nid); const KmNodeB nb = kb_nodeB(X, nid);
+        T.nid[f] = nid; T.tid[f] = na.tid; T.tin[f] = nb.tin; T.tout[f] = nb.tout;
+        T.depth[f] = (uint16_t)(na.meta & KM_META_DEPTH_MASK);
+        T.flags[f] = (uint8_t)(((na.meta & KM_META_HUMAN) ? 1 : 0) | ((na.meta & KM_META_PHIX) ? 2 : 0) | ((na.meta & KM_META_PLASMID) ? 4 : 0));
+        hasHuman |= (na.meta & KM_META_HUMAN) != 0;
+        T.score[f] = __fdiv_rn((float)hits, (float)cand16);                     // label_prob (:761)
+        if (useRandMod) {
+            const int32_t row = X.mrow[(size_t)model * X.n_nodes + nid];
+            if (row < 0) { bad_model = true; continue; }                        // :773-778: the reference asserts here
+            // val_vec[bin_sel]: bin_sel == nbins (GC 100 %) reads past the vector in the reference (:770); 0 here
+            const float val = bin >= 0 && bin < X.nbins ? X.cut[(size_t)row * X.nbins + bin] : 0.0f;
+            const float rp = __double2float_rn(__dadd_rn((double)val, 0.0001)); // :771
+            const int cid = X.cls[row];
+            T.cls[f] = (uint8_t)cid;
+            if (!T.track_has[cid]) { T.track_has[cid] = 1; T.track_val[cid] = rp; }
+            else T.track_val[cid] = rp < T.track_val[cid] ? T.track_val[cid] : rp;          // std::max(random_prob, track[cval])
+            for (int ti = (int)X.class_ranknum[cid] - 1; ti >= 0; ti--) {                     // :787-790 / :795-798
+                if (!T.track_has[ti]) { T.track_has[ti] = 1; T.track_val[ti] = 0.0f; }      // operator[] default-inserts 0
+                T.track_val[cid] = T.track_val[cid] < T.track_val[ti] ? T.track_val[ti] : T.track_val[cid];
+            }
+        }
+    }
+    if (bad_model) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_FORMAT; res.n_cand = 0; P.out[r] = res; return; }
+    // ---- :807-837 log-odds and sums in taxid_lst order
+    bool fndPhiX = false;
+    float log_sum = 0.0f, pos_log_sum = 0.0f, top_score = 0.0f, phiXscore = 0.0f;
+    unsigned sig_hits = 0, pos_sig_hits = 0;
+    for (int f = 0; f < C; f++) {
+        float lo = T.score[f];
+        if (useRandMod) {
+            const float random_prob = T.track_val[T.cls[f]];
+            const float denom = random_prob <= 0 ? 0.00001f : random_prob;      // :687
+            lo = km_logf(__fdiv_rn(lo, denom));                                 // :688
+            T.score[f] = lo;
+        }
+        log_sum = __fadd_rn(log_sum, lo);
+        sig_hits++;
+        if (lo > 0) { pos_sig_hits++; pos_log_sum = __fadd_rn(pos_log_sum, lo); }
+        if (X.opt.phix_screen && (T.flags[f] & 2)) { phiXscore = lo; fndPhiX = true; }
+        if (f == 0 || lo > top_score) top_score = lo;
+    }
+    if (X.opt.phix_screen && phiXscore >= top_score && fndPhiX) {              // :841-848
+        res.status = KMAT_ST_PHIX; res.match = KMAT_DIRECT; res.tid = 32630u; res.score = phiXscore; res.n_cand = 0;
+        P.out[r] = res;
+        return;
+    }
+    float log_avg; unsigned use_sig_hits;
+    const unsigned min_pos_examples = 3;
+    if (pos_sig_hits > min_pos_examples) { use_sig_hits = pos_sig_hits; log_avg = __fdiv_rn(pos_log_sum, (float)pos_sig_hits); }
+    else { use_sig_hits = sig_hits; log_avg = sig_hits > 0 ? __fdiv_rn(log_sum, (float)sig_hits) : 0.0f; }
+    float log_std = 0.0f;
+    for (int f = 0; f < C; f++) {                                              // :865-880
+        const float sc = T.score[f];
+        if (sc > 0 && pos_sig_hits > min_pos_examples) { const float v = __fsub_rn(log_avg, sc); log_std = __fadd_rn(log_std, __fmul_rn(v, v)); }
+        if (pos_sig_hits <= min_pos_examples) { const float v = __fsub_rn(log_avg, sc); log_std = __fadd_rn(log_std, __fmul_rn(v, v)); }
+    }
+    const float stdev1 = use_sig_hits > 1 ? __fsqrt_rn(__fdiv_rn(log_std, (float)(use_sig_hits - 1))) : 0.0f;   // :881
+    res.status = KMAT_ST_LABELED; res.log_avg = log_avg; res.stdev = stdev1;
+    // rank_label = (tid, score [+ hbias*stdev for human tids]) in taxid_lst order, then sort(TCmp)   :882-893
+    for (int f = 0; f < C; f++) {
+        float sc = T.score[f];
+        if (hasHuman && (T.flags[f] & 1)) sc = __fadd_rn(sc, __fmul_rn(X.opt.hbias, stdev1));
+        T.rl[f].score = sc; T.rl[f].idx = (uint32_t)f;
+    }
+    kmstd::sort(T.rl, C, KsTCmp{T.depth});
+    const float diff_thresh = __fmul_rn(stdev1, X.opt.sdiff);                  // :895
+    // ---- findReadLabelVer2 (:284-419)
+    int nlin = 0;
+    bool plasmidTopHit = false; int savePlasmid = -1;
+    unsigned lowest_depth = 0, highest_depth = 0;
+    int lowest = -1, highest = -1; float lowest_score = 0;
+    int lidx = -1; bool linDone = false, lin_overflow = false;
+    for (int i = C - 1; i >= 0; --i) {                                          // :295-325
+        const int ci = (int)T.rl[i].idx; const float sc = T.rl[i].score;
+        const unsigned cdepth = T.depth[ci];
+        if (sc >= top_score && (T.flags[ci] & 4)) { plasmidTopHit = true; savePlasmid = ci; }
+        bool added = false;
+        if (!linDone) {                                                         // addToCandLineage :225-262
+            bool addNode = true;
+            for (int q = 0; q < nlin; q++) {
+                const unsigned chk = T.l_depth[q];
+                if (chk > cdepth && !kb_is_anc(T.tin[ci], T.tout[ci], T.l_tin[q])) { addNode = false; break; }
+                else if (chk < cdepth && !kb_is_anc(T.l_tin[q], T.l_tout[q], T.tin[ci])) { addNode = false; break; }
+                else if (chk == cdepth) { addNode = false; break; }
+            }
+            if (addNode) {
+                if (nlin >= KB_LIN) lin_overflow = true;
+                else {
+                    T.l_tid[nlin] = T.tid[ci]; T.l_tin[nlin] = T.tin[ci]; T.l_tout[nlin] = T.tout[ci]; T.l_score[nlin] = sc;
+                    T.l_depth[nlin] = (uint16_t)cdepth; T.l_nogood[nlin] = 0; nlin++;
+                }
+                added = true;
+            }
+        }
+        if (!linDone && !added) { lidx = i; linDone = true; }
+        else if (!linDone) {
+            if (cdepth > lowest_depth || i == C - 1) { lowest = ci; lowest_score = sc; lowest_depth = cdepth; }
+            if (cdepth < highest_depth || i == C - 1) { highest = ci; highest_depth = cdepth; }
+        }
+        if (linDone && sc < top_score) break;
+    }
+    const int add_lo = nlin; int add_hi = nlin;                                 // add_set = lineage entries [add_lo, add_hi)
+    if (highest_depth != 0 && highest >= 0) {                                   // :327-343
+        const KmNodeB hb = kb_nodeB(X, T.nid[highest]);
+        for (uint32_t q = 0; q < hb.path_len; q++) {
+            const uint32_t a = X.paths[hb.path_off + q];
+            if (nlin >= KB_LIN) { lin_overflow = true; break; }
+            int fc = -1;
+            for (int c2 = 0; c2 < C; c2++) if (T.nid[c2] == a) { fc = c2; break; }
+            if (fc >= 0) {                                                      // all_cand_set holds the un-biased score
+                T.l_tid[nlin] = T.tid[fc]; T.l_tin[nlin] = T.tin[fc]; T.l_tout[nlin] = T.tout[fc]; T.l_score[nlin] = T.score[fc];
+                T.l_depth[nlin] = T.depth[fc];
+            } else {
+                const KmNodeA na = kb_nodeA(X, a); const KmNodeB nb = kb_nodeB(X, a);
+                T.l_tid[nlin] = na.tid; T.l_tin[nlin] = nb.tin; T.l_tout[nlin] = nb.tout; T.l_score[nlin] = -10000.0f;
+                T.l_depth[nlin] = (uint16_t)(na.meta & KM_META_DEPTH_MASK);
+            }
+            T.l_nogood[nlin] = 0; nlin++;
+        }
+        add_hi = nlin;
+    }
+    if (lin_overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; res.n_cand = 0; P.out[r] = res; return; }
+    for (int q = 0; q < nlin; q++) T.l_perm[q] = (uint8_t)q;
+    kmstd::sort(T.l_perm, nlin, KsLinDepthDesc{T.l_depth});                     // cand_lin_vec sorted by depth desc :350-351
+    bool any_nogood = false;
+    for (int i = lidx; i >= 0; --i) {                                           // :355-362
+        const int ci = (int)T.rl[i].idx; const float sc = T.rl[i].score;
+        bool in_add = false;
+        for (int q = add_lo; q < add_hi && !in_add; q++) in_add = T.l_tid[q] == T.tid[ci];
+        if (in_add) continue;
+        bool keep_going = true;                                                 // cmpCompLineage :264-282
+        for (int z = 0; z < nlin; z++) {
+            const int q = T.l_perm[z];
+            if (kb_is_anc(T.l_tin[q], T.l_tout[q], T.tin[ci])) break;
+            const float dlt = __fsub_rn(T.l_score[q], sc);
+            if (T.l_score[q] != -10000.0f && dlt > diff_thresh) { keep_going = false; break; }
+            if (dlt <= diff_thresh) { T.l_nogood[q] = 1; any_nogood = true; }
+        }
+        if (!keep_going) break;
+    }
+    uint32_t call_tid = 0; float call_score = 0; int match = KMAT_NOMATCH;
+    uint32_t call_tin = 0, call_tout = 0; bool call_has_node = false;
+    if (nlin == 0 && !any_nogood) match = KMAT_NOMATCH;
+    else if (nlin != 0 && !any_nogood) {                                        // :366-368
+        call_tid = T.tid[lowest]; call_score = lowest_score; match = KMAT_DIRECT;
+        call_tin = T.tin[lowest]; call_tout = T.tout[lowest]; call_has_node = true;
+    } else {                                                                    // :369-409
+        float max_val = -10000.0f; int root = -1;
+        for (int z = 0; z < nlin; z++) {
+            const int q = T.l_perm[z];
+            max_val = T.l_score[q] < max_val ? max_val : T.l_score[q];         // std::max(cand, max_val)
+            bool ng = false;                                                    // no_good is a set of taxids
+            for (int y = 0; y < nlin && !ng; y++) ng = T.l_nogood[y] && T.l_tid[y] == T.l_tid[q];
+            if (!ng) { root = q; break; }
+        }
+        if (root < 0) { call_tid = 0; call_score = -1.0f; match = KMAT_LCA_ERROR; }
+        else {
+            match = KMAT_MULTI;
+            bool in_all = false;
+            for (int c2 = 0; c2 < C && !in_all; c2++) in_all = T.tid[c2] == T.l_tid[root];
+            if (in_all && max_val < T.l_score[root]) { match = KMAT_PARTIAL; max_val = T.l_score[root]; }   // :400-406 (unreachable in practice)
+            call_tid = T.l_tid[root]; call_score = max_val; call_tin = T.l_tin[root]; call_tout = T.l_tout[root]; call_has_node = true;
+        }
+    }
+    if (plasmidTopHit && call_has_node && kb_is_anc(call_tin, call_tout, T.tin[savePlasmid])) call_tid = T.tid[savePlasmid];   // :410-416
+    res.match = match;
+    if (match == KMAT_DIRECT || match == KMAT_MULTI || match == KMAT_PARTIAL) { res.tid = call_tid; res.score = call_score; }
+    else { res.tid = 0; res.score = 0; }                                        // best_guess stays (0,0), :839
+    // ---- outputs: sorted rank_label overwrites the (nid, hits) hand-over in place; lineage on request
+    if (P.cands && co + C <= P.cand_cap) for (int i = 0; i < C; i++) P.cands[co + i] = kmat_pair{T.tid[T.rl[i].idx], T.rl[i].score};
+    if (X.opt.want_lineage) {
+        res.n_lin = (uint32_t)nlin;
+        const unsigned long long lo2 = atomicAdd(P.lin_cursor, (unsigned long long)nlin);
+        res.lin_off = lo2;
+        if (P.lin && lo2 + nlin <= P.lin_cap) for (int q = 0; q < nlin; q++) P.lin[lo2 + q] = kmat_pair{T.l_tid[q], T.l_score[q]};
+    }
+    P.out[r] = res;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -734,9 +775,9 @@ struct kmat_ctx {
     char *h_bases = nullptr; uint64_t hcap_bases = 0;
     uint64_t *h_offs = nullptr; uint32_t hcap_reads = 0;
     kmat_read_result *h_out = nullptr;
-    int score_grid = 0;
+    int score_grid = 0;          // grid of the candidate kernel (persistent, warp per read)
     size_t score_smem = 0;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // around the probe and the scoring kernel of the last batch
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around the three kernels of the last batch
 };
 
 template <typename T>
@@ -763,13 +804,13 @@ extern "C" int kmat_ctx_create(const kmat_db *db, const kmat_inputs *in, const k
     UP(d_model_of_cand, model_of_cand); UP(d_mrow, mrow); UP(d_cut, cut); UP(d_cls, cls);
 #undef UP
     KM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 3; i++) KM_CUDA(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 4; i++) KM_CUDA(cudaEventCreate(&c->ev[i]));
     KM_CUDA(cudaMalloc((void **)&c->d_cursors, 16));
     KM_CUDA(cudaMalloc((void **)&c->d_stats, sizeof(KmStatsDev)));
     c->score_smem = sizeof(KmWarpB) * KB_WARPS;
-    KM_CUDA(cudaFuncSetAttribute(km_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->score_smem));
+    KM_CUDA(cudaFuncSetAttribute(km_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->score_smem));
     int per_sm = 0;
-    KM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_score_kernel, KB_WARPS * 32, c->score_smem));
+    KM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_cand_kernel, KB_WARPS * 32, c->score_smem));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     c->score_grid = std::max(1, per_sm) * sms;
@@ -794,7 +835,7 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
     cudaFree(c->d_cands); cudaFree(c->d_lin); cudaFree(c->d_cursors); cudaFree(c->d_big); cudaFree(c->d_long_sets); cudaFree(c->d_stats);
     cudaFreeHost(c->h_bases); cudaFreeHost(c->h_offs); cudaFreeHost(c->h_out);
     if (c->stream) cudaStreamDestroy(c->stream);
-    for (int i = 0; i < 3; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
 }
 
@@ -867,7 +908,11 @@ static int km_run_device(kmat_ctx *c, const char *d_bases, const uint64_t *d_off
     P.lin = c->d_lin; P.lin_cursor = c->d_cursors + 1; P.lin_cap = c->cap_lin;
     P.big_scratch = c->d_big; P.stats = c->collect_stats ? c->d_stats : nullptr;
     const int grid = std::max(1, std::min<int>(c->score_grid, (int)((n_reads + KB_WARPS - 1) / KB_WARPS)));
-    km_score_kernel<<<grid, KB_WARPS * 32, c->score_smem, st>>>(P);
+    km_cand_kernel<<<grid, KB_WARPS * 32, c->score_smem, st>>>(P);
+    g_km_launches++;
+    KM_CUDA(cudaGetLastError());
+    KM_CUDA(cudaEventRecord(c->ev[3], st));
+    km_score_kernel<<<(n_reads + KS_THREADS - 1) / KS_THREADS, KS_THREADS, 0, st>>>(P);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     KM_CUDA(cudaEventRecord(c->ev[2], st));
@@ -885,15 +930,17 @@ extern "C" int kmat_label_batch_device(kmat_ctx *c, const char *d_bases, const u
     if (!d_out) d_out = c->d_out;
     return km_run_device(c, d_bases, d_offs, n_reads, total_bases, max_read_len, d_out, st);
 }
-extern "C" int kmat_ctx_last_kernel_ms(kmat_ctx *c, float *probe_ms, float *score_ms) {
+extern "C" int kmat_ctx_last_kernel_ms(kmat_ctx *c, float *probe_ms, float *cand_ms, float *score_ms) {
     if (!c) return KMAT_ERR_ARG;
     KM_CUDA(cudaSetDevice(c->device));
     KM_CUDA(cudaEventSynchronize(c->ev[2]));
-    float a = 0, b = 0;
+    float a = 0, b = 0, d = 0;
     KM_CUDA(cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
-    KM_CUDA(cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
+    KM_CUDA(cudaEventElapsedTime(&b, c->ev[1], c->ev[3]));
+    KM_CUDA(cudaEventElapsedTime(&d, c->ev[3], c->ev[2]));
     if (probe_ms) *probe_ms = a;
-    if (score_ms) *score_ms = b;
+    if (cand_ms) *cand_ms = b;
+    if (score_ms) *score_ms = d;
     return KMAT_OK;
 }
 extern "C" int kmat_ctx_set_stats(kmat_ctx *c, int enable) {
