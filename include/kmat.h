@@ -193,6 +193,31 @@ uint64_t kmat_launch_count(void);
 int kmat_format_tail(const kmat_read_result *, const kmat_pair *cands, const kmat_pair *lineage, int prn_all,
                      char *buf, size_t cap);
 
+/* ---- read ingest (host) -------------------------------------------------------------------------
+ * Replaces the single-producer FASTA/FASTQ parser of read_label main() (read_label.cpp:1651-1713) and the
+ * header substitution of :1728-1732, quirks included: FASTA lines of length <= 1 are ignored and wrapped lines
+ * are joined; a read is emitted when the next '>' line (or EOF) arrives; with fastq != 0 the '+'/'-' line
+ * emits the read paired with the PREVIOUS record's header and the quality line is skipped; an empty header
+ * becomes "unknown_hdr:<n>", n = 1-based ordinal of the read.  path "-" = stdin. */
+typedef struct kmat_reader kmat_reader;
+typedef struct kmat_read_batch kmat_read_batch;   /* one batch of reads: owned buffers, reusable */
+int kmat_reader_open(const char *path, int fastq, kmat_reader **out);
+void kmat_reader_close(kmat_reader *);
+kmat_read_batch *kmat_read_batch_new(void);
+void kmat_read_batch_free(kmat_read_batch *);
+/* Fill `b` with up to max_reads reads / about max_bases bases (at least one read).  Returns the number of
+ * reads (0 = end of input) or a negative KMAT_ERR_*. */
+int64_t kmat_reader_next(kmat_reader *, uint32_t max_reads, uint64_t max_bases, kmat_read_batch *b);
+/* Borrowed views, valid until the batch is refilled or freed: bases/offs[n+1] as kmat_label_batch takes
+ * them, hdrs/hdr_offs[n+1] the headers, first_ordinal the 1-based ordinal of read 0. */
+int kmat_read_batch_view(const kmat_read_batch *, const char **bases, const uint64_t **offs, const char **hdrs,
+                         const uint64_t **hdr_offs, uint32_t *n_reads, uint64_t *first_ordinal);
+
+/* Per-read tally of proc_line (read_label.cpp:1241-1277): which counter a finished read increments.
+ * Returns 0 = counted for (tid, score) [track_taxids / track_tscores], 1 = ReadTooShort, 2 = NoDbHits,
+ * 3 = LowScore, -1 = nothing (NaN score). */
+int kmat_tally_class(const kmat_read_result *, float min_score, int32_t min_kmer);
+
 /* Random-access HBM roofline probe: uniform random `access_bytes`-wide loads
  * (8, 16 or 32) over a `span_bytes` device allocation; returns achieved gathers/s. */
 int kmat_gather_bench(int device, uint64_t span_bytes, int access_bytes, uint64_t n_gathers, int iters,

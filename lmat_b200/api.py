@@ -48,7 +48,8 @@ EXPORTS = [
     "kmat_lookup_batch", "kmat_encode_batch", "kmat_inputs_load", "kmat_inputs_free", "kmat_opts_default",
     "kmat_ctx_create", "kmat_ctx_set_opts", "kmat_ctx_destroy", "kmat_label_batch", "kmat_label_batch_device",
     "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench",
-    "kmat_set_l2_fetch_granularity",
+    "kmat_set_l2_fetch_granularity", "kmat_reader_open", "kmat_reader_close", "kmat_read_batch_new", "kmat_read_batch_free",
+    "kmat_reader_next", "kmat_read_batch_view", "kmat_tally_class",
 ]
 
 _lib = None
@@ -103,6 +104,14 @@ def lib():
     L.kmat_format_tail.argtypes = [vp, vp, vp, C.c_int, C.c_char_p, C.c_size_t]
     L.kmat_gather_bench.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.kmat_set_l2_fetch_granularity.argtypes = [C.c_int, C.c_int]
+    L.kmat_reader_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.kmat_reader_close.argtypes = [vp]
+    L.kmat_read_batch_new.restype = vp
+    L.kmat_read_batch_free.argtypes = [vp]
+    L.kmat_reader_next.restype = C.c_int64
+    L.kmat_reader_next.argtypes = [vp, C.c_uint32, C.c_uint64, vp]
+    L.kmat_read_batch_view.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+    L.kmat_tally_class.argtypes = [vp, C.c_float, C.c_int32]
     _lib = L
     return L
 
@@ -344,3 +353,31 @@ def gather_bench(device=0, span_bytes=1 << 30, access_bytes=8, n_gathers=1 << 28
     g, s = C.c_double(), C.c_double()
     _check(lib().kmat_gather_bench(device, span_bytes, access_bytes, n_gathers, iters, C.byref(g), C.byref(s)))
     return g.value, s.value
+
+
+def read_file(path, fastq=False, max_reads=1 << 20, max_bases=1 << 28):
+    """(headers, reads) through kmat_reader_* -- the host parser that replaces read_label.cpp:1651-1732."""
+    L = lib()
+    r, hdrs, seqs = C.c_void_p(), [], []
+    _check(L.kmat_reader_open(_b(path), int(fastq), C.byref(r)))
+    b = C.c_void_p(L.kmat_read_batch_new())
+    try:
+        while True:
+            n = L.kmat_reader_next(r, max_reads, max_bases, b)
+            _check(n)
+            if n == 0:
+                break
+            bp, op_, hp, hop = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+            nn, first = C.c_uint32(), C.c_uint64()
+            _check(L.kmat_read_batch_view(b, C.byref(bp), C.byref(op_), C.byref(hp), C.byref(hop), C.byref(nn), C.byref(first)))
+            offs = np.ctypeslib.as_array(C.cast(op_, C.POINTER(C.c_uint64)), shape=(n + 1,))
+            hoffs = np.ctypeslib.as_array(C.cast(hop, C.POINTER(C.c_uint64)), shape=(n + 1,))
+            bases = C.string_at(bp, int(offs[n]))
+            hd = C.string_at(hp, int(hoffs[n]))
+            for i in range(n):
+                seqs.append(bases[int(offs[i]):int(offs[i + 1])].decode("latin-1"))
+                hdrs.append(hd[int(hoffs[i]):int(hoffs[i + 1])].decode("latin-1"))
+    finally:
+        L.kmat_read_batch_free(b)
+        L.kmat_reader_close(r)
+    return hdrs, seqs

@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libkmat.so")
 BIN = os.path.join(HERE, "bin", "read_label")
 
 CUDA_SRCS = ["kmat_db.cu", "kmat_label.cu"]
-HOST_SRCS = ["kmat_host.cpp"]
+HOST_SRCS = ["kmat_host.cpp", "kmat_reader.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

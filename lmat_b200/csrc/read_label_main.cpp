@@ -1,0 +1,421 @@
+// read_label -- drop-in host for LMAT's read_label (src/read_label.cpp main(), :1328-1871) over libkmat's C ABI.
+//
+// Same getopt string, same required options, same <ofbase><i>.out / .fastsummary / .nomatchsum outputs and the
+// same stdout milestones ("Total query time").  The per-read work (proc_line, :1211-1279) runs on the GPUs:
+//   reader thread  : kmat_reader_next -> batches of reads                       (replaces the thread-0 parser, :1651-1713)
+//   device workers : one per GPU, kmat_label_batch on its replica (or shard set) (replaces the OpenMP proc_line loop)
+//   writer threads : one per -t "thread": batch i goes to file i mod t, in input order, so -t 1 reproduces the
+//                    reference's single-thread output byte for byte and any -t gives the same multiset of lines;
+//                    each writer keeps the reference's per-thread tallies (float sums in file order), merged in
+//                    thread order like :1760-1800.
+// Environment: KMAT_DEVICES="0,2,.." (default: every visible GPU), KMAT_BATCH_READS (default 262144),
+// KMAT_TID_BYTES (2|4: sizeof(DBTID_T) of the DB, default 2), LMAT_DIR as in the reference (:555-560).
+#include <getopt.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <mutex>
+#include <set>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "kmat.h"
+
+#ifndef KMAT_LMAT_VERSION
+#define KMAT_LMAT_VERSION "1.2.4_2018a"     /* include/version.h:1 of the reference this build tracks */
+#endif
+
+namespace {
+
+struct Batch {
+    uint64_t seq = 0;
+    kmat_read_batch *rb = nullptr;
+    std::vector<kmat_read_result> res;
+    std::vector<kmat_pair> cands, lin;
+    int rc = 0;
+    std::string err;
+};
+
+template <typename T>
+class Channel {            // bounded FIFO; close() wakes everybody
+  public:
+    explicit Channel(size_t cap) : cap_(cap) {}
+    bool push(T v) {
+        std::unique_lock<std::mutex> l(m_);
+        cv_space_.wait(l, [&] { return q_.size() < cap_ || closed_; });
+        if (closed_) return false;
+        q_.push_back(std::move(v));
+        cv_item_.notify_one();
+        return true;
+    }
+    bool pop(T &out) {
+        std::unique_lock<std::mutex> l(m_);
+        cv_item_.wait(l, [&] { return !q_.empty() || closed_; });
+        if (q_.empty()) return false;
+        out = std::move(q_.front());
+        q_.erase(q_.begin());
+        cv_space_.notify_one();
+        return true;
+    }
+    void close() { std::lock_guard<std::mutex> l(m_); closed_ = true; cv_item_.notify_all(); cv_space_.notify_all(); }
+  private:
+    std::mutex m_;
+    std::condition_variable cv_item_, cv_space_;
+    std::vector<T> q_;
+    size_t cap_;
+    bool closed_ = false;
+};
+
+// Per output "thread": batches arrive in any order (several GPUs), are written in seq order.
+struct Writer {
+    std::mutex m;
+    std::condition_variable cv;
+    std::map<uint64_t, Batch *> ready;
+    uint64_t next_seq = 0;       // first seq this writer expects (index, then += n_writers)
+    bool done = false;
+    std::map<uint32_t, int> track_match;          // read_label.cpp:1606-1608
+    std::map<uint32_t, float> track_tscore;
+    std::map<int, int> track_nomatch;             // 1 ReadTooShort, 2 NoDbHits, 3 LowScore
+};
+
+void usage(const char *exe) {
+    std::cout << "==============================================\n"
+                 "  kmat read_label -- B200-native drop-in for\n"
+                 "  the Livermore Metagenomics Analysis Toolkit\n"
+                 "==============================================\n\n"
+                 "Taxonomic classification module usage:\n"
+              << exe << " -d <input db file> -i <query fasta file | -> -t <number of output threads>\n"
+                 "-o <output path> -e <depth file> -c <tax tree file> [-f <32-to-16-bit id map>] [-w <rank map>]\n"
+                 "[-u <rank/name table>] [-n <null model list>] [-m <numeric rank file>] [-g <tid-cutoff>]\n"
+                 "[-r <low-number plasmid list>] [-x <min score>] [-j <min valid k-mers>] [-z <min found k-mers>]\n"
+                 "[-b <sdiff>] [-l <human bias>] [-k <kmer size>] [-v <pct cutoff>] [-q:fastq] [-p:print all candidates]\n"
+                 "[-a:hide read] [-s:permissive] [-h:turn phiX screening off] [-y:verbose]\n"
+                 "[-V:print version and exit] [-H:print this usage help and exit]\n";
+}
+
+std::string fmt_g(float v) {                 // ostream << float at default precision == "%g"
+    char b[64];
+    snprintf(b, sizeof b, "%g", (double)v);
+    return b;
+}
+
+struct SimpleCmpDesc {                        // SimpleCmp, read_label.cpp:153-157
+    bool operator()(const std::pair<uint32_t, float> &a, const std::pair<uint32_t, float> &b) const { return a.second > b.second; }
+};
+
+}  // namespace
+
+int main(int argc, char *argv[]) {
+    int k_size = -1, n_threads = 0;
+    float min_score = 0.0f;
+    std::string rank_map_file, rank_ids, kmer_db_fn, query_fn, ofbase, tax_tree_fn, depth_file, rand_hits_file, rank_table_file,
+        id_bit_conv_fn, low_num_plasmid_file;
+    bool fastq = false, prn_read = true, prn_all = false, verbose = false;
+    kmat_opts opt;
+    kmat_opts_default(&opt);
+    int c;
+    while ((c = getopt(argc, argv, "u:ahn:j:b:ye:w:pk:c:v:k:i:d:l:t:r:sm:o:x:f:g:z:qVH")) != -1) {     // :1351
+        switch (c) {
+            case 'h': opt.phix_screen = 0; break;
+            case 'r': low_num_plasmid_file = optarg; break;
+            case 'f': id_bit_conv_fn = optarg; break;
+            case 'j': opt.min_kmer = atoi(optarg); break;
+            case 'z': opt.min_fnd_kmer = atoi(optarg); break;
+            case 'u': rank_ids = optarg; break;
+            case 'x': min_score = (float)atof(optarg); break;
+            case 'a': prn_read = false; break;
+            case 'w': rank_map_file = optarg; break;
+            case 's': opt.permissive = 1; break;
+            case 'n': rand_hits_file = optarg; break;
+            case 'b': opt.sdiff = (float)atof(optarg); break;
+            case 'l': opt.hbias = (float)atof(optarg); break;
+            case 'y': verbose = true; break;
+            case 'e': depth_file = optarg; break;
+            case 'q': fastq = true; break;
+            case 'p': prn_all = true; break;
+            case 'm': rank_table_file = optarg; break;
+            case 't': n_threads = atoi(optarg); break;
+            case 'v': break;                                   // threshold: parsed and never used by the reference (:1336,1409)
+            case 'c': tax_tree_fn = optarg; break;
+            case 'k': k_size = atoi(optarg); break;
+            case 'g': opt.max_count = (int32_t)(uint16_t)atoi(optarg); break;      // uint16_t max_count (:1346,1422)
+            case 'i': query_fn = optarg; break;
+            case 'd': kmer_db_fn = optarg; break;
+            case 'o': ofbase = optarg; break;
+            case 'V': std::cout << "LMAT version " << KMAT_LMAT_VERSION << " (kmat B200 host, ABI " << kmat_abi_version() << ")" << std::endl; return 0;
+            case 'H': usage(argv[0]); return 0;
+            default: std::cerr << "WARNING! Unrecognized option " << (char)c << " to ignore." << std::endl;
+        }
+    }
+    if (depth_file.empty()) std::cerr << "ERROR! Missing depth_file" << std::endl;
+    if (ofbase.empty()) std::cerr << "ERROR! Missing ofbase" << std::endl;
+    if (n_threads == 0) std::cerr << "ERROR! Missing n_threads" << std::endl;
+    if (kmer_db_fn.empty()) std::cerr << "ERROR! Missing kmer_db_fn" << std::endl;
+    if (query_fn.empty()) std::cerr << "ERROR! Missing query_fn" << std::endl;
+    if (depth_file.empty() || ofbase.empty() || n_threads <= 0 || kmer_db_fn.empty() || query_fn.empty()) {
+        std::cerr << "Params: " << ofbase << " " << n_threads << " " << kmer_db_fn << " " << query_fn << " " << depth_file << std::endl;
+        usage(argv[0]);
+        return -1;
+    }
+    opt.min_score = min_score;
+    opt.want_lineage = prn_all ? 0 : 1;
+    if (verbose) std::cerr << "WARNING! -y (per-k-mer debug traces) is not produced by the GPU path; ignored." << std::endl;
+
+    std::cout << "=== LMAT === read_label === ver. " << KMAT_LMAT_VERSION << " === kmat/B200 ===" << std::endl;
+    std::cout << "Start kmer DB load..." << std::endl;
+    const char *tb = getenv("KMAT_TID_BYTES");
+    const int tid_bytes = tb ? atoi(tb) : 2;
+    kmat_table *table = nullptr;
+    if (kmat_table_open(kmer_db_fn.c_str(), tid_bytes, &table) != KMAT_OK) {
+        std::cerr << "Error: unable to open kmer db [" << kmer_db_fn << "]: " << kmat_last_error() << std::endl;
+        return -1;
+    }
+    const int db_k = kmat_table_kmer_length(table);
+    if (k_size < 1) k_size = db_k;
+    if (k_size != db_k) std::cerr << "WARNING! -k " << k_size << " differs from the database's k-mer length " << db_k << "; using " << db_k << std::endl;
+    std::cout << "Mapping flat table. Num of k-mers: " << kmat_table_size(table) << " of size " << db_k << std::endl;
+    if (db_k <= 0) { std::cerr << "ERROR! Unable to read database, k-mer size=" << db_k << std::endl; return -1; }
+
+    // devices
+    std::vector<int> devs;
+    if (const char *dv = getenv("KMAT_DEVICES")) {
+        std::stringstream ss(dv);
+        std::string tok;
+        while (std::getline(ss, tok, ',')) if (!tok.empty()) devs.push_back(atoi(tok.c_str()));
+    } else for (int i = 0; i < kmat_device_count(); i++) devs.push_back(i);
+    if (devs.empty()) { std::cerr << "ERROR! No CUDA device: this build has no CPU path (" << kmat_last_error() << ")" << std::endl; return -1; }
+
+    std::cout << "Reading taxonomy tree " << tax_tree_fn << std::endl;
+    std::cout << "Reading taxonomy depth " << depth_file << std::endl;
+    if (!id_bit_conv_fn.empty()) std::cout << "Loading map file " << id_bit_conv_fn << "... ";
+    kmat_inputs *inputs = nullptr;
+    const char *lmat_dir = getenv("LMAT_DIR");
+    auto nz = [](const std::string &s) { return s.empty() ? nullptr : s.c_str(); };
+    int rc = kmat_inputs_load(nz(tax_tree_fn), depth_file.c_str(), nz(rank_map_file), nz(id_bit_conv_fn), nz(rank_table_file),
+                              nz(low_num_plasmid_file), nz(rand_hits_file), lmat_dir, &inputs);
+    if (rc != KMAT_OK) { std::cerr << "ERROR! " << kmat_last_error() << std::endl; return -1; }
+    if (!id_bit_conv_fn.empty()) std::cout << "OK!" << std::endl;
+
+    const auto t_start = std::chrono::steady_clock::now();                       // StopWatch clock (:1604-1605)
+    std::vector<kmat_db *> dbs(devs.size(), nullptr);
+    std::vector<kmat_ctx *> ctxs(devs.size(), nullptr);
+    {
+        std::vector<std::thread> up;
+        std::vector<int> urc(devs.size(), 0);
+        std::vector<std::string> uerr(devs.size());
+        for (size_t d = 0; d < devs.size(); d++)
+            up.emplace_back([&, d] {
+                urc[d] = kmat_db_upload(table, devs[d], 0, 1, &dbs[d]);
+                if (urc[d] == KMAT_OK) urc[d] = kmat_ctx_create(dbs[d], inputs, &opt, &ctxs[d]);
+                if (urc[d] != KMAT_OK) uerr[d] = kmat_last_error();
+            });
+        for (auto &t : up) t.join();
+        for (size_t d = 0; d < devs.size(); d++)
+            if (urc[d] != KMAT_OK) { std::cerr << "ERROR! device " << devs[d] << ": " << uerr[d] << std::endl; return -1; }
+    }
+    kmat_table_free(table);
+    const auto t_query = std::chrono::steady_clock::now();
+
+    kmat_reader *reader = nullptr;
+    if (kmat_reader_open(query_fn.c_str(), fastq ? 1 : 0, &reader) != KMAT_OK) {
+        std::cerr << "ERROR! Did not open for reading: " << query_fn << std::endl;
+        return -1;
+    }
+    std::cout << "Classifing reads on " << devs.size() << " GPU(s), writing " << n_threads << " .out files..." << std::endl;
+
+    const char *be = getenv("KMAT_BATCH_READS");
+    const uint32_t batch_reads = be ? (uint32_t)std::max(1, atoi(be)) : 262144u;
+    const uint64_t batch_bases = (uint64_t)batch_reads * 400;
+    const size_t n_inflight = 2 * devs.size() + 2 * (size_t)n_threads + 2;
+    Channel<Batch *> free_q(n_inflight + 1), work_q(n_inflight + 1);
+    std::vector<Batch> pool(n_inflight);
+    for (auto &b : pool) { b.rb = kmat_read_batch_new(); free_q.push(&b); }
+    std::vector<Writer> writers(n_threads);
+    for (int w = 0; w < n_threads; w++) writers[w].next_seq = (uint64_t)w;
+    std::atomic<uint64_t> reads_loaded{0};
+    std::atomic<int> failed{0};
+    std::string fail_msg;
+    std::mutex fail_m;
+    auto fail = [&](const std::string &m) { std::lock_guard<std::mutex> l(fail_m); if (!failed.exchange(1)) fail_msg = m; };
+
+    std::thread reader_thr([&] {
+        uint64_t seq = 0;
+        for (;;) {
+            Batch *b;
+            if (!free_q.pop(b)) break;
+            const int64_t n = kmat_reader_next(reader, batch_reads, batch_bases, b->rb);
+            if (n < 0) { fail(kmat_last_error()); break; }
+            if (n == 0) break;
+            reads_loaded += (uint64_t)n;
+            b->seq = seq++;
+            if (!work_q.push(b)) break;
+        }
+        std::cout << "Total reads loaded: " << reads_loaded.load() << std::endl;
+        work_q.close();
+    });
+
+    auto deliver = [&](Batch *b) {
+        Writer &w = writers[b->seq % (uint64_t)n_threads];
+        std::lock_guard<std::mutex> l(w.m);
+        w.ready[b->seq] = b;
+        w.cv.notify_one();
+    };
+    std::vector<std::thread> dev_thr;
+    for (size_t d = 0; d < devs.size(); d++)
+        dev_thr.emplace_back([&, d] {
+            Batch *b;
+            while (work_q.pop(b)) {
+                const char *bases; const uint64_t *offs; uint32_t n;
+                kmat_read_batch_view(b->rb, &bases, &offs, nullptr, nullptr, &n, nullptr);
+                b->res.resize(n);
+                if (b->cands.size() < (size_t)n * 24 + 1024) b->cands.resize((size_t)n * 24 + 1024);
+                if (opt.want_lineage && b->lin.size() < (size_t)n * 24 + 1024) b->lin.resize((size_t)n * 24 + 1024);
+                uint64_t nc = 0, nl = 0;
+                for (int attempt = 0; attempt < 3; attempt++) {
+                    b->rc = kmat_label_batch(ctxs[d], bases, offs, n, b->res.data(), b->cands.data(), b->cands.size(), &nc,
+                                             opt.want_lineage ? b->lin.data() : nullptr, b->lin.size(), &nl);
+                    if (b->rc != KMAT_ERR_OVERFLOW) break;
+                    if (nc > b->cands.size()) b->cands.resize(nc + nc / 8);
+                    if (nl > b->lin.size()) b->lin.resize(nl + nl / 8);
+                }
+                if (b->rc != KMAT_OK) { b->err = kmat_last_error(); fail("device " + std::to_string(devs[d]) + ": " + b->err); }
+                deliver(b);
+            }
+        });
+
+    std::vector<std::thread> wr_thr;
+    for (int wi = 0; wi < n_threads; wi++)
+        wr_thr.emplace_back([&, wi] {
+            Writer &w = writers[wi];
+            const std::string ofname = ofbase + std::to_string(wi) + ".out";         // :1642-1647
+            FILE *ofs = fopen(ofname.c_str(), "w");
+            if (!ofs) fail("could not open for writing " + ofname);
+            std::vector<char> out;
+            char tail[1 << 16];
+            for (;;) {
+                Batch *b = nullptr;
+                {
+                    std::unique_lock<std::mutex> l(w.m);
+                    w.cv.wait(l, [&] { return w.done || w.ready.count(w.next_seq); });
+                    auto it = w.ready.find(w.next_seq);
+                    if (it == w.ready.end()) break;
+                    b = it->second;
+                    w.ready.erase(it);
+                    w.next_seq += (uint64_t)n_threads;
+                }
+                if (b->rc == KMAT_OK && ofs) {
+                    const char *bases, *hdrs; const uint64_t *offs, *hoffs; uint32_t n;
+                    kmat_read_batch_view(b->rb, &bases, &offs, &hdrs, &hoffs, &n, nullptr);
+                    out.clear();
+                    for (uint32_t i = 0; i < n; i++) {
+                        const kmat_read_result &r = b->res[i];
+                        out.insert(out.end(), hdrs + hoffs[i], hdrs + hoffs[i + 1]);             // :1733-1738
+                        out.push_back('\t');
+                        if (prn_read) out.insert(out.end(), bases + offs[i], bases + offs[i + 1]); else out.push_back('X');
+                        out.push_back('\t');
+                        if (r.status == KMAT_ST_ERROR) { fail("read " + std::string(hdrs + hoffs[i], hdrs + hoffs[i + 1]) + ": " + kmat_strerror(r.err)); continue; }
+                        int tn = kmat_format_tail(&r, b->cands.data(), b->lin.data(), prn_all ? 1 : 0, tail, sizeof tail);
+                        if (tn == KMAT_ERR_OVERFLOW) {                                           // very long candidate list
+                            std::vector<char> big(1 << 24);
+                            tn = kmat_format_tail(&r, b->cands.data(), b->lin.data(), prn_all ? 1 : 0, big.data(), big.size());
+                            if (tn >= 0) out.insert(out.end(), big.data(), big.data() + tn);
+                        } else if (tn >= 0) out.insert(out.end(), tail, tail + tn);
+                        if (tn < 0) { fail("formatting failed"); continue; }
+                        switch (kmat_tally_class(&r, min_score, opt.min_kmer)) {                 // :1217-1277
+                            case 0: {
+                                auto it = w.track_tscore.find(r.tid);
+                                if (it == w.track_tscore.end()) { w.track_match[r.tid] = 1; w.track_tscore[r.tid] = r.score; }
+                                else { w.track_match[r.tid] += 1; it->second += r.score; }
+                                break;
+                            }
+                            case 1: w.track_nomatch[1] += 1; break;
+                            case 2: w.track_nomatch[2] += 1; break;
+                            case 3: w.track_nomatch[3] += 1; break;
+                            default: break;
+                        }
+                    }
+                    if (fwrite(out.data(), 1, out.size(), ofs) != out.size()) fail("write failed: " + ofname);
+                }
+                free_q.push(b);
+            }
+            if (ofs) fclose(ofs);
+        });
+
+    reader_thr.join();
+    for (auto &t : dev_thr) t.join();
+    for (auto &w : writers) { std::lock_guard<std::mutex> l(w.m); w.done = true; w.cv.notify_all(); }
+    for (auto &t : wr_thr) t.join();
+    free_q.close();
+    kmat_reader_close(reader);
+    for (auto &b : pool) kmat_read_batch_free(b.rb);
+    if (failed.load()) { std::cerr << "ERROR! " << fail_msg << std::endl; return -1; }
+
+    std::cout << "Finished classifing reads, doing final steps sequentially..." << std::endl;
+    // merge the per-thread tallies in thread order (:1760-1800)
+    std::map<uint32_t, int> merge_count;
+    std::map<uint32_t, float> merge_score;
+    std::map<int, int> nomatch_merge_count;
+    for (auto &w : writers) {
+        for (auto &kv : w.track_tscore) { auto it = merge_score.find(kv.first); if (it == merge_score.end()) merge_score.insert(kv); else it->second += kv.second; }
+        for (auto &kv : w.track_match) merge_count[kv.first] += kv.second;
+        for (auto &kv : w.track_nomatch) nomatch_merge_count[kv.first] += kv.second;
+    }
+    std::vector<std::pair<uint32_t, float>> sort_val(merge_score.begin(), merge_score.end());
+    std::set<uint32_t> cand_tid;
+    for (auto &p : sort_val) cand_tid.insert(p.first);
+    std::map<uint32_t, std::string> save_id;                                      // names from -u (:1812-1835)
+    if (!rank_ids.empty()) {
+        std::ifstream tax_strm(rank_ids.c_str());
+        std::string proc;
+        while (std::getline(tax_strm, proc)) {
+            std::vector<char> buf(proc.begin(), proc.end());
+            buf.push_back('\0');
+            char *save = nullptr;
+            for (char *val = strtok_r(buf.data(), "=,", &save); val; val = strtok_r(nullptr, "=,", &save)) {
+                if (strcmp(val, "taxid") == 0) {
+                    val = strtok_r(nullptr, "=,", &save);
+                    if (!val) break;
+                    const uint32_t cid = (uint32_t)strtoul(val, nullptr, 10);
+                    if (cand_tid.count(cid)) {
+                        const size_t pos = proc.rfind('\t');
+                        save_id.insert(std::make_pair(cid, pos == std::string::npos ? proc : proc.substr(pos + 1)));
+                    }
+                    break;
+                }
+            }
+        }
+    }
+    const std::string base = ofbase + "." + fmt_g(min_score) + "." + std::to_string(opt.min_kmer);
+    {
+        std::ofstream sum_ofs((base + ".fastsummary").c_str());
+        if (!sum_ofs) { std::cerr << "ERROR! Could not open for writing " << base << ".fastsummary" << std::endl; return -1; }
+        std::cout << "Writing FastSummary file in " << base << ".fastsummary" << std::endl;
+        std::sort(sort_val.begin(), sort_val.end(), SimpleCmpDesc());                   // :1844
+        for (auto &p : sort_val) sum_ofs << p.second << "\t" << merge_count[p.first] << "\t" << p.first << "\t" << save_id[p.first] << std::endl;
+    }
+    {
+        std::ofstream nom_ofs((base + ".nomatchsum").c_str());
+        if (!nom_ofs) { std::cerr << "ERROR! Could not open for writing " << base << ".nomatchsum" << std::endl; return -1; }
+        std::cout << "Writing NoMatchSum file in " << base << ".nomatchsum" << std::endl;
+        static const char *names[] = {"Error", "ReadTooShort", "NoDbHits", "LowScore"};
+        for (auto &kv : nomatch_merge_count) nom_ofs << names[kv.first] << "\t" << kv.second << std::endl;
+    }
+    for (size_t d = 0; d < devs.size(); d++) { kmat_ctx_destroy(ctxs[d]); kmat_db_free(dbs[d]); }
+    kmat_inputs_free(inputs);
+    const auto t_end = std::chrono::steady_clock::now();
+    const double q = std::chrono::duration<double>(t_end - t_query).count(), up = std::chrono::duration<double>(t_query - t_start).count();
+    std::cout << "Table upload time: " << up << " sec (" << devs.size() << " device(s))" << std::endl;
+    std::cout << "DONE! Total query time: " << q << " sec = " << q / 60 << " min" << std::endl;
+    return 0;
+}

@@ -1,0 +1,56 @@
+"""CPU: the C host parser (kmat_reader_*, replaces read_label.cpp:1651-1732) against the oracle's reader
+restatement, which tests/test_oracle_golden.py pins to the reference's own outputs for FASTA, wrapped FASTA
+and FASTQ (the previous-record-header quirk included)."""
+import os
+
+import pytest
+
+from lmat_b200 import api
+from oracle import oracle_py as op
+
+
+@pytest.mark.parametrize("key,fastq", [("reads", False), ("reads_wrapped", False), ("reads_fq", True)])
+@pytest.mark.parametrize("max_reads", [1, 7, 1 << 20])
+def test_reader_matches_oracle_reader(golden_small, key, fastq, max_reads):
+    path = golden_small.paths[key]
+    want = op.read_fasta_like_reference(path, fastq=fastq)
+    got = api.read_file(path, fastq=fastq, max_reads=max_reads)
+    assert got[0] == want[0] and got[1] == want[1]
+
+
+CASES = {
+    "empty": b"",
+    "no_trailing_newline": b">a\nACGTACGT\n>b\nGGGG",
+    "blank_and_single_char_lines": b">a\nACGT\n\nA\nTTTT\n>b\n\n>c\nCC\n",
+    "no_header": b"ACGTACGTAC\nGGGT\n>x\nAAAA\n",
+    "crlf": b">a\r\nACGT\r\n>b\r\nGG\r\n",
+    "empty_header": b">\nACGT\n>\nGGCC\n",
+    "fasta_read_as_fastq": b">h1\nACGT\n>h2\nGGGG\n",
+    "fastq_multi": b"@r1\nACGT\n+\nIIII\n@r2\nGGCC\nTT\n-r2\nIIIIII\n@r3\nAA\n+\nII",
+    "fastq_no_quality_at_end": b"@r1\nACGT\n+\n",
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("fastq", [False, True])
+def test_reader_edge_cases(tmp_path, name, fastq):
+    p = os.path.join(tmp_path, name + ".txt")
+    open(p, "wb").write(CASES[name])
+    want = op.read_fasta_like_reference(p, fastq=fastq)
+    for mr in (1, 3, 1000):
+        got = api.read_file(p, fastq=fastq, max_reads=mr)
+        assert got[0] == want[0] and got[1] == want[1], (name, fastq, mr)
+
+
+def test_reader_long_line_and_chunk_boundaries(tmp_path):
+    # one 40 MB sequence line (larger than the reader's chunk) between normal records
+    p = os.path.join(tmp_path, "big.fa")
+    with open(p, "wb") as f:
+        f.write(b">a\nACGT\n>big\n" + b"ACGT" * (10 << 20) + b"\n>c\nGG\nTT\n")
+    hdrs, seqs = api.read_file(p, max_reads=2)
+    assert hdrs == ["a", "big", "c"] and [len(s) for s in seqs] == [4, 40 << 20, 4] and seqs[2] == "GGTT"
+
+
+def test_reader_missing_file():
+    with pytest.raises(api.KmatError):
+        api.read_file("/nonexistent/reads.fa")
