@@ -15,12 +15,9 @@
 #include "kmat_std_emul.cuh"
 
 #define KB_WARPS 8         // warps per CTA of the candidate kernel
-#define KB_PMAX 320        // k-mer positions per read handled by the shared-memory path
-#define KB_CMAX 64         // candidate taxids per read (one 64-bit mask)
-#define KB_HSLOTS 128
-#define KB_LFAST 16        // list length sorted in place per lane (libstdc++ uses plain insertion sort up to 16)
+#define KB_CMAX 64         // candidate taxids per read: candidate i lives in lane i & 31, register slot i >> 5
+#define KB_LFAST 16        // list length resolved in registers (libstdc++ uses plain insertion sort up to 16)
 #define KB_LIN 128         // lineage entries in findReadLabelVer2
-#define KB_BIGCAP 8192     // per-warp global scratch for longer lists / run-time pruning
 #define KS_THREADS 128     // threads per CTA of the scoring kernel (one read per thread)
 #define KMAT_ST_PENDING 7  // internal: candidates built, scoring still to run
 
@@ -30,6 +27,10 @@
 #define KB_SID_DROP 0x40000000u
 #define KB_SID_NIDMASK 0x3FFFFFFFu
 
+// resolved list record (pool2, built once per ctx by km_resolve_kernel): header word, then node ids
+#define KR_ERR_BAD 0xFFFFFFFFu    // a stored id is missing from the -f map (TaxNodeStat.hpp:235-238 asserts)
+#define KR_ERR_BIG 0xFFFFFFFEu    // deferred to the big-list pass (internal, never left behind)
+
 struct KmCtxDev {
     KmDbDev db;
     const KmNodeA *nodeA; const KmNodeB *nodeB; const uint32_t *paths; const uint32_t *prune_rank; const uint32_t *sid2nid;
@@ -38,6 +39,8 @@ struct KmCtxDev {
     const int16_t *model_of_cand; const int32_t *mrow; const float *cut; const uint8_t *cls;
     int8_t class_ranknum[64];
     kmat_opts opt;
+    const uint32_t *pool2;     // resolved lists: record of the list at pool word offset o starts at pool2[o * pool2_mul]
+    int pool2_mul;
 };
 
 struct KmScoreParams {
@@ -46,64 +49,15 @@ struct KmScoreParams {
     kmat_read_result *out;
     kmat_pair *cands; unsigned long long *cand_cursor; unsigned long long cand_cap;
     kmat_pair *lin; unsigned long long *lin_cursor; unsigned long long lin_cap;
-    uint2 *big_scratch;
+    unsigned long long *long_masks; uint32_t long_cap;    // per-warp position-mask scratch for reads longer than the register path
     KmStatsDev *stats;
 };
 
 struct KmRl { float score; uint32_t idx; };          // rank_label element: candidate index + (bias-adjusted) score
 
-struct __align__(16) KmWarpB {
-    // candidate hash: nid -> slot; h_idx[slot] = candidate id (dense, in insertion order)
-    uint32_t h_nid[KB_HSLOTS], h_seq[KB_HSLOTS], h_leaf[KB_HSLOTS];
-    uint8_t h_idx[KB_HSLOTS];
-    // candidates, indexed by candidate id.  order[f] = id of the f-th entry of the reference's taxid_lst.
-    uint32_t c_nid[KB_CMAX], c_tid[KB_CMAX], c_meta[KB_CMAX], c_spec[KB_CMAX], c_poff[KB_CMAX], c_plen[KB_CMAX];
-    uint32_t c_leaf[KB_CMAX], c_first[KB_CMAX], c_hits[KB_CMAX];
-    unsigned long long c_anc[KB_CMAX];
-    uint8_t c_qual[KB_CMAX], c_slot[KB_CMAX], order[KB_CMAX];
-    // per position: bit set of the candidate ids kept there (label_vec[pos].second before the post-pass)
-    unsigned long long posmask[KB_PMAX];
-    uint32_t lst[32][KB_LFAST];          // position loop: per-lane list scratch
-    uint16_t dep[32][KB_LFAST];
-    uint32_t n_used;
-};
-
 // ---------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t kb_hash(uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; return x & (KB_HSLOTS - 1); }
-// insert-or-find; returns slot or -1 when the table would exceed KB_CMAX distinct keys.  The inserting lane
-// assigns the dense candidate id; other lanes may read h_idx[slot] only after a __syncwarp.
-__device__ int kb_cand_insert(KmWarpB &S, uint32_t nid) {
-    uint32_t h = kb_hash(nid);
-    for (int step = 0; step < KB_HSLOTS; step++) {
-        const uint32_t cur = ((volatile uint32_t *)S.h_nid)[h];
-        if (cur == nid) return (int)h;
-        if (cur == KMAT_NONE) {
-            if (((volatile uint32_t *)&S.n_used)[0] >= KB_CMAX) return -1;
-            const uint32_t old = atomicCAS(&S.h_nid[h], KMAT_NONE, nid);
-            if (old == KMAT_NONE) {
-                const uint32_t id = atomicAdd(&S.n_used, 1u);
-                if (id >= KB_CMAX) return -1;
-                S.h_idx[h] = (uint8_t)id; S.c_slot[id] = (uint8_t)h;
-                return (int)h;
-            }
-            if (old == nid) return (int)h;
-        }
-        h = (h + 1) & (KB_HSLOTS - 1);
-    }
-    return -1;
-}
-__device__ __forceinline__ int kb_cand_find(const KmWarpB &S, uint32_t nid) {
-    uint32_t h = kb_hash(nid);
-    for (int step = 0; step < KB_HSLOTS; step++) {
-        const uint32_t cur = S.h_nid[h];
-        if (cur == nid) return (int)h;
-        if (cur == KMAT_NONE) return -1;
-        h = (h + 1) & (KB_HSLOTS - 1);
-    }
-    return -1;
-}
 __device__ __forceinline__ KmNodeA kb_nodeA(const KmCtxDev &C, uint32_t nid) {
     const uint4 v = __ldg((const uint4 *)(C.nodeA + nid));
     return KmNodeA{v.x, v.y, v.z, v.w};
@@ -119,27 +73,15 @@ __device__ __forceinline__ unsigned long long kb_warp_min64(unsigned long long v
     const uint32_t lo = __reduce_min_sync(KM_FULL, (uint32_t)(v >> 32) == hi ? (uint32_t)v : 0xFFFFFFFFu);
     return ((unsigned long long)hi << 32) | lo;
 }
+__device__ __forceinline__ unsigned long long kb_shfl64(unsigned long long v, int src) {
+    const uint32_t lo = __shfl_sync(KM_FULL, (uint32_t)v, src), hi = __shfl_sync(KM_FULL, (uint32_t)(v >> 32), src);
+    return ((unsigned long long)hi << 32) | lo;
+}
 __device__ __forceinline__ uint32_t kb_list_count(const KmDbDev &db, uint32_t off) {
     return db.tid_bytes == 2 ? (uint32_t)(*(const uint16_t *)(db.pool + off)) : db.pool[off];
 }
 __device__ __forceinline__ uint32_t kb_list_id(const KmDbDev &db, uint32_t off, uint32_t j) {
     return db.tid_bytes == 2 ? (uint32_t)((const uint16_t *)(db.pool + off))[1 + j] : db.pool[off + 1 + j];
-}
-
-// Leaf filter (read_label.cpp:1103-1134): ids sorted by depth descending; keep an id unless it is a strict
-// ancestor of an id kept before it.  In place; returns the number kept.
-__device__ int kb_leaf_filter(const KmCtxDev &C, uint32_t *ids, int n) {
-    if (n <= 1) return n;
-    int m = 1;                                   // the deepest id is always kept
-    uint32_t first_tin = kb_nodeB(C, ids[0]).tin;
-    for (int i = 1; i < n; i++) {
-        const uint32_t t = ids[i];
-        const KmNodeB tb = kb_nodeB(C, t);
-        bool anc = kb_is_anc(tb.tin, tb.tout, first_tin);
-        for (int j = 1; j < m && !anc; j++) anc = kb_is_anc(tb.tin, tb.tout, kb_nodeB(C, ids[j]).tin);
-        if (!anc) ids[m++] = t;
-    }
-    return m;
 }
 
 struct KbDepthDesc {      // CmpDepth1 (read_label.cpp:169-177) over {nid, depth} pairs
@@ -149,30 +91,73 @@ struct KbRankLess {       // MyPair::operator< (SortedDb.hpp:133-135): by rank n
     __device__ bool operator()(const uint2 &a, const uint2 &b) const { return a.y < b.y; }
 };
 
-// Long list / run-time pruning path, one lane, per-warp global scratch.  Restates TaxNodeStat::begin + next
-// (TaxNodeStat.hpp:60-256) followed by the filters of read_label.cpp:1031-1074.  Returns kept member count
-// (members left in scratch[0..m).x) or <0 on error (-1 bad taxid, -2 list too long for the scratch).
-__device__ int kb_big_list(const KmCtxDev &C, uint32_t hw, uint2 *scratch) {
-    const uint32_t lo = hw & 0x7FFFFFFFu;
+// ---------------------------------------------------------------------------------------------
+// List resolution, once per ctx (the result depends on the table, the taxonomy and the -g / -s options, not on
+// the read).  For every stored taxid list the record in pool2 holds what retrieve_kmer_labels derives from it:
+//   TaxNodeStat::begin + next (TaxNodeStat.hpp:60-256, run-time -g pruning included), the 16->32 conversion,
+//   human collapse and dropped ids (read_label.cpp:1031-1038), the depth sort (:1073-1074) and
+//   default mode : the leaf filter (:1103-1134)       -> [m | n_raw << 16][m node ids, insertion order]
+//   permissive   : (:1050-1058, 1075-1102)            -> [a | n_raw << 16][b][a ids in list order][b ids in depth
+//                  order whose root paths are added: every id before the first depth-0 one]
+// seq = n entries {node id, -} in next() order.  Returns nothing; writes the record.
+// ---------------------------------------------------------------------------------------------
+__device__ void kr_finish(const KmCtxDev &C, uint2 *seq, int n, uint32_t n_raw, uint32_t *rec) {
+    bool seenHuman = false;
+    int w = 0;
+    for (int i = 0; i < n; i++) {                                         // :1031-1038
+        uint32_t nid = seq[i].x;
+        uint32_t meta = kb_nodeA(C, nid).meta;
+        if (meta & KM_META_HUMAN) {
+            if (seenHuman) continue;
+            nid = C.nid_human; meta = kb_nodeA(C, nid).meta; seenHuman = true;
+        }
+        if (meta & KM_META_DROP) continue;
+        seq[w++] = make_uint2(nid, meta & KM_META_DEPTH_MASK);
+    }
+    if (C.opt.permissive) {
+        rec[0] = (uint32_t)w | (n_raw << 16);
+        for (int i = 0; i < w; i++) rec[2 + i] = seq[i].x;                // inserted in next() order (:1050-1058)
+        kmstd::sort(seq, w, KbDepthDesc());                               // :1073-1074
+        int b = 0;
+        for (int i = 0; i < w; i++) {                                     // :1077-1101 (last_depth is never updated there)
+            if (seq[i].y == 0) break;
+            rec[2 + w + b] = seq[i].x; b++;
+        }
+        rec[1] = (uint32_t)b;
+        return;
+    }
+    kmstd::sort(seq, w, KbDepthDesc());                                   // :1073-1074
+    int m = 0;                                                            // leaf filter :1103-1134
+    for (int i = 0; i < w; i++) {
+        const KmNodeB tb = kb_nodeB(C, seq[i].x);
+        bool anc = false;
+        for (int j = 0; j < m && !anc; j++) anc = kb_is_anc(tb.tin, tb.tout, kb_nodeB(C, seq[j].x).tin);
+        if (!anc) seq[m++] = seq[i];
+    }
+    rec[0] = (uint32_t)m | (n_raw << 16);
+    for (int j = 0; j < m; j++) rec[1 + j] = seq[j].x;
+}
+
+// One list.  scratch: 2 * count entries when the pruning heap is needed, else count entries.
+__device__ void kr_resolve_list(const KmCtxDev &C, uint32_t lo, uint2 *scratch, uint32_t *rec) {
     int count = (int)kb_list_count(C.db, lo);
-    if (count > KB_BIGCAP / 2) return -2;
+    const uint32_t n_raw = (uint32_t)count;
     uint2 *seq = scratch;                  // ids in next() order
-    uint2 *heap = scratch + KB_BIGCAP / 2;
     int n = 0;
     const int tid_cut = C.opt.max_count;
     if (tid_cut > 0 && count > tid_cut) {
-        if (!C.prune_rank) {               // p_map.size() == 0: count forced to 1, next() reads the first stored id (:78-81)
-            count = 1;
+        if (!C.prune_rank) {               // p_map.size() == 0: count forced to 1, next() reads the first stored id (TaxNodeStat.hpp:78-81)
             const uint32_t sid = kb_list_id(C.db, lo, 0);
             const uint32_t e = sid < C.n_sid ? C.sid2nid[sid] : KMAT_NONE;
-            if (e == KMAT_NONE) return -1;
+            if (e == KMAT_NONE) { rec[0] = KR_ERR_BAD; return; }
             seq[n++] = make_uint2(e & KB_SID_NIDMASK, 0);
-        } else {                           // :118-201
+        } else {                           // TaxNodeStat.hpp:118-201
+            uint2 *heap = scratch + count;
             int hn = 0;
             for (int i = 0; i < count; i++) {
                 const uint32_t sid = kb_list_id(C.db, lo, i);
                 const uint32_t e = sid < C.n_sid ? C.sid2nid[sid] : KMAT_NONE;
-                if (e == KMAT_NONE) return -1;
+                if (e == KMAT_NONE) { rec[0] = KR_ERR_BAD; return; }
                 const uint32_t nid = e & KB_SID_NIDMASK;
                 kmstd::pq_push(heap, hn, make_uint2(nid, C.prune_rank[nid]), KbRankLess());
             }
@@ -183,57 +168,172 @@ __device__ int kb_big_list(const KmCtxDev &C, uint32_t hw, uint2 *scratch) {
                 if (hn <= tid_cut) { newcount = hn; break; }
             }
             if (hn == 0) { newcount = 1; kmstd::pq_push(heap, hn, make_uint2(C.nid_one, 1u), KbRankLess()); }
-            count = newcount;
-            for (int i = 0; i < count; i++) seq[n++] = kmstd::pq_pop(heap, hn, KbRankLess());
+            for (int i = 0; i < newcount; i++) seq[n++] = kmstd::pq_pop(heap, hn, KbRankLess());
         }
     } else {
         for (int i = 0; i < count; i++) {
             const uint32_t sid = kb_list_id(C.db, lo, i);
             const uint32_t e = sid < C.n_sid ? C.sid2nid[sid] : KMAT_NONE;
-            if (e == KMAT_NONE) return -1;
+            if (e == KMAT_NONE) { rec[0] = KR_ERR_BAD; return; }
             seq[n++] = make_uint2(e & KB_SID_NIDMASK, 0);
         }
     }
-    // human collapse, dropped ids, depth lookup (read_label.cpp:1031-1066)
-    bool seenHuman = false;
-    int w = 0;
-    for (int i = 0; i < n; i++) {
-        uint32_t nid = seq[i].x;
-        uint32_t meta = kb_nodeA(C, nid).meta;
-        if (meta & KM_META_HUMAN) {
-            if (seenHuman) continue;
-            nid = C.nid_human; meta = kb_nodeA(C, nid).meta; seenHuman = true;
+    kr_finish(C, seq, n, n_raw, rec);
+}
+
+struct KmResolveParams {
+    KmCtxDev C;
+    uint32_t *pool2;
+    unsigned long long n_slots;
+    uint32_t *big_queue; uint32_t big_cap;       // pool offsets of the lists left to the big pass
+    unsigned int *counters;                      // [0] lists queued, [1] longest list (entries), [2] lists seen
+    uint2 *scratch; uint32_t scratch_entries;    // big pass: per-thread scratch
+};
+// pass 1: one thread per table slot; short lists are resolved in local memory, the others queued
+__global__ void __launch_bounds__(256) km_resolve_kernel(KmResolveParams R) {
+    const KmCtxDev &C = R.C;
+    uint2 local[2 * KB_LFAST];
+    for (unsigned long long s = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; s < R.n_slots; s += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint64_t v = C.db.slots[s];
+        if (!(v >> 63) || !((v >> 62) & 1)) continue;
+        const uint32_t lo = (uint32_t)v & 0x7FFFFFFFu;
+        const uint32_t count = kb_list_count(C.db, lo);
+        atomicMax(&R.counters[1], count);
+        atomicAdd(&R.counters[2], 1u);
+        uint32_t *rec = R.pool2 + (size_t)lo * C.pool2_mul;
+        if (count <= KB_LFAST) kr_resolve_list(C, lo, local, rec);
+        else {
+            rec[0] = KR_ERR_BIG;
+            const unsigned int q = atomicAdd(&R.counters[0], 1u);
+            if (q < R.big_cap) R.big_queue[q] = lo;
         }
-        if (meta & KM_META_DROP) continue;
-        seq[w++] = make_uint2(nid, meta & KM_META_DEPTH_MASK);
     }
-    kmstd::sort(seq, w, KbDepthDesc());                                  // :1073-1074
-    // leaf filter
-    int m = 0;
-    for (int i = 0; i < w; i++) {
-        const uint32_t t = seq[i].x;
-        const KmNodeB tb = kb_nodeB(C, t);
-        bool anc = false;
-        for (int j = 0; j < m && !anc; j++) anc = kb_is_anc(tb.tin, tb.tout, kb_nodeB(C, seq[j].x).tin);
-        if (!anc) seq[m++] = seq[i];
+}
+// pass 2: the queued long lists, one thread each over a per-thread global scratch
+__global__ void __launch_bounds__(128) km_resolve_big_kernel(KmResolveParams R, uint32_t n_big) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint2 *scratch = R.scratch + (size_t)t * R.scratch_entries;
+    for (uint32_t q = t; q < n_big; q += gridDim.x * blockDim.x) {
+        const uint32_t lo = R.big_queue[q];
+        kr_resolve_list(R.C, lo, scratch, R.pool2 + (size_t)lo * R.C.pool2_mul);
     }
-    return m;
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: candidate sets.  One warp per read.  Restates the list handling and the post-pass of retrieve_kmer_labels
-// (read_label.cpp:1031-1204) and the per-taxid position counts of construct_labels (:748-759).  Leaves, per
-// read, the candidates in taxid_lst order as (nid, hits) pairs in the cands buffer for the scoring kernel.
+// K3: candidate sets.  One warp per read, all per-read state in registers:
+//   * candidate i (taxid_lst entry) lives in lane i & 31, slot i >> 5: node id, first-appearance key, leaf count ...
+//   * position p lives in lane p & 31, chunk p >> 5: a 64-bit set of candidate indices (label_vec[pos].second)
+// Restates the list handling and the post-pass of retrieve_kmer_labels (read_label.cpp:1031-1204) and the
+// per-taxid position counts of construct_labels (:748-759).  Leaves, per read, the candidates in taxid_lst order
+// as (node id, hits) pairs in the cands buffer for the scoring kernel.
+// NCH = chunks of 32 positions kept in registers (0: per-warp global scratch, any length).
 // ---------------------------------------------------------------------------------------------
+struct KbCand {            // per lane, two candidate slots
+    uint32_t nid[2], key[2], leaf[2];
+};
+
+// find-or-append `v` (warp-uniform) among the candidates; returns its index or -1 when KB_CMAX is exceeded
+__device__ __forceinline__ int kb_find_or_add(KbCand &K, int &C, uint32_t v, int lane) {
+    const uint32_t f0 = __ballot_sync(KM_FULL, K.nid[0] == v);
+    if (f0) return __ffs(f0) - 1;
+    if (C > 32) {
+        const uint32_t f1 = __ballot_sync(KM_FULL, K.nid[1] == v);
+        if (f1) return 32 + __ffs(f1) - 1;
+    }
+    if (C >= KB_CMAX) return -1;
+    const int idx = C++;
+    if (lane == (idx & 31)) {
+        if (idx < 32) { K.nid[0] = v; K.key[0] = 0xFFFFFFFFu; K.leaf[0] = 0; }
+        else { K.nid[1] = v; K.key[1] = 0xFFFFFFFFu; K.leaf[1] = 0; }
+    }
+    return idx;
+}
+
+// One chunk of 32 positions (lane = position): insert the members of every position into the candidate set and
+// return this lane's position mask.  All lanes of the warp call it together.
+__device__ __forceinline__ unsigned long long kb_chunk(const KmScoreParams &P, KbCand &K, int &C, int c, uint64_t off, int np, int lane,
+                                                        int &cand_cnt, int &fnd_cnt, int &err, bool &overflow,
+                                                        unsigned long long &st_list_ids, unsigned long long &st_list_sectors) {
+    const KmCtxDev &X = P.C;
+    const bool permissive = X.opt.permissive != 0;
+    const int p = (c << 5) + lane;
+    const uint32_t hw = p < np ? __ldg(P.hit + off + p) : KM_HIT_INVALID;
+    // member iterator state: `a` ids first (a single id in v0, or a resolved record at rec), then (permissive) the
+    // root paths of `b` ids
+    uint32_t a = 0, b = 0, v0 = KMAT_NONE;
+    const uint32_t *rec = nullptr;
+    if (hw != KM_HIT_INVALID) {
+        cand_cnt++;                                                   // label_vec[pos].first >= 0 (:1015, :702)
+        if (hw != KM_HIT_MISS) {
+            if (!(hw & KM_HIT_LIST)) {
+                // singleton: one stored id.  16->32 conversion, human collapse, dropped tids (:1031-1038)
+                const uint32_t e = hw < X.n_sid ? __ldg(X.sid2nid + hw) : KMAT_NONE;
+                if (e == KMAT_NONE) err = KMAT_ERR_BAD_TAXID;          // "bad taxid" assert (TaxNodeStat.hpp:235-238)
+                else if (!(e & KB_SID_DROP)) {
+                    v0 = (e & KB_SID_HUMAN) ? X.nid_human : (e & KB_SID_NIDMASK); a = 1;
+                    if (permissive) b = (kb_nodeA(X, v0).meta & KM_META_DEPTH_MASK) ? 1 : 0;
+                }
+            } else {
+                rec = X.pool2 + (size_t)(hw & 0x7FFFFFFFu) * X.pool2_mul;
+                const uint32_t h = rec[0];
+                if (h == KR_ERR_BAD) { err = KMAT_ERR_BAD_TAXID; rec = nullptr; }
+                else {
+                    a = h & 0xFFFFu;
+                    const uint32_t n_raw = h >> 16;
+                    st_list_ids += n_raw;
+                    st_list_sectors += (2 + n_raw * X.db.tid_bytes + 31) / 32;
+                    if (permissive) { b = rec[1]; rec += 2; } else rec += 1;
+                }
+            }
+        }
+    }
+    if (a) fnd_cnt++;
+    unsigned long long mymask = 0;
+    uint32_t seqno = 0;                               // index of the next member in this position's insertion order
+    uint32_t bi = 0, pq = 0, poff = 0, plen = 0;      // permissive: current path owner / cursor
+    for (;;) {
+        uint32_t val = KMAT_NONE;                     // next member of this lane
+        if (seqno < a) val = rec ? rec[seqno] : v0;
+        else if (permissive) {
+            while (bi < b && pq >= plen) {            // open the next path
+                const uint32_t owner = rec ? rec[a + bi] : v0;
+                const KmNodeB nb = kb_nodeB(X, owner);
+                poff = nb.path_off; plen = nb.path_len; pq = 0; bi++;
+            }
+            if (pq < plen) val = X.paths[poff + pq++];
+        }
+        uint32_t pending = __ballot_sync(KM_FULL, val != KMAT_NONE);
+        if (!pending) break;
+        while (pending) {                             // one round per distinct taxid among the lanes
+            const int leader = __ffs(pending) - 1;
+            const uint32_t v = __shfl_sync(KM_FULL, val, leader);
+            const uint32_t grp = __ballot_sync(KM_FULL, val == v);
+            const int idx = kb_find_or_add(K, C, v, lane);
+            if (idx < 0) { overflow = true; break; }
+            if (lane == (idx & 31)) {
+                // first appearance in taxid_lst order: lowest position, then insertion order (:1111-1122)
+                // (leader = lowest lane of the group = its lowest position; seqno is the same in every lane)
+                const uint32_t key = ((uint32_t)((c << 5) + leader) << 16) | min(seqno, 0xFFFFu);
+                if (idx < 32) { K.key[0] = min(K.key[0], key); K.leaf[0] += __popc(grp); }
+                else { K.key[1] = min(K.key[1], key); K.leaf[1] += __popc(grp); }
+            }
+            if (val == v) mymask |= 1ull << idx;
+            pending &= ~grp;
+        }
+        if (overflow) break;
+        seqno++;
+    }
+    return mymask;
+}
+
+template <int NCH>
 __global__ void __launch_bounds__(KB_WARPS * 32) km_cand_kernel(KmScoreParams P) {
-    extern __shared__ __align__(16) unsigned char kb_smem[];
-    KmWarpB &S = reinterpret_cast<KmWarpB *>(kb_smem)[threadIdx.x >> 5];
     const KmCtxDev &X = P.C;
     const int lane = threadIdx.x & 31;
     const uint32_t warp_global = blockIdx.x * KB_WARPS + (threadIdx.x >> 5), n_warps = gridDim.x * KB_WARPS;
     const int k = X.db.kmer_len;
-    uint2 *big = P.big_scratch + (size_t)warp_global * KB_BIGCAP;
-    const uint32_t lt_mask = (1u << lane) - 1;
+    const bool permissive = X.opt.permissive != 0;
+    unsigned long long *gmask = NCH == 0 ? P.long_masks + (size_t)warp_global * P.long_cap : nullptr;
     unsigned long long st_list_ids = 0, st_list_sectors = 0, st_fast = 0, st_err = 0;
 
     for (uint32_t r = warp_global; r < P.n_reads; r += n_warps) {
@@ -247,131 +347,33 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_cand_kernel(KmScoreParams P)
         bool done = false;
         if (len < k) { res.status = KMAT_ST_SHORT_LEN; res.n1 = len; res.n2 = k; res.valid_kmers = 0; done = true; }             // :1217-1218
         else if (hd.x < X.opt.min_kmer) { res.status = KMAT_ST_SHORT_VALID; res.n1 = hd.x; res.n2 = X.opt.min_kmer; done = true; }   // :1232-1233
-        else if (np > KB_PMAX) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; done = true; st_err++; }
+        else if (NCH ? np > NCH * 32 : (uint32_t)np > P.long_cap) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; done = true; st_err++; }
         if (done) { if (lane == 0) P.out[r] = res; continue; }
 
-        for (int i = lane; i < KB_HSLOTS; i += 32) { S.h_nid[i] = KMAT_NONE; S.h_seq[i] = 0xFFFFFFFFu; S.h_leaf[i] = 0; }
-        if (lane == 0) S.n_used = 0;
-        __syncwarp();
+        KbCand K;
+        K.nid[0] = K.nid[1] = KMAT_NONE; K.key[0] = K.key[1] = 0xFFFFFFFFu; K.leaf[0] = K.leaf[1] = 0;
+        int C = 0;                                   // candidates so far (warp-uniform)
+        unsigned long long pm[NCH ? NCH : 1];        // position masks of this lane
         int cand_cnt = 0, fnd_cnt = 0, err = 0;
         bool overflow = false;
-        // ---- per position: list -> filtered, depth-sorted, leaf-filtered members (read_label.cpp:1019-1134)
-        for (int p0 = 0; p0 < np; p0 += 32) {
-            const int p = p0 + lane;
-            const uint32_t hw = p < np ? P.hit[off + p] : KM_HIT_INVALID;
-            uint32_t *L = S.lst[lane];
-            uint16_t *D = S.dep[lane];
-            int m = 0;
-            bool bigl = false;
-            uint32_t single = KMAT_NONE;                                      // the kept member when there is exactly one
-            if (hw != KM_HIT_INVALID) {
-                cand_cnt++;                                                   // label_vec[pos].first >= 0 (:1015, :702)
-                if (hw != KM_HIT_MISS) {
-                    if (!(hw & KM_HIT_LIST)) {
-                        // singleton: one stored id.  16->32 conversion, human collapse, dropped tids (:1031-1038)
-                        const uint32_t e = hw < X.n_sid ? X.sid2nid[hw] : KMAT_NONE;
-                        if (e == KMAT_NONE) err = KMAT_ERR_BAD_TAXID;          // "bad taxid" assert (TaxNodeStat.hpp:235-238)
-                        else if (!(e & KB_SID_DROP)) { single = (e & KB_SID_HUMAN) ? X.nid_human : (e & KB_SID_NIDMASK); m = 1; }
-                    } else {
-                        const uint32_t lo = hw & 0x7FFFFFFFu;
-                        const int n_raw = (int)kb_list_count(X.db, lo);
-                        st_list_ids += n_raw;
-                        st_list_sectors += (2 + n_raw * X.db.tid_bytes + 31) / 32;
-                        if (n_raw > KB_LFAST || n_raw > X.opt.max_count) bigl = true;
-                        else {
-                            bool seenHuman = false;
-                            int n = 0;
-                            for (int j = 0; j < n_raw; j++) {
-                                const uint32_t sid = kb_list_id(X.db, lo, j);
-                                const uint32_t e = sid < X.n_sid ? X.sid2nid[sid] : KMAT_NONE;
-                                if (e == KMAT_NONE) { err = KMAT_ERR_BAD_TAXID; break; }
-                                if (e & KB_SID_DROP) continue;                                       // :1038
-                                uint32_t nid = e & KB_SID_NIDMASK;
-                                if (e & KB_SID_HUMAN) {                                               // :1033-1037
-                                    if (seenHuman) continue;
-                                    nid = X.nid_human; seenHuman = true;
-                                }
-                                // insertion into depth-descending order == std::sort's insertion sort for n <= 16 (stable)
-                                const uint16_t dpt = (uint16_t)(kb_nodeA(X, nid).meta & KM_META_DEPTH_MASK);
-                                int q = n;
-                                while (q > 0 && D[q - 1] < dpt) { L[q] = L[q - 1]; D[q] = D[q - 1]; q--; }
-                                L[q] = nid; D[q] = dpt;
-                                n++;
-                            }
-                            m = err ? 0 : kb_leaf_filter(X, L, n);
-                            if (m == 1) single = L[0];
-                        }
-                    }
-                }
-            }
-            // insert the kept members (taxid_lst / leaf_track bookkeeping, :1111-1122)
-            // (a) positions with exactly one member: lanes holding the same taxid elect a leader
-            {
-                const uint32_t smask = __ballot_sync(KM_FULL, m == 1);
-                if (m == 1) {
-                    const uint32_t grp = __match_any_sync(smask, single);
-                    const int leader = __ffs(grp) - 1;
-                    int slot = 0;
-                    if (lane == leader) {
-                        slot = kb_cand_insert(S, single);
-                        if (slot >= 0) {
-                            atomicMin(&S.h_seq[slot], (uint32_t)p << 16);             // first appearance: lowest position of the group
-                            atomicAdd(&S.h_leaf[slot], (uint32_t)__popc(grp));        // leaf_track
-                        }
-                    }
-                    slot = __shfl_sync(grp, slot, leader);
-                    if (slot < 0) { overflow = true; m = 0; } else L[0] = (uint32_t)slot;
-                    fnd_cnt++;
-                }
-            }
-            // (b) positions with several members
-            if (m > 1) {
-                fnd_cnt++;
-                for (int j = 0; j < m; j++) {
-                    const int slot = kb_cand_insert(S, L[j]);
-                    if (slot < 0) { overflow = true; m = 0; break; }
-                    atomicMin(&S.h_seq[slot], ((uint32_t)p << 16) | (uint32_t)j);   // first appearance in taxid_lst order
-                    atomicAdd(&S.h_leaf[slot], 1u);
-                    L[j] = (uint32_t)slot;
-                }
-            }
-            __syncwarp();                                                     // candidate ids of this chunk's inserts are visible
-            if (p < np) {
-                unsigned long long mask = 0;
-                for (int j = 0; j < m; j++) mask |= 1ull << S.h_idx[L[j]];
-                S.posmask[p] = mask;
-            }
-            // (c) long lists / run-time pruning: one lane at a time through the per-warp global scratch
-            uint32_t bigmask = __ballot_sync(KM_FULL, bigl);
-            while (bigmask) {
-                const int src = __ffs(bigmask) - 1;
-                bigmask &= bigmask - 1;
-                if (lane == src) {
-                    const int mm = kb_big_list(X, hw, big);
-                    if (mm == -1) err = KMAT_ERR_BAD_TAXID;
-                    else if (mm < 0) overflow = true;
-                    else if (mm > 0) {
-                        unsigned long long mask = 0;
-                        for (int j = 0; j < mm; j++) {
-                            const int slot = kb_cand_insert(S, big[j].x);
-                            if (slot < 0) { overflow = true; break; }
-                            atomicMin(&S.h_seq[slot], ((uint32_t)p << 16) | (uint32_t)min(j, 0xFFFF));
-                            atomicAdd(&S.h_leaf[slot], 1u);
-                            mask |= 1ull << ((volatile uint8_t *)S.h_idx)[slot];   // inserted by this lane now, or before the last __syncwarp
-                        }
-                        S.posmask[p] = mask; fnd_cnt++;
-                    }
-                }
-                __syncwarp();
+        const int nch = (np + 31) >> 5;
+        // ---- per position: members of label_vec[pos].second in insertion order (read_label.cpp:1019-1134)
+        if (NCH) {
+#pragma unroll
+            for (int c = 0; c < (NCH ? NCH : 1); c++)
+                pm[c] = (c < nch && !overflow) ? kb_chunk(P, K, C, c, off, np, lane, cand_cnt, fnd_cnt, err, overflow, st_list_ids, st_list_sectors) : 0ull;
+        } else {
+            for (int c = 0; c < nch && !overflow; c++) {
+                const unsigned long long m = kb_chunk(P, K, C, c, off, np, lane, cand_cnt, fnd_cnt, err, overflow, st_list_ids, st_list_sectors);
+                if ((c << 5) + lane < np) gmask[(c << 5) + lane] = m;
             }
         }
-        __syncwarp();
         cand_cnt = km_warp_sum(cand_cnt); fnd_cnt = km_warp_sum(fnd_cnt);
         err = __reduce_max_sync(KM_FULL, err < 0 ? -err : 0);
         overflow = __any_sync(KM_FULL, overflow);
         if (err) { res.status = KMAT_ST_ERROR; res.err = -err; if (lane == 0) P.out[r] = res; st_err++; continue; }
         if (overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; if (lane == 0) P.out[r] = res; st_err++; continue; }
-        const int C1 = (int)S.n_used;
+        const int C1 = C;
         if (C1 == 0) {                                                       // taxid_lst.empty() -> NoDbHits (:1270-1271)
             res.status = KMAT_ST_NODBHITS; res.n1 = len; res.n2 = k;
             if (lane == 0) P.out[r] = res;
@@ -386,125 +388,109 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_cand_kernel(KmScoreParams P)
             st_fast++;
             continue;
         }
-        // ---- taxid_lst order of the first C1 candidates = order of first appearance (position, then list order)
-        for (int i = lane; i < C1; i += 32) {
-            const int s = S.c_slot[i];
-            const uint32_t q = S.h_seq[s];
-            int rank = 0;
-            for (int j = 0; j < C1; j++) rank += S.h_seq[S.c_slot[j]] < q;
-            S.order[rank] = (uint8_t)i;
-            const uint32_t nid = S.h_nid[s];
-            const KmNodeA na = kb_nodeA(X, nid); const KmNodeB nb = kb_nodeB(X, nid);
-            S.c_nid[i] = nid; S.c_tid[i] = na.tid; S.c_meta[i] = na.meta; S.c_spec[i] = na.species_anc;
-            S.c_poff[i] = nb.path_off; S.c_plen[i] = nb.path_len;
-            S.c_leaf[i] = S.h_leaf[s]; S.c_first[i] = q >> 16; S.c_anc[i] = 0ull;
-        }
-        for (int i = lane; i < KB_CMAX; i += 32) S.c_hits[i] = 0;
-        __syncwarp();
-        // ---- representative strain per species (:1143-1177) -> which members get their lineage added
-        for (int i = lane; i < C1; i += 32) {
-            const uint32_t rk = (S.c_meta[i] >> KM_META_RANK_SHIFT) & 3;
-            uint8_t qual = 1;
-            if (rk == 1) {                                                    // gRank_table[tid] == "strain"
-                bool rep = false;
-                const uint32_t sp = S.c_spec[i];
-                if (sp != KMAT_NONE) {
-                    rep = true;
-                    for (int j = 0; j < C1 && rep; j++) {
-                        if (j == i || ((S.c_meta[j] >> KM_META_RANK_SHIFT) & 3) != 1 || S.c_spec[j] != sp) continue;
-                        if (S.c_leaf[j] > S.c_leaf[i] || (S.c_leaf[j] == S.c_leaf[i] && S.c_tid[j] < S.c_tid[i])) rep = false;
-                    }
-                }
-                qual = rep;
+        // ---- per candidate: node data; taxid_lst index = rank of the first-appearance key; representative strain
+        //      per species (:1143-1177) -> which members get their lineage added
+        uint32_t c_tid[2], c_meta[2], c_spec[2], c_poff[2], c_plen[2], c_ord[2];
+        unsigned long long c_anc[2] = {0ull, 0ull};
+        bool c_qual[2] = {false, false};
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            c_tid[s] = c_meta[s] = 0; c_spec[s] = KMAT_NONE; c_poff[s] = c_plen[s] = 0; c_ord[s] = 0;
+            if (lane + 32 * s < C1) {
+                const KmNodeA na = kb_nodeA(X, K.nid[s]); const KmNodeB nb = kb_nodeB(X, K.nid[s]);
+                c_tid[s] = na.tid; c_meta[s] = na.meta; c_spec[s] = na.species_anc; c_poff[s] = nb.path_off; c_plen[s] = nb.path_len;
             }
-            S.c_qual[i] = qual;
         }
-        __syncwarp();
-        // ---- lineage expansion (:1178-1203): qualifying members in (first position, taxid) order; the ancestors
-        //      appended to taxid_lst get the next candidate ids, so for them id == taxid_lst index
-        int C = C1;
-        {
-            unsigned long long key0 = ~0ull, key1 = ~0ull;
-            if (lane < C1 && S.c_qual[lane]) key0 = ((unsigned long long)S.c_first[lane] << 32) | S.c_tid[lane];
-            if (lane + 32 < C1 && S.c_qual[lane + 32]) key1 = ((unsigned long long)S.c_first[lane + 32] << 32) | S.c_tid[lane + 32];
+        if (!permissive) {
+            bool beaten[2] = {false, false};
+            for (int j = 0; j < C1; j++) {
+                const int src = j & 31;
+                uint32_t kj, mj, sj, lj, tj;
+                if (j < 32) { kj = __shfl_sync(KM_FULL, K.key[0], src); mj = __shfl_sync(KM_FULL, c_meta[0], src); sj = __shfl_sync(KM_FULL, c_spec[0], src); lj = __shfl_sync(KM_FULL, K.leaf[0], src); tj = __shfl_sync(KM_FULL, c_tid[0], src); }
+                else { kj = __shfl_sync(KM_FULL, K.key[1], src); mj = __shfl_sync(KM_FULL, c_meta[1], src); sj = __shfl_sync(KM_FULL, c_spec[1], src); lj = __shfl_sync(KM_FULL, K.leaf[1], src); tj = __shfl_sync(KM_FULL, c_tid[1], src); }
+                const bool strain_j = ((mj >> KM_META_RANK_SHIFT) & 3) == 1;
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+                    c_ord[s] += kj < K.key[s];
+                    // another strain of the same species with more leaf hits, or as many and a smaller taxid (:1159)
+                    if (strain_j && sj == c_spec[s] && (lj > K.leaf[s] || (lj == K.leaf[s] && tj < c_tid[s]))) beaten[s] = true;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const bool strain = ((c_meta[s] >> KM_META_RANK_SHIFT) & 3) == 1;      // gRank_table[tid] == "strain"
+                c_qual[s] = lane + 32 * s < C1 && (!strain || (c_spec[s] != KMAT_NONE && !beaten[s]));
+            }
+            // ---- lineage expansion (:1178-1203): qualifying members in (first position, taxid) order; the ancestors
+            //      appended to taxid_lst get the next candidate indices
+            unsigned long long key0 = c_qual[0] ? (((unsigned long long)(K.key[0] >> 16) << 32) | c_tid[0]) : ~0ull;
+            unsigned long long key1 = c_qual[1] ? (((unsigned long long)(K.key[1] >> 16) << 32) | c_tid[1]) : ~0ull;
             for (;;) {
                 const unsigned long long mine = key0 < key1 ? key0 : key1;
                 const unsigned long long best = kb_warp_min64(mine);
                 if (best == ~0ull) break;
-                const uint32_t who = __ballot_sync(KM_FULL, mine == best);
-                const int src = __ffs(who) - 1;
-                int ci = -1;
-                if (lane == src) { if (key0 == best) { ci = lane; key0 = ~0ull; } else { ci = lane + 32; key1 = ~0ull; } }
-                ci = __shfl_sync(KM_FULL, ci, src);
-                const uint32_t poff = S.c_poff[ci], plen = S.c_plen[ci];
+                const int src = __ffs(__ballot_sync(KM_FULL, mine == best)) - 1;
+                int slot = 0;
+                if (lane == src) { if (key0 == best) { slot = 0; key0 = ~0ull; } else { slot = 1; key1 = ~0ull; } }
+                slot = __shfl_sync(KM_FULL, slot, src);
+                const uint32_t poff = __shfl_sync(KM_FULL, slot ? c_poff[1] : c_poff[0], src), plen = __shfl_sync(KM_FULL, slot ? c_plen[1] : c_plen[0], src);
                 unsigned long long anc = 0;
-                for (uint32_t c0 = 0; c0 < plen; c0 += 32) {
-                    const uint32_t a = c0 + lane < plen ? X.paths[poff + c0 + lane] : KMAT_NONE;
-                    int slot = a != KMAT_NONE ? kb_cand_find(S, a) : -1;
-                    const bool isnew = a != KMAT_NONE && slot < 0;
-                    const uint32_t nm = __ballot_sync(KM_FULL, isnew);
-                    const int nnew = __popc(nm);
-                    if (C + nnew > KB_CMAX) { overflow = true; break; }
-                    // claim ids C.. in path order (nearest ancestor first) = the order the reference appends them
-                    if (lane == 0) S.n_used = (uint32_t)(C + nnew);
-                    if (isnew) {
-                        const int idx = C + __popc(nm & lt_mask);
-                        uint32_t h = kb_hash(a);
-                        for (;;) {                                            // distinct new keys: plain CAS insert
-                            if (atomicCAS(&S.h_nid[h], KMAT_NONE, a) == KMAT_NONE) break;
-                            h = (h + 1) & (KB_HSLOTS - 1);
-                        }
-                        slot = (int)h;
-                        S.h_idx[h] = (uint8_t)idx; S.c_slot[idx] = (uint8_t)h; S.order[idx] = (uint8_t)idx;
-                        S.c_nid[idx] = a; S.c_anc[idx] = 0ull; S.c_qual[idx] = 0;
+                for (uint32_t c0 = 0; c0 < plen && !overflow; c0 += 32) {
+                    const uint32_t av = c0 + lane < plen ? X.paths[poff + c0 + lane] : KMAT_NONE;
+                    const int cnt = min(32u, plen - c0);
+                    for (int q = 0; q < cnt; q++) {                            // path order = the order the reference appends them
+                        const int idx = kb_find_or_add(K, C, __shfl_sync(KM_FULL, av, q), lane);
+                        if (idx < 0) { overflow = true; break; }
+                        anc |= 1ull << idx;
                     }
-                    C += nnew;
-                    __syncwarp();
-                    anc |= km_warp_or64(a != KMAT_NONE ? (1ull << S.h_idx[slot]) : 0ull);
                 }
                 if (overflow) break;
-                if (lane == 0) S.c_anc[ci] = anc;
-                __syncwarp();
+                if (lane == src) c_anc[slot] = anc;
+            }
+            if (overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; if (lane == 0) P.out[r] = res; st_err++; continue; }
+            // ---- expanded position sets: every qualifying member brings its ancestors
+            for (int j = 0; j < C1; j++) {
+                const unsigned long long aj = kb_shfl64(j < 32 ? c_anc[0] : c_anc[1], j & 31);
+                if (!aj) continue;
+                if (NCH) {
+#pragma unroll
+                    for (int c = 0; c < (NCH ? NCH : 1); c++) if ((pm[c] >> j) & 1) pm[c] |= aj;
+                } else for (int p = lane; p < np; p += 32) { const unsigned long long m = gmask[p]; if ((m >> j) & 1) gmask[p] = m | aj; }
+            }
+        } else {
+            for (int j = 0; j < C1; j++) {
+                const uint32_t kj = __shfl_sync(KM_FULL, j < 32 ? K.key[0] : K.key[1], j & 31);
+#pragma unroll
+                for (int s = 0; s < 2; s++) c_ord[s] += kj < K.key[s];
             }
         }
-        if (overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; if (lane == 0) P.out[r] = res; st_err++; continue; }
-        // ---- hits per candidate = number of positions whose (expanded) set holds it (:748-759).  Positions of a
-        //      chunk with the same set are counted once by a leader lane.
-        for (int p0 = 0; p0 < np; p0 += 32) {
-            const int p = p0 + lane;
-            unsigned long long mask = 0;
-            if (p < np) {
-                unsigned long long mm = S.posmask[p];
-                mask = mm;
-                while (mm) {
-                    const int idx = __ffsll((long long)mm) - 1;
-                    mm &= mm - 1;
-                    if (S.c_qual[idx]) mask |= S.c_anc[idx];
-                }
+        // ---- hits per candidate = number of positions whose set holds it (:748-759)
+        uint32_t c_hits[2] = {0, 0};
+        if (NCH) {
+            for (int i = 0; i < C; i++) {
+                uint32_t cnt = 0;
+#pragma unroll
+                for (int c = 0; c < (NCH ? NCH : 1); c++) if (c < nch) cnt += __popc(__ballot_sync(KM_FULL, (pm[c] >> i) & 1));
+                if (lane == (i & 31)) c_hits[i >> 5] = cnt;
             }
-            const uint32_t act = __ballot_sync(KM_FULL, mask != 0);
-            if (mask != 0) {
-                const uint32_t grp = __match_any_sync(act, mask);
-                if (lane == __ffs(grp) - 1) {
-                    const uint32_t cnt = (uint32_t)__popc(grp);
-                    while (mask) {
-                        const int idx = __ffsll((long long)mask) - 1;
-                        mask &= mask - 1;
-                        atomicAdd(&S.c_hits[idx], cnt);
-                    }
-                }
+        } else {
+            __syncwarp();
+            for (int i = 0; i < C; i++) {
+                uint32_t cnt = 0;
+                for (int p0 = 0; p0 < np; p0 += 32) cnt += __popc(__ballot_sync(KM_FULL, p0 + lane < np && ((gmask[p0 + lane] >> i) & 1)));
+                if (lane == (i & 31)) c_hits[i >> 5] = cnt;
             }
         }
-        __syncwarp();
         // ---- hand over to the scoring kernel: (nid, hits) in taxid_lst order
         unsigned long long co = 0;
         if (lane == 0) co = atomicAdd(P.cand_cursor, (unsigned long long)C);
         co = __shfl_sync(KM_FULL, co, 0);
         res.status = KMAT_ST_PENDING; res.n_cand = (uint32_t)C; res.cand_off = co;
         if (P.cands && co + C <= P.cand_cap) {
-            for (int f = lane; f < C; f += 32) {
-                const int i = S.order[f];
-                P.cands[co + f] = kmat_pair{S.c_nid[i], __uint_as_float(S.c_hits[i])};
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const int i = lane + 32 * s;
+                if (i < C) P.cands[co + (i < C1 ? c_ord[s] : (uint32_t)i)] = kmat_pair{K.nid[s], __uint_as_float(c_hits[s])};
             }
         } else { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_OVERFLOW; }       // candidate buffer too small: the host re-runs with the size asked for
         if (lane == 0) P.out[r] = res;
@@ -766,7 +752,9 @@ struct kmat_ctx {
     int2 *d_hdr = nullptr; kmat_read_result *d_out = nullptr;
     kmat_pair *d_cands = nullptr, *d_lin = nullptr; uint64_t cap_cands = 0, cap_lin = 0;
     unsigned long long *d_cursors = nullptr;     // [0] cands, [1] lineage
-    uint2 *d_big = nullptr; int big_warps = 0;
+    uint32_t *d_pool2 = nullptr; int pool2_mul = 1;            // resolved lists (km_resolve_kernel)
+    int resolved_max_count = -1, resolved_permissive = -1;
+    unsigned long long *d_long_masks = nullptr; uint32_t long_mask_cap = 0;
     unsigned long long *d_long_sets = nullptr; uint32_t long_slots = 0; int long_warps = 0;
     KmStatsDev *d_stats = nullptr;
     int collect_stats = 1;
@@ -775,8 +763,7 @@ struct kmat_ctx {
     char *h_bases = nullptr; uint64_t hcap_bases = 0;
     uint64_t *h_offs = nullptr; uint32_t hcap_reads = 0;
     kmat_read_result *h_out = nullptr;
-    int score_grid = 0;          // grid of the candidate kernel (persistent, warp per read)
-    size_t score_smem = 0;
+    int cand_grid[3] = {0, 0, 0};   // persistent grids of km_cand_kernel<5>, <10>, <0> (warp per read)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around the three kernels of the last batch
 };
 
@@ -789,11 +776,59 @@ static int km_upload(T **dst, const std::vector<T> &src) {
     return KMAT_OK;
 }
 
+static KmCtxDev km_ctx_dev(const kmat_ctx *c);
+
+// (Re)build the resolved list pool for the ctx's current -g / -s options.
+static int km_resolve_lists(kmat_ctx *c) {
+    const kmat_db *db = c->db;
+    if (!db->pool_words) return KMAT_OK;
+    if (c->d_pool2 && c->resolved_max_count == c->opt.max_count && c->resolved_permissive == (c->opt.permissive != 0)) return KMAT_OK;
+    KM_CUDA(cudaStreamSynchronize(c->stream));
+    const int mul = (db->tid_bytes == 2 ? 2 : 1) * (c->opt.permissive ? 2 : 1);
+    if (!c->d_pool2 || mul != c->pool2_mul) {
+        cudaFree(c->d_pool2); c->d_pool2 = nullptr;
+        KM_CUDA(cudaMalloc((void **)&c->d_pool2, ((size_t)db->pool_words * mul + 8) * 4));
+        c->pool2_mul = mul;
+    }
+    KmResolveParams R;
+    R.C = km_ctx_dev(c);
+    R.pool2 = c->d_pool2;
+    R.n_slots = db->n_buckets * KM_SLOTS_PER_BUCKET;
+    R.big_cap = (uint32_t)(db->pool_words / 9 + 16);         // a list of > KB_LFAST 16-bit ids occupies >= 9 pool words
+    R.scratch = nullptr; R.scratch_entries = 0;
+    KM_CUDA(cudaMalloc((void **)&R.big_queue, (size_t)R.big_cap * 4));
+    KM_CUDA(cudaMalloc((void **)&R.counters, 16));
+    KM_CUDA(cudaMemsetAsync(R.counters, 0, 16, c->stream));
+    const int grid = (int)std::min<unsigned long long>((R.n_slots + 255) / 256, 148ull * 32);
+    km_resolve_kernel<<<grid, 256, 0, c->stream>>>(R);
+    g_km_launches++;
+    unsigned int cnt[4] = {0, 0, 0, 0};
+    KM_CUDA(cudaMemcpyAsync(cnt, R.counters, 16, cudaMemcpyDeviceToHost, c->stream));
+    KM_CUDA(cudaStreamSynchronize(c->stream));
+    int rc = KMAT_OK;
+    if (cnt[0] > R.big_cap) { kmat_set_error("resolve: %u long lists exceed the queue of %u", cnt[0], R.big_cap); rc = KMAT_ERR_UNSUPPORTED; }
+    else if (cnt[0]) {
+        const uint32_t per = 2 * cnt[1] + 2;                                  // ids in next() order + the pruning heap
+        uint32_t threads = std::min<uint32_t>(cnt[0], 148u * 128);
+        while (threads > 128 && (size_t)threads * per * sizeof(uint2) > ((size_t)512 << 20)) threads /= 2;
+        threads = (threads + 127) / 128 * 128;
+        R.scratch_entries = per;
+        KM_CUDA(cudaMalloc((void **)&R.scratch, (size_t)threads * per * sizeof(uint2)));
+        km_resolve_big_kernel<<<threads / 128, 128, 0, c->stream>>>(R, cnt[0]);
+        g_km_launches++;
+        KM_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(R.scratch);
+    }
+    cudaFree(R.big_queue); cudaFree(R.counters);
+    KM_CUDA(cudaGetLastError());
+    c->resolved_max_count = c->opt.max_count; c->resolved_permissive = c->opt.permissive != 0;
+    return rc;
+}
+
 extern "C" int kmat_ctx_create(const kmat_db *db, const kmat_inputs *in, const kmat_opts *opt, kmat_ctx **out) {
     if (!db || !in || !out) { kmat_set_error("kmat_ctx_create: bad argument"); return KMAT_ERR_ARG; }
     kmat_opts o;
     if (opt) o = *opt; else kmat_opts_default(&o);
-    if (o.permissive) { kmat_set_error("permissive matching (-s) is not implemented in this build"); return KMAT_ERR_UNSUPPORTED; }
     kmat_ctx *c = new kmat_ctx();
     c->db = db; c->device = db->device; c->opt = o;
     int rc = kmat_build_host_ctx(*in, db->tid_bytes, db->stored_tids, c->h);
@@ -807,23 +842,22 @@ extern "C" int kmat_ctx_create(const kmat_db *db, const kmat_inputs *in, const k
     for (int i = 0; i < 4; i++) KM_CUDA(cudaEventCreate(&c->ev[i]));
     KM_CUDA(cudaMalloc((void **)&c->d_cursors, 16));
     KM_CUDA(cudaMalloc((void **)&c->d_stats, sizeof(KmStatsDev)));
-    c->score_smem = sizeof(KmWarpB) * KB_WARPS;
-    KM_CUDA(cudaFuncSetAttribute(km_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->score_smem));
-    int per_sm = 0;
-    KM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_cand_kernel, KB_WARPS * 32, c->score_smem));
-    int sms = 148;
+    int per_sm[3] = {0, 0, 0}, sms = 148;
+    KM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], km_cand_kernel<5>, KB_WARPS * 32, 0));
+    KM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], km_cand_kernel<10>, KB_WARPS * 32, 0));
+    KM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], km_cand_kernel<0>, KB_WARPS * 32, 0));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    c->score_grid = std::max(1, per_sm) * sms;
-    c->big_warps = c->score_grid * KB_WARPS;
-    KM_CUDA(cudaMalloc((void **)&c->d_big, (size_t)c->big_warps * KB_BIGCAP * sizeof(uint2)));
+    for (int i = 0; i < 3; i++) c->cand_grid[i] = std::max(1, per_sm[i]) * sms;
+    rc = km_resolve_lists(c);
+    if (rc != KMAT_OK) { kmat_ctx_destroy(c); return rc; }
     *out = c;
     return KMAT_OK;
 }
 extern "C" int kmat_ctx_set_opts(kmat_ctx *c, const kmat_opts *o) {
     if (!c || !o) return KMAT_ERR_ARG;
-    if (o->permissive) { kmat_set_error("permissive matching (-s) is not implemented in this build"); return KMAT_ERR_UNSUPPORTED; }
     c->opt = *o;
-    return KMAT_OK;
+    KM_CUDA(cudaSetDevice(c->device));
+    return km_resolve_lists(c);          // the resolved lists depend on -g and -s
 }
 extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
     if (!c) return;
@@ -832,7 +866,7 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
     cudaFree(c->d_nodeA); cudaFree(c->d_nodeB); cudaFree(c->d_paths); cudaFree(c->d_prune); cudaFree(c->d_sid2nid);
     cudaFree(c->d_model_of_cand); cudaFree(c->d_mrow); cudaFree(c->d_cut); cudaFree(c->d_cls);
     cudaFree(c->d_bases); cudaFree(c->d_offs); cudaFree(c->d_hit); cudaFree(c->d_hdr); cudaFree(c->d_out);
-    cudaFree(c->d_cands); cudaFree(c->d_lin); cudaFree(c->d_cursors); cudaFree(c->d_big); cudaFree(c->d_long_sets); cudaFree(c->d_stats);
+    cudaFree(c->d_cands); cudaFree(c->d_lin); cudaFree(c->d_cursors); cudaFree(c->d_pool2); cudaFree(c->d_long_masks); cudaFree(c->d_long_sets); cudaFree(c->d_stats);
     cudaFreeHost(c->h_bases); cudaFreeHost(c->h_offs); cudaFreeHost(c->h_out);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -849,6 +883,7 @@ static KmCtxDev km_ctx_dev(const kmat_ctx *c) {
     memset(X.class_ranknum, 0, sizeof X.class_ranknum);
     for (int i = 0; i < c->h.n_classes && i < 64; i++) X.class_ranknum[i] = (int8_t)c->h.class_ranknum[i];
     X.opt = c->opt;
+    X.pool2 = c->d_pool2; X.pool2_mul = c->pool2_mul;
     return X;
 }
 
@@ -906,9 +941,23 @@ static int km_run_device(kmat_ctx *c, const char *d_bases, const uint64_t *d_off
     P.offs = d_offs; P.n_reads = n_reads; P.hit = c->d_hit; P.hdr = c->d_hdr; P.out = d_out;
     P.cands = c->d_cands; P.cand_cursor = c->d_cursors; P.cand_cap = c->cap_cands;
     P.lin = c->d_lin; P.lin_cursor = c->d_cursors + 1; P.lin_cap = c->cap_lin;
-    P.big_scratch = c->d_big; P.stats = c->collect_stats ? c->d_stats : nullptr;
-    const int grid = std::max(1, std::min<int>(c->score_grid, (int)((n_reads + KB_WARPS - 1) / KB_WARPS)));
-    km_cand_kernel<<<grid, KB_WARPS * 32, c->score_smem, st>>>(P);
+    P.stats = c->collect_stats ? c->d_stats : nullptr;
+    P.long_masks = nullptr; P.long_cap = 0;
+    const int want_grid = (int)((n_reads + KB_WARPS - 1) / KB_WARPS);
+    const int max_pos = (int)max_len - c->db->kmer_len + 1;
+    if (max_pos <= 5 * 32) km_cand_kernel<5><<<std::max(1, std::min(c->cand_grid[0], want_grid)), KB_WARPS * 32, 0, st>>>(P);
+    else if (max_pos <= 10 * 32) km_cand_kernel<10><<<std::max(1, std::min(c->cand_grid[1], want_grid)), KB_WARPS * 32, 0, st>>>(P);
+    else {
+        // long reads: the position masks live in a per-warp global scratch
+        const uint32_t cap = ((uint32_t)max_pos + 31u) & ~31u;
+        if (cap > c->long_mask_cap) {
+            cudaFree(c->d_long_masks); c->d_long_masks = nullptr;
+            KM_CUDA(cudaMalloc((void **)&c->d_long_masks, (size_t)c->cand_grid[2] * KB_WARPS * cap * 8));
+            c->long_mask_cap = cap;
+        }
+        P.long_masks = c->d_long_masks; P.long_cap = c->long_mask_cap;
+        km_cand_kernel<0><<<std::max(1, std::min(c->cand_grid[2], want_grid)), KB_WARPS * 32, 0, st>>>(P);
+    }
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     KM_CUDA(cudaEventRecord(c->ev[3], st));

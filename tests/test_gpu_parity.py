@@ -68,7 +68,7 @@ def test_encode_matches_oracle(golden_small, dbs):
 
 
 @pytest.mark.parametrize("scen", ["golden_small", "golden_lists"])
-@pytest.mark.parametrize("opts", [k for k in S.OPTION_SETS if k != "permissive"])
+@pytest.mark.parametrize("opts", list(S.OPTION_SETS))
 def test_labels_match_reference_golden(scen, opts, request, dbs):
     """kmat_label_batch -> kmat_format_tail reproduces the reference read_label .out byte for byte."""
     g = request.getfixturevalue(scen)
@@ -117,3 +117,37 @@ def test_batch_split_invariance(golden_small, dbs):
         r, c, l = ctx.label(seqs[a:a + 37])
         parts += ctx.tails(r, c, l)
     assert parts == whole
+
+
+@pytest.mark.parametrize("opts", ["run_rl", "permissive", "prune3"])
+def test_long_and_ragged_reads_match_oracle(golden_lists, dbs, opts):
+    """Variable-length batch (BASELINE config 5 shape): reads from 0 to 12 kbp in one call exercise the three
+    position-mask paths of the candidate kernel (<= 160 positions in registers, <= 320, global scratch) and the
+    probe kernel's global dedup sets; compared line for line with the oracle."""
+    g = golden_lists
+    inp = S.build_inputs("lists", g.workdir + "/long_" + opts)
+    rng = np.random.default_rng(11)
+    names = list(inp["genomes"])
+    seqs = []
+    for L in [0, 5, 19, 20, 21, 150, 179, 180, 181, 250, 339, 340, 341, 700, 2999, 6000, 12000]:
+        for rep in range(3):
+            parts = []
+            while sum(map(len, parts)) < L:
+                gsel = fx.codes_to_str(inp["genomes"][names[int(rng.integers(0, 4))]])      # a few related genomes only
+                a = int(rng.integers(0, max(1, len(gsel) - 500)))
+                parts.append(gsel[a:a + int(rng.integers(100, 2500))])
+            s = "".join(parts)[:L]
+            if L > 100 and rep == 1:
+                s = s[:60] + "N" + s[61:]
+            if L > 100 and rep == 2:
+                s = s.lower()
+            seqs.append(s)
+    ctx = make_ctx(g, dbs[g.name], opts)
+    orc = oracle_for(g, opts)
+    res, cands, lin = ctx.label(seqs)
+    ores, _, _ = orc.label(seqs)
+    unsupported = (res["status"] == 6)
+    assert unsupported.sum() <= 2, "more than a couple of reads exceed the candidate capacity"
+    mine = ctx.tails(res[~unsupported], cands, lin, prn_all=True)
+    want = [t for t, u in zip(orc.tails(ores), unsupported) if not u]
+    assert mine == want
