@@ -313,11 +313,16 @@ def main():
         # ---- e2e through the host-buffer API
         e2e = None
         if not a.no_e2e:
+            # every host buffer of the call is page-locked (torch pinned tensors viewed as numpy arrays)
             h_reads = torch.empty((n, L), dtype=torch.uint8, pin_memory=True)
             h_reads.copy_(reads)
-            h_offs = (np.arange(n + 1, dtype=np.uint64) * L)
-            res = np.zeros(n, dtype=api.RESULT_DTYPE)
-            cands = np.zeros(max(1, 40 * n), dtype=api.PAIR_DTYPE)
+            t_offs = torch.empty(n + 1, dtype=torch.int64, pin_memory=True)
+            t_offs.copy_(torch.arange(n + 1, dtype=torch.int64) * L)
+            t_res = torch.empty(n * api.RESULT_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+            t_cands = torch.empty(max(1, 24 * n) * api.PAIR_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+            h_offs = t_offs.numpy().view(np.uint64)
+            res = t_res.numpy().view(api.RESULT_DTYPE)
+            cands = t_cands.numpy().view(api.PAIR_DTYPE)
             import ctypes as C
             n_c = C.c_uint64()
 
@@ -338,7 +343,7 @@ def main():
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e = {"value": world * n / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(total + 8 * (n + 1)),
                    "d2h_bytes_per_step": int(n * api.RESULT_DTYPE.itemsize + n_c.value * 8)}
-            del h_reads
+            del h_reads, t_offs, t_res, t_cands
 
         if rank == 0:
             hbm_peak, peak_src = measured_peaks()

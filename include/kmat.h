@@ -164,6 +164,10 @@ int kmat_label_batch(kmat_ctx *, const char *bases, const uint64_t *offs, uint32
                      kmat_pair *cands, uint64_t cands_cap, uint64_t *n_cands,
                      kmat_pair *lineage, uint64_t lineage_cap, uint64_t *n_lineage);
 
+/* Page-locked host memory for the buffers of kmat_label_batch (optional; NULL when no device / out of memory). */
+void *kmat_host_alloc(size_t bytes);
+void kmat_host_free(void *);
+
 /* Device-resident variant used for kernel-only timing and multi-batch pipelines: inputs already in
  * HBM (d_bases, d_offs on the ctx's device); results stay on the device (d_out) unless NULL.
  * max_read_len bounds the longest read of the batch (sizes the per-warp dedup sets).

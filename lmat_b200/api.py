@@ -49,7 +49,7 @@ EXPORTS = [
     "kmat_ctx_create", "kmat_ctx_set_opts", "kmat_ctx_destroy", "kmat_label_batch", "kmat_label_batch_device",
     "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench",
     "kmat_set_l2_fetch_granularity", "kmat_reader_open", "kmat_reader_close", "kmat_read_batch_new", "kmat_read_batch_free",
-    "kmat_reader_next", "kmat_read_batch_view", "kmat_tally_class",
+    "kmat_reader_next", "kmat_read_batch_view", "kmat_tally_class", "kmat_host_alloc", "kmat_host_free",
 ]
 
 _lib = None
@@ -112,6 +112,9 @@ def lib():
     L.kmat_reader_next.argtypes = [vp, C.c_uint32, C.c_uint64, vp]
     L.kmat_read_batch_view.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
     L.kmat_tally_class.argtypes = [vp, C.c_float, C.c_int32]
+    L.kmat_host_alloc.restype = vp
+    L.kmat_host_alloc.argtypes = [C.c_size_t]
+    L.kmat_host_free.argtypes = [vp]
     _lib = L
     return L
 

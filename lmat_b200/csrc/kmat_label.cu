@@ -745,11 +745,18 @@ struct kmat_ctx {
     KmNodeA *d_nodeA = nullptr; KmNodeB *d_nodeB = nullptr; uint32_t *d_paths = nullptr, *d_prune = nullptr, *d_sid2nid = nullptr;
     int16_t *d_model_of_cand = nullptr; int32_t *d_mrow = nullptr; float *d_cut = nullptr; uint8_t *d_cls = nullptr;
     KmHostCtx h;
-    // batch buffers (grown on demand)
-    char *d_bases = nullptr; uint64_t cap_bases = 0;
-    uint64_t *d_offs = nullptr; uint32_t cap_reads = 0;
+    // batch buffers (grown on demand).  Host-buffer batches are cut into chunks that alternate between two slots so
+    // that the H2D copy of chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i.
+    struct Slot {
+        char *d_bases = nullptr; uint64_t cap_bases = 0;
+        uint64_t *d_offs = nullptr; kmat_read_result *d_out = nullptr; uint32_t cap_reads = 0;
+        unsigned long long *h_cur = nullptr;       // pinned: cursors after this slot's chunk
+        cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
+    } slot[2];
+    cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
     uint32_t *d_hit = nullptr; uint64_t cap_hit = 0;
-    int2 *d_hdr = nullptr; kmat_read_result *d_out = nullptr;
+    int2 *d_hdr = nullptr; uint32_t cap_hdr = 0;
+    kmat_read_result *d_out_dev = nullptr; uint32_t cap_out_dev = 0;   // kmat_label_batch_device with d_out == NULL
     kmat_pair *d_cands = nullptr, *d_lin = nullptr; uint64_t cap_cands = 0, cap_lin = 0;
     unsigned long long *d_cursors = nullptr;     // [0] cands, [1] lineage
     uint32_t *d_pool2 = nullptr; int pool2_mul = 1;            // resolved lists (km_resolve_kernel)
@@ -759,10 +766,6 @@ struct kmat_ctx {
     KmStatsDev *d_stats = nullptr;
     int collect_stats = 1;
     kmat_batch_stats last{};
-    // pinned staging
-    char *h_bases = nullptr; uint64_t hcap_bases = 0;
-    uint64_t *h_offs = nullptr; uint32_t hcap_reads = 0;
-    kmat_read_result *h_out = nullptr;
     int cand_grid[3] = {0, 0, 0};   // persistent grids of km_cand_kernel<5>, <10>, <0> (warp per read)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around the three kernels of the last batch
 };
@@ -839,7 +842,15 @@ extern "C" int kmat_ctx_create(const kmat_db *db, const kmat_inputs *in, const k
     UP(d_model_of_cand, model_of_cand); UP(d_mrow, mrow); UP(d_cut, cut); UP(d_cls, cls);
 #undef UP
     KM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    KM_CUDA(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
+    KM_CUDA(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
     for (int i = 0; i < 4; i++) KM_CUDA(cudaEventCreate(&c->ev[i]));
+    for (auto &sl : c->slot) {
+        KM_CUDA(cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
+        KM_CUDA(cudaEventCreateWithFlags(&sl.ev_comp, cudaEventDisableTiming));
+        KM_CUDA(cudaEventCreateWithFlags(&sl.ev_d2h, cudaEventDisableTiming));
+        KM_CUDA(cudaMallocHost((void **)&sl.h_cur, 16));
+    }
     KM_CUDA(cudaMalloc((void **)&c->d_cursors, 16));
     KM_CUDA(cudaMalloc((void **)&c->d_stats, sizeof(KmStatsDev)));
     int per_sm[3] = {0, 0, 0}, sms = 148;
@@ -865,9 +876,16 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_nodeA); cudaFree(c->d_nodeB); cudaFree(c->d_paths); cudaFree(c->d_prune); cudaFree(c->d_sid2nid);
     cudaFree(c->d_model_of_cand); cudaFree(c->d_mrow); cudaFree(c->d_cut); cudaFree(c->d_cls);
-    cudaFree(c->d_bases); cudaFree(c->d_offs); cudaFree(c->d_hit); cudaFree(c->d_hdr); cudaFree(c->d_out);
+    for (auto &sl : c->slot) {
+        cudaFree(sl.d_bases); cudaFree(sl.d_offs); cudaFree(sl.d_out); cudaFreeHost(sl.h_cur);
+        if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
+        if (sl.ev_comp) cudaEventDestroy(sl.ev_comp);
+        if (sl.ev_d2h) cudaEventDestroy(sl.ev_d2h);
+    }
+    cudaFree(c->d_hit); cudaFree(c->d_hdr); cudaFree(c->d_out_dev);
+    if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
+    if (c->st_d2h) cudaStreamDestroy(c->st_d2h);
     cudaFree(c->d_cands); cudaFree(c->d_lin); cudaFree(c->d_cursors); cudaFree(c->d_pool2); cudaFree(c->d_long_masks); cudaFree(c->d_long_sets); cudaFree(c->d_stats);
-    cudaFreeHost(c->h_bases); cudaFreeHost(c->h_offs); cudaFreeHost(c->h_out);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
@@ -897,60 +915,56 @@ static int km_grow(T **p, uint64_t *cap, uint64_t want) {
     return KMAT_OK;
 }
 
-// per-read device buffers share one capacity
-static int km_reserve_reads(kmat_ctx *c, uint32_t n_reads) {
-    if (n_reads <= c->cap_reads && c->d_hdr) return KMAT_OK;
-    cudaFree(c->d_hdr); cudaFree(c->d_offs); cudaFree(c->d_out);
-    c->d_hdr = nullptr; c->d_offs = nullptr; c->d_out = nullptr; c->cap_reads = 0;
-    const size_t cap = (size_t)n_reads + n_reads / 4 + 64;
-    KM_CUDA(cudaMalloc((void **)&c->d_hdr, cap * sizeof(int2)));
-    KM_CUDA(cudaMalloc((void **)&c->d_offs, (cap + 1) * 8));
-    KM_CUDA(cudaMalloc((void **)&c->d_out, cap * sizeof(kmat_read_result)));
-    c->cap_reads = (uint32_t)std::min<size_t>(cap, 0xFFFFFFFFull);
-    return KMAT_OK;
-}
+// One pass of the kernels over reads already on the device.  d_bases / the hit array are addressed as
+// base[offs[r] + j], so a chunk of a larger batch passes pointers shifted by -offs[first read].
+struct KmPass {
+    const char *d_bases; const uint64_t *d_offs; uint32_t n_reads;
+    uint64_t first_off, total_bases; uint32_t max_len;
+    kmat_read_result *d_out;
+    bool reset;                 // zero the candidate cursors and the statistics first
+};
 
-// Launch K1+K2 then K3+K4 on d_bases / d_offs (already on the device).  max_len bounds the longest read.
-static int km_run_device(kmat_ctx *c, const char *d_bases, const uint64_t *d_offs, uint32_t n_reads, uint64_t total_bases,
-                         uint32_t max_len, kmat_read_result *d_out, cudaStream_t st) {
+static int km_run_device(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
     int rc;
-    if ((rc = km_grow(&c->d_hit, &c->cap_hit, total_bases + 1)) != KMAT_OK) return rc;
-    if ((rc = km_reserve_reads(c, n_reads)) != KMAT_OK) return rc;
-    const int pgrid = km_probe_grid(n_reads);
-    const uint32_t max_np = max_len;
-    if (max_np > 256) {
-        uint32_t slots = 1024; while (slots < 2 * max_np) slots <<= 1;
+    if ((rc = km_grow(&c->d_hit, &c->cap_hit, L.total_bases + 1)) != KMAT_OK) return rc;
+    { uint64_t cap = c->cap_hdr; if ((rc = km_grow(&c->d_hdr, &cap, L.n_reads)) != KMAT_OK) return rc; c->cap_hdr = (uint32_t)cap; }
+    const int pgrid = km_probe_grid(L.n_reads);
+    if (L.max_len > 256) {
+        uint32_t slots = 1024; while (slots < 2 * L.max_len) slots <<= 1;
         const int warps = 148 * 6 * KM_PROBE_WARPS_HOST;
         if (slots > c->long_slots || warps > c->long_warps) {
+            KM_CUDA(cudaStreamSynchronize(st));
             cudaFree(c->d_long_sets); c->d_long_sets = nullptr;
             KM_CUDA(cudaMalloc((void **)&c->d_long_sets, (size_t)warps * slots * 8));
             c->long_slots = slots; c->long_warps = warps;
         }
     }
-    if (!c->d_cands) { if ((rc = km_grow(&c->d_cands, &c->cap_cands, (uint64_t)n_reads * 24 + 4096)) != KMAT_OK) return rc; }
-    if (c->opt.want_lineage && !c->d_lin) { if ((rc = km_grow(&c->d_lin, &c->cap_lin, (uint64_t)n_reads * 24 + 4096)) != KMAT_OK) return rc; }
-    KM_CUDA(cudaMemsetAsync(c->d_cursors, 0, 16, st));
-    if (c->collect_stats) KM_CUDA(cudaMemsetAsync(c->d_stats, 0, sizeof(KmStatsDev), st));
+    if (L.reset) {
+        KM_CUDA(cudaMemsetAsync(c->d_cursors, 0, 16, st));
+        if (c->collect_stats) KM_CUDA(cudaMemsetAsync(c->d_stats, 0, sizeof(KmStatsDev), st));
+    }
+    uint32_t *hit = c->d_hit - L.first_off;
     KM_CUDA(cudaEventRecord(c->ev[0], st));
-    rc = km_launch_encode_probe(c->db, d_bases, d_offs, n_reads, c->d_hit, c->d_hdr, nullptr, nullptr, c->d_long_sets, c->long_slots,
+    rc = km_launch_encode_probe(c->db, L.d_bases, L.d_offs, L.n_reads, hit, c->d_hdr, nullptr, nullptr, c->d_long_sets, c->long_slots,
                                 pgrid, c->collect_stats ? c->d_stats : nullptr, 1, st);
     if (rc != KMAT_OK) return rc;
     KM_CUDA(cudaEventRecord(c->ev[1], st));
     KmScoreParams P;
     P.C = km_ctx_dev(c);
-    P.offs = d_offs; P.n_reads = n_reads; P.hit = c->d_hit; P.hdr = c->d_hdr; P.out = d_out;
+    P.offs = L.d_offs; P.n_reads = L.n_reads; P.hit = hit; P.hdr = c->d_hdr; P.out = L.d_out;
     P.cands = c->d_cands; P.cand_cursor = c->d_cursors; P.cand_cap = c->cap_cands;
     P.lin = c->d_lin; P.lin_cursor = c->d_cursors + 1; P.lin_cap = c->cap_lin;
     P.stats = c->collect_stats ? c->d_stats : nullptr;
     P.long_masks = nullptr; P.long_cap = 0;
-    const int want_grid = (int)((n_reads + KB_WARPS - 1) / KB_WARPS);
-    const int max_pos = (int)max_len - c->db->kmer_len + 1;
+    const int want_grid = (int)((L.n_reads + KB_WARPS - 1) / KB_WARPS);
+    const int max_pos = (int)L.max_len - c->db->kmer_len + 1;
     if (max_pos <= 5 * 32) km_cand_kernel<5><<<std::max(1, std::min(c->cand_grid[0], want_grid)), KB_WARPS * 32, 0, st>>>(P);
     else if (max_pos <= 10 * 32) km_cand_kernel<10><<<std::max(1, std::min(c->cand_grid[1], want_grid)), KB_WARPS * 32, 0, st>>>(P);
     else {
         // long reads: the position masks live in a per-warp global scratch
         const uint32_t cap = ((uint32_t)max_pos + 31u) & ~31u;
         if (cap > c->long_mask_cap) {
+            KM_CUDA(cudaStreamSynchronize(st));
             cudaFree(c->d_long_masks); c->d_long_masks = nullptr;
             KM_CUDA(cudaMalloc((void **)&c->d_long_masks, (size_t)c->cand_grid[2] * KB_WARPS * cap * 8));
             c->long_mask_cap = cap;
@@ -961,10 +975,17 @@ static int km_run_device(kmat_ctx *c, const char *d_bases, const uint64_t *d_off
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     KM_CUDA(cudaEventRecord(c->ev[3], st));
-    km_score_kernel<<<(n_reads + KS_THREADS - 1) / KS_THREADS, KS_THREADS, 0, st>>>(P);
+    km_score_kernel<<<(L.n_reads + KS_THREADS - 1) / KS_THREADS, KS_THREADS, 0, st>>>(P);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     KM_CUDA(cudaEventRecord(c->ev[2], st));
+    return KMAT_OK;
+}
+
+static int km_reserve_cands(kmat_ctx *c, uint64_t n_reads) {
+    int rc;
+    if (!c->d_cands || c->cap_cands < n_reads * 12 + 4096) { if ((rc = km_grow(&c->d_cands, &c->cap_cands, n_reads * 24 + 4096)) != KMAT_OK) return rc; }
+    if (c->opt.want_lineage && (!c->d_lin || c->cap_lin < n_reads * 12 + 4096)) { if ((rc = km_grow(&c->d_lin, &c->cap_lin, n_reads * 24 + 4096)) != KMAT_OK) return rc; }
     return KMAT_OK;
 }
 
@@ -974,10 +995,16 @@ extern "C" int kmat_label_batch_device(kmat_ctx *c, const char *d_bases, const u
     KM_CUDA(cudaSetDevice(c->device));
     if (!n_reads) return KMAT_OK;
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    int rc = km_reserve_reads(c, n_reads);
-    if (rc != KMAT_OK) return rc;
-    if (!d_out) d_out = c->d_out;
-    return km_run_device(c, d_bases, d_offs, n_reads, total_bases, max_read_len, d_out, st);
+    int rc;
+    if (!d_out) {
+        uint64_t cap = c->cap_out_dev;
+        if ((rc = km_grow(&c->d_out_dev, &cap, n_reads)) != KMAT_OK) return rc;
+        c->cap_out_dev = (uint32_t)cap;
+        d_out = c->d_out_dev;
+    }
+    if ((rc = km_reserve_cands(c, n_reads)) != KMAT_OK) return rc;
+    KmPass L{d_bases, d_offs, n_reads, 0, total_bases, max_read_len, d_out, true};
+    return km_run_device(c, L, st);
 }
 extern "C" int kmat_ctx_last_kernel_ms(kmat_ctx *c, float *probe_ms, float *cand_ms, float *score_ms) {
     if (!c) return KMAT_ERR_ARG;
@@ -1025,6 +1052,10 @@ extern "C" int kmat_ctx_last_stats(kmat_ctx *c, kmat_batch_stats *out) {
     return KMAT_OK;
 }
 
+// Host buffers in, host buffers out.  The batch is cut into chunks; chunk i's kernels (one stream, in order, so the
+// candidate records of a chunk are contiguous behind one running cursor) overlap the H2D copy of chunk i+1 and the
+// D2H copy of chunk i-1 on two copy streams.  Pinned caller buffers (kmat_host_alloc) make those copies truly
+// asynchronous; pageable ones are staged by the driver and still overlap the kernels.
 extern "C" int kmat_label_batch(kmat_ctx *c, const char *bases, const uint64_t *offs, uint32_t n_reads, kmat_read_result *out,
                                 kmat_pair *cands, uint64_t cands_cap, uint64_t *n_cands, kmat_pair *lineage, uint64_t lineage_cap,
                                 uint64_t *n_lineage) {
@@ -1033,46 +1064,99 @@ extern "C" int kmat_label_batch(kmat_ctx *c, const char *bases, const uint64_t *
     if (n_lineage) *n_lineage = 0;
     if (!n_reads) return KMAT_OK;
     KM_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = c->stream;
-    const uint64_t total = offs[n_reads] - offs[0];
-    uint32_t max_len = 0;
-    for (uint32_t r = 0; r < n_reads; r++) max_len = std::max<uint32_t>(max_len, (uint32_t)(offs[r + 1] - offs[r]));
+    static const uint32_t chunk_reads = [] { const char *e = getenv("KMAT_CHUNK_READS"); const long v = e ? atol(e) : 0; return (uint32_t)(v > 0 ? v : (1 << 20)); }();
+    const uint64_t chunk_bases = (uint64_t)256 << 20;
     int rc;
-    // pinned staging (the caller's buffers are ordinary host memory)
-    if (total + 1 > c->hcap_bases) { cudaFreeHost(c->h_bases); c->h_bases = nullptr; c->hcap_bases = total + total / 4 + 4096; KM_CUDA(cudaMallocHost((void **)&c->h_bases, c->hcap_bases)); }
-    if (n_reads + 1 > c->hcap_reads) {
-        cudaFreeHost(c->h_offs); cudaFreeHost(c->h_out); c->h_offs = nullptr; c->h_out = nullptr;
-        c->hcap_reads = n_reads + n_reads / 4 + 64;
-        KM_CUDA(cudaMallocHost((void **)&c->h_offs, (size_t)c->hcap_reads * 8));
-        KM_CUDA(cudaMallocHost((void **)&c->h_out, (size_t)c->hcap_reads * sizeof(kmat_read_result)));
-    }
-    memcpy(c->h_bases, bases + offs[0], total);
-    for (uint32_t r = 0; r <= n_reads; r++) c->h_offs[r] = offs[r] - offs[0];
-    if ((rc = km_grow(&c->d_bases, &c->cap_bases, total + 1)) != KMAT_OK) return rc;
-    if ((rc = km_reserve_reads(c, n_reads)) != KMAT_OK) return rc;
-    KM_CUDA(cudaMemcpyAsync(c->d_bases, c->h_bases, total, cudaMemcpyHostToDevice, st));
-    KM_CUDA(cudaMemcpyAsync(c->d_offs, c->h_offs, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
     for (int attempt = 0; attempt < 3; attempt++) {
-        rc = km_run_device(c, c->d_bases, c->d_offs, n_reads, total, max_len, c->d_out, st);
-        if (rc != KMAT_OK) return rc;
-        unsigned long long cur[2];
-        KM_CUDA(cudaMemcpyAsync(cur, c->d_cursors, 16, cudaMemcpyDeviceToHost, st));
-        KM_CUDA(cudaStreamSynchronize(st));
+        if ((rc = km_reserve_cands(c, n_reads)) != KMAT_OK) return rc;
+        unsigned long long done_c = 0, done_l = 0;      // candidate / lineage pairs already copied out
+        struct Chunk { uint32_t r0 = 0, r1 = 0; int slot = 0; bool valid = false; } prev;
+        auto drain = [&](const Chunk &ch) -> int {      // results of a finished chunk -> caller buffers
+            kmat_ctx::Slot &sl = c->slot[ch.slot];
+            KM_CUDA(cudaEventSynchronize(sl.ev_comp));
+            const unsigned long long cur_c = std::min<unsigned long long>(sl.h_cur[0], c->cap_cands), cur_l = std::min<unsigned long long>(sl.h_cur[1], c->cap_lin);
+            KM_CUDA(cudaMemcpyAsync(out + ch.r0, sl.d_out, (size_t)(ch.r1 - ch.r0) * sizeof(kmat_read_result), cudaMemcpyDeviceToHost, c->st_d2h));
+            if (cands && cur_c > done_c && done_c < cands_cap) {
+                const unsigned long long hi = std::min<unsigned long long>(cur_c, cands_cap);
+                KM_CUDA(cudaMemcpyAsync(cands + done_c, c->d_cands + done_c, (size_t)(hi - done_c) * sizeof(kmat_pair), cudaMemcpyDeviceToHost, c->st_d2h));
+            }
+            if (lineage && c->opt.want_lineage && cur_l > done_l && done_l < lineage_cap) {
+                const unsigned long long hi = std::min<unsigned long long>(cur_l, lineage_cap);
+                KM_CUDA(cudaMemcpyAsync(lineage + done_l, c->d_lin + done_l, (size_t)(hi - done_l) * sizeof(kmat_pair), cudaMemcpyDeviceToHost, c->st_d2h));
+            }
+            done_c = std::max(done_c, cur_c); done_l = std::max(done_l, cur_l);
+            KM_CUDA(cudaEventRecord(sl.ev_d2h, c->st_d2h));
+            return KMAT_OK;
+        };
+        uint32_t r0 = 0;
+        int ci = 0;
+        unsigned long long total_c = 0, total_l = 0;
+        while (r0 < n_reads) {
+            // chunk [r0, r1): bounded by reads and by bases (at least one read)
+            uint32_t r1 = std::min<uint64_t>(n_reads, (uint64_t)r0 + chunk_reads);
+            if (offs[r1] - offs[r0] > chunk_bases) {
+                uint32_t lo = r0 + 1, hi = r1;                      // largest r1 with offs[r1] - offs[r0] <= chunk_bases
+                while (lo < hi) { const uint32_t mid = lo + (hi - lo + 1) / 2; if (offs[mid] - offs[r0] <= chunk_bases) lo = mid; else hi = mid - 1; }
+                r1 = lo;
+            }
+            const uint32_t n = r1 - r0;
+            const uint64_t nb = offs[r1] - offs[r0];
+            uint32_t max_len = 0;
+            for (uint32_t r = r0; r < r1; r++) max_len = std::max<uint32_t>(max_len, (uint32_t)(offs[r + 1] - offs[r]));
+            kmat_ctx::Slot &sl = c->slot[ci & 1];
+            if (nb + 1 > sl.cap_bases || n + 1 > sl.cap_reads) {
+                // growing a slot: everything queued on it must have finished
+                KM_CUDA(cudaStreamSynchronize(c->st_h2d)); KM_CUDA(cudaStreamSynchronize(c->stream)); KM_CUDA(cudaStreamSynchronize(c->st_d2h));
+                if (nb + 1 > sl.cap_bases) { if ((rc = km_grow(&sl.d_bases, &sl.cap_bases, nb + 1)) != KMAT_OK) return rc; }
+                if (n + 1 > sl.cap_reads) {
+                    cudaFree(sl.d_offs); cudaFree(sl.d_out); sl.d_offs = nullptr; sl.d_out = nullptr;
+                    const size_t cap = (size_t)n + n / 4 + 64;
+                    KM_CUDA(cudaMalloc((void **)&sl.d_offs, (cap + 1) * 8));
+                    KM_CUDA(cudaMalloc((void **)&sl.d_out, cap * sizeof(kmat_read_result)));
+                    sl.cap_reads = (uint32_t)cap;
+                }
+            }
+            // H2D once the kernels that last read this slot's inputs are done
+            if (ci >= 2) KM_CUDA(cudaStreamWaitEvent(c->st_h2d, sl.ev_comp, 0));
+            KM_CUDA(cudaMemcpyAsync(sl.d_bases, bases + offs[r0], nb, cudaMemcpyHostToDevice, c->st_h2d));
+            KM_CUDA(cudaMemcpyAsync(sl.d_offs, offs + r0, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->st_h2d));
+            KM_CUDA(cudaEventRecord(sl.ev_h2d, c->st_h2d));
+            // kernels once the inputs are in and the previous results of this slot have been copied out
+            KM_CUDA(cudaStreamWaitEvent(c->stream, sl.ev_h2d, 0));
+            if (ci >= 2) KM_CUDA(cudaStreamWaitEvent(c->stream, sl.ev_d2h, 0));
+            KmPass L{sl.d_bases - offs[r0], sl.d_offs, n, offs[r0], nb, max_len, sl.d_out, ci == 0};
+            if ((rc = km_run_device(c, L, c->stream)) != KMAT_OK) return rc;
+            KM_CUDA(cudaMemcpyAsync(sl.h_cur, c->d_cursors, 16, cudaMemcpyDeviceToHost, c->stream));
+            KM_CUDA(cudaEventRecord(sl.ev_comp, c->stream));
+            if (prev.valid && (rc = drain(prev)) != KMAT_OK) return rc;
+            prev.r0 = r0; prev.r1 = r1; prev.slot = ci & 1; prev.valid = true;
+            r0 = r1; ci++;
+        }
+        if ((rc = drain(prev)) != KMAT_OK) return rc;
+        total_c = c->slot[prev.slot].h_cur[0]; total_l = c->slot[prev.slot].h_cur[1];
+        KM_CUDA(cudaStreamSynchronize(c->st_d2h));
         bool again = false;
-        if (cur[0] > c->cap_cands) { if ((rc = km_grow(&c->d_cands, &c->cap_cands, cur[0])) != KMAT_OK) return rc; again = true; }
-        if (c->opt.want_lineage && cur[1] > c->cap_lin) { if ((rc = km_grow(&c->d_lin, &c->cap_lin, cur[1])) != KMAT_OK) return rc; again = true; }
+        if (total_c > c->cap_cands) { KM_CUDA(cudaStreamSynchronize(c->stream)); if ((rc = km_grow(&c->d_cands, &c->cap_cands, total_c)) != KMAT_OK) return rc; again = true; }
+        if (c->opt.want_lineage && total_l > c->cap_lin) { KM_CUDA(cudaStreamSynchronize(c->stream)); if ((rc = km_grow(&c->d_lin, &c->cap_lin, total_l)) != KMAT_OK) return rc; again = true; }
         if (again) continue;                     // candidate buffer was too small: re-run with the exact size
-        KM_CUDA(cudaMemcpyAsync(c->h_out, c->d_out, (size_t)n_reads * sizeof(kmat_read_result), cudaMemcpyDeviceToHost, st));
-        if (n_cands) *n_cands = cur[0];
-        if (n_lineage) *n_lineage = c->opt.want_lineage ? cur[1] : 0;
-        int ret = KMAT_OK;
-        if (cands) { if (cur[0] <= cands_cap) { if (cur[0]) KM_CUDA(cudaMemcpyAsync(cands, c->d_cands, cur[0] * sizeof(kmat_pair), cudaMemcpyDeviceToHost, st)); } else ret = KMAT_ERR_OVERFLOW; }
-        if (lineage && c->opt.want_lineage) { if (cur[1] <= lineage_cap) { if (cur[1]) KM_CUDA(cudaMemcpyAsync(lineage, c->d_lin, cur[1] * sizeof(kmat_pair), cudaMemcpyDeviceToHost, st)); } else ret = KMAT_ERR_OVERFLOW; }
-        KM_CUDA(cudaStreamSynchronize(st));
-        memcpy(out, c->h_out, (size_t)n_reads * sizeof(kmat_read_result));
-        if (ret == KMAT_ERR_OVERFLOW) kmat_set_error("candidate buffer too small: need %llu pairs", cur[0]);
-        return ret;
+        if (n_cands) *n_cands = total_c;
+        if (n_lineage) *n_lineage = c->opt.want_lineage ? total_l : 0;
+        if ((rc = km_fetch_stats(c, c->stream)) != KMAT_OK) return rc;
+        if ((cands && total_c > cands_cap) || (lineage && c->opt.want_lineage && total_l > lineage_cap)) {
+            kmat_set_error("candidate buffer too small: need %llu candidate and %llu lineage pairs", total_c, total_l);
+            return KMAT_ERR_OVERFLOW;
+        }
+        return KMAT_OK;
     }
     kmat_set_error("candidate buffer kept overflowing");
     return KMAT_ERR_CUDA;
 }
+
+// Page-locked host memory for the buffers handed to kmat_label_batch (optional: pageable buffers work, pinned
+// ones make the copies asynchronous).
+extern "C" void *kmat_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void kmat_host_free(void *p) { if (p) cudaFreeHost(p); }

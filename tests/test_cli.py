@@ -99,7 +99,7 @@ def test_cli_reproduces_reference_run(scen, request, cli, flat_dbs, tmp_path):
     """-t 1: .out, .fastsummary and .nomatchsum byte-identical to the reference's (run_rl.sh option set)."""
     g = request.getfixturevalue(scen)
     ofb = str(tmp_path / "rl_")
-    p = run_cli(cli, ref_args(g, S.OPTION_SETS["run_rl"], flat_dbs[g.name], g.paths["reads"], ofb, 1), env={"LMAT_DIR": g.workdir, "KMAT_BATCH_READS": "100"})
+    p = run_cli(cli, ref_args(g, S.OPTION_SETS["run_rl"], flat_dbs[g.name], g.paths["reads"], ofb, 1), env={"LMAT_DIR": g.workdir, "KMAT_BATCH_READS": "100", "KMAT_CHUNK_READS": "37"})   # 3 pipelined chunks per batch
     assert p.returncode == 0, p.stderr
     assert "Total query time" in p.stdout and "Total reads loaded" in p.stdout
     assert open(ofb + "0.out", encoding="latin-1").read() == g.golden_out("run_rl")
