@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -25,7 +26,8 @@ extern "C" int kmat_device_count(void) {
 // ---------------------------------------------------------------------------------------------
 static int km_choose_bucket_bits(uint64_t n, int kmer_bits) {
     int b = 4;
-    while (((uint64_t)1 << b) * 2 < n) b++;           // load <= 2 keys per 4-slot bucket
+    while (((uint64_t)1 << b) < n) b++;               // <= 1 key per 4-slot bucket on average: ~1.5 % of the home buckets are full
+    if (getenv("KMAT_TEST_TIGHT_TABLE")) b = b > 6 ? b - 2 : 4;   // tests: a nearly full table exercises displacement, the stash and doubling
     if (b < kmer_bits - KM_REM_BITS) b = kmer_bits - KM_REM_BITS;
     if (b > kmer_bits) b = kmer_bits;
     return b;
@@ -46,8 +48,10 @@ extern "C" uint32_t kmat_shard_of(uint64_t kmer, int kmer_length, int shard_coun
 // ---------------------------------------------------------------------------------------------
 // build
 // ---------------------------------------------------------------------------------------------
+#define KM_STASH_CAP 65536u
 __global__ void km_insert_kernel(const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ payload, uint64_t n,
-                                 unsigned long long *slots, uint64_t bucket_mask, int kmer_bits, int rem_bits, int *fail) {
+                                 unsigned long long *slots, uint64_t bucket_mask, int kmer_bits, int rem_bits,
+                                 unsigned int *stash_n, uint64_t *stash_x, uint32_t *stash_hit) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t x = km_mix(kmers[i], kmer_bits);
         const uint64_t home = x >> rem_bits, rem = x & ((1ull << rem_bits) - 1);
@@ -61,7 +65,10 @@ __global__ void km_insert_kernel(const uint64_t *__restrict__ kmers, const uint3
                 if (b[s] == 0ull && atomicCAS(b + s, 0ull, v) == 0ull) done = true;
             }
         }
-        if (!done) atomicExch(fail, 1);
+        if (!done) {                                   // KM_MAX_DISP + 1 full buckets: the key goes to the stash
+            const unsigned int q = atomicAdd(stash_n, 1u);
+            if (q < KM_STASH_CAP) { stash_x[q] = x; stash_hit[q] = pl; }
+        }
     }
 }
 __global__ void km_prefix_bits_kernel(const uint64_t *__restrict__ kmers, uint64_t n, uint32_t *bits, int shift) {
@@ -80,22 +87,39 @@ static int km_db_alloc_and_insert(kmat_db *db, const uint64_t *d_kmers, const ui
         const size_t bytes = db->n_buckets * KM_SLOTS_PER_BUCKET * sizeof(uint64_t);
         KM_CUDA(cudaMalloc((void **)&db->d_slots, bytes));
         KM_CUDA(cudaMemset(db->d_slots, 0, bytes));
-        int *d_fail;
-        KM_CUDA(cudaMalloc((void **)&d_fail, sizeof(int)));
-        KM_CUDA(cudaMemset(d_fail, 0, sizeof(int)));
+        unsigned int *d_sn; uint64_t *d_sx; uint32_t *d_sh;
+        KM_CUDA(cudaMalloc((void **)&d_sn, sizeof(unsigned int)));
+        KM_CUDA(cudaMalloc((void **)&d_sx, (size_t)KM_STASH_CAP * 8)); KM_CUDA(cudaMalloc((void **)&d_sh, (size_t)KM_STASH_CAP * 4));
+        KM_CUDA(cudaMemset(d_sn, 0, sizeof(unsigned int)));
         if (n) {
             const int threads = 256;
             const int blocks = (int)std::min<uint64_t>((n + threads - 1) / threads, 148ull * 16);
             km_insert_kernel<<<blocks, threads>>>(d_kmers, d_payload, n, (unsigned long long *)db->d_slots, db->n_buckets - 1,
-                                                  kmer_bits, db->geom.rem_bits, d_fail);
+                                                  kmer_bits, db->geom.rem_bits, d_sn, d_sx, d_sh);
             g_km_launches++;
             KM_CUDA(cudaGetLastError());
         }
-        int fail = 0;
-        KM_CUDA(cudaMemcpy(&fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost));
-        cudaFree(d_fail);
-        if (!fail) break;
-        cudaFree(db->d_slots); db->d_slots = nullptr;       // a key was displaced > KM_MAX_DISP buckets: double the table
+        unsigned int sn = 0;
+        KM_CUDA(cudaMemcpy(&sn, d_sn, sizeof sn, cudaMemcpyDeviceToHost));
+        if (sn <= KM_STASH_CAP) {
+            // the stash: sorted by mixed key on the host (a few hundred entries at most), searched by km_probe_x
+            if (sn) {
+                std::vector<uint64_t> sx(sn); std::vector<uint32_t> sh(sn), ord(sn);
+                KM_CUDA(cudaMemcpy(sx.data(), d_sx, (size_t)sn * 8, cudaMemcpyDeviceToHost));
+                KM_CUDA(cudaMemcpy(sh.data(), d_sh, (size_t)sn * 4, cudaMemcpyDeviceToHost));
+                for (unsigned int i = 0; i < sn; i++) ord[i] = i;
+                std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b2) { return sx[a] < sx[b2]; });
+                std::vector<uint64_t> sx2(sn); std::vector<uint32_t> sh2(sn);
+                for (unsigned int i = 0; i < sn; i++) { sx2[i] = sx[ord[i]]; sh2[i] = sh[ord[i]]; }
+                KM_CUDA(cudaMalloc((void **)&db->d_stash_x, (size_t)sn * 8)); KM_CUDA(cudaMalloc((void **)&db->d_stash_hit, (size_t)sn * 4));
+                KM_CUDA(cudaMemcpy(db->d_stash_x, sx2.data(), (size_t)sn * 8, cudaMemcpyHostToDevice));
+                KM_CUDA(cudaMemcpy(db->d_stash_hit, sh2.data(), (size_t)sn * 4, cudaMemcpyHostToDevice));
+            }
+            db->n_stash = sn;
+        }
+        cudaFree(d_sn); cudaFree(d_sx); cudaFree(d_sh);
+        if (sn <= KM_STASH_CAP) break;
+        cudaFree(db->d_slots); db->d_slots = nullptr;       // too many displaced keys for the stash: double the table
     }
     // bitmap of the reference's non-empty top-tier prefixes: only used to count "prefix miss" lookups exactly
     // for the algorithmic-bytes statistic; 2^27 bits = 16 MiB
@@ -122,6 +146,7 @@ KmDbDev km_db_dev(const kmat_db *db) {
     d.slots = db->d_slots; d.bucket_mask = db->n_buckets - 1; d.kmer_bits = db->geom.kmer_bits; d.rem_bits = db->geom.rem_bits;
     d.kmer_len = db->kmer_len; d.tid_bytes = db->tid_bytes; d.pool = db->d_pool; d.prefix_bits = db->d_prefix_bits;
     d.prefix_shift = db->prefix_shift;
+    d.stash_x = db->d_stash_x; d.stash_hit = db->d_stash_hit; d.n_stash = db->n_stash;
     return d;
 }
 
@@ -204,13 +229,13 @@ extern "C" int kmat_db_upload(const kmat_table *t, int device, int shard_index, 
 }
 
 extern "C" uint64_t kmat_db_size(const kmat_db *db) { return db ? db->n_kmers : 0; }
-extern "C" uint64_t kmat_db_bytes(const kmat_db *db) { return db ? db->n_buckets * 32 + db->pool_words * 4 + db->prefix_bytes : 0; }
+extern "C" uint64_t kmat_db_bytes(const kmat_db *db) { return db ? db->n_buckets * 32 + db->pool_words * 4 + db->prefix_bytes + (uint64_t)db->n_stash * 12 : 0; }
 extern "C" int kmat_db_kmer_length(const kmat_db *db) { return db ? db->kmer_len : 0; }
 extern "C" int kmat_db_device(const kmat_db *db) { return db ? db->device : -1; }
 extern "C" void kmat_db_free(kmat_db *db) {
     if (!db) return;
     cudaSetDevice(db->device);
-    cudaFree(db->d_slots); cudaFree(db->d_pool); cudaFree(db->d_prefix_bits);
+    cudaFree(db->d_slots); cudaFree(db->d_pool); cudaFree(db->d_prefix_bits); cudaFree(db->d_stash_x); cudaFree(db->d_stash_hit);
     delete db;
 }
 
@@ -304,14 +329,17 @@ struct KmProbeParams {
 };
 
 __device__ __forceinline__ int km_code(unsigned char ch) {
-    // ENCODE macro, read_label.cpp:943-950: a/A 0, c/C 1, g/G 2, t/T 3, anything else resets
-    switch (ch) {
-        case 'a': case 'A': return 0;
-        case 'c': case 'C': return 1;
-        case 'g': case 'G': return 2;
-        case 't': case 'T': return 3;
-        default: return -1;
-    }
+    // ENCODE macro, read_label.cpp:943-950: a/A 0, c/C 1, g/G 2, t/T 3, anything else resets (-1).  Branch-free:
+    // letters live in 0x40..0x7F and (ch & 31) is 1, 3, 7, 20 for A, C, G, T in either case; bits 2:1 of the ASCII
+    // code are 00, 01, 11, 10 for A, C, G, T, which x ^ (x >> 1) turns into 0, 1, 2, 3.
+    const uint32_t c = ch;
+    const bool ok = (c & 0xC0u) == 0x40u && ((0x0010008Au >> (c & 31u)) & 1u);
+    const uint32_t x = (c >> 1) & 3u;
+    return ok ? (int)(x ^ (x >> 1)) : -1;
+}
+__device__ __forceinline__ uint64_t kb_shfl_u64(uint64_t v, int src) {
+    const uint32_t lo = __shfl_sync(KM_FULL, (uint32_t)v, src), hi = __shfl_sync(KM_FULL, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
 }
 __device__ __forceinline__ uint64_t km_revcomp(uint64_t fwd, int kmer_bits) {
     uint64_t x = ~fwd << (64 - kmer_bits);            // complement; k-mer now left-aligned
@@ -447,14 +475,218 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32) km_encode_probe_kernel(Km
     }
 }
 
-int km_launch_encode_probe(const kmat_db *db, const char *d_bases, const uint64_t *d_offs, uint32_t n_reads, uint32_t *d_hit,
-                           int2 *d_hdr, uint64_t *d_kmers, uint8_t *d_flags, unsigned long long *d_long_sets, uint32_t long_slots,
-                           int grid, KmStatsDev *d_stats, int do_probe, cudaStream_t stream) {
+// ---------------------------------------------------------------------------------------------
+// K1 + K2 for short reads (the Illumina case): variant of the kernel above for batches whose reads have at most
+// 32 * NCH bases (NCH <= 8) and k <= 24.  Same results; what changes is how many table requests are in flight.
+// Measured on B200 (profiles/r01_probe_kernel_notes.md): uniform random table reads are limited to ~37 G requests/s
+// chip-wide whatever their width (and a second request to the same sector costs as much as the first), so the
+// kernel must (a) issue exactly one 32-byte request per lookup and (b) keep enough of them in flight.
+//   * the bases of the warp's NEXT read (and the offsets of the one after) are loaded while the current one is
+//     processed, so no iteration starts with an exposed global load;
+//   * all NCH chunks are encoded and deduplicated first; then every lane issues the home-bucket gather (one
+//     LDG.E.256) of ALL its first-occurrence k-mers back to back and only then looks at the first one: NCH
+//     independent gathers per lane, 32 * NCH per warp, instead of one per chunk.  That costs 8 registers per
+//     gather (2 CTAs of 8 warps per SM at ~100 registers) and is what lifts the kernel from 25 to 34.5 G lookups/s;
+//   * dedup without a hash set: duplicates inside a read are rare, so every valid k-mer sets one bit of a per-warp
+//     bitmap (atomicOr on shared memory, SETN bits hashed from the mixed k-mer).  Whoever finds its bit clear is the
+//     first k-mer with that hash; the few that find it set (a real duplicate or a hash collision) are "suspects"
+//     and are settled exactly, one at a time and warp-wide: the suspect's k-mer is broadcast, every lane compares
+//     it with its own NCH k-mers, an equal k-mer at a lower position makes the suspect a duplicate, and equal
+//     k-mers at higher positions are marked duplicates themselves.  The outcome is "the lowest position of every
+//     distinct k-mer survives" (read_label.cpp:1010-1017) whatever order the atomics were served in.  Keys are the
+//     mixed k-mers (km_mix is a bijection), which the probe needs anyway;
+//   * the home bucket answers ~98.5 % of the lookups; a full home bucket continues with km_probe_x(d = 1).
+// Dynamic shared memory per warp: SETN / 8 B dedup bitmap.
+// ---------------------------------------------------------------------------------------------
+#ifndef KM_FAST_CTAS
+#define KM_FAST_CTAS 2
+#endif
+template <int NCH, int SETN, bool STATS>
+__global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS : 1) km_encode_probe_fast_kernel(KmProbeParams P) {
+    extern __shared__ __align__(16) unsigned char km_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t *bitmap = (uint32_t *)(km_smem + (size_t)wib * (SETN / 8));
+    const uint64_t warp_global = blockIdx.x * KM_PROBE_WARPS + wib, n_warps = gridDim.x * KM_PROBE_WARPS;
+    const int k = P.db.kmer_len, kmer_bits = P.db.kmer_bits;
+    const uint64_t kmask = (1ull << kmer_bits) - 1;
+    for (int i = lane; i < SETN / 32; i += 32) bitmap[i] = 0;
+    unsigned long long st_lookups = 0, st_hits = 0, st_lists = 0, st_extra = 0, st_pmiss = 0;
+    __syncwarp();
+
+    const uint64_t n = P.n_reads;
+    uint64_t r = warp_global;
+    uint64_t offA = 0, offB = 0; int lenA = 0, lenB = 0;          // read r (A) and read r + n_warps (B)
+    if (r < n) { offA = P.offs[r]; lenA = (int)(P.offs[r + 1] - offA); }
+    if (r + n_warps < n) { offB = P.offs[r + n_warps]; lenB = (int)(P.offs[r + n_warps + 1] - offB); }
+    unsigned char raw[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) { const int j = (c << 5) + lane; raw[c] = j < lenA ? (unsigned char)P.bases[offA + j] : (unsigned char)0; }
+
+    for (; r < n; r += n_warps) {
+        const uint64_t off = offA; const int len = lenA;
+        int code[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; c++) code[c] = km_code(raw[c]);
+        // ---- next read's bases, and the offsets of the one after it: in flight during this iteration
+        offA = offB; lenA = lenB;
+#pragma unroll
+        for (int c = 0; c < NCH; c++) { const int j = (c << 5) + lane; raw[c] = j < lenA ? (unsigned char)P.bases[offA + j] : (unsigned char)0; }
+        { const uint64_t r2 = r + 2 * n_warps; lenB = 0; if (r2 < n) { offB = P.offs[r2]; lenB = (int)(P.offs[r2 + 1] - offB); } }
+
+        // ---- encode every chunk (read_label.cpp:943-950, 978-1009, GC bookkeeping :994-1008); start the bucket gathers
+        uint64_t xk[NCH];                  // mixed canonical k-mer ending at base j = 32 c + lane
+        uint64_t canon_s[STATS ? NCH : 1];
+        uint32_t okbits = 0;
+        uint64_t prev = 0; uint32_t pinv = 0xFFFFFFFFu, pgc = 0;
+        int valid = 0, vgc = 0, vtot = 0;
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const uint32_t cinv = __ballot_sync(KM_FULL, code[c] < 0);
+            const uint32_t cgc = __ballot_sync(KM_FULL, code[c] == 1 || code[c] == 2);
+            const uint32_t cc = code[c] < 0 ? 0u : (uint32_t)code[c];
+            const uint32_t hi = __reduce_or_sync(KM_FULL, lane < 16 ? cc << (30 - 2 * lane) : 0u);
+            const uint32_t lo = __reduce_or_sync(KM_FULL, lane >= 16 ? cc << (62 - 2 * lane) : 0u);
+            const uint64_t cur = ((uint64_t)hi << 32) | lo;
+            const int s = 62 - 2 * lane;
+            const uint64_t fwd = ((cur >> s) | (s ? (prev << (64 - s)) : 0ull)) & kmask;
+            const uint64_t inv64 = ((uint64_t)cinv << 32) | pinv, gc64 = ((uint64_t)cgc << 32) | pgc;
+            const uint64_t wmask = (1ull << k) - 1;
+            const int wsh = 32 + lane - k + 1;
+            const bool ok = ((inv64 >> wsh) & wmask) == 0;
+            const bool ok_prev = wsh > 0 && ((inv64 >> (wsh - 1)) & wmask) == 0;
+            xk[c] = 0;
+            if (STATS) canon_s[c] = 0;
+            if (ok) {
+                const uint64_t rc = km_revcomp(fwd, kmer_bits);
+                const uint64_t canon = fwd < rc ? fwd : rc;                    // read_label.cpp:1009
+                xk[c] = km_mix(canon, kmer_bits);
+                if (STATS) canon_s[c] = canon;
+                okbits |= 1u << c;
+            }
+            const int add_tot = ok ? (ok_prev ? 1 : k) : 0;
+            const int add_gc = ok ? (ok_prev ? (int)((cgc >> lane) & 1) : __popcll((gc64 >> wsh) & wmask)) : 0;
+            valid += ok; vtot += add_tot; vgc += add_gc;
+            prev = cur; pinv = cinv; pgc = cgc;
+        }
+        // ---- dedup: the lowest position of every distinct k-mer wins
+        uint32_t first = 0, suspect = 0;       // per chunk bits of this lane
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            if ((okbits >> c) & 1) {
+                const uint32_t h = (uint32_t)(xk[c] >> 7) & (SETN - 1);
+                const uint32_t old = atomicOr(bitmap + (h >> 5), 1u << (h & 31));
+                if ((old >> (h & 31)) & 1) suspect |= 1u << c; else first |= 1u << c;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            uint32_t pend = __ballot_sync(KM_FULL, (suspect >> c) & 1);
+            while (pend) {                                        // rare: ~ (k-mers per read)^2 / (2 SETN) suspects per read
+                const int src = __ffs(pend) - 1;
+                pend &= pend - 1;
+                const uint64_t key = kb_shfl_u64(xk[c], src);
+                const int ps = (c << 5) + src;                    // the suspect's position index (base index of its last base)
+                bool lower = false;
+#pragma unroll
+                for (int c2 = 0; c2 < NCH; c2++) {
+                    if (((okbits >> c2) & 1) && xk[c2] == key) {
+                        const int pq = (c2 << 5) + lane;
+                        if (pq < ps) lower = true;
+                        else if (pq > ps) first &= ~(1u << c2);    // a later copy of the suspect's k-mer is never the first
+                    }
+                }
+                const bool dup = __any_sync(KM_FULL, lower);
+                if (lane == src && !dup) first |= 1u << c;
+            }
+        }
+        // the words this lane touched go back to zero for the next read (every set bit lies in such a word)
+#pragma unroll
+        for (int c = 0; c < NCH; c++) if ((okbits >> c) & 1) bitmap[((uint32_t)(xk[c] >> 7) & (SETN - 1)) >> 5] = 0;
+        // ---- probe the first occurrences: every home-bucket gather of the read is issued before the first one is
+        //      looked at (NCH independent LDG.256 per lane in flight), then one hit word per k-mer start position
+        uint64_t bk[NCH][4];
+        if (P.do_probe) {
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                bk[c][0] = bk[c][1] = bk[c][2] = bk[c][3] = 0;
+                if ((first >> c) & 1)
+                    km_load_bucket(P.db.slots + ((xk[c] >> P.db.rem_bits) & P.db.bucket_mask) * KM_SLOTS_PER_BUCKET, bk[c][0], bk[c][1], bk[c][2], bk[c][3]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const int j = (c << 5) + lane, p = j - k + 1;
+            uint32_t hw = KM_HIT_INVALID;
+            if ((first >> c) & 1) {
+                hw = KM_HIT_MISS;
+                if (P.do_probe) {
+                    uint32_t extra = 0;
+                    if (km_bucket_match(bk[c][0], bk[c][1], bk[c][2], bk[c][3], xk[c] & ((1ull << P.db.rem_bits) - 1), 0, hw) == 2) {
+                        hw = km_probe_x(P.db, xk[c], extra, 1);
+                        extra++;
+                    }
+                    if (STATS) {
+                        st_lookups++; st_extra += extra;
+                        if (hw != KM_HIT_MISS) { st_hits++; if (hw & KM_HIT_LIST) st_lists++; }
+                        else if (P.db.prefix_bits) {
+                            const uint64_t pf = canon_s[c] >> P.db.prefix_shift;
+                            if (!((P.db.prefix_bits[pf >> 5] >> (pf & 31)) & 1)) st_pmiss++;
+                        }
+                    }
+                }
+            }
+            if (p >= 0 && j < len) P.hit[off + p] = hw;
+        }
+        valid = km_warp_sum(valid); vgc = km_warp_sum(vgc); vtot = km_warp_sum(vtot);
+        if (lane == 0) {
+            const float frac = __fdiv_rn((float)vgc, (float)vtot);                         // :1205-1206
+            const float gc_pcnt = __double2float_rn(__dmul_rn((double)frac, 100.0));
+            const float q = __fdiv_rn(gc_pcnt, 10.0f);
+            P.hdr[r] = make_int2(valid, vtot > 0 ? (int)q : 0);
+        }
+        __syncwarp();                      // the bitmap is clean again before the next read's atomics
+    }
+    if (STATS) {
+        st_lookups = km_warp_sum((int)st_lookups); st_hits = km_warp_sum((int)st_hits); st_lists = km_warp_sum((int)st_lists);
+        st_extra = km_warp_sum((int)st_extra); st_pmiss = km_warp_sum((int)st_pmiss);
+        if (lane == 0) {
+            atomicAdd(&P.stats->lookups, st_lookups); atomicAdd(&P.stats->hits, st_hits); atomicAdd(&P.stats->list_hits, st_lists);
+            atomicAdd(&P.stats->extra_buckets, st_extra); atomicAdd(&P.stats->prefix_miss, st_pmiss);
+        }
+    }
+}
+
+template <int NCH, int SETN, bool STATS>
+static int km_launch_fast(const KmProbeParams &P, int grid, cudaStream_t stream) {
+    const int smem = KM_PROBE_WARPS * (SETN / 8);
+    static int resident = 0;               // per instantiation: CTAs that fit the device at once (persistent grid)
+    if (!resident) {
+        KM_CUDA(cudaFuncSetAttribute(km_encode_probe_fast_kernel<NCH, SETN, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        KM_CUDA(cudaFuncSetAttribute(km_encode_probe_fast_kernel<NCH, SETN, STATS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int per_sm = 0, dev = 0, sms = 148;
+        KM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_encode_probe_fast_kernel<NCH, SETN, STATS>, KM_PROBE_WARPS * 32, smem));
+        cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        resident = std::max(1, per_sm) * sms;
+    }
+    const uint32_t want = (P.n_reads + KM_PROBE_WARPS - 1) / KM_PROBE_WARPS;
+    grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(want, (uint32_t)resident));
+    km_encode_probe_fast_kernel<NCH, SETN, STATS><<<grid, KM_PROBE_WARPS * 32, smem, stream>>>(P);
+    return KMAT_OK;
+}
+
+int km_launch_encode_probe(const kmat_db *db, const char *d_bases, const uint64_t *d_offs, uint32_t n_reads, uint32_t max_len,
+                           uint32_t *d_hit, int2 *d_hdr, uint64_t *d_kmers, uint8_t *d_flags, unsigned long long *d_long_sets,
+                           uint32_t long_slots, int grid, KmStatsDev *d_stats, int do_probe, cudaStream_t stream) {
     KmProbeParams P;
     P.db = km_db_dev(db); P.bases = d_bases; P.offs = d_offs; P.n_reads = n_reads; P.hit = d_hit; P.hdr = d_hdr;
     P.out_kmers = d_kmers; P.out_flags = d_flags; P.long_sets = d_long_sets; P.long_slots = long_slots; P.stats = d_stats;
     P.do_probe = do_probe;
-    km_encode_probe_kernel<<<grid, KM_PROBE_WARPS * 32, 0, stream>>>(P);
+    const bool fast = !d_kmers && !d_flags && max_len <= 256 && db->kmer_len <= 24 && !getenv("KMAT_NO_FAST_PROBE");
+    int rc = KMAT_OK;
+    if (fast && max_len <= 160) rc = d_stats ? km_launch_fast<5, 4096, true>(P, grid, stream) : km_launch_fast<5, 4096, false>(P, grid, stream);
+    else if (fast) rc = d_stats ? km_launch_fast<8, 8192, true>(P, grid, stream) : km_launch_fast<8, 8192, false>(P, grid, stream);
+    else km_encode_probe_kernel<<<grid, KM_PROBE_WARPS * 32, 0, stream>>>(P);
+    if (rc != KMAT_OK) return rc;
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     return KMAT_OK;
@@ -487,7 +719,7 @@ extern "C" int kmat_encode_batch(const kmat_db *db, const char *bases, const uin
         long_slots = 1024; while (long_slots < 2 * max_np) long_slots <<= 1;
         KM_CUDA(cudaMalloc((void **)&d_long, (size_t)grid * KM_PROBE_WARPS * long_slots * 8));
     }
-    int rc = km_launch_encode_probe(db, d_b, d_o, n_reads, d_hit, d_hdr, d_k, d_f, d_long, long_slots, grid, nullptr, 0, 0);
+    int rc = km_launch_encode_probe(db, d_b, d_o, n_reads, max_np, d_hit, d_hdr, d_k, d_f, d_long, long_slots, grid, nullptr, 0, 0);
     if (rc == KMAT_OK) {
         std::vector<int2> hdr(n_reads);
         KM_CUDA(cudaMemcpy(hdr.data(), d_hdr, (size_t)n_reads * sizeof(int2), cudaMemcpyDeviceToHost));

@@ -21,6 +21,9 @@ struct KmDbDev {
     const uint32_t *pool;         // list pool, 4-byte words
     const uint32_t *prefix_bits;  // bitmap over the reference's top-tier prefixes (stats only), may be null
     int prefix_shift;             // BITS_PER_2ND of the reference layout (13 for k=20, 9 for k=18)
+    const uint64_t *stash_x;      // overflow stash: mixed keys (km_mix) of the few k-mers whose KM_MAX_DISP+1 buckets were
+    const uint32_t *stash_hit;    //   all full at build time, ascending, and their hit words; searched only after 4 full buckets
+    uint32_t n_stash;
 };
 
 struct KmStatsDev {
@@ -33,28 +36,47 @@ __device__ __forceinline__ void km_load_bucket(const uint64_t *p, uint64_t &a, u
     asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 }
 
-// Probe: returns the hit word.  extra = number of additional buckets visited (linear probing past a full bucket).
-__device__ __forceinline__ uint32_t km_probe(const KmDbDev &db, uint64_t kmer, uint32_t &extra) {
-    const uint64_t x = km_mix(kmer, db.kmer_bits);
+// One bucket of the probe sequence against (rem, displacement d): 0 = found (hw set), 1 = absent for good (a free
+// slot: the key cannot have been displaced further), 2 = bucket full, look at the next one.
+__device__ __forceinline__ int km_bucket_match(uint64_t s0, uint64_t s1, uint64_t s2, uint64_t s3, uint64_t rem, int d, uint32_t &hw) {
+    const uint64_t want = (1ull << 63) | ((uint64_t)d << 60) | (rem << 32);
+    const uint64_t keymask = ~((1ull << 62) | 0xFFFFFFFFull);
+    uint64_t hit = 0;
+    if ((s0 & keymask) == want) hit = s0;
+    if ((s1 & keymask) == want) hit = s1;
+    if ((s2 & keymask) == want) hit = s2;
+    if ((s3 & keymask) == want) hit = s3;
+    if (hit) { hw = (uint32_t)hit | (((hit >> 62) & 1) ? KM_HIT_LIST : 0u); return 0; }
+    hw = KM_HIT_MISS;
+    return (s0 && s1 && s2 && s3) ? 2 : 1;
+}
+
+// Probe with the mixed key x = km_mix(kmer), starting at displacement d0: returns the hit word.  extra = number of
+// additional buckets visited (linear probing past a full bucket).
+__device__ __forceinline__ uint32_t km_probe_x(const KmDbDev &db, uint64_t x, uint32_t &extra, int d0 = 0) {
     const uint64_t home = x >> db.rem_bits;
     const uint64_t rem = x & ((1ull << db.rem_bits) - 1);
     extra = 0;
 #pragma unroll 1
-    for (int d = 0; d <= KM_MAX_DISP; d++) {
+    for (int d = d0; d <= KM_MAX_DISP; d++) {
         uint64_t s0, s1, s2, s3;
         km_load_bucket(db.slots + ((home + d) & db.bucket_mask) * KM_SLOTS_PER_BUCKET, s0, s1, s2, s3);
-        const uint64_t want = (1ull << 63) | ((uint64_t)d << 60) | (rem << 32);
-        const uint64_t keymask = ~((1ull << 62) | 0xFFFFFFFFull);
-        uint64_t hit = 0;
-        if ((s0 & keymask) == want) hit = s0;
-        if ((s1 & keymask) == want) hit = s1;
-        if ((s2 & keymask) == want) hit = s2;
-        if ((s3 & keymask) == want) hit = s3;
-        if (hit) return (uint32_t)hit | (((hit >> 62) & 1) ? KM_HIT_LIST : 0u);
-        if (!(s0 && s1 && s2 && s3)) return KM_HIT_MISS;   // a free slot: the key cannot have been displaced further
+        uint32_t hw;
+        if (km_bucket_match(s0, s1, s2, s3, rem, d, hw) != 2) return hw;
         extra++;
     }
+    // every bucket of the probe window is full: the key, if present, sits in the stash
+    uint32_t lo = 0, hi = db.n_stash;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const uint64_t v = db.stash_x[mid];
+        if (v == x) return db.stash_hit[mid];
+        if (v < x) lo = mid + 1; else hi = mid;
+    }
     return KM_HIT_MISS;
+}
+__device__ __forceinline__ uint32_t km_probe(const KmDbDev &db, uint64_t kmer, uint32_t &extra) {
+    return km_probe_x(db, km_mix(kmer, db.kmer_bits), extra);
 }
 
 __device__ __forceinline__ int km_warp_sum(int v) { return __reduce_add_sync(KM_FULL, v); }

@@ -184,7 +184,7 @@ __device__ void kr_resolve_list(const KmCtxDev &C, uint32_t lo, uint2 *scratch, 
 struct KmResolveParams {
     KmCtxDev C;
     uint32_t *pool2;
-    unsigned long long n_slots;
+    unsigned long long n_slots, n_table_slots;   // n_slots = table slots + stash entries
     uint32_t *big_queue; uint32_t big_cap;       // pool offsets of the lists left to the big pass
     unsigned int *counters;                      // [0] lists queued, [1] longest list (entries), [2] lists seen
     uint2 *scratch; uint32_t scratch_entries;    // big pass: per-thread scratch
@@ -194,9 +194,16 @@ __global__ void __launch_bounds__(256) km_resolve_kernel(KmResolveParams R) {
     const KmCtxDev &C = R.C;
     uint2 local[2 * KB_LFAST];
     for (unsigned long long s = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; s < R.n_slots; s += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint64_t v = C.db.slots[s];
-        if (!(v >> 63) || !((v >> 62) & 1)) continue;
-        const uint32_t lo = (uint32_t)v & 0x7FFFFFFFu;
+        uint32_t lo;
+        if (s < R.n_table_slots) {
+            const uint64_t v = C.db.slots[s];
+            if (!(v >> 63) || !((v >> 62) & 1)) continue;
+            lo = (uint32_t)v & 0x7FFFFFFFu;
+        } else {                                          // the overflow stash holds hit words
+            const uint32_t hw = C.db.stash_hit[s - R.n_table_slots];
+            if (!(hw & KM_HIT_LIST)) continue;
+            lo = hw & 0x7FFFFFFFu;
+        }
         const uint32_t count = kb_list_count(C.db, lo);
         atomicMax(&R.counters[1], count);
         atomicAdd(&R.counters[2], 1u);
@@ -796,7 +803,8 @@ static int km_resolve_lists(kmat_ctx *c) {
     KmResolveParams R;
     R.C = km_ctx_dev(c);
     R.pool2 = c->d_pool2;
-    R.n_slots = db->n_buckets * KM_SLOTS_PER_BUCKET;
+    R.n_table_slots = db->n_buckets * KM_SLOTS_PER_BUCKET;
+    R.n_slots = R.n_table_slots + db->n_stash;
     R.big_cap = (uint32_t)(db->pool_words / 9 + 16);         // a list of > KB_LFAST 16-bit ids occupies >= 9 pool words
     R.scratch = nullptr; R.scratch_entries = 0;
     KM_CUDA(cudaMalloc((void **)&R.big_queue, (size_t)R.big_cap * 4));
@@ -945,7 +953,7 @@ static int km_run_device(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
     }
     uint32_t *hit = c->d_hit - L.first_off;
     KM_CUDA(cudaEventRecord(c->ev[0], st));
-    rc = km_launch_encode_probe(c->db, L.d_bases, L.d_offs, L.n_reads, hit, c->d_hdr, nullptr, nullptr, c->d_long_sets, c->long_slots,
+    rc = km_launch_encode_probe(c->db, L.d_bases, L.d_offs, L.n_reads, L.max_len, hit, c->d_hdr, nullptr, nullptr, c->d_long_sets, c->long_slots,
                                 pgrid, c->collect_stats ? c->d_stats : nullptr, 1, st);
     if (rc != KMAT_OK) return rc;
     KM_CUDA(cudaEventRecord(c->ev[1], st));

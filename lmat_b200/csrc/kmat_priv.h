@@ -28,6 +28,7 @@ struct kmat_db {
     uint64_t *d_slots = nullptr;
     uint32_t *d_pool = nullptr;
     uint32_t *d_prefix_bits = nullptr;
+    uint64_t *d_stash_x = nullptr; uint32_t *d_stash_hit = nullptr; uint32_t n_stash = 0;   // overflow stash (see km_probe_x)
     int prefix_shift = 13;
     uint32_t n_sid = 65536;
     std::vector<uint32_t> stored_tids;     // 32-bit tables: dense stored id -> tid
@@ -37,8 +38,8 @@ struct KmDbDev;
 struct KmStatsDev;
 KmDbDev km_db_dev(const kmat_db *db);
 int km_probe_grid(uint32_t n_reads);
-int km_launch_encode_probe(const kmat_db *db, const char *d_bases, const uint64_t *d_offs, uint32_t n_reads, uint32_t *d_hit,
-                           int2 *d_hdr, uint64_t *d_kmers, uint8_t *d_flags, unsigned long long *d_long_sets, uint32_t long_slots,
-                           int grid, KmStatsDev *d_stats, int do_probe, cudaStream_t stream);
+int km_launch_encode_probe(const kmat_db *db, const char *d_bases, const uint64_t *d_offs, uint32_t n_reads, uint32_t max_len,
+                           uint32_t *d_hit, int2 *d_hdr, uint64_t *d_kmers, uint8_t *d_flags, unsigned long long *d_long_sets,
+                           uint32_t long_slots, int grid, KmStatsDev *d_stats, int do_probe, cudaStream_t stream);
 #define KM_PROBE_WARPS_HOST 8
 #endif

@@ -151,3 +151,67 @@ def test_long_and_ragged_reads_match_oracle(golden_lists, dbs, opts):
     mine = ctx.tails(res[~unsupported], cands, lin, prn_all=True)
     want = [t for t, u in zip(orc.tails(ores), unsupported) if not u]
     assert mine == want
+
+
+def _sample_reads(g, workdir, lengths, seed, reps=4):
+    inp = S.build_inputs("lists", workdir)
+    rng = np.random.default_rng(seed)
+    names = list(inp["genomes"])
+    seqs = []
+    for L in lengths:
+        for rep in range(reps):
+            gsel = fx.codes_to_str(inp["genomes"][names[int(rng.integers(0, len(names)))]])
+            a = int(rng.integers(0, max(1, len(gsel) - 400)))
+            s = gsel[a:a + L]
+            if L > 60 and rep == 1:
+                s = s[:40] + "N" + s[41:]
+            if L > 60 and rep == 2:
+                s = (s[:L // 2] + s[:L // 2])[:L]          # repeated half: duplicate k-mers across chunks
+            if rep == 3:
+                s = s.lower()
+            seqs.append(s)
+    return seqs
+
+
+@pytest.mark.parametrize("lengths", [[0, 5, 19, 20, 21, 52, 100, 150, 159, 160], [30, 161, 200, 255, 256]], ids=["nch5", "nch8"])
+@pytest.mark.parametrize("variant", ["fast", "streaming"])
+def test_short_read_probe_kernels_match_oracle(golden_lists, dbs, lengths, variant, monkeypatch):
+    """The register-resident encode+probe kernel (<= 160 / <= 256 bases) and the streaming one give the oracle's lines."""
+    g = golden_lists
+    if variant == "streaming":
+        monkeypatch.setenv("KMAT_NO_FAST_PROBE", "1")
+    seqs = _sample_reads(g, g.workdir + f"/short_{max(lengths)}_{variant}", lengths, 5)
+    ctx = make_ctx(g, dbs[g.name], "run_rl")
+    orc = oracle_for(g, "run_rl")
+    res, cands, lin = ctx.label(seqs)
+    ores, _, _ = orc.label(seqs)
+    assert (res["status"] != 6).all()
+    assert np.array_equal(res["valid_kmers"], ores["valid_kmers"])
+    assert ctx.tails(res, cands, lin, prn_all=True) == orc.tails(ores)
+    st = ctx.stats()
+    assert st.lookups > 0 and st.hits > 0
+
+
+def test_tight_table_uses_displacement_and_stash(golden_lists, monkeypatch):
+    """A nearly full table (test knob) pushes keys through every displacement and into the overflow stash: lookups
+    and labels must not change."""
+    g = golden_lists
+    t = api.Table.from_arrays(g.kmers, g.offs, g.ids, g.kmer_len, g.tid_bytes)
+    roomy = api.Db.upload(t)
+    monkeypatch.setenv("KMAT_TEST_TIGHT_TABLE", "1")
+    tight = api.Db.upload(t)
+    monkeypatch.delenv("KMAT_TEST_TIGHT_TABLE")
+    assert tight.bytes < roomy.bytes
+    rng = np.random.default_rng(9)
+    q = np.concatenate([g.kmers, rng.integers(0, 1 << 40, 50000, dtype=np.uint64)])
+    a_offs, a_ids = roomy.lookup(q)
+    b_offs, b_ids = tight.lookup(q)
+    assert np.array_equal(a_offs, b_offs) and np.array_equal(a_ids, b_ids)
+    n = len(g.kmers)
+    assert np.array_equal(b_offs[:n + 1], g.offs) and np.array_equal(b_ids[:int(g.offs[-1])], g.ids)
+    ctx = make_ctx(g, tight, "run_rl")
+    hdrs, seqs = op.read_fasta_like_reference(g.paths["reads"])
+    res, cands, lin = ctx.label(seqs)
+    mine = op.assemble_lines(hdrs, seqs, ctx.tails(res, cands, lin, prn_all=True))
+    assert mine == g.golden_out("run_rl")
+    assert ctx.stats().probe_extra_buckets > 0
