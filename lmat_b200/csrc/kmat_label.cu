@@ -258,13 +258,23 @@ __device__ __forceinline__ int kb_find_or_add(KbCand &K, int &C, uint32_t v, int
 
 // One chunk of 32 positions (lane = position): insert the members of every position into the candidate set and
 // return this lane's position mask.  All lanes of the warp call it together.
-__device__ __forceinline__ unsigned long long kb_chunk(const KmScoreParams &P, KbCand &K, int &C, int c, uint64_t off, int np, int lane,
+// the two dependent loads of a position, split off so that a caller can issue them for every chunk of a read up front:
+// the hit word, and then the word it points at (stored id -> node entry for a singleton, record header for a list)
+__device__ __forceinline__ uint32_t kb_load_hit(const KmScoreParams &P, int c, uint64_t off, int np, int lane) {
+    const int p = (c << 5) + lane;
+    return p < np ? __ldg(P.hit + off + p) : KM_HIT_INVALID;
+}
+__device__ __forceinline__ uint32_t kb_load_aux(const KmCtxDev &X, uint32_t hw) {
+    if (hw == KM_HIT_INVALID || hw == KM_HIT_MISS) return 0;
+    if (!(hw & KM_HIT_LIST)) return hw < X.n_sid ? __ldg(X.sid2nid + hw) : KMAT_NONE;
+    return __ldg(X.pool2 + (size_t)(hw & 0x7FFFFFFFu) * X.pool2_mul);
+}
+
+__device__ __forceinline__ unsigned long long kb_chunk(const KmScoreParams &P, KbCand &K, int &C, int c, uint32_t hw, uint32_t aux, int lane,
                                                         int &cand_cnt, int &fnd_cnt, int &err, bool &overflow,
                                                         unsigned long long &st_list_ids, unsigned long long &st_list_sectors) {
     const KmCtxDev &X = P.C;
     const bool permissive = X.opt.permissive != 0;
-    const int p = (c << 5) + lane;
-    const uint32_t hw = p < np ? __ldg(P.hit + off + p) : KM_HIT_INVALID;
     // member iterator state: `a` ids first (a single id in v0, or a resolved record at rec), then (permissive) the
     // root paths of `b` ids
     uint32_t a = 0, b = 0, v0 = KMAT_NONE;
@@ -274,7 +284,7 @@ __device__ __forceinline__ unsigned long long kb_chunk(const KmScoreParams &P, K
         if (hw != KM_HIT_MISS) {
             if (!(hw & KM_HIT_LIST)) {
                 // singleton: one stored id.  16->32 conversion, human collapse, dropped tids (:1031-1038)
-                const uint32_t e = hw < X.n_sid ? __ldg(X.sid2nid + hw) : KMAT_NONE;
+                const uint32_t e = aux;
                 if (e == KMAT_NONE) err = KMAT_ERR_BAD_TAXID;          // "bad taxid" assert (TaxNodeStat.hpp:235-238)
                 else if (!(e & KB_SID_DROP)) {
                     v0 = (e & KB_SID_HUMAN) ? X.nid_human : (e & KB_SID_NIDMASK); a = 1;
@@ -282,7 +292,7 @@ __device__ __forceinline__ unsigned long long kb_chunk(const KmScoreParams &P, K
                 }
             } else {
                 rec = X.pool2 + (size_t)(hw & 0x7FFFFFFFu) * X.pool2_mul;
-                const uint32_t h = rec[0];
+                const uint32_t h = aux;
                 if (h == KR_ERR_BAD) { err = KMAT_ERR_BAD_TAXID; rec = nullptr; }
                 else {
                     a = h & 0xFFFFu;
@@ -366,12 +376,19 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_cand_kernel(KmScoreParams P)
         const int nch = (np + 31) >> 5;
         // ---- per position: members of label_vec[pos].second in insertion order (read_label.cpp:1019-1134)
         if (NCH) {
+            // every hit word of the read, then every word they point at, before the first chunk is walked
+            uint32_t hws[NCH ? NCH : 1], auxs[NCH ? NCH : 1];
+#pragma unroll
+            for (int c = 0; c < (NCH ? NCH : 1); c++) hws[c] = c < nch ? kb_load_hit(P, c, off, np, lane) : KM_HIT_INVALID;
+#pragma unroll
+            for (int c = 0; c < (NCH ? NCH : 1); c++) auxs[c] = kb_load_aux(X, hws[c]);
 #pragma unroll
             for (int c = 0; c < (NCH ? NCH : 1); c++)
-                pm[c] = (c < nch && !overflow) ? kb_chunk(P, K, C, c, off, np, lane, cand_cnt, fnd_cnt, err, overflow, st_list_ids, st_list_sectors) : 0ull;
+                pm[c] = (c < nch && !overflow) ? kb_chunk(P, K, C, c, hws[c], auxs[c], lane, cand_cnt, fnd_cnt, err, overflow, st_list_ids, st_list_sectors) : 0ull;
         } else {
             for (int c = 0; c < nch && !overflow; c++) {
-                const unsigned long long m = kb_chunk(P, K, C, c, off, np, lane, cand_cnt, fnd_cnt, err, overflow, st_list_ids, st_list_sectors);
+                const uint32_t hw1 = kb_load_hit(P, c, off, np, lane);
+                const unsigned long long m = kb_chunk(P, K, C, c, hw1, kb_load_aux(X, hw1), lane, cand_cnt, fnd_cnt, err, overflow, st_list_ids, st_list_sectors);
                 if ((c << 5) + lane < np) gmask[(c << 5) + lane] = m;
             }
         }
@@ -474,11 +491,24 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_cand_kernel(KmScoreParams P)
         // ---- hits per candidate = number of positions whose set holds it (:748-759)
         uint32_t c_hits[2] = {0, 0};
         if (NCH) {
-            for (int i = 0; i < C; i++) {
-                uint32_t cnt = 0;
+            // bit-sliced: the (up to) five masks of a lane are added per candidate bit with carry-save logic into three
+            // bit planes (counts 0..5 for all 64 candidates at once); four candidates' counts are then spread into the
+            // bytes of one word and summed over the warp by a single redux.add (32 lanes x 5 <= 160 fits a byte)
 #pragma unroll
-                for (int c = 0; c < (NCH ? NCH : 1); c++) if (c < nch) cnt += __popc(__ballot_sync(KM_FULL, (pm[c] >> i) & 1));
-                if (lane == (i & 31)) c_hits[i >> 5] = cnt;
+            for (int g5 = 0; g5 < (NCH ? NCH : 1); g5 += 5) {
+                const unsigned long long a = pm[g5], b = g5 + 1 < NCH ? pm[g5 + 1] : 0ull, d = g5 + 2 < NCH ? pm[g5 + 2] : 0ull,
+                                         e = g5 + 3 < NCH ? pm[g5 + 3] : 0ull, f = g5 + 4 < NCH ? pm[g5 + 4] : 0ull;
+                const unsigned long long s1 = a ^ b ^ d, c1 = (a & b) | (a & d) | (b & d);
+                const unsigned long long p0 = s1 ^ e ^ f, c2 = (s1 & e) | (s1 & f) | (e & f);
+                const unsigned long long p1 = c1 ^ c2, p2 = c1 & c2;
+                for (int g = 0; g * 4 < C; g++) {
+                    const uint32_t n0 = (uint32_t)(p0 >> (4 * g)) & 15u, n1 = (uint32_t)(p1 >> (4 * g)) & 15u, n2 = (uint32_t)(p2 >> (4 * g)) & 15u;
+                    // (n * 0x00204081) & 0x01010101 moves bit q of the nibble to bit 0 of byte q
+                    const uint32_t w = ((n0 * 0x00204081u) & 0x01010101u) + 2u * ((n1 * 0x00204081u) & 0x01010101u) + 4u * ((n2 * 0x00204081u) & 0x01010101u);
+                    const uint32_t tot = __reduce_add_sync(KM_FULL, w);
+                    const uint32_t mine = (lane >> 2) == (g & 7) ? (tot >> (8 * (lane & 3))) & 0xFFu : 0u;
+                    if (g < 8) c_hits[0] += mine; else c_hits[1] += mine;
+                }
             }
         } else {
             __syncwarp();
