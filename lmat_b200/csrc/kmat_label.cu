@@ -344,7 +344,7 @@ __device__ __forceinline__ unsigned long long kb_chunk(const KmScoreParams &P, K
 }
 
 template <int NCH>
-__global__ void __launch_bounds__(KB_WARPS * 32) km_cand_kernel(KmScoreParams P) {
+__global__ void __launch_bounds__(KB_WARPS * 32, NCH == 5 ? 4 : 1) km_cand_kernel(KmScoreParams P) {
     const KmCtxDev &X = P.C;
     const int lane = threadIdx.x & 31;
     const uint32_t warp_global = blockIdx.x * KB_WARPS + (threadIdx.x >> 5), n_warps = gridDim.x * KB_WARPS;
@@ -383,8 +383,18 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_cand_kernel(KmScoreParams P)
 #pragma unroll
             for (int c = 0; c < (NCH ? NCH : 1); c++) auxs[c] = kb_load_aux(X, hws[c]);
 #pragma unroll
-            for (int c = 0; c < (NCH ? NCH : 1); c++)
-                pm[c] = (c < nch && !overflow) ? kb_chunk(P, K, C, c, hws[c], auxs[c], lane, cand_cnt, fnd_cnt, err, overflow, st_list_ids, st_list_sectors) : 0ull;
+            for (int c = 0; c < (NCH ? NCH : 1); c++) pm[c] = 0ull;
+            // one copy of the chunk walk in the instruction stream (it is the bulk of the kernel's code): the chunk's
+            // words are selected into scalars and its mask selected back, so pm[] / hws[] stay in registers
+#pragma unroll 1
+            for (int c = 0; c < nch && !overflow; c++) {
+                uint32_t hw1 = hws[0], aux1 = auxs[0];
+#pragma unroll
+                for (int q = 1; q < (NCH ? NCH : 1); q++) if (c == q) { hw1 = hws[q]; aux1 = auxs[q]; }
+                const unsigned long long m = kb_chunk(P, K, C, c, hw1, aux1, lane, cand_cnt, fnd_cnt, err, overflow, st_list_ids, st_list_sectors);
+#pragma unroll
+                for (int q = 0; q < (NCH ? NCH : 1); q++) if (c == q) pm[q] = m;
+            }
         } else {
             for (int c = 0; c < nch && !overflow; c++) {
                 const uint32_t hw1 = kb_load_hit(P, c, off, np, lane);
