@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--cpu-reads", type=int, default=200_000, help="reads in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=1, help="sub-batches per pass (kmat_ctx_set_pipeline); -1 automatic, 1 serial")
     return ap.parse_args()
 
 
@@ -184,6 +185,18 @@ def run_cpu_sample(sample, workdir, threads):
     return n / dt, dt
 
 
+def traffic_from_profile(a):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the encode+probe kernel, from the committed ncu
+    pass of this same workload (profiles/traffic.json, written by tools/ncu_traffic.py); None for other workloads."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if t["reads"] == a.reads and t["genomes"] == a.genomes and t["read_len"] == a.read_len and t["genome_len"] == a.genome_len:
+            return t["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -281,6 +294,7 @@ def main():
 
         # statistics counters (instrumentation) are off in every timed region and collected by one extra step below
         ctx.set_stats(False)
+        ctx.set_pipeline(a.pipeline)
         for _ in range(a.warmup):
             step()
         barrier()
@@ -296,7 +310,9 @@ def main():
         barrier()
         ms_total = e0.elapsed_time(e1)
         clocks = sampler.stop()
-        # per-kernel durations (CUDA events on the same stream), one extra untimed step each
+        # per-kernel durations (CUDA events on the same stream): extra untimed steps with the kernels run one after the
+        # other (the timed steps above overlap them on two streams, see kmat_ctx_set_pipeline)
+        ctx.set_pipeline(1)
         for _ in range(3):
             step()
             p, c_, s = ctx.kernel_ms()
@@ -304,6 +320,7 @@ def main():
             cand_ms.append(c_)
             score_ms.append(s)
         torch.cuda.synchronize()
+        ctx.set_pipeline(a.pipeline)
         ctx.set_stats(True)
         step()
         torch.cuda.synchronize()
@@ -368,9 +385,10 @@ def main():
                            "parallelism": f"read-sharded x{world}, table replicated, no data-path collective"},
                 "kmer_lookups_per_s": value * lookups_per_read, "lookups_per_read": lookups_per_read,
                 "hit_rate": st.hits / max(1, st.lookups), "reads_error": int(errs),
-                "kernels_ms": {"encode_probe": pm, "candidates": cm_, "score": sm_},
+                "kernels_ms": {"encode_probe": pm, "candidates": cm_, "score": sm_, "how": "CUDA events around each kernel of one serial pass"},
+                "pipeline_sub_batches": a.pipeline,
                 "roofline": {"bound": "hbm", "kernel": "km_encode_probe_fast_kernel<5>" if L <= 160 else ("km_encode_probe_fast_kernel<8>" if L <= 256 else "km_encode_probe_kernel"), "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                             "frac": achieved / hbm_peak, "traffic": traffic_from_profile(a), "peak_source": peak_src,
                              "random_access_peak": gather_gbps, "frac_random_access": achieved / gather_gbps,
                              "random_access_how": "uniform random 8-byte loads, one per 32-byte sector, over 16 GiB, best of 10 (kmat_gather_bench)",
                              "algorithmic_bytes_per_lookup": st.algorithmic_bytes / max(1, st.lookups)},

@@ -184,9 +184,15 @@ typedef struct {
 int kmat_ctx_last_stats(kmat_ctx *, kmat_batch_stats *);
 /* Turn the statistics counters on (default) or off for subsequent batches. */
 int kmat_ctx_set_stats(kmat_ctx *, int enable);
+/* Intra-pass pipeline.  sub_batches > 1: a pass is cut into that many sub-batches (<= 16) and the encode+probe kernel
+ * of sub-batch i+1 runs next to the candidate / scoring kernels of sub-batch i on a second stream; 0 or 1: the three
+ * kernels run one after the other (default; needed for kmat_ctx_last_kernel_ms' per-kernel split); -1: automatic
+ * (8 sub-batches for passes of >= 2^19 short reads).  Results do not depend on the setting.  On B200 the overlap
+ * gains nothing for the 150 bp workload (profiles/r01_probe_kernel_notes.md), hence serial by default. */
+int kmat_ctx_set_pipeline(kmat_ctx *, int sub_batches);
 /* Device time of the three kernels of the last batch (CUDA events on the launching stream): the
  * encode+probe kernel (K1+K2), the candidate-set kernel (K3) and the scoring/LCA kernel (K4).
- * Synchronises on the batch. */
+ * Synchronises on the batch.  In pipelined passes the kernels overlap: probe_ms is then the whole pass, the others 0. */
 int kmat_ctx_last_kernel_ms(kmat_ctx *, float *probe_ms, float *cand_ms, float *score_ms);
 /* Kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t kmat_launch_count(void);

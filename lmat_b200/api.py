@@ -47,7 +47,7 @@ EXPORTS = [
     "kmat_shard_of", "kmat_db_size", "kmat_db_bytes", "kmat_db_kmer_length", "kmat_db_device", "kmat_db_free",
     "kmat_lookup_batch", "kmat_encode_batch", "kmat_inputs_load", "kmat_inputs_free", "kmat_opts_default",
     "kmat_ctx_create", "kmat_ctx_set_opts", "kmat_ctx_destroy", "kmat_label_batch", "kmat_label_batch_device",
-    "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench",
+    "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_set_pipeline", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench",
     "kmat_set_l2_fetch_granularity", "kmat_reader_open", "kmat_reader_close", "kmat_read_batch_new", "kmat_read_batch_free",
     "kmat_reader_next", "kmat_read_batch_view", "kmat_tally_class", "kmat_host_alloc", "kmat_host_free",
 ]
@@ -99,6 +99,7 @@ def lib():
     L.kmat_ctx_sync.argtypes = [vp]
     L.kmat_ctx_last_stats.argtypes = [vp, C.POINTER(BatchStats)]
     L.kmat_ctx_set_stats.argtypes = [vp, C.c_int]
+    L.kmat_ctx_set_pipeline.argtypes = [vp, C.c_int]
     L.kmat_ctx_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.kmat_launch_count.restype = C.c_uint64
     L.kmat_format_tail.argtypes = [vp, vp, vp, C.c_int, C.c_char_p, C.c_size_t]
@@ -333,6 +334,9 @@ class Ctx:
         a, b, d = C.c_float(), C.c_float(), C.c_float()
         _check(lib().kmat_ctx_last_kernel_ms(self.h, C.byref(a), C.byref(b), C.byref(d)))
         return a.value, b.value, d.value
+
+    def set_pipeline(self, sub_batches):
+        _check(lib().kmat_ctx_set_pipeline(self.h, int(sub_batches)))
 
     def set_stats(self, enable):
         _check(lib().kmat_ctx_set_stats(self.h, int(enable)))

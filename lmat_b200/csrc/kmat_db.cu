@@ -657,34 +657,35 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
 }
 
 template <int NCH, int SETN, bool STATS>
-static int km_launch_fast(const KmProbeParams &P, int grid, cudaStream_t stream) {
+static int km_launch_fast(const KmProbeParams &P, int ctas_per_sm, cudaStream_t stream) {
     const int smem = KM_PROBE_WARPS * (SETN / 8);
-    static int resident = 0;               // per instantiation: CTAs that fit the device at once (persistent grid)
+    static int resident = 0, sms = 148;    // per instantiation: CTAs that fit the device at once (persistent grid)
     if (!resident) {
         KM_CUDA(cudaFuncSetAttribute(km_encode_probe_fast_kernel<NCH, SETN, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        KM_CUDA(cudaFuncSetAttribute(km_encode_probe_fast_kernel<NCH, SETN, STATS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        int per_sm = 0, dev = 0, sms = 148;
+        int per_sm = 0, dev = 0;
         KM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_encode_probe_fast_kernel<NCH, SETN, STATS>, KM_PROBE_WARPS * 32, smem));
         cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (const char *e = getenv("KMAT_PROBE_CTAS")) { const int v = atoi(e); if (v > 0 && v < per_sm) per_sm = v; }
         resident = std::max(1, per_sm) * sms;
     }
     const uint32_t want = (P.n_reads + KM_PROBE_WARPS - 1) / KM_PROBE_WARPS;
-    grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(want, (uint32_t)resident));
+    const uint32_t cap = ctas_per_sm > 0 ? std::min<uint32_t>((uint32_t)resident, (uint32_t)(ctas_per_sm * sms)) : (uint32_t)resident;
+    const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(want, cap));
     km_encode_probe_fast_kernel<NCH, SETN, STATS><<<grid, KM_PROBE_WARPS * 32, smem, stream>>>(P);
     return KMAT_OK;
 }
 
 int km_launch_encode_probe(const kmat_db *db, const char *d_bases, const uint64_t *d_offs, uint32_t n_reads, uint32_t max_len,
                            uint32_t *d_hit, int2 *d_hdr, uint64_t *d_kmers, uint8_t *d_flags, unsigned long long *d_long_sets,
-                           uint32_t long_slots, int grid, KmStatsDev *d_stats, int do_probe, cudaStream_t stream) {
+                           uint32_t long_slots, int grid, KmStatsDev *d_stats, int do_probe, cudaStream_t stream, int ctas_per_sm) {
     KmProbeParams P;
     P.db = km_db_dev(db); P.bases = d_bases; P.offs = d_offs; P.n_reads = n_reads; P.hit = d_hit; P.hdr = d_hdr;
     P.out_kmers = d_kmers; P.out_flags = d_flags; P.long_sets = d_long_sets; P.long_slots = long_slots; P.stats = d_stats;
     P.do_probe = do_probe;
     const bool fast = !d_kmers && !d_flags && max_len <= 256 && db->kmer_len <= 24 && !getenv("KMAT_NO_FAST_PROBE");
     int rc = KMAT_OK;
-    if (fast && max_len <= 160) rc = d_stats ? km_launch_fast<5, 4096, true>(P, grid, stream) : km_launch_fast<5, 4096, false>(P, grid, stream);
-    else if (fast) rc = d_stats ? km_launch_fast<8, 8192, true>(P, grid, stream) : km_launch_fast<8, 8192, false>(P, grid, stream);
+    if (fast && max_len <= 160) rc = d_stats ? km_launch_fast<5, 4096, true>(P, ctas_per_sm, stream) : km_launch_fast<5, 4096, false>(P, ctas_per_sm, stream);
+    else if (fast) rc = d_stats ? km_launch_fast<8, 8192, true>(P, ctas_per_sm, stream) : km_launch_fast<8, 8192, false>(P, ctas_per_sm, stream);
     else km_encode_probe_kernel<<<grid, KM_PROBE_WARPS * 32, 0, stream>>>(P);
     if (rc != KMAT_OK) return rc;
     g_km_launches++;
@@ -719,7 +720,7 @@ extern "C" int kmat_encode_batch(const kmat_db *db, const char *bases, const uin
         long_slots = 1024; while (long_slots < 2 * max_np) long_slots <<= 1;
         KM_CUDA(cudaMalloc((void **)&d_long, (size_t)grid * KM_PROBE_WARPS * long_slots * 8));
     }
-    int rc = km_launch_encode_probe(db, d_b, d_o, n_reads, max_np, d_hit, d_hdr, d_k, d_f, d_long, long_slots, grid, nullptr, 0, 0);
+    int rc = km_launch_encode_probe(db, d_b, d_o, n_reads, max_np, d_hit, d_hdr, d_k, d_f, d_long, long_slots, grid, nullptr, 0, 0, 0);
     if (rc == KMAT_OK) {
         std::vector<int2> hdr(n_reads);
         KM_CUDA(cudaMemcpy(hdr.data(), d_hdr, (size_t)n_reads * sizeof(int2), cudaMemcpyDeviceToHost));

@@ -31,9 +31,11 @@ struct KmStatsDev {
     unsigned long long reads_fast, reads_slow, reads_error;
 };
 
-// 256-bit load of one bucket (one 32-byte sector): LDG.E.256 on sm_100a
+// 256-bit load of one bucket (one 32-byte sector): LDG.E.NA.LTC64B.256 on sm_100a.  L1 is bypassed (no reuse) and the
+// L2 fill is limited to 64 bytes: by default a miss brings the whole 128-byte line in from DRAM (measured: 127 B of
+// DRAM traffic per random gather, 64 B with this hint, same request rate - profiles/r01_gather_modes.md).
 __device__ __forceinline__ void km_load_bucket(const uint64_t *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 }
 
 // One bucket of the probe sequence against (rem, displacement d): 0 = found (hw set), 1 = absent for good (a free

@@ -801,6 +801,12 @@ struct kmat_ctx {
         cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
     } slot[2];
     cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
+    // intra-pass pipeline: the encode+probe kernel of sub-batch i+1 (request-rate bound, few warps) runs next to the
+    // candidate and scoring kernels of sub-batch i (issue bound) on a second stream
+    cudaStream_t st_aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sub[16] = {};
+    int pipeline = 1;                        // sub-batches per pass: 0/1 serial (default), -1 automatic
+    int sms = 148;
     uint32_t *d_hit = nullptr; uint64_t cap_hit = 0;
     int2 *d_hdr = nullptr; uint32_t cap_hdr = 0;
     kmat_read_result *d_out_dev = nullptr; uint32_t cap_out_dev = 0;   // kmat_label_batch_device with d_out == NULL
@@ -892,6 +898,9 @@ extern "C" int kmat_ctx_create(const kmat_db *db, const kmat_inputs *in, const k
     KM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     KM_CUDA(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
     KM_CUDA(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
+    KM_CUDA(cudaStreamCreateWithFlags(&c->st_aux, cudaStreamNonBlocking));
+    KM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)); KM_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    for (auto &e : c->ev_sub) KM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (int i = 0; i < 4; i++) KM_CUDA(cudaEventCreate(&c->ev[i]));
     for (auto &sl : c->slot) {
         KM_CUDA(cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
@@ -906,6 +915,7 @@ extern "C" int kmat_ctx_create(const kmat_db *db, const kmat_inputs *in, const k
     KM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], km_cand_kernel<10>, KB_WARPS * 32, 0));
     KM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], km_cand_kernel<0>, KB_WARPS * 32, 0));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    c->sms = sms;
     for (int i = 0; i < 3; i++) c->cand_grid[i] = std::max(1, per_sm[i]) * sms;
     rc = km_resolve_lists(c);
     if (rc != KMAT_OK) { kmat_ctx_destroy(c); return rc; }
@@ -933,6 +943,10 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
     cudaFree(c->d_hit); cudaFree(c->d_hdr); cudaFree(c->d_out_dev);
     if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
     if (c->st_d2h) cudaStreamDestroy(c->st_d2h);
+    if (c->st_aux) { cudaStreamSynchronize(c->st_aux); cudaStreamDestroy(c->st_aux); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    for (auto &e : c->ev_sub) if (e) cudaEventDestroy(e);
     cudaFree(c->d_cands); cudaFree(c->d_lin); cudaFree(c->d_cursors); cudaFree(c->d_pool2); cudaFree(c->d_long_masks); cudaFree(c->d_long_sets); cudaFree(c->d_stats);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -976,7 +990,6 @@ static int km_run_device(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
     int rc;
     if ((rc = km_grow(&c->d_hit, &c->cap_hit, L.total_bases + 1)) != KMAT_OK) return rc;
     { uint64_t cap = c->cap_hdr; if ((rc = km_grow(&c->d_hdr, &cap, L.n_reads)) != KMAT_OK) return rc; c->cap_hdr = (uint32_t)cap; }
-    const int pgrid = km_probe_grid(L.n_reads);
     if (L.max_len > 256) {
         uint32_t slots = 1024; while (slots < 2 * L.max_len) slots <<= 1;
         const int warps = 148 * 6 * KM_PROBE_WARPS_HOST;
@@ -992,47 +1005,73 @@ static int km_run_device(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
         if (c->collect_stats) KM_CUDA(cudaMemsetAsync(c->d_stats, 0, sizeof(KmStatsDev), st));
     }
     uint32_t *hit = c->d_hit - L.first_off;
-    KM_CUDA(cudaEventRecord(c->ev[0], st));
-    rc = km_launch_encode_probe(c->db, L.d_bases, L.d_offs, L.n_reads, L.max_len, hit, c->d_hdr, nullptr, nullptr, c->d_long_sets, c->long_slots,
-                                pgrid, c->collect_stats ? c->d_stats : nullptr, 1, st);
-    if (rc != KMAT_OK) return rc;
-    KM_CUDA(cudaEventRecord(c->ev[1], st));
-    KmScoreParams P;
-    P.C = km_ctx_dev(c);
-    P.offs = L.d_offs; P.n_reads = L.n_reads; P.hit = hit; P.hdr = c->d_hdr; P.out = L.d_out;
-    P.cands = c->d_cands; P.cand_cursor = c->d_cursors; P.cand_cap = c->cap_cands;
-    P.lin = c->d_lin; P.lin_cursor = c->d_cursors + 1; P.lin_cap = c->cap_lin;
-    P.stats = c->collect_stats ? c->d_stats : nullptr;
-    P.long_masks = nullptr; P.long_cap = 0;
-    const int want_grid = (int)((L.n_reads + KB_WARPS - 1) / KB_WARPS);
     const int max_pos = (int)L.max_len - c->db->kmer_len + 1;
-    if (max_pos <= 5 * 32) km_cand_kernel<5><<<std::max(1, std::min(c->cand_grid[0], want_grid)), KB_WARPS * 32, 0, st>>>(P);
-    else if (max_pos <= 10 * 32) km_cand_kernel<10><<<std::max(1, std::min(c->cand_grid[1], want_grid)), KB_WARPS * 32, 0, st>>>(P);
-    else {
+    const int variant = max_pos <= 5 * 32 ? 0 : max_pos <= 10 * 32 ? 1 : 2;
+    if (variant == 2) {
         // long reads: the position masks live in a per-warp global scratch
         const uint32_t cap = ((uint32_t)max_pos + 31u) & ~31u;
         if (cap > c->long_mask_cap) {
-            KM_CUDA(cudaStreamSynchronize(st));
+            KM_CUDA(cudaStreamSynchronize(st)); KM_CUDA(cudaStreamSynchronize(c->st_aux));
             cudaFree(c->d_long_masks); c->d_long_masks = nullptr;
             KM_CUDA(cudaMalloc((void **)&c->d_long_masks, (size_t)c->cand_grid[2] * KB_WARPS * cap * 8));
             c->long_mask_cap = cap;
         }
-        P.long_masks = c->d_long_masks; P.long_cap = c->long_mask_cap;
-        km_cand_kernel<0><<<std::max(1, std::min(c->cand_grid[2], want_grid)), KB_WARPS * 32, 0, st>>>(P);
     }
-    g_km_launches++;
-    KM_CUDA(cudaGetLastError());
-    KM_CUDA(cudaEventRecord(c->ev[3], st));
-    km_score_kernel<<<(L.n_reads + KS_THREADS - 1) / KS_THREADS, KS_THREADS, 0, st>>>(P);
-    g_km_launches++;
-    KM_CUDA(cudaGetLastError());
+    // Sub-batches.  Serial: probe, candidates, scoring one after the other on `st` (per-kernel times through ev[]).
+    // Pipelined (short reads, large passes): the probe kernel keeps ~1 CTA per SM (it is bound by the table request
+    // rate and loses ~15 % at 8 warps per SM) and the other two kernels work on the previous sub-batch in the rest of
+    // every SM, on st_aux.
+    int S = c->pipeline;
+    if (S < 0) S = (variant == 0 && L.n_reads >= (1u << 19)) ? 8 : 1;
+    if (variant != 0 || S < 1) S = 1;
+    if (S > 16) S = 16;
+    const bool piped = S > 1;
+    KM_CUDA(cudaEventRecord(c->ev[0], st));
+    if (piped) { KM_CUDA(cudaEventRecord(c->ev_fork, st)); KM_CUDA(cudaStreamWaitEvent(c->st_aux, c->ev_fork, 0)); }
+    for (int sb = 0; sb < S; sb++) {
+        const uint32_t r0 = (uint32_t)((uint64_t)L.n_reads * sb / S), r1 = (uint32_t)((uint64_t)L.n_reads * (sb + 1) / S);
+        if (r1 == r0) continue;
+        const uint32_t n = r1 - r0;
+        rc = km_launch_encode_probe(c->db, L.d_bases, L.d_offs + r0, n, L.max_len, hit, c->d_hdr + r0, nullptr, nullptr, c->d_long_sets, c->long_slots,
+                                    km_probe_grid(n), c->collect_stats ? c->d_stats : nullptr, 1, st, piped ? 1 : 0);
+        if (rc != KMAT_OK) return rc;
+        cudaStream_t s2 = st;
+        if (piped) { KM_CUDA(cudaEventRecord(c->ev_sub[sb], st)); KM_CUDA(cudaStreamWaitEvent(c->st_aux, c->ev_sub[sb], 0)); s2 = c->st_aux; }
+        else KM_CUDA(cudaEventRecord(c->ev[1], st));
+        KmScoreParams P;
+        P.C = km_ctx_dev(c);
+        P.offs = L.d_offs + r0; P.n_reads = n; P.hit = hit; P.hdr = c->d_hdr + r0; P.out = L.d_out + r0;
+        P.cands = c->d_cands; P.cand_cursor = c->d_cursors; P.cand_cap = c->cap_cands;
+        P.lin = c->d_lin; P.lin_cursor = c->d_cursors + 1; P.lin_cap = c->cap_lin;
+        P.stats = c->collect_stats ? c->d_stats : nullptr;
+        P.long_masks = nullptr; P.long_cap = 0;
+        const int want_grid = (int)((n + KB_WARPS - 1) / KB_WARPS);
+        const int g0 = piped ? std::min(c->cand_grid[0], 2 * c->sms) : c->cand_grid[0];
+        if (variant == 0) km_cand_kernel<5><<<std::max(1, std::min(g0, want_grid)), KB_WARPS * 32, 0, s2>>>(P);
+        else if (variant == 1) km_cand_kernel<10><<<std::max(1, std::min(c->cand_grid[1], want_grid)), KB_WARPS * 32, 0, s2>>>(P);
+        else {
+            P.long_masks = c->d_long_masks; P.long_cap = c->long_mask_cap;
+            km_cand_kernel<0><<<std::max(1, std::min(c->cand_grid[2], want_grid)), KB_WARPS * 32, 0, s2>>>(P);
+        }
+        g_km_launches++;
+        KM_CUDA(cudaGetLastError());
+        if (!piped) KM_CUDA(cudaEventRecord(c->ev[3], st));
+        km_score_kernel<<<(n + KS_THREADS - 1) / KS_THREADS, KS_THREADS, 0, s2>>>(P);
+        g_km_launches++;
+        KM_CUDA(cudaGetLastError());
+    }
+    if (piped) {
+        KM_CUDA(cudaEventRecord(c->ev_join, c->st_aux)); KM_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
+        KM_CUDA(cudaEventRecord(c->ev[1], st)); KM_CUDA(cudaEventRecord(c->ev[3], st));     // no per-kernel split in this mode
+    }
     KM_CUDA(cudaEventRecord(c->ev[2], st));
     return KMAT_OK;
 }
 
+static int km_grow_cands(kmat_ctx *c, uint64_t want) { return km_grow(&c->d_cands, &c->cap_cands, want); }
 static int km_reserve_cands(kmat_ctx *c, uint64_t n_reads) {
     int rc;
-    if (!c->d_cands || c->cap_cands < n_reads * 12 + 4096) { if ((rc = km_grow(&c->d_cands, &c->cap_cands, n_reads * 24 + 4096)) != KMAT_OK) return rc; }
+    if (!c->d_cands || c->cap_cands < n_reads * 12 + 4096) { if ((rc = km_grow_cands(c, n_reads * 24 + 4096)) != KMAT_OK) return rc; }
     if (c->opt.want_lineage && (!c->d_lin || c->cap_lin < n_reads * 12 + 4096)) { if ((rc = km_grow(&c->d_lin, &c->cap_lin, n_reads * 24 + 4096)) != KMAT_OK) return rc; }
     return KMAT_OK;
 }
@@ -1065,6 +1104,11 @@ extern "C" int kmat_ctx_last_kernel_ms(kmat_ctx *c, float *probe_ms, float *cand
     if (probe_ms) *probe_ms = a;
     if (cand_ms) *cand_ms = b;
     if (score_ms) *score_ms = d;
+    return KMAT_OK;
+}
+extern "C" int kmat_ctx_set_pipeline(kmat_ctx *c, int sub_batches) {
+    if (!c) return KMAT_ERR_ARG;
+    c->pipeline = sub_batches;
     return KMAT_OK;
 }
 extern "C" int kmat_ctx_set_stats(kmat_ctx *c, int enable) {
@@ -1184,7 +1228,7 @@ extern "C" int kmat_label_batch(kmat_ctx *c, const char *bases, const uint64_t *
         total_c = c->slot[prev.slot].h_cur[0]; total_l = c->slot[prev.slot].h_cur[1];
         KM_CUDA(cudaStreamSynchronize(c->st_d2h));
         bool again = false;
-        if (total_c > c->cap_cands) { KM_CUDA(cudaStreamSynchronize(c->stream)); if ((rc = km_grow(&c->d_cands, &c->cap_cands, total_c)) != KMAT_OK) return rc; again = true; }
+        if (total_c > c->cap_cands) { KM_CUDA(cudaStreamSynchronize(c->stream)); if ((rc = km_grow_cands(c, total_c)) != KMAT_OK) return rc; again = true; }
         if (c->opt.want_lineage && total_l > c->cap_lin) { KM_CUDA(cudaStreamSynchronize(c->stream)); if ((rc = km_grow(&c->d_lin, &c->cap_lin, total_l)) != KMAT_OK) return rc; again = true; }
         if (again) continue;                     // candidate buffer was too small: re-run with the exact size
         if (n_cands) *n_cands = total_c;

@@ -40,6 +40,6 @@ KmDbDev km_db_dev(const kmat_db *db);
 int km_probe_grid(uint32_t n_reads);
 int km_launch_encode_probe(const kmat_db *db, const char *d_bases, const uint64_t *d_offs, uint32_t n_reads, uint32_t max_len,
                            uint32_t *d_hit, int2 *d_hdr, uint64_t *d_kmers, uint8_t *d_flags, unsigned long long *d_long_sets,
-                           uint32_t long_slots, int grid, KmStatsDev *d_stats, int do_probe, cudaStream_t stream);
+                           uint32_t long_slots, int grid, KmStatsDev *d_stats, int do_probe, cudaStream_t stream, int ctas_per_sm /* 0 = all that fit */);
 #define KM_PROBE_WARPS_HOST 8
 #endif

@@ -215,3 +215,20 @@ def test_tight_table_uses_displacement_and_stash(golden_lists, monkeypatch):
     mine = op.assemble_lines(hdrs, seqs, ctx.tails(res, cands, lin, prn_all=True))
     assert mine == g.golden_out("run_rl")
     assert ctx.stats().probe_extra_buckets > 0
+
+
+def test_pipelined_pass_matches_serial(golden_lists, dbs):
+    """kmat_ctx_set_pipeline: overlapping the probe kernel of one sub-batch with the candidate / scoring kernels of the
+    previous one (two streams) must not change a single result; candidates are addressed through cand_off."""
+    g = golden_lists
+    ctx = make_ctx(g, dbs[g.name], "run_rl")
+    hdrs, seqs = op.read_fasta_like_reference(g.paths["reads"])
+    seqs = seqs * 3
+    ctx.set_pipeline(1)
+    res, cands, lin = ctx.label(seqs)
+    serial = ctx.tails(res, cands, lin, prn_all=True)
+    for sub in (2, 5, 16):
+        ctx.set_pipeline(sub)
+        r2, c2, l2 = ctx.label(seqs)
+        assert ctx.tails(r2, c2, l2, prn_all=True) == serial, sub
+        assert np.array_equal(r2["status"], res["status"]) and np.array_equal(r2["n_cand"], res["n_cand"])

@@ -15,3 +15,6 @@ timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'km
     -o gpurun_out/${TAG}_prof -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --genomes 400 --reads 2000000 \
     > gpurun_out/${TAG}_prof_bench.log 2>&1; echo "ncu full rc=$?"
 ls -la gpurun_out
+# DRAM traffic of the dominant kernel at the full bench workload (roofline.traffic)
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:km_encode_probe -s 1 -c 3 --csv --log-file gpurun_out/${TAG}_traffic.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_traffic_bench.log 2>&1; echo "traffic rc=$?"
