@@ -79,7 +79,9 @@ int kmat_db_upload(const kmat_table *, int device, int shard_index, int shard_co
  * 4-byte words) for lists; pool = the list pool ([count][ids...] records). */
 int kmat_db_build_device(int device, int kmer_length, int tid_bytes, uint64_t n_kmers,
                          const uint64_t *d_kmers, const uint32_t *d_payload,
-                         const uint32_t *d_pool, uint64_t pool_words, uint32_t n_stored_ids, kmat_db **out);
+                         const uint32_t *d_pool, uint64_t pool_words, uint32_t n_stored_ids,
+                         int shard_index, int shard_count /* keep kmat_shard_of() == shard_index only; 0, 1 = all */,
+                         kmat_db **out);
 uint32_t kmat_shard_of(uint64_t kmer, int kmer_length, int shard_count);
 uint64_t kmat_db_size(const kmat_db *);
 uint64_t kmat_db_bytes(const kmat_db *);             /* device bytes held */
@@ -163,6 +165,34 @@ typedef struct {
 int kmat_label_batch(kmat_ctx *, const char *bases, const uint64_t *offs, uint32_t n_reads, kmat_read_result *out,
                      kmat_pair *cands, uint64_t cands_cap, uint64_t *n_cands,
                      kmat_pair *lineage, uint64_t lineage_cap, uint64_t *n_lineage);
+
+/* ---- DB-sharded mode (SURVEY.md 8(e) mode B: table partitioned by kmat_shard_of over n_shards ranks) ---------------
+ * One pass over a batch = three device phases around two exchange steps that the CALLER performs (NCCL all-to-all
+ * between one-process-per-GPU ranks -- lmat_b200/sharded.py over torch.distributed -- or peer copies in one process).
+ * Every rank calls all three phases every round, with n_reads == 0 when it has no reads left.  Results are identical
+ * to the replicated table's.  All pointers named d_* are device pointers on the ctx's device.
+ *
+ * 1. home: K1 (encode, dedup) and grouping of the first-occurrence k-mers by owner.  *d_queries (library-owned, valid
+ *    until the next kmat_shard_encode) holds the mixed k-mers, owner 0's first; counts[o] = how many go to owner o. */
+int kmat_shard_encode(kmat_ctx *, const char *d_bases, const uint64_t *d_offs, uint32_t n_reads, uint64_t total_bases,
+                      uint32_t max_read_len, int n_shards, const uint64_t **d_queries, uint64_t *counts /* host [n_shards] */,
+                      void *stream);
+/* 2. owner: probe this rank's shard.  d_queries = the received k-mers, source rank 0's first, counts[s] from source s.
+ *    *d_reply: one 32-bit hit word per query, same order (goes back to the sources with the same split);
+ *    *d_payload: the resolved list records of the list hits, packed per source; payload_counts[s] = 32-bit words for
+ *    source s.  Both buffers are library-owned and valid until the next kmat_shard_serve. */
+int kmat_shard_serve(kmat_ctx *, const uint64_t *d_queries, const uint64_t *counts /* host [n_shards] */, int n_shards,
+                     const uint32_t **d_reply, const uint32_t **d_payload, uint64_t *payload_counts /* host [n_shards] */,
+                     void *stream);
+/* 3. home: d_reply = the hit words received for this rank's queries (owner 0's first, i.e. the order of *d_queries),
+ *    d_payload = the received list records, owner 0's first, payload_counts[o] words from owner o.  Writes the hit
+ *    words back to their read positions and runs K3 / K4; results to d_out (or, if NULL, to a library buffer
+ *    readable through kmat_ctx_device_results).  Does not synchronise. */
+int kmat_shard_finish(kmat_ctx *, const uint32_t *d_reply, const uint32_t *d_payload, const uint64_t *payload_counts /* host [n_shards] */,
+                      int n_shards, kmat_read_result *d_out, void *stream);
+/* Device-resident results of the last pass that was given d_out == NULL, and the device candidate pairs that
+ * cand_off / n_cand index (rank_label after sort(TCmp), ascending).  Synchronises. */
+int kmat_ctx_device_results(kmat_ctx *, const kmat_read_result **d_out, const kmat_pair **d_cands, uint64_t *n_cands);
 
 /* Page-locked host memory for the buffers of kmat_label_batch (optional; NULL when no device / out of memory). */
 void *kmat_host_alloc(size_t bytes);

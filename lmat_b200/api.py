@@ -47,7 +47,7 @@ EXPORTS = [
     "kmat_shard_of", "kmat_db_size", "kmat_db_bytes", "kmat_db_kmer_length", "kmat_db_device", "kmat_db_free",
     "kmat_lookup_batch", "kmat_encode_batch", "kmat_inputs_load", "kmat_inputs_free", "kmat_opts_default",
     "kmat_ctx_create", "kmat_ctx_set_opts", "kmat_ctx_destroy", "kmat_label_batch", "kmat_label_batch_device",
-    "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_set_pipeline", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench",
+    "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_set_pipeline", "kmat_shard_encode", "kmat_shard_serve", "kmat_shard_finish", "kmat_ctx_device_results", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench",
     "kmat_set_l2_fetch_granularity", "kmat_reader_open", "kmat_reader_close", "kmat_read_batch_new", "kmat_read_batch_free",
     "kmat_reader_next", "kmat_read_batch_view", "kmat_tally_class", "kmat_host_alloc", "kmat_host_free",
 ]
@@ -76,7 +76,7 @@ def lib():
     L.kmat_table_view.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.kmat_table_free.argtypes = [vp]
     L.kmat_db_upload.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
-    L.kmat_db_build_device.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, vp, vp, vp, C.c_uint64, C.c_uint32, C.POINTER(vp)]
+    L.kmat_db_build_device.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, vp, vp, vp, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.POINTER(vp)]
     L.kmat_shard_of.restype = C.c_uint32
     L.kmat_shard_of.argtypes = [C.c_uint64, C.c_int, C.c_int]
     L.kmat_db_size.restype = C.c_uint64
@@ -100,6 +100,10 @@ def lib():
     L.kmat_ctx_last_stats.argtypes = [vp, C.POINTER(BatchStats)]
     L.kmat_ctx_set_stats.argtypes = [vp, C.c_int]
     L.kmat_ctx_set_pipeline.argtypes = [vp, C.c_int]
+    L.kmat_shard_encode.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(vp), vp, vp]
+    L.kmat_shard_serve.argtypes = [vp, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(vp), vp, vp]
+    L.kmat_shard_finish.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp]
+    L.kmat_ctx_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.kmat_ctx_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.kmat_launch_count.restype = C.c_uint64
     L.kmat_format_tail.argtypes = [vp, vp, vp, C.c_int, C.c_char_p, C.c_size_t]
@@ -207,9 +211,11 @@ class Db:
         return cls(h)
 
     @classmethod
-    def build_device(cls, device, kmer_len, tid_bytes, n, d_kmers_ptr, d_payload_ptr, d_pool_ptr, pool_words, n_stored_ids=0):
+    def build_device(cls, device, kmer_len, tid_bytes, n, d_kmers_ptr, d_payload_ptr, d_pool_ptr, pool_words, n_stored_ids=0,
+                     shard_index=0, shard_count=1):
         h = C.c_void_p()
-        _check(lib().kmat_db_build_device(device, kmer_len, tid_bytes, n, d_kmers_ptr, d_payload_ptr, d_pool_ptr, pool_words, n_stored_ids, C.byref(h)))
+        _check(lib().kmat_db_build_device(device, kmer_len, tid_bytes, n, d_kmers_ptr, d_payload_ptr, d_pool_ptr, pool_words, n_stored_ids,
+                                          shard_index, shard_count, C.byref(h)))
         return cls(h)
 
     @property
@@ -329,6 +335,32 @@ class Ctx:
     def label_device(self, d_bases_ptr, d_offs_ptr, n_reads, total_bases, max_read_len, d_out_ptr=None, stream=None):
         """kmat_label_batch_device: inputs already in HBM, results stay on the device; asynchronous."""
         _check(lib().kmat_label_batch_device(self.h, d_bases_ptr, d_offs_ptr, n_reads, total_bases, max_read_len, d_out_ptr, stream))
+
+    # ---- DB-sharded mode: the three device phases of one round (the exchange between them is lmat_b200.sharded's)
+    def shard_encode(self, d_bases_ptr, d_offs_ptr, n_reads, total_bases, max_read_len, n_shards, stream=None):
+        """-> (device pointer of the queries grouped by owner, counts[n_shards])"""
+        q = C.c_void_p()
+        counts = np.zeros(n_shards, dtype=np.uint64)
+        _check(lib().kmat_shard_encode(self.h, d_bases_ptr, d_offs_ptr, n_reads, total_bases, max_read_len, n_shards, C.byref(q), counts.ctypes.data, stream))
+        return q.value or 0, counts
+
+    def shard_serve(self, d_queries_ptr, counts, stream=None):
+        """-> (device pointer of the hit words, device pointer of the list payload, payload_counts[n_shards])"""
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        rep, pay = C.c_void_p(), C.c_void_p()
+        pc = np.zeros(len(counts), dtype=np.uint64)
+        _check(lib().kmat_shard_serve(self.h, d_queries_ptr, counts.ctypes.data, len(counts), C.byref(rep), C.byref(pay), pc.ctypes.data, stream))
+        return rep.value or 0, pay.value or 0, pc
+
+    def shard_finish(self, d_reply_ptr, d_payload_ptr, payload_counts, d_out_ptr=None, stream=None):
+        pc = np.ascontiguousarray(payload_counts, dtype=np.uint64)
+        _check(lib().kmat_shard_finish(self.h, d_reply_ptr or None, d_payload_ptr or None, pc.ctypes.data, len(pc), d_out_ptr, stream))
+
+    def device_results(self):
+        """-> (device pointer of the results of the last pass run with d_out=None, device pointer of the candidate pairs, n_cands)"""
+        o, cd, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        _check(lib().kmat_ctx_device_results(self.h, C.byref(o), C.byref(cd), C.byref(n)))
+        return o.value or 0, cd.value or 0, n.value
 
     def kernel_ms(self):
         a, b, d = C.c_float(), C.c_float(), C.c_float()

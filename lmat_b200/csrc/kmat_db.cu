@@ -35,14 +35,7 @@ static int km_choose_bucket_bits(uint64_t n, int kmer_bits) {
 
 extern "C" uint32_t kmat_shard_of(uint64_t kmer, int kmer_length, int shard_count) {
     if (shard_count <= 1) return 0;
-    // hash prefix of the canonical k-mer (a raw k-mer prefix would be skewed); a different
-    // odd multiplier than km_mix so that shard and bucket are independent
-    uint64_t x = kmer * 0xA24BAED4963EE407ull;
-    x ^= x >> 29;
-    x *= 0x9FB21C651E98DF25ull;
-    x ^= x >> 32;
-    (void)kmer_length;
-    return (uint32_t)((x >> 11) % (uint64_t)shard_count);
+    return km_owner_of_x(km_mix(kmer, 2 * kmer_length), (uint32_t)shard_count);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -51,9 +44,13 @@ extern "C" uint32_t kmat_shard_of(uint64_t kmer, int kmer_length, int shard_coun
 #define KM_STASH_CAP 65536u
 __global__ void km_insert_kernel(const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ payload, uint64_t n,
                                  unsigned long long *slots, uint64_t bucket_mask, int kmer_bits, int rem_bits,
-                                 unsigned int *stash_n, uint64_t *stash_x, uint32_t *stash_hit) {
+                                 unsigned int *stash_n, uint64_t *stash_x, uint32_t *stash_hit,
+                                 uint32_t shard_index, uint32_t shard_count, unsigned long long *n_kept) {
+    unsigned long long kept = 0;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t x = km_mix(kmers[i], kmer_bits);
+        if (shard_count > 1 && km_owner_of_x(x, shard_count) != shard_index) continue;     // another shard's k-mer
+        kept++;
         const uint64_t home = x >> rem_bits, rem = x & ((1ull << rem_bits) - 1);
         const uint32_t pl = payload[i];
         const uint64_t base = (1ull << 63) | ((uint64_t)((pl >> 31) & 1) << 62) | (rem << 32) | (pl & 0x7FFFFFFFu);
@@ -70,6 +67,8 @@ __global__ void km_insert_kernel(const uint64_t *__restrict__ kmers, const uint3
             if (q < KM_STASH_CAP) { stash_x[q] = x; stash_hit[q] = pl; }
         }
     }
+    kept = __reduce_add_sync(0xffffffffu, (unsigned)kept);      // < 2^32 per warp pass: grid-stride, 32 lanes
+    if ((threadIdx.x & 31) == 0 && kept) atomicAdd(n_kept, kept);
 }
 __global__ void km_prefix_bits_kernel(const uint64_t *__restrict__ kmers, uint64_t n, uint32_t *bits, int shift) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -78,9 +77,14 @@ __global__ void km_prefix_bits_kernel(const uint64_t *__restrict__ kmers, uint64
     }
 }
 
-static int km_db_alloc_and_insert(kmat_db *db, const uint64_t *d_kmers, const uint32_t *d_payload, uint64_t n) {
+static int km_db_alloc_and_insert(kmat_db *db, const uint64_t *d_kmers, const uint32_t *d_payload, uint64_t n, int shard_index, int shard_count) {
     const int kmer_bits = 2 * db->kmer_len;
-    for (int b = km_choose_bucket_bits(n, kmer_bits);; b++) {
+    unsigned long long *d_kept;
+    KM_CUDA(cudaMalloc((void **)&d_kept, 8));
+    unsigned long long kept = 0;
+    // a shard keeps ~n / shard_count of the k-mers (the owner hash is uniform); the table is sized for that plus 5 %
+    const uint64_t expect = shard_count > 1 ? n / shard_count + n / (20 * (uint64_t)shard_count) + 1024 : n;
+    for (int b = km_choose_bucket_bits(expect, kmer_bits);; b++) {
         if (b > kmer_bits) { kmat_set_error("hash table build failed: displacement limit at maximum size"); return KMAT_ERR_UNSUPPORTED; }
         db->geom.kmer_bits = kmer_bits; db->geom.bucket_bits = b; db->geom.rem_bits = kmer_bits - b;
         db->n_buckets = 1ull << b;
@@ -91,16 +95,18 @@ static int km_db_alloc_and_insert(kmat_db *db, const uint64_t *d_kmers, const ui
         KM_CUDA(cudaMalloc((void **)&d_sn, sizeof(unsigned int)));
         KM_CUDA(cudaMalloc((void **)&d_sx, (size_t)KM_STASH_CAP * 8)); KM_CUDA(cudaMalloc((void **)&d_sh, (size_t)KM_STASH_CAP * 4));
         KM_CUDA(cudaMemset(d_sn, 0, sizeof(unsigned int)));
+        KM_CUDA(cudaMemset(d_kept, 0, 8));
         if (n) {
             const int threads = 256;
             const int blocks = (int)std::min<uint64_t>((n + threads - 1) / threads, 148ull * 16);
             km_insert_kernel<<<blocks, threads>>>(d_kmers, d_payload, n, (unsigned long long *)db->d_slots, db->n_buckets - 1,
-                                                  kmer_bits, db->geom.rem_bits, d_sn, d_sx, d_sh);
+                                                  kmer_bits, db->geom.rem_bits, d_sn, d_sx, d_sh, (uint32_t)shard_index, (uint32_t)shard_count, d_kept);
             g_km_launches++;
             KM_CUDA(cudaGetLastError());
         }
         unsigned int sn = 0;
         KM_CUDA(cudaMemcpy(&sn, d_sn, sizeof sn, cudaMemcpyDeviceToHost));
+        KM_CUDA(cudaMemcpy(&kept, d_kept, 8, cudaMemcpyDeviceToHost));
         if (sn <= KM_STASH_CAP) {
             // the stash: sorted by mixed key on the host (a few hundred entries at most), searched by km_probe_x
             if (sn) {
@@ -137,7 +143,9 @@ static int km_db_alloc_and_insert(kmat_db *db, const uint64_t *d_kmers, const ui
         db->prefix_bytes = words * 4;
     }
     KM_CUDA(cudaDeviceSynchronize());
-    db->n_kmers = n;
+    cudaFree(d_kept);
+    db->n_kmers = kept;
+    db->shard_index = shard_index; db->shard_count = shard_count;
     return KMAT_OK;
 }
 
@@ -152,8 +160,8 @@ KmDbDev km_db_dev(const kmat_db *db) {
 
 extern "C" int kmat_db_build_device(int device, int kmer_len, int tid_bytes, uint64_t n, const uint64_t *d_kmers,
                                     const uint32_t *d_payload, const uint32_t *d_pool, uint64_t pool_words, uint32_t n_stored_ids,
-                                    kmat_db **out) {
-    if (!out || (tid_bytes != 2 && tid_bytes != 4) || kmer_len < 8 || kmer_len > 28) { kmat_set_error("kmat_db_build_device: bad argument"); return KMAT_ERR_ARG; }
+                                    int shard_index, int shard_count, kmat_db **out) {
+    if (!out || (tid_bytes != 2 && tid_bytes != 4) || kmer_len < 8 || kmer_len > 28 || shard_count < 1 || shard_count > KM_MAX_SHARDS || shard_index < 0 || shard_index >= shard_count) { kmat_set_error("kmat_db_build_device: bad argument"); return KMAT_ERR_ARG; }
     if (kmat_device_count() <= device) { kmat_set_error("CUDA device %d not available", device); return KMAT_ERR_NO_DEVICE; }
     if (pool_words >= (1ull << 31)) { kmat_set_error("list pool of %llu words exceeds the 31-bit offset range", (unsigned long long)pool_words); return KMAT_ERR_UNSUPPORTED; }
     KM_CUDA(cudaSetDevice(device));
@@ -164,7 +172,7 @@ extern "C" int kmat_db_build_device(int device, int kmer_len, int tid_bytes, uin
         KM_CUDA(cudaMalloc((void **)&db->d_pool, pool_words * 4));
         KM_CUDA(cudaMemcpy(db->d_pool, d_pool, pool_words * 4, cudaMemcpyDeviceToDevice));
     }
-    int rc = km_db_alloc_and_insert(db, d_kmers, d_payload, n);
+    int rc = km_db_alloc_and_insert(db, d_kmers, d_payload, n, shard_index, shard_count);
     if (rc != KMAT_OK) { kmat_db_free(db); return rc; }
     *out = db;
     return KMAT_OK;
@@ -173,7 +181,7 @@ extern "C" int kmat_db_build_device(int device, int kmer_len, int tid_bytes, uin
 // Host table -> device.  List pool record: 16-bit ids: [u16 count][u16 id]*count ; 32-bit ids: [u32 count][u32 id]*count,
 // padded to 4 bytes; a record of <= 32 bytes never straddles a 32-byte sector, so a list fetch is one sector.
 extern "C" int kmat_db_upload(const kmat_table *t, int device, int shard_index, int shard_count, kmat_db **out) {
-    if (!t || !out || shard_count < 1 || shard_index < 0 || shard_index >= shard_count) { kmat_set_error("kmat_db_upload: bad argument"); return KMAT_ERR_ARG; }
+    if (!t || !out || shard_count < 1 || shard_count > KM_MAX_SHARDS || shard_index < 0 || shard_index >= shard_count) { kmat_set_error("kmat_db_upload: bad argument"); return KMAT_ERR_ARG; }
     if (kmat_device_count() <= device) { kmat_set_error("CUDA device %d not available", device); return KMAT_ERR_NO_DEVICE; }
     if (t->kmer_len < 8 || t->kmer_len > 28) { kmat_set_error("k-mer length %d unsupported", t->kmer_len); return KMAT_ERR_UNSUPPORTED; }
     std::vector<uint64_t> kmers; std::vector<uint32_t> payload, pool;
@@ -222,7 +230,9 @@ extern "C" int kmat_db_upload(const kmat_table *t, int device, int shard_index, 
         KM_CUDA(cudaMalloc((void **)&d_pool, pool.size() * 4));
         KM_CUDA(cudaMemcpy(d_pool, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice));
     }
-    int rc = kmat_db_build_device(device, t->kmer_len, t->tid_bytes, n, d_k, d_p, d_pool, pool.size(), (uint32_t)stored.size(), out);
+    // the host loop above already kept this shard's k-mers only (and only their lists), so no device-side filter
+    int rc = kmat_db_build_device(device, t->kmer_len, t->tid_bytes, n, d_k, d_p, d_pool, pool.size(), (uint32_t)stored.size(), 0, 1, out);
+    if (rc == KMAT_OK) { (*out)->shard_index = shard_index; (*out)->shard_count = shard_count; }
     cudaFree(d_k); cudaFree(d_p); cudaFree(d_pool);
     if (rc == KMAT_OK) (*out)->stored_tids = stored;
     return rc;
@@ -326,6 +336,7 @@ struct KmProbeParams {
     unsigned long long *long_sets; uint32_t long_slots;   // global dedup sets for long reads: one per warp in the grid
     KmStatsDev *stats;             // optional
     int do_probe;
+    uint64_t *xq;                  // DB-sharded mode (with do_probe == 0): mixed k-mer of every first occurrence, per base offset
 };
 
 __device__ __forceinline__ int km_code(unsigned char ch) {
@@ -452,6 +463,7 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32) km_encode_probe_kernel(Km
             }
             if (p >= 0 && j < len) {
                 P.hit[off + p] = hw;
+                if (P.xq && first) P.xq[off + p] = km_mix(canon, kmer_bits);
                 if (P.out_kmers) { P.out_kmers[off + p] = ok ? canon : 0; P.out_flags[off + p] = ok ? (first ? 1 : 2) : 0; }
             }
             prev = cur; pinv = cinv; pgc = cgc;
@@ -635,7 +647,10 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
                     }
                 }
             }
-            if (p >= 0 && j < len) P.hit[off + p] = hw;
+            if (p >= 0 && j < len) {
+                P.hit[off + p] = hw;
+                if (P.xq && ((first >> c) & 1)) P.xq[off + p] = xk[c];
+            }
         }
         valid = km_warp_sum(valid); vgc = km_warp_sum(vgc); vtot = km_warp_sum(vtot);
         if (lane == 0) {
@@ -677,11 +692,11 @@ static int km_launch_fast(const KmProbeParams &P, int ctas_per_sm, cudaStream_t 
 
 int km_launch_encode_probe(const kmat_db *db, const char *d_bases, const uint64_t *d_offs, uint32_t n_reads, uint32_t max_len,
                            uint32_t *d_hit, int2 *d_hdr, uint64_t *d_kmers, uint8_t *d_flags, unsigned long long *d_long_sets,
-                           uint32_t long_slots, int grid, KmStatsDev *d_stats, int do_probe, cudaStream_t stream, int ctas_per_sm) {
+                           uint32_t long_slots, int grid, KmStatsDev *d_stats, int do_probe, cudaStream_t stream, int ctas_per_sm, uint64_t *d_xq) {
     KmProbeParams P;
     P.db = km_db_dev(db); P.bases = d_bases; P.offs = d_offs; P.n_reads = n_reads; P.hit = d_hit; P.hdr = d_hdr;
     P.out_kmers = d_kmers; P.out_flags = d_flags; P.long_sets = d_long_sets; P.long_slots = long_slots; P.stats = d_stats;
-    P.do_probe = do_probe;
+    P.do_probe = do_probe; P.xq = d_xq;
     const bool fast = !d_kmers && !d_flags && max_len <= 256 && db->kmer_len <= 24 && !getenv("KMAT_NO_FAST_PROBE");
     int rc = KMAT_OK;
     if (fast && max_len <= 160) rc = d_stats ? km_launch_fast<5, 4096, true>(P, ctas_per_sm, stream) : km_launch_fast<5, 4096, false>(P, ctas_per_sm, stream);
@@ -720,7 +735,7 @@ extern "C" int kmat_encode_batch(const kmat_db *db, const char *bases, const uin
         long_slots = 1024; while (long_slots < 2 * max_np) long_slots <<= 1;
         KM_CUDA(cudaMalloc((void **)&d_long, (size_t)grid * KM_PROBE_WARPS * long_slots * 8));
     }
-    int rc = km_launch_encode_probe(db, d_b, d_o, n_reads, max_np, d_hit, d_hdr, d_k, d_f, d_long, long_slots, grid, nullptr, 0, 0, 0);
+    int rc = km_launch_encode_probe(db, d_b, d_o, n_reads, max_np, d_hit, d_hdr, d_k, d_f, d_long, long_slots, grid, nullptr, 0, 0, 0, nullptr);
     if (rc == KMAT_OK) {
         std::vector<int2> hdr(n_reads);
         KM_CUDA(cudaMemcpy(hdr.data(), d_hdr, (size_t)n_reads * sizeof(int2), cudaMemcpyDeviceToHost));

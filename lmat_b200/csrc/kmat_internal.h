@@ -124,4 +124,15 @@ KM_HD uint64_t km_mix(uint64_t x, int kmer_bits) {
     x ^= x >> s;
     return x;
 }
+// Owner shard of a mixed key x = km_mix(kmer) in DB-sharded mode (SURVEY.md 8(e) mode B: hash prefix of the canonical
+// k-mer; a raw k-mer prefix would be skewed).  A second multiply/xor-shift round so that owner and bucket index (the top
+// bits of x) are independent; multiply-shift range reduction instead of a modulo.
+#define KM_MAX_SHARDS 16
+KM_HD uint32_t km_owner_of_x(uint64_t x, uint32_t n_shards) {
+    uint64_t y = x * 0xA24BAED4963EE407ull;
+    y ^= y >> 29;
+    y *= 0x9FB21C651E98DF25ull;
+    y ^= y >> 32;
+    return (uint32_t)(((y >> 32) * (uint64_t)n_shards) >> 32);
+}
 #endif

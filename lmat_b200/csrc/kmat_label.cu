@@ -783,8 +783,11 @@ __global__ void __launch_bounds__(KS_THREADS) km_score_kernel(KmScoreParams P) {
 // ---------------------------------------------------------------------------------------------
 // kmat_ctx
 // ---------------------------------------------------------------------------------------------
+struct KmShardState;
+static void km_shard_free(KmShardState *);
 struct kmat_ctx {
     const kmat_db *db = nullptr;
+    KmShardState *shard = nullptr;           // DB-sharded mode buffers (kmat_shard.cuh), allocated on first use
     int device = 0;
     kmat_opts opt{};
     cudaStream_t stream = nullptr;
@@ -940,6 +943,7 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
         if (sl.ev_comp) cudaEventDestroy(sl.ev_comp);
         if (sl.ev_d2h) cudaEventDestroy(sl.ev_d2h);
     }
+    km_shard_free(c->shard);
     cudaFree(c->d_hit); cudaFree(c->d_hdr); cudaFree(c->d_out_dev);
     if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
     if (c->st_d2h) cudaStreamDestroy(c->st_d2h);
@@ -986,7 +990,9 @@ struct KmPass {
     bool reset;                 // zero the candidate cursors and the statistics first
 };
 
-static int km_run_device(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
+// Buffers of a pass (hit words, per-read headers, long-read scratch) and the reset of cursors / statistics.
+// variant: which candidate-kernel instantiation the longest read needs (0: <= 160 positions, 1: <= 320, 2: any).
+static int km_prepare_pass(kmat_ctx *c, const KmPass &L, cudaStream_t st, uint32_t **hit, int *variant) {
     int rc;
     if ((rc = km_grow(&c->d_hit, &c->cap_hit, L.total_bases + 1)) != KMAT_OK) return rc;
     { uint64_t cap = c->cap_hdr; if ((rc = km_grow(&c->d_hdr, &cap, L.n_reads)) != KMAT_OK) return rc; c->cap_hdr = (uint32_t)cap; }
@@ -1004,10 +1010,10 @@ static int km_run_device(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
         KM_CUDA(cudaMemsetAsync(c->d_cursors, 0, 16, st));
         if (c->collect_stats) KM_CUDA(cudaMemsetAsync(c->d_stats, 0, sizeof(KmStatsDev), st));
     }
-    uint32_t *hit = c->d_hit - L.first_off;
+    *hit = c->d_hit - L.first_off;
     const int max_pos = (int)L.max_len - c->db->kmer_len + 1;
-    const int variant = max_pos <= 5 * 32 ? 0 : max_pos <= 10 * 32 ? 1 : 2;
-    if (variant == 2) {
+    *variant = max_pos <= 5 * 32 ? 0 : max_pos <= 10 * 32 ? 1 : 2;
+    if (*variant == 2) {
         // long reads: the position masks live in a per-warp global scratch
         const uint32_t cap = ((uint32_t)max_pos + 31u) & ~31u;
         if (cap > c->long_mask_cap) {
@@ -1017,6 +1023,43 @@ static int km_run_device(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
             c->long_mask_cap = cap;
         }
     }
+    return KMAT_OK;
+}
+
+// K3 + K4 over reads [r0, r0 + n) of a pass on stream s2.  pool2 / pool2_mul override the ctx's resolved list pool
+// (DB-sharded mode: the records fetched from the owning shards for this batch).  ev_mid, if set, is recorded between
+// the two kernels.
+static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint32_t n, uint32_t *hit, int variant, int cand_ctas_per_sm,
+                                cudaStream_t s2, const uint32_t *pool2, int pool2_mul, cudaEvent_t ev_mid) {
+    KmScoreParams P;
+    P.C = km_ctx_dev(c);
+    if (pool2) { P.C.pool2 = pool2; P.C.pool2_mul = pool2_mul; }
+    P.offs = L.d_offs + r0; P.n_reads = n; P.hit = hit; P.hdr = c->d_hdr + r0; P.out = L.d_out + r0;
+    P.cands = c->d_cands; P.cand_cursor = c->d_cursors; P.cand_cap = c->cap_cands;
+    P.lin = c->d_lin; P.lin_cursor = c->d_cursors + 1; P.lin_cap = c->cap_lin;
+    P.stats = c->collect_stats ? c->d_stats : nullptr;
+    P.long_masks = nullptr; P.long_cap = 0;
+    const int want_grid = (int)((n + KB_WARPS - 1) / KB_WARPS);
+    const int g0 = cand_ctas_per_sm > 0 ? std::min(c->cand_grid[0], cand_ctas_per_sm * c->sms) : c->cand_grid[0];
+    if (variant == 0) km_cand_kernel<5><<<std::max(1, std::min(g0, want_grid)), KB_WARPS * 32, 0, s2>>>(P);
+    else if (variant == 1) km_cand_kernel<10><<<std::max(1, std::min(c->cand_grid[1], want_grid)), KB_WARPS * 32, 0, s2>>>(P);
+    else {
+        P.long_masks = c->d_long_masks; P.long_cap = c->long_mask_cap;
+        km_cand_kernel<0><<<std::max(1, std::min(c->cand_grid[2], want_grid)), KB_WARPS * 32, 0, s2>>>(P);
+    }
+    g_km_launches++;
+    KM_CUDA(cudaGetLastError());
+    if (ev_mid) KM_CUDA(cudaEventRecord(ev_mid, s2));
+    km_score_kernel<<<(n + KS_THREADS - 1) / KS_THREADS, KS_THREADS, 0, s2>>>(P);
+    g_km_launches++;
+    KM_CUDA(cudaGetLastError());
+    return KMAT_OK;
+}
+
+static int km_run_device(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
+    int rc, variant;
+    uint32_t *hit;
+    if ((rc = km_prepare_pass(c, L, st, &hit, &variant)) != KMAT_OK) return rc;
     // Sub-batches.  Serial: probe, candidates, scoring one after the other on `st` (per-kernel times through ev[]).
     // Pipelined (short reads, large passes): the probe kernel keeps ~1 CTA per SM (it is bound by the table request
     // rate and loses ~15 % at 8 warps per SM) and the other two kernels work on the previous sub-batch in the rest of
@@ -1033,32 +1076,12 @@ static int km_run_device(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
         if (r1 == r0) continue;
         const uint32_t n = r1 - r0;
         rc = km_launch_encode_probe(c->db, L.d_bases, L.d_offs + r0, n, L.max_len, hit, c->d_hdr + r0, nullptr, nullptr, c->d_long_sets, c->long_slots,
-                                    km_probe_grid(n), c->collect_stats ? c->d_stats : nullptr, 1, st, piped ? 1 : 0);
+                                    km_probe_grid(n), c->collect_stats ? c->d_stats : nullptr, 1, st, piped ? 1 : 0, nullptr);
         if (rc != KMAT_OK) return rc;
         cudaStream_t s2 = st;
         if (piped) { KM_CUDA(cudaEventRecord(c->ev_sub[sb], st)); KM_CUDA(cudaStreamWaitEvent(c->st_aux, c->ev_sub[sb], 0)); s2 = c->st_aux; }
         else KM_CUDA(cudaEventRecord(c->ev[1], st));
-        KmScoreParams P;
-        P.C = km_ctx_dev(c);
-        P.offs = L.d_offs + r0; P.n_reads = n; P.hit = hit; P.hdr = c->d_hdr + r0; P.out = L.d_out + r0;
-        P.cands = c->d_cands; P.cand_cursor = c->d_cursors; P.cand_cap = c->cap_cands;
-        P.lin = c->d_lin; P.lin_cursor = c->d_cursors + 1; P.lin_cap = c->cap_lin;
-        P.stats = c->collect_stats ? c->d_stats : nullptr;
-        P.long_masks = nullptr; P.long_cap = 0;
-        const int want_grid = (int)((n + KB_WARPS - 1) / KB_WARPS);
-        const int g0 = piped ? std::min(c->cand_grid[0], 2 * c->sms) : c->cand_grid[0];
-        if (variant == 0) km_cand_kernel<5><<<std::max(1, std::min(g0, want_grid)), KB_WARPS * 32, 0, s2>>>(P);
-        else if (variant == 1) km_cand_kernel<10><<<std::max(1, std::min(c->cand_grid[1], want_grid)), KB_WARPS * 32, 0, s2>>>(P);
-        else {
-            P.long_masks = c->d_long_masks; P.long_cap = c->long_mask_cap;
-            km_cand_kernel<0><<<std::max(1, std::min(c->cand_grid[2], want_grid)), KB_WARPS * 32, 0, s2>>>(P);
-        }
-        g_km_launches++;
-        KM_CUDA(cudaGetLastError());
-        if (!piped) KM_CUDA(cudaEventRecord(c->ev[3], st));
-        km_score_kernel<<<(n + KS_THREADS - 1) / KS_THREADS, KS_THREADS, 0, s2>>>(P);
-        g_km_launches++;
-        KM_CUDA(cudaGetLastError());
+        if ((rc = km_launch_cand_score(c, L, r0, n, hit, variant, piped ? 2 : 0, s2, nullptr, 0, piped ? nullptr : c->ev[3])) != KMAT_OK) return rc;
     }
     if (piped) {
         KM_CUDA(cudaEventRecord(c->ev_join, c->st_aux)); KM_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
@@ -1252,3 +1275,5 @@ extern "C" void *kmat_host_alloc(size_t bytes) {
     return p;
 }
 extern "C" void kmat_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+#include "kmat_shard.cuh"

@@ -31,6 +31,7 @@ struct kmat_db {
     uint64_t *d_stash_x = nullptr; uint32_t *d_stash_hit = nullptr; uint32_t n_stash = 0;   // overflow stash (see km_probe_x)
     int prefix_shift = 13;
     uint32_t n_sid = 65536;
+    int shard_index = 0, shard_count = 1;  // DB-sharded mode: this table holds the k-mers with kmat_shard_of() == shard_index
     std::vector<uint32_t> stored_tids;     // 32-bit tables: dense stored id -> tid
 };
 
@@ -40,6 +41,7 @@ KmDbDev km_db_dev(const kmat_db *db);
 int km_probe_grid(uint32_t n_reads);
 int km_launch_encode_probe(const kmat_db *db, const char *d_bases, const uint64_t *d_offs, uint32_t n_reads, uint32_t max_len,
                            uint32_t *d_hit, int2 *d_hdr, uint64_t *d_kmers, uint8_t *d_flags, unsigned long long *d_long_sets,
-                           uint32_t long_slots, int grid, KmStatsDev *d_stats, int do_probe, cudaStream_t stream, int ctas_per_sm /* 0 = all that fit */);
+                           uint32_t long_slots, int grid, KmStatsDev *d_stats, int do_probe, cudaStream_t stream, int ctas_per_sm /* 0 = all that fit */,
+                           uint64_t *d_xq /* DB-sharded mode: mixed first-occurrence k-mers per base offset, else NULL */);
 #define KM_PROBE_WARPS_HOST 8
 #endif

@@ -1,0 +1,287 @@
+// kmat_shard.cuh -- DB-sharded mode (SURVEY.md 8(e) mode B); included at the end of kmat_label.cu.
+//
+// When the table does not fit one GPU it is partitioned by kmat_shard_of() (a hash of the canonical k-mer) and every
+// rank holds one shard.  A batch of reads stays on its "home" rank; only k-mers travel:
+//
+//   home   kmat_shard_encode   K1 (encode + dedup, no probe) -> first-occurrence k-mers, grouped by owner shard
+//   ------ exchange 1: all-to-all of the (mixed) k-mers, 8 bytes each -------------------------------------------
+//   owner  kmat_shard_serve    probe the local shard; reply = one hit word per query (+ for list hits the resolved
+//                              list record, packed per source rank)
+//   ------ exchange 2: all-to-all of the hit words (4 bytes each) and of the list records ------------------------
+//   home   kmat_shard_finish   hit words back to their read positions, then K3 / K4 exactly as in replicated mode,
+//                              reading list records from the received payload instead of the local resolved pool
+//
+// The exchange itself is the caller's: NCCL all-to-all between one-process-per-GPU ranks (lmat_b200/sharded.py over
+// torch.distributed) or peer copies inside one process.  Everything after the lookup stays on the home rank, so the
+// results are bit-identical to the replicated table's.
+#include <cub/device/device_scan.cuh>
+
+struct KmShardSeg { unsigned long long start[KM_MAX_SHARDS + 1]; };
+
+struct KmShardState {
+    // home side
+    uint64_t *d_xq = nullptr; uint64_t cap_xq = 0;          // mixed k-mer per base offset (first occurrences only)
+    uint64_t *d_q = nullptr; uint64_t cap_q = 0;            // queries grouped by owner
+    uint32_t *d_origin = nullptr; uint64_t cap_origin = 0;  // base offset of each query, relative to the pass
+    unsigned long long *d_counts = nullptr;                 // [0..16) counts, [16..32) scatter cursors
+    KmPass pass{}; uint32_t *hit = nullptr; int variant = 0; int n_shards = 0;
+    uint64_t counts[KM_MAX_SHARDS] = {}; uint64_t n_q = 0;
+    bool open = false;
+    // owner side
+    uint32_t *d_reply = nullptr; uint64_t cap_reply = 0;
+    uint32_t *d_len = nullptr, *d_pos = nullptr; uint64_t cap_len = 0, cap_pos = 0;
+    uint32_t *d_payload = nullptr; uint64_t cap_payload = 0;
+    void *d_scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+    unsigned long long *d_bounds = nullptr;                 // payload word offset at every source boundary
+};
+
+static void km_shard_free(KmShardState *s) {
+    if (!s) return;
+    cudaFree(s->d_xq); cudaFree(s->d_q); cudaFree(s->d_origin); cudaFree(s->d_counts); cudaFree(s->d_reply); cudaFree(s->d_len);
+    cudaFree(s->d_pos); cudaFree(s->d_payload); cudaFree(s->d_scan_tmp); cudaFree(s->d_bounds);
+    delete s;
+}
+static int km_shard_state(kmat_ctx *c, KmShardState **out) {
+    if (!c->shard) {
+        KmShardState *s = new KmShardState();
+        c->shard = s;
+        KM_CUDA(cudaMalloc((void **)&s->d_counts, 2 * KM_MAX_SHARDS * sizeof(unsigned long long)));
+        KM_CUDA(cudaMalloc((void **)&s->d_bounds, (KM_MAX_SHARDS + 1) * sizeof(unsigned long long)));
+    }
+    *out = c->shard;
+    return KMAT_OK;
+}
+
+__device__ __forceinline__ int km_seg_of(const KmShardSeg &g, int n, unsigned long long i) {
+    int s = 0;
+#pragma unroll 1
+    while (s + 1 < n && i >= g.start[s + 1]) s++;
+    return s;
+}
+
+// ---- home: count and scatter the first-occurrence k-mers by owner -------------------------------------------------
+__global__ void __launch_bounds__(256) km_shard_count_kernel(const uint32_t *__restrict__ hit, const uint64_t *__restrict__ xq, uint64_t n_pos,
+                                                             uint32_t n_shards, unsigned long long *counts) {
+    __shared__ unsigned int hist[KM_MAX_SHARDS];
+    if (threadIdx.x < KM_MAX_SHARDS) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_pos; i += (uint64_t)gridDim.x * blockDim.x)
+        if (hit[i] == KM_HIT_MISS) atomicAdd(&hist[km_owner_of_x(xq[i], n_shards)], 1u);
+    __syncthreads();
+    if (threadIdx.x < n_shards && hist[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) km_shard_scatter_kernel(const uint32_t *__restrict__ hit, const uint64_t *__restrict__ xq, uint64_t n_pos,
+                                                               uint32_t n_shards, KmShardSeg base, unsigned long long *cursors,
+                                                               uint64_t *q, uint32_t *origin) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t first = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31);           // warp-uniform loop bounds
+    for (uint64_t i0 = first; i0 < n_pos; i0 += stride) {
+        const uint64_t i = i0 + lane;
+        const bool m = i < n_pos && hit[i] == KM_HIT_MISS;
+        const uint64_t x = m ? xq[i] : 0;
+        const uint32_t owner = m ? km_owner_of_x(x, n_shards) : 0xFFFFFFFFu;
+        const uint32_t act = __ballot_sync(KM_FULL, m);
+        if (m) {
+            const uint32_t grp = __match_any_sync(act, owner);                                   // one atomic per owner and warp
+            const int leader = __ffs(grp) - 1;
+            unsigned long long b = 0;
+            if (lane == leader) b = atomicAdd(&cursors[owner], (unsigned long long)__popc(grp));
+            b = ((unsigned long long)__shfl_sync(grp, (uint32_t)(b >> 32), leader) << 32) | __shfl_sync(grp, (uint32_t)b, leader);
+            const unsigned long long dst = base.start[owner] + b + __popc(grp & ((1u << lane) - 1));
+            q[dst] = x; origin[dst] = (uint32_t)i;
+        }
+    }
+}
+
+// ---- owner: probe, measure, pack ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) km_shard_probe_kernel(KmDbDev db, const uint32_t *__restrict__ pool2, int mul, int permissive,
+                                                             const uint64_t *__restrict__ q, uint64_t n, uint32_t *reply, uint32_t *len) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { len[i] = 0; return; }                    // sentinel for the exclusive scan
+    uint32_t extra;
+    const uint32_t hw = km_probe_x(db, q[i], extra);
+    uint32_t l = 0;
+    if (hw != KM_HIT_MISS && (hw & KM_HIT_LIST)) {
+        const uint32_t *rec = pool2 + (size_t)(hw & 0x7FFFFFFFu) * mul;
+        const uint32_t h = rec[0];
+        if (h == KR_ERR_BAD) l = 1;                         // the home rank reports the bad stored id
+        else l = permissive ? 2 + (h & 0xFFFFu) + rec[1] : 1 + (h & 0xFFFFu);
+    }
+    reply[i] = hw; len[i] = l;
+}
+__global__ void __launch_bounds__(256) km_shard_pack_kernel(const uint32_t *__restrict__ pool2, int mul, uint32_t *reply, const uint32_t *__restrict__ len,
+                                                            const uint32_t *__restrict__ pos, uint64_t n, KmShardSeg src, int n_shards,
+                                                            uint32_t *payload, unsigned long long *bounds) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i <= (uint64_t)n_shards) bounds[i] = pos[src.start[i]];             // payload word offset at every source boundary
+    if (i >= n) return;
+    const uint32_t l = len[i];
+    if (!l) return;
+    const uint32_t hw = reply[i];
+    const uint32_t *rec = pool2 + (size_t)(hw & 0x7FFFFFFFu) * mul;
+    const uint32_t at = pos[i];
+    for (uint32_t w = 0; w < l; w++) payload[at + w] = rec[w];
+    const int s = km_seg_of(src, n_shards, i);
+    reply[i] = KM_HIT_LIST | (at - pos[src.start[s]]);                      // offset inside the source's own payload segment
+}
+
+// ---- home: replies back to their read positions --------------------------------------------------------------------
+__global__ void __launch_bounds__(256) km_shard_fix_kernel(const uint32_t *__restrict__ reply, const uint32_t *__restrict__ origin, uint64_t n_q,
+                                                           KmShardSeg qseg, KmShardSeg pbase, int n_shards, uint32_t *hit) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n_q) return;
+    uint32_t hw = reply[i];
+    if (hw != KM_HIT_MISS && (hw & KM_HIT_LIST)) {
+        const int s = km_seg_of(qseg, n_shards, i);
+        hw = KM_HIT_LIST | (uint32_t)(pbase.start[s] + (hw & 0x7FFFFFFFu));
+    }
+    hit[origin[i]] = hw;
+}
+
+extern "C" int kmat_shard_encode(kmat_ctx *c, const char *d_bases, const uint64_t *d_offs, uint32_t n_reads, uint64_t total_bases,
+                                 uint32_t max_read_len, int n_shards, const uint64_t **d_queries, uint64_t *counts, void *stream) {
+    if (!c || !d_offs || !counts || !d_queries || n_shards < 1 || n_shards > KM_MAX_SHARDS || (n_reads && !d_bases)) { kmat_set_error("kmat_shard_encode: bad argument"); return KMAT_ERR_ARG; }
+    if (total_bases >= (1ull << 32)) { kmat_set_error("kmat_shard_encode: a sharded pass is limited to 2^32 bases (got %llu); split the batch", (unsigned long long)total_bases); return KMAT_ERR_UNSUPPORTED; }
+    if (c->db->shard_count != n_shards) { kmat_set_error("kmat_shard_encode: the ctx's table is shard %d of %d, not of %d", c->db->shard_index, c->db->shard_count, n_shards); return KMAT_ERR_ARG; }
+    KM_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    KmShardState *s;
+    int rc;
+    if ((rc = km_shard_state(c, &s)) != KMAT_OK) return rc;
+    for (int i = 0; i < n_shards; i++) counts[i] = 0;
+    *d_queries = nullptr;
+    s->open = false; s->n_q = 0; s->n_shards = n_shards;
+    if (!n_reads) { s->pass = KmPass{d_bases, d_offs, 0, 0, 0, max_read_len, nullptr, true}; s->open = true; return KMAT_OK; }
+    if ((rc = km_reserve_cands(c, n_reads)) != KMAT_OK) return rc;
+    s->pass = KmPass{d_bases, d_offs, n_reads, 0, total_bases, max_read_len, nullptr, true};
+    if ((rc = km_prepare_pass(c, s->pass, st, &s->hit, &s->variant)) != KMAT_OK) return rc;
+    if ((rc = km_grow(&s->d_xq, &s->cap_xq, total_bases + 1)) != KMAT_OK) return rc;
+    // positions no k-mer starts at (the last k-1 bases of a read) are never written by the encode kernel
+    KM_CUDA(cudaMemsetAsync(c->d_hit, 0xFF, (size_t)total_bases * 4, st));
+    rc = km_launch_encode_probe(c->db, d_bases, d_offs, n_reads, max_read_len, s->hit, c->d_hdr, nullptr, nullptr, c->d_long_sets, c->long_slots,
+                                km_probe_grid(n_reads), nullptr, 0, st, 0, s->d_xq);
+    if (rc != KMAT_OK) return rc;
+    KM_CUDA(cudaMemsetAsync(s->d_counts, 0, 2 * KM_MAX_SHARDS * sizeof(unsigned long long), st));
+    const int grid = (int)std::min<uint64_t>((total_bases + 255) / 256, 148ull * 8);
+    km_shard_count_kernel<<<grid, 256, 0, st>>>(c->d_hit, s->d_xq, total_bases, (uint32_t)n_shards, s->d_counts);
+    g_km_launches++;
+    unsigned long long h_counts[KM_MAX_SHARDS];
+    KM_CUDA(cudaMemcpyAsync(h_counts, s->d_counts, sizeof h_counts, cudaMemcpyDeviceToHost, st));
+    KM_CUDA(cudaStreamSynchronize(st));
+    KmShardSeg base;
+    unsigned long long tot = 0;
+    for (int i = 0; i <= KM_MAX_SHARDS; i++) { base.start[i] = tot; if (i < n_shards) { counts[i] = s->counts[i] = h_counts[i]; tot += h_counts[i]; } }
+    s->n_q = tot;
+    if ((rc = km_grow(&s->d_q, &s->cap_q, tot + 1)) != KMAT_OK) return rc;
+    if ((rc = km_grow(&s->d_origin, &s->cap_origin, tot + 1)) != KMAT_OK) return rc;
+    km_shard_scatter_kernel<<<grid, 256, 0, st>>>(c->d_hit, s->d_xq, total_bases, (uint32_t)n_shards, base, s->d_counts + KM_MAX_SHARDS, s->d_q, s->d_origin);
+    g_km_launches++;
+    KM_CUDA(cudaGetLastError());
+    *d_queries = s->d_q;
+    s->open = true;
+    return KMAT_OK;
+}
+
+extern "C" int kmat_shard_serve(kmat_ctx *c, const uint64_t *d_queries, const uint64_t *counts, int n_shards, const uint32_t **d_reply,
+                                const uint32_t **d_payload, uint64_t *payload_counts, void *stream) {
+    if (!c || !counts || !d_reply || !d_payload || !payload_counts || n_shards < 1 || n_shards > KM_MAX_SHARDS) { kmat_set_error("kmat_shard_serve: bad argument"); return KMAT_ERR_ARG; }
+    KM_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    KmShardState *s;
+    int rc;
+    if ((rc = km_shard_state(c, &s)) != KMAT_OK) return rc;
+    KmShardSeg src;
+    unsigned long long n = 0;
+    for (int i = 0; i <= KM_MAX_SHARDS; i++) { src.start[i] = n; if (i < n_shards) n += counts[i]; }
+    for (int i = 0; i < n_shards; i++) payload_counts[i] = 0;
+    *d_reply = nullptr; *d_payload = nullptr;
+    if (!n) return KMAT_OK;
+    if (!d_queries) { kmat_set_error("kmat_shard_serve: bad argument"); return KMAT_ERR_ARG; }
+    if (n >= (1ull << 32) - 1) { kmat_set_error("kmat_shard_serve: too many queries in one round"); return KMAT_ERR_UNSUPPORTED; }
+    if ((rc = km_grow(&s->d_reply, &s->cap_reply, n + 1)) != KMAT_OK) return rc;
+    if ((rc = km_grow(&s->d_len, &s->cap_len, n + 2)) != KMAT_OK) return rc;
+    if ((rc = km_grow(&s->d_pos, &s->cap_pos, n + 2)) != KMAT_OK) return rc;
+    const KmCtxDev X = km_ctx_dev(c);
+    const int grid = (int)((n + 1 + 255) / 256);
+    km_shard_probe_kernel<<<grid, 256, 0, st>>>(X.db, X.pool2, X.pool2_mul, X.opt.permissive != 0, d_queries, n, s->d_reply, s->d_len);
+    g_km_launches++;
+    size_t need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, s->d_len, s->d_pos, (uint32_t)(n + 1), st);
+    if (need > s->scan_tmp_bytes) {
+        KM_CUDA(cudaStreamSynchronize(st));
+        cudaFree(s->d_scan_tmp); s->d_scan_tmp = nullptr;
+        KM_CUDA(cudaMalloc(&s->d_scan_tmp, need + 256));
+        s->scan_tmp_bytes = need + 256;
+    }
+    size_t tmp_bytes = s->scan_tmp_bytes;
+    cub::DeviceScan::ExclusiveSum(s->d_scan_tmp, tmp_bytes, s->d_len, s->d_pos, (uint32_t)(n + 1), st);
+    g_km_launches++;
+    // total payload words = pos[n]; the payload buffer is sized before the pack kernel runs
+    uint32_t total_words = 0;
+    KM_CUDA(cudaMemcpyAsync(&total_words, s->d_pos + n, 4, cudaMemcpyDeviceToHost, st));
+    KM_CUDA(cudaStreamSynchronize(st));
+    if (total_words >= (1u << 31)) { kmat_set_error("kmat_shard_serve: list payload of %u words exceeds the 31-bit offset range; use smaller rounds", total_words); return KMAT_ERR_UNSUPPORTED; }
+    if ((rc = km_grow(&s->d_payload, &s->cap_payload, (uint64_t)total_words + 8)) != KMAT_OK) return rc;
+    km_shard_pack_kernel<<<grid, 256, 0, st>>>(X.pool2, X.pool2_mul, s->d_reply, s->d_len, s->d_pos, n, src, n_shards, s->d_payload, s->d_bounds);
+    g_km_launches++;
+    unsigned long long h_bounds[KM_MAX_SHARDS + 1];
+    KM_CUDA(cudaMemcpyAsync(h_bounds, s->d_bounds, sizeof h_bounds, cudaMemcpyDeviceToHost, st));
+    KM_CUDA(cudaStreamSynchronize(st));
+    KM_CUDA(cudaGetLastError());
+    for (int i = 0; i < n_shards; i++) payload_counts[i] = h_bounds[i + 1] - h_bounds[i];
+    *d_reply = s->d_reply; *d_payload = s->d_payload;
+    return KMAT_OK;
+}
+
+extern "C" int kmat_shard_finish(kmat_ctx *c, const uint32_t *d_reply, const uint32_t *d_payload, const uint64_t *payload_counts, int n_shards,
+                                 kmat_read_result *d_out, void *stream) {
+    if (!c || !payload_counts || n_shards < 1 || n_shards > KM_MAX_SHARDS) { kmat_set_error("kmat_shard_finish: bad argument"); return KMAT_ERR_ARG; }
+    KmShardState *s = c->shard;
+    if (!s || !s->open || s->n_shards != n_shards) { kmat_set_error("kmat_shard_finish: no open pass (call kmat_shard_encode first)"); return KMAT_ERR_ARG; }
+    KM_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    s->open = false;
+    if (!s->pass.n_reads) return KMAT_OK;
+    if (s->n_q && !d_reply) { kmat_set_error("kmat_shard_finish: bad argument"); return KMAT_ERR_ARG; }
+    int rc;
+    KmPass L = s->pass;
+    if (!d_out) {
+        uint64_t cap = c->cap_out_dev;
+        if ((rc = km_grow(&c->d_out_dev, &cap, L.n_reads)) != KMAT_OK) return rc;
+        c->cap_out_dev = (uint32_t)cap;
+        d_out = c->d_out_dev;
+    }
+    L.d_out = d_out;
+    KmShardSeg qseg, pbase;
+    unsigned long long a = 0, b = 0;
+    for (int i = 0; i <= KM_MAX_SHARDS; i++) { qseg.start[i] = a; pbase.start[i] = b; if (i < n_shards) { a += s->counts[i]; b += payload_counts[i]; } }
+    if (b >= (1ull << 31)) { kmat_set_error("kmat_shard_finish: list payload exceeds the 31-bit offset range; use smaller rounds"); return KMAT_ERR_UNSUPPORTED; }
+    if (s->n_q) {
+        km_shard_fix_kernel<<<(int)((s->n_q + 255) / 256), 256, 0, st>>>(d_reply, s->d_origin, s->n_q, qseg, pbase, n_shards, c->d_hit);
+        g_km_launches++;
+        KM_CUDA(cudaGetLastError());
+    }
+    KM_CUDA(cudaEventRecord(c->ev[0], st)); KM_CUDA(cudaEventRecord(c->ev[1], st));
+    // list records come from the received payload (mul 1); a batch without list hits never dereferences it
+    rc = km_launch_cand_score(c, L, 0, L.n_reads, s->hit, s->variant, 0, st, d_payload ? d_payload : c->d_pool2, d_payload ? 1 : c->pool2_mul, c->ev[3]);
+    if (rc != KMAT_OK) return rc;
+    KM_CUDA(cudaEventRecord(c->ev[2], st));
+    return KMAT_OK;
+}
+
+/* Results of the last finished sharded pass when kmat_shard_finish was called with d_out == NULL: device pointer of the
+ * n_reads results, plus the device candidate pairs (rank_label after sort) they index through cand_off. */
+extern "C" int kmat_ctx_device_results(kmat_ctx *c, const kmat_read_result **d_out, const kmat_pair **d_cands, uint64_t *n_cands) {
+    if (!c) return KMAT_ERR_ARG;
+    KM_CUDA(cudaSetDevice(c->device));
+    if (d_out) *d_out = c->d_out_dev;
+    if (d_cands) *d_cands = c->d_cands;
+    if (n_cands) {
+        unsigned long long cur[2] = {0, 0};
+        KM_CUDA(cudaMemcpy(cur, c->d_cursors, 16, cudaMemcpyDeviceToHost));
+        *n_cands = cur[0];
+    }
+    return KMAT_OK;
+}

@@ -1,0 +1,244 @@
+"""DB-sharded read labeling (SURVEY.md 8(e) mode B): the k-mer table is partitioned over the ranks by kmat_shard_of,
+reads stay on their home rank, query k-mers travel.
+
+One round over (a chunk of) a rank's reads:
+
+    home   ctx.shard_encode   encode + dedup, first-occurrence k-mers grouped by owner       [CUDA, libkmat]
+    ------ all-to-all: per-owner counts, then the k-mers (8 B each) ------------------------ [exchange]
+    owner  ctx.shard_serve    probe the local shard -> hit words + packed list records       [CUDA, libkmat]
+    ------ all-to-all: per-source payload sizes, hit words (4 B each), list records --------- [exchange]
+    home   ctx.shard_finish   hit words back to the read positions, candidate + scoring kernels
+
+`ShardedLabeler` is the per-rank driver.  The exchange is pluggable: `DistExchange` = torch.distributed
+all_to_all_single (NCCL over NVLink between one-process-per-GPU ranks; gloo in the CPU tests), `LocalExchange` =
+several ranks as threads of one process (tests on a single GPU; a single-process multi-GPU host).  The device phases
+are pluggable too (`CudaPhases` wraps the C ABI); the CPU tests drive the same protocol with a numpy stand-in.
+"""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+
+
+# ------------------------------------------------------------------------------------------------
+# exchanges
+# ------------------------------------------------------------------------------------------------
+class DistExchange:
+    """torch.distributed backend: all_to_all_single over the default (or a given) process group."""
+
+    def __init__(self, device, group=None):
+        import torch.distributed as dist
+        self.dist, self.group, self.device = dist, group, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def counts(self, send_counts):
+        import torch
+        s = torch.as_tensor(np.asarray(send_counts, dtype=np.int64), device=self.device)
+        r = torch.empty_like(s)
+        self.dist.all_to_all_single(r, s, group=self.group)
+        return r.cpu().numpy().astype(np.uint64)
+
+    def all_to_all(self, send, send_counts, recv_counts):
+        import torch
+        recv = torch.empty(int(np.sum(recv_counts)), dtype=send.dtype, device=send.device)
+        self.dist.all_to_all_single(recv, send, output_split_sizes=[int(x) for x in recv_counts],
+                                    input_split_sizes=[int(x) for x in send_counts], group=self.group)
+        return recv
+
+    def any(self, flag):
+        import torch
+        t = torch.tensor([1 if flag else 0], dtype=torch.int64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return bool(t.item())
+
+
+class LocalGroup:
+    """Shared state of `world` ranks running as threads of one process."""
+
+    def __init__(self, world):
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots = [None] * world
+
+
+class LocalExchange:
+    def __init__(self, group: LocalGroup, rank, sync=None):
+        self.g, self.rank, self.world = group, rank, group.world
+        self.sync = sync or (lambda: None)          # makes this rank's device work visible (torch.cuda.synchronize)
+
+    def counts(self, send_counts):
+        self.g.slots[self.rank] = np.asarray(send_counts, dtype=np.uint64).copy()
+        self.g.barrier.wait()
+        recv = np.array([self.g.slots[s][self.rank] for s in range(self.world)], dtype=np.uint64)
+        self.g.barrier.wait()
+        return recv
+
+    def all_to_all(self, send, send_counts, recv_counts):
+        import torch
+        offs = np.concatenate([[0], np.cumsum(np.asarray(send_counts, dtype=np.int64))])
+        self.sync()
+        self.g.slots[self.rank] = (send, offs)
+        self.g.barrier.wait()
+        parts = []
+        for s in range(self.world):
+            t, o = self.g.slots[s]
+            part = t[int(o[self.rank]):int(o[self.rank + 1])]
+            assert part.numel() == int(recv_counts[s])
+            parts.append(part.to(send.device))
+        recv = torch.cat(parts) if parts else send[:0]
+        self.sync()
+        self.g.barrier.wait()
+        return recv
+
+    def any(self, flag):
+        self.g.slots[self.rank] = bool(flag)
+        self.g.barrier.wait()
+        r = any(self.g.slots)
+        self.g.barrier.wait()
+        return r
+
+
+# ------------------------------------------------------------------------------------------------
+# device phases over the C ABI
+# ------------------------------------------------------------------------------------------------
+class _DevMem:
+    """Library-owned device memory as something torch.as_tensor() accepts."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+def _wrap(ptr, count, dtype, device):
+    import torch
+    if not count:
+        return torch.empty(0, dtype=dtype, device=device)
+    itemsize = torch.empty(0, dtype=dtype).element_size()
+    return torch.as_tensor(_DevMem(ptr, count * itemsize), device=device).view(dtype)
+
+
+class CudaPhases:
+    """The three libkmat phases of a round for one rank (api.Ctx over this rank's table shard)."""
+
+    def __init__(self, ctx, device, n_shards, stream=None):
+        self.ctx, self.device, self.n_shards, self.stream = ctx, device, n_shards, stream
+
+    def empty_round(self):
+        """Arguments of a round without reads (this rank still serves the others' queries)."""
+        import torch
+        if not hasattr(self, "_zero"):
+            self._zero = torch.zeros(2, dtype=torch.int64, device=self.device)
+        return (None, self._zero.data_ptr(), 0, 0, 0, None)
+
+    def encode(self, bases_ptr, offs_ptr, n_reads, total_bases, max_len):
+        import torch
+        q, counts = self.ctx.shard_encode(bases_ptr, offs_ptr, n_reads, total_bases, max_len, self.n_shards, self.stream)
+        return _wrap(q, int(counts.sum()), torch.int64, self.device), counts
+
+    def serve(self, queries, counts):
+        import torch
+        rep, pay, pc = self.ctx.shard_serve(queries.data_ptr() if queries.numel() else None, counts, self.stream)
+        return _wrap(rep, int(np.sum(counts)), torch.int32, self.device), _wrap(pay, int(pc.sum()), torch.int32, self.device), pc
+
+    def finish(self, reply, payload, payload_counts, out_ptr):
+        self.ctx.shard_finish(reply.data_ptr() if reply.numel() else None, payload.data_ptr() if payload.numel() else None,
+                              payload_counts, out_ptr, self.stream)
+
+
+# ------------------------------------------------------------------------------------------------
+# per-rank driver
+# ------------------------------------------------------------------------------------------------
+class ShardedLabeler:
+    """Runs the rounds of one rank.  Every rank of the group must call run() the same number of times; inside, ranks
+    keep exchanging (with empty contributions once their own reads are done) until every rank has finished."""
+
+    def __init__(self, phases, exchange, round_reads=1 << 20, round_bases=(1 << 32) - (1 << 20)):
+        self.ph, self.ex = phases, exchange
+        self.round_reads, self.round_bases = int(round_reads), int(round_bases)
+        self.lookups = 0            # first-occurrence k-mers this rank sent out (its unique lookups)
+        self.served = 0             # queries this rank answered
+        self.payload_words = 0
+        self.rounds = 0
+
+    def plan(self, offs_host):
+        """Cut reads [0, n) into rounds bounded by round_reads and round_bases; offs_host = n+1 absolute offsets."""
+        n = len(offs_host) - 1
+        out, r0 = [], 0
+        while r0 < n:
+            r1 = min(n, r0 + self.round_reads)
+            if int(offs_host[r1]) - int(offs_host[r0]) > self.round_bases:
+                r1 = int(np.searchsorted(offs_host, int(offs_host[r0]) + self.round_bases, side="right")) - 1
+                r1 = max(r1, r0 + 1)
+            out.append((r0, r1))
+            r0 = r1
+        return out
+
+    def run(self, rounds, round_args, on_round=None):
+        """rounds: list of (r0, r1); round_args(r0, r1) -> (*encode_args, out): what the phases' encode() takes (CudaPhases:
+        bases_ptr, offs_ptr, n_reads, total_bases, max_len with offsets local to the chunk) followed by what finish()
+        gets as its output argument.  on_round(r0, r1) is called after each finished round of this rank."""
+        i = 0
+        while True:
+            mine = i < len(rounds)
+            if not self.ex.any(mine):
+                break
+            if mine:
+                r0, r1 = rounds[i]
+                args = round_args(r0, r1)
+            else:
+                r0 = r1 = 0
+                args = self.ph.empty_round()
+            self._round(args)
+            if mine and on_round:
+                on_round(r0, r1)
+            i += 1
+            self.rounds += 1
+
+    def _round(self, args):
+        out_ptr = args[-1]
+        send_q, send_counts = self.ph.encode(*args[:-1])
+        self.lookups += int(np.sum(send_counts))
+        recv_counts = self.ex.counts(send_counts)                          # how many queries each source sends me
+        recv_q = self.ex.all_to_all(send_q, send_counts, recv_counts)
+        reply, payload, pay_counts = self.ph.serve(recv_q, recv_counts)    # pay_counts[s]: list words for source s
+        self.served += int(np.sum(recv_counts))
+        self.payload_words += int(np.sum(pay_counts))
+        my_pay_counts = self.ex.counts(pay_counts)                         # list words each owner sends me
+        my_reply = self.ex.all_to_all(reply, recv_counts, send_counts)     # hit words, in the order of send_q
+        my_payload = self.ex.all_to_all(payload, pay_counts, my_pay_counts)
+        self.ph.finish(my_reply, my_payload, my_pay_counts, out_ptr)
+
+
+def label_sequences(ctx, exchange, device, seqs, n_shards, round_reads=1 << 20):
+    """Convenience (tests, small inputs): label a list of reads through the sharded rounds of this rank and return
+    (results, candidates) like api.Ctx.label -- numpy arrays, cand_off indexing the returned candidate array."""
+    import torch
+    from . import api
+    lens = np.array([len(x) for x in seqs], dtype=np.int64)
+    offs_host = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    flat = b"".join(x if isinstance(x, bytes) else x.encode("latin-1") for x in seqs)
+    bases = torch.frombuffer(bytearray(flat if flat else b"\0"), dtype=torch.uint8).to(device)
+    lab = ShardedLabeler(CudaPhases(ctx, device, n_shards), exchange, round_reads=round_reads)
+    res_parts, cand_parts, keep = [], [], []
+    state = {"cands": 0}
+
+    def round_args(r0, r1):
+        o = torch.as_tensor(offs_host[r0:r1 + 1] - offs_host[r0], device=device)
+        keep.append(o)
+        return (bases.data_ptr() + int(offs_host[r0]), o.data_ptr(), r1 - r0, int(offs_host[r1] - offs_host[r0]),
+                int(lens[r0:r1].max()) if r1 > r0 else 0, None)
+
+    def on_round(r0, r1):
+        torch.cuda.synchronize(device)
+        optr, cptr, n_c = ctx.device_results()
+        res = _wrap(optr, (r1 - r0) * api.RESULT_DTYPE.itemsize, torch.uint8, device).cpu().numpy().view(api.RESULT_DTYPE).copy()
+        cands = _wrap(cptr, n_c * api.PAIR_DTYPE.itemsize, torch.uint8, device).cpu().numpy().view(api.PAIR_DTYPE).copy()
+        res["cand_off"] += np.uint64(state["cands"])
+        state["cands"] += len(cands)
+        res_parts.append(res)
+        cand_parts.append(cands)
+
+    lab.run(lab.plan(offs_host), round_args, on_round)
+    res = np.concatenate(res_parts) if res_parts else np.zeros(0, dtype=api.RESULT_DTYPE)
+    cands = np.concatenate(cand_parts) if cand_parts else np.zeros(0, dtype=api.PAIR_DTYPE)
+    return res, cands, lab

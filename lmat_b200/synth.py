@@ -176,14 +176,15 @@ def build_table_gpu(codes, anc_sid, k=20, chunk_genomes=None):
     return out
 
 
-def upload_table(tbl, device_index=0, k=20):
-    """kmat_db_build_device on the arrays of build_table_gpu."""
+def upload_table(tbl, device_index=0, k=20, shard_index=0, shard_count=1):
+    """kmat_db_build_device on the arrays of build_table_gpu (optionally one shard of the table only)."""
     pay = (tbl.payload_i64 & 0xFFFFFFFF).to(torch.int64)
     pay32 = torch.empty(tbl.n, dtype=torch.int32, device=tbl.kmers.device)
     pay32.copy_(torch.where(pay >= (1 << 31), pay - (1 << 32), pay).to(torch.int32))
     kmers = tbl.kmers.contiguous()
     torch.cuda.synchronize()
-    db = api.Db.build_device(device_index, k, 2, tbl.n, kmers.data_ptr(), pay32.data_ptr(), tbl.pool16.data_ptr(), tbl.pool_words)
+    db = api.Db.build_device(device_index, k, 2, tbl.n, kmers.data_ptr(), pay32.data_ptr(), tbl.pool16.data_ptr(), tbl.pool_words,
+                             shard_index=shard_index, shard_count=shard_count)
     torch.cuda.synchronize()
     return db
 

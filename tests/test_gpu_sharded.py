@@ -1,0 +1,90 @@
+"""GPU (-m gpu): DB-sharded mode (SURVEY 8(e) mode B).  The table is split into `world` shards by kmat_shard_of; the
+ranks run as threads of this process on one GPU (LocalExchange), each with its own shard, context and reads, and go
+through the same rounds (encode -> all-to-all -> serve -> all-to-all -> finish) as the one-process-per-GPU NCCL path.
+The labels must equal the replicated table's, which test_gpu_parity.py pins to the reference's own output."""
+import threading
+
+import numpy as np
+import pytest
+
+import scenarios as S
+from lmat_b200 import api, sharded
+from oracle import oracle_py as op
+from test_gpu_parity import make_ctx
+
+pytestmark = pytest.mark.gpu
+
+
+def run_ranks(world, fn):
+    out, err = [None] * world, [None] * world
+
+    def body(r):
+        try:
+            out[r] = fn(r)
+        except BaseException as e:       # noqa: BLE001 - re-raised in the main thread
+            err[r] = e
+            raise
+    ts = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    for e in err:
+        if e is not None:
+            raise e
+    assert all(o is not None for o in out), "a rank did not finish"
+    return out
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("opts", ["run_rl", "permissive", "prune3"])
+def test_sharded_labels_equal_replicated(golden_lists, world, opts):
+    import torch
+    g = golden_lists
+    t = api.Table.from_arrays(g.kmers, g.offs, g.ids, g.kmer_len, g.tid_bytes)
+    full = api.Db.upload(t)
+    shards = [api.Db.upload(t, 0, r, world) for r in range(world)]
+    assert sum(db.size for db in shards) == full.size == len(g.kmers)
+    assert all(0 < db.size < full.size for db in shards)
+    for r in range(world):                               # kmat_shard_of is the partition
+        own = np.array([api.lib().kmat_shard_of(int(k), g.kmer_len, world) == r for k in g.kmers[:2000]])
+        offs, ids = shards[r].lookup(g.kmers[:2000])
+        assert np.array_equal(np.diff(offs.astype(np.int64)) > 0, own)
+    hdrs, seqs = op.read_fasta_like_reference(g.paths["reads"])
+    seqs = seqs + ["", "ACGT", "N" * 40, seqs[0][:25]]
+    ref_ctx = make_ctx(g, full, opts)
+    res, cands, lin = ref_ctx.label(seqs)
+    want = ref_ctx.tails(res, cands, lin, prn_all=True)
+    # uneven split: rank 0 gets half of the reads, so the others keep serving after their own reads are done
+    cut = [0, len(seqs) // 2] + [len(seqs) // 2 + (len(seqs) - len(seqs) // 2) * (i + 1) // (world - 1) for i in range(world - 1)]
+    ctxs = [make_ctx(g, shards[r], opts) for r in range(world)]
+    grp = sharded.LocalGroup(world)
+
+    def rank(r):
+        ex = sharded.LocalExchange(grp, r, sync=lambda: torch.cuda.synchronize())
+        mine = seqs[cut[r]:cut[r + 1]]
+        rr, cc, lab = sharded.label_sequences(ctxs[r], ex, "cuda:0", mine, world, round_reads=97)
+        return ctxs[r].tails(rr, cc, np.zeros(0, dtype=api.PAIR_DTYPE), prn_all=True), lab
+
+    outs = run_ranks(world, rank)
+    got = [t for tails, _ in outs for t in tails]
+    assert got == want
+    labs = [lab for _, lab in outs]
+    assert sum(l.lookups for l in labs) == sum(l.served for l in labs) > 0
+    assert len({l.rounds for l in labs}) == 1            # every rank took part in every round
+
+
+def test_sharded_single_rank_is_a_plain_pass(golden_small):
+    """world = 1: the exchange is the identity; exercises the three phases against the replicated path."""
+    import torch
+    g = golden_small
+    db = api.Db.upload(api.Table.from_arrays(g.kmers, g.offs, g.ids, g.kmer_len, g.tid_bytes))
+    ctx = make_ctx(g, db, "run_rl")
+    hdrs, seqs = op.read_fasta_like_reference(g.paths["reads"])
+    res, cands, lin = ctx.label(seqs)
+    want = ctx.tails(res, cands, lin, prn_all=True)
+    grp = sharded.LocalGroup(1)
+    rr, cc, lab = sharded.label_sequences(ctx, sharded.LocalExchange(grp, 0, sync=lambda: torch.cuda.synchronize()), "cuda:0", seqs, 1)
+    assert ctx.tails(rr, cc, np.zeros(0, dtype=api.PAIR_DTYPE), prn_all=True) == want
+    mine = op.assemble_lines(hdrs, seqs, ctx.tails(rr, cc, np.zeros(0, dtype=api.PAIR_DTYPE), prn_all=True))
+    assert mine == g.golden_out("run_rl")
