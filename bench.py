@@ -48,6 +48,10 @@ def parse_args():
     ap.add_argument("--cpu-reads", type=int, default=200_000, help="reads in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--table-mode", default="replicated", choices=["replicated", "sharded"],
+                    help="replicated: every GPU holds the whole table (configs[1]); sharded: table partitioned by k-mer hash over "
+                         "the ranks, query k-mers exchanged with an NCCL all-to-all (configs[3] layout on the configs[1] table)")
+    ap.add_argument("--round-reads", type=int, default=1 << 20, help="reads per exchange round in sharded mode")
     ap.add_argument("--pipeline", type=int, default=1, help="sub-batches per pass (kmat_ctx_set_pipeline); -1 automatic, 1 serial")
     return ap.parse_args()
 
@@ -185,6 +189,81 @@ def run_cpu_sample(sample, workdir, threads):
     return n / dt, dt
 
 
+def sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, setup_s, launches0, tstream):
+    """DB-sharded arm: every rank holds 1/world of the table and its own reads; per round of --round-reads reads the
+    first-occurrence k-mers go to their owner ranks (all-to-all), hit words and list records come back (all-to-all)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lmat_b200 import api, sharded
+    n, L = reads.shape
+    stream = tstream.cuda_stream
+    ex = sharded.DistExchange(dev) if world > 1 else sharded.LocalExchange(sharded.LocalGroup(1), 0, sync=torch.cuda.synchronize)
+    lab = sharded.ShardedLabeler(sharded.CudaPhases(ctx, dev, world, stream), ex, round_reads=a.round_reads)
+    rr = min(a.round_reads, n)
+    offs_full = (torch.arange(rr + 1, device=dev, dtype=torch.int64) * L).contiguous()       # chunk-local offsets, every round
+    d_out = torch.empty(n * api.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    rounds = [(r0, min(n, r0 + rr)) for r0 in range(0, n, rr)]
+
+    def round_args(r0, r1):
+        return (reads.data_ptr() + r0 * L, offs_full.data_ptr(), r1 - r0, (r1 - r0) * L, L, d_out.data_ptr() + r0 * api.RESULT_DTYPE.itemsize)
+
+    def step():
+        lab.run(rounds, round_args)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx.set_stats(False)
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    lab.lookups = lab.served = lab.payload_words = lab.rounds = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    res = d_out.cpu().numpy().view(api.RESULT_DTYPE)
+    errs = int((res["status"] == 6).sum())
+    labeled = int((res["status"] == 5).sum())
+    t = torch.tensor([ms_total, 0.0], device=dev, dtype=torch.float64)
+    tot = torch.tensor([lab.lookups, lab.payload_words, errs, labeled], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_step = float(t[0].item()) / a.steps
+    lookups_step = int(tot[0].item()) / a.steps
+    if rank == 0:
+        hbm_peak, peak_src = measured_peaks()
+        value = world * n / (ms_step * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/f32", "data": "synthetic",
+            "config": {"workload": workload_name(a).replace("C2-replicated", "C2 table, DB-sharded"), "db_kmers": int(n_kmers), "db_lists": n_lists,
+                       "db_bytes_per_gpu": int(db.bytes), "db_kmers_this_shard": int(db.size), "reads_per_gpu": n, "read_len": L, "k": 20,
+                       "options": "run_rl.sh:243 (-j 30 -l 0 -b 1 -p, null models on)", "round_reads": a.round_reads,
+                       "l2_policy": "inputs larger than L2; no flush needed",
+                       "parallelism": f"table sharded x{world} by kmat_shard_of (k-mer hash), reads stay home; per round: all-to-all of query k-mers "
+                                      f"(8 B), all-to-all of hit words (4 B) + list records back ({'NCCL, torch.distributed' if world > 1 else 'single rank'})"},
+            "kmer_lookups_per_s": lookups_step / (ms_step * 1e-3), "lookups_per_read": lookups_step / (world * n),
+            "exchange_bytes_per_step": int(lookups_step * 12 + int(tot[1].item()) / a.steps * 4), "reads_error": int(tot[2].item()),
+            "reads_labeled": int(tot[3].item()),
+            "roofline": {"bound": "hbm", "kernel": "km_shard_probe_kernel", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
+                         "peak_source": peak_src, "note": "per-kernel split not measured in sharded mode; see the replicated line"},
+            "e2e": None, "gpu_launches": int(api.lib().kmat_launch_count() - launches0), "clocks": clocks, "setup_s": setup_s,
+        }
+        print(json.dumps(line), flush=True)
+
+
 def traffic_from_profile(a):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the encode+probe kernel, from the committed ncu
     pass of this same workload (profiles/traffic.json, written by tools/ncu_traffic.py); None for other workloads."""
@@ -263,7 +342,8 @@ def main():
         codes = synth.make_genomes_gpu(20240, tax, a.genomes, a.genome_len, dev)
         tbl = synth.build_table_gpu(codes, anc_sid)
         n_kmers, n_lists = tbl.n, int((~tbl.single).sum().item())
-        db = synth.upload_table(tbl, local)
+        sharded_mode = a.table_mode == "sharded"
+        db = synth.upload_table(tbl, local, shard_index=rank if sharded_mode else 0, shard_count=world if sharded_mode else 1)
         del tbl
         torch.cuda.empty_cache()
         inputs = api.Inputs(tree=paths["tree"], depth=paths["depth"], rank=paths["rank"], map16=paths["map16"], null_lst=null_lst, lmat_dir=workdir)
@@ -286,6 +366,10 @@ def main():
 
         def step():
             ctx.label_device(reads.data_ptr(), d_offs.data_ptr(), n, total, L, None, stream)
+
+        if sharded_mode:
+            sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, setup_s, launches0, tstream)
+            return
 
         def barrier():
             if world > 1:

@@ -48,7 +48,7 @@ EXPORTS = [
     "kmat_lookup_batch", "kmat_encode_batch", "kmat_inputs_load", "kmat_inputs_free", "kmat_opts_default",
     "kmat_ctx_create", "kmat_ctx_set_opts", "kmat_ctx_destroy", "kmat_label_batch", "kmat_label_batch_device",
     "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_set_pipeline", "kmat_shard_encode", "kmat_shard_serve", "kmat_shard_finish", "kmat_ctx_device_results", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench",
-    "kmat_set_l2_fetch_granularity", "kmat_reader_open", "kmat_reader_close", "kmat_read_batch_new", "kmat_read_batch_free",
+    "kmat_set_l2_fetch_granularity", "kmat_reader_open", "kmat_reader_open_mt", "kmat_reader_close", "kmat_read_batch_new", "kmat_read_batch_free",
     "kmat_reader_next", "kmat_read_batch_view", "kmat_tally_class", "kmat_host_alloc", "kmat_host_free",
 ]
 
@@ -110,6 +110,7 @@ def lib():
     L.kmat_gather_bench.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.kmat_set_l2_fetch_granularity.argtypes = [C.c_int, C.c_int]
     L.kmat_reader_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.kmat_reader_open_mt.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
     L.kmat_reader_close.argtypes = [vp]
     L.kmat_read_batch_new.restype = vp
     L.kmat_read_batch_free.argtypes = [vp]
@@ -394,11 +395,11 @@ def gather_bench(device=0, span_bytes=1 << 30, access_bytes=8, n_gathers=1 << 28
     return g.value, s.value
 
 
-def read_file(path, fastq=False, max_reads=1 << 20, max_bases=1 << 28):
+def read_file(path, fastq=False, max_reads=1 << 20, max_bases=1 << 28, threads=1):
     """(headers, reads) through kmat_reader_* -- the host parser that replaces read_label.cpp:1651-1732."""
     L = lib()
     r, hdrs, seqs = C.c_void_p(), [], []
-    _check(L.kmat_reader_open(_b(path), int(fastq), C.byref(r)))
+    _check(L.kmat_reader_open_mt(_b(path), int(fastq), int(threads), C.byref(r)))
     b = C.c_void_p(L.kmat_read_batch_new())
     try:
         while True:

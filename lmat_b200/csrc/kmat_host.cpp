@@ -8,6 +8,8 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <charconv>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -546,43 +548,127 @@ static const char *match_str(int m) {
         default: return "LCA_ERROR";
     }
 }
+// ---- number formatting.  The reference prints floats with ostream << float, i.e. printf("%g") of the promoted
+// double (6 significant digits, trailing zeros stripped, exponent form outside [1e-4, 1e6)).  At tens of millions of
+// reads per second the host writes ~20 such numbers per read, so snprintf (~300 ns) is the bottleneck of the writers.
+// km_fmt_g is exact: scores in the common range are scaled to a 6-digit integer in double arithmetic (the float ->
+// double conversion and the power of ten are exact, so the product is off by at most half an ulp, ~1e-10 in the
+// fraction); whenever the fraction is within 1e-6 of a rounding boundary, or the value is outside the fixed-notation
+// range, std::to_chars(general, 6) -- specified to equal printf("%.6g") -- decides.  tests/test_abi_cpu.py compares it
+// with printf over random bit patterns and the score-like ranges.
+static inline char *km_fmt_u32(char *p, uint32_t v) {
+    char t[10];
+    int n = 0;
+    do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = t[--n];
+    return p;
+}
+static inline char *km_fmt_i32(char *p, int32_t v) {
+    if (v < 0) { *p++ = '-'; return km_fmt_u32(p, (uint32_t)(-(int64_t)v)); }
+    return km_fmt_u32(p, (uint32_t)v);
+}
+static char *km_fmt_g_slow(char *p, double x) {
+    auto r = std::to_chars(p, p + 32, x, std::chars_format::general, 6);
+    return r.ptr;
+}
+static inline char *km_fmt_g(char *p, float f) {
+    const double x = (double)f;
+    double v = x < 0 ? -x : x;
+    if (!(v >= 1e-4 && v < 999999.0)) {                  // zero, tiny, huge, inf, nan
+        if (v == 0) { if (std::signbit(x)) *p++ = '-'; *p++ = '0'; return p; }
+        return km_fmt_g_slow(p, x);
+    }
+    static const double P10[] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10};
+    int e;                                               // floor(log10(v)), -4 .. 5
+    if (v >= 1.0) e = v < 10.0 ? 0 : v < 100.0 ? 1 : v < 1e3 ? 2 : v < 1e4 ? 3 : v < 1e5 ? 4 : 5;
+    else e = v >= 0.1 ? -1 : v >= 0.01 ? -2 : v >= 1e-3 ? -3 : -4;
+    const double t = v * P10[5 - e];                     // 1e5 <= t < 1e6 up to rounding
+    uint64_t n = (uint64_t)t;
+    const double frac = t - (double)n;
+    if (frac > 0.499999 && frac < 0.500001) return km_fmt_g_slow(p, x);
+    if (frac > 0.5) n++;
+    if (n >= 1000000) { n = 100000; e++; if (e > 5) return km_fmt_g_slow(p, x); }
+    if (n < 100000) return km_fmt_g_slow(p, x);          // cannot happen for exact inputs; be safe
+    if (x < 0) *p++ = '-';
+    char d[6];
+    for (int i = 5; i >= 0; i--) { d[i] = (char)('0' + n % 10); n /= 10; }
+    int last = 5;
+    while (last > 0 && d[last] == '0') last--;           // significant digits d[0..last]
+    if (e >= 0) {
+        for (int i = 0; i <= e; i++) *p++ = d[i];        // integer part: e + 1 digits (zeros included)
+        if (last > e) { *p++ = '.'; for (int i = e + 1; i <= last; i++) *p++ = d[i]; }
+    } else {
+        *p++ = '0'; *p++ = '.';
+        for (int i = 0; i < -e - 1; i++) *p++ = '0';
+        for (int i = 0; i <= last; i++) *p++ = d[i];
+    }
+    return p;
+}
+static inline char *km_fmt_str(char *p, const char *s) { while (*s) *p++ = *s++; return p; }
+// "<tid> <score>" with the text of the previous score reused when the value repeats (lineage ancestors share scores)
+struct KmScoreMemo { float v; int n; char s[32]; bool ok = false; };
+static inline char *km_fmt_pair(char *p, uint32_t tid, float score, KmScoreMemo &m) {
+    p = km_fmt_u32(p, tid);
+    *p++ = ' ';
+    uint32_t a, b;
+    memcpy(&a, &score, 4); memcpy(&b, &m.v, 4);
+    if (!m.ok || a != b) { m.v = score; m.n = (int)(km_fmt_g(m.s, score) - m.s); m.ok = true; }
+    memcpy(p, m.s, (size_t)m.n);
+    return p + m.n;
+}
+
 extern "C" int kmat_format_tail(const kmat_read_result *r, const kmat_pair *cands, const kmat_pair *lineage, int prn_all, char *buf, size_t cap) {
-    size_t w = 0;
-#define EMIT(...) do { int n_ = snprintf(buf + w, w < cap ? cap - w : 0, __VA_ARGS__); if (n_ < 0 || w + (size_t)n_ >= cap) return KMAT_ERR_OVERFLOW; w += (size_t)n_; } while (0)
+    // worst case per number: 16 bytes; every fixed part below is < 64 bytes
+    auto need = [&](size_t pairs) { return 160 + pairs * 40; };
+    char *p = buf;
     switch (r->status) {
-        case KMAT_ST_SHORT_LEN: case KMAT_ST_SHORT_VALID: EMIT("-1 -1 -1\t-1 -1\t%d %d ReadTooShort\n", r->n1, r->n2); break;
-        case KMAT_ST_NODBHITS: EMIT("-1 -1 %d\t-1 -1\t%d %d NoDbHits\n", r->valid_kmers, r->n1, r->n2); break;
+        case KMAT_ST_SHORT_LEN: case KMAT_ST_SHORT_VALID:
+            if (cap < need(0)) return KMAT_ERR_OVERFLOW;
+            p = km_fmt_str(p, "-1 -1 -1\t-1 -1\t"); p = km_fmt_i32(p, r->n1); *p++ = ' '; p = km_fmt_i32(p, r->n2); p = km_fmt_str(p, " ReadTooShort\n");
+            break;
+        case KMAT_ST_NODBHITS:
+            if (cap < need(0)) return KMAT_ERR_OVERFLOW;
+            p = km_fmt_str(p, "-1 -1 "); p = km_fmt_i32(p, r->valid_kmers); p = km_fmt_str(p, "\t-1 -1\t"); p = km_fmt_i32(p, r->n1); *p++ = ' ';
+            p = km_fmt_i32(p, r->n2); p = km_fmt_str(p, " NoDbHits\n");
+            break;
         case KMAT_ST_SILENT: break;
-        case KMAT_ST_PHIX: EMIT("-1 -1 %d\t%u %g\t%u %g %s\n", r->cand_kmer_cnt, r->tid, (double)r->score, r->tid, (double)r->score, match_str(KMAT_DIRECT)); break;
+        case KMAT_ST_PHIX:
+            if (cap < need(0)) return KMAT_ERR_OVERFLOW;
+            p = km_fmt_str(p, "-1 -1 "); p = km_fmt_i32(p, r->cand_kmer_cnt); *p++ = '\t';
+            p = km_fmt_u32(p, r->tid); *p++ = ' '; p = km_fmt_g(p, r->score); *p++ = '\t';
+            p = km_fmt_u32(p, r->tid); *p++ = ' '; p = km_fmt_g(p, r->score); *p++ = ' '; p = km_fmt_str(p, match_str(KMAT_DIRECT)); *p++ = '\n';
+            break;
         case KMAT_ST_LABELED: {
-            EMIT("%g %g %d\t", (double)r->log_avg, (double)r->stdev, r->cand_kmer_cnt);
+            const size_t pairs = prn_all ? r->n_cand : ((r->match == KMAT_MULTI || r->match == KMAT_PARTIAL) ? r->n_lin : 0);
+            if (cap < need(pairs)) return KMAT_ERR_OVERFLOW;
+            KmScoreMemo memo;
+            p = km_fmt_g(p, r->log_avg); *p++ = ' '; p = km_fmt_g(p, r->stdev); *p++ = ' '; p = km_fmt_i32(p, r->cand_kmer_cnt); *p++ = '\t';
             if (prn_all) {
                 if (!cands && r->n_cand) return KMAT_ERR_ARG;
                 bool prn = false;
                 for (int i = (int)r->n_cand - 1; i >= 0; --i) {
-                    const kmat_pair &p = cands[r->cand_off + (uint64_t)i];
-                    if (p.score >= 0) { EMIT(" %u %g", p.tid, (double)p.score); prn = true; }
+                    const kmat_pair &c = cands[r->cand_off + (uint64_t)i];
+                    if (c.score >= 0) { *p++ = ' '; p = km_fmt_pair(p, c.tid, c.score, memo); prn = true; }
                 }
-                if (!prn) EMIT("-1 -1");
-                EMIT("\t");
+                if (!prn) p = km_fmt_str(p, "-1 -1");
+                *p++ = '\t';
             }
-            if (r->match == KMAT_DIRECT) EMIT("%u %g %s", r->tid, (double)r->score, match_str(r->match));
+            if (r->match == KMAT_DIRECT) { p = km_fmt_pair(p, r->tid, r->score, memo); *p++ = ' '; p = km_fmt_str(p, match_str(r->match)); }
             else if (r->match == KMAT_MULTI || r->match == KMAT_PARTIAL) {
                 if (!prn_all) {
                     if (!lineage && r->n_lin) return KMAT_ERR_ARG;
-                    for (uint32_t i = 0; i < r->n_lin; i++) EMIT(" %u %g", lineage[r->lin_off + i].tid, (double)lineage[r->lin_off + i].score);
-                    if (!r->n_lin) EMIT("-1 -1");
-                    EMIT("\t");
+                    for (uint32_t i = 0; i < r->n_lin; i++) { *p++ = ' '; p = km_fmt_pair(p, lineage[r->lin_off + i].tid, lineage[r->lin_off + i].score, memo); }
+                    if (!r->n_lin) p = km_fmt_str(p, "-1 -1");
+                    *p++ = '\t';
                 }
-                EMIT("%u %g %s", r->tid, (double)r->score, match_str(r->match));
-            } else if (r->match == KMAT_NOMATCH) EMIT("-1 -1 %s", match_str(r->match));
-            else EMIT("-1 -1 Unmatched");
-            EMIT("\n");
+                p = km_fmt_pair(p, r->tid, r->score, memo); *p++ = ' '; p = km_fmt_str(p, match_str(r->match));
+            } else if (r->match == KMAT_NOMATCH) { p = km_fmt_str(p, "-1 -1 "); p = km_fmt_str(p, match_str(r->match)); }
+            else p = km_fmt_str(p, "-1 -1 Unmatched");
+            *p++ = '\n';
             break;
         }
         default: return KMAT_ERR_ARG;
     }
-#undef EMIT
-    if (w < cap) buf[w] = 0;
-    return (int)w;
+    if ((size_t)(p - buf) < cap) *p = 0;
+    return (int)(p - buf);
 }

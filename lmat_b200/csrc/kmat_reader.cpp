@@ -5,13 +5,21 @@
 // refills its queue in rounds of 2*n_threads reads; a round always ends right after a read was pushed, and the
 // header variables it resets per round are always reassigned before the next push, so one continuous state
 // machine yields the same (header, read) sequence.
+#include <atomic>
 #include <cerrno>
+#include <condition_variable>
+#include <map>
+#include <mutex>
+#include <thread>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include "kmat_internal.h"
@@ -19,48 +27,47 @@
 struct kmat_read_batch {
     std::string bases, hdrs;
     std::vector<uint64_t> offs, hdr_offs;
+    std::vector<uint32_t> unknown;      // reads whose header is "unknown_hdr:<ordinal>" (needs the global ordinal)
     uint64_t first_ordinal = 1;
     uint32_t n = 0;
+    void clear() { bases.clear(); hdrs.clear(); offs.assign(1, 0); hdr_offs.assign(1, 0); unknown.clear(); n = 0; }
+};
+
+// The line state machine of read_label main() (:1651-1713), independent of where the lines come from.
+struct KmParseState {
+    bool fastq = false;
+    bool in_finished = false;   // the reference's flag: a getline failed
+    std::string hdr_buff, last_hdr_buff;      // the pending read itself accumulates at the tail of the batch's `bases`
+    uint64_t n_emitted = 0;     // read_count_in == read_count_out ordinal
 };
 
 struct kmat_reader {
     int fd = -1;
-    bool own_fd = false, fastq = false;
+    bool own_fd = false;
     bool file_eof = false;      // read(2) returned 0
-    bool in_finished = false;   // the reference's flag: a getline failed
     std::vector<char> buf;
     size_t pos = 0, end = 0;
-    std::string read_buff, hdr_buff, last_hdr_buff;
-    uint64_t n_emitted = 0;     // read_count_in == read_count_out ordinal
+    KmParseState st;
+    // ---- parallel mode (FASTA, regular file): the file is mapped and cut at header lines into segments that a pool
+    //      of threads parses independently; kmat_reader_next hands the parsed segments out in file order
+    bool mt = false;
+    const char *map = nullptr; size_t map_len = 0;
+    std::vector<size_t> seg;                 // segment boundaries, seg.size() - 1 segments
+    std::atomic<size_t> next_seg{0};
+    size_t next_out = 0, window = 4;
+    std::mutex m;
+    std::condition_variable cv_done, cv_space;
+    std::map<size_t, kmat_read_batch *> done;
+    std::vector<std::thread> workers;
+    bool stop = false;
+    uint64_t ordinal = 0;
 };
 
 static const size_t kChunk = 8u << 20;
 
-extern "C" int kmat_reader_open(const char *path, int fastq, kmat_reader **out) {
-    if (!path || !out) { kmat_set_error("kmat_reader_open: bad argument"); return KMAT_ERR_ARG; }
-    kmat_reader *r = new kmat_reader();
-    r->fastq = fastq != 0;
-    if (strcmp(path, "-") == 0) r->fd = 0;
-    else {
-        r->fd = open(path, O_RDONLY);
-        r->own_fd = true;
-        if (r->fd < 0) { kmat_set_error("Did not open for reading: %s (%s)", path, strerror(errno)); delete r; return KMAT_ERR_IO; }
-    }
-    r->buf.resize(kChunk);
-    *out = r;
-    return KMAT_OK;
-}
-extern "C" void kmat_reader_close(kmat_reader *r) {
-    if (!r) return;
-    if (r->own_fd && r->fd >= 0) close(r->fd);
-    delete r;
-}
-extern "C" kmat_read_batch *kmat_read_batch_new(void) { return new kmat_read_batch(); }
-extern "C" void kmat_read_batch_free(kmat_read_batch *b) { delete b; }
-
 // std::getline over the chunk buffer: false when no byte is left.  The line excludes the '\n'; a final line
 // without '\n' is still returned.
-static bool next_line(kmat_reader *r, const char **line, size_t *len) {
+static bool next_line_fd(kmat_reader *r, const char **line, size_t *len) {
     for (;;) {
         if (r->pos < r->end) {
             const char *p = r->buf.data() + r->pos;
@@ -76,41 +83,184 @@ static bool next_line(kmat_reader *r, const char **line, size_t *len) {
         if (got <= 0) r->file_eof = true; else r->end += (size_t)got;
     }
 }
+struct KmMemLines {             // the same over a memory range
+    const char *p, *e;
+    bool next(const char **line, size_t *len) {
+        if (p >= e) return false;
+        const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
+        *line = p;
+        if (nl) { *len = (size_t)(nl - p); p = nl + 1; } else { *len = (size_t)(e - p); p = e; }
+        return true;
+    }
+};
 
-static void emit(kmat_reader *r, kmat_read_batch *b, const std::string &hdr) {
-    r->n_emitted++;
-    b->bases.append(r->read_buff);
+static void emit(KmParseState &st, kmat_read_batch *b, const std::string &hdr) {
+    st.n_emitted++;
     b->offs.push_back(b->bases.size());
     if (hdr.empty() || hdr[0] == '\0') {                 // :1728-1732
         char tmp[48];
-        snprintf(tmp, sizeof tmp, "unknown_hdr:%llu", (unsigned long long)r->n_emitted);
+        snprintf(tmp, sizeof tmp, "unknown_hdr:%llu", (unsigned long long)st.n_emitted);
         b->hdrs.append(tmp);
+        b->unknown.push_back(b->n);
     } else b->hdrs.append(hdr);
     b->hdr_offs.push_back(b->hdrs.size());
     b->n++;
-    r->read_buff.clear();
 }
+
+// Runs the state machine until the batch is full or the lines run out.  read_buff of the reference = the bytes of
+// `bases` past the last emitted read; it is empty whenever the loop is left (a batch only fills up right after an
+// emit), so batches never split a read.
+template <typename NextLine>
+static void parse_lines(KmParseState &st, NextLine &&next_line, uint32_t max_reads, uint64_t max_bases, kmat_read_batch *b) {
+    while (!st.in_finished && b->n < max_reads && b->bases.size() < max_bases) {
+        const char *line = ""; size_t len = 0;
+        if (!next_line(&line, &len)) { st.in_finished = true; line = ""; len = 0; }          // :1663-1669
+        char c0 = len ? line[0] : '\0';
+        if (c0 == '>' || (st.fastq && c0 == '@')) {                                           // :1672-1677
+            st.last_hdr_buff.swap(st.hdr_buff);
+            st.hdr_buff.assign(line + 1, len - 1);
+        }
+        if (c0 != '>' && len > 1 && !st.fastq) { b->bases.append(line, len); len = 0; c0 = '\0'; }              // :1679-1682
+        if (st.fastq && c0 != '@' && c0 != '+' && c0 != '-') { b->bases.append(line, len); len = 0; c0 = '\0'; } // :1684-1687
+        if (((c0 == '>' || st.in_finished) || (st.fastq && (c0 == '+' || c0 == '-'))) && b->bases.size() > b->offs.back()) {    // :1688-1707
+            emit(st, b, st.in_finished ? st.hdr_buff : st.last_hdr_buff);
+            if (st.fastq) { const char *q; size_t ql; next_line(&q, &ql); }                   // the quality line is skipped
+        }
+    }
+}
+
+// ---- parallel mode ----------------------------------------------------------------------------------------------
+// A FASTA file cut right before a header line parses independently on both sides: at a '>' line the reference
+// pushes the pending read with the header that preceded it, which is also what the end-of-input branch (:1663-1669)
+// does for the last read of the left part, and the right part starts from the same fresh state as the file does.
+// Only "unknown_hdr:<n>" (empty header, :1728-1732) needs the global read ordinal; it is patched when the segment is
+// handed out in order.
+static void km_reader_worker(kmat_reader *r) {
+    for (;;) {
+        size_t s;
+        {
+            std::unique_lock<std::mutex> l(r->m);
+            r->cv_space.wait(l, [&] { return r->stop || r->next_seg.load() < r->next_out + r->window; });
+            if (r->stop) return;
+            s = r->next_seg.fetch_add(1);
+        }
+        if (s + 1 >= r->seg.size()) return;
+        kmat_read_batch *b = new kmat_read_batch();
+        b->clear();
+        b->bases.reserve(r->seg[s + 1] - r->seg[s]);
+        KmParseState st;
+        KmMemLines src{r->map + r->seg[s], r->map + r->seg[s + 1]};
+        while (!st.in_finished) parse_lines(st, [&](const char **ln, size_t *n) { return src.next(ln, n); }, 0xFFFFFFFFu, ~0ull, b);
+        {
+            std::lock_guard<std::mutex> l(r->m);
+            r->done[s] = b;
+        }
+        r->cv_done.notify_all();
+    }
+}
+
+static bool km_reader_start_mt(kmat_reader *r, int threads) {
+    struct stat sb;
+    if (fstat(r->fd, &sb) != 0 || !S_ISREG(sb.st_mode) || sb.st_size <= 0) return false;
+    void *m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, r->fd, 0);
+    if (m == MAP_FAILED) return false;
+    madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
+    r->map = (const char *)m; r->map_len = (size_t)sb.st_size;
+    size_t seg_bytes = 8u << 20;
+    if (const char *e = getenv("KMAT_READER_SEG_BYTES")) { const long v = atol(e); if (v > 0) seg_bytes = (size_t)v; }
+    r->seg.push_back(0);
+    for (size_t at = seg_bytes; at < r->map_len; at += seg_bytes) {
+        // first header line at or after `at`
+        size_t p = at;
+        const char *hit = nullptr;
+        while (p < r->map_len) {
+            const char *nl = (const char *)memchr(r->map + p, '\n', r->map_len - p);
+            if (!nl) break;
+            if ((size_t)(nl - r->map) + 1 < r->map_len && nl[1] == '>') { hit = nl + 1; break; }
+            p = (size_t)(nl - r->map) + 1;
+        }
+        if (!hit) break;
+        const size_t cut = (size_t)(hit - r->map);
+        if (cut > r->seg.back()) r->seg.push_back(cut);
+        if (cut > at) at = cut - (cut % seg_bytes);          // a very long record: continue after it
+    }
+    r->seg.push_back(r->map_len);
+    r->window = (size_t)threads * 2 + 2;
+    r->mt = true;
+    for (int t = 0; t < threads; t++) r->workers.emplace_back(km_reader_worker, r);
+    return true;
+}
+
+extern "C" int kmat_reader_open_mt(const char *path, int fastq, int threads, kmat_reader **out) {
+    if (!path || !out) { kmat_set_error("kmat_reader_open: bad argument"); return KMAT_ERR_ARG; }
+    kmat_reader *r = new kmat_reader();
+    r->st.fastq = fastq != 0;
+    if (strcmp(path, "-") == 0) r->fd = 0;
+    else {
+        r->fd = open(path, O_RDONLY);
+        r->own_fd = true;
+        if (r->fd < 0) { kmat_set_error("Did not open for reading: %s (%s)", path, strerror(errno)); delete r; return KMAT_ERR_IO; }
+    }
+    // FASTQ records cannot be told apart without context ('@' also starts quality lines) and stdin cannot be mapped
+    if (!(threads > 1 && !fastq && r->own_fd && km_reader_start_mt(r, threads))) r->buf.resize(kChunk);
+    *out = r;
+    return KMAT_OK;
+}
+extern "C" int kmat_reader_open(const char *path, int fastq, kmat_reader **out) { return kmat_reader_open_mt(path, fastq, 1, out); }
+extern "C" void kmat_reader_close(kmat_reader *r) {
+    if (!r) return;
+    if (r->mt) {
+        { std::lock_guard<std::mutex> l(r->m); r->stop = true; }
+        r->cv_space.notify_all();
+        for (auto &t : r->workers) t.join();
+        for (auto &kv : r->done) delete kv.second;
+        munmap((void *)r->map, r->map_len);
+    }
+    if (r->own_fd && r->fd >= 0) close(r->fd);
+    delete r;
+}
+extern "C" kmat_read_batch *kmat_read_batch_new(void) { return new kmat_read_batch(); }
+extern "C" void kmat_read_batch_free(kmat_read_batch *b) { delete b; }
 
 extern "C" int64_t kmat_reader_next(kmat_reader *r, uint32_t max_reads, uint64_t max_bases, kmat_read_batch *b) {
     if (!r || !b) { kmat_set_error("kmat_reader_next: bad argument"); return KMAT_ERR_ARG; }
     if (max_reads == 0) max_reads = 1;
-    b->bases.clear(); b->hdrs.clear(); b->offs.assign(1, 0); b->hdr_offs.assign(1, 0); b->n = 0;
-    b->first_ordinal = r->n_emitted + 1;
-    while (!r->in_finished && b->n < max_reads && b->bases.size() < max_bases) {
-        const char *line = ""; size_t len = 0;
-        if (!next_line(r, &line, &len)) { r->in_finished = true; line = ""; len = 0; }      // :1663-1669
-        char c0 = len ? line[0] : '\0';
-        if (c0 == '>' || (r->fastq && c0 == '@')) {                                           // :1672-1677
-            r->last_hdr_buff.swap(r->hdr_buff);
-            r->hdr_buff.assign(line + 1, len - 1);
-        }
-        if (c0 != '>' && len > 1 && !r->fastq) { r->read_buff.append(line, len); len = 0; c0 = '\0'; }              // :1679-1682
-        if (r->fastq && c0 != '@' && c0 != '+' && c0 != '-') { r->read_buff.append(line, len); len = 0; c0 = '\0'; } // :1684-1687
-        if (((c0 == '>' || r->in_finished) || (r->fastq && (c0 == '+' || c0 == '-'))) && !r->read_buff.empty()) {    // :1688-1707
-            emit(r, b, r->in_finished ? r->hdr_buff : r->last_hdr_buff);
-            if (r->fastq) { const char *q; size_t ql; next_line(r, &q, &ql); }                // the quality line is skipped
+    b->clear();
+    if (r->mt) {
+        // segments come out in file order, each as one batch (max_reads / max_bases do not apply); empty ones are skipped
+        for (;;) {
+            if (r->next_out + 1 >= r->seg.size()) return 0;
+            kmat_read_batch *d = nullptr;
+            {
+                std::unique_lock<std::mutex> l(r->m);
+                r->cv_done.wait(l, [&] { return r->done.count(r->next_out) != 0; });
+                d = r->done[r->next_out];
+                r->done.erase(r->next_out);
+                r->next_out++;
+            }
+            r->cv_space.notify_all();
+            std::swap(*b, *d);
+            delete d;
+            b->first_ordinal = r->ordinal + 1;
+            if (!b->unknown.empty()) {                         // rebuild the headers with the global ordinals
+                std::string h; std::vector<uint64_t> ho(1, 0);
+                size_t u = 0;
+                for (uint32_t i = 0; i < b->n; i++) {
+                    if (u < b->unknown.size() && b->unknown[u] == i) {
+                        char tmp[48];
+                        snprintf(tmp, sizeof tmp, "unknown_hdr:%llu", (unsigned long long)(r->ordinal + i + 1));
+                        h.append(tmp); u++;
+                    } else h.append(b->hdrs, b->hdr_offs[i], b->hdr_offs[i + 1] - b->hdr_offs[i]);
+                    ho.push_back(h.size());
+                }
+                b->hdrs.swap(h); b->hdr_offs.swap(ho);
+            }
+            r->ordinal += b->n;
+            if (b->n) return (int64_t)b->n;
         }
     }
+    b->first_ordinal = r->st.n_emitted + 1;
+    parse_lines(r->st, [&](const char **ln, size_t *n) { return next_line_fd(r, ln, n); }, max_reads, max_bases, b);
     return (int64_t)b->n;
 }
 

@@ -8,7 +8,8 @@
 //                    reference's single-thread output byte for byte and any -t gives the same multiset of lines;
 //                    each writer keeps the reference's per-thread tallies (float sums in file order), merged in
 //                    thread order like :1760-1800.
-// Environment: KMAT_DEVICES="0,2,.." (default: every visible GPU), KMAT_BATCH_READS (default 262144),
+// Environment: KMAT_DEVICES="0,2,.." (default: every visible GPU), KMAT_BATCH_READS (default 131072),
+// KMAT_READER_THREADS (FASTA files are parsed in parallel segments; default hw threads / 4, 2..8),
 // KMAT_TID_BYTES (2|4: sizeof(DBTID_T) of the DB, default 2), LMAT_DIR as in the reference (:555-560).
 #include <getopt.h>
 #include <unistd.h>
@@ -228,16 +229,20 @@ int main(int argc, char *argv[]) {
     const auto t_query = std::chrono::steady_clock::now();
 
     kmat_reader *reader = nullptr;
-    if (kmat_reader_open(query_fn.c_str(), fastq ? 1 : 0, &reader) != KMAT_OK) {
+    const char *rt = getenv("KMAT_READER_THREADS");
+    const int reader_threads = rt ? std::max(1, atoi(rt)) : (int)std::max(2u, std::min(8u, std::thread::hardware_concurrency() / 4));
+    if (kmat_reader_open_mt(query_fn.c_str(), fastq ? 1 : 0, reader_threads, &reader) != KMAT_OK) {
         std::cerr << "ERROR! Did not open for reading: " << query_fn << std::endl;
         return -1;
     }
     std::cout << "Classifing reads on " << devs.size() << " GPU(s), writing " << n_threads << " .out files..." << std::endl;
 
     const char *be = getenv("KMAT_BATCH_READS");
-    const uint32_t batch_reads = be ? (uint32_t)std::max(1, atoi(be)) : 262144u;
+    const uint32_t batch_reads = be ? (uint32_t)std::max(1, atoi(be)) : 131072u;
     const uint64_t batch_bases = (uint64_t)batch_reads * 400;
-    const size_t n_inflight = 2 * devs.size() + 2 * (size_t)n_threads + 2;
+    // batches in flight: one being read, two per GPU (one queued), one per writer + one waiting for it; the buffers are
+    // reused, so a small pool also keeps the working set (and its first-touch page faults) small
+    const size_t n_inflight = 2 * devs.size() + (size_t)n_threads + 3;
     Channel<Batch *> free_q(n_inflight + 1), work_q(n_inflight + 1);
     std::vector<Batch> pool(n_inflight);
     for (auto &b : pool) { b.rb = kmat_read_batch_new(); free_q.push(&b); }
@@ -279,8 +284,8 @@ int main(int argc, char *argv[]) {
                 const char *bases; const uint64_t *offs; uint32_t n;
                 kmat_read_batch_view(b->rb, &bases, &offs, nullptr, nullptr, &n, nullptr);
                 b->res.resize(n);
-                if (b->cands.size() < (size_t)n * 24 + 1024) b->cands.resize((size_t)n * 24 + 1024);
-                if (opt.want_lineage && b->lin.size() < (size_t)n * 24 + 1024) b->lin.resize((size_t)n * 24 + 1024);
+                if (b->cands.size() < (size_t)n * 20 + 1024) b->cands.resize((size_t)n * 20 + 1024);
+                if (opt.want_lineage && b->lin.size() < (size_t)n * 20 + 1024) b->lin.resize((size_t)n * 20 + 1024);
                 uint64_t nc = 0, nl = 0;
                 for (int attempt = 0; attempt < 3; attempt++) {
                     b->rc = kmat_label_batch(ctxs[d], bases, offs, n, b->res.data(), b->cands.data(), b->cands.size(), &nc,
@@ -302,7 +307,6 @@ int main(int argc, char *argv[]) {
             FILE *ofs = fopen(ofname.c_str(), "w");
             if (!ofs) fail("could not open for writing " + ofname);
             std::vector<char> out;
-            char tail[1 << 16];
             for (;;) {
                 Batch *b = nullptr;
                 {
@@ -317,21 +321,22 @@ int main(int argc, char *argv[]) {
                 if (b->rc == KMAT_OK && ofs) {
                     const char *bases, *hdrs; const uint64_t *offs, *hoffs; uint32_t n;
                     kmat_read_batch_view(b->rb, &bases, &offs, &hdrs, &hoffs, &n, nullptr);
-                    out.clear();
+                    // upper bound of the text of this batch: header + read + tail (160 fixed + 40 per printed pair)
+                    size_t bound = (size_t)hoffs[n] + (prn_read ? (size_t)offs[n] : (size_t)n) + (size_t)n * 164;
+                    for (uint32_t i = 0; i < n; i++) bound += (size_t)(prn_all ? b->res[i].n_cand : b->res[i].n_lin) * 40;
+                    if (out.size() < bound) out.resize(bound + bound / 8);
+                    char *p = out.data();
                     for (uint32_t i = 0; i < n; i++) {
                         const kmat_read_result &r = b->res[i];
-                        out.insert(out.end(), hdrs + hoffs[i], hdrs + hoffs[i + 1]);             // :1733-1738
-                        out.push_back('\t');
-                        if (prn_read) out.insert(out.end(), bases + offs[i], bases + offs[i + 1]); else out.push_back('X');
-                        out.push_back('\t');
+                        const size_t hl = (size_t)(hoffs[i + 1] - hoffs[i]), rl = (size_t)(offs[i + 1] - offs[i]);
+                        memcpy(p, hdrs + hoffs[i], hl); p += hl;                                  // :1733-1738
+                        *p++ = '\t';
+                        if (prn_read) { memcpy(p, bases + offs[i], rl); p += rl; } else *p++ = 'X';
+                        *p++ = '\t';
                         if (r.status == KMAT_ST_ERROR) { fail("read " + std::string(hdrs + hoffs[i], hdrs + hoffs[i + 1]) + ": " + kmat_strerror(r.err)); continue; }
-                        int tn = kmat_format_tail(&r, b->cands.data(), b->lin.data(), prn_all ? 1 : 0, tail, sizeof tail);
-                        if (tn == KMAT_ERR_OVERFLOW) {                                           // very long candidate list
-                            std::vector<char> big(1 << 24);
-                            tn = kmat_format_tail(&r, b->cands.data(), b->lin.data(), prn_all ? 1 : 0, big.data(), big.size());
-                            if (tn >= 0) out.insert(out.end(), big.data(), big.data() + tn);
-                        } else if (tn >= 0) out.insert(out.end(), tail, tail + tn);
+                        const int tn = kmat_format_tail(&r, b->cands.data(), b->lin.data(), prn_all ? 1 : 0, p, (size_t)(out.data() + out.size() - p));
                         if (tn < 0) { fail("formatting failed"); continue; }
+                        p += tn;
                         switch (kmat_tally_class(&r, min_score, opt.min_kmer)) {                 // :1217-1277
                             case 0: {
                                 auto it = w.track_tscore.find(r.tid);
@@ -345,7 +350,8 @@ int main(int argc, char *argv[]) {
                             default: break;
                         }
                     }
-                    if (fwrite(out.data(), 1, out.size(), ofs) != out.size()) fail("write failed: " + ofname);
+                    const size_t out_n = (size_t)(p - out.data());
+                    if (fwrite(out.data(), 1, out_n, ofs) != out_n) fail("write failed: " + ofname);
                 }
                 free_q.push(b);
             }

@@ -96,3 +96,31 @@ def test_format_tail_matches_oracle_formatter(golden_small):
             n = api.lib().kmat_format_tail(r2[i:i + 1].ctypes.data, cands.ctypes.data if len(cands) else None,
                                            lin.ctypes.data if len(lin) else None, int(prn), buf, len(buf))
             assert n >= 0 and buf.raw[:n].decode() == want[i]
+
+
+def test_format_tail_numbers_match_printf_g():
+    """The fast float formatter behind kmat_format_tail equals printf("%g") of the promoted double (what
+    ostream << float prints, read_label.cpp:894-937) on random bit patterns, score-like values and rounding boundaries."""
+    rng = np.random.default_rng(12)
+    vals = [rng.integers(0, 2 ** 32, 200000, dtype=np.uint64).astype(np.uint32).view(np.float32),           # any bit pattern
+            (rng.random(200000) * 30 - 15).astype(np.float32), rng.random(200000).astype(np.float32),
+            np.log(rng.integers(1, 131, 100000) / 131.0 / 0.0301).astype(np.float32),
+            (rng.integers(0, 10 ** 6, 100000) / 10 ** rng.integers(0, 9, 100000)).astype(np.float32),     # short decimals
+            ((rng.integers(0, 10 ** 6, 100000) + 0.5) / 10 ** rng.integers(0, 9, 100000)).astype(np.float32),   # near ties
+            np.array([0.0, -0.0, 1e-4, 9.99995e-5, 999999.0, 999999.5, 1e6, 0.1, 1.0, 100000.0, 0.000123456, 1e-38, 3e38, np.inf, -np.inf], dtype=np.float32)]
+    v = np.concatenate(vals)
+    v = v[~np.isnan(v)]
+    res = np.zeros(1, dtype=api.RESULT_DTYPE)
+    res["status"], res["match"], res["n_cand"], res["cand_off"] = 5, 0, 16, 0
+    cands = np.zeros(16, dtype=api.PAIR_DTYPE)
+    buf = C.create_string_buffer(4096)
+    for a in range(0, len(v) - 18, 18):
+        blk = v[a:a + 18]
+        res["log_avg"], res["stdev"], res["cand_kmer_cnt"], res["tid"], res["score"] = blk[0], blk[1], 131, 9606, abs(blk[2])
+        cands["tid"] = np.arange(16) + 7
+        cands["score"] = np.abs(blk[2:18])
+        cands["score"][5] = cands["score"][4]                       # repeated score: the memoised text
+        n = api.lib().kmat_format_tail(res.ctypes.data, cands.ctypes.data, None, 1, buf, len(buf))
+        want = "%g %g 131\t" % (float(blk[0]), float(blk[1])) + "".join(" %d %g" % (int(t), float(s)) for t, s in zip(cands["tid"][::-1], cands["score"][::-1]))
+        want += "\t9606 %g DirectMatch\n" % float(abs(blk[2]))
+        assert n >= 0 and buf.raw[:n].decode() == want

@@ -54,3 +54,24 @@ def test_reader_long_line_and_chunk_boundaries(tmp_path):
 def test_reader_missing_file():
     with pytest.raises(api.KmatError):
         api.read_file("/nonexistent/reads.fa")
+
+
+@pytest.mark.parametrize("seg_bytes", [1, 7, 64, 4096])
+def test_parallel_reader_equals_sequential(tmp_path, golden_small, seg_bytes, monkeypatch):
+    """kmat_reader_open_mt: FASTA cut at header lines into segments parsed by several threads gives the same
+    (header, read) sequence as the sequential state machine -- wrapped lines, blank lines, empty headers
+    ("unknown_hdr:<global ordinal>"), consecutive headers, no trailing newline, data before the first header."""
+    monkeypatch.setenv("KMAT_READER_SEG_BYTES", str(seg_bytes))
+    files = {k: open(golden_small.paths[k], "rb").read() for k in ("reads", "reads_wrapped")}
+    files["mixed"] = (b"ACGTACGTAA\nCCGG\n>h1\nACGT\nTTGA\n\nA\n>\nGGGTTT\n>h3\n>h4\nAC\n>\n>\nTTTTT\nGG\n>h7 with spaces\tand tab\r\nACGT\r\n" * 40
+                      + b">last\nACGTACGTT")
+    files["headers_only"] = b">a\n>b\n>c\n"
+    files["one_record"] = b">only\nACGT\n"
+    for name, data in files.items():
+        p = os.path.join(tmp_path, f"{name}_{seg_bytes}.fa")
+        open(p, "wb").write(data)
+        want = api.read_file(p, threads=1)
+        for th in (2, 5):
+            got = api.read_file(p, threads=th)
+            assert got == want, (name, th)
+        assert want == tuple(op.read_fasta_like_reference(p)) or list(want) == list(op.read_fasta_like_reference(p))
