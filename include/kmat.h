@@ -62,6 +62,24 @@ int kmat_table_from_arrays(const uint64_t *kmers, const uint64_t *offs, const ui
  * oracle/_ref/make_db_table writes (real perm-je heaps: parity unpinned, KMAT_ERR_FORMAT). */
 int kmat_table_open(const char *path, int tid_bytes, kmat_table **out);
 int kmat_table_save(const kmat_table *, const char *path);
+/* Build the logical table straight from tax_histo files.  Replaces make_db_table main() +
+ * SortedDb<tid_T>::add_data (src/make_db_table.cpp:105-433, src/kmerdb/SortedDb.cpp:84-751): files in ascending k-mer
+ * order, optional 32->16-bit id map (-f), run of the rank-priority pruning (-g N -m ranks), sorted human k-mer stream
+ * (-j) and adaptor k-mer set (-u).  The result holds exactly the lists a reader of the reference-built DB sees through
+ * begin_/next, in the same order; save it with kmat_table_save or upload it with kmat_db_upload. */
+typedef struct {
+    int32_t kmer_length;        /* -k */
+    int32_t tax_histo_format;   /* 1 (default); 0 = -h: kmerPrefixCounter records (u32 counts, sanity word every 1000) */
+    int32_t tid_cutoff;         /* -g, 0 = no pruning */
+    int32_t reserved;
+    uint64_t stopper;           /* -q, 0 = none: records 0..stopper of every file */
+    const char *map16;          /* -f, NULL: 32-bit ids are stored */
+    const char *numrank;        /* -m, only read when tid_cutoff > 0 (make_db_table.cpp:303) */
+    const char *human_kmers;    /* -j */
+    const char *adaptor_kmers;  /* -u */
+} kmat_build_opts;
+void kmat_build_opts_default(kmat_build_opts *);
+int kmat_table_build(const char *const *files, int n_files, const kmat_build_opts *, kmat_table **out);
 uint64_t kmat_table_size(const kmat_table *);        /* SortedDb::size()            (SortedDb.hpp:438) */
 int kmat_table_kmer_length(const kmat_table *);      /* SortedDb::get_kmer_length() (SortedDb.hpp:433) */
 int kmat_table_tid_bytes(const kmat_table *);

@@ -43,7 +43,7 @@ class KmatError(RuntimeError):
 EXPORTS = [
     "kmat_strerror", "kmat_last_error", "kmat_abi_version", "kmat_device_count", "kmat_table_from_sorteddb",
     "kmat_table_from_arrays", "kmat_table_open", "kmat_table_save", "kmat_table_size", "kmat_table_kmer_length",
-    "kmat_table_tid_bytes", "kmat_table_view", "kmat_table_free", "kmat_db_upload", "kmat_db_build_device",
+    "kmat_table_tid_bytes", "kmat_table_build", "kmat_build_opts_default", "kmat_table_view", "kmat_table_free", "kmat_db_upload", "kmat_db_build_device",
     "kmat_shard_of", "kmat_db_size", "kmat_db_bytes", "kmat_db_kmer_length", "kmat_db_device", "kmat_db_free",
     "kmat_lookup_batch", "kmat_encode_batch", "kmat_inputs_load", "kmat_inputs_free", "kmat_opts_default",
     "kmat_ctx_create", "kmat_ctx_set_opts", "kmat_ctx_destroy", "kmat_label_batch", "kmat_label_batch_device",
@@ -140,6 +140,12 @@ def _b(s):
     return None if s is None else os.fsencode(s)
 
 
+class BuildOpts(C.Structure):
+    _fields_ = [("kmer_length", C.c_int32), ("tax_histo_format", C.c_int32), ("tid_cutoff", C.c_int32), ("reserved", C.c_int32),
+                ("stopper", C.c_uint64), ("map16", C.c_char_p), ("numrank", C.c_char_p), ("human_kmers", C.c_char_p),
+                ("adaptor_kmers", C.c_char_p)]
+
+
 class Table:
     """Host logical table (SortedDb contents flattened)."""
 
@@ -168,6 +174,19 @@ class Table:
     def open(cls, path, tid_bytes=2):
         h = C.c_void_p()
         _check(lib().kmat_table_open(_b(path), tid_bytes, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def build(cls, files, kmer_len=20, map16=None, tid_cutoff=0, numrank=None, human_kmers=None, adaptor_kmers=None,
+              tax_histo_format=True, stopper=0):
+        """kmat_table_build: the table make_db_table would build from these tax_histo files (-f -g -m -j -u -h -q)."""
+        o = BuildOpts()
+        lib().kmat_build_opts_default(C.byref(o))
+        o.kmer_length, o.tax_histo_format, o.tid_cutoff, o.stopper = kmer_len, int(tax_histo_format), tid_cutoff, stopper
+        o.map16, o.numrank, o.human_kmers, o.adaptor_kmers = (_b(x) if x else None for x in (map16, numrank, human_kmers, adaptor_kmers))
+        arr = (C.c_char_p * len(files))(*[_b(f) for f in files])
+        h = C.c_void_p()
+        _check(lib().kmat_table_build(arr, len(files), C.byref(o), C.byref(h)))
         return cls(h)
 
     def save(self, path):

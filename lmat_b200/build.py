@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libkmat.so")
 BIN = os.path.join(HERE, "bin", "read_label")
 
 CUDA_SRCS = ["kmat_db.cu", "kmat_label.cu"]
-HOST_SRCS = ["kmat_host.cpp", "kmat_reader.cpp"]
+HOST_SRCS = ["kmat_host.cpp", "kmat_reader.cpp", "kmat_build.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 
@@ -84,9 +84,26 @@ def build_cli(force=False):
     return BIN
 
 
+MDT_BIN = os.path.join(HERE, "bin", "make_db_table")
+
+
+def build_tools(force=False):
+    """The other host binaries over libkmat (drop-ins for the reference tools of the same name)."""
+    src = os.path.join(CSRC, "make_db_table_main.cpp")
+    if force or _newer(MDT_BIN, [src, LIB]):
+        os.makedirs(os.path.dirname(MDT_BIN), exist_ok=True)
+        cmd = ["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), src, "-o", MDT_BIN, "-L" + HERE, "-lkmat",
+               "-Wl,-rpath,$ORIGIN/..", "-lpthread"]
+        p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if p.returncode != 0:
+            raise RuntimeError(f"g++ failed for make_db_table_main.cpp:\n{p.stdout}")
+    return MDT_BIN
+
+
 def build_all(force=False, verbose=False):
     lib = build_lib(force=force, verbose=verbose)
     cli = build_cli(force=force)
+    build_tools(force=force)
     return lib, cli
 
 
