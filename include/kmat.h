@@ -212,6 +212,20 @@ int kmat_shard_finish(kmat_ctx *, const uint32_t *d_reply, const uint32_t *d_pay
  * cand_off / n_cand index (rank_label after sort(TCmp), ascending).  Synchronises. */
 int kmat_ctx_device_results(kmat_ctx *, const kmat_read_result **d_out, const kmat_pair **d_cands, uint64_t *n_cands);
 
+/* ---- gene_label -------------------------------------------------------------------------------
+ * Replaces retrieve_kmer_labels + the top-gene pick of proc_line in src/gene_label.cpp (:217-301) for a batch of reads
+ * against a gene DB (a table of 32-bit gene ids; no id map, no pruning).  Host buffers in and out. */
+typedef struct {
+    int32_t status;        /* 1 = a line is printed; 0 = no gene hit / read shorter than k (the reference prints nothing);
+                              < 0 = KMAT_ERR_* (more than 64 distinct genes in one read: KMAT_ERR_UNSUPPORTED)            */
+    uint32_t valid_kmers;  /* cnt: unique canonical k-mers of the read                                       (:245)      */
+    uint32_t n_genes;      /* geneid_lst.size()                                                                            */
+    uint32_t gene;         /* gsort[0].first after sort(Cmp)                                                 (:297-299)  */
+    uint32_t count;        /* gsort[0].second: k-mers of the read that carry this gene                                     */
+    float score;           /* (float)count / (float)cnt                                                      (:298)      */
+} kmat_gene_result;
+int kmat_gene_batch(const kmat_db *, const char *bases, const uint64_t *offs, uint32_t n_reads, kmat_gene_result *out);
+
 /* Page-locked host memory for the buffers of kmat_label_batch (optional; NULL when no device / out of memory). */
 void *kmat_host_alloc(size_t bytes);
 void kmat_host_free(void *);

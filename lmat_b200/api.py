@@ -21,6 +21,7 @@ RESULT_DTYPE = np.dtype([("status", "<i4"), ("n1", "<i4"), ("n2", "<i4"), ("vali
                          ("log_avg", "<f4"), ("stdev", "<f4"), ("n_cand", "<u4"), ("n_lin", "<u4"),
                          ("cand_off", "<u8"), ("lin_off", "<u8"), ("bin_sel", "<i4"), ("err", "<i4")])
 PAIR_DTYPE = np.dtype([("tid", "<u4"), ("score", "<f4")])
+GENE_DTYPE = np.dtype([("status", "<i4"), ("valid_kmers", "<u4"), ("n_genes", "<u4"), ("gene", "<u4"), ("count", "<u4"), ("score", "<f4")])
 
 
 class Opts(C.Structure):
@@ -47,7 +48,7 @@ EXPORTS = [
     "kmat_shard_of", "kmat_db_size", "kmat_db_bytes", "kmat_db_kmer_length", "kmat_db_device", "kmat_db_free",
     "kmat_lookup_batch", "kmat_encode_batch", "kmat_inputs_load", "kmat_inputs_free", "kmat_opts_default",
     "kmat_ctx_create", "kmat_ctx_set_opts", "kmat_ctx_destroy", "kmat_label_batch", "kmat_label_batch_device",
-    "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_set_pipeline", "kmat_shard_encode", "kmat_shard_serve", "kmat_shard_finish", "kmat_ctx_device_results", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench",
+    "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_set_pipeline", "kmat_gene_batch", "kmat_shard_encode", "kmat_shard_serve", "kmat_shard_finish", "kmat_ctx_device_results", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench",
     "kmat_set_l2_fetch_granularity", "kmat_reader_open", "kmat_reader_open_mt", "kmat_reader_close", "kmat_read_batch_new", "kmat_read_batch_free",
     "kmat_reader_next", "kmat_read_batch_view", "kmat_tally_class", "kmat_host_alloc", "kmat_host_free",
 ]
@@ -100,6 +101,7 @@ def lib():
     L.kmat_ctx_last_stats.argtypes = [vp, C.POINTER(BatchStats)]
     L.kmat_ctx_set_stats.argtypes = [vp, C.c_int]
     L.kmat_ctx_set_pipeline.argtypes = [vp, C.c_int]
+    L.kmat_gene_batch.argtypes = [vp, C.c_char_p, vp, C.c_uint32, vp]
     L.kmat_shard_encode.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(vp), vp, vp]
     L.kmat_shard_serve.argtypes = [vp, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(vp), vp, vp]
     L.kmat_shard_finish.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp]
@@ -249,6 +251,13 @@ class Db:
     @property
     def kmer_length(self):
         return lib().kmat_db_kmer_length(self.h)
+
+    def gene_label(self, seqs):
+        """kmat_gene_batch over a list of reads -> numpy array of GENE_DTYPE."""
+        bases, offs = pack_reads(seqs)
+        out = np.zeros(len(seqs), dtype=GENE_DTYPE)
+        _check(lib().kmat_gene_batch(self.h, bases, offs.ctypes.data, len(seqs), out.ctypes.data))
+        return out
 
     def lookup(self, kmers):
         kmers = np.ascontiguousarray(kmers, dtype=np.uint64)

@@ -87,16 +87,20 @@ def build_cli(force=False):
 MDT_BIN = os.path.join(HERE, "bin", "make_db_table")
 
 
+GL_BIN = os.path.join(HERE, "bin", "gene_label")
+
+
 def build_tools(force=False):
     """The other host binaries over libkmat (drop-ins for the reference tools of the same name)."""
-    src = os.path.join(CSRC, "make_db_table_main.cpp")
-    if force or _newer(MDT_BIN, [src, LIB]):
-        os.makedirs(os.path.dirname(MDT_BIN), exist_ok=True)
-        cmd = ["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), src, "-o", MDT_BIN, "-L" + HERE, "-lkmat",
-               "-Wl,-rpath,$ORIGIN/..", "-lpthread"]
-        p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-        if p.returncode != 0:
-            raise RuntimeError(f"g++ failed for make_db_table_main.cpp:\n{p.stdout}")
+    for name, out in (("make_db_table_main.cpp", MDT_BIN), ("gene_label_main.cpp", GL_BIN)):
+        src = os.path.join(CSRC, name)
+        if force or _newer(out, [src, LIB]):
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            cmd = ["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), src, "-o", out, "-L" + HERE, "-lkmat",
+                   "-Wl,-rpath,$ORIGIN/..", "-lpthread", "-lz"]
+            p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if p.returncode != 0:
+                raise RuntimeError(f"g++ failed for {name}:\n{p.stdout}")
     return MDT_BIN
 
 

@@ -233,6 +233,10 @@ extern "C" int kmat_db_upload(const kmat_table *t, int device, int shard_index, 
     // the host loop above already kept this shard's k-mers only (and only their lists), so no device-side filter
     int rc = kmat_db_build_device(device, t->kmer_len, t->tid_bytes, n, d_k, d_p, d_pool, pool.size(), (uint32_t)stored.size(), 0, 1, out);
     if (rc == KMAT_OK) { (*out)->shard_index = shard_index; (*out)->shard_count = shard_count; }
+    if (rc == KMAT_OK && !stored.empty()) {
+        KM_CUDA(cudaMalloc((void **)&(*out)->d_stored_tids, stored.size() * 4));
+        KM_CUDA(cudaMemcpy((*out)->d_stored_tids, stored.data(), stored.size() * 4, cudaMemcpyHostToDevice));
+    }
     cudaFree(d_k); cudaFree(d_p); cudaFree(d_pool);
     if (rc == KMAT_OK) (*out)->stored_tids = stored;
     return rc;
@@ -245,7 +249,7 @@ extern "C" int kmat_db_device(const kmat_db *db) { return db ? db->device : -1; 
 extern "C" void kmat_db_free(kmat_db *db) {
     if (!db) return;
     cudaSetDevice(db->device);
-    cudaFree(db->d_slots); cudaFree(db->d_pool); cudaFree(db->d_prefix_bits); cudaFree(db->d_stash_x); cudaFree(db->d_stash_hit);
+    cudaFree(db->d_slots); cudaFree(db->d_pool); cudaFree(db->d_prefix_bits); cudaFree(db->d_stash_x); cudaFree(db->d_stash_hit); cudaFree(db->d_stored_tids);
     delete db;
 }
 

@@ -1277,3 +1277,4 @@ extern "C" void *kmat_host_alloc(size_t bytes) {
 extern "C" void kmat_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 #include "kmat_shard.cuh"
+#include "kmat_gene.cuh"

@@ -33,6 +33,7 @@ struct kmat_db {
     uint32_t n_sid = 65536;
     int shard_index = 0, shard_count = 1;  // DB-sharded mode: this table holds the k-mers with kmat_shard_of() == shard_index
     std::vector<uint32_t> stored_tids;     // 32-bit tables: dense stored id -> tid
+    uint32_t *d_stored_tids = nullptr;     //   the same on the device (gene_label path)
 };
 
 struct KmDbDev;

@@ -585,6 +585,44 @@ int64_t kmo_lookup_batch(const kmo_db *db, const uint64_t *kmers, uint32_t n, ui
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* gene_label: retrieve_kmer_labels + the top-gene pick of proc_line -- gene_label.cpp:217-301     */
+/* Unique canonical k-mers of the read (first occurrence wins, :242-245); every id of every hit     */
+/* list counts once per k-mer, ids in first-appearance order (:249-258); std::sort by count         */
+/* descending (Cmp, :84-88; libstdc++ order on ties) and the front element is the call (:297-299). */
+/* Returns the number of distinct gene ids (0: the reference prints nothing for the read).        */
+/* ------------------------------------------------------------------------------------------- */
+static int gene_cmp_less(const kmo_pair *a, const kmo_pair *b, void *ctx) { (void)ctx; return a->score > b->score; }
+int kmo_gene_label_read(const kmo_db *db, const char *seq, int len, uint32_t *valid_cnt, uint32_t *gene, uint32_t *count) {
+    const int k = db->kmer_len;
+    *valid_cnt = 0; *gene = 0; *count = 0;
+    if (len < k) return 0;
+    const int np = len - k + 1;
+    uint64_t *km = (uint64_t *)malloc((size_t)np * 8);
+    uint8_t *fl = (uint8_t *)malloc((size_t)np);
+    int bin;
+    kmo_encode_read(seq, len, k, km, fl, &bin);
+    kmo_pair *g = NULL; size_t ng = 0, cap = 0;
+    uint32_t ids[65536];
+    for (int p = 0; p < np; p++) {
+        if (fl[p] != 1) continue;
+        (*valid_cnt)++;
+        uint64_t ho[2];
+        const int64_t n = kmo_lookup_batch(db, &km[p], 1, ho, ids, 65536);
+        for (int64_t j = 0; j < n; j++) {
+            size_t q = 0;
+            while (q < ng && g[q].tid != ids[j]) q++;
+            if (q == ng) {
+                if (ng == cap) { cap = cap ? cap * 2 : 16; g = (kmo_pair *)realloc(g, cap * sizeof *g); }
+                g[ng].tid = ids[j]; g[ng].score = 1.0f; ng++;
+            } else g[q].score += 1.0f;
+        }
+    }
+    if (ng) { kmo_std_sort(g, ng, gene_cmp_less, NULL); *gene = g[0].tid; *count = (uint32_t)g[0].score; }
+    free(g); free(km); free(fl);
+    return (int)ng;
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* TaxNodeStat::begin / next -- TaxNodeStat.hpp:60-256                                           */
 /* Produces the tid sequence next() would hand out (32-bit ids) and taxidCount().              */
 /* ------------------------------------------------------------------------------------------- */

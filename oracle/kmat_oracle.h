@@ -100,6 +100,10 @@ const kmo_pair *kmo_lineage(const kmo_ctx *);
 int64_t kmo_lookup_batch(const kmo_db *, const uint64_t *kmers, uint32_t n, uint64_t *hit_off, uint32_t *ids,
                          uint64_t cap);
 
+/* gene_label.cpp:217-301 for one read against a gene DB: number of unique canonical k-mers (cnt), the gene id std::sort
+ * puts first and its k-mer count; returns the number of distinct gene ids hit (0 = the reference prints nothing). */
+int kmo_gene_label_read(const kmo_db *, const char *seq, int len, uint32_t *valid_cnt, uint32_t *gene, uint32_t *count);
+
 /* K1 hook: canonical k-mers of one read exactly as retrieve_kmer_labels walks it
  * (read_label.cpp:978-1017).  out_kmer[p]: canonical k-mer at position p; out_flag[p]: 0 = no valid
  * k-mer ends here, 1 = valid first occurrence, 2 = valid duplicate.  Returns valid_kmers; bin_sel

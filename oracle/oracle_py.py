@@ -82,6 +82,7 @@ def lib():
         L.kmo_lookup_batch.argtypes = [C.POINTER(Db), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64]
         L.kmo_encode_read.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         L.kmo_format_tail.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_size_t]
+        L.kmo_gene_label_read.argtypes = [C.POINTER(Db), C.c_char_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.kmo_logf.restype = C.c_float
         L.kmo_logf.argtypes = [C.c_float]
         _lib = L
@@ -331,6 +332,16 @@ class Oracle:
         for i in range(len(res)):
             n = self.L.kmo_format_tail(self.ctx, res[i:i + 1].ctypes.data, buf, len(buf))
             out.append(buf.raw[:n].decode())
+        return out
+
+    def gene_label(self, seqs):
+        """gene_label.cpp:217-301 per read -> list of (n_genes, valid_cnt, gene, count)."""
+        out = []
+        v, g, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        for s_ in seqs:
+            b = s_ if isinstance(s_, bytes) else s_.encode("latin-1")
+            n = self.L.kmo_gene_label_read(C.byref(self.cdb), b, len(b), C.byref(v), C.byref(g), C.byref(c))
+            out.append((n, v.value, g.value, c.value))
         return out
 
     def lookup(self, kmers):

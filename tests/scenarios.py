@@ -66,3 +66,34 @@ def build_inputs(name: str, workdir: str) -> dict:
         f.write(f"{tax.leaves[0]}\n{tax.leaves[3]}\n")
     paths["workdir"] = workdir
     return dict(paths=paths, tax=tax, genomes=genomes, hdrs=hdrs, seqs=seqs)
+
+
+# ------------------------------------------------------------------------------------------------
+# gene_label scenario: a gene DB over the genomes of a read_label scenario
+# ------------------------------------------------------------------------------------------------
+GENE_LEN = 500
+GENE_ID0 = 7_000_000            # 32-bit ids, far above the 16-bit range
+
+
+def build_gene_table(name: str):
+    """Cut every genome of scenario `name` into GENE_LEN-base "genes" (ids GENE_ID0 + running index) and map every
+    canonical k-mer to the ascending list of genes containing it.  Returns (kmers, offs, gene ids, annotation lines);
+    genes of sibling genomes share k-mers through the scenario's shared segments, so multi-gene lists occur."""
+    import numpy as np
+    sc = SCENARIOS[name]
+    tax = fx.make_taxonomy(sc["seed"], sc["n_leaves"], specials=True)
+    genomes = fx.make_genomes(sc["seed"] + 1, tax, sc["genome_len"], share_frac=sc["share"],
+                              conserved_rank=sc["cons_rank"], conserved_len=sc["cons_len"])
+    pairs, annot, gid = [], [], GENE_ID0
+    for tid, codes in genomes.items():
+        for a in range(0, len(codes) - GENE_LEN + 1, GENE_LEN):
+            km = np.unique(fx.canonical_kmers(codes[a:a + GENE_LEN], K))
+            pairs.append(np.stack([km, np.full(len(km), gid, dtype=np.uint64)], axis=1))
+            annot.append(f"{tid}\t{gid}\tgene_{gid - GENE_ID0}_of_{tid}\thypothetical protein {a}..{a + GENE_LEN}")
+            gid += 1
+    allp = np.concatenate(pairs)
+    order = np.lexsort((allp[:, 1], allp[:, 0]))
+    allp = allp[order]
+    kmers, start = np.unique(allp[:, 0], return_index=True)
+    offs = np.concatenate([start, [len(allp)]]).astype(np.uint64)
+    return kmers.astype(np.uint64), offs, allp[:, 1].astype(np.uint32), annot
