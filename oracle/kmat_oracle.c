@@ -266,6 +266,8 @@ struct kmo_ctx {
     int models_loaded;             /* loadRandHits ran (gRank2num populated) */
     char *class_names[KMO_MAX_CLASSES]; int n_classes;
     pairvec cands, lineage;
+    /* rand_read_label accumulators (max_match / match_cnt, rand_read_label.cpp:182-183) */
+    u32map null_row; u32vec null_tids; float *null_max; int32_t *null_cnt; uint32_t null_cap;
 };
 
 static int class_id(kmo_ctx *c, const char *s) {
@@ -305,12 +307,13 @@ void kmo_ctx_free(kmo_ctx *c) {
     free(c->models); free(c->read_len_vec); free(c->read_len_avgs);
     for (int i = 0; i < c->n_classes; i++) free(c->class_names[i]);
     free(c->cands.v); free(c->lineage.v);
+    u32map_free(&c->null_row); free(c->null_tids.v); free(c->null_max); free(c->null_cnt);
     free(c);
 }
 void kmo_default_opts(kmo_opts *o) {
     /* read_label.cpp:1336-1347 and ScoreOptions ctor :488 */
     o->min_kmer = 35; o->min_fnd_kmer = 1; o->sdiff = 1.0f; o->hbias = 3.0f; o->min_score = 0.0f;
-    o->max_count = 65535; o->permissive = 0; o->phix_screen = 1; o->prn_all = 0; o->prn_read = 1;
+    o->max_count = 65535; o->permissive = 0; o->phix_screen = 1; o->prn_all = 0; o->prn_read = 1; o->rkmer = 0;
 }
 void kmo_set_opts(kmo_ctx *c, const kmo_opts *o) { c->opt = *o; }
 void kmo_set_db(kmo_ctx *c, const kmo_db *d) { c->db = *d; }
@@ -805,8 +808,9 @@ static void retrieve_kmer_labels(kmo_ctx *c, read_state *rs, const char *str, in
         if (++k >= klen) {                                                        /* :1002 */
             valid_kmers++; valid_gc_cnt += gc_cnt; valid_tot_cnt += tot_cnt; gc_cnt = 0; tot_cnt = 0;
             uint64_t kmer_id = forward < reverse ? forward : reverse;            /* :1009 */
-            if (!u64set_insert(&rs->seen, kmer_id)) continue;                     /* :1010,1017 */
             const int pos = j - klen + 1;
+            if (c->opt.rkmer) rs->label[pos].first = 0;                           /* rkmer.hpp:104, before the dup check :106 */
+            if (!u64set_insert(&rs->seen, kmer_id)) continue;                     /* :1010,1017 */
             rs->label[pos].first = 0;                                             /* :1015 */
             tns_run(c, kmer_id, &rs->tns, &rs->heap);                             /* :1019-1026 */
             if (rs->tns.err) { rs->err = rs->tns.err; return; }
@@ -815,8 +819,10 @@ static void retrieve_kmer_labels(kmo_ctx *c, read_state *rs, const char *str, in
             rs->obs.n = 0;
             for (size_t q = 0; q < rs->tns.tids.n; q++) {                         /* while(h->next()) :1031-1066 */
                 uint32_t tid = rs->tns.tids.v[q];
-                if (is_human(tid) && seenHuman) continue;
-                else if (is_human(tid) && !seenHuman) { tid = 9606; seenHuman = 1; }
+                if (!c->opt.rkmer) {                                              /* absent from rkmer.hpp:119-121 */
+                    if (is_human(tid) && seenHuman) continue;
+                    else if (is_human(tid) && !seenHuman) { tid = 9606; seenHuman = 1; }
+                }
                 if (tid == 20999999u || bad_genome(tid)) continue;
                 uint16_t ng = rs->tns.count;
                 if (dcnt == 0) { if (ng <= 0) ng = 1; rs->label[pos].first = (int16_t)ng; }   /* :1040-1046 */
@@ -1133,6 +1139,12 @@ static void construct_labels(kmo_ctx *c, read_state *rs, int bin_sel, kmo_result
 }
 
 /* proc_line -- read_label.cpp:1211-1279 */
+static void rs_free(read_state *rs) {
+    for (int p = 0; p < rs->cap_label; p++) free(rs->label[p].set.v);
+    free(rs->label); free(rs->taxid_lst.v); u32map_free(&rs->tax2idx); u32map_free(&rs->leaf_track); free(rs->leaf_keys.v);
+    free(rs->path.v); free(rs->path2.v); free(rs->obs.v); free(rs->sortbuf.v); free(rs->heap.v); free(rs->tns.tids.v);
+    free(rs->seen.k); free(rs->seen.u);
+}
 static void proc_read(kmo_ctx *c, read_state *rs, const char *seq, int len, kmo_result *res) {
     memset(res, 0, sizeof *res);
     const int k = c->db.kmer_len;
@@ -1163,11 +1175,139 @@ int kmo_label_batch(kmo_ctx *c, const char *bases, const uint64_t *offs, uint32_
     read_state rs; memset(&rs, 0, sizeof rs);
     c->cands.n = 0; c->lineage.n = 0;
     for (uint32_t i = 0; i < n; i++) proc_read(c, &rs, bases + offs[i], (int)(offs[i + 1] - offs[i]), &results[i]);
-    for (int p = 0; p < rs.cap_label; p++) free(rs.label[p].set.v);
-    free(rs.label); free(rs.taxid_lst.v); u32map_free(&rs.tax2idx); u32map_free(&rs.leaf_track); free(rs.leaf_keys.v);
-    free(rs.path.v); free(rs.path2.v); free(rs.obs.v); free(rs.sortbuf.v); free(rs.heap.v); free(rs.tns.tids.v);
-    free(rs.seen.k); free(rs.seen.u);
+    rs_free(&rs);
     return 0;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* rand_read_label (null-model generation) -- src/rand_read_label.cpp, src/rkmer.hpp               */
+/* ------------------------------------------------------------------------------------------- */
+/* glibc stdlib/random_r.c: __srandom_r / __random_r for the default TYPE_3 state (degree 31, separation 3) */
+void kmo_srand(kmo_glibc_rand *g, unsigned seed) {
+    if (seed == 0) seed = 1;
+    int32_t word = (int32_t)seed;
+    g->st[0] = word;
+    for (int i = 1; i < 31; i++) {                 /* 16807 * word % 2147483647 without overflow */
+        long hi = word / 127773, lo = word % 127773;
+        word = (int32_t)(16807 * lo - 2836 * hi);
+        if (word < 0) word += 2147483647;
+        g->st[i] = word;
+    }
+    g->f = 3; g->r = 0;
+    for (int i = 0; i < 310; i++) (void)kmo_rand(g);
+}
+int kmo_rand(kmo_glibc_rand *g) {
+    uint32_t v = (uint32_t)g->st[g->f] + (uint32_t)g->st[g->r];
+    g->st[g->f] = (int32_t)v;
+    if (++g->f >= 31) { g->f = 0; ++g->r; }
+    else if (++g->r >= 31) g->r = 0;
+    return (int)(v >> 1);
+}
+void kmo_gen_rand_reads(kmo_glibc_rand *g, uint64_t first, uint64_t n, int read_len, char *bases) {
+    const unsigned rl = (unsigned)read_len;
+    for (uint64_t i = 0; i < n; i++) {
+        char *rb = bases + i * rl;
+        const int gc_bucket = (int)((first + i) % 10);                 /* :693 */
+        const int beg = gc_bucket * 10, end = gc_bucket * 10 + 9;      /* gc_range, :677-685: (int)lval, (int)(lval+width-1) */
+        const int range = (end - beg) + 1;
+        const int gc_draw = (kmo_rand(g) % range) + beg;               /* :88 */
+        const float gc_pcnt = (float)(gc_draw / 100.0);                /* :89 */
+        const unsigned num_gc = (unsigned)(gc_pcnt * (float)rl);       /* :90 (float * unsigned -> float) */
+        for (unsigned q = 0; q < num_gc; q++) rb[q] = (kmo_rand(g) % 100) < 50 ? 'g' : 'c';      /* :91-95 */
+        for (unsigned q = num_gc; q < rl; q++) rb[q] = (kmo_rand(g) % 100) < 50 ? 'a' : 't';     /* :96-100 */
+        for (unsigned q = 1; q < rl; q++) {                            /* std::random_shuffle, libstdc++ stl_algo.h */
+            const unsigned j = (unsigned)kmo_rand(g) % (q + 1);
+            if (j != q) { char t = rb[q]; rb[q] = rb[j]; rb[j] = t; }
+        }
+    }
+}
+
+static uint32_t null_row_of(kmo_ctx *c, uint32_t tid) {
+    uint32_t row;
+    if (u32map_find(&c->null_row, tid, &row)) return row;
+    if (!c->null_row.cap) u32map_init(&c->null_row, 1024);
+    row = (uint32_t)c->null_tids.n;
+    if (row >= c->null_cap) {
+        uint32_t ncap = c->null_cap ? c->null_cap * 2 : 1024;
+        c->null_max = (float *)realloc(c->null_max, (size_t)ncap * 10 * sizeof(float));
+        c->null_cnt = (int32_t *)realloc(c->null_cnt, (size_t)ncap * 10 * sizeof(int32_t));
+        memset(c->null_max + (size_t)c->null_cap * 10, 0, (size_t)(ncap - c->null_cap) * 10 * sizeof(float));
+        memset(c->null_cnt + (size_t)c->null_cap * 10, 0, (size_t)(ncap - c->null_cap) * 10 * sizeof(int32_t));
+        c->null_cap = ncap;
+    }
+    u32map_put(&c->null_row, tid, row);
+    u32vec_push(&c->null_tids, tid);
+    return row;
+}
+
+int kmo_null_batch(kmo_ctx *c, const char *bases, const uint64_t *offs, uint32_t n, uint64_t first_index) {
+    read_state rs; memset(&rs, 0, sizeof rs);
+    const int k = c->db.kmer_len;
+    const int save_rkmer = c->opt.rkmer;
+    c->opt.rkmer = 1;
+    int rc = 0;
+    u32map cnt_tids; memset(&cnt_tids, 0, sizeof cnt_tids);
+    u32vec cnt_keys = {0};
+    for (uint32_t i = 0; i < n && rc == 0; i++) {
+        const char *seq = bases + offs[i];
+        const int len = (int)(offs[i + 1] - offs[i]);
+        const unsigned gcbucket = (unsigned)((first_index + i) % 10);
+        if (len < k) continue;                                                       /* :372-374 */
+        const int np = len - k + 1;
+        if (np > rs.cap_label) {
+            rs.label = (label_info *)realloc(rs.label, (size_t)np * sizeof(label_info));
+            memset(rs.label + rs.cap_label, 0, (size_t)(np - rs.cap_label) * sizeof(label_info));
+            rs.cap_label = np;
+        }
+        rs.n_label = np;
+        for (int p = 0; p < np; p++) { rs.label[p].first = -1; rs.label[p].set.n = 0; }  /* :377 */
+        rs.taxid_lst.n = 0;
+        u32map_free(&rs.tax2idx); u32map_init(&rs.tax2idx, 64);
+        rs.err = 0;
+        int valid = 0, bin_sel = 0;
+        retrieve_kmer_labels(c, &rs, seq, len, k, &valid, &bin_sel);                 /* rkmer.hpp:76-294 */
+        if (rs.err) { rc = rs.err; break; }
+        if (valid <= 0) continue;                                                    /* :381 */
+        u32map_free(&cnt_tids); u32map_init(&cnt_tids, 64); cnt_keys.n = 0;
+        for (int p = 0; p < np; p++)                                                 /* :382-393 */
+            for (size_t q = 0; q < rs.label[p].set.n; q++) {
+                const uint32_t tid = rs.label[p].set.v[q];
+                uint32_t v;
+                if (u32map_find(&cnt_tids, tid, &v)) u32map_put(&cnt_tids, tid, v + 1);
+                else { u32map_put(&cnt_tids, tid, 1); u32vec_push(&cnt_keys, tid); }
+            }
+        for (size_t q = 0; q < cnt_keys.n; q++) {                                    /* construct_labels :184-213 */
+            const uint32_t tid = cnt_keys.v[q];
+            uint32_t found = 0; u32map_find(&cnt_tids, tid, &found);
+            const float label_prob = (float)(int)found / (float)valid;               /* :195 */
+            const uint32_t row = null_row_of(c, tid);
+            float *mx = c->null_max + (size_t)row * 10 + gcbucket;
+            if (*mx < label_prob) *mx = label_prob;                                   /* :203-210 (first insert: 0 -> prob) */
+            c->null_cnt[(size_t)row * 10 + gcbucket] += 1;
+        }
+    }
+    c->opt.rkmer = save_rkmer;
+    u32map_free(&cnt_tids); free(cnt_keys.v);
+    rs_free(&rs);
+    return rc;
+}
+uint32_t kmo_null_rows(const kmo_ctx *c) { return (uint32_t)c->null_tids.n; }
+void kmo_null_get(const kmo_ctx *c, uint32_t *tids, float *max_frac, int32_t *cnt) {
+    const uint32_t n = (uint32_t)c->null_tids.n;
+    uint32_t *ord = (uint32_t *)malloc((size_t)(n ? n : 1) * sizeof(uint32_t));
+    memcpy(ord, c->null_tids.v, (size_t)n * sizeof(uint32_t));
+    qsort(ord, n, 4, u32_cmp);
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t row = 0; u32map_find(&c->null_row, ord[i], &row);
+        tids[i] = ord[i];
+        memcpy(max_frac + (size_t)i * 10, c->null_max + (size_t)row * 10, 10 * sizeof(float));
+        memcpy(cnt + (size_t)i * 10, c->null_cnt + (size_t)row * 10, 10 * sizeof(int32_t));
+    }
+    free(ord);
+}
+void kmo_null_reset(kmo_ctx *c) {
+    u32map_free(&c->null_row); c->null_tids.n = 0;
+    free(c->null_max); free(c->null_cnt); c->null_max = NULL; c->null_cnt = NULL; c->null_cap = 0;
 }
 
 /* Text after "hdr\tread\t" -- read_label.cpp:1218,1233,1271,844-848,894-937.  Floats go through

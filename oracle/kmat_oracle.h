@@ -61,6 +61,8 @@ typedef struct {
     int phix_screen;    /* default 1, -h clears */
     int prn_all;        /* -p */
     int prn_read;       /* default 1, -a clears */
+    int rkmer;          /* 1: src/rkmer.hpp's retrieve_kmer_labels (rand_read_label): no human collapse (rkmer.hpp:119-121);
+                           set by kmo_null_batch, never by read_label */
 } kmo_opts;
 
 typedef struct {
@@ -103,6 +105,26 @@ int64_t kmo_lookup_batch(const kmo_db *, const uint64_t *kmers, uint32_t n, uint
 /* gene_label.cpp:217-301 for one read against a gene DB: number of unique canonical k-mers (cnt), the gene id std::sort
  * puts first and its k-mer count; returns the number of distinct gene ids hit (0 = the reference prints nothing). */
 int kmo_gene_label_read(const kmo_db *, const char *seq, int len, uint32_t *valid_cnt, uint32_t *gene, uint32_t *count);
+
+/* ---- rand_read_label: null-model generation ---------------------------------------------
+ * glibc's srand()/rand() (stdlib/random_r.c, TYPE_3: x^31 + x^3 + 1 additive feedback, 310 outputs discarded after
+ * seeding) restated, so that the reads the UNMODIFIED reference draws under a fixed time(0) are known here. */
+typedef struct { int32_t st[31]; int f, r; } kmo_glibc_rand;
+void kmo_srand(kmo_glibc_rand *, unsigned seed);
+int kmo_rand(kmo_glibc_rand *);
+/* genRandRead (rand_read_label.cpp:85-103) + libstdc++'s std::random_shuffle(first, last) (bits/stl_algo.h: for i in
+ * 1..n-1 swap(i, rand() % (i+1))), for reads first..first+n-1 of the OMP loop (:692-699) on ONE thread: read i is drawn
+ * for GC bucket i % 10 with range [10*b, 10*b+9] (:673-685).  bases receives n * read_len lower-case letters. */
+void kmo_gen_rand_reads(kmo_glibc_rand *, uint64_t first, uint64_t n, int read_len, char *bases);
+/* proc_line + construct_labels of rand_read_label.cpp (:367-397, :184-213) for n reads; read i belongs to GC bucket
+ * (first_index + i) % 10.  Accumulates per (tid, bucket) the maximum hit fraction and the number of reads; the
+ * accumulator lives in the ctx until kmo_null_reset. */
+int kmo_null_batch(kmo_ctx *, const char *bases, const uint64_t *offs, uint32_t n, uint64_t first_index);
+uint32_t kmo_null_rows(const kmo_ctx *);
+/* rows in ascending tid order (the std::map order the .rand_lst file is written in, :745-754): tids[rows],
+ * max_frac[rows*10], cnt[rows*10] */
+void kmo_null_get(const kmo_ctx *, uint32_t *tids, float *max_frac, int32_t *cnt);
+void kmo_null_reset(kmo_ctx *);
 
 /* K1 hook: canonical k-mers of one read exactly as retrieve_kmer_labels walks it
  * (read_label.cpp:978-1017).  out_kmer[p]: canonical k-mer at position p; out_flag[p]: 0 = no valid

@@ -42,7 +42,11 @@ assert RESULT_DTYPE.itemsize == C.sizeof(Result)
 class Opts(C.Structure):
     _fields_ = [("min_kmer", C.c_int), ("min_fnd_kmer", C.c_int), ("sdiff", C.c_float), ("hbias", C.c_float),
                 ("min_score", C.c_float), ("max_count", C.c_int), ("permissive", C.c_int), ("phix_screen", C.c_int),
-                ("prn_all", C.c_int), ("prn_read", C.c_int)]
+                ("prn_all", C.c_int), ("prn_read", C.c_int), ("rkmer", C.c_int)]
+
+
+class GlibcRand(C.Structure):
+    _fields_ = [("st", C.c_int32 * 31), ("f", C.c_int), ("r", C.c_int)]
 
 
 class Db(C.Structure):
@@ -83,6 +87,14 @@ def lib():
         L.kmo_encode_read.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         L.kmo_format_tail.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_size_t]
         L.kmo_gene_label_read.argtypes = [C.POINTER(Db), C.c_char_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.kmo_srand.argtypes = [C.POINTER(GlibcRand), C.c_uint]
+        L.kmo_rand.argtypes = [C.POINTER(GlibcRand)]
+        L.kmo_gen_rand_reads.argtypes = [C.POINTER(GlibcRand), C.c_uint64, C.c_uint64, C.c_int, C.c_char_p]
+        L.kmo_null_batch.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint64]
+        L.kmo_null_rows.restype = C.c_uint32
+        L.kmo_null_rows.argtypes = [C.c_void_p]
+        L.kmo_null_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.kmo_null_reset.argtypes = [C.c_void_p]
         L.kmo_logf.restype = C.c_float
         L.kmo_logf.argtypes = [C.c_float]
         _lib = L
@@ -334,6 +346,29 @@ class Oracle:
             out.append(buf.raw[:n].decode())
         return out
 
+    def null_batch(self, seqs, first_index=0):
+        """rand_read_label.cpp proc_line/construct_labels over reads whose GC bucket is (first_index + i) % 10;
+        accumulates into the ctx."""
+        bs = [s.encode() if isinstance(s, str) else s for s in seqs]
+        offs = np.zeros(len(bs) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(b) for b in bs])
+        rc = self.L.kmo_null_batch(self.ctx, b"".join(bs), offs.ctypes.data, len(bs), first_index)
+        if rc:
+            raise RuntimeError(f"kmo_null_batch rc={rc}")
+
+    def null_table(self):
+        """(tids ascending, max fraction [rows,10] f32, read count [rows,10] i32)"""
+        n = self.L.kmo_null_rows(self.ctx)
+        t = np.zeros(n, dtype=np.uint32)
+        m = np.zeros((n, 10), dtype=np.float32)
+        c = np.zeros((n, 10), dtype=np.int32)
+        if n:
+            self.L.kmo_null_get(self.ctx, t.ctypes.data, m.ctypes.data, c.ctypes.data)
+        return t, m, c
+
+    def null_reset(self):
+        self.L.kmo_null_reset(self.ctx)
+
     def gene_label(self, seqs):
         """gene_label.cpp:217-301 per read -> list of (n_genes, valid_cnt, gene, count)."""
         out = []
@@ -423,3 +458,23 @@ def assemble_lines(hdrs, seqs, tails, prn_read=True):
     for h, s, t in zip(hdrs, seqs, tails):
         parts.append(f"{h}\t{s if prn_read else 'X'}\t{t}")
     return "".join(parts)
+
+
+def gen_rand_reads(seed, n_reads, read_len, first=0):
+    """The reads the reference rand_read_label draws on one thread after srand(seed) (rand_read_label.cpp:85-103,
+    :687-699): list of n_reads lower-case strings."""
+    g = GlibcRand()
+    lib().kmo_srand(C.byref(g), C.c_uint(seed & 0xFFFFFFFF))
+    buf = C.create_string_buffer(n_reads * read_len + 1)
+    lib().kmo_gen_rand_reads(C.byref(g), first, n_reads, read_len, buf)
+    raw = buf.raw[:n_reads * read_len].decode()
+    return [raw[i * read_len:(i + 1) * read_len] for i in range(n_reads)]
+
+
+def format_rand_lst(tids, mx, cnt):
+    """The .rand_lst text (rand_read_label.cpp:745-754): 'tid' then ' max cnt' per GC bucket; floats through
+    ostream<<float == %g."""
+    out = []
+    for i in range(len(tids)):
+        out.append(str(int(tids[i])) + "".join(" %g %d" % (float(mx[i, b]), int(cnt[i, b])) for b in range(mx.shape[1])) + "\n")
+    return "".join(out)

@@ -119,3 +119,22 @@ def collect_out_lines(ofbase, threads):
             with open(p) as f:
                 lines += f.read().split("\n")
     return [ln for ln in lines if ln]
+
+
+def rand_read_label(db, ofbase, depth, tree, n_reads, read_len, threads=1, map16=None, rank=None, prune=None, numrank=None,
+                    fixed_time=None, log=None, timeout=None):
+    """Invoke the reference rand_read_label with the flags of bin/gen_rand_mod.sh:137 (-w rank -f map -g N -i L -e depth
+    -p -t T -d db -c tree -o out; -h cut -r numeric ranks for the run-time pruning).  fixed_time: preload the time() shim
+    so that srand(time(0)) (rand_read_label.cpp:412) gets this seed.  Writes <ofbase>.rand_lst."""
+    cmd = [os.path.join(REF_BIN, "rand_read_label")]
+    if rank:
+        cmd += ["-w", rank]
+    if map16:
+        cmd += ["-f", map16]
+    cmd += ["-g", str(n_reads), "-i", str(read_len), "-e", depth, "-p", "-t", str(threads), "-d", db, "-c", tree, "-o", ofbase]
+    if prune:
+        cmd += ["-h", str(prune), "-r", numrank]
+    env = None
+    if fixed_time is not None:
+        env = {"LD_PRELOAD": os.path.join(REF_BIN, "libfixedtime.so"), "KMAT_FIXED_TIME": str(fixed_time)}
+    return _run(cmd, log=log, env=env, timeout=timeout)

@@ -97,3 +97,54 @@ def build_gene_table(name: str):
     kmers, start = np.unique(allp[:, 0], return_index=True)
     offs = np.concatenate([start, [len(allp)]]).astype(np.uint64)
     return kmers.astype(np.uint64), offs, allp[:, 1].astype(np.uint32), annot
+
+
+# ------------------------------------------------------------------------------------------------
+# rand_read_label scenario.  The reference draws its reads itself (rand(), seeded by time(0)); with
+# the seed fixed (oracle/standins/fixed_time.c) they are the reads oracle_py.gen_rand_reads predicts, and the DB is
+# built FROM mutated fragments of those reads so that "random" reads do hit it (a 20-mer of a truly random read is in a
+# small DB with probability ~1e-7).
+# ------------------------------------------------------------------------------------------------
+NULLGEN_TIME = 1700000123            # the value time(0) returns under the shim = the srand() seed
+NULLGEN_RUNS = {
+    # tag: read length (-i), reads per thread (-g), pruning (-h N with -r numeric ranks)
+    "rl150": dict(read_len=150, n_reads=600, prune=None),
+    "rl64p": dict(read_len=64, n_reads=500, prune=3),
+}
+NULLGEN_TAX = dict(seed=37, n_leaves=30)
+
+
+def build_nullgen_inputs(workdir: str) -> dict:
+    import numpy as np
+    from oracle import oracle_py as op
+    os.makedirs(workdir, exist_ok=True)
+    tax = fx.make_taxonomy(NULLGEN_TAX["seed"], NULLGEN_TAX["n_leaves"], specials=True)
+    paths = fx.write_taxonomy_files(tax, workdir)
+    rng = fx.rng_for(NULLGEN_TAX["seed"] + 1)
+    code = {"a": 0, "c": 1, "g": 2, "t": 3}
+    frags = {t: [fx.random_codes(rng, 300, 0.5)] for t in tax.leaves}
+    leaves = list(tax.leaves)
+    for tag, run in NULLGEN_RUNS.items():
+        reads = op.gen_rand_reads(NULLGEN_TIME, run["n_reads"], run["read_len"])
+        for r in reads:
+            if rng.random() > 0.6:
+                continue
+            codes = np.array([code[ch] for ch in r], dtype=np.uint8)
+            li = int(rng.integers(0, len(leaves)))
+            owners = [leaves[li]]
+            if rng.random() < 0.5:
+                owners.append(leaves[(li + 1) % len(leaves)])     # usually a sibling: shared k-mers, multi-tid lists
+            if rng.random() < 0.2:
+                owners.append(leaves[int(rng.integers(0, len(leaves)))])
+            for o in owners:
+                a = int(rng.integers(0, max(1, len(codes) - 30)))
+                b = int(rng.integers(min(len(codes), a + 30), len(codes) + 1))
+                seg = codes[a:b].copy()
+                flip = rng.random(len(seg)) < rng.uniform(0, 0.03)
+                seg[flip] = (seg[flip] + rng.integers(1, 4, size=int(flip.sum()))) % 4
+                frags[o].append(seg)
+    genomes = {t: np.concatenate(v) for t, v in frags.items()}
+    paths["genomes"] = os.path.join(workdir, "genomes.fa")
+    fx.write_kpc_fasta(paths["genomes"], genomes)
+    paths["workdir"] = workdir
+    return dict(paths=paths, tax=tax, genomes=genomes)
