@@ -139,6 +139,9 @@ typedef struct {
     int32_t permissive;    /* -s                                           :1382      */
     int32_t phix_screen;   /* default 1; -h clears                         :41,1355   */
     int32_t want_lineage;  /* also return the valid_cand list (printed on MultiMatch without -p, :917-927) */
+    int32_t rkmer_mode;    /* 1: the ctx serves kmat_null_* (rand_read_label): src/rkmer.hpp's retrieve_kmer_labels, i.e. NO
+                              human collapse (absent at rkmer.hpp:119-121) and no -j / -z thresholds (min_kmer and
+                              min_fnd_kmer are forced to 0); kmat_label_batch* then return KMAT_ERR_ARG.  default 0 */
 } kmat_opts;
 void kmat_opts_default(kmat_opts *);
 
@@ -225,6 +228,34 @@ typedef struct {
     float score;           /* (float)count / (float)cnt                                                      (:298)      */
 } kmat_gene_result;
 int kmat_gene_batch(const kmat_db *, const char *bases, const uint64_t *offs, uint32_t n_reads, kmat_gene_result *out);
+
+/* ---- null-model generation: rand_read_label -------------------------------
+ * Replaces the body of rand_read_label's OMP loop and its merge phase (src/rand_read_label.cpp:687-735): genRandRead
+ * (:85-103), proc_line (:367-397) over rkmer.hpp's retrieve_kmer_labels (rkmer.hpp:76-294), construct_labels (:184-213).
+ * The ctx must have been created with opts.rkmer_mode = 1.  Read i of the run (0-based, all "threads" concatenated)
+ * belongs to GC bucket i % KMAT_NULL_BUCKETS (:693); per (taxid, bucket) the ctx accumulates on the device the maximum
+ * over reads of hits / valid_kmers (float, :195) and the number of reads that hit the taxid. */
+#define KMAT_NULL_BUCKETS 10
+int kmat_null_reset(kmat_ctx *);
+/* Caller-provided reads (host buffers), read r of the batch having run index first_index + r. */
+int kmat_null_batch(kmat_ctx *, const char *bases, const uint64_t *offs, uint32_t n_reads, uint64_t first_index);
+/* Reads drawn ON THE DEVICE, n_reads of read_len bases with run indices first_index.., from a counter-based generator
+ * keyed by (seed, run index): the same (seed, index) gives the same read whatever the batching or the number of GPUs.
+ * Distribution as genRandRead: gc_draw uniform in [10 b, 10 b + 9], num_gc = (unsigned)((float)(gc_draw / 100.0) * len)
+ * positions chosen uniformly at random hold g/c (fair coin), the others a/t (fair coin). */
+int kmat_null_random(kmat_ctx *, uint64_t seed, uint64_t first_index, uint32_t n_reads, uint32_t read_len);
+/* The same reads written to a host buffer (n_reads * read_len bytes) instead of being labeled (test hook). */
+int kmat_null_draw_reads(int device, uint64_t seed, uint64_t first_index, uint32_t n_reads, uint32_t read_len, char *bases);
+/* Accumulated rows in ascending taxid order = the lines of <ofbase>.rand_lst (:736-755): every taxid hit by at least one
+ * read.  tids[cap_rows], max_frac / counts[cap_rows * KMAT_NULL_BUCKETS]; *n_rows receives the number of rows (also
+ * when it exceeds cap_rows: KMAT_ERR_OVERFLOW, nothing written).  *reads_error: reads the kernels could not process
+ * (more than 64 candidate taxids); they contribute nothing. */
+int kmat_null_fetch(kmat_ctx *, uint32_t *tids, float *max_frac, uint64_t *counts, uint32_t cap_rows, uint32_t *n_rows,
+                    uint64_t *reads_error);
+/* Merge rows of several contexts / GPUs (max of maxima, sum of counts; what :702-735 does across threads) and write the
+ * .rand_lst text.  sets = n_sets pointers to (tids, max_frac, counts) triples with n_rows[i] rows each, each ascending. */
+int kmat_null_write(const char *path, int n_sets, const uint32_t *const *tids, const float *const *max_frac,
+                    const uint64_t *const *counts, const uint32_t *n_rows);
 
 /* Page-locked host memory for the buffers of kmat_label_batch (optional; NULL when no device / out of memory). */
 void *kmat_host_alloc(size_t bytes);

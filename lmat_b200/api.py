@@ -27,7 +27,7 @@ GENE_DTYPE = np.dtype([("status", "<i4"), ("valid_kmers", "<u4"), ("n_genes", "<
 class Opts(C.Structure):
     _fields_ = [("min_kmer", C.c_int32), ("min_fnd_kmer", C.c_int32), ("sdiff", C.c_float), ("hbias", C.c_float),
                 ("min_score", C.c_float), ("max_count", C.c_int32), ("permissive", C.c_int32),
-                ("phix_screen", C.c_int32), ("want_lineage", C.c_int32)]
+                ("phix_screen", C.c_int32), ("want_lineage", C.c_int32), ("rkmer_mode", C.c_int32)]
 
 
 class BatchStats(C.Structure):
@@ -51,6 +51,7 @@ EXPORTS = [
     "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_set_pipeline", "kmat_gene_batch", "kmat_shard_encode", "kmat_shard_serve", "kmat_shard_finish", "kmat_ctx_device_results", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench",
     "kmat_set_l2_fetch_granularity", "kmat_reader_open", "kmat_reader_open_mt", "kmat_reader_close", "kmat_read_batch_new", "kmat_read_batch_free",
     "kmat_reader_next", "kmat_read_batch_view", "kmat_tally_class", "kmat_host_alloc", "kmat_host_free",
+    "kmat_null_reset", "kmat_null_batch", "kmat_null_random", "kmat_null_draw_reads", "kmat_null_fetch", "kmat_null_write",
 ]
 
 _lib = None
@@ -123,6 +124,12 @@ def lib():
     L.kmat_host_alloc.restype = vp
     L.kmat_host_alloc.argtypes = [C.c_size_t]
     L.kmat_host_free.argtypes = [vp]
+    L.kmat_null_reset.argtypes = [vp]
+    L.kmat_null_batch.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64]
+    L.kmat_null_random.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
+    L.kmat_null_draw_reads.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, vp]
+    L.kmat_null_fetch.argtypes = [vp, vp, vp, vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+    L.kmat_null_write.argtypes = [C.c_char_p, C.c_int, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -361,6 +368,31 @@ class Ctx:
             out.append(buf.raw[:n].decode())
         return out
 
+    # ---- null-model generation (rand_read_label); the ctx must have been created with rkmer_mode = 1
+    def null_reset(self):
+        _check(lib().kmat_null_reset(self.h))
+
+    def null_batch(self, seqs=None, blob=None, offs=None, first_index=0):
+        if seqs is not None:
+            blob, offs = pack_reads(seqs)
+        ptr = blob if isinstance(blob, (bytes, bytearray)) else blob.ctypes.data
+        _check(lib().kmat_null_batch(self.h, ptr, offs.ctypes.data, len(offs) - 1, first_index))
+
+    def null_random(self, seed, first_index, n_reads, read_len):
+        _check(lib().kmat_null_random(self.h, seed, first_index, n_reads, read_len))
+
+    def null_table(self):
+        """(tids ascending, max fraction [rows, 10] f32, read counts [rows, 10] u64, reads the kernels could not process)"""
+        n, err = C.c_uint32(), C.c_uint64()
+        rc = lib().kmat_null_fetch(self.h, None, None, None, 0, C.byref(n), C.byref(err))
+        if rc not in (0, -10):
+            _check(rc)
+        t = np.zeros(n.value, dtype=np.uint32)
+        m = np.zeros((n.value, 10), dtype=np.float32)
+        c = np.zeros((n.value, 10), dtype=np.uint64)
+        _check(lib().kmat_null_fetch(self.h, t.ctypes.data, m.ctypes.data, c.ctypes.data, n.value, C.byref(n), C.byref(err)))
+        return t, m, c, err.value
+
     def label_device(self, d_bases_ptr, d_offs_ptr, n_reads, total_bases, max_read_len, d_out_ptr=None, stream=None):
         """kmat_label_batch_device: inputs already in HBM, results stay on the device; asynchronous."""
         _check(lib().kmat_label_batch_device(self.h, d_bases_ptr, d_offs_ptr, n_reads, total_bases, max_read_len, d_out_ptr, stream))
@@ -449,3 +481,22 @@ def read_file(path, fastq=False, max_reads=1 << 20, max_bases=1 << 28, threads=1
         L.kmat_read_batch_free(b)
         L.kmat_reader_close(r)
     return hdrs, seqs
+
+
+def null_draw_reads(seed, first_index, n_reads, read_len, device=0):
+    """The reads kmat_null_random draws on the device for run indices first_index.. (test hook): list of bytes."""
+    buf = np.zeros(n_reads * read_len, dtype=np.uint8)
+    _check(lib().kmat_null_draw_reads(device, seed, first_index, n_reads, read_len, buf.ctypes.data))
+    raw = buf.tobytes()
+    return [raw[i * read_len:(i + 1) * read_len] for i in range(n_reads)]
+
+
+def null_write(path, sets):
+    """kmat_null_write: merge (tids, max, counts) row sets (max / sum) and write the .rand_lst text."""
+    n = len(sets)
+    keep = [(np.ascontiguousarray(t, np.uint32), np.ascontiguousarray(m, np.float32), np.ascontiguousarray(c, np.uint64)) for t, m, c in sets]
+    tp = (C.c_void_p * n)(*[k[0].ctypes.data for k in keep])
+    mp = (C.c_void_p * n)(*[k[1].ctypes.data for k in keep])
+    cp = (C.c_void_p * n)(*[k[2].ctypes.data for k in keep])
+    nr = np.array([len(k[0]) for k in keep], dtype=np.uint32)
+    _check(lib().kmat_null_write(_b(path), n, tp, mp, cp, nr.ctypes.data))

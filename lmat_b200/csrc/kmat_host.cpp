@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <map>
 #include <sstream>
 #include <unordered_map>
 
@@ -50,7 +51,7 @@ extern "C" int kmat_abi_version(void) { return KMAT_ABI_VERSION; }
 extern "C" void kmat_opts_default(kmat_opts *o) {
     // read_label.cpp:1336-1347 and the ScoreOptions ctor (:488)
     o->min_kmer = 35; o->min_fnd_kmer = 1; o->sdiff = 1.0f; o->hbias = 3.0f; o->min_score = 0.0f;
-    o->max_count = 65535; o->permissive = 0; o->phix_screen = 1; o->want_lineage = 0;
+    o->max_count = 65535; o->permissive = 0; o->phix_screen = 1; o->want_lineage = 0; o->rkmer_mode = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -671,4 +672,38 @@ extern "C" int kmat_format_tail(const kmat_read_result *r, const kmat_pair *cand
     }
     if ((size_t)(p - buf) < cap) *p = 0;
     return (int)(p - buf);
+}
+
+// ---------------------------------------------------------------------------------------------
+// rand_read_label: merge phase and the .rand_lst writer (src/rand_read_label.cpp:702-755)
+// ---------------------------------------------------------------------------------------------
+extern "C" int kmat_null_write(const char *path, int n_sets, const uint32_t *const *tids, const float *const *max_frac,
+                               const uint64_t *const *counts, const uint32_t *n_rows) {
+    if (!path || n_sets < 0 || (n_sets && (!tids || !max_frac || !counts || !n_rows))) { kmat_set_error("kmat_null_write: bad argument"); return KMAT_ERR_ARG; }
+    struct Row { float mx[KMAT_NULL_BUCKETS]; uint64_t cnt[KMAT_NULL_BUCKETS]; };
+    std::map<uint32_t, Row> merged;                                  // merge_score / merge_count (:703-735)
+    for (int s = 0; s < n_sets; s++)
+        for (uint32_t i = 0; i < n_rows[s]; i++) {
+            auto it = merged.find(tids[s][i]);
+            if (it == merged.end()) { Row z; memset(&z, 0, sizeof z); it = merged.emplace(tids[s][i], z).first; }
+            for (int b = 0; b < KMAT_NULL_BUCKETS; b++) {
+                const float v = max_frac[s][(size_t)i * KMAT_NULL_BUCKETS + b];
+                if (v > it->second.mx[b]) it->second.mx[b] = v;
+                it->second.cnt[b] += counts[s][(size_t)i * KMAT_NULL_BUCKETS + b];
+            }
+        }
+    FILE *f = fopen(path, "w");
+    if (!f) { kmat_set_error("Could not open for writing %s", path); return KMAT_ERR_IO; }
+    char buf[64 * KMAT_NULL_BUCKETS + 32];
+    for (const auto &kv : merged) {                                  // sum_ofs<<tid; " "<<max_score[val]<<" "<<cnt[val]; endl (:745-754)
+        char *p = km_fmt_u32(buf, kv.first);
+        for (int b = 0; b < KMAT_NULL_BUCKETS; b++) {
+            *p++ = ' '; p = km_fmt_g(p, kv.second.mx[b]);
+            *p++ = ' '; p += snprintf(p, 24, "%llu", (unsigned long long)kv.second.cnt[b]);
+        }
+        *p++ = '\n';
+        if (fwrite(buf, 1, (size_t)(p - buf), f) != (size_t)(p - buf)) { fclose(f); kmat_set_error("write to %s failed", path); return KMAT_ERR_IO; }
+    }
+    if (fclose(f) != 0) { kmat_set_error("write to %s failed", path); return KMAT_ERR_IO; }
+    return KMAT_OK;
 }

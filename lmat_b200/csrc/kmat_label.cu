@@ -107,7 +107,7 @@ __device__ void kr_finish(const KmCtxDev &C, uint2 *seq, int n, uint32_t n_raw, 
     for (int i = 0; i < n; i++) {                                         // :1031-1038
         uint32_t nid = seq[i].x;
         uint32_t meta = kb_nodeA(C, nid).meta;
-        if (meta & KM_META_HUMAN) {
+        if ((meta & KM_META_HUMAN) && !C.opt.rkmer_mode) {              // no collapse in rkmer.hpp (:119-121)
             if (seenHuman) continue;
             nid = C.nid_human; meta = kb_nodeA(C, nid).meta; seenHuman = true;
         }
@@ -287,7 +287,7 @@ __device__ __forceinline__ unsigned long long kb_chunk(const KmScoreParams &P, K
                 const uint32_t e = aux;
                 if (e == KMAT_NONE) err = KMAT_ERR_BAD_TAXID;          // "bad taxid" assert (TaxNodeStat.hpp:235-238)
                 else if (!(e & KB_SID_DROP)) {
-                    v0 = (e & KB_SID_HUMAN) ? X.nid_human : (e & KB_SID_NIDMASK); a = 1;
+                    v0 = ((e & KB_SID_HUMAN) && !X.opt.rkmer_mode) ? X.nid_human : (e & KB_SID_NIDMASK); a = 1;
                     if (permissive) b = (kb_nodeA(X, v0).meta & KM_META_DEPTH_MASK) ? 1 : 0;
                 }
             } else {
@@ -816,7 +816,11 @@ struct kmat_ctx {
     kmat_pair *d_cands = nullptr, *d_lin = nullptr; uint64_t cap_cands = 0, cap_lin = 0;
     unsigned long long *d_cursors = nullptr;     // [0] cands, [1] lineage
     uint32_t *d_pool2 = nullptr; int pool2_mul = 1;            // resolved lists (km_resolve_kernel)
-    int resolved_max_count = -1, resolved_permissive = -1;
+    int resolved_max_count = -1, resolved_permissive = -1, resolved_rkmer = -1;
+    // rand_read_label accumulators (kmat_null.cuh): [n_nodes * KMAT_NULL_BUCKETS] max fraction (float bits) / read counts
+    uint32_t *d_null_max = nullptr, *d_null_cnt = nullptr; unsigned long long *d_null_err = nullptr;
+    uint64_t null_first = 0;                 // run index of read 0 of the pass being launched
+    char *d_null_bases = nullptr; uint64_t *d_null_offs = nullptr; uint64_t cap_null_bases = 0, cap_null_offs = 0;
     unsigned long long *d_long_masks = nullptr; uint32_t long_mask_cap = 0;
     unsigned long long *d_long_sets = nullptr; uint32_t long_slots = 0; int long_warps = 0;
     KmStatsDev *d_stats = nullptr;
@@ -841,7 +845,8 @@ static KmCtxDev km_ctx_dev(const kmat_ctx *c);
 static int km_resolve_lists(kmat_ctx *c) {
     const kmat_db *db = c->db;
     if (!db->pool_words) return KMAT_OK;
-    if (c->d_pool2 && c->resolved_max_count == c->opt.max_count && c->resolved_permissive == (c->opt.permissive != 0)) return KMAT_OK;
+    if (c->d_pool2 && c->resolved_max_count == c->opt.max_count && c->resolved_permissive == (c->opt.permissive != 0) &&
+        c->resolved_rkmer == (c->opt.rkmer_mode != 0)) return KMAT_OK;
     KM_CUDA(cudaStreamSynchronize(c->stream));
     const int mul = (db->tid_bytes == 2 ? 2 : 1) * (c->opt.permissive ? 2 : 1);
     if (!c->d_pool2 || mul != c->pool2_mul) {
@@ -881,7 +886,7 @@ static int km_resolve_lists(kmat_ctx *c) {
     }
     cudaFree(R.big_queue); cudaFree(R.counters);
     KM_CUDA(cudaGetLastError());
-    c->resolved_max_count = c->opt.max_count; c->resolved_permissive = c->opt.permissive != 0;
+    c->resolved_max_count = c->opt.max_count; c->resolved_permissive = c->opt.permissive != 0; c->resolved_rkmer = c->opt.rkmer_mode != 0;
     return rc;
 }
 
@@ -890,6 +895,7 @@ extern "C" int kmat_ctx_create(const kmat_db *db, const kmat_inputs *in, const k
     kmat_opts o;
     if (opt) o = *opt; else kmat_opts_default(&o);
     kmat_ctx *c = new kmat_ctx();
+    if (o.rkmer_mode) { o.min_kmer = 0; o.min_fnd_kmer = 0; o.permissive = 0; o.want_lineage = 0; }   // rand_read_label has neither -j nor -z (and never sets gPERMISSIVE_MATCH)
     c->db = db; c->device = db->device; c->opt = o;
     int rc = kmat_build_host_ctx(*in, db->tid_bytes, db->stored_tids, c->h);
     if (rc != KMAT_OK) { delete c; return rc; }
@@ -928,6 +934,7 @@ extern "C" int kmat_ctx_create(const kmat_db *db, const kmat_inputs *in, const k
 extern "C" int kmat_ctx_set_opts(kmat_ctx *c, const kmat_opts *o) {
     if (!c || !o) return KMAT_ERR_ARG;
     c->opt = *o;
+    if (c->opt.rkmer_mode) { c->opt.min_kmer = 0; c->opt.min_fnd_kmer = 0; c->opt.permissive = 0; c->opt.want_lineage = 0; }
     KM_CUDA(cudaSetDevice(c->device));
     return km_resolve_lists(c);          // the resolved lists depend on -g and -s
 }
@@ -944,6 +951,7 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
         if (sl.ev_d2h) cudaEventDestroy(sl.ev_d2h);
     }
     km_shard_free(c->shard);
+    cudaFree(c->d_null_max); cudaFree(c->d_null_cnt); cudaFree(c->d_null_err); cudaFree(c->d_null_bases); cudaFree(c->d_null_offs);
     cudaFree(c->d_hit); cudaFree(c->d_hdr); cudaFree(c->d_out_dev);
     if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
     if (c->st_d2h) cudaStreamDestroy(c->st_d2h);
@@ -1026,6 +1034,7 @@ static int km_prepare_pass(kmat_ctx *c, const KmPass &L, cudaStream_t st, uint32
     return KMAT_OK;
 }
 
+static int km_launch_nullacc(kmat_ctx *c, const KmScoreParams &P, uint32_t r0, uint32_t n, cudaStream_t s2);   // kmat_null.cuh
 // K3 + K4 over reads [r0, r0 + n) of a pass on stream s2.  pool2 / pool2_mul override the ctx's resolved list pool
 // (DB-sharded mode: the records fetched from the owning shards for this batch).  ev_mid, if set, is recorded between
 // the two kernels.
@@ -1050,6 +1059,7 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     if (ev_mid) KM_CUDA(cudaEventRecord(ev_mid, s2));
+    if (c->opt.rkmer_mode) return km_launch_nullacc(c, P, r0, n, s2);     // rand_read_label: accumulate instead of scoring
     km_score_kernel<<<(n + KS_THREADS - 1) / KS_THREADS, KS_THREADS, 0, s2>>>(P);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
@@ -1102,6 +1112,7 @@ static int km_reserve_cands(kmat_ctx *c, uint64_t n_reads) {
 extern "C" int kmat_label_batch_device(kmat_ctx *c, const char *d_bases, const uint64_t *d_offs, uint32_t n_reads, uint64_t total_bases,
                                        uint32_t max_read_len, kmat_read_result *d_out, void *stream) {
     if (!c || !d_offs || (n_reads && !d_bases)) { kmat_set_error("kmat_label_batch_device: bad argument"); return KMAT_ERR_ARG; }
+    if (c->opt.rkmer_mode) { kmat_set_error("kmat_label_batch_device: the ctx was created with rkmer_mode (kmat_null_* only)"); return KMAT_ERR_ARG; }
     KM_CUDA(cudaSetDevice(c->device));
     if (!n_reads) return KMAT_OK;
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
@@ -1175,6 +1186,7 @@ extern "C" int kmat_label_batch(kmat_ctx *c, const char *bases, const uint64_t *
                                 kmat_pair *cands, uint64_t cands_cap, uint64_t *n_cands, kmat_pair *lineage, uint64_t lineage_cap,
                                 uint64_t *n_lineage) {
     if (!c || !offs || !out || (n_reads && !bases)) { kmat_set_error("kmat_label_batch: bad argument"); return KMAT_ERR_ARG; }
+    if (c->opt.rkmer_mode) { kmat_set_error("kmat_label_batch: the ctx was created with rkmer_mode (kmat_null_* only)"); return KMAT_ERR_ARG; }
     if (n_cands) *n_cands = 0;
     if (n_lineage) *n_lineage = 0;
     if (!n_reads) return KMAT_OK;
@@ -1278,3 +1290,4 @@ extern "C" void kmat_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 #include "kmat_shard.cuh"
 #include "kmat_gene.cuh"
+#include "kmat_null.cuh"
