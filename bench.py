@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--cpu-reads", type=int, default=200_000, help="reads in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--table-mode", default="replicated", choices=["replicated", "sharded"],
+    ap.add_argument("--table-mode", default="replicated", choices=["replicated", "sharded", "direct"],
                     help="replicated: every GPU holds the whole table (configs[1]); sharded: table partitioned by k-mer hash over "
                          "the ranks, query k-mers exchanged with an NCCL all-to-all (configs[3] layout on the configs[1] table)")
     ap.add_argument("--round-reads", type=int, default=1 << 20, help="reads per exchange round in sharded mode")
@@ -232,9 +232,20 @@ def sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, 
     barrier()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop()
+    # one more, untimed step with a CUDA event after every phase: where a round's time goes
+    lab.timing = {}
+    keep = (lab.lookups, lab.served, lab.payload_words, lab.rounds)
+    step()
+    phase_ms = {k: round(v, 2) for k, v in lab.timing.items()}
+    lab.timing = None
+    lab.lookups, lab.served, lab.payload_words, lab.rounds = keep
     res = d_out.cpu().numpy().view(api.RESULT_DTYPE)
     errs = int((res["status"] == 6).sum())
     labeled = int((res["status"] == 5).sum())
+    if errs:
+        bad = np.nonzero(res["status"] == 6)[0]
+        print(f"[rank {rank}] {errs} reads in error: err codes {np.unique(res['err'][bad], return_counts=True)}, first reads {bad[:8].tolist()}, "
+              f"valid_kmers {res['valid_kmers'][bad[:8]].tolist()}", file=sys.stderr, flush=True)
     t = torch.tensor([ms_total, 0.0], device=dev, dtype=torch.float64)
     tot = torch.tensor([lab.lookups, lab.payload_words, errs, labeled], device=dev, dtype=torch.int64)
     if world > 1:
@@ -256,7 +267,7 @@ def sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, 
                                       f"(8 B), all-to-all of hit words (4 B) + list records back ({'NCCL, torch.distributed' if world > 1 else 'single rank'})"},
             "kmer_lookups_per_s": lookups_step / (ms_step * 1e-3), "lookups_per_read": lookups_step / (world * n),
             "exchange_bytes_per_step": int(lookups_step * 12 + int(tot[1].item()) / a.steps * 4), "reads_error": int(tot[2].item()),
-            "reads_labeled": int(tot[3].item()),
+            "reads_labeled": int(tot[3].item()), "phase_ms_rank0": phase_ms,
             "roofline": {"bound": "hbm", "kernel": "km_shard_probe_kernel", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
                          "peak_source": peak_src, "note": "per-kernel split not measured in sharded mode; see the replicated line"},
             "e2e": None, "gpu_launches": int(api.lib().kmat_launch_count() - launches0), "clocks": clocks, "setup_s": setup_s,
@@ -343,12 +354,17 @@ def main():
         tbl = synth.build_table_gpu(codes, anc_sid)
         n_kmers, n_lists = tbl.n, int((~tbl.single).sum().item())
         sharded_mode = a.table_mode == "sharded"
-        db = synth.upload_table(tbl, local, shard_index=rank if sharded_mode else 0, shard_count=world if sharded_mode else 1)
+        direct_mode = a.table_mode == "direct"        # table sharded, probes go to the owner GPU's memory over NVLink (no rounds)
+        split = sharded_mode or direct_mode
+        db = synth.upload_table(tbl, local, shard_index=rank if split else 0, shard_count=world if split else 1)
         del tbl
         torch.cuda.empty_cache()
         inputs = api.Inputs(tree=paths["tree"], depth=paths["depth"], rank=paths["rank"], map16=paths["map16"], null_lst=null_lst, lmat_dir=workdir)
         # options of bin/run_rl.sh:243: -j 30 -l 0 -b 1.0 -x 0 -p, null models on
         ctx = api.Ctx(db, inputs, api.default_opts(min_kmer=30, hbias=0.0, sdiff=1.0, min_score=0.0, want_lineage=0))
+        if direct_mode and world > 1:
+            from lmat_b200 import sharded
+            sharded.attach_peers(ctx, device=dev)
         reads = synth.make_reads_gpu(20241 + rank, codes, a.reads, a.read_len)           # weak scaling: every rank its own R reads
         del codes
         torch.cuda.empty_cache()
@@ -463,16 +479,18 @@ def main():
             line = {
                 "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/f32", "data": "synthetic",
-                "config": {"workload": workload_name(a), "db_kmers": int(n_kmers), "db_lists": n_lists, "db_bytes": int(db.bytes),
+                "config": {"workload": workload_name(a).replace("C2-replicated", "C2 table, DB-sharded (direct peer reads)") if direct_mode else workload_name(a), "db_kmers": int(n_kmers), "db_lists": n_lists, "db_bytes": int(db.bytes),
                            "reads_per_gpu": n, "read_len": L, "k": 20, "options": "run_rl.sh:243 (-j 30 -l 0 -b 1 -p, null models on)",
                            "l2_policy": "inputs larger than L2 (reads 1.5 GB, table >> 126 MB); no flush needed",
-                           "parallelism": f"read-sharded x{world}, table replicated, no data-path collective"},
+                           "parallelism": (f"table sharded x{world} by kmat_shard_of (k-mer hash), {int(db.bytes)} B per GPU; every bucket gather goes to the owner "
+                                           f"GPU's memory (CUDA IPC peer mapping, NVLink reads); reads stay home, no exchange rounds, no collective")
+                           if direct_mode else f"read-sharded x{world}, table replicated, no data-path collective"},
                 "kmer_lookups_per_s": value * lookups_per_read, "lookups_per_read": lookups_per_read,
                 "hit_rate": st.hits / max(1, st.lookups), "reads_error": int(errs),
                 "kernels_ms": {"encode_probe": pm, "candidates": cm_, "score": sm_, "how": "CUDA events around each kernel of one serial pass"},
                 "pipeline_sub_batches": a.pipeline,
                 "roofline": {"bound": "hbm", "kernel": "km_encode_probe_fast_kernel<5>" if L <= 160 else ("km_encode_probe_fast_kernel<8>" if L <= 256 else "km_encode_probe_kernel"), "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": achieved / hbm_peak, "traffic": traffic_from_profile(a), "peak_source": peak_src,
+                             "frac": achieved / hbm_peak, "traffic": None if direct_mode else traffic_from_profile(a), "peak_source": peak_src,
                              "random_access_peak": gather_gbps, "frac_random_access": achieved / gather_gbps,
                              "random_access_how": "uniform random 8-byte loads, one per 32-byte sector, over 16 GiB, best of 10 (kmat_gather_bench)",
                              "algorithmic_bytes_per_lookup": st.algorithmic_bytes / max(1, st.lookups)},
@@ -490,6 +508,8 @@ def main():
                 except Exception as ex:          # the baseline must never take the GPU number down with it
                     line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)[:200]}
             print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.barrier()          # direct mode: peers read this rank's table until they are done
     finally:
         shutil.rmtree(workdir, ignore_errors=True)
         if world > 1:

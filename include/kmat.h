@@ -257,6 +257,19 @@ int kmat_null_fetch(kmat_ctx *, uint32_t *tids, float *max_frac, uint64_t *count
 int kmat_null_write(const char *path, int n_sets, const uint32_t *const *tids, const float *const *max_frac,
                     const uint64_t *const *counts, const uint32_t *n_rows);
 
+/* ---- DB-sharded mode, direct variant (SURVEY.md 8(e) mode B without exchange rounds) ----------
+ * Every rank holds one shard (kmat_db_upload / kmat_db_build_device with shard_index / shard_count) and a ctx over it.
+ * kmat_ctx_peer_export describes the rank's shard (CUDA IPC handles of its bucket array, stash and resolved list pool);
+ * the ranks exchange these blobs by any means (MPI / torch.distributed all-gather; plain memory inside one process)
+ * and each calls kmat_ctx_peer_attach with all of them, indexed by shard.  From then on kmat_label_batch and
+ * kmat_label_batch_device of that ctx label reads against the WHOLE table: the probe kernel sends every bucket gather
+ * to the owner's memory (NVLink peer reads), list records are read from the owner's pool the same way.  A rank must keep
+ * its table and ctx alive until every peer has finished (barrier before kmat_ctx_destroy / kmat_db_free).
+ * All shards must have the same geometry and the contexts the same -g / -s options (checked). */
+typedef struct { unsigned char opaque[512]; } kmat_peer_info;
+int kmat_ctx_peer_export(kmat_ctx *, kmat_peer_info *out);
+int kmat_ctx_peer_attach(kmat_ctx *, int n_shards, const kmat_peer_info *all /* [n_shards], entry s = export of shard s */);
+
 /* Page-locked host memory for the buffers of kmat_label_batch (optional; NULL when no device / out of memory). */
 void *kmat_host_alloc(size_t bytes);
 void kmat_host_free(void *);
@@ -330,6 +343,11 @@ int kmat_tally_class(const kmat_read_result *, float min_score, int32_t min_kmer
  * (8, 16 or 32) over a `span_bytes` device allocation; returns achieved gathers/s. */
 int kmat_gather_bench(int device, uint64_t span_bytes, int access_bytes, uint64_t n_gathers, int iters,
                       double *gathers_per_s, double *sector_gbps);
+
+/* The same with the gathered allocation on another GPU (`mem_device`, peer access over NVLink): the ceiling of the direct
+ * sharded mode's remote bucket reads.  access_bytes also selects load flavours (see km_gather_kernel). */
+int kmat_gather_bench_peer(int device, int mem_device, uint64_t span_bytes, int access_bytes, uint64_t n_gathers, int iters,
+                           double *gathers_per_s, double *sector_gbps);
 
 /* cudaLimitMaxL2FetchGranularity hint (32 / 64 / 128) on `device`; bytes <= 0 only queries.  Returns the
  * granularity in effect, or a negative error. */

@@ -48,9 +48,10 @@ EXPORTS = [
     "kmat_shard_of", "kmat_db_size", "kmat_db_bytes", "kmat_db_kmer_length", "kmat_db_device", "kmat_db_free",
     "kmat_lookup_batch", "kmat_encode_batch", "kmat_inputs_load", "kmat_inputs_free", "kmat_opts_default",
     "kmat_ctx_create", "kmat_ctx_set_opts", "kmat_ctx_destroy", "kmat_label_batch", "kmat_label_batch_device",
-    "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_set_pipeline", "kmat_gene_batch", "kmat_shard_encode", "kmat_shard_serve", "kmat_shard_finish", "kmat_ctx_device_results", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench",
+    "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_set_pipeline", "kmat_gene_batch", "kmat_shard_encode", "kmat_shard_serve", "kmat_shard_finish", "kmat_ctx_device_results", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench", "kmat_gather_bench_peer",
     "kmat_set_l2_fetch_granularity", "kmat_reader_open", "kmat_reader_open_mt", "kmat_reader_close", "kmat_read_batch_new", "kmat_read_batch_free",
     "kmat_reader_next", "kmat_read_batch_view", "kmat_tally_class", "kmat_host_alloc", "kmat_host_free",
+    "kmat_ctx_peer_export", "kmat_ctx_peer_attach",
     "kmat_null_reset", "kmat_null_batch", "kmat_null_random", "kmat_null_draw_reads", "kmat_null_fetch", "kmat_null_write",
 ]
 
@@ -111,6 +112,7 @@ def lib():
     L.kmat_launch_count.restype = C.c_uint64
     L.kmat_format_tail.argtypes = [vp, vp, vp, C.c_int, C.c_char_p, C.c_size_t]
     L.kmat_gather_bench.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.kmat_gather_bench_peer.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.kmat_set_l2_fetch_granularity.argtypes = [C.c_int, C.c_int]
     L.kmat_reader_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.kmat_reader_open_mt.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
@@ -124,6 +126,8 @@ def lib():
     L.kmat_host_alloc.restype = vp
     L.kmat_host_alloc.argtypes = [C.c_size_t]
     L.kmat_host_free.argtypes = [vp]
+    L.kmat_ctx_peer_export.argtypes = [vp, vp]
+    L.kmat_ctx_peer_attach.argtypes = [vp, C.c_int, vp]
     L.kmat_null_reset.argtypes = [vp]
     L.kmat_null_batch.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64]
     L.kmat_null_random.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
@@ -368,6 +372,18 @@ class Ctx:
             out.append(buf.raw[:n].decode())
         return out
 
+    # ---- DB-sharded mode, direct variant: probes go to the owner shard's memory (CUDA IPC / peer access over NVLink)
+    def peer_export(self):
+        """-> 512-byte blob describing this rank's shard (numpy uint8), to be all-gathered."""
+        blob = np.zeros(512, dtype=np.uint8)
+        _check(lib().kmat_ctx_peer_export(self.h, blob.ctypes.data))
+        return blob
+
+    def peer_attach(self, blobs):
+        """blobs: the exports of all shards, indexed by shard ([n_shards, 512] uint8)."""
+        b = np.ascontiguousarray(np.stack([np.asarray(x, dtype=np.uint8) for x in blobs]))
+        _check(lib().kmat_ctx_peer_attach(self.h, len(b), b.ctypes.data))
+
     # ---- null-model generation (rand_read_label); the ctx must have been created with rkmer_mode = 1
     def null_reset(self):
         _check(lib().kmat_null_reset(self.h))
@@ -452,6 +468,12 @@ class Ctx:
 def gather_bench(device=0, span_bytes=1 << 30, access_bytes=8, n_gathers=1 << 28, iters=5):
     g, s = C.c_double(), C.c_double()
     _check(lib().kmat_gather_bench(device, span_bytes, access_bytes, n_gathers, iters, C.byref(g), C.byref(s)))
+    return g.value, s.value
+
+
+def gather_bench_peer(device, mem_device, span_bytes=1 << 30, access_bytes=32, n_gathers=1 << 27, iters=3):
+    g, s = C.c_double(), C.c_double()
+    _check(lib().kmat_gather_bench_peer(device, mem_device, span_bytes, access_bytes, n_gathers, iters, C.byref(g), C.byref(s)))
     return g.value, s.value
 
 

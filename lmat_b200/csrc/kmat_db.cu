@@ -151,6 +151,7 @@ static int km_db_alloc_and_insert(kmat_db *db, const uint64_t *d_kmers, const ui
 
 KmDbDev km_db_dev(const kmat_db *db) {
     KmDbDev d;
+    d.peers = nullptr; d.n_peers = 0;
     d.slots = db->d_slots; d.bucket_mask = db->n_buckets - 1; d.kmer_bits = db->geom.kmer_bits; d.rem_bits = db->geom.rem_bits;
     d.kmer_len = db->kmer_len; d.tid_bytes = db->tid_bytes; d.pool = db->d_pool; d.prefix_bits = db->d_prefix_bits;
     d.prefix_shift = db->prefix_shift;
@@ -625,8 +626,10 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
 #pragma unroll
             for (int c = 0; c < NCH; c++) {
                 bk[c][0] = bk[c][1] = bk[c][2] = bk[c][3] = 0;
-                if ((first >> c) & 1)
-                    km_load_bucket(P.db.slots + ((xk[c] >> P.db.rem_bits) & P.db.bucket_mask) * KM_SLOTS_PER_BUCKET, bk[c][0], bk[c][1], bk[c][2], bk[c][3]);
+                if ((first >> c) & 1) {
+                    uint32_t owner;                                   // direct sharded mode: the gather goes to the owner's memory
+                    km_load_bucket(km_slots_of(P.db, xk[c], owner) + ((xk[c] >> P.db.rem_bits) & P.db.bucket_mask) * KM_SLOTS_PER_BUCKET, bk[c][0], bk[c][1], bk[c][2], bk[c][3]);
+                }
             }
         }
 #pragma unroll
@@ -640,7 +643,7 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
                     if (km_bucket_match(bk[c][0], bk[c][1], bk[c][2], bk[c][3], xk[c] & ((1ull << P.db.rem_bits) - 1), 0, hw) == 2) {
                         hw = km_probe_x(P.db, xk[c], extra, 1);
                         extra++;
-                    }
+                    } else if (P.db.n_peers) hw = km_tag_owner(P.db, hw, km_owner_of_x(xk[c], P.db.n_peers));
                     if (STATS) {
                         st_lookups++; st_extra += extra;
                         if (hw != KM_HIT_MISS) { st_hits++; if (hw & KM_HIT_LIST) st_lists++; }
@@ -696,9 +699,10 @@ static int km_launch_fast(const KmProbeParams &P, int ctas_per_sm, cudaStream_t 
 
 int km_launch_encode_probe(const kmat_db *db, const char *d_bases, const uint64_t *d_offs, uint32_t n_reads, uint32_t max_len,
                            uint32_t *d_hit, int2 *d_hdr, uint64_t *d_kmers, uint8_t *d_flags, unsigned long long *d_long_sets,
-                           uint32_t long_slots, int grid, KmStatsDev *d_stats, int do_probe, cudaStream_t stream, int ctas_per_sm, uint64_t *d_xq) {
+                           uint32_t long_slots, int grid, KmStatsDev *d_stats, int do_probe, cudaStream_t stream, int ctas_per_sm, uint64_t *d_xq,
+                           const KmPeer *d_peers, uint32_t n_peers) {
     KmProbeParams P;
-    P.db = km_db_dev(db); P.bases = d_bases; P.offs = d_offs; P.n_reads = n_reads; P.hit = d_hit; P.hdr = d_hdr;
+    P.db = km_db_dev(db); P.db.peers = d_peers; P.db.n_peers = d_peers ? n_peers : 0; P.bases = d_bases; P.offs = d_offs; P.n_reads = n_reads; P.hit = d_hit; P.hdr = d_hdr;
     P.out_kmers = d_kmers; P.out_flags = d_flags; P.long_sets = d_long_sets; P.long_slots = long_slots; P.stats = d_stats;
     P.do_probe = do_probe; P.xq = d_xq;
     const bool fast = !d_kmers && !d_flags && max_len <= 256 && db->kmer_len <= 24 && !getenv("KMAT_NO_FAST_PROBE");
@@ -774,19 +778,58 @@ __global__ void km_gather_kernel(const uint8_t *__restrict__ base, uint64_t n_un
         else if (MODE == 104) asm volatile("ld.global.cs.u64 %0, [%1];" : "=l"(v) : "l"(p));
         else if (MODE == 105) asm volatile("ld.global.L1::no_allocate.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(p));
         else if (MODE == 106) asm volatile("ld.global.lu.u64 %0, [%1];" : "=l"(v) : "l"(p));
+        else if (MODE == 107) { uint64_t a, b, c, d; asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p)); v = a ^ b ^ c ^ d; }
+        else if (MODE == 108) { uint64_t a, b; asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p)); v = a ^ b; }
+        else if (MODE == 109) { uint64_t a, b; asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p)); v = a ^ b; }
+        else if (MODE == 110) {
+            // one 32-byte bulk copy (TMA, non-tensor) per lane into shared memory, one mbarrier per warp
+            __shared__ __align__(32) unsigned char s_buf[256 * 32];
+            __shared__ __align__(8) unsigned long long s_bar[8];
+            const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[w]);
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_buf + threadIdx.x * 32);
+            const uint32_t iter = (uint32_t)((i - (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x)) / ((uint64_t)gridDim.x * blockDim.x));
+            if (iter == 0) { if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar)); __syncwarp(); }
+            const uint32_t act = __activemask();
+            if (lane == __ffs(act) - 1) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(32u * __popc(act)));
+            __syncwarp(act);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 32, [%2];" :: "r"(dst), "l"(p), "r"(bar) : "memory");
+            uint32_t done = 0;
+            while (!done) asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }" : "=r"(done) : "r"(bar), "r"(iter & 1) : "memory");
+            v = *(const unsigned long long *)(s_buf + threadIdx.x * 32);
+            __syncwarp(act);
+        }
         acc += v;
     }
     if (acc == 0x123456789abcdefull) *sink = acc;
 }
+static int km_gather_bench_impl(int device, int mem_device, uint64_t span_bytes, int access_bytes, uint64_t n_gathers, int iters,
+                                double *gathers_per_s, double *sector_gbps);
 extern "C" int kmat_gather_bench(int device, uint64_t span_bytes, int access_bytes, uint64_t n_gathers, int iters,
                                  double *gathers_per_s, double *sector_gbps) {
-    if (kmat_device_count() <= device) { kmat_set_error("CUDA device %d not available", device); return KMAT_ERR_NO_DEVICE; }
+    return km_gather_bench_impl(device, device, span_bytes, access_bytes, n_gathers, iters, gathers_per_s, sector_gbps);
+}
+extern "C" int kmat_gather_bench_peer(int device, int mem_device, uint64_t span_bytes, int access_bytes, uint64_t n_gathers, int iters,
+                                      double *gathers_per_s, double *sector_gbps) {
+    return km_gather_bench_impl(device, mem_device, span_bytes, access_bytes, n_gathers, iters, gathers_per_s, sector_gbps);
+}
+static int km_gather_bench_impl(int device, int mem_device, uint64_t span_bytes, int access_bytes, uint64_t n_gathers, int iters,
+                                double *gathers_per_s, double *sector_gbps) {
+    if (kmat_device_count() <= device || kmat_device_count() <= mem_device) { kmat_set_error("CUDA device %d / %d not available", device, mem_device); return KMAT_ERR_NO_DEVICE; }
     const int mode = access_bytes;
-    if (mode != 8 && mode != 16 && mode != 32 && !(mode >= 101 && mode <= 106)) return KMAT_ERR_ARG;
-    KM_CUDA(cudaSetDevice(device));
+    if (mode != 8 && mode != 16 && mode != 32 && !(mode >= 101 && mode <= 110)) return KMAT_ERR_ARG;
     uint8_t *buf; unsigned long long *sink;
-    KM_CUDA(cudaMalloc((void **)&buf, span_bytes)); KM_CUDA(cudaMalloc((void **)&sink, 8));
+    KM_CUDA(cudaSetDevice(mem_device));
+    KM_CUDA(cudaMalloc((void **)&buf, span_bytes));
     KM_CUDA(cudaMemset(buf, 1, span_bytes));
+    KM_CUDA(cudaDeviceSynchronize());
+    KM_CUDA(cudaSetDevice(device));
+    if (mem_device != device) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(mem_device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaFree(buf); kmat_set_error("cudaDeviceEnablePeerAccess(%d): %s", mem_device, cudaGetErrorString(e)); cudaGetLastError(); return KMAT_ERR_UNSUPPORTED; }
+        cudaGetLastError();
+    }
+    KM_CUDA(cudaMalloc((void **)&sink, 8));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const uint64_t n_units = span_bytes / 32;
     float best = 1e30f;
@@ -794,7 +837,7 @@ extern "C" int kmat_gather_bench(int device, uint64_t span_bytes, int access_byt
         cudaEventRecord(e0);
         const int blocks = 148 * 16, threads = 256;
 #define KM_G(M) case M: km_gather_kernel<M><<<blocks, threads>>>(buf, n_units, n_gathers, 977 * it, sink); break;
-        switch (mode) { KM_G(8) KM_G(16) KM_G(32) KM_G(101) KM_G(102) KM_G(103) KM_G(104) KM_G(105) KM_G(106) }
+        switch (mode) { KM_G(8) KM_G(16) KM_G(32) KM_G(101) KM_G(102) KM_G(103) KM_G(104) KM_G(105) KM_G(106) KM_G(107) KM_G(108) KM_G(109) KM_G(110) }
 #undef KM_G
         g_km_launches++;
         cudaEventRecord(e1); cudaEventSynchronize(e1);

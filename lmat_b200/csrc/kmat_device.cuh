@@ -14,7 +14,21 @@
 #define KM_HIT_MISS 0xFFFFFFFEu      // valid first occurrence, not in the table (first = 0, empty set)
 #define KM_HIT_LIST 0x80000000u      // bit 31: payload is a list-pool offset (4-byte words); else a stored id
 
+// DB-sharded mode, direct variant (kmat_ctx_peer_attach): where shard `owner` lives.  The pointers are device addresses
+// valid on THIS GPU: the shard's own memory, another GPU's memory mapped through CUDA IPC / peer access (the loads then
+// travel over NVLink), or simply another allocation of the same device (virtual ranks in the tests).
+struct KmPeer {
+    const uint64_t *slots;        // the owner's bucket array (same geometry on every shard)
+    const uint64_t *stash_x; const uint32_t *stash_hit;
+    const uint32_t *pool2;        // the owner ctx's resolved list pool
+    uint32_t n_stash, pad;
+};
+#define KM_PEER_SHIFT 27          // direct mode: a list hit word is LIST | owner << 27 | pool word offset (< 2^27)
+#define KM_PEER_OFFMASK 0x07FFFFFFu
+
 struct KmDbDev {
+    const KmPeer *peers;          // direct sharded mode: n_peers entries indexed by km_owner_of_x; else null
+    uint32_t n_peers;
     const uint64_t *slots;        // n_buckets * 4
     uint64_t bucket_mask;
     int kmer_bits, rem_bits, kmer_len, tid_bytes;
@@ -55,24 +69,39 @@ __device__ __forceinline__ int km_bucket_match(uint64_t s0, uint64_t s1, uint64_
 
 // Probe with the mixed key x = km_mix(kmer), starting at displacement d0: returns the hit word.  extra = number of
 // additional buckets visited (linear probing past a full bucket).
+// Direct sharded mode: the bucket array that holds mixed key x, and its owner shard (0 and the local table otherwise).
+__device__ __forceinline__ const uint64_t *km_slots_of(const KmDbDev &db, uint64_t x, uint32_t &owner) {
+    owner = 0;
+    if (!db.n_peers) return db.slots;
+    owner = km_owner_of_x(x, db.n_peers);
+    return (const uint64_t *)__ldg((const unsigned long long *)&db.peers[owner].slots);
+}
+// A hit word found in shard `owner`: list offsets are local to the owner's pool, so the owner rides along (direct mode)
+__device__ __forceinline__ uint32_t km_tag_owner(const KmDbDev &db, uint32_t hw, uint32_t owner) {
+    return (db.n_peers && hw != KM_HIT_MISS && (hw & KM_HIT_LIST)) ? hw | (owner << KM_PEER_SHIFT) : hw;
+}
 __device__ __forceinline__ uint32_t km_probe_x(const KmDbDev &db, uint64_t x, uint32_t &extra, int d0 = 0) {
     const uint64_t home = x >> db.rem_bits;
     const uint64_t rem = x & ((1ull << db.rem_bits) - 1);
     extra = 0;
+    uint32_t owner;
+    const uint64_t *slots = km_slots_of(db, x, owner);
 #pragma unroll 1
     for (int d = d0; d <= KM_MAX_DISP; d++) {
         uint64_t s0, s1, s2, s3;
-        km_load_bucket(db.slots + ((home + d) & db.bucket_mask) * KM_SLOTS_PER_BUCKET, s0, s1, s2, s3);
+        km_load_bucket(slots + ((home + d) & db.bucket_mask) * KM_SLOTS_PER_BUCKET, s0, s1, s2, s3);
         uint32_t hw;
-        if (km_bucket_match(s0, s1, s2, s3, rem, d, hw) != 2) return hw;
+        if (km_bucket_match(s0, s1, s2, s3, rem, d, hw) != 2) return km_tag_owner(db, hw, owner);
         extra++;
     }
     // every bucket of the probe window is full: the key, if present, sits in the stash
+    const uint64_t *stash_x = db.stash_x; const uint32_t *stash_hit = db.stash_hit;
     uint32_t lo = 0, hi = db.n_stash;
+    if (db.n_peers) { const KmPeer pr = db.peers[owner]; stash_x = pr.stash_x; stash_hit = pr.stash_hit; hi = pr.n_stash; }
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        const uint64_t v = db.stash_x[mid];
-        if (v == x) return db.stash_hit[mid];
+        const uint64_t v = stash_x[mid];
+        if (v == x) return km_tag_owner(db, stash_hit[mid], owner);
         if (v < x) lo = mid + 1; else hi = mid;
     }
     return KM_HIT_MISS;

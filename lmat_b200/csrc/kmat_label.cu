@@ -260,6 +260,12 @@ __device__ __forceinline__ int kb_find_or_add(KbCand &K, int &C, uint32_t v, int
 // return this lane's position mask.  All lanes of the warp call it together.
 // the two dependent loads of a position, split off so that a caller can issue them for every chunk of a read up front:
 // the hit word, and then the word it points at (stored id -> node entry for a singleton, record header for a list)
+// resolved record of a list hit word: local pool2, or (direct sharded mode) the owner's pool2 through the peer table
+__device__ __forceinline__ const uint32_t *kb_rec_of(const KmCtxDev &X, uint32_t hw) {
+    if (X.db.n_peers)
+        return (const uint32_t *)__ldg((const unsigned long long *)&X.db.peers[(hw >> KM_PEER_SHIFT) & (KM_MAX_SHARDS - 1)].pool2) + (size_t)(hw & KM_PEER_OFFMASK) * X.pool2_mul;
+    return X.pool2 + (size_t)(hw & 0x7FFFFFFFu) * X.pool2_mul;
+}
 __device__ __forceinline__ uint32_t kb_load_hit(const KmScoreParams &P, int c, uint64_t off, int np, int lane) {
     const int p = (c << 5) + lane;
     return p < np ? __ldg(P.hit + off + p) : KM_HIT_INVALID;
@@ -267,7 +273,7 @@ __device__ __forceinline__ uint32_t kb_load_hit(const KmScoreParams &P, int c, u
 __device__ __forceinline__ uint32_t kb_load_aux(const KmCtxDev &X, uint32_t hw) {
     if (hw == KM_HIT_INVALID || hw == KM_HIT_MISS) return 0;
     if (!(hw & KM_HIT_LIST)) return hw < X.n_sid ? __ldg(X.sid2nid + hw) : KMAT_NONE;
-    return __ldg(X.pool2 + (size_t)(hw & 0x7FFFFFFFu) * X.pool2_mul);
+    return __ldg(kb_rec_of(X, hw));
 }
 
 __device__ __forceinline__ unsigned long long kb_chunk(const KmScoreParams &P, KbCand &K, int &C, int c, uint32_t hw, uint32_t aux, int lane,
@@ -291,7 +297,7 @@ __device__ __forceinline__ unsigned long long kb_chunk(const KmScoreParams &P, K
                     if (permissive) b = (kb_nodeA(X, v0).meta & KM_META_DEPTH_MASK) ? 1 : 0;
                 }
             } else {
-                rec = X.pool2 + (size_t)(hw & 0x7FFFFFFFu) * X.pool2_mul;
+                rec = kb_rec_of(X, hw);
                 const uint32_t h = aux;
                 if (h == KR_ERR_BAD) { err = KMAT_ERR_BAD_TAXID; rec = nullptr; }
                 else {
@@ -820,6 +826,8 @@ struct kmat_ctx {
     // rand_read_label accumulators (kmat_null.cuh): [n_nodes * KMAT_NULL_BUCKETS] max fraction (float bits) / read counts
     uint32_t *d_null_max = nullptr, *d_null_cnt = nullptr; unsigned long long *d_null_err = nullptr;
     uint64_t null_first = 0;                 // run index of read 0 of the pass being launched
+    // direct sharded mode (kmat_ctx_peer_attach): where every shard's buckets / stash / resolved pool are mapped on this GPU
+    KmPeer *d_peers = nullptr; uint32_t n_peers = 0; std::vector<void *> ipc_mapped;
     char *d_null_bases = nullptr; uint64_t *d_null_offs = nullptr; uint64_t cap_null_bases = 0, cap_null_offs = 0;
     unsigned long long *d_long_masks = nullptr; uint32_t long_mask_cap = 0;
     unsigned long long *d_long_sets = nullptr; uint32_t long_slots = 0; int long_warps = 0;
@@ -951,6 +959,8 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
         if (sl.ev_d2h) cudaEventDestroy(sl.ev_d2h);
     }
     km_shard_free(c->shard);
+    for (void *p : c->ipc_mapped) cudaIpcCloseMemHandle(p);
+    cudaFree(c->d_peers);
     cudaFree(c->d_null_max); cudaFree(c->d_null_cnt); cudaFree(c->d_null_err); cudaFree(c->d_null_bases); cudaFree(c->d_null_offs);
     cudaFree(c->d_hit); cudaFree(c->d_hdr); cudaFree(c->d_out_dev);
     if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
@@ -967,7 +977,7 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
 
 static KmCtxDev km_ctx_dev(const kmat_ctx *c) {
     KmCtxDev X;
-    X.db = km_db_dev(c->db);
+    X.db = km_db_dev(c->db); X.db.peers = c->d_peers; X.db.n_peers = c->d_peers ? c->n_peers : 0;
     X.nodeA = c->d_nodeA; X.nodeB = c->d_nodeB; X.paths = c->d_paths; X.prune_rank = c->d_prune; X.sid2nid = c->d_sid2nid;
     X.n_sid = (uint32_t)c->h.sid2nid.size(); X.n_nodes = (uint32_t)c->h.nodeA.size(); X.nid_human = c->h.nid_human; X.nid_one = c->h.nid_one;
     X.nbins = c->h.nbins; X.n_models = c->h.n_models; X.n_classes = c->h.n_classes;
@@ -1086,7 +1096,7 @@ static int km_run_device(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
         if (r1 == r0) continue;
         const uint32_t n = r1 - r0;
         rc = km_launch_encode_probe(c->db, L.d_bases, L.d_offs + r0, n, L.max_len, hit, c->d_hdr + r0, nullptr, nullptr, c->d_long_sets, c->long_slots,
-                                    km_probe_grid(n), c->collect_stats ? c->d_stats : nullptr, 1, st, piped ? 1 : 0, nullptr);
+                                    km_probe_grid(n), c->collect_stats ? c->d_stats : nullptr, 1, st, piped ? 1 : 0, nullptr, c->d_peers, c->n_peers);
         if (rc != KMAT_OK) return rc;
         cudaStream_t s2 = st;
         if (piped) { KM_CUDA(cudaEventRecord(c->ev_sub[sb], st)); KM_CUDA(cudaStreamWaitEvent(c->st_aux, c->ev_sub[sb], 0)); s2 = c->st_aux; }
@@ -1113,6 +1123,7 @@ extern "C" int kmat_label_batch_device(kmat_ctx *c, const char *d_bases, const u
                                        uint32_t max_read_len, kmat_read_result *d_out, void *stream) {
     if (!c || !d_offs || (n_reads && !d_bases)) { kmat_set_error("kmat_label_batch_device: bad argument"); return KMAT_ERR_ARG; }
     if (c->opt.rkmer_mode) { kmat_set_error("kmat_label_batch_device: the ctx was created with rkmer_mode (kmat_null_* only)"); return KMAT_ERR_ARG; }
+    if (c->db->shard_count > 1 && !c->d_peers) { kmat_set_error("kmat_label_batch_device: the table is shard %d of %d; attach the peers (kmat_ctx_peer_attach) or use the kmat_shard_* rounds", c->db->shard_index, c->db->shard_count); return KMAT_ERR_ARG; }
     KM_CUDA(cudaSetDevice(c->device));
     if (!n_reads) return KMAT_OK;
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
@@ -1187,6 +1198,7 @@ extern "C" int kmat_label_batch(kmat_ctx *c, const char *bases, const uint64_t *
                                 uint64_t *n_lineage) {
     if (!c || !offs || !out || (n_reads && !bases)) { kmat_set_error("kmat_label_batch: bad argument"); return KMAT_ERR_ARG; }
     if (c->opt.rkmer_mode) { kmat_set_error("kmat_label_batch: the ctx was created with rkmer_mode (kmat_null_* only)"); return KMAT_ERR_ARG; }
+    if (c->db->shard_count > 1 && !c->d_peers) { kmat_set_error("kmat_label_batch: the table is shard %d of %d; attach the peers (kmat_ctx_peer_attach) or use the kmat_shard_* rounds", c->db->shard_index, c->db->shard_count); return KMAT_ERR_ARG; }
     if (n_cands) *n_cands = 0;
     if (n_lineage) *n_lineage = 0;
     if (!n_reads) return KMAT_OK;

@@ -37,12 +37,14 @@ struct kmat_db {
 };
 
 struct KmDbDev;
+struct KmPeer;
 struct KmStatsDev;
 KmDbDev km_db_dev(const kmat_db *db);
 int km_probe_grid(uint32_t n_reads);
 int km_launch_encode_probe(const kmat_db *db, const char *d_bases, const uint64_t *d_offs, uint32_t n_reads, uint32_t max_len,
                            uint32_t *d_hit, int2 *d_hdr, uint64_t *d_kmers, uint8_t *d_flags, unsigned long long *d_long_sets,
                            uint32_t long_slots, int grid, KmStatsDev *d_stats, int do_probe, cudaStream_t stream, int ctas_per_sm /* 0 = all that fit */,
-                           uint64_t *d_xq /* DB-sharded mode: mixed first-occurrence k-mers per base offset, else NULL */);
+                           uint64_t *d_xq /* DB-sharded mode: mixed first-occurrence k-mers per base offset, else NULL */,
+                           const KmPeer *d_peers = nullptr, uint32_t n_peers = 0 /* direct sharded mode: probes go to the owner's memory */);
 #define KM_PROBE_WARPS_HOST 8
 #endif

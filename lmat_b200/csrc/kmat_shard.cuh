@@ -285,3 +285,93 @@ extern "C" int kmat_ctx_device_results(kmat_ctx *c, const kmat_read_result **d_o
     }
     return KMAT_OK;
 }
+
+// =====================================================================================================================
+// Direct variant of the DB-sharded mode: no exchange rounds at all.  Every rank maps the bucket arrays, stashes and
+// resolved list pools of ALL shards into its own address space (CUDA IPC between one-process-per-GPU ranks; plain peer
+// access or the same device inside one process) and the unchanged K1+K2 / K3 kernels send each gather to the memory of
+// the shard that owns the k-mer: over NVLink 5 / NVSwitch every peer is one hop away at full bandwidth, a 32-byte bucket
+// read is one NVLink read request.  Nothing else moves; the labels are those of the replicated table by construction.
+// =====================================================================================================================
+struct KmPeerBlob {
+    uint32_t magic; int32_t pid, device, shard_index, shard_count;
+    int32_t bucket_bits, rem_bits, kmer_bits, tid_bytes, pool2_mul, rkmer, permissive, max_count;
+    uint32_t n_stash; uint64_t pool_words;
+    uint64_t p_slots, p_stash_x, p_stash_hit, p_pool2;                 // raw device pointers (valid inside the exporting process)
+    cudaIpcMemHandle_t h_slots, h_stash_x, h_stash_hit, h_pool2;       // the same allocations for other processes
+};
+static_assert(sizeof(KmPeerBlob) <= sizeof(kmat_peer_info), "kmat_peer_info too small");
+#define KM_PEER_MAGIC 0x4B4D5045u
+
+extern "C" int kmat_ctx_peer_export(kmat_ctx *c, kmat_peer_info *out) {
+    if (!c || !out) { kmat_set_error("kmat_ctx_peer_export: bad argument"); return KMAT_ERR_ARG; }
+    KM_CUDA(cudaSetDevice(c->device));
+    KM_CUDA(cudaStreamSynchronize(c->stream));
+    memset(out, 0, sizeof *out);
+    KmPeerBlob b;
+    memset(&b, 0, sizeof b);
+    const kmat_db *db = c->db;
+    b.magic = KM_PEER_MAGIC; b.pid = (int32_t)getpid(); b.device = c->device; b.shard_index = db->shard_index; b.shard_count = db->shard_count;
+    b.bucket_bits = db->geom.bucket_bits; b.rem_bits = db->geom.rem_bits; b.kmer_bits = db->geom.kmer_bits; b.tid_bytes = db->tid_bytes;
+    b.pool2_mul = c->pool2_mul; b.rkmer = c->opt.rkmer_mode != 0; b.permissive = c->opt.permissive != 0; b.max_count = c->opt.max_count;
+    b.n_stash = db->n_stash; b.pool_words = db->pool_words;
+    b.p_slots = (uint64_t)db->d_slots; b.p_stash_x = (uint64_t)db->d_stash_x; b.p_stash_hit = (uint64_t)db->d_stash_hit; b.p_pool2 = (uint64_t)c->d_pool2;
+    KM_CUDA(cudaIpcGetMemHandle(&b.h_slots, db->d_slots));
+    if (db->n_stash) { KM_CUDA(cudaIpcGetMemHandle(&b.h_stash_x, db->d_stash_x)); KM_CUDA(cudaIpcGetMemHandle(&b.h_stash_hit, db->d_stash_hit)); }
+    if (c->d_pool2) KM_CUDA(cudaIpcGetMemHandle(&b.h_pool2, c->d_pool2));
+    memcpy(out, &b, sizeof b);
+    return KMAT_OK;
+}
+
+extern "C" int kmat_ctx_peer_attach(kmat_ctx *c, int n_shards, const kmat_peer_info *all) {
+    if (!c || !all || n_shards < 1 || n_shards > KM_MAX_SHARDS) { kmat_set_error("kmat_ctx_peer_attach: bad argument"); return KMAT_ERR_ARG; }
+    if (c->d_peers) { kmat_set_error("kmat_ctx_peer_attach: peers already attached"); return KMAT_ERR_ARG; }
+    const kmat_db *db = c->db;
+    if (db->shard_count != n_shards) { kmat_set_error("kmat_ctx_peer_attach: the ctx's table is shard %d of %d, not of %d", db->shard_index, db->shard_count, n_shards); return KMAT_ERR_ARG; }
+    KM_CUDA(cudaSetDevice(c->device));
+    std::vector<KmPeer> peers((size_t)n_shards);
+    const int me = (int)getpid();
+    for (int s = 0; s < n_shards; s++) {
+        KmPeerBlob b;
+        memcpy(&b, &all[s], sizeof b);
+        if (b.magic != KM_PEER_MAGIC || b.shard_index != s || b.shard_count != n_shards) { kmat_set_error("kmat_ctx_peer_attach: entry %d is not the export of shard %d of %d", s, s, n_shards); return KMAT_ERR_ARG; }
+        if (b.bucket_bits != db->geom.bucket_bits || b.rem_bits != db->geom.rem_bits || b.kmer_bits != db->geom.kmer_bits || b.tid_bytes != db->tid_bytes) {
+            kmat_set_error("kmat_ctx_peer_attach: shard %d has a different table geometry (2^%d buckets, here 2^%d)", s, b.bucket_bits, db->geom.bucket_bits); return KMAT_ERR_UNSUPPORTED; }
+        if (b.pool2_mul != c->pool2_mul || b.rkmer != (c->opt.rkmer_mode != 0) || b.permissive != (c->opt.permissive != 0) || b.max_count != c->opt.max_count) {
+            kmat_set_error("kmat_ctx_peer_attach: shard %d's context was created with different options (-g / -s / rkmer)", s); return KMAT_ERR_ARG; }
+        if (b.pool_words > (1ull << KM_PEER_SHIFT)) { kmat_set_error("kmat_ctx_peer_attach: shard %d's list pool (%llu words) exceeds the 2^%d-word offset range of direct mode", s, (unsigned long long)b.pool_words, KM_PEER_SHIFT); return KMAT_ERR_UNSUPPORTED; }
+        KmPeer &p = peers[(size_t)s];
+        p.n_stash = b.n_stash; p.pad = 0;
+        if (s == db->shard_index) {
+            p.slots = db->d_slots; p.stash_x = db->d_stash_x; p.stash_hit = db->d_stash_hit; p.pool2 = c->d_pool2;
+        } else if (b.pid == me) {
+            // same process: the exporter's pointers are ours too; another device needs peer access switched on
+            if (b.device != c->device) {
+                int can = 0;
+                KM_CUDA(cudaDeviceCanAccessPeer(&can, c->device, b.device));
+                if (!can) { kmat_set_error("kmat_ctx_peer_attach: device %d cannot access device %d", c->device, b.device); return KMAT_ERR_UNSUPPORTED; }
+                const cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { kmat_set_error("cudaDeviceEnablePeerAccess(%d): %s", b.device, cudaGetErrorString(e)); cudaGetLastError(); return KMAT_ERR_CUDA; }
+                cudaGetLastError();
+            }
+            p.slots = (const uint64_t *)b.p_slots; p.stash_x = (const uint64_t *)b.p_stash_x; p.stash_hit = (const uint32_t *)b.p_stash_hit; p.pool2 = (const uint32_t *)b.p_pool2;
+        } else {
+            auto open = [&](const cudaIpcMemHandle_t &h, const void **dst) -> int {
+                void *q = nullptr;
+                KM_CUDA(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+                c->ipc_mapped.push_back(q);
+                *dst = q;
+                return KMAT_OK;
+            };
+            int rc;
+            if ((rc = open(b.h_slots, (const void **)&p.slots)) != KMAT_OK) return rc;
+            p.stash_x = nullptr; p.stash_hit = nullptr; p.pool2 = nullptr;
+            if (b.n_stash) { if ((rc = open(b.h_stash_x, (const void **)&p.stash_x)) != KMAT_OK) return rc; if ((rc = open(b.h_stash_hit, (const void **)&p.stash_hit)) != KMAT_OK) return rc; }
+            if (b.p_pool2) { if ((rc = open(b.h_pool2, (const void **)&p.pool2)) != KMAT_OK) return rc; }
+        }
+    }
+    KM_CUDA(cudaMalloc((void **)&c->d_peers, peers.size() * sizeof(KmPeer)));
+    KM_CUDA(cudaMemcpy(c->d_peers, peers.data(), peers.size() * sizeof(KmPeer), cudaMemcpyHostToDevice));
+    c->n_peers = (uint32_t)n_shards;
+    return KMAT_OK;
+}

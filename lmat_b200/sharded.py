@@ -159,6 +159,8 @@ class ShardedLabeler:
         self.served = 0             # queries this rank answered
         self.payload_words = 0
         self.rounds = 0
+        self.timing = None          # set to {} to collect per-phase device time (ms, summed over rounds)
+        self._marks = []
 
     def plan(self, offs_host):
         """Cut reads [0, n) into rounds bounded by round_reads and round_bases; offs_host = n+1 absolute offsets."""
@@ -193,20 +195,48 @@ class ShardedLabeler:
                 on_round(r0, r1)
             i += 1
             self.rounds += 1
+        self._collect_timing()
+
+    def _mark(self, name):
+        """Phase timing (opt-in: self.timing = {} before run()): a CUDA event on the current stream after each phase."""
+        if self.timing is None:
+            return
+        import torch
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self._marks.append((name, e))
+
+    def _collect_timing(self):
+        if self.timing is None or not self._marks:
+            return
+        import torch
+        torch.cuda.synchronize()
+        prev = None
+        for name, e in self._marks:
+            if prev is not None and name != "start":
+                self.timing[name] = self.timing.get(name, 0.0) + prev.elapsed_time(e)
+            prev = e
+        self._marks = []
 
     def _round(self, args):
         out_ptr = args[-1]
+        self._mark("start")
         send_q, send_counts = self.ph.encode(*args[:-1])
+        self._mark("encode")
         self.lookups += int(np.sum(send_counts))
         recv_counts = self.ex.counts(send_counts)                          # how many queries each source sends me
         recv_q = self.ex.all_to_all(send_q, send_counts, recv_counts)
+        self._mark("exchange_queries")
         reply, payload, pay_counts = self.ph.serve(recv_q, recv_counts)    # pay_counts[s]: list words for source s
+        self._mark("serve")
         self.served += int(np.sum(recv_counts))
         self.payload_words += int(np.sum(pay_counts))
         my_pay_counts = self.ex.counts(pay_counts)                         # list words each owner sends me
         my_reply = self.ex.all_to_all(reply, recv_counts, send_counts)     # hit words, in the order of send_q
         my_payload = self.ex.all_to_all(payload, pay_counts, my_pay_counts)
+        self._mark("exchange_replies")
         self.ph.finish(my_reply, my_payload, my_pay_counts, out_ptr)
+        self._mark("finish")
 
 
 def label_sequences(ctx, exchange, device, seqs, n_shards, round_reads=1 << 20):
@@ -242,3 +272,26 @@ def label_sequences(ctx, exchange, device, seqs, n_shards, round_reads=1 << 20):
     res = np.concatenate(res_parts) if res_parts else np.zeros(0, dtype=api.RESULT_DTYPE)
     cands = np.concatenate(cand_parts) if cand_parts else np.zeros(0, dtype=api.PAIR_DTYPE)
     return res, cands, lab
+
+
+def attach_peers(ctx, group=None, device=None):
+    """Direct variant of the DB-sharded mode for one-process-per-GPU ranks: all-gather the shard descriptions
+    (kmat_ctx_peer_export) over torch.distributed and map every peer's table into this rank (kmat_ctx_peer_attach).
+    Afterwards ctx.label / ctx.label_device work against the whole table with no exchange rounds."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    mine = torch.from_numpy(ctx.peer_export())
+    if device is not None:
+        mine = mine.to(device)
+    allb = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allb, mine, group=group)
+    ctx.peer_attach([b.cpu().numpy() for b in allb])
+    dist.barrier(group=group)
+
+
+def attach_peers_local(ctxs):
+    """The same inside one process (several GPUs driven by one host, or virtual ranks on one GPU in the tests)."""
+    blobs = [c.peer_export() for c in ctxs]
+    for c in ctxs:
+        c.peer_attach(blobs)

@@ -36,8 +36,7 @@ def run_ranks(world, fn):
     return out
 
 
-@pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("opts", ["run_rl", "permissive", "prune3"])
+@pytest.mark.parametrize("world,opts", [(2, "run_rl"), (2, "permissive"), (2, "prune3"), (3, "run_rl"), (3, "permissive"), (3, "prune3"), (8, "run_rl")])
 def test_sharded_labels_equal_replicated(golden_lists, world, opts):
     import torch
     g = golden_lists
@@ -88,3 +87,32 @@ def test_sharded_single_rank_is_a_plain_pass(golden_small):
     assert ctx.tails(rr, cc, np.zeros(0, dtype=api.PAIR_DTYPE), prn_all=True) == want
     mine = op.assemble_lines(hdrs, seqs, ctx.tails(rr, cc, np.zeros(0, dtype=api.PAIR_DTYPE), prn_all=True))
     assert mine == g.golden_out("run_rl")
+
+
+@pytest.mark.parametrize("world,opts", [(2, "run_rl"), (3, "permissive"), (3, "prune3"), (8, "run_rl")])
+def test_direct_sharded_labels_equal_replicated(golden_lists, world, opts, monkeypatch):
+    """Direct variant: every virtual rank maps all shards (same process, same device: plain pointers) and labels its reads
+    with the ordinary kmat_label_batch; the probe kernel sends each gather to the owner shard's arrays."""
+    monkeypatch.setenv("KMAT_TEST_TIGHT_TABLE", "1")      # nearly full shards: displaced keys and the per-shard stash are exercised too
+    g = golden_lists
+    t = api.Table.from_arrays(g.kmers, g.offs, g.ids, g.kmer_len, g.tid_bytes)
+    shards = [api.Db.upload(t, 0, r, world) for r in range(world)]
+    monkeypatch.delenv("KMAT_TEST_TIGHT_TABLE")
+    full = api.Db.upload(t)
+    hdrs, seqs = op.read_fasta_like_reference(g.paths["reads"])
+    seqs = seqs + ["", "ACGT", "N" * 40, seqs[0][:25], seqs[1] * 3, seqs[2] * 9]        # every K1 / K3 variant
+    ref_ctx = make_ctx(g, full, opts)
+    res, cands, lin = ref_ctx.label(seqs)
+    want = ref_ctx.tails(res, cands, lin, prn_all=True)
+    ctxs = [make_ctx(g, shards[r], opts) for r in range(world)]
+    with pytest.raises(api.KmatError):                    # a shard alone does not answer for the whole table
+        ctxs[0].label(seqs[:3])
+    sharded.attach_peers_local(ctxs)
+    for r in range(world):
+        mine = seqs[r::world]
+        rr, cc, ll = ctxs[r].label(mine)
+        assert ctxs[r].tails(rr, cc, ll, prn_all=True) == want[r::world], r
+    # mismatched options are refused
+    other = make_ctx(g, shards[0], "prune3" if opts != "prune3" else "run_rl")
+    with pytest.raises(api.KmatError):
+        other.peer_attach([c.peer_export() for c in ctxs])

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Multi-GPU pass on one box: the replicated (mode A) and DB-sharded (mode B) bench lines at N GPUs.  usage: gpu_scale.sh <tag> <N>
+# Multi-GPU pass on one box: the replicated (mode A) and DB-sharded (mode B) bench lines at N GPUs.  usage: gpu_scale.sh <tag> <N> ["modes"]
 set -u
 mkdir -p gpurun_out
 TAG=${1:-s}; N=${2:-2}
@@ -10,5 +10,7 @@ run() { # name, extra args
       bench.py --gpus $N --steps 5 --warmup 3 --no-cpu-baseline $2 > gpurun_out/${TAG}_$1.json 2> gpurun_out/${TAG}_$1.err
   echo "$1 rc=$?"; tail -c 1500 gpurun_out/${TAG}_$1.json; tail -3 gpurun_out/${TAG}_$1.err
 }
-run replicated ""
-run sharded "--table-mode sharded"
+MODES=${3:-"replicated sharded direct"}
+for m in $MODES; do
+  case $m in replicated) run replicated "";; *) run $m "--table-mode $m";; esac
+done
