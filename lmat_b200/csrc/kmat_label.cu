@@ -260,10 +260,8 @@ __device__ __forceinline__ int kb_find_or_add(KbCand &K, int &C, uint32_t v, int
 // return this lane's position mask.  All lanes of the warp call it together.
 // the two dependent loads of a position, split off so that a caller can issue them for every chunk of a read up front:
 // the hit word, and then the word it points at (stored id -> node entry for a singleton, record header for a list)
-// resolved record of a list hit word: local pool2, or (direct sharded mode) the owner's pool2 through the peer table
+// resolved record of a list hit word
 __device__ __forceinline__ const uint32_t *kb_rec_of(const KmCtxDev &X, uint32_t hw) {
-    if (X.db.n_peers)
-        return (const uint32_t *)__ldg((const unsigned long long *)&X.db.peers[(hw >> KM_PEER_SHIFT) & (KM_MAX_SHARDS - 1)].pool2) + (size_t)(hw & KM_PEER_OFFMASK) * X.pool2_mul;
     return X.pool2 + (size_t)(hw & 0x7FFFFFFFu) * X.pool2_mul;
 }
 __device__ __forceinline__ uint32_t kb_load_hit(const KmScoreParams &P, int c, uint64_t off, int np, int lane) {
@@ -828,6 +826,9 @@ struct kmat_ctx {
     uint64_t null_first = 0;                 // run index of read 0 of the pass being launched
     // direct sharded mode (kmat_ctx_peer_attach): where every shard's buckets / stash / resolved pool are mapped on this GPU
     KmPeer *d_peers = nullptr; uint32_t n_peers = 0; std::vector<void *> ipc_mapped;
+    uint32_t *d_peer_recs = nullptr; uint64_t cap_peer_recs = 0;      // list records of the pass copied from their owners (km_peer_fetch_kernel)
+    unsigned long long *d_peer_cur = nullptr;                         // [0] words used (per pass), [1] list hits dropped for lack of room (monotonic)
+    unsigned long long peer_dropped_seen = 0; int peer_grow = 1;
     char *d_null_bases = nullptr; uint64_t *d_null_offs = nullptr; uint64_t cap_null_bases = 0, cap_null_offs = 0;
     unsigned long long *d_long_masks = nullptr; uint32_t long_mask_cap = 0;
     unsigned long long *d_long_sets = nullptr; uint32_t long_slots = 0; int long_warps = 0;
@@ -859,7 +860,7 @@ static int km_resolve_lists(kmat_ctx *c) {
     const int mul = (db->tid_bytes == 2 ? 2 : 1) * (c->opt.permissive ? 2 : 1);
     if (!c->d_pool2 || mul != c->pool2_mul) {
         cudaFree(c->d_pool2); c->d_pool2 = nullptr;
-        KM_CUDA(cudaMalloc((void **)&c->d_pool2, ((size_t)db->pool_words * mul + 8) * 4));
+        KM_CUDA(cudaMalloc((void **)&c->d_pool2, ((size_t)db->pool_words * mul + 32) * 4));      // + padding: the direct-mode fetch reads two whole sectors from a record's start
         c->pool2_mul = mul;
     }
     KmResolveParams R;
@@ -960,7 +961,7 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
     }
     km_shard_free(c->shard);
     for (void *p : c->ipc_mapped) cudaIpcCloseMemHandle(p);
-    cudaFree(c->d_peers);
+    cudaFree(c->d_peers); cudaFree(c->d_peer_recs); cudaFree(c->d_peer_cur);
     cudaFree(c->d_null_max); cudaFree(c->d_null_cnt); cudaFree(c->d_null_err); cudaFree(c->d_null_bases); cudaFree(c->d_null_offs);
     cudaFree(c->d_hit); cudaFree(c->d_hdr); cudaFree(c->d_out_dev);
     if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
@@ -977,7 +978,7 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
 
 static KmCtxDev km_ctx_dev(const kmat_ctx *c) {
     KmCtxDev X;
-    X.db = km_db_dev(c->db); X.db.peers = c->d_peers; X.db.n_peers = c->d_peers ? c->n_peers : 0;
+    X.db = km_db_dev(c->db);           // peers stay out of K3 / K4: direct mode copies the remote list records first (km_peer_fetch_kernel)
     X.nodeA = c->d_nodeA; X.nodeB = c->d_nodeB; X.paths = c->d_paths; X.prune_rank = c->d_prune; X.sid2nid = c->d_sid2nid;
     X.n_sid = (uint32_t)c->h.sid2nid.size(); X.n_nodes = (uint32_t)c->h.nodeA.size(); X.nid_human = c->h.nid_human; X.nid_one = c->h.nid_one;
     X.nbins = c->h.nbins; X.n_models = c->h.n_models; X.n_classes = c->h.n_classes;
@@ -1070,12 +1071,20 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
     KM_CUDA(cudaGetLastError());
     if (ev_mid) KM_CUDA(cudaEventRecord(ev_mid, s2));
     if (c->opt.rkmer_mode) return km_launch_nullacc(c, P, r0, n, s2);     // rand_read_label: accumulate instead of scoring
-    km_score_kernel<<<(n + KS_THREADS - 1) / KS_THREADS, KS_THREADS, 0, s2>>>(P);
+    // KMAT_SCORE_SMEM (experiment knob): dummy dynamic shared memory per CTA, to cap the resident CTAs of the scoring
+    // kernel -- its per-thread local arrays then fit the L1 instead of spilling through L2 to DRAM
+    static const int score_smem = [] {
+        const char *e = getenv("KMAT_SCORE_SMEM"); const int v = e ? atoi(e) : 0;
+        if (v > 48 * 1024) cudaFuncSetAttribute(km_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+        return v > 0 ? v : 0; }();
+    km_score_kernel<<<(n + KS_THREADS - 1) / KS_THREADS, KS_THREADS, score_smem, s2>>>(P);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     return KMAT_OK;
 }
 
+static int km_peer_prepare(kmat_ctx *c, const KmPass &L, cudaStream_t st);      // kmat_shard.cuh
+static int km_peer_fetch(kmat_ctx *c, const KmPass &L, cudaStream_t st);
 static int km_run_device(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
     int rc, variant;
     uint32_t *hit;
@@ -1086,7 +1095,8 @@ static int km_run_device(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
     // every SM, on st_aux.
     int S = c->pipeline;
     if (S < 0) S = (variant == 0 && L.n_reads >= (1u << 19)) ? 8 : 1;
-    if (variant != 0 || S < 1) S = 1;
+    if (variant != 0 || S < 1 || c->d_peers) S = 1;
+    if (c->d_peers && (rc = km_peer_prepare(c, L, st)) != KMAT_OK) return rc;
     if (S > 16) S = 16;
     const bool piped = S > 1;
     KM_CUDA(cudaEventRecord(c->ev[0], st));
@@ -1101,6 +1111,14 @@ static int km_run_device(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
         cudaStream_t s2 = st;
         if (piped) { KM_CUDA(cudaEventRecord(c->ev_sub[sb], st)); KM_CUDA(cudaStreamWaitEvent(c->st_aux, c->ev_sub[sb], 0)); s2 = c->st_aux; }
         else KM_CUDA(cudaEventRecord(c->ev[1], st));
+        if (c->d_peers) {
+            // direct sharded mode: the list records the hits point at live in their owners' pools; copy them next to the
+            // batch (many remote reads in flight) so that K3 only touches local memory
+            if ((rc = km_peer_fetch(c, L, st)) != KMAT_OK) return rc;
+            KM_CUDA(cudaEventRecord(c->ev[1], st));
+            if ((rc = km_launch_cand_score(c, L, r0, n, hit, variant, 0, s2, c->d_peer_recs, 1, c->ev[3])) != KMAT_OK) return rc;
+            continue;
+        }
         if ((rc = km_launch_cand_score(c, L, r0, n, hit, variant, piped ? 2 : 0, s2, nullptr, 0, piped ? nullptr : c->ev[3])) != KMAT_OK) return rc;
     }
     if (piped) {
@@ -1161,11 +1179,24 @@ extern "C" int kmat_ctx_set_stats(kmat_ctx *c, int enable) {
     c->collect_stats = enable ? 1 : 0;
     return KMAT_OK;
 }
+// direct sharded mode: list hits the record buffer had no room for were turned into misses (never into garbage); report
+// that once and size the buffer larger for the next pass
+static int km_peer_check(kmat_ctx *c) {
+    if (!c->d_peers || !c->d_peer_cur) return KMAT_OK;
+    unsigned long long cur[2] = {0, 0};
+    KM_CUDA(cudaMemcpy(cur, c->d_peer_cur, 16, cudaMemcpyDeviceToHost));
+    if (cur[1] == c->peer_dropped_seen) return KMAT_OK;
+    const unsigned long long d = cur[1] - c->peer_dropped_seen;
+    c->peer_dropped_seen = cur[1];
+    c->peer_grow *= 2;
+    kmat_set_error("direct sharded mode: the list-record buffer was too small for %llu list hits of the last pass; it is doubled now, run the batch again", d);
+    return KMAT_ERR_OVERFLOW;
+}
 extern "C" int kmat_ctx_sync(kmat_ctx *c) {
     if (!c) return KMAT_ERR_ARG;
     KM_CUDA(cudaSetDevice(c->device));
     KM_CUDA(cudaStreamSynchronize(c->stream));
-    return KMAT_OK;
+    return km_peer_check(c);
 }
 
 static int km_fetch_stats(kmat_ctx *c, cudaStream_t st) {
@@ -1277,6 +1308,11 @@ extern "C" int kmat_label_batch(kmat_ctx *c, const char *bases, const uint64_t *
         bool again = false;
         if (total_c > c->cap_cands) { KM_CUDA(cudaStreamSynchronize(c->stream)); if ((rc = km_grow_cands(c, total_c)) != KMAT_OK) return rc; again = true; }
         if (c->opt.want_lineage && total_l > c->cap_lin) { KM_CUDA(cudaStreamSynchronize(c->stream)); if ((rc = km_grow(&c->d_lin, &c->cap_lin, total_l)) != KMAT_OK) return rc; again = true; }
+        if (c->d_peers) {                        // direct sharded mode: list-record buffer too small -> doubled by km_peer_check, re-run
+            KM_CUDA(cudaStreamSynchronize(c->stream));
+            const int prc = km_peer_check(c);
+            if (prc == KMAT_ERR_OVERFLOW && attempt < 2) again = true; else if (prc != KMAT_OK) return prc;
+        }
         if (again) continue;                     // candidate buffer was too small: re-run with the exact size
         if (n_cands) *n_cands = total_c;
         if (n_lineage) *n_lineage = c->opt.want_lineage ? total_l : 0;

@@ -62,11 +62,23 @@ __device__ __forceinline__ int km_seg_of(const KmShardSeg &g, int n, unsigned lo
 // ---- home: count and scatter the first-occurrence k-mers by owner -------------------------------------------------
 __global__ void __launch_bounds__(256) km_shard_count_kernel(const uint32_t *__restrict__ hit, const uint64_t *__restrict__ xq, uint64_t n_pos,
                                                              uint32_t n_shards, unsigned long long *counts) {
+    // per-lane private counter of owner `lane` (n_shards <= 16 < 32), fed by one ballot per owner: no contended atomics
     __shared__ unsigned int hist[KM_MAX_SHARDS];
     if (threadIdx.x < KM_MAX_SHARDS) hist[threadIdx.x] = 0;
     __syncthreads();
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_pos; i += (uint64_t)gridDim.x * blockDim.x)
-        if (hit[i] == KM_HIT_MISS) atomicAdd(&hist[km_owner_of_x(xq[i], n_shards)], 1u);
+    const int lane = threadIdx.x & 31;
+    unsigned int mine = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31); i0 < n_pos; i0 += stride) {       // warp-uniform bounds
+        const uint64_t i = i0 + lane;
+        const bool m = i < n_pos && hit[i] == KM_HIT_MISS;
+        const uint32_t owner = m ? km_owner_of_x(xq[i], n_shards) : 0xFFFFFFFFu;
+        for (uint32_t o = 0; o < n_shards; o++) {
+            const uint32_t b = __ballot_sync(KM_FULL, owner == o);
+            if ((uint32_t)lane == o) mine += __popc(b);
+        }
+    }
+    if ((uint32_t)lane < n_shards && mine) atomicAdd(&hist[lane], mine);
     __syncthreads();
     if (threadIdx.x < n_shards && hist[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
 }
@@ -373,5 +385,78 @@ extern "C" int kmat_ctx_peer_attach(kmat_ctx *c, int n_shards, const kmat_peer_i
     KM_CUDA(cudaMalloc((void **)&c->d_peers, peers.size() * sizeof(KmPeer)));
     KM_CUDA(cudaMemcpy(c->d_peers, peers.data(), peers.size() * sizeof(KmPeer), cudaMemcpyHostToDevice));
     c->n_peers = (uint32_t)n_shards;
+    return KMAT_OK;
+}
+
+
+// ---- direct mode: bring the list records of a pass home ---------------------------------------------------------------
+// After K1+K2 a list hit word is LIST | owner << 27 | offset into the OWNER's resolved pool.  One thread per hit word
+// reads the first two 32-byte sectors of the record from the owner's memory (two NVLink reads in flight per list hit,
+// thousands per SM), appends the record to the pass's local buffer and rewrites the hit word to LIST | local offset
+// (pool2_mul = 1, exactly what K3 gets in the exchange variant).
+struct KmFetchParams {
+    uint32_t *hit; uint64_t n_pos; const KmPeer *peers; int mul, permissive;
+    uint32_t *recs; unsigned long long *cur; unsigned long long cap;
+};
+__global__ void __launch_bounds__(256) km_peer_fetch_kernel(KmFetchParams F) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31); i0 < F.n_pos; i0 += stride) {
+        const uint64_t i = i0 + lane;
+        const uint32_t hw = i < F.n_pos ? F.hit[i] : KM_HIT_INVALID;
+        const bool is_list = hw != KM_HIT_INVALID && hw != KM_HIT_MISS && (hw & KM_HIT_LIST);
+        if (!__any_sync(KM_FULL, is_list)) continue;
+        uint32_t S[16];
+        const uint32_t *rec = nullptr;
+        uint32_t w0 = 0, len = 0;
+        if (is_list) {
+            const KmPeer pr = F.peers[(hw >> KM_PEER_SHIFT) & (KM_MAX_SHARDS - 1)];
+            rec = pr.pool2 + (size_t)(hw & KM_PEER_OFFMASK) * F.mul;
+            const uint64_t *a0 = (const uint64_t *)((uintptr_t)rec & ~(uintptr_t)31);
+            w0 = (uint32_t)(((uintptr_t)rec & 31) >> 2);
+            uint64_t q[8];
+            km_load_bucket(a0, q[0], q[1], q[2], q[3]);
+            km_load_bucket(a0 + 4, q[4], q[5], q[6], q[7]);
+#pragma unroll
+            for (int j = 0; j < 8; j++) { S[2 * j] = (uint32_t)q[j]; S[2 * j + 1] = (uint32_t)(q[j] >> 32); }
+            const uint32_t h = S[w0];
+            if (h == KR_ERR_BAD) len = 1;                               // the candidate kernel reports the bad stored id
+            else len = F.permissive ? 2 + (h & 0xFFFFu) + S[w0 + 1] : 1 + (h & 0xFFFFu);
+        }
+        // warp-aggregated allocation in the local record buffer
+        uint32_t incl = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(KM_FULL, incl, d); if (lane >= d) incl += t; }
+        const uint32_t total = __shfl_sync(KM_FULL, incl, 31);
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(F.cur, (unsigned long long)total);
+        base = ((unsigned long long)__shfl_sync(KM_FULL, (uint32_t)(base >> 32), 0) << 32) | __shfl_sync(KM_FULL, (uint32_t)base, 0);
+        if (!is_list) continue;
+        const unsigned long long dst = base + (incl - len);
+        if (dst + len > F.cap) { atomicAdd(F.cur + 1, 1ull); F.hit[i] = KM_HIT_MISS; continue; }
+        for (uint32_t w = 0; w < len; w++) F.recs[dst + w] = w0 + w < 16 ? S[w0 + w] : rec[w];
+        F.hit[i] = KM_HIT_LIST | (uint32_t)dst;
+    }
+}
+
+static int km_peer_prepare(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
+    if (!c->d_peer_cur) { KM_CUDA(cudaMalloc((void **)&c->d_peer_cur, 16)); KM_CUDA(cudaMemsetAsync(c->d_peer_cur, 0, 16, st)); }
+    // room for one short record at every other k-mer position (C2: ~5 list hits of ~6 words per 131 positions)
+    uint64_t want = std::max<uint64_t>(1u << 20, L.total_bases / 2 * (uint64_t)c->peer_grow);
+    if (const char *e = getenv("KMAT_TEST_PEER_RECS")) want = (uint64_t)atoll(e) * (uint64_t)c->peer_grow;      // tests: force the overflow path
+    if (want >= (1ull << 31)) want = (1ull << 31) - 1;
+    if (want > c->cap_peer_recs) { KM_CUDA(cudaStreamSynchronize(st)); int rc = km_grow(&c->d_peer_recs, &c->cap_peer_recs, want); if (rc != KMAT_OK) return rc; }
+    KM_CUDA(cudaMemsetAsync(c->d_peer_cur, 0, 8, st));               // words used; the dropped counter is monotonic
+    return KMAT_OK;
+}
+static int km_peer_fetch(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
+    KmFetchParams F;
+    F.hit = c->d_hit; F.n_pos = L.total_bases; F.peers = c->d_peers; F.mul = c->pool2_mul; F.permissive = c->opt.permissive != 0;
+    F.recs = c->d_peer_recs; F.cur = c->d_peer_cur; F.cap = std::min<uint64_t>(c->cap_peer_recs, (1ull << 31) - 1);
+    if (const char *e = getenv("KMAT_TEST_PEER_RECS")) F.cap = std::min<uint64_t>(F.cap, (uint64_t)atoll(e) * (uint64_t)c->peer_grow);
+    const int grid = (int)std::min<uint64_t>((L.total_bases + 255) / 256, (uint64_t)c->sms * 8);
+    km_peer_fetch_kernel<<<std::max(1, grid), 256, 0, st>>>(F);
+    g_km_launches++;
+    KM_CUDA(cudaGetLastError());
     return KMAT_OK;
 }

@@ -116,3 +116,30 @@ def test_direct_sharded_labels_equal_replicated(golden_lists, world, opts, monke
     other = make_ctx(g, shards[0], "prune3" if opts != "prune3" else "run_rl")
     with pytest.raises(api.KmatError):
         other.peer_attach([c.peer_export() for c in ctxs])
+
+
+def test_direct_sharded_record_buffer_overflow_is_reported_and_recovers(golden_lists, monkeypatch):
+    """The local list-record buffer of the direct variant: hits it has no room for are dropped AND reported
+    (KMAT_ERR_OVERFLOW after the internal retries), never mislabeled; the buffer doubles until the batch fits."""
+    g = golden_lists
+    t = api.Table.from_arrays(g.kmers, g.offs, g.ids, g.kmer_len, g.tid_bytes)
+    world = 2
+    shards = [api.Db.upload(t, 0, r, world) for r in range(world)]
+    full = api.Db.upload(t)
+    hdrs, seqs = op.read_fasta_like_reference(g.paths["reads"])
+    ref_ctx = make_ctx(g, full, "run_rl")
+    res, cands, lin = ref_ctx.label(seqs)
+    want = ref_ctx.tails(res, cands, lin, prn_all=True)
+    ctxs = [make_ctx(g, shards[r], "run_rl") for r in range(world)]
+    sharded.attach_peers_local(ctxs)
+    monkeypatch.setenv("KMAT_TEST_PEER_RECS", "16")
+    import ctypes as C
+    blob, offs = api.pack_reads(seqs)
+    out = np.zeros(len(seqs), dtype=api.RESULT_DTYPE)
+    cands = np.zeros(64 * len(seqs), dtype=api.PAIR_DTYPE)
+    n_c = C.c_uint64()
+    rc = api.lib().kmat_label_batch(ctxs[0].h, blob, offs.ctypes.data, len(seqs), out.ctypes.data, cands.ctypes.data, len(cands), C.byref(n_c), None, 0, None)
+    assert rc == -10, rc                                   # 16, 32, 64 words: still too small after the internal retries
+    assert b"list-record buffer" in api.lib().kmat_last_error()
+    rr, cc, ll = ctxs[0].label(seqs)                       # the Python wrapper retries on KMAT_ERR_OVERFLOW; the buffer doubles each time
+    assert ctxs[0].tails(rr, cc, ll, prn_all=True) == want
