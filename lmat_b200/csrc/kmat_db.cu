@@ -518,8 +518,9 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32) km_encode_probe_kernel(Km
 #ifndef KM_FAST_CTAS
 #define KM_FAST_CTAS 2
 #endif
-template <int NCH, int SETN, bool STATS>
+template <int NCH, int SETN, bool STATS, bool PEERS>
 __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS : 1) km_encode_probe_fast_kernel(KmProbeParams P) {
+    if (!PEERS) P.db.n_peers = 0;                 // the replicated table's instantiation carries no owner logic at all
     extern __shared__ __align__(16) unsigned char km_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint32_t *bitmap = (uint32_t *)(km_smem + (size_t)wib * (SETN / 8));
@@ -678,14 +679,14 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
     }
 }
 
-template <int NCH, int SETN, bool STATS>
+template <int NCH, int SETN, bool STATS, bool PEERS>
 static int km_launch_fast(const KmProbeParams &P, int ctas_per_sm, cudaStream_t stream) {
     const int smem = KM_PROBE_WARPS * (SETN / 8);
     static int resident = 0, sms = 148;    // per instantiation: CTAs that fit the device at once (persistent grid)
     if (!resident) {
-        KM_CUDA(cudaFuncSetAttribute(km_encode_probe_fast_kernel<NCH, SETN, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        KM_CUDA(cudaFuncSetAttribute(km_encode_probe_fast_kernel<NCH, SETN, STATS, PEERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int per_sm = 0, dev = 0;
-        KM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_encode_probe_fast_kernel<NCH, SETN, STATS>, KM_PROBE_WARPS * 32, smem));
+        KM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_encode_probe_fast_kernel<NCH, SETN, STATS, PEERS>, KM_PROBE_WARPS * 32, smem));
         cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (const char *e = getenv("KMAT_PROBE_CTAS")) { const int v = atoi(e); if (v > 0 && v < per_sm) per_sm = v; }
         resident = std::max(1, per_sm) * sms;
@@ -693,7 +694,7 @@ static int km_launch_fast(const KmProbeParams &P, int ctas_per_sm, cudaStream_t 
     const uint32_t want = (P.n_reads + KM_PROBE_WARPS - 1) / KM_PROBE_WARPS;
     const uint32_t cap = ctas_per_sm > 0 ? std::min<uint32_t>((uint32_t)resident, (uint32_t)(ctas_per_sm * sms)) : (uint32_t)resident;
     const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(want, cap));
-    km_encode_probe_fast_kernel<NCH, SETN, STATS><<<grid, KM_PROBE_WARPS * 32, smem, stream>>>(P);
+    km_encode_probe_fast_kernel<NCH, SETN, STATS, PEERS><<<grid, KM_PROBE_WARPS * 32, smem, stream>>>(P);
     return KMAT_OK;
 }
 
@@ -707,8 +708,11 @@ int km_launch_encode_probe(const kmat_db *db, const char *d_bases, const uint64_
     P.do_probe = do_probe; P.xq = d_xq;
     const bool fast = !d_kmers && !d_flags && max_len <= 256 && db->kmer_len <= 24 && !getenv("KMAT_NO_FAST_PROBE");
     int rc = KMAT_OK;
-    if (fast && max_len <= 160) rc = d_stats ? km_launch_fast<5, 4096, true>(P, ctas_per_sm, stream) : km_launch_fast<5, 4096, false>(P, ctas_per_sm, stream);
-    else if (fast) rc = d_stats ? km_launch_fast<8, 8192, true>(P, ctas_per_sm, stream) : km_launch_fast<8, 8192, false>(P, ctas_per_sm, stream);
+    const bool peers = P.db.n_peers != 0;
+    if (fast && max_len <= 160 && !peers) rc = d_stats ? km_launch_fast<5, 4096, true, false>(P, ctas_per_sm, stream) : km_launch_fast<5, 4096, false, false>(P, ctas_per_sm, stream);
+    else if (fast && max_len <= 160) rc = d_stats ? km_launch_fast<5, 4096, true, true>(P, ctas_per_sm, stream) : km_launch_fast<5, 4096, false, true>(P, ctas_per_sm, stream);
+    else if (fast && !peers) rc = d_stats ? km_launch_fast<8, 8192, true, false>(P, ctas_per_sm, stream) : km_launch_fast<8, 8192, false, false>(P, ctas_per_sm, stream);
+    else if (fast) rc = d_stats ? km_launch_fast<8, 8192, true, true>(P, ctas_per_sm, stream) : km_launch_fast<8, 8192, false, true>(P, ctas_per_sm, stream);
     else km_encode_probe_kernel<<<grid, KM_PROBE_WARPS * 32, 0, stream>>>(P);
     if (rc != KMAT_OK) return rc;
     g_km_launches++;

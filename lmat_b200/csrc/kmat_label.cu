@@ -20,6 +20,11 @@
 #define KB_LIN 128         // lineage entries in findReadLabelVer2
 #define KS_THREADS 128     // threads per CTA of the scoring kernel (one read per thread)
 #define KMAT_ST_PENDING 7  // internal: candidates built, scoring still to run
+#define KMAT_ST_PENDING_BIG 8   // internal: candidates built by the slow kernel (more than KB_CMAX of them), scored by the big scoring kernel
+#define KMAT_ST_DEFERRED 9      // internal: queued for the slow candidate kernel
+#define KB_CBIG 512        // candidate taxids per read the slow path holds (reads beyond it: KMAT_ERR_UNSUPPORTED)
+#define KB_LBIG 1024       // lineage entries of the big scoring kernel
+#define KB_BIGQ 65536      // reads per pass the slow path takes
 
 // stored id -> node: low 30 bits nid, bit 31 = isHuman, bit 30 = dropped tid (flags folded in so that the common
 // singleton hit needs no node-record load)
@@ -51,6 +56,10 @@ struct KmScoreParams {
     kmat_pair *lin; unsigned long long *lin_cursor; unsigned long long lin_cap;
     unsigned long long *long_masks; uint32_t long_cap;    // per-warp position-mask scratch for reads longer than the register path
     KmStatsDev *stats;
+    // slow path for reads with more than KB_CMAX candidate taxids (or more than KB_LIN lineage entries): K3 queues them
+    // in big_qa for km_cand_slow_kernel, which (like K4 on a lineage overflow) queues them in big_qb for the big scoring kernel
+    uint32_t *big_qa, *big_qb; unsigned int *big_cnt;     // big_cnt[0] / [1]: entries of big_qa / big_qb (may exceed KB_BIGQ: the excess is dropped)
+    unsigned char *big_scratch3, *big_scratch4; uint32_t big_np_cap, big_threads3, big_threads4;
 };
 
 struct KmRl { float score; uint32_t idx; };          // rank_label element: candidate index + (bias-adjusted) score
@@ -347,6 +356,17 @@ __device__ __forceinline__ unsigned long long kb_chunk(const KmScoreParams &P, K
     return mymask;
 }
 
+// A read K3's register-resident candidate set cannot hold: hand it to the slow kernel (all lanes call; lane 0 acts)
+__device__ __forceinline__ void kb_defer_big(const KmScoreParams &P, uint32_t r, kmat_read_result &res, int lane) {
+    if (lane != 0) return;
+    res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED;
+    if (P.big_qa) {
+        const unsigned int q = atomicAdd(P.big_cnt, 1u);
+        if (q < KB_BIGQ) { P.big_qa[q] = r; res.status = KMAT_ST_DEFERRED; res.err = 0; }
+    }
+    P.out[r] = res;
+}
+
 template <int NCH>
 __global__ void __launch_bounds__(KB_WARPS * 32, NCH == 5 ? 4 : 1) km_cand_kernel(KmScoreParams P) {
     const KmCtxDev &X = P.C;
@@ -410,7 +430,7 @@ __global__ void __launch_bounds__(KB_WARPS * 32, NCH == 5 ? 4 : 1) km_cand_kerne
         err = __reduce_max_sync(KM_FULL, err < 0 ? -err : 0);
         overflow = __any_sync(KM_FULL, overflow);
         if (err) { res.status = KMAT_ST_ERROR; res.err = -err; if (lane == 0) P.out[r] = res; st_err++; continue; }
-        if (overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; if (lane == 0) P.out[r] = res; st_err++; continue; }
+        if (overflow) { kb_defer_big(P, r, res, lane); continue; }
         const int C1 = C;
         if (C1 == 0) {                                                       // taxid_lst.empty() -> NoDbHits (:1270-1271)
             res.status = KMAT_ST_NODBHITS; res.n1 = len; res.n2 = k;
@@ -485,7 +505,7 @@ __global__ void __launch_bounds__(KB_WARPS * 32, NCH == 5 ? 4 : 1) km_cand_kerne
                 if (overflow) break;
                 if (lane == src) c_anc[slot] = anc;
             }
-            if (overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; if (lane == 0) P.out[r] = res; st_err++; continue; }
+            if (overflow) { kb_defer_big(P, r, res, lane); continue; }
             // ---- expanded position sets: every qualifying member brings its ancestors
             for (int j = 0; j < C1; j++) {
                 const unsigned long long aj = kb_shfl64(j < 32 ? c_anc[0] : c_anc[1], j & 31);
@@ -561,19 +581,23 @@ __global__ void __launch_bounds__(KB_WARPS * 32, NCH == 5 ? 4 : 1) km_cand_kerne
 // lanes; running 32 reads per warp keeps the lanes busy instead).  Restates construct_labels from the null-model
 // lookup on (read_label.cpp:735-941) and findReadLabelVer2 (:284-419) in the reference's float operation order.
 // ---------------------------------------------------------------------------------------------
-struct KsLocal {
-    uint32_t nid[KB_CMAX], tid[KB_CMAX], tin[KB_CMAX], tout[KB_CMAX];
-    float score[KB_CMAX], rp[KB_CMAX];
-    uint16_t depth[KB_CMAX];
-    uint8_t flags[KB_CMAX], cls[KB_CMAX];        // flags: 1 human, 2 phix, 4 plasmid
-    KmRl rl[KB_CMAX];
-    uint32_t l_tid[KB_LIN], l_tin[KB_LIN], l_tout[KB_LIN];
-    float l_score[KB_LIN];
-    uint16_t l_depth[KB_LIN];
-    uint8_t l_nogood[KB_LIN], l_perm[KB_LIN];
+template <int CMAX, int LIN, typename PermT>
+struct KsLocalT {
+    uint32_t nid[CMAX], tid[CMAX], tin[CMAX], tout[CMAX];
+    float score[CMAX];
+    uint16_t depth[CMAX];
+    uint8_t flags[CMAX], cls[CMAX];              // flags: 1 human, 2 phix, 4 plasmid
+    KmRl rl[CMAX];
+    uint32_t l_tid[LIN], l_tin[LIN], l_tout[LIN];
+    float l_score[LIN];
+    uint16_t l_depth[LIN];
+    uint8_t l_nogood[LIN];
+    PermT l_perm[LIN];
     float track_val[64];
     uint8_t track_has[64];
 };
+typedef KsLocalT<KB_CMAX, KB_LIN, uint8_t> KsLocal;          // per-thread local arrays of the regular kernel
+typedef KsLocalT<KB_CBIG, KB_LBIG, uint16_t> KsLocalBig;     // global scratch slot of the big kernel
 struct KsTCmp {           // TCmp, read_label.cpp:475-485: |a-b| < 0.001 (double compare) -> shallower first, else by score
     const uint16_t *depth;
     __device__ bool operator()(const KmRl &a, const KmRl &b) const {
@@ -581,18 +605,18 @@ struct KsTCmp {           // TCmp, read_label.cpp:475-485: |a-b| < 0.001 (double
         return a.score < b.score;
     }
 };
+template <typename PermT>
 struct KsLinDepthDesc {   // CmpDepth over lineage entries (:159-167), sorting a permutation
     const uint16_t *l_depth;
-    __device__ bool operator()(const uint8_t &a, const uint8_t &b) const { return (int)l_depth[a] > (int)l_depth[b]; }
+    __device__ bool operator()(const PermT &a, const PermT &b) const { return (int)l_depth[a] > (int)l_depth[b]; }
 };
 
-__global__ void __launch_bounds__(KS_THREADS) km_score_kernel(KmScoreParams P) {
-    const uint32_t r = blockIdx.x * KS_THREADS + threadIdx.x;
-    if (r >= P.n_reads) return;
+// One read.  T: the thread's working arrays (local memory in the regular kernel, a global scratch slot in the big one).
+template <int LIN, typename PermT, bool BIG, typename TT>
+__device__ __forceinline__ void ks_score_one(const KmScoreParams &P, const uint32_t r, TT &T) {
     kmat_read_result res = P.out[r];
-    if (res.status != KMAT_ST_PENDING) return;
+    if (res.status != KMAT_ST_PENDING && !(BIG && res.status == KMAT_ST_PENDING_BIG)) return;
     const KmCtxDev &X = P.C;
-    KsLocal T;
     const int C = (int)res.n_cand;
     const unsigned long long co = res.cand_off;
     const uint16_t cand16 = (uint16_t)res.cand_kmer_cnt;
@@ -691,7 +715,7 @@ __global__ void __launch_bounds__(KS_THREADS) km_score_kernel(KmScoreParams P) {
                 else if (chk == cdepth) { addNode = false; break; }
             }
             if (addNode) {
-                if (nlin >= KB_LIN) lin_overflow = true;
+                if (nlin >= LIN) lin_overflow = true;
                 else {
                     T.l_tid[nlin] = T.tid[ci]; T.l_tin[nlin] = T.tin[ci]; T.l_tout[nlin] = T.tout[ci]; T.l_score[nlin] = sc;
                     T.l_depth[nlin] = (uint16_t)cdepth; T.l_nogood[nlin] = 0; nlin++;
@@ -711,7 +735,7 @@ __global__ void __launch_bounds__(KS_THREADS) km_score_kernel(KmScoreParams P) {
         const KmNodeB hb = kb_nodeB(X, T.nid[highest]);
         for (uint32_t q = 0; q < hb.path_len; q++) {
             const uint32_t a = X.paths[hb.path_off + q];
-            if (nlin >= KB_LIN) { lin_overflow = true; break; }
+            if (nlin >= LIN) { lin_overflow = true; break; }
             int fc = -1;
             for (int c2 = 0; c2 < C; c2++) if (T.nid[c2] == a) { fc = c2; break; }
             if (fc >= 0) {                                                      // all_cand_set holds the un-biased score
@@ -726,9 +750,15 @@ __global__ void __launch_bounds__(KS_THREADS) km_score_kernel(KmScoreParams P) {
         }
         add_hi = nlin;
     }
-    if (lin_overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; res.n_cand = 0; P.out[r] = res; return; }
-    for (int q = 0; q < nlin; q++) T.l_perm[q] = (uint8_t)q;
-    kmstd::sort(T.l_perm, nlin, KsLinDepthDesc{T.l_depth});                     // cand_lin_vec sorted by depth desc :350-351
+    if (lin_overflow) {
+        if (!BIG && P.big_qb) {                      // more lineage entries than the local arrays hold: the big kernel redoes this read
+            const unsigned int q = atomicAdd(P.big_cnt + 1, 1u);
+            if (q < KB_BIGQ) { P.big_qb[q] = r; return; }
+        }
+        res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; res.n_cand = 0; P.out[r] = res; return;
+    }
+    for (int q = 0; q < nlin; q++) T.l_perm[q] = (PermT)q;
+    kmstd::sort(T.l_perm, nlin, KsLinDepthDesc<PermT>{T.l_depth});                     // cand_lin_vec sorted by depth desc :350-351
     bool any_nogood = false;
     for (int i = lidx; i >= 0; --i) {                                           // :355-362
         const int ci = (int)T.rl[i].idx; const float sc = T.rl[i].score;
@@ -784,6 +814,172 @@ __global__ void __launch_bounds__(KS_THREADS) km_score_kernel(KmScoreParams P) {
     P.out[r] = res;
 }
 
+__global__ void __launch_bounds__(KS_THREADS) km_score_kernel(KmScoreParams P) {
+    const uint32_t r = blockIdx.x * KS_THREADS + threadIdx.x;
+    if (r >= P.n_reads) return;
+    KsLocal T;
+    ks_score_one<KB_LIN, uint8_t, false>(P, r, T);
+}
+// The reads of big_qb (more than KB_CMAX candidates, or a lineage the regular kernel could not hold): same code, working
+// arrays in a global scratch slot per thread.
+__global__ void __launch_bounds__(32) km_score_big_kernel(KmScoreParams P) {
+    const uint32_t slot = blockIdx.x * 32 + threadIdx.x, n_threads = gridDim.x * 32;
+    if (slot >= P.big_threads4) return;
+    KsLocalBig &T = *(KsLocalBig *)(P.big_scratch4 + (size_t)slot * sizeof(KsLocalBig));
+    const uint32_t n = min(P.big_cnt[1], (unsigned int)KB_BIGQ);
+    for (uint32_t q = slot; q < n; q += min(n_threads, P.big_threads4)) ks_score_one<KB_LBIG, uint16_t, true>(P, P.big_qb[q], T);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3, slow path: one THREAD per read of big_qa, candidate set and position sets in a global scratch slot, up to KB_CBIG
+// candidates.  Restates km_cand_kernel step by step (same member order, same in-place expansion); nothing here is hot:
+// about one read in ten million of the synthetic workloads, more on reads from conserved regions of real databases.
+// ---------------------------------------------------------------------------------------------
+#define KB_BIGW (KB_CBIG / 64)
+struct KbSlow {
+    uint32_t nid[KB_CBIG], leaf[KB_CBIG], firstpos[KB_CBIG], hits[KB_CBIG];
+    unsigned long long anc[KB_CBIG][KB_BIGW];
+};
+__device__ __forceinline__ int kbs_find_or_add(KbSlow &S, int &C, uint32_t v, uint32_t pos) {
+    for (int i = 0; i < C; i++) if (S.nid[i] == v) return i;
+    if (C >= KB_CBIG) return -1;
+    S.nid[C] = v; S.leaf[C] = 0; S.firstpos[C] = pos; S.hits[C] = 0;
+    for (int w = 0; w < KB_BIGW; w++) S.anc[C][w] = 0ull;
+    return C++;
+}
+__global__ void __launch_bounds__(32) km_cand_slow_kernel(KmScoreParams P) {
+    const KmCtxDev &X = P.C;
+    const uint32_t slot = blockIdx.x * 32 + threadIdx.x, n_threads = min((uint32_t)gridDim.x * 32, P.big_threads3);
+    if (slot >= P.big_threads3) return;
+    const size_t slot_bytes = sizeof(KbSlow) + (size_t)P.big_np_cap * KB_BIGW * 8;
+    KbSlow &S = *(KbSlow *)(P.big_scratch3 + (size_t)slot * slot_bytes);
+    unsigned long long *mask = (unsigned long long *)(P.big_scratch3 + (size_t)slot * slot_bytes + sizeof(KbSlow));
+    const int k = X.db.kmer_len;
+    const bool permissive = X.opt.permissive != 0;
+    const uint32_t nq = min(P.big_cnt[0], (unsigned int)KB_BIGQ);
+    for (uint32_t q = slot; q < nq; q += n_threads) {
+        const uint32_t r = P.big_qa[q];
+        const uint64_t off = P.offs[r];
+        const int len = (int)(P.offs[r + 1] - off);
+        const int np = len - k + 1;
+        const int2 hd = P.hdr[r];
+        kmat_read_result res;
+        memset(&res, 0, sizeof res);
+        res.valid_kmers = hd.x; res.bin_sel = hd.y; res.match = KMAT_NOMATCH;
+        if (np <= 0 || (uint32_t)np > P.big_np_cap) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; P.out[r] = res; continue; }
+        int C = 0, cand_cnt = 0, fnd_cnt = 0, err = 0;
+        bool overflow = false;
+        // ---- per position: members in insertion order (kb_chunk)
+        for (int p = 0; p < np && !overflow && !err; p++) {
+            unsigned long long *m = mask + (size_t)p * KB_BIGW;
+            for (int w = 0; w < KB_BIGW; w++) m[w] = 0ull;
+            const uint32_t hw = P.hit[off + p];
+            if (hw == KM_HIT_INVALID) continue;
+            cand_cnt++;
+            uint32_t a = 0, b = 0, v0 = KMAT_NONE;
+            const uint32_t *rec = nullptr;
+            if (hw != KM_HIT_MISS) {
+                if (!(hw & KM_HIT_LIST)) {
+                    const uint32_t e = hw < X.n_sid ? X.sid2nid[hw] : KMAT_NONE;
+                    if (e == KMAT_NONE) { err = KMAT_ERR_BAD_TAXID; break; }
+                    if (!(e & KB_SID_DROP)) {
+                        v0 = ((e & KB_SID_HUMAN) && !X.opt.rkmer_mode) ? X.nid_human : (e & KB_SID_NIDMASK); a = 1;
+                        if (permissive) b = (kb_nodeA(X, v0).meta & KM_META_DEPTH_MASK) ? 1 : 0;
+                    }
+                } else {
+                    rec = kb_rec_of(X, hw);
+                    const uint32_t h = rec[0];
+                    if (h == KR_ERR_BAD) { err = KMAT_ERR_BAD_TAXID; break; }
+                    a = h & 0xFFFFu;
+                    if (permissive) { b = rec[1]; rec += 2; } else rec += 1;
+                }
+            }
+            if (a) fnd_cnt++;
+            for (uint32_t sq = 0; sq < a && !overflow; sq++) {
+                const int idx = kbs_find_or_add(S, C, rec ? rec[sq] : v0, (uint32_t)p);
+                if (idx < 0) { overflow = true; break; }
+                S.leaf[idx]++; m[idx >> 6] |= 1ull << (idx & 63);
+            }
+            for (uint32_t bi = 0; bi < b && !overflow; bi++) {               // permissive: root paths of the deepest ids
+                const KmNodeB nb = kb_nodeB(X, rec ? rec[a + bi] : v0);
+                for (uint32_t pq = 0; pq < nb.path_len; pq++) {
+                    const int idx = kbs_find_or_add(S, C, X.paths[nb.path_off + pq], (uint32_t)p);
+                    if (idx < 0) { overflow = true; break; }
+                    S.leaf[idx]++; m[idx >> 6] |= 1ull << (idx & 63);
+                }
+            }
+        }
+        if (err) { res.status = KMAT_ST_ERROR; res.err = err; P.out[r] = res; continue; }
+        if (overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; P.out[r] = res; continue; }
+        const int C1 = C;
+        if (C1 == 0) { res.status = KMAT_ST_NODBHITS; res.n1 = len; res.n2 = k; P.out[r] = res; continue; }
+        const uint16_t cand16 = (uint16_t)cand_cnt;
+        res.cand_kmer_cnt = cand16;
+        if (fnd_cnt < X.opt.min_fnd_kmer || (int)cand16 < X.opt.min_kmer) { res.status = KMAT_ST_SILENT; res.match = KMAT_NOMATCH; res.tid = 0; res.score = -1.0f; P.out[r] = res; continue; }
+        if (!permissive) {
+            // ---- representative strain per species, then the lineage of every qualifying member in (first position, taxid)
+            //      order; S.hits doubles as the "done" marker of that selection sort until the counts are taken
+            for (;;) {
+                int best = -1; unsigned long long bkey = ~0ull;
+                for (int s2 = 0; s2 < C1; s2++) {
+                    if (S.hits[s2]) continue;
+                    const KmNodeA na = kb_nodeA(X, S.nid[s2]);
+                    const unsigned long long key = ((unsigned long long)S.firstpos[s2] << 32) | na.tid;
+                    if (key < bkey) { bkey = key; best = s2; }
+                }
+                if (best < 0) break;
+                S.hits[best] = 1;
+                const KmNodeA na = kb_nodeA(X, S.nid[best]);
+                const bool strain = ((na.meta >> KM_META_RANK_SHIFT) & 3) == 1;
+                bool qual = !strain;
+                if (strain && na.species_anc != KMAT_NONE) {
+                    bool beaten = false;
+                    for (int j = 0; j < C1 && !beaten; j++) {
+                        const KmNodeA nj = kb_nodeA(X, S.nid[j]);
+                        beaten = ((nj.meta >> KM_META_RANK_SHIFT) & 3) == 1 && nj.species_anc == na.species_anc &&
+                                 (S.leaf[j] > S.leaf[best] || (S.leaf[j] == S.leaf[best] && nj.tid < na.tid));
+                    }
+                    qual = !beaten;
+                }
+                if (!qual) continue;
+                const KmNodeB nb = kb_nodeB(X, S.nid[best]);
+                for (uint32_t pq = 0; pq < nb.path_len; pq++) {
+                    const int idx = kbs_find_or_add(S, C, X.paths[nb.path_off + pq], 0xFFFFFFFFu);
+                    if (idx < 0) { overflow = true; break; }
+                    S.anc[best][idx >> 6] |= 1ull << (idx & 63);
+                }
+                if (overflow) break;
+            }
+            if (overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; P.out[r] = res; continue; }
+            for (int i = 0; i < C; i++) S.hits[i] = 0;
+            // ---- expanded position sets, in place and in candidate order like the warp kernel
+            for (int p = 0; p < np; p++) {
+                unsigned long long *m = mask + (size_t)p * KB_BIGW;
+                for (int j = 0; j < C1; j++) {
+                    if (!((m[j >> 6] >> (j & 63)) & 1)) continue;
+                    for (int w = 0; w < KB_BIGW; w++) m[w] |= S.anc[j][w];
+                }
+            }
+        }
+        // ---- hits per candidate
+        for (int p = 0; p < np; p++) {
+            const unsigned long long *m = mask + (size_t)p * KB_BIGW;
+            for (int w = 0; w < KB_BIGW; w++) {
+                unsigned long long v = m[w];
+                while (v) { const int bit = __ffsll((long long)v) - 1; v &= v - 1; S.hits[w * 64 + bit]++; }
+            }
+        }
+        // ---- hand over in taxid_lst order: first-appearance order of the members (= insertion order here), then the
+        //      ancestors in the order the expansion appended them
+        const unsigned long long co = atomicAdd(P.cand_cursor, (unsigned long long)C);
+        res.status = KMAT_ST_PENDING_BIG; res.n_cand = (uint32_t)C; res.cand_off = co;
+        if (P.cands && co + C <= P.cand_cap) { for (int i = 0; i < C; i++) P.cands[co + i] = kmat_pair{S.nid[i], __uint_as_float(S.hits[i])}; }
+        else { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_OVERFLOW; }
+        P.out[r] = res;
+        if (res.status == KMAT_ST_PENDING_BIG) { const unsigned int q2 = atomicAdd(P.big_cnt + 1, 1u); if (q2 < KB_BIGQ) P.big_qb[q2] = r; else { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; P.out[r] = res; } }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // kmat_ctx
 // ---------------------------------------------------------------------------------------------
@@ -825,6 +1021,9 @@ struct kmat_ctx {
     uint32_t *d_null_max = nullptr, *d_null_cnt = nullptr; unsigned long long *d_null_err = nullptr;
     uint64_t null_first = 0;                 // run index of read 0 of the pass being launched
     // direct sharded mode (kmat_ctx_peer_attach): where every shard's buckets / stash / resolved pool are mapped on this GPU
+    // slow path for reads with more than KB_CMAX candidates: queues, counters and per-thread scratch slots
+    uint32_t *d_bigq = nullptr; unsigned int *d_bigcnt = nullptr;
+    unsigned char *d_big3 = nullptr, *d_big4 = nullptr; uint64_t cap_big3 = 0; uint32_t big_np_cap = 0, big_threads3 = 0;
     KmPeer *d_peers = nullptr; uint32_t n_peers = 0; std::vector<void *> ipc_mapped;
     uint32_t *d_peer_recs = nullptr; uint64_t cap_peer_recs = 0;      // list records of the pass copied from their owners (km_peer_fetch_kernel)
     unsigned long long *d_peer_cur = nullptr;                         // [0] words used (per pass), [1] list hits dropped for lack of room (monotonic)
@@ -962,6 +1161,7 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
     km_shard_free(c->shard);
     for (void *p : c->ipc_mapped) cudaIpcCloseMemHandle(p);
     cudaFree(c->d_peers); cudaFree(c->d_peer_recs); cudaFree(c->d_peer_cur);
+    cudaFree(c->d_bigq); cudaFree(c->d_bigcnt); cudaFree(c->d_big3); cudaFree(c->d_big4);
     cudaFree(c->d_null_max); cudaFree(c->d_null_cnt); cudaFree(c->d_null_err); cudaFree(c->d_null_bases); cudaFree(c->d_null_offs);
     cudaFree(c->d_hit); cudaFree(c->d_hdr); cudaFree(c->d_out_dev);
     if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
@@ -1059,6 +1259,25 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
     P.lin = c->d_lin; P.lin_cursor = c->d_cursors + 1; P.lin_cap = c->cap_lin;
     P.stats = c->collect_stats ? c->d_stats : nullptr;
     P.long_masks = nullptr; P.long_cap = 0;
+    // slow path buffers (first use / longer reads than before)
+    const uint32_t KBIG_THREADS = 128;
+    const uint32_t np_need = (uint32_t)std::max<int>(1, (int)L.max_len - c->db->kmer_len + 1);
+    if (!c->d_bigq) {
+        KM_CUDA(cudaMalloc((void **)&c->d_bigq, (size_t)2 * KB_BIGQ * 4));
+        KM_CUDA(cudaMalloc((void **)&c->d_bigcnt, 8));
+        KM_CUDA(cudaMalloc((void **)&c->d_big4, (size_t)KBIG_THREADS * sizeof(KsLocalBig)));
+    }
+    if (np_need > c->big_np_cap) {
+        const size_t per = sizeof(KbSlow) + (size_t)np_need * KB_BIGW * 8;
+        uint32_t threads = (uint32_t)std::min<size_t>(KBIG_THREADS, std::max<size_t>(1, ((size_t)512 << 20) / per));
+        KM_CUDA(cudaStreamSynchronize(s2));
+        int rc3 = km_grow(&c->d_big3, &c->cap_big3, (uint64_t)per * threads);
+        if (rc3 != KMAT_OK) return rc3;
+        c->big_np_cap = np_need; c->big_threads3 = threads;
+    }
+    P.big_qa = c->d_bigq; P.big_qb = c->d_bigq + KB_BIGQ; P.big_cnt = c->d_bigcnt;
+    P.big_scratch3 = c->d_big3; P.big_scratch4 = c->d_big4; P.big_np_cap = c->big_np_cap; P.big_threads3 = c->big_threads3; P.big_threads4 = KBIG_THREADS;
+    KM_CUDA(cudaMemsetAsync(c->d_bigcnt, 0, 8, s2));
     const int want_grid = (int)((n + KB_WARPS - 1) / KB_WARPS);
     const int g0 = cand_ctas_per_sm > 0 ? std::min(c->cand_grid[0], cand_ctas_per_sm * c->sms) : c->cand_grid[0];
     if (variant == 0) km_cand_kernel<5><<<std::max(1, std::min(g0, want_grid)), KB_WARPS * 32, 0, s2>>>(P);
@@ -1067,6 +1286,10 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
         P.long_masks = c->d_long_masks; P.long_cap = c->long_mask_cap;
         km_cand_kernel<0><<<std::max(1, std::min(c->cand_grid[2], want_grid)), KB_WARPS * 32, 0, s2>>>(P);
     }
+    g_km_launches++;
+    KM_CUDA(cudaGetLastError());
+    // the (rare) reads K3 could not hold in registers; an empty queue costs two tiny launches
+    km_cand_slow_kernel<<<(c->big_threads3 + 31) / 32, 32, 0, s2>>>(P);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     if (ev_mid) KM_CUDA(cudaEventRecord(ev_mid, s2));
@@ -1078,6 +1301,9 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
         if (v > 48 * 1024) cudaFuncSetAttribute(km_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
         return v > 0 ? v : 0; }();
     km_score_kernel<<<(n + KS_THREADS - 1) / KS_THREADS, KS_THREADS, score_smem, s2>>>(P);
+    g_km_launches++;
+    KM_CUDA(cudaGetLastError());
+    km_score_big_kernel<<<KBIG_THREADS / 32, 32, 0, s2>>>(P);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     return KMAT_OK;

@@ -398,44 +398,79 @@ struct KmFetchParams {
     uint32_t *hit; uint64_t n_pos; const KmPeer *peers; int mul, permissive;
     uint32_t *recs; unsigned long long *cur; unsigned long long cap;
 };
+#define KM_FETCH_TILE 4096
 __global__ void __launch_bounds__(256) km_peer_fetch_kernel(KmFetchParams F) {
-    const int lane = threadIdx.x & 31;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31); i0 < F.n_pos; i0 += stride) {
-        const uint64_t i = i0 + lane;
-        const uint32_t hw = i < F.n_pos ? F.hit[i] : KM_HIT_INVALID;
-        const bool is_list = hw != KM_HIT_INVALID && hw != KM_HIT_MISS && (hw & KM_HIT_LIST);
-        if (!__any_sync(KM_FULL, is_list)) continue;
-        uint32_t S[16];
-        const uint32_t *rec = nullptr;
-        uint32_t w0 = 0, len = 0;
-        if (is_list) {
-            const KmPeer pr = F.peers[(hw >> KM_PEER_SHIFT) & (KM_MAX_SHARDS - 1)];
-            rec = pr.pool2 + (size_t)(hw & KM_PEER_OFFMASK) * F.mul;
-            const uint64_t *a0 = (const uint64_t *)((uintptr_t)rec & ~(uintptr_t)31);
-            w0 = (uint32_t)(((uintptr_t)rec & 31) >> 2);
-            uint64_t q[8];
-            km_load_bucket(a0, q[0], q[1], q[2], q[3]);
-            km_load_bucket(a0 + 4, q[4], q[5], q[6], q[7]);
-#pragma unroll
-            for (int j = 0; j < 8; j++) { S[2 * j] = (uint32_t)q[j]; S[2 * j + 1] = (uint32_t)(q[j] >> 32); }
-            const uint32_t h = S[w0];
-            if (h == KR_ERR_BAD) len = 1;                               // the candidate kernel reports the bad stored id
-            else len = F.permissive ? 2 + (h & 0xFFFFu) + S[w0 + 1] : 1 + (h & 0xFFFFu);
+    // A CTA takes a tile of 4096 hit words: the list hits among them (~3 %) are first queued in shared memory, then one
+    // thread per queued hit issues its two remote sector reads -- so a tile waits ONCE for the NVLink round trip (tens of
+    // microseconds while the peers' probe kernels keep the fabric saturated), not once per 32 hit words.
+    __shared__ uint32_t s_pos[KM_FETCH_TILE];
+    __shared__ uint32_t s_n, s_warp[8];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t n_tiles = (F.n_pos + KM_FETCH_TILE - 1) / KM_FETCH_TILE;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t t0 = tile * KM_FETCH_TILE;
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        for (int j = 0; j < KM_FETCH_TILE / 256; j++) {
+            const uint64_t i = t0 + (uint64_t)j * 256 + threadIdx.x;
+            const uint32_t hw = i < F.n_pos ? F.hit[i] : KM_HIT_INVALID;
+            const bool is_list = hw != KM_HIT_INVALID && hw != KM_HIT_MISS && (hw & KM_HIT_LIST);
+            const uint32_t bal = __ballot_sync(KM_FULL, is_list);
+            if (bal) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&s_n, (uint32_t)__popc(bal));
+                base = __shfl_sync(KM_FULL, base, 0);
+                if (is_list) s_pos[base + __popc(bal & ((1u << lane) - 1))] = (uint32_t)(i - t0);
+            }
         }
-        // warp-aggregated allocation in the local record buffer
-        uint32_t incl = len;
+        __syncthreads();
+        const uint32_t n = s_n;
+        for (uint32_t e0 = 0; e0 < n; e0 += 256) {
+            const uint32_t e = e0 + threadIdx.x;
+            const bool act = e < n;
+            uint32_t S[16];
+            const uint32_t *rec = nullptr;
+            uint32_t w0 = 0, len = 0;
+            uint64_t i = 0;
+            if (act) {
+                i = t0 + s_pos[e];
+                const uint32_t hw = F.hit[i];
+                const KmPeer pr = F.peers[(hw >> KM_PEER_SHIFT) & (KM_MAX_SHARDS - 1)];
+                rec = pr.pool2 + (size_t)(hw & KM_PEER_OFFMASK) * F.mul;
+                const uint64_t *a0 = (const uint64_t *)((uintptr_t)rec & ~(uintptr_t)31);
+                w0 = (uint32_t)(((uintptr_t)rec & 31) >> 2);
+                uint64_t q[8];
+                km_load_bucket(a0, q[0], q[1], q[2], q[3]);
+                km_load_bucket(a0 + 4, q[4], q[5], q[6], q[7]);
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(KM_FULL, incl, d); if (lane >= d) incl += t; }
-        const uint32_t total = __shfl_sync(KM_FULL, incl, 31);
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(F.cur, (unsigned long long)total);
-        base = ((unsigned long long)__shfl_sync(KM_FULL, (uint32_t)(base >> 32), 0) << 32) | __shfl_sync(KM_FULL, (uint32_t)base, 0);
-        if (!is_list) continue;
-        const unsigned long long dst = base + (incl - len);
-        if (dst + len > F.cap) { atomicAdd(F.cur + 1, 1ull); F.hit[i] = KM_HIT_MISS; continue; }
-        for (uint32_t w = 0; w < len; w++) F.recs[dst + w] = w0 + w < 16 ? S[w0 + w] : rec[w];
-        F.hit[i] = KM_HIT_LIST | (uint32_t)dst;
+                for (int j = 0; j < 8; j++) { S[2 * j] = (uint32_t)q[j]; S[2 * j + 1] = (uint32_t)(q[j] >> 32); }
+                const uint32_t h = S[w0];
+                if (h == KR_ERR_BAD) len = 1;                               // the candidate kernel reports the bad stored id
+                else len = F.permissive ? 2 + (h & 0xFFFFu) + S[w0 + 1] : 1 + (h & 0xFFFFu);
+            }
+            // CTA-wide allocation in the local record buffer: one global atomic per round
+            uint32_t incl = len;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(KM_FULL, incl, d); if (lane >= d) incl += t; }
+            if (lane == 31) s_warp[wid] = incl;
+            __syncthreads();
+            uint32_t before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { const uint32_t v = s_warp[w]; if (w < wid) before += v; total += v; }
+            if (threadIdx.x == 0) s_base = atomicAdd(F.cur, (unsigned long long)total);
+            __syncthreads();
+            if (act) {
+                const unsigned long long dst = s_base + before + (incl - len);
+                if (dst + len > F.cap) { atomicAdd(F.cur + 1, 1ull); F.hit[i] = KM_HIT_MISS; }
+                else {
+                    for (uint32_t w = 0; w < len; w++) F.recs[dst + w] = w0 + w < 16 ? S[w0 + w] : rec[w];
+                    F.hit[i] = KM_HIT_LIST | (uint32_t)dst;
+                }
+            }
+            __syncthreads();
+        }
+        __syncthreads();
     }
 }
 
@@ -454,7 +489,7 @@ static int km_peer_fetch(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
     F.hit = c->d_hit; F.n_pos = L.total_bases; F.peers = c->d_peers; F.mul = c->pool2_mul; F.permissive = c->opt.permissive != 0;
     F.recs = c->d_peer_recs; F.cur = c->d_peer_cur; F.cap = std::min<uint64_t>(c->cap_peer_recs, (1ull << 31) - 1);
     if (const char *e = getenv("KMAT_TEST_PEER_RECS")) F.cap = std::min<uint64_t>(F.cap, (uint64_t)atoll(e) * (uint64_t)c->peer_grow);
-    const int grid = (int)std::min<uint64_t>((L.total_bases + 255) / 256, (uint64_t)c->sms * 8);
+    const int grid = (int)std::min<uint64_t>((L.total_bases + KM_FETCH_TILE - 1) / KM_FETCH_TILE, (uint64_t)c->sms * 8);
     km_peer_fetch_kernel<<<std::max(1, grid), 256, 0, st>>>(F);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());

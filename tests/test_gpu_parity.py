@@ -146,11 +146,41 @@ def test_long_and_ragged_reads_match_oracle(golden_lists, dbs, opts):
     orc = oracle_for(g, opts)
     res, cands, lin = ctx.label(seqs)
     ores, _, _ = orc.label(seqs)
-    unsupported = (res["status"] == 6)
-    assert unsupported.sum() <= 2, "more than a couple of reads exceed the candidate capacity"
-    mine = ctx.tails(res[~unsupported], cands, lin, prn_all=True)
-    want = [t for t, u in zip(orc.tails(ores), unsupported) if not u]
-    assert mine == want
+    assert (res["status"] != 6).all()
+    assert ctx.tails(res, cands, lin, prn_all=True) == orc.tails(ores)
+
+
+@pytest.mark.parametrize("opts", ["run_rl", "permissive", "prune3", "defaults"])
+def test_reads_with_more_than_64_candidates_match_oracle(golden_lists, dbs, opts):
+    """Chimeric reads stitched from many genomes carry more candidate taxids than the warp kernel's 64 register slots:
+    they take the slow path (km_cand_slow_kernel + km_score_big_kernel, up to 512 candidates) and must come out exactly
+    like the oracle's -- short reads (the <= 160-position kernel), medium and long ones (global position masks)."""
+    g = golden_lists
+    inp = S.build_inputs("lists", g.workdir + "/big_" + opts)
+    rng = np.random.default_rng(23)
+    names = list(inp["genomes"])
+    gstr = [fx.codes_to_str(inp["genomes"][n]) for n in names]
+    seqs = []
+    for L, piece in [(150, 21), (150, 24), (160, 22), (300, 23), (900, 25), (4000, 30), (12000, 40)]:
+        for rep in range(6):
+            parts = []
+            while sum(map(len, parts)) < L:
+                gs = gstr[int(rng.integers(0, len(gstr)))]
+                a = int(rng.integers(0, len(gs) - piece))
+                parts.append(gs[a:a + piece])
+            seqs.append("".join(parts)[:L])
+    seqs += [gstr[0][:150], gstr[1][100:400]]              # ordinary reads in the same batch
+    ctx = make_ctx(g, dbs[g.name], opts)
+    orc = oracle_for(g, opts)
+    res, cands, lin = ctx.label(seqs)
+    ores, ocands, _ = orc.label(seqs)
+    big = ores["n_cand"] > 64
+    assert big.sum() >= 12, (int(big.sum()), ores["n_cand"].tolist())
+    if opts != "prune3":
+        assert (ores["n_cand"][:18] > 64).any()            # also among the 150 / 160-base reads (the register-mask kernel)
+    assert (res["status"] != 6).all(), res["err"][res["status"] == 6]
+    assert np.array_equal(res["n_cand"], ores["n_cand"])
+    assert ctx.tails(res, cands, lin, prn_all=S.OPTION_SETS[opts]["prn_all"]) == orc.tails(ores)
 
 
 def _sample_reads(g, workdir, lengths, seed, reps=4):
