@@ -240,6 +240,7 @@ def sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, 
     lab.timing = None
     lab.lookups, lab.served, lab.payload_words, lab.rounds = keep
     res = d_out.cpu().numpy().view(api.RESULT_DTYPE)
+    labels_checksum = int(((res["status"].astype(np.int64) * 1000003 + res["tid"].astype(np.int64) * 7919 + res["score"].view(np.int32).astype(np.int64)) & 0xFFFFFFFF).sum())
     errs = int((res["status"] == 6).sum())
     labeled = int((res["status"] == 5).sum())
     if errs:
@@ -267,7 +268,7 @@ def sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, 
                                       f"(8 B), all-to-all of hit words (4 B) + list records back ({'NCCL, torch.distributed' if world > 1 else 'single rank'})"},
             "kmer_lookups_per_s": lookups_step / (ms_step * 1e-3), "lookups_per_read": lookups_step / (world * n),
             "exchange_bytes_per_step": int(lookups_step * 12 + int(tot[1].item()) / a.steps * 4), "reads_error": int(tot[2].item()),
-            "reads_labeled": int(tot[3].item()), "phase_ms_rank0": phase_ms,
+            "reads_labeled": int(tot[3].item()), "phase_ms_rank0": phase_ms, "labels_checksum_rank0": labels_checksum,
             "roofline": {"bound": "hbm", "kernel": "km_shard_probe_kernel", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
                          "peak_source": peak_src, "note": "per-kernel split not measured in sharded mode; see the replicated line"},
             "e2e": None, "gpu_launches": int(api.lib().kmat_launch_count() - launches0), "clocks": clocks, "setup_s": setup_s,
@@ -424,6 +425,16 @@ def main():
         ctx.set_stats(True)
         step()
         torch.cuda.synchronize()
+        # order-independent checksum of the labels of rank 0's reads (status, taxid, score bits): the replicated, the
+        # exchange and the direct arm label the same seeded reads against the same table, so their checksums must agree
+        labels_checksum = None
+        try:
+            from lmat_b200 import sharded as _sh
+            optr, _, _ = ctx.device_results()
+            rv = _sh._wrap(optr, n * api.RESULT_DTYPE.itemsize, torch.uint8, dev).view(torch.int32).view(n, api.RESULT_DTYPE.itemsize // 4).to(torch.int64)
+            labels_checksum = int(((rv[:, 0] * 1000003 + rv[:, 6] * 7919 + rv[:, 7]) & 0xFFFFFFFF).sum().item())
+        except Exception as ex:
+            labels_checksum = repr(ex)[:100]
         st = ctx.stats()
         ctx.set_stats(False)
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
@@ -486,7 +497,7 @@ def main():
                                            f"GPU's memory (CUDA IPC peer mapping, NVLink reads); reads stay home, no exchange rounds, no collective")
                            if direct_mode else f"read-sharded x{world}, table replicated, no data-path collective"},
                 "kmer_lookups_per_s": value * lookups_per_read, "lookups_per_read": lookups_per_read,
-                "hit_rate": st.hits / max(1, st.lookups), "reads_error": int(errs),
+                "hit_rate": st.hits / max(1, st.lookups), "reads_error": int(errs), "labels_checksum_rank0": labels_checksum,
                 "kernels_ms": {"encode_probe": pm, "candidates": cm_, "score": sm_, "how": "CUDA events around each kernel of one serial pass"},
                 "pipeline_sub_batches": a.pipeline,
                 "roofline": {"bound": "hbm", "kernel": "km_encode_probe_fast_kernel<5>" if L <= 160 else ("km_encode_probe_fast_kernel<8>" if L <= 256 else "km_encode_probe_kernel"), "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

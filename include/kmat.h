@@ -46,6 +46,7 @@ const char *kmat_strerror(int code);
 const char *kmat_last_error(void);      /* thread-local detail of the last failure */
 int kmat_abi_version(void);
 int kmat_device_count(void);            /* 0 when no usable GPU (never an error) */
+int kmat_device_memory(int device, uint64_t *free_bytes, uint64_t *total_bytes);   /* HBM of `device` right now */
 
 /* ---- table ingest (host) ---------------------------------------------------------------------
  * Replaces: `perm(&taxtable,..); mopen(db,"r",0)` + the SortedDb members reached through begin_/next

@@ -42,7 +42,7 @@ class KmatError(RuntimeError):
 
 
 EXPORTS = [
-    "kmat_strerror", "kmat_last_error", "kmat_abi_version", "kmat_device_count", "kmat_table_from_sorteddb",
+    "kmat_strerror", "kmat_last_error", "kmat_abi_version", "kmat_device_count", "kmat_device_memory", "kmat_table_from_sorteddb",
     "kmat_table_from_arrays", "kmat_table_open", "kmat_table_save", "kmat_table_size", "kmat_table_kmer_length",
     "kmat_table_tid_bytes", "kmat_table_build", "kmat_build_opts_default", "kmat_table_view", "kmat_table_free", "kmat_db_upload", "kmat_db_build_device",
     "kmat_shard_of", "kmat_db_size", "kmat_db_bytes", "kmat_db_kmer_length", "kmat_db_device", "kmat_db_free",
@@ -68,6 +68,7 @@ def lib():
     L.kmat_strerror.restype = C.c_char_p
     L.kmat_strerror.argtypes = [C.c_int]
     L.kmat_last_error.restype = C.c_char_p
+    L.kmat_device_memory.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.kmat_table_from_sorteddb.argtypes = [vp, C.c_uint64, C.c_int, vp, C.c_uint64, vp, C.c_uint64, C.c_int, C.c_int, C.POINTER(vp)]
     L.kmat_table_from_arrays.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, C.POINTER(vp)]
     L.kmat_table_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]

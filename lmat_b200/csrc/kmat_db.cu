@@ -21,6 +21,16 @@ extern "C" int kmat_device_count(void) {
     return n;
 }
 
+extern "C" int kmat_device_memory(int device, uint64_t *free_bytes, uint64_t *total_bytes) {
+    if (kmat_device_count() <= device || device < 0) { kmat_set_error("CUDA device %d not available", device); return KMAT_ERR_NO_DEVICE; }
+    KM_CUDA(cudaSetDevice(device));
+    size_t f = 0, t = 0;
+    KM_CUDA(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return KMAT_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // geometry
 // ---------------------------------------------------------------------------------------------

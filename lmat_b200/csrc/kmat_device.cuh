@@ -21,8 +21,12 @@ struct KmPeer {
     const uint64_t *slots;        // the owner's bucket array (same geometry on every shard)
     const uint64_t *stash_x; const uint32_t *stash_hit;
     const uint32_t *pool2;        // the owner ctx's resolved list pool
-    uint32_t n_stash, pad;
+    uint32_t n_stash;
+    uint32_t pool_base;           // KM_PEER_NO_BASE: list hits are tagged with the owner (records fetched from its pool);
+                                  // else the owner's resolved pool has been copied into this rank's concatenated pool at this
+                                  // (raw) word offset and list hit words carry offsets into that local copy
 };
+#define KM_PEER_NO_BASE 0xFFFFFFFFu
 #define KM_PEER_SHIFT 27          // direct mode: a list hit word is LIST | owner << 27 | pool word offset (< 2^27)
 #define KM_PEER_OFFMASK 0x07FFFFFFu
 
@@ -78,7 +82,9 @@ __device__ __forceinline__ const uint64_t *km_slots_of(const KmDbDev &db, uint64
 }
 // A hit word found in shard `owner`: list offsets are local to the owner's pool, so the owner rides along (direct mode)
 __device__ __forceinline__ uint32_t km_tag_owner(const KmDbDev &db, uint32_t hw, uint32_t owner) {
-    return (db.n_peers && hw != KM_HIT_MISS && (hw & KM_HIT_LIST)) ? hw | (owner << KM_PEER_SHIFT) : hw;
+    if (!db.n_peers || hw == KM_HIT_MISS || !(hw & KM_HIT_LIST)) return hw;
+    const uint32_t base = __ldg(&db.peers[owner].pool_base);
+    return base == KM_PEER_NO_BASE ? hw | (owner << KM_PEER_SHIFT) : KM_HIT_LIST | (base + (hw & 0x7FFFFFFFu));
 }
 __device__ __forceinline__ uint32_t km_probe_x(const KmDbDev &db, uint64_t x, uint32_t &extra, int d0 = 0) {
     const uint64_t home = x >> db.rem_bits;

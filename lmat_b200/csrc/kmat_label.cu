@@ -1025,6 +1025,7 @@ struct kmat_ctx {
     uint32_t *d_bigq = nullptr; unsigned int *d_bigcnt = nullptr;
     unsigned char *d_big3 = nullptr, *d_big4 = nullptr; uint64_t cap_big3 = 0; uint32_t big_np_cap = 0, big_threads3 = 0;
     KmPeer *d_peers = nullptr; uint32_t n_peers = 0; std::vector<void *> ipc_mapped;
+    uint32_t *d_pool2_all = nullptr;                                  // every shard's resolved pool, concatenated (list hits stay local)
     uint32_t *d_peer_recs = nullptr; uint64_t cap_peer_recs = 0;      // list records of the pass copied from their owners (km_peer_fetch_kernel)
     unsigned long long *d_peer_cur = nullptr;                         // [0] words used (per pass), [1] list hits dropped for lack of room (monotonic)
     unsigned long long peer_dropped_seen = 0; int peer_grow = 1;
@@ -1035,7 +1036,7 @@ struct kmat_ctx {
     int collect_stats = 1;
     kmat_batch_stats last{};
     int cand_grid[3] = {0, 0, 0};   // persistent grids of km_cand_kernel<5>, <10>, <0> (warp per read)
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around the three kernels of the last batch
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // around the three kernels of the last batch; [4]: before the direct-mode list fetch
 };
 
 template <typename T>
@@ -1118,7 +1119,7 @@ extern "C" int kmat_ctx_create(const kmat_db *db, const kmat_inputs *in, const k
     KM_CUDA(cudaStreamCreateWithFlags(&c->st_aux, cudaStreamNonBlocking));
     KM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)); KM_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (auto &e : c->ev_sub) KM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (int i = 0; i < 4; i++) KM_CUDA(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 5; i++) KM_CUDA(cudaEventCreate(&c->ev[i]));
     for (auto &sl : c->slot) {
         KM_CUDA(cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
         KM_CUDA(cudaEventCreateWithFlags(&sl.ev_comp, cudaEventDisableTiming));
@@ -1160,7 +1161,7 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
     }
     km_shard_free(c->shard);
     for (void *p : c->ipc_mapped) cudaIpcCloseMemHandle(p);
-    cudaFree(c->d_peers); cudaFree(c->d_peer_recs); cudaFree(c->d_peer_cur);
+    cudaFree(c->d_peers); cudaFree(c->d_peer_recs); cudaFree(c->d_peer_cur); cudaFree(c->d_pool2_all);
     cudaFree(c->d_bigq); cudaFree(c->d_bigcnt); cudaFree(c->d_big3); cudaFree(c->d_big4);
     cudaFree(c->d_null_max); cudaFree(c->d_null_cnt); cudaFree(c->d_null_err); cudaFree(c->d_null_bases); cudaFree(c->d_null_offs);
     cudaFree(c->d_hit); cudaFree(c->d_hdr); cudaFree(c->d_out_dev);
@@ -1172,7 +1173,7 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
     for (auto &e : c->ev_sub) if (e) cudaEventDestroy(e);
     cudaFree(c->d_cands); cudaFree(c->d_lin); cudaFree(c->d_cursors); cudaFree(c->d_pool2); cudaFree(c->d_long_masks); cudaFree(c->d_long_sets); cudaFree(c->d_stats);
     if (c->stream) cudaStreamDestroy(c->stream);
-    for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
 }
 
@@ -1322,7 +1323,7 @@ static int km_run_device(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
     int S = c->pipeline;
     if (S < 0) S = (variant == 0 && L.n_reads >= (1u << 19)) ? 8 : 1;
     if (variant != 0 || S < 1 || c->d_peers) S = 1;
-    if (c->d_peers && (rc = km_peer_prepare(c, L, st)) != KMAT_OK) return rc;
+    if (c->d_peers && !c->d_pool2_all && (rc = km_peer_prepare(c, L, st)) != KMAT_OK) return rc;
     if (S > 16) S = 16;
     const bool piped = S > 1;
     KM_CUDA(cudaEventRecord(c->ev[0], st));
@@ -1337,11 +1338,25 @@ static int km_run_device(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
         cudaStream_t s2 = st;
         if (piped) { KM_CUDA(cudaEventRecord(c->ev_sub[sb], st)); KM_CUDA(cudaStreamWaitEvent(c->st_aux, c->ev_sub[sb], 0)); s2 = c->st_aux; }
         else KM_CUDA(cudaEventRecord(c->ev[1], st));
+        if (c->d_peers && c->d_pool2_all) {
+            // direct sharded mode with a local copy of every shard's list pool: the hit words already point into it
+            if (!piped) KM_CUDA(cudaEventRecord(c->ev[1], st));
+            if ((rc = km_launch_cand_score(c, L, r0, n, hit, variant, 0, s2, c->d_pool2_all, c->pool2_mul, c->ev[3])) != KMAT_OK) return rc;
+            continue;
+        }
         if (c->d_peers) {
             // direct sharded mode: the list records the hits point at live in their owners' pools; copy them next to the
             // batch (many remote reads in flight) so that K3 only touches local memory
+            KM_CUDA(cudaEventRecord(c->ev[4], st));
             if ((rc = km_peer_fetch(c, L, st)) != KMAT_OK) return rc;
             KM_CUDA(cudaEventRecord(c->ev[1], st));
+            if (getenv("KMAT_DEBUG_TIMING")) {              // debugging aid: split of the probe time (synchronises)
+                KM_CUDA(cudaEventSynchronize(c->ev[1]));
+                float a = 0, b = 0; unsigned long long cur[2] = {0, 0};
+                cudaEventElapsedTime(&a, c->ev[0], c->ev[4]); cudaEventElapsedTime(&b, c->ev[4], c->ev[1]);
+                cudaMemcpy(cur, c->d_peer_cur, 16, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[kmat dev %d] probe %.2f ms, list fetch %.2f ms, %llu record words, %llu dropped\n", c->device, a, b, cur[0], cur[1]);
+            }
             if ((rc = km_launch_cand_score(c, L, r0, n, hit, variant, 0, s2, c->d_peer_recs, 1, c->ev[3])) != KMAT_OK) return rc;
             continue;
         }

@@ -353,7 +353,7 @@ extern "C" int kmat_ctx_peer_attach(kmat_ctx *c, int n_shards, const kmat_peer_i
             kmat_set_error("kmat_ctx_peer_attach: shard %d's context was created with different options (-g / -s / rkmer)", s); return KMAT_ERR_ARG; }
         if (b.pool_words > (1ull << KM_PEER_SHIFT)) { kmat_set_error("kmat_ctx_peer_attach: shard %d's list pool (%llu words) exceeds the 2^%d-word offset range of direct mode", s, (unsigned long long)b.pool_words, KM_PEER_SHIFT); return KMAT_ERR_UNSUPPORTED; }
         KmPeer &p = peers[(size_t)s];
-        p.n_stash = b.n_stash; p.pad = 0;
+        p.n_stash = b.n_stash; p.pool_base = KM_PEER_NO_BASE;
         if (s == db->shard_index) {
             p.slots = db->d_slots; p.stash_x = db->d_stash_x; p.stash_hit = db->d_stash_hit; p.pool2 = c->d_pool2;
         } else if (b.pid == me) {
@@ -380,6 +380,31 @@ extern "C" int kmat_ctx_peer_attach(kmat_ctx *c, int n_shards, const kmat_peer_i
             p.stash_x = nullptr; p.stash_hit = nullptr; p.pool2 = nullptr;
             if (b.n_stash) { if ((rc = open(b.h_stash_x, (const void **)&p.stash_x)) != KMAT_OK) return rc; if ((rc = open(b.h_stash_hit, (const void **)&p.stash_hit)) != KMAT_OK) return rc; }
             if (b.p_pool2) { if ((rc = open(b.h_pool2, (const void **)&p.pool2)) != KMAT_OK) return rc; }
+        }
+    }
+    // List records.  Default: copy every shard's resolved pool into one local pool (a bulk NVLink copy, once) -- list
+    // hits then never leave the GPU again; the hit words carry offsets into the concatenation.  When the pools together
+    // are too large for that (KMAT_PEER_LISTS=fetch forces it), list hits are tagged with their owner instead and the
+    // records of every pass are fetched from the owners (km_peer_fetch_kernel).
+    {
+        uint64_t total_raw = 0;
+        std::vector<uint64_t> raw(n_shards);
+        for (int s = 0; s < n_shards; s++) { KmPeerBlob b; memcpy(&b, &all[s], sizeof b); raw[s] = b.pool_words; total_raw += b.pool_words; }
+        size_t free_b = 0, total_b = 0;
+        KM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t bytes = (total_raw * (uint64_t)c->pool2_mul + 64) * 4;
+        const char *mode = getenv("KMAT_PEER_LISTS");
+        bool replicate = total_raw > 0 && total_raw < (1ull << 31) && bytes < free_b / 4;
+        if (mode && strcmp(mode, "fetch") == 0) replicate = false;
+        if (mode && strcmp(mode, "replicate") == 0 && total_raw > 0 && total_raw < (1ull << 31)) replicate = true;
+        if (replicate) {
+            KM_CUDA(cudaMalloc((void **)&c->d_pool2_all, bytes));
+            uint64_t at = 0;
+            for (int s = 0; s < n_shards; s++) {
+                if (raw[s]) KM_CUDA(cudaMemcpy(c->d_pool2_all + at * c->pool2_mul, peers[(size_t)s].pool2, raw[s] * (uint64_t)c->pool2_mul * 4, cudaMemcpyDefault));
+                peers[(size_t)s].pool_base = (uint32_t)at;
+                at += raw[s];
+            }
         }
     }
     KM_CUDA(cudaMalloc((void **)&c->d_peers, peers.size() * sizeof(KmPeer)));

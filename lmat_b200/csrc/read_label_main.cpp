@@ -215,15 +215,37 @@ int main(int argc, char *argv[]) {
         std::vector<std::thread> up;
         std::vector<int> urc(devs.size(), 0);
         std::vector<std::string> uerr(devs.size());
+        // KMAT_TABLE_MODE=sharded (or a table that one GPU cannot hold): GPU d keeps the k-mers with kmat_shard_of() == d
+        // and every GPU maps the others' shards (peer access over NVLink); the probe kernel then reads each bucket from
+        // its owner.  Default: the whole table on every GPU.
+        const char *tm = getenv("KMAT_TABLE_MODE");
+        bool split = tm && strcmp(tm, "sharded") == 0;
+        if (!tm && devs.size() > 1) {
+            uint64_t free_b = 0, total_b = 0;
+            if (kmat_device_memory(devs[0], &free_b, &total_b) == KMAT_OK) {
+                const double need = 36.0 * (double)kmat_table_size(table) * 1.2;          // ~32 B of bucket + list pool share per k-mer, + batches
+                if (need > (double)free_b) { split = true; std::cout << "Table does not fit one GPU (" << need / 1e9 << " GB needed): sharding it over " << devs.size() << " GPUs" << std::endl; }
+            }
+        }
+        if (split && devs.size() > 16) { std::cerr << "ERROR! at most 16 table shards" << std::endl; return -1; }
+        const int n_sh = split ? (int)devs.size() : 1;
         for (size_t d = 0; d < devs.size(); d++)
             up.emplace_back([&, d] {
-                urc[d] = kmat_db_upload(table, devs[d], 0, 1, &dbs[d]);
+                urc[d] = kmat_db_upload(table, devs[d], split ? (int)d : 0, n_sh, &dbs[d]);
                 if (urc[d] == KMAT_OK) urc[d] = kmat_ctx_create(dbs[d], inputs, &opt, &ctxs[d]);
                 if (urc[d] != KMAT_OK) uerr[d] = kmat_last_error();
             });
         for (auto &t : up) t.join();
         for (size_t d = 0; d < devs.size(); d++)
             if (urc[d] != KMAT_OK) { std::cerr << "ERROR! device " << devs[d] << ": " << uerr[d] << std::endl; return -1; }
+        if (split && n_sh > 1) {
+            std::vector<kmat_peer_info> blobs(devs.size());
+            for (size_t d = 0; d < devs.size(); d++)
+                if (kmat_ctx_peer_export(ctxs[d], &blobs[d]) != KMAT_OK) { std::cerr << "ERROR! device " << devs[d] << ": " << kmat_last_error() << std::endl; return -1; }
+            for (size_t d = 0; d < devs.size(); d++)
+                if (kmat_ctx_peer_attach(ctxs[d], n_sh, blobs.data()) != KMAT_OK) { std::cerr << "ERROR! device " << devs[d] << ": " << kmat_last_error() << std::endl; return -1; }
+            std::cout << "Table sharded over " << n_sh << " GPUs (direct peer reads)" << std::endl;
+        }
     }
     kmat_table_free(table);
     const auto t_query = std::chrono::steady_clock::now();

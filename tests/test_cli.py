@@ -150,3 +150,17 @@ def test_cli_multi_file_output_is_same_multiset(golden_small, cli, flat_dbs, tmp
             out += [m.group(1), m.group(2)] if m else [ln]
         return sorted(x for x in out if x)
     assert records(got) == records(want)
+
+
+@pytest.mark.gpu
+def test_cli_sharded_table_mode(golden_lists, cli, flat_dbs, tmp_path):
+    """KMAT_TABLE_MODE=sharded: each worker holds one shard and reads the others' buckets through the peer table (here
+    three workers on the same device); the records are the reference's, as a multiset over the workers' batches."""
+    g = golden_lists
+    ofb = str(tmp_path / "rl_")
+    args = ref_args(g, S.OPTION_SETS["run_rl"], flat_dbs[g.name], g.paths["reads"], ofb, 1)
+    p = run_cli(cli, args, env={"LMAT_DIR": g.workdir, "KMAT_TABLE_MODE": "sharded", "KMAT_DEVICES": "0,0,0", "KMAT_BATCH_READS": "50"})
+    assert p.returncode == 0, p.stderr
+    assert "Table sharded over 3 GPUs" in p.stdout
+    assert open(ofb + "0.out", encoding="latin-1").read() == g.golden_out("run_rl")      # -t 1: one writer, input order
+    assert open(ofb + ".0.30.fastsummary").read() == g.golden_file("run_rl.fastsummary")

@@ -89,10 +89,12 @@ def test_sharded_single_rank_is_a_plain_pass(golden_small):
     assert mine == g.golden_out("run_rl")
 
 
+@pytest.mark.parametrize("lists", ["replicate", "fetch"])
 @pytest.mark.parametrize("world,opts", [(2, "run_rl"), (3, "permissive"), (3, "prune3"), (8, "run_rl")])
-def test_direct_sharded_labels_equal_replicated(golden_lists, world, opts, monkeypatch):
+def test_direct_sharded_labels_equal_replicated(golden_lists, world, opts, lists, monkeypatch):
     """Direct variant: every virtual rank maps all shards (same process, same device: plain pointers) and labels its reads
     with the ordinary kmat_label_batch; the probe kernel sends each gather to the owner shard's arrays."""
+    monkeypatch.setenv("KMAT_PEER_LISTS", lists)          # list pools copied to every rank / records fetched from their owners per pass
     monkeypatch.setenv("KMAT_TEST_TIGHT_TABLE", "1")      # nearly full shards: displaced keys and the per-shard stash are exercised too
     g = golden_lists
     t = api.Table.from_arrays(g.kmers, g.offs, g.ids, g.kmer_len, g.tid_bytes)
@@ -131,6 +133,7 @@ def test_direct_sharded_record_buffer_overflow_is_reported_and_recovers(golden_l
     res, cands, lin = ref_ctx.label(seqs)
     want = ref_ctx.tails(res, cands, lin, prn_all=True)
     ctxs = [make_ctx(g, shards[r], "run_rl") for r in range(world)]
+    monkeypatch.setenv("KMAT_PEER_LISTS", "fetch")
     sharded.attach_peers_local(ctxs)
     monkeypatch.setenv("KMAT_TEST_PEER_RECS", "16")
     import ctypes as C
