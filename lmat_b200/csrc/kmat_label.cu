@@ -24,7 +24,7 @@
 #define KMAT_ST_DEFERRED 9      // internal: queued for the slow candidate kernel
 #define KB_CBIG 512        // candidate taxids per read the slow path holds (reads beyond it: KMAT_ERR_UNSUPPORTED)
 #define KB_LBIG 1024       // lineage entries of the big scoring kernel
-#define KB_BIGQ 65536      // reads per pass the slow path takes
+#define KB_BIGQ (1u << 20)  // reads per pass the slow path takes
 
 // stored id -> node: low 30 bits nid, bit 31 = isHuman, bit 30 = dropped tid (flags folded in so that the common
 // singleton hit needs no node-record load)
@@ -57,7 +57,7 @@ struct KmScoreParams {
     unsigned long long *long_masks; uint32_t long_cap;    // per-warp position-mask scratch for reads longer than the register path
     KmStatsDev *stats;
     // slow path for reads with more than KB_CMAX candidate taxids (or more than KB_LIN lineage entries): K3 queues them
-    // in big_qa for km_cand_slow_kernel, which (like K4 on a lineage overflow) queues them in big_qb for the big scoring kernel
+    // in big_qa for km_cand_big_kernel, which (like K4 on a lineage overflow) queues them in big_qb for the big scoring kernel
     uint32_t *big_qa, *big_qb; unsigned int *big_cnt;     // big_cnt[0] / [1]: entries of big_qa / big_qb (may exceed KB_BIGQ: the excess is dropped)
     unsigned char *big_scratch3, *big_scratch4; uint32_t big_np_cap, big_threads3, big_threads4;
 };
@@ -507,14 +507,14 @@ __global__ void __launch_bounds__(KB_WARPS * 32, NCH == 5 ? 4 : 1) km_cand_kerne
             }
             if (overflow) { kb_defer_big(P, r, res, lane); continue; }
             // ---- expanded position sets: every qualifying member brings its ancestors
-            for (int j = 0; j < C1; j++) {
-                const unsigned long long aj = kb_shfl64(j < 32 ? c_anc[0] : c_anc[1], j & 31);
-                if (!aj) continue;
-                if (NCH) {
+            if (NCH) {
+                for (int j = 0; j < C1; j++) {
+                    const unsigned long long aj = kb_shfl64(j < 32 ? c_anc[0] : c_anc[1], j & 31);
+                    if (!aj) continue;
 #pragma unroll
                     for (int c = 0; c < (NCH ? NCH : 1); c++) if ((pm[c] >> j) & 1) pm[c] |= aj;
-                } else for (int p = lane; p < np; p += 32) { const unsigned long long m = gmask[p]; if ((m >> j) & 1) gmask[p] = m | aj; }
-            }
+                }
+            }                                   // NCH == 0: done in the counting sweep below, one pass over the global masks
         } else {
             for (int j = 0; j < C1; j++) {
                 const uint32_t kj = __shfl_sync(KM_FULL, j < 32 ? K.key[0] : K.key[1], j & 31);
@@ -545,11 +545,26 @@ __global__ void __launch_bounds__(KB_WARPS * 32, NCH == 5 ? 4 : 1) km_cand_kerne
                 }
             }
         } else {
+            // long reads: ONE sweep over the position masks in global scratch, 32 positions per step.  Expansion first (a
+            // closure: an ancestor's lineage is part of its descendant's, so the member order does not matter), then one
+            // ballot per candidate bit present in any of the 32 sets (neighbouring positions carry nearly the same set).
             __syncwarp();
-            for (int i = 0; i < C; i++) {
-                uint32_t cnt = 0;
-                for (int p0 = 0; p0 < np; p0 += 32) cnt += __popc(__ballot_sync(KM_FULL, p0 + lane < np && ((gmask[p0 + lane] >> i) & 1)));
-                if (lane == (i & 31)) c_hits[i >> 5] = cnt;
+            const unsigned long long qualmask = permissive ? 0ull
+                : ((unsigned long long)__ballot_sync(KM_FULL, c_anc[0] != 0ull) | ((unsigned long long)__ballot_sync(KM_FULL, c_anc[1] != 0ull) << 32));
+            for (int p0 = 0; p0 < np; p0 += 32) {
+                unsigned long long m = p0 + lane < np ? gmask[p0 + lane] : 0ull;
+                unsigned long long todo = qualmask & km_warp_or64(m);
+                while (todo) {
+                    const int j = __ffsll((long long)todo) - 1; todo &= todo - 1;
+                    const unsigned long long aj = kb_shfl64(j < 32 ? c_anc[0] : c_anc[1], j & 31);
+                    if ((m >> j) & 1) m |= aj;
+                }
+                unsigned long long u = km_warp_or64(m);
+                while (u) {
+                    const int i = __ffsll((long long)u) - 1; u &= u - 1;
+                    const uint32_t cnt = __popc(__ballot_sync(KM_FULL, (m >> i) & 1));
+                    if (lane == (i & 31)) { if (i < 32) c_hits[0] += cnt; else c_hits[1] += cnt; }
+                }
             }
         }
         // ---- hand over to the scoring kernel: (nid, hits) in taxid_lst order
@@ -831,33 +846,44 @@ __global__ void __launch_bounds__(32) km_score_big_kernel(KmScoreParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3, slow path: one THREAD per read of big_qa, candidate set and position sets in a global scratch slot, up to KB_CBIG
-// candidates.  Restates km_cand_kernel step by step (same member order, same in-place expansion); nothing here is hot:
-// about one read in ten million of the synthetic workloads, more on reads from conserved regions of real databases.
+// K3 for the reads of big_qa (more than KB_CMAX candidate taxids): one WARP per read, the candidate set (up to KB_CBIG)
+// in shared memory, the per-position candidate sets (KB_CBIG bits each) in a global scratch slot of the warp.  Same
+// steps as km_cand_kernel.  Not rare for long reads (a 10 kbp read with no relative in the table still collects ~17
+// chance hits all over the taxonomy) and for the low-complexity reads of the null-model generator.
 // ---------------------------------------------------------------------------------------------
 #define KB_BIGW (KB_CBIG / 64)
-struct KbSlow {
-    uint32_t nid[KB_CBIG], leaf[KB_CBIG], firstpos[KB_CBIG], hits[KB_CBIG];
-    unsigned long long anc[KB_CBIG][KB_BIGW];
+#define KBG_WARPS 8
+struct KbBigW {                                   // one warp's candidate set: 12 KB of shared memory (2 CTAs of 8 warps per SM)
+    uint32_t nid[KB_CBIG], leaf[KB_CBIG], key[KB_CBIG], hits[KB_CBIG], tid[KB_CBIG], spec[KB_CBIG];   // leaf: count | rank code << 30 once the node data is in
+    unsigned long long *anc;                      // [KB_CBIG][KB_BIGW] lineage sets of the qualifying members, in the warp's global scratch slot
 };
-__device__ __forceinline__ int kbs_find_or_add(KbSlow &S, int &C, uint32_t v, uint32_t pos) {
-    for (int i = 0; i < C; i++) if (S.nid[i] == v) return i;
+// find-or-append `v` (warp-uniform); returns the index or -1 when KB_CBIG is exceeded
+__device__ __forceinline__ int kbg_find_or_add(KbBigW &W, int &C, uint32_t v, int lane) {
+    for (int t = 0; t < C; t += 32) {
+        const uint32_t f = __ballot_sync(KM_FULL, t + lane < C && W.nid[t + lane] == v);
+        if (f) return t + __ffs(f) - 1;
+    }
     if (C >= KB_CBIG) return -1;
-    S.nid[C] = v; S.leaf[C] = 0; S.firstpos[C] = pos; S.hits[C] = 0;
-    for (int w = 0; w < KB_BIGW; w++) S.anc[C][w] = 0ull;
-    return C++;
+    const int idx = C++;
+    if (lane == 0) { W.nid[idx] = v; W.leaf[idx] = 0; W.key[idx] = 0xFFFFFFFFu; W.hits[idx] = 0; }
+    if (lane < KB_BIGW) W.anc[(size_t)idx * KB_BIGW + lane] = 0ull;
+    __syncwarp();
+    return idx;
 }
-__global__ void __launch_bounds__(32) km_cand_slow_kernel(KmScoreParams P) {
+__global__ void __launch_bounds__(KBG_WARPS * 32) km_cand_big_kernel(KmScoreParams P) {
+    extern __shared__ __align__(16) unsigned char kbg_smem[];
     const KmCtxDev &X = P.C;
-    const uint32_t slot = blockIdx.x * 32 + threadIdx.x, n_threads = min((uint32_t)gridDim.x * 32, P.big_threads3);
-    if (slot >= P.big_threads3) return;
-    const size_t slot_bytes = sizeof(KbSlow) + (size_t)P.big_np_cap * KB_BIGW * 8;
-    KbSlow &S = *(KbSlow *)(P.big_scratch3 + (size_t)slot * slot_bytes);
-    unsigned long long *mask = (unsigned long long *)(P.big_scratch3 + (size_t)slot * slot_bytes + sizeof(KbSlow));
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t warp_global = blockIdx.x * KBG_WARPS + wib, n_warps = min((uint32_t)gridDim.x * KBG_WARPS, P.big_threads3);
+    if (warp_global >= P.big_threads3) return;
+    KbBigW &W = *(KbBigW *)(kbg_smem + (size_t)wib * sizeof(KbBigW));
+    unsigned long long *gmask = (unsigned long long *)P.big_scratch3 + (size_t)warp_global * ((size_t)P.big_np_cap + KB_CBIG) * KB_BIGW;
+    if (lane == 0) W.anc = gmask + (size_t)P.big_np_cap * KB_BIGW;
+    __syncwarp();
     const int k = X.db.kmer_len;
     const bool permissive = X.opt.permissive != 0;
     const uint32_t nq = min(P.big_cnt[0], (unsigned int)KB_BIGQ);
-    for (uint32_t q = slot; q < nq; q += n_threads) {
+    for (uint32_t q = warp_global; q < nq; q += n_warps) {
         const uint32_t r = P.big_qa[q];
         const uint64_t off = P.offs[r];
         const int len = (int)(P.offs[r + 1] - off);
@@ -866,117 +892,187 @@ __global__ void __launch_bounds__(32) km_cand_slow_kernel(KmScoreParams P) {
         kmat_read_result res;
         memset(&res, 0, sizeof res);
         res.valid_kmers = hd.x; res.bin_sel = hd.y; res.match = KMAT_NOMATCH;
-        if (np <= 0 || (uint32_t)np > P.big_np_cap) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; P.out[r] = res; continue; }
+        if (np <= 0 || (uint32_t)np > P.big_np_cap || np > 0xFFFF) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; if (lane == 0) P.out[r] = res; continue; }
         int C = 0, cand_cnt = 0, fnd_cnt = 0, err = 0;
         bool overflow = false;
-        // ---- per position: members in insertion order (kb_chunk)
-        for (int p = 0; p < np && !overflow && !err; p++) {
-            unsigned long long *m = mask + (size_t)p * KB_BIGW;
-            for (int w = 0; w < KB_BIGW; w++) m[w] = 0ull;
-            const uint32_t hw = P.hit[off + p];
-            if (hw == KM_HIT_INVALID) continue;
-            cand_cnt++;
+        // ---- per position: members in insertion order (kb_chunk with the set in shared memory)
+        const int nch = (np + 31) >> 5;
+        for (int c = 0; c < nch && !overflow; c++) {
+            const int p = (c << 5) + lane;
+            const uint32_t hw = p < np ? __ldg(P.hit + off + p) : KM_HIT_INVALID;
+            unsigned long long *mym = gmask + (size_t)p * KB_BIGW;
+            if (p < np) for (int w = 0; w < KB_BIGW; w++) mym[w] = 0ull;
             uint32_t a = 0, b = 0, v0 = KMAT_NONE;
             const uint32_t *rec = nullptr;
-            if (hw != KM_HIT_MISS) {
-                if (!(hw & KM_HIT_LIST)) {
-                    const uint32_t e = hw < X.n_sid ? X.sid2nid[hw] : KMAT_NONE;
-                    if (e == KMAT_NONE) { err = KMAT_ERR_BAD_TAXID; break; }
-                    if (!(e & KB_SID_DROP)) {
-                        v0 = ((e & KB_SID_HUMAN) && !X.opt.rkmer_mode) ? X.nid_human : (e & KB_SID_NIDMASK); a = 1;
-                        if (permissive) b = (kb_nodeA(X, v0).meta & KM_META_DEPTH_MASK) ? 1 : 0;
+            if (hw != KM_HIT_INVALID) {
+                cand_cnt++;
+                if (hw != KM_HIT_MISS) {
+                    if (!(hw & KM_HIT_LIST)) {
+                        const uint32_t e = hw < X.n_sid ? __ldg(X.sid2nid + hw) : KMAT_NONE;
+                        if (e == KMAT_NONE) err = KMAT_ERR_BAD_TAXID;
+                        else if (!(e & KB_SID_DROP)) {
+                            v0 = ((e & KB_SID_HUMAN) && !X.opt.rkmer_mode) ? X.nid_human : (e & KB_SID_NIDMASK); a = 1;
+                            if (permissive) b = (kb_nodeA(X, v0).meta & KM_META_DEPTH_MASK) ? 1 : 0;
+                        }
+                    } else {
+                        rec = kb_rec_of(X, hw);
+                        const uint32_t h = __ldg(rec);
+                        if (h == KR_ERR_BAD) { err = KMAT_ERR_BAD_TAXID; rec = nullptr; }
+                        else { a = h & 0xFFFFu; if (permissive) { b = rec[1]; rec += 2; } else rec += 1; }
                     }
-                } else {
-                    rec = kb_rec_of(X, hw);
-                    const uint32_t h = rec[0];
-                    if (h == KR_ERR_BAD) { err = KMAT_ERR_BAD_TAXID; break; }
-                    a = h & 0xFFFFu;
-                    if (permissive) { b = rec[1]; rec += 2; } else rec += 1;
                 }
             }
             if (a) fnd_cnt++;
-            for (uint32_t sq = 0; sq < a && !overflow; sq++) {
-                const int idx = kbs_find_or_add(S, C, rec ? rec[sq] : v0, (uint32_t)p);
-                if (idx < 0) { overflow = true; break; }
-                S.leaf[idx]++; m[idx >> 6] |= 1ull << (idx & 63);
-            }
-            for (uint32_t bi = 0; bi < b && !overflow; bi++) {               // permissive: root paths of the deepest ids
-                const KmNodeB nb = kb_nodeB(X, rec ? rec[a + bi] : v0);
-                for (uint32_t pq = 0; pq < nb.path_len; pq++) {
-                    const int idx = kbs_find_or_add(S, C, X.paths[nb.path_off + pq], (uint32_t)p);
-                    if (idx < 0) { overflow = true; break; }
-                    S.leaf[idx]++; m[idx >> 6] |= 1ull << (idx & 63);
-                }
-            }
-        }
-        if (err) { res.status = KMAT_ST_ERROR; res.err = err; P.out[r] = res; continue; }
-        if (overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; P.out[r] = res; continue; }
-        const int C1 = C;
-        if (C1 == 0) { res.status = KMAT_ST_NODBHITS; res.n1 = len; res.n2 = k; P.out[r] = res; continue; }
-        const uint16_t cand16 = (uint16_t)cand_cnt;
-        res.cand_kmer_cnt = cand16;
-        if (fnd_cnt < X.opt.min_fnd_kmer || (int)cand16 < X.opt.min_kmer) { res.status = KMAT_ST_SILENT; res.match = KMAT_NOMATCH; res.tid = 0; res.score = -1.0f; P.out[r] = res; continue; }
-        if (!permissive) {
-            // ---- representative strain per species, then the lineage of every qualifying member in (first position, taxid)
-            //      order; S.hits doubles as the "done" marker of that selection sort until the counts are taken
+            uint32_t seqno = 0, bi = 0, pq = 0, poff = 0, plen = 0;
             for (;;) {
-                int best = -1; unsigned long long bkey = ~0ull;
-                for (int s2 = 0; s2 < C1; s2++) {
-                    if (S.hits[s2]) continue;
-                    const KmNodeA na = kb_nodeA(X, S.nid[s2]);
-                    const unsigned long long key = ((unsigned long long)S.firstpos[s2] << 32) | na.tid;
-                    if (key < bkey) { bkey = key; best = s2; }
-                }
-                if (best < 0) break;
-                S.hits[best] = 1;
-                const KmNodeA na = kb_nodeA(X, S.nid[best]);
-                const bool strain = ((na.meta >> KM_META_RANK_SHIFT) & 3) == 1;
-                bool qual = !strain;
-                if (strain && na.species_anc != KMAT_NONE) {
-                    bool beaten = false;
-                    for (int j = 0; j < C1 && !beaten; j++) {
-                        const KmNodeA nj = kb_nodeA(X, S.nid[j]);
-                        beaten = ((nj.meta >> KM_META_RANK_SHIFT) & 3) == 1 && nj.species_anc == na.species_anc &&
-                                 (S.leaf[j] > S.leaf[best] || (S.leaf[j] == S.leaf[best] && nj.tid < na.tid));
+                uint32_t val = KMAT_NONE;
+                if (seqno < a) val = rec ? rec[seqno] : v0;
+                else if (permissive) {
+                    while (bi < b && pq >= plen) {
+                        const KmNodeB nb = kb_nodeB(X, rec ? rec[a + bi] : v0);
+                        poff = nb.path_off; plen = nb.path_len; pq = 0; bi++;
                     }
-                    qual = !beaten;
+                    if (pq < plen) val = X.paths[poff + pq++];
                 }
-                if (!qual) continue;
-                const KmNodeB nb = kb_nodeB(X, S.nid[best]);
-                for (uint32_t pq = 0; pq < nb.path_len; pq++) {
-                    const int idx = kbs_find_or_add(S, C, X.paths[nb.path_off + pq], 0xFFFFFFFFu);
+                uint32_t pending = __ballot_sync(KM_FULL, val != KMAT_NONE);
+                if (!pending) break;
+                while (pending) {
+                    const int leader = __ffs(pending) - 1;
+                    const uint32_t v = __shfl_sync(KM_FULL, val, leader);
+                    const uint32_t grp = __ballot_sync(KM_FULL, val == v);
+                    const int idx = kbg_find_or_add(W, C, v, lane);
                     if (idx < 0) { overflow = true; break; }
-                    S.anc[best][idx >> 6] |= 1ull << (idx & 63);
+                    if (lane == 0) {
+                        const uint32_t key = ((uint32_t)((c << 5) + leader) << 16) | min(seqno, 0xFFFFu);
+                        W.key[idx] = min(W.key[idx], key); W.leaf[idx] += __popc(grp);
+                    }
+                    if (val == v) mym[idx >> 6] |= 1ull << (idx & 63);
+                    pending &= ~grp;
                 }
                 if (overflow) break;
+                seqno++;
             }
-            if (overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; P.out[r] = res; continue; }
-            for (int i = 0; i < C; i++) S.hits[i] = 0;
-            // ---- expanded position sets, in place and in candidate order like the warp kernel
-            for (int p = 0; p < np; p++) {
-                unsigned long long *m = mask + (size_t)p * KB_BIGW;
-                for (int j = 0; j < C1; j++) {
-                    if (!((m[j >> 6] >> (j & 63)) & 1)) continue;
-                    for (int w = 0; w < KB_BIGW; w++) m[w] |= S.anc[j][w];
+            __syncwarp();
+        }
+        cand_cnt = km_warp_sum(cand_cnt); fnd_cnt = km_warp_sum(fnd_cnt);
+        err = __reduce_max_sync(KM_FULL, err < 0 ? -err : 0);
+        overflow = __any_sync(KM_FULL, overflow);
+        if (err) { res.status = KMAT_ST_ERROR; res.err = -err; if (lane == 0) P.out[r] = res; continue; }
+        if (overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; if (lane == 0) P.out[r] = res; continue; }
+        const int C1 = C;
+        if (C1 == 0) { res.status = KMAT_ST_NODBHITS; res.n1 = len; res.n2 = k; if (lane == 0) P.out[r] = res; continue; }
+        const uint16_t cand16 = (uint16_t)cand_cnt;
+        res.cand_kmer_cnt = cand16;
+        if (fnd_cnt < X.opt.min_fnd_kmer || (int)cand16 < X.opt.min_kmer) {
+            res.status = KMAT_ST_SILENT; res.match = KMAT_NOMATCH; res.tid = 0; res.score = -1.0f;
+            if (lane == 0) P.out[r] = res;
+            continue;
+        }
+        if (!permissive) {
+            // ---- node data of the members; representative strain per species -> which members bring their lineage
+            for (int i = lane; i < C1; i += 32) {
+                const KmNodeA na = kb_nodeA(X, W.nid[i]);
+                W.tid[i] = na.tid; W.spec[i] = na.species_anc; W.leaf[i] = (W.leaf[i] & 0x3FFFFFFFu) | (((na.meta >> KM_META_RANK_SHIFT) & 3u) << 30);
+            }
+            __syncwarp();
+            for (int i = lane; i < C1; i += 32) {
+                const bool strain = (W.leaf[i] >> 30) == 1;
+                bool qual = !strain;
+                if (strain && W.spec[i] != KMAT_NONE) {
+                    bool beaten = false;                    // same rank code in the top bits of both: comparing the words compares the counts
+                    for (int j = 0; j < C1 && !beaten; j++)
+                        beaten = (W.leaf[j] >> 30) == 1 && W.spec[j] == W.spec[i] && (W.leaf[j] > W.leaf[i] || (W.leaf[j] == W.leaf[i] && W.tid[j] < W.tid[i]));
+                    qual = !beaten;
+                }
+                W.hits[i] = qual ? 1u : 0u;                 // "still to expand" marker until the counts are taken
+            }
+            __syncwarp();
+            // ---- lineage expansion in (first position, taxid) order: the appended ancestors take the next indices
+            for (;;) {
+                unsigned long long mine = ~0ull;
+                for (int i = lane; i < C1; i += 32)
+                    if (W.hits[i]) { const unsigned long long kk = ((unsigned long long)(W.key[i] >> 16) << 32) | W.tid[i]; if (kk < mine) mine = kk; }
+                const unsigned long long best = kb_warp_min64(mine);
+                if (best == ~0ull) break;
+                int s2 = -1;
+                for (int i = lane; i < C1; i += 32)
+                    if (W.hits[i] && ((((unsigned long long)(W.key[i] >> 16) << 32) | W.tid[i]) == best)) s2 = i;
+                s2 = __reduce_max_sync(KM_FULL, s2);
+                if (lane == 0) W.hits[s2] = 0;
+                const KmNodeB nb = kb_nodeB(X, W.nid[s2]);
+                for (uint32_t c0 = 0; c0 < nb.path_len && !overflow; c0 += 32) {
+                    const uint32_t av = c0 + lane < nb.path_len ? X.paths[nb.path_off + c0 + lane] : KMAT_NONE;
+                    const int cnt = min(32u, nb.path_len - c0);
+                    for (int z = 0; z < cnt; z++) {
+                        const int idx = kbg_find_or_add(W, C, __shfl_sync(KM_FULL, av, z), lane);
+                        if (idx < 0) { overflow = true; break; }
+                        if (lane == 0) W.anc[(size_t)s2 * KB_BIGW + (idx >> 6)] |= 1ull << (idx & 63);
+                    }
+                }
+                __syncwarp();
+                if (overflow) break;
+            }
+            if (overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; if (lane == 0) P.out[r] = res; continue; }
+        }
+        for (int i = lane; i < C; i += 32) W.hits[i] = 0;
+        __syncwarp();
+        // ---- expanded position sets and hits per candidate in one sweep: lane = position, 32 positions per step.  The
+        //      expansion is a closure (an ancestor's lineage is part of its descendant's), so the order of the members does
+        //      not matter.  Counting: for every candidate bit present in ANY of the 32 sets one ballot gives its count --
+        //      the sets of neighbouring positions are nearly identical, shared-memory atomics would serialise 32-fold.
+        for (int p0 = 0; p0 < np; p0 += 32) {
+            const int p = p0 + lane;
+            unsigned long long m[KB_BIGW];
+            const unsigned long long *mym = gmask + (size_t)p * KB_BIGW;
+#pragma unroll
+            for (int w = 0; w < KB_BIGW; w++) m[w] = p < np ? mym[w] : 0ull;
+            if (!permissive) {
+                unsigned long long o[KB_BIGW];
+#pragma unroll
+                for (int w = 0; w < KB_BIGW; w++) o[w] = m[w];
+#pragma unroll
+                for (int w = 0; w < KB_BIGW; w++) {
+                    unsigned long long v = o[w];
+                    while (v) {
+                        const int j = w * 64 + __ffsll((long long)v) - 1; v &= v - 1;
+                        if (j < C1) {
+#pragma unroll
+                            for (int w2 = 0; w2 < KB_BIGW; w2++) m[w2] |= W.anc[(size_t)j * KB_BIGW + w2];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < KB_BIGW; w++) {
+                unsigned long long u = km_warp_or64(m[w]);
+                while (u) {
+                    const int bit = __ffsll((long long)u) - 1; u &= u - 1;
+                    const uint32_t cnt = __popc(__ballot_sync(KM_FULL, (m[w] >> bit) & 1));
+                    if (lane == 0) W.hits[w * 64 + bit] += cnt;
                 }
             }
         }
-        // ---- hits per candidate
-        for (int p = 0; p < np; p++) {
-            const unsigned long long *m = mask + (size_t)p * KB_BIGW;
-            for (int w = 0; w < KB_BIGW; w++) {
-                unsigned long long v = m[w];
-                while (v) { const int bit = __ffsll((long long)v) - 1; v &= v - 1; S.hits[w * 64 + bit]++; }
-            }
-        }
-        // ---- hand over in taxid_lst order: first-appearance order of the members (= insertion order here), then the
-        //      ancestors in the order the expansion appended them
-        const unsigned long long co = atomicAdd(P.cand_cursor, (unsigned long long)C);
+        __syncwarp();
+        // ---- hand over in taxid_lst order: members by first appearance (rank of the key), then the appended ancestors
+        unsigned long long co = 0;
+        if (lane == 0) co = atomicAdd(P.cand_cursor, (unsigned long long)C);
+        co = kb_shfl64(co, 0);
         res.status = KMAT_ST_PENDING_BIG; res.n_cand = (uint32_t)C; res.cand_off = co;
-        if (P.cands && co + C <= P.cand_cap) { for (int i = 0; i < C; i++) P.cands[co + i] = kmat_pair{S.nid[i], __uint_as_float(S.hits[i])}; }
-        else { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_OVERFLOW; }
-        P.out[r] = res;
-        if (res.status == KMAT_ST_PENDING_BIG) { const unsigned int q2 = atomicAdd(P.big_cnt + 1, 1u); if (q2 < KB_BIGQ) P.big_qb[q2] = r; else { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; P.out[r] = res; } }
+        if (P.cands && co + C <= P.cand_cap) {
+            for (int i = lane; i < C; i += 32) {
+                uint32_t ord = (uint32_t)i;
+                if (i < C1) { ord = 0; const uint32_t ki = W.key[i]; for (int j = 0; j < C1; j++) ord += W.key[j] < ki; }
+                P.cands[co + ord] = kmat_pair{W.nid[i], __uint_as_float(W.hits[i])};
+            }
+        } else { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_OVERFLOW; }
+        if (lane == 0) {
+            if (res.status == KMAT_ST_PENDING_BIG) {
+                const unsigned int q2 = atomicAdd(P.big_cnt + 1, 1u);
+                if (q2 < KB_BIGQ) P.big_qb[q2] = r; else { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; }
+            }
+            P.out[r] = res;
+        }
+        __syncwarp();
     }
 }
 
@@ -1261,7 +1357,7 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
     P.stats = c->collect_stats ? c->d_stats : nullptr;
     P.long_masks = nullptr; P.long_cap = 0;
     // slow path buffers (first use / longer reads than before)
-    const uint32_t KBIG_THREADS = 128;
+    const uint32_t KBIG_THREADS = 2048;            // threads (global scratch slots) of the big scoring kernel
     const uint32_t np_need = (uint32_t)std::max<int>(1, (int)L.max_len - c->db->kmer_len + 1);
     if (!c->d_bigq) {
         KM_CUDA(cudaMalloc((void **)&c->d_bigq, (size_t)2 * KB_BIGQ * 4));
@@ -1269,8 +1365,10 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
         KM_CUDA(cudaMalloc((void **)&c->d_big4, (size_t)KBIG_THREADS * sizeof(KsLocalBig)));
     }
     if (np_need > c->big_np_cap) {
-        const size_t per = sizeof(KbSlow) + (size_t)np_need * KB_BIGW * 8;
-        uint32_t threads = (uint32_t)std::min<size_t>(KBIG_THREADS, std::max<size_t>(1, ((size_t)512 << 20) / per));
+        const size_t per = ((size_t)np_need + KB_CBIG) * KB_BIGW * 8;                       // one warp's position sets + lineage sets
+        uint32_t threads = (uint32_t)std::min<size_t>((size_t)c->sms * KBG_WARPS * 2, std::max<size_t>(1, ((size_t)1 << 30) / per));
+        static bool attr_set = false;
+        if (!attr_set) { KM_CUDA(cudaFuncSetAttribute(km_cand_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KBG_WARPS * sizeof(KbBigW)))); attr_set = true; }
         KM_CUDA(cudaStreamSynchronize(s2));
         int rc3 = km_grow(&c->d_big3, &c->cap_big3, (uint64_t)per * threads);
         if (rc3 != KMAT_OK) return rc3;
@@ -1290,7 +1388,7 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     // the (rare) reads K3 could not hold in registers; an empty queue costs two tiny launches
-    km_cand_slow_kernel<<<(c->big_threads3 + 31) / 32, 32, 0, s2>>>(P);
+    km_cand_big_kernel<<<(c->big_threads3 + KBG_WARPS - 1) / KBG_WARPS, KBG_WARPS * 32, KBG_WARPS * sizeof(KbBigW), s2>>>(P);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     if (ev_mid) KM_CUDA(cudaEventRecord(ev_mid, s2));
