@@ -11,6 +11,7 @@ struct KmGeneParams {
     const uint32_t *hit;
     kmat_gene_result *out;
     const uint32_t *stored;        // dense id -> stored id for 32-bit tables (NULL: the id is the stored id)
+    uint32_t *big_q; unsigned int *big_cnt; uint32_t big_cap;     // reads with more than KB_CMAX genes: queued for km_gene_big_kernel
 };
 struct KgCountDesc {
     __device__ bool operator()(const uint2 &a, const uint2 &b) const { return a.y > b.y; }
@@ -68,7 +69,14 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_gene_kernel(KmGeneParams P) 
         cnt = km_warp_sum(cnt);
         overflow = __any_sync(KM_FULL, overflow) || np > 0xFFFF;           // first-appearance keys hold 16-bit positions
         res.valid_kmers = (uint32_t)cnt; res.n_genes = (uint32_t)C;
-        if (overflow) { res.status = KMAT_ERR_UNSUPPORTED; if (lane == 0) P.out[r] = res; continue; }
+        if (overflow) {                                                    // more than 64 genes (or a very long read): the big kernel takes it
+            res.status = KMAT_ERR_UNSUPPORTED;
+            if (lane == 0) {
+                if (P.big_q) { const unsigned int q = atomicAdd(P.big_cnt, 1u); if (q < P.big_cap) P.big_q[q] = r; }
+                P.out[r] = res;
+            }
+            continue;
+        }
         if (C == 0) { if (lane == 0) P.out[r] = res; continue; }           // geneid_lst.empty(): nothing is printed (:309-312)
         // geneid_lst order = rank of the first-appearance key
         uint32_t ord[2] = {0, 0};
@@ -91,6 +99,89 @@ __global__ void __launch_bounds__(KB_WARPS * 32) km_gene_kernel(KmGeneParams P) 
     }
 }
 
+// The reads km_gene_kernel could not hold in registers: one warp per read, up to KG_CBIG distinct genes in shared memory
+// (id, first-appearance key, count), same member walk, same final std::sort.
+#define KG_CBIG 1024
+#define KG_WARPS 8
+struct KgBigW { uint32_t gid[KG_CBIG], cnt[KG_CBIG]; unsigned long long key[KG_CBIG]; uint2 sorted[KG_CBIG]; };     // 24 KB per warp
+__global__ void __launch_bounds__(KG_WARPS * 32) km_gene_big_kernel(KmGeneParams P) {
+    extern __shared__ __align__(16) unsigned char kg_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    KgBigW &W = *(KgBigW *)(kg_smem + (size_t)wib * sizeof(KgBigW));
+    const uint32_t warp_global = blockIdx.x * KG_WARPS + wib, n_warps = gridDim.x * KG_WARPS;
+    const int k = P.db.kmer_len;
+    const uint32_t nq = min(*P.big_cnt, P.big_cap);
+    for (uint32_t q = warp_global; q < nq; q += n_warps) {
+        const uint32_t r = P.big_q[q];
+        const uint64_t off = P.offs[r];
+        const int len = (int)(P.offs[r + 1] - off);
+        const int np = len - k + 1;
+        kmat_gene_result res;
+        res.status = 0; res.valid_kmers = 0; res.n_genes = 0; res.gene = 0; res.count = 0; res.score = 0.0f;
+        int C = 0, cnt = 0;
+        bool overflow = false;
+        const int nch = (np + 31) >> 5;
+        for (int c = 0; c < nch && !overflow; c++) {
+            const int p = (c << 5) + lane;
+            const uint32_t hw = p < np ? __ldg(P.hit + off + p) : KM_HIT_INVALID;
+            uint32_t a = 0, lo = 0;
+            if (hw != KM_HIT_INVALID) {
+                cnt++;
+                if (hw != KM_HIT_MISS) { if (hw & KM_HIT_LIST) { lo = hw & 0x7FFFFFFFu; a = kb_list_count(P.db, lo); } else a = 1; }
+            }
+            for (uint32_t seqno = 0;; seqno++) {
+                uint32_t val = KMAT_NONE;
+                if (seqno < a) val = (hw & KM_HIT_LIST) ? kb_list_id(P.db, lo, seqno) : hw;
+                uint32_t pending = __ballot_sync(KM_FULL, val != KMAT_NONE);
+                if (!pending) break;
+                while (pending) {
+                    const int leader = __ffs(pending) - 1;
+                    const uint32_t v = __shfl_sync(KM_FULL, val, leader);
+                    const uint32_t grp = __ballot_sync(KM_FULL, val == v);
+                    int idx = -1;
+                    for (int t = 0; t < C && idx < 0; t += 32) {
+                        const uint32_t f = __ballot_sync(KM_FULL, t + lane < C && W.gid[t + lane] == v);
+                        if (f) idx = t + __ffs(f) - 1;
+                    }
+                    if (idx < 0) {
+                        if (C >= KG_CBIG) { overflow = true; break; }
+                        idx = C++;
+                        if (lane == 0) { W.gid[idx] = v; W.cnt[idx] = 0; W.key[idx] = ~0ull; }
+                        __syncwarp();
+                    }
+                    if (lane == 0) {
+                        const unsigned long long key = ((unsigned long long)((c << 5) + leader) << 32) | seqno;
+                        if (key < W.key[idx]) W.key[idx] = key;
+                        W.cnt[idx] += __popc(grp);
+                    }
+                    pending &= ~grp;
+                }
+                if (overflow) break;
+            }
+            __syncwarp();
+        }
+        cnt = km_warp_sum(cnt);
+        overflow = __any_sync(KM_FULL, overflow);
+        res.valid_kmers = (uint32_t)cnt; res.n_genes = (uint32_t)C;
+        if (overflow) { res.status = KMAT_ERR_UNSUPPORTED; if (lane == 0) P.out[r] = res; continue; }
+        if (C == 0) { if (lane == 0) P.out[r] = res; continue; }
+        for (int i = lane; i < C; i += 32) {                                   // geneid_lst order = rank of the first-appearance key
+            uint32_t ord = 0;
+            const unsigned long long ki = W.key[i];
+            for (int j = 0; j < C; j++) ord += W.key[j] < ki;
+            W.sorted[ord] = make_uint2(P.stored ? P.stored[W.gid[i]] : W.gid[i], W.cnt[i]);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            kmstd::sort(W.sorted, C, KgCountDesc());
+            res.status = 1; res.gene = W.sorted[0].x; res.count = W.sorted[0].y;
+            res.score = __fdiv_rn((float)res.count, (float)cnt);
+            P.out[r] = res;
+        }
+        __syncwarp();
+    }
+}
+
 extern "C" int kmat_gene_batch(const kmat_db *db, const char *bases, const uint64_t *offs, uint32_t n_reads, kmat_gene_result *out) {
     if (!db || !offs || !out || (n_reads && !bases)) { kmat_set_error("kmat_gene_batch: bad argument"); return KMAT_ERR_ARG; }
     if (kmat_device_count() <= db->device) { kmat_set_error("CUDA device %d not available", db->device); return KMAT_ERR_NO_DEVICE; }
@@ -102,7 +193,14 @@ extern "C" int kmat_gene_batch(const kmat_db *db, const char *bases, const uint6
     unsigned long long *d_long = nullptr; uint32_t long_slots = 0;
     uint64_t cap_b = 0; uint32_t cap_r = 0;
     int rc = KMAT_OK;
-    auto cleanup = [&] { cudaFree(d_b); cudaFree(d_o); cudaFree(d_hit); cudaFree(d_hdr); cudaFree(d_out); cudaFree(d_long); };
+    uint32_t *d_bigq = nullptr; unsigned int *d_bigcnt = nullptr;
+    const uint32_t bigq_cap = chunk_reads;
+    if (cudaMalloc((void **)&d_bigq, (size_t)bigq_cap * 4) != cudaSuccess || cudaMalloc((void **)&d_bigcnt, 4) != cudaSuccess) {
+        cudaFree(d_bigq); cudaGetLastError(); kmat_set_error("kmat_gene_batch: out of device memory"); return KMAT_ERR_NOMEM;
+    }
+    static bool big_attr = false;
+    if (!big_attr) { KM_CUDA(cudaFuncSetAttribute(km_gene_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * sizeof(KgBigW)))); big_attr = true; }
+    auto cleanup = [&] { cudaFree(d_b); cudaFree(d_o); cudaFree(d_hit); cudaFree(d_hdr); cudaFree(d_out); cudaFree(d_long); cudaFree(d_bigq); cudaFree(d_bigcnt); };
     for (uint32_t r0 = 0; r0 < n_reads && rc == KMAT_OK;) {
         uint32_t r1 = (uint32_t)std::min<uint64_t>(n_reads, (uint64_t)r0 + chunk_reads);
         while (r1 > r0 + 1 && offs[r1] - offs[r0] > chunk_bases) r1 = r0 + (r1 - r0) / 2;
@@ -128,7 +226,11 @@ extern "C" int kmat_gene_batch(const kmat_db *db, const char *bases, const uint6
         if (rc != KMAT_OK) break;
         KmGeneParams P;
         P.db = km_db_dev(db); P.offs = d_o; P.n_reads = n; P.hit = d_hit; P.out = d_out; P.stored = db->d_stored_tids;
+        P.big_q = d_bigq; P.big_cnt = d_bigcnt; P.big_cap = bigq_cap;
+        if (cudaMemsetAsync(d_bigcnt, 0, 4) != cudaSuccess) { rc = KMAT_ERR_CUDA; break; }
         km_gene_kernel<<<std::max(1u, std::min((n + KB_WARPS - 1) / KB_WARPS, 148u * 4)), KB_WARPS * 32>>>(P);
+        g_km_launches++;
+        km_gene_big_kernel<<<148, KG_WARPS * 32, KG_WARPS * sizeof(KgBigW)>>>(P);           // the reads with more than 64 genes (usually none)
         g_km_launches++;
         if (cudaMemcpy(out + r0, d_out, (size_t)n * sizeof(kmat_gene_result), cudaMemcpyDeviceToHost) != cudaSuccess) { rc = KMAT_ERR_CUDA; break; }
         r0 = r1;

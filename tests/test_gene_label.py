@@ -97,6 +97,36 @@ def test_gene_batch_equals_oracle(gene_table, gene_oracle):
 
 
 @pytest.mark.gpu
+def test_gene_batch_reads_with_many_genes(gene_table, gene_oracle):
+    """Reads stitched from many genomes hit more genes than the 64 register slots of km_gene_kernel: the big kernel
+    (up to 1024 genes in shared memory) must give the oracle's top gene, count and score."""
+    db = api.Db.upload(api.Table.from_arrays(*gene_table, 20, 4))
+    inp = S.build_inputs("small", "/tmp/kmat_gene_inputs_big")
+    gstr = [fx.codes_to_str(g) for g in inp["genomes"].values()]
+    rng = np.random.default_rng(5)
+    reads = []
+    for L, piece in [(150, 21), (2000, 21), (2000, 30), (6000, 25), (30000, 40)]:
+        for rep in range(4):
+            parts = []
+            while sum(map(len, parts)) < L:
+                gs = gstr[int(rng.integers(0, len(gstr)))]
+                a = int(rng.integers(0, len(gs) - piece))
+                parts.append(gs[a:a + piece])
+            reads.append("".join(parts)[:L])
+    reads.append(gstr[0][:150])
+    got = db.gene_label(reads)
+    want = gene_oracle.gene_label(reads)
+    assert max(n for n, *_ in want) > 64
+    assert (got["status"] >= 0).all(), got["status"]
+    for i, (n, cnt, gene, count) in enumerate(want):
+        assert got["n_genes"][i] == n and got["valid_kmers"][i] == cnt, i
+        assert got["status"][i] == (1 if n else 0)
+        if n:
+            assert got["gene"][i] == gene and got["count"][i] == count, (i, n)
+            assert got["score"][i] == np.float32(count) / np.float32(cnt)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("tag,extra", [("gene", ["-x", "0", "-q", "0", "-b", "0"]), ("gene_thr", ["-x", "0.3", "-q", "40", "-b", "0.5"])])
 def test_gene_label_cli_equals_reference(gene_table, tmp_path, tag, extra):
     build.build_all()
