@@ -25,6 +25,9 @@
 #define KB_CBIG 512        // candidate taxids per read the slow path holds (reads beyond it: KMAT_ERR_UNSUPPORTED)
 #define KB_LBIG 1024       // lineage entries of the big scoring kernel
 #define KB_BIGQ (1u << 20)  // reads per pass the slow path takes
+#define KB_PASS_SHIFT 40   // per-pass cursor: pairs in the low 40 bits, reads queued for K4 above
+#define KB_PASS_MASK ((1ull << KB_PASS_SHIFT) - 1)
+#define KB_PASS_ONE_READ (1ull << KB_PASS_SHIFT)
 
 // stored id -> node: low 30 bits nid, bit 31 = isHuman, bit 30 = dropped tid (flags folded in so that the common
 // singleton hit needs no node-record load)
@@ -53,6 +56,11 @@ struct KmScoreParams {
     const uint64_t *offs; uint32_t n_reads; const uint32_t *hit; const int2 *hdr;
     kmat_read_result *out;
     kmat_pair *cands; unsigned long long *cand_cursor; unsigned long long cand_cap;
+    // cand_cursor: pairs handed out by the passes before this one (read-only here).  pass_cursor: this pass's packed
+    // cursor -- low 40 bits pairs, high 24 bits reads queued in pend_q -- so that ONE atomic per read gives K3 both the
+    // place of its pairs and a slot in the dense queue of reads K4 has to score (km_cursor_roll_kernel folds it into
+    // cand_cursor afterwards).  pend_q == NULL: no queue, K4 walks all reads.
+    unsigned long long *pass_cursor; uint32_t *pend_q;
     kmat_pair *lin; unsigned long long *lin_cursor; unsigned long long lin_cap;
     unsigned long long *long_masks; uint32_t long_cap;    // per-warp position-mask scratch for reads longer than the register path
     KmStatsDev *stats;
@@ -375,6 +383,7 @@ __global__ void __launch_bounds__(KB_WARPS * 32, NCH == 5 ? 4 : 1) km_cand_kerne
     const int k = X.db.kmer_len;
     const bool permissive = X.opt.permissive != 0;
     unsigned long long *gmask = NCH == 0 ? P.long_masks + (size_t)warp_global * P.long_cap : nullptr;
+    const unsigned long long cand_base = *P.cand_cursor;
     unsigned long long st_list_ids = 0, st_list_sectors = 0, st_fast = 0, st_err = 0;
 
     for (uint32_t r = warp_global; r < P.n_reads; r += n_warps) {
@@ -569,8 +578,10 @@ __global__ void __launch_bounds__(KB_WARPS * 32, NCH == 5 ? 4 : 1) km_cand_kerne
         }
         // ---- hand over to the scoring kernel: (nid, hits) in taxid_lst order
         unsigned long long co = 0;
-        if (lane == 0) co = atomicAdd(P.cand_cursor, (unsigned long long)C);
+        if (lane == 0) co = atomicAdd(P.pass_cursor, (unsigned long long)C | (P.pend_q ? KB_PASS_ONE_READ : 0ull));
         co = __shfl_sync(KM_FULL, co, 0);
+        const uint32_t qi = (uint32_t)(co >> KB_PASS_SHIFT);
+        co = cand_base + (co & KB_PASS_MASK);
         res.status = KMAT_ST_PENDING; res.n_cand = (uint32_t)C; res.cand_off = co;
         if (P.cands && co + C <= P.cand_cap) {
 #pragma unroll
@@ -579,7 +590,7 @@ __global__ void __launch_bounds__(KB_WARPS * 32, NCH == 5 ? 4 : 1) km_cand_kerne
                 if (i < C) P.cands[co + (i < C1 ? c_ord[s] : (uint32_t)i)] = kmat_pair{K.nid[s], __uint_as_float(c_hits[s])};
             }
         } else { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_OVERFLOW; }       // candidate buffer too small: the host re-runs with the size asked for
-        if (lane == 0) P.out[r] = res;
+        if (lane == 0) { P.out[r] = res; if (P.pend_q) P.pend_q[qi] = r; }
         st_fast++;
     }
     if (P.stats && lane == 0) {
@@ -830,8 +841,11 @@ __device__ __forceinline__ void ks_score_one(const KmScoreParams &P, const uint3
 }
 
 __global__ void __launch_bounds__(KS_THREADS) km_score_kernel(KmScoreParams P) {
-    const uint32_t r = blockIdx.x * KS_THREADS + threadIdx.x;
-    if (r >= P.n_reads) return;
+    uint32_t r = blockIdx.x * KS_THREADS + threadIdx.x;
+    if (P.pend_q) {                                 // dense queue of the reads K3 left PENDING: no lane idles on a read without candidates
+        if (r >= (uint32_t)(*P.pass_cursor >> KB_PASS_SHIFT)) return;
+        r = P.pend_q[r];
+    } else if (r >= P.n_reads) return;
     KsLocal T;
     ks_score_one<KB_LIN, uint8_t, false>(P, r, T);
 }
@@ -843,6 +857,11 @@ __global__ void __launch_bounds__(32) km_score_big_kernel(KmScoreParams P) {
     KsLocalBig &T = *(KsLocalBig *)(P.big_scratch4 + (size_t)slot * sizeof(KsLocalBig));
     const uint32_t n = min(P.big_cnt[1], (unsigned int)KB_BIGQ);
     for (uint32_t q = slot; q < n; q += min(n_threads, P.big_threads4)) ks_score_one<KB_LBIG, uint16_t, true>(P, P.big_qb[q], T);
+}
+
+__global__ void km_cursor_roll_kernel(unsigned long long *cand_cursor, unsigned long long *pass_cursor) {
+    *cand_cursor += *pass_cursor & KB_PASS_MASK;
+    *pass_cursor = 0ull;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -883,6 +902,7 @@ __global__ void __launch_bounds__(KBG_WARPS * 32) km_cand_big_kernel(KmScorePara
     const int k = X.db.kmer_len;
     const bool permissive = X.opt.permissive != 0;
     const uint32_t nq = min(P.big_cnt[0], (unsigned int)KB_BIGQ);
+    const unsigned long long cand_base = *P.cand_cursor;
     for (uint32_t q = warp_global; q < nq; q += n_warps) {
         const uint32_t r = P.big_qa[q];
         const uint64_t off = P.offs[r];
@@ -1055,8 +1075,8 @@ __global__ void __launch_bounds__(KBG_WARPS * 32) km_cand_big_kernel(KmScorePara
         __syncwarp();
         // ---- hand over in taxid_lst order: members by first appearance (rank of the key), then the appended ancestors
         unsigned long long co = 0;
-        if (lane == 0) co = atomicAdd(P.cand_cursor, (unsigned long long)C);
-        co = kb_shfl64(co, 0);
+        if (lane == 0) co = atomicAdd(P.pass_cursor, (unsigned long long)C);
+        co = cand_base + (kb_shfl64(co, 0) & KB_PASS_MASK);
         res.status = KMAT_ST_PENDING_BIG; res.n_cand = (uint32_t)C; res.cand_off = co;
         if (P.cands && co + C <= P.cand_cap) {
             for (int i = lane; i < C; i += 32) {
@@ -1118,6 +1138,8 @@ struct kmat_ctx {
     uint64_t null_first = 0;                 // run index of read 0 of the pass being launched
     // direct sharded mode (kmat_ctx_peer_attach): where every shard's buckets / stash / resolved pool are mapped on this GPU
     // slow path for reads with more than KB_CMAX candidates: queues, counters and per-thread scratch slots
+    unsigned long long *d_pass = nullptr;            // per-pass packed cursor (KmScoreParams::pass_cursor)
+    uint32_t *d_pendq = nullptr; uint64_t cap_pendq = 0;
     uint32_t *d_bigq = nullptr; unsigned int *d_bigcnt = nullptr;
     unsigned char *d_big3 = nullptr, *d_big4 = nullptr; uint64_t cap_big3 = 0; uint32_t big_np_cap = 0, big_threads3 = 0;
     KmPeer *d_peers = nullptr; uint32_t n_peers = 0; std::vector<void *> ipc_mapped;
@@ -1223,6 +1245,8 @@ extern "C" int kmat_ctx_create(const kmat_db *db, const kmat_inputs *in, const k
         KM_CUDA(cudaMallocHost((void **)&sl.h_cur, 16));
     }
     KM_CUDA(cudaMalloc((void **)&c->d_cursors, 16));
+    KM_CUDA(cudaMalloc((void **)&c->d_pass, 8));
+    KM_CUDA(cudaMemset(c->d_pass, 0, 8));
     KM_CUDA(cudaMalloc((void **)&c->d_stats, sizeof(KmStatsDev)));
     int per_sm[3] = {0, 0, 0}, sms = 148;
     KM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], km_cand_kernel<5>, KB_WARPS * 32, 0));
@@ -1258,7 +1282,7 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
     km_shard_free(c->shard);
     for (void *p : c->ipc_mapped) cudaIpcCloseMemHandle(p);
     cudaFree(c->d_peers); cudaFree(c->d_peer_recs); cudaFree(c->d_peer_cur); cudaFree(c->d_pool2_all);
-    cudaFree(c->d_bigq); cudaFree(c->d_bigcnt); cudaFree(c->d_big3); cudaFree(c->d_big4);
+    cudaFree(c->d_bigq); cudaFree(c->d_bigcnt); cudaFree(c->d_big3); cudaFree(c->d_big4); cudaFree(c->d_pass); cudaFree(c->d_pendq);
     cudaFree(c->d_null_max); cudaFree(c->d_null_cnt); cudaFree(c->d_null_err); cudaFree(c->d_null_bases); cudaFree(c->d_null_offs);
     cudaFree(c->d_hit); cudaFree(c->d_hdr); cudaFree(c->d_out_dev);
     if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
@@ -1353,6 +1377,11 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
     if (pool2) { P.C.pool2 = pool2; P.C.pool2_mul = pool2_mul; }
     P.offs = L.d_offs + r0; P.n_reads = n; P.hit = hit; P.hdr = c->d_hdr + r0; P.out = L.d_out + r0;
     P.cands = c->d_cands; P.cand_cursor = c->d_cursors; P.cand_cap = c->cap_cands;
+    P.pass_cursor = c->d_pass; P.pend_q = nullptr;
+    if (!c->opt.rkmer_mode && n < (1u << (64 - KB_PASS_SHIFT)) && !getenv("KMAT_NO_PEND_QUEUE")) {
+        if ((uint64_t)n > c->cap_pendq) { KM_CUDA(cudaStreamSynchronize(s2)); int rcq = km_grow(&c->d_pendq, &c->cap_pendq, (uint64_t)n); if (rcq != KMAT_OK) return rcq; }
+        P.pend_q = c->d_pendq;
+    }
     P.lin = c->d_lin; P.lin_cursor = c->d_cursors + 1; P.lin_cap = c->cap_lin;
     P.stats = c->collect_stats ? c->d_stats : nullptr;
     P.long_masks = nullptr; P.long_cap = 0;
@@ -1392,7 +1421,14 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     if (ev_mid) KM_CUDA(cudaEventRecord(ev_mid, s2));
-    if (c->opt.rkmer_mode) return km_launch_nullacc(c, P, r0, n, s2);     // rand_read_label: accumulate instead of scoring
+    if (c->opt.rkmer_mode) {                      // rand_read_label: accumulate instead of scoring
+        const int rcn = km_launch_nullacc(c, P, r0, n, s2);
+        if (rcn != KMAT_OK) return rcn;
+        km_cursor_roll_kernel<<<1, 1, 0, s2>>>(c->d_cursors, c->d_pass);
+        g_km_launches++;
+        KM_CUDA(cudaGetLastError());
+        return KMAT_OK;
+    }
     // KMAT_SCORE_SMEM (experiment knob): dummy dynamic shared memory per CTA, to cap the resident CTAs of the scoring
     // kernel -- its per-thread local arrays then fit the L1 instead of spilling through L2 to DRAM
     static const int score_smem = [] {
@@ -1403,6 +1439,9 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     km_score_big_kernel<<<KBIG_THREADS / 32, 32, 0, s2>>>(P);
+    g_km_launches++;
+    KM_CUDA(cudaGetLastError());
+    km_cursor_roll_kernel<<<1, 1, 0, s2>>>(c->d_cursors, c->d_pass);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     return KMAT_OK;
