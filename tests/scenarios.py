@@ -148,3 +148,46 @@ def build_nullgen_inputs(workdir: str) -> dict:
     fx.write_kpc_fasta(paths["genomes"], genomes)
     paths["workdir"] = workdir
     return dict(paths=paths, tax=tax, genomes=genomes)
+
+
+# ------------------------------------------------------------------------------------------------
+# content_summ scenario: the read_label output of the `lists` scenario, summarised
+# ------------------------------------------------------------------------------------------------
+CONTENT_SUMM_RUNS = {
+    # flags of bin/run_cs.sh:148 (k-values 8,10,12,14,17; ranks plasmid,species,genus; the extra plasmid list)
+    "run_cs": dict(k="8,10,12,14,17", ranks="plasmid,species,genus", threshold=None, skip_human=False, plasmids=True),
+    "k20_thr": dict(k="20,9", ranks="species", threshold=0.4, skip_human=True, plasmids=False),
+}
+
+
+def content_summ_inputs(workdir: str, golden_dir: str) -> dict:
+    """The reference read_label output of the lists scenario cut into two files (two "threads"), the list naming them
+    and the .fastsummary."""
+    import gzip
+    raw = gzip.open(os.path.join(golden_dir, "lists.run_rl.out.gz")).read()
+    cut = raw.index(b"\n", len(raw) // 2) + 1
+    parts = []
+    for i, blob in enumerate((raw[:cut], raw[cut:])):
+        p = os.path.join(workdir, f"rl{i}.out")
+        with open(p, "wb") as f:
+            f.write(blob)
+        parts.append(p)
+    lst = os.path.join(workdir, "rl.lst")
+    with open(lst, "w") as f:
+        f.write("\n".join(parts) + "\n")
+    fs = os.path.join(workdir, "rl.fastsummary")
+    with open(os.path.join(golden_dir, "lists.run_rl.fastsummary"), "rb") as src, open(fs, "wb") as dst:
+        dst.write(src.read())
+    return dict(lst=lst, fastsummary=fs, parts=parts)
+
+
+def content_summ_args(run: dict, P: dict, files: dict, ofbase: str) -> list:
+    a = []
+    if run["skip_human"]:
+        a += ["-s"]
+    if run["plasmids"]:
+        a += ["-p", P["plasmids"]]
+    a += ["-c", P["tree"], "-l", files["fastsummary"], "-k", run["k"], "-f", files["lst"], "-r", P["rank"], "-a", run["ranks"]]
+    if run["threshold"] is not None:
+        a += ["-v", str(run["threshold"])]
+    return a + ["-o", ofbase]
