@@ -271,6 +271,23 @@ typedef struct { unsigned char opaque[512]; } kmat_peer_info;
 int kmat_ctx_peer_export(kmat_ctx *, kmat_peer_info *out);
 int kmat_ctx_peer_attach(kmat_ctx *, int n_shards, const kmat_peer_info *all /* [n_shards], entry s = export of shard s */);
 
+/* ---- content_summ: k-mer coverage of the called taxids ---------------------
+ * Replaces retrieve_kmer_labels / storeKmers (src/content_summ.cpp:114-160: per read and per k of the -k list, every
+ * DISTINCT canonical k-mer of the read counts once for the read's taxid) and the merge + histogram of compKmerCov
+ * (:527-571).  `groups[r]` is the caller's dense index (< 2^21) of the taxid read r counts for, KMAT_GROUP_SKIP = the
+ * read is left out.  k <= 20, at most 8 values. */
+#define KMAT_GROUP_SKIP 0xFFFFFFFFu
+typedef struct kmat_kcov kmat_kcov;
+int kmat_kcov_create(int device, const int32_t *k_sizes, int n_k, kmat_kcov **out);
+int kmat_kcov_add(kmat_kcov *, const char *bases, const uint64_t *offs, const uint32_t *groups, uint32_t n_reads);
+int kmat_kcov_finish(kmat_kcov *);     /* merge everything added so far; required before kmat_kcov_query */
+/* For (k_sizes[k_index], group): number of distinct k-mers, sum of their counts, and the histogram of the counts --
+ * hist_count[i] ascending, hist_n[i] k-mers seen in exactly hist_count[i] reads (what :556-569 prints).  *n_hist receives
+ * the number of histogram entries (KMAT_ERR_OVERFLOW if cap > 0 is too small; cap == 0 only queries). */
+int kmat_kcov_query(kmat_kcov *, int k_index, uint32_t group, uint64_t *distinct, uint64_t *total, uint32_t *hist_count, uint64_t *hist_n,
+                    uint32_t cap, uint32_t *n_hist);
+void kmat_kcov_free(kmat_kcov *);
+
 /* Page-locked host memory for the buffers of kmat_label_batch (optional; NULL when no device / out of memory). */
 void *kmat_host_alloc(size_t bytes);
 void kmat_host_free(void *);

@@ -52,6 +52,7 @@ EXPORTS = [
     "kmat_set_l2_fetch_granularity", "kmat_reader_open", "kmat_reader_open_mt", "kmat_reader_close", "kmat_read_batch_new", "kmat_read_batch_free",
     "kmat_reader_next", "kmat_read_batch_view", "kmat_tally_class", "kmat_host_alloc", "kmat_host_free",
     "kmat_ctx_peer_export", "kmat_ctx_peer_attach",
+    "kmat_kcov_create", "kmat_kcov_add", "kmat_kcov_finish", "kmat_kcov_query", "kmat_kcov_free",
     "kmat_null_reset", "kmat_null_batch", "kmat_null_random", "kmat_null_draw_reads", "kmat_null_fetch", "kmat_null_write",
 ]
 
@@ -129,6 +130,11 @@ def lib():
     L.kmat_host_free.argtypes = [vp]
     L.kmat_ctx_peer_export.argtypes = [vp, vp]
     L.kmat_ctx_peer_attach.argtypes = [vp, C.c_int, vp]
+    L.kmat_kcov_create.argtypes = [C.c_int, vp, C.c_int, C.POINTER(vp)]
+    L.kmat_kcov_add.argtypes = [vp, vp, vp, vp, C.c_uint32]
+    L.kmat_kcov_finish.argtypes = [vp]
+    L.kmat_kcov_query.argtypes = [vp, C.c_int, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.kmat_kcov_free.argtypes = [vp]
     L.kmat_null_reset.argtypes = [vp]
     L.kmat_null_batch.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64]
     L.kmat_null_random.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
@@ -523,3 +529,36 @@ def null_write(path, sets):
     cp = (C.c_void_p * n)(*[k[2].ctypes.data for k in keep])
     nr = np.array([len(k[0]) for k in keep], dtype=np.uint32)
     _check(lib().kmat_null_write(_b(path), n, tp, mp, cp, nr.ctypes.data))
+
+
+class KmerCov:
+    """kmat_kcov_*: per (k, group) distinct canonical k-mers of the added reads, each counted once per read."""
+
+    def __init__(self, k_sizes, device=0):
+        self.k = np.ascontiguousarray(k_sizes, dtype=np.int32)
+        self.h = C.c_void_p()
+        _check(lib().kmat_kcov_create(device, self.k.ctypes.data, len(self.k), C.byref(self.h)))
+
+    def __del__(self):
+        try:
+            lib().kmat_kcov_free(self.h)
+        except Exception:
+            pass
+
+    def add(self, seqs, groups):
+        blob, offs = pack_reads(seqs)
+        g = np.ascontiguousarray(groups, dtype=np.uint32)
+        ptr = blob if isinstance(blob, (bytes, bytearray)) else blob.ctypes.data
+        _check(lib().kmat_kcov_add(self.h, ptr, offs.ctypes.data, g.ctypes.data, len(g)))
+
+    def finish(self):
+        _check(lib().kmat_kcov_finish(self.h))
+
+    def query(self, k_index, group):
+        """-> (distinct, total, {count: number of k-mers})"""
+        d, t, n = C.c_uint64(), C.c_uint64(), C.c_uint32()
+        _check(lib().kmat_kcov_query(self.h, k_index, group, C.byref(d), C.byref(t), None, None, 0, C.byref(n)))
+        hc = np.zeros(max(1, n.value), dtype=np.uint32)
+        hn = np.zeros(max(1, n.value), dtype=np.uint64)
+        _check(lib().kmat_kcov_query(self.h, k_index, group, C.byref(d), C.byref(t), hc.ctypes.data, hn.ctypes.data, len(hc), C.byref(n)))
+        return d.value, t.value, {int(hc[i]): int(hn[i]) for i in range(n.value)}

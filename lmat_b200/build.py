@@ -89,11 +89,13 @@ MDT_BIN = os.path.join(HERE, "bin", "make_db_table")
 
 GL_BIN = os.path.join(HERE, "bin", "gene_label")
 RRL_BIN = os.path.join(HERE, "bin", "rand_read_label")
+CS_BIN = os.path.join(HERE, "bin", "content_summ")
 
 
 def build_tools(force=False):
     """The other host binaries over libkmat (drop-ins for the reference tools of the same name)."""
-    for name, out in (("make_db_table_main.cpp", MDT_BIN), ("gene_label_main.cpp", GL_BIN), ("rand_read_label_main.cpp", RRL_BIN)):
+    for name, out in (("make_db_table_main.cpp", MDT_BIN), ("gene_label_main.cpp", GL_BIN), ("rand_read_label_main.cpp", RRL_BIN),
+                      ("content_summ_main.cpp", CS_BIN)):
         src = os.path.join(CSRC, name)
         if force or _newer(out, [src, LIB]):
             os.makedirs(os.path.dirname(out), exist_ok=True)

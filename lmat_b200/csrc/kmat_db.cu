@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "kmat_device.cuh"
@@ -875,3 +876,5 @@ extern "C" int kmat_set_l2_fetch_granularity(int device, int bytes) {
     KM_CUDA(cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity));
     return (int)v;
 }
+
+#include "kmat_kcov.cuh"
