@@ -433,10 +433,13 @@ def main():
             optr, _, _ = ctx.device_results()
             rv = _sh._wrap(optr, n * api.RESULT_DTYPE.itemsize, torch.uint8, dev).view(torch.int32).view(n, api.RESULT_DTYPE.itemsize // 4).to(torch.int64)
             labels_checksum = int(((rv[:, 0] * 1000003 + rv[:, 6] * 7919 + rv[:, 7]) & 0xFFFFFFFF).sum().item())
+            if os.environ.get("KMAT_BENCH_DUMP") and rank == 0:        # debugging aid: the raw results of rank 0's reads
+                np.save(os.environ["KMAT_BENCH_DUMP"], rv.to(torch.int32).cpu().numpy())
         except Exception as ex:
             labels_checksum = repr(ex)[:100]
         st = ctx.stats()
         ctx.set_stats(False)
+        ctx.sync()          # raises if a pass overflowed its candidate buffer (reads left in error): the line would be invalid
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

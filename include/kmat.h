@@ -298,6 +298,8 @@ void kmat_host_free(void *);
  * stream = a cudaStream_t cast to void* (NULL = the ctx's own stream); does not synchronise. */
 int kmat_label_batch_device(kmat_ctx *, const char *d_bases, const uint64_t *d_offs, uint32_t n_reads,
                             uint64_t total_bases, uint32_t max_read_len, kmat_read_result *d_out, void *stream);
+/* Waits for the ctx's own stream.  KMAT_ERR_OVERFLOW: the candidate buffer of the last device-resident pass was too small
+ * (reads in KMAT_ST_ERROR / KMAT_ERR_OVERFLOW); it is enlarged for the next call, run the batch again. */
 int kmat_ctx_sync(kmat_ctx *);
 /* Statistics of the last batch (device counters read back): unique k-mer lookups issued, hits, list
  * hits, total list ids, and the algorithmic table bytes of SURVEY.md 8(d). */

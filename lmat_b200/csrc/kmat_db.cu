@@ -353,7 +353,14 @@ struct KmProbeParams {
     KmStatsDev *stats;             // optional
     int do_probe;
     uint64_t *xq;                  // DB-sharded mode (with do_probe == 0): mixed k-mer of every first occurrence, per base offset
+    int skip_mid;                  // 1: reads of KM_LONG_MIN..KM_LONG_MAX bases are left to km_encode_probe_long_kernel
 };
+// Reads of this many bases get a whole CTA (km_encode_probe_long_kernel): their dedup set fits shared memory
+#define KM_LONG_MIN 257
+#define KM_LONG_MAX 12000
+#define KM_LONG_SLOTS 16384
+#define KM_LONG_THREADS 512
+#define KM_LONG_POS_BITS 24
 
 __device__ __forceinline__ int km_code(unsigned char ch) {
     // ENCODE macro, read_label.cpp:943-950: a/A 0, c/C 1, g/G 2, t/T 3, anything else resets (-1).  Branch-free:
@@ -393,6 +400,7 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32) km_encode_probe_kernel(Km
         const uint64_t off = P.offs[r];
         const int len = (int)(P.offs[r + 1] - off);
         const int np = len - k + 1;
+        if (P.skip_mid && len >= KM_LONG_MIN && len <= KM_LONG_MAX) continue;
         // pick the dedup set
         unsigned long long *set; uint32_t smask; uint32_t epoch;
         if (np <= KM_DEDUP_SLOTS / 2 || !lset) {
@@ -526,6 +534,144 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32) km_encode_probe_kernel(Km
 //   * the home bucket answers ~98.5 % of the lookups; a full home bucket continues with km_probe_x(d = 1).
 // Dynamic shared memory per warp: SETN / 8 B dedup bitmap.
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// K1 + K2 for long reads (257 .. 12000 bases, k <= 20): one CTA per read.  The any-length kernel above keeps the dedup set
+// of such a read in global memory, which costs two more random DRAM requests per k-mer than the table gather itself
+// (the path is request-rate bound: 70 ms per 10^9 bases).  Here the set lives in shared memory (16 K slots of
+// [canonical k-mer : position], 128 KB): phase 1 inserts every k-mer window with "lowest position wins" (atomicMin on the
+// packed word), phase 2 re-encodes, asks the set whether a window is the first occurrence and gathers the buckets of the
+// first occurrences, four chunks in flight per warp.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void kl_encode_chunk(const KmProbeParams &P, uint64_t off, int len, int c, int lane, int k, uint64_t kmask, int kmer_bits,
+                                                uint64_t &canon, bool &ok, bool &ok_prev, uint32_t &cgc_bit, int &gc_win) {
+    // the 32 bases of chunk c and of the chunk before it (re-read: they are in L1/L2), packed as in the any-length kernel
+    const int j = (c << 5) + lane;
+    const int code = j < len ? km_code((unsigned char)P.bases[off + j]) : -1;
+    const int jp = j - 32;
+    const int codep = jp >= 0 ? km_code((unsigned char)P.bases[off + jp]) : -1;
+    const uint32_t cinv = __ballot_sync(KM_FULL, code < 0), pinv = __ballot_sync(KM_FULL, codep < 0);
+    const uint32_t cgc = __ballot_sync(KM_FULL, code == 1 || code == 2), pgc = __ballot_sync(KM_FULL, codep == 1 || codep == 2);
+    const uint32_t cc = code < 0 ? 0u : (uint32_t)code, cp = codep < 0 ? 0u : (uint32_t)codep;
+    const uint64_t cur = ((uint64_t)__reduce_or_sync(KM_FULL, lane < 16 ? cc << (30 - 2 * lane) : 0u) << 32) | __reduce_or_sync(KM_FULL, lane >= 16 ? cc << (62 - 2 * lane) : 0u);
+    const uint64_t prev = ((uint64_t)__reduce_or_sync(KM_FULL, lane < 16 ? cp << (30 - 2 * lane) : 0u) << 32) | __reduce_or_sync(KM_FULL, lane >= 16 ? cp << (62 - 2 * lane) : 0u);
+    const int s = 62 - 2 * lane;
+    const uint64_t fwd = ((cur >> s) | (s ? (prev << (64 - s)) : 0ull)) & kmask;
+    const uint64_t inv64 = ((uint64_t)cinv << 32) | pinv, gc64 = ((uint64_t)cgc << 32) | pgc;
+    const uint64_t wmask = (1ull << k) - 1;
+    const int wsh = 32 + lane - k + 1;
+    ok = ((inv64 >> wsh) & wmask) == 0;
+    ok_prev = wsh > 0 && ((inv64 >> (wsh - 1)) & wmask) == 0;
+    canon = 0;
+    if (ok) { const uint64_t rc = km_revcomp(fwd, kmer_bits); canon = fwd < rc ? fwd : rc; }
+    cgc_bit = (cgc >> lane) & 1;
+    gc_win = __popcll((gc64 >> wsh) & wmask);
+}
+__device__ __forceinline__ uint32_t kl_slot(uint64_t canon) { return (uint32_t)((canon * 0x9E3779B97F4A7C15ull) >> 40) & (KM_LONG_SLOTS - 1); }
+
+__global__ void __launch_bounds__(KM_LONG_THREADS, 1) km_encode_probe_long_kernel(KmProbeParams P) {
+    extern __shared__ __align__(16) unsigned long long kl_set[];          // KM_LONG_SLOTS entries, ~0 = empty
+    __shared__ int s_valid, s_vgc, s_vtot;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int NW = KM_LONG_THREADS / 32;
+    const int k = P.db.kmer_len, kmer_bits = P.db.kmer_bits;
+    const uint64_t kmask = (1ull << kmer_bits) - 1;
+    unsigned long long st_lookups = 0, st_hits = 0, st_lists = 0, st_extra = 0, st_pmiss = 0;
+    for (int i = threadIdx.x; i < KM_LONG_SLOTS; i += KM_LONG_THREADS) kl_set[i] = ~0ull;
+    if (threadIdx.x == 0) { s_valid = 0; s_vgc = 0; s_vtot = 0; }
+    __syncthreads();
+    for (uint32_t r = blockIdx.x; r < P.n_reads; r += gridDim.x) {
+        const uint64_t off = P.offs[r];
+        const int len = (int)(P.offs[r + 1] - off);
+        if (len < KM_LONG_MIN || len > KM_LONG_MAX) continue;                 // block-uniform
+        const int nchunks = (len + 31) >> 5;
+        // ---- phase 1: every k-mer window into the set, lowest position wins; GC bookkeeping (:994-1008)
+        int valid = 0, vgc = 0, vtot = 0;
+        for (int c = wid; c < nchunks; c += NW) {
+            uint64_t canon; bool ok, ok_prev; uint32_t gcb; int gcw;
+            kl_encode_chunk(P, off, len, c, lane, k, kmask, kmer_bits, canon, ok, ok_prev, gcb, gcw);
+            valid += ok; vtot += ok ? (ok_prev ? 1 : k) : 0; vgc += ok ? (ok_prev ? (int)gcb : gcw) : 0;
+            if (ok) {
+                const int p = (c << 5) + lane - k + 1;
+                const unsigned long long e = (canon << KM_LONG_POS_BITS) | (unsigned long long)p;
+                uint32_t h = kl_slot(canon);
+                for (;;) {
+                    unsigned long long cur_e = kl_set[h];
+                    if (cur_e == ~0ull) { cur_e = atomicCAS(&kl_set[h], ~0ull, e); if (cur_e == ~0ull) break; }
+                    if ((cur_e >> KM_LONG_POS_BITS) == canon) { atomicMin(&kl_set[h], e); break; }
+                    h = (h + 1) & (KM_LONG_SLOTS - 1);
+                }
+            }
+        }
+        valid = km_warp_sum(valid); vgc = km_warp_sum(vgc); vtot = km_warp_sum(vtot);
+        if (lane == 0) { atomicAdd(&s_valid, valid); atomicAdd(&s_vgc, vgc); atomicAdd(&s_vtot, vtot); }
+        __syncthreads();
+        // ---- phase 2: first occurrences probe the table, four chunks of gathers in flight per warp
+        for (int c0 = wid * 4; c0 < nchunks; c0 += NW * 4) {
+            uint64_t xk[4], cn[4], bk[4][4]; bool first[4]; uint32_t owner[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                first[u] = false; xk[u] = 0; cn[u] = 0; owner[u] = 0;
+                bk[u][0] = bk[u][1] = bk[u][2] = bk[u][3] = 0;
+                const int c = c0 + u;
+                if (c >= nchunks) continue;                                   // warp-uniform
+                uint64_t canon; bool ok, ok_prev; uint32_t gcb; int gcw;
+                kl_encode_chunk(P, off, len, c, lane, k, kmask, kmer_bits, canon, ok, ok_prev, gcb, gcw);
+                if (ok) {
+                    const int p = (c << 5) + lane - k + 1;
+                    uint32_t h = kl_slot(canon);
+                    for (;;) {
+                        const unsigned long long cur_e = kl_set[h];
+                        if ((cur_e >> KM_LONG_POS_BITS) == canon) { first[u] = (int)(cur_e & ((1ull << KM_LONG_POS_BITS) - 1)) == p; break; }
+                        h = (h + 1) & (KM_LONG_SLOTS - 1);
+                    }
+                    if (first[u]) {
+                        cn[u] = canon;
+                        xk[u] = km_mix(canon, kmer_bits);
+                        if (P.do_probe)
+                            km_load_bucket(km_slots_of(P.db, xk[u], owner[u]) + ((xk[u] >> P.db.rem_bits) & P.db.bucket_mask) * KM_SLOTS_PER_BUCKET, bk[u][0], bk[u][1], bk[u][2], bk[u][3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int c = c0 + u;
+                if (c >= nchunks) continue;
+                const int j = (c << 5) + lane, p = j - k + 1;
+                uint32_t hw = KM_HIT_INVALID;
+                if (first[u]) {
+                    hw = KM_HIT_MISS;
+                    if (P.do_probe) {
+                        uint32_t extra = 0;
+                        if (km_bucket_match(bk[u][0], bk[u][1], bk[u][2], bk[u][3], xk[u] & ((1ull << P.db.rem_bits) - 1), 0, hw) == 2) { hw = km_probe_x(P.db, xk[u], extra, 1); extra++; }
+                        else hw = km_tag_owner(P.db, hw, owner[u]);
+                        if (P.stats) {
+                            st_lookups++; st_extra += extra;
+                            if (hw != KM_HIT_MISS) { st_hits++; if (hw & KM_HIT_LIST) st_lists++; }
+                            else if (P.db.prefix_bits) { const uint64_t pf = cn[u] >> P.db.prefix_shift; if (!((P.db.prefix_bits[pf >> 5] >> (pf & 31)) & 1)) st_pmiss++; }
+                        }
+                    }
+                }
+                if (p >= 0 && j < len) P.hit[off + p] = hw;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const float frac = __fdiv_rn((float)s_vgc, (float)s_vtot);                     // :1205-1206
+            const float gc_pcnt = __double2float_rn(__dmul_rn((double)frac, 100.0));
+            const float q = __fdiv_rn(gc_pcnt, 10.0f);
+            P.hdr[r] = make_int2(s_valid, s_vtot > 0 ? (int)q : 0);
+            s_valid = 0; s_vgc = 0; s_vtot = 0;
+        }
+        for (int i = threadIdx.x; i < KM_LONG_SLOTS; i += KM_LONG_THREADS) kl_set[i] = ~0ull;
+        __syncthreads();
+    }
+    if (P.stats) {
+        st_lookups = km_warp_sum((int)st_lookups); st_hits = km_warp_sum((int)st_hits); st_lists = km_warp_sum((int)st_lists); st_extra = km_warp_sum((int)st_extra);
+        st_pmiss = km_warp_sum((int)st_pmiss);
+        if (lane == 0) { atomicAdd(&P.stats->lookups, st_lookups); atomicAdd(&P.stats->hits, st_hits); atomicAdd(&P.stats->list_hits, st_lists); atomicAdd(&P.stats->extra_buckets, st_extra); atomicAdd(&P.stats->prefix_miss, st_pmiss); }
+    }
+}
+
 #ifndef KM_FAST_CTAS
 #define KM_FAST_CTAS 2
 #endif
@@ -716,7 +862,7 @@ int km_launch_encode_probe(const kmat_db *db, const char *d_bases, const uint64_
     KmProbeParams P;
     P.db = km_db_dev(db); P.db.peers = d_peers; P.db.n_peers = d_peers ? n_peers : 0; P.bases = d_bases; P.offs = d_offs; P.n_reads = n_reads; P.hit = d_hit; P.hdr = d_hdr;
     P.out_kmers = d_kmers; P.out_flags = d_flags; P.long_sets = d_long_sets; P.long_slots = long_slots; P.stats = d_stats;
-    P.do_probe = do_probe; P.xq = d_xq;
+    P.do_probe = do_probe; P.xq = d_xq; P.skip_mid = 0;
     const bool fast = !d_kmers && !d_flags && max_len <= 256 && db->kmer_len <= 24 && !getenv("KMAT_NO_FAST_PROBE");
     int rc = KMAT_OK;
     const bool peers = P.db.n_peers != 0;
@@ -724,7 +870,20 @@ int km_launch_encode_probe(const kmat_db *db, const char *d_bases, const uint64_
     else if (fast && max_len <= 160) rc = d_stats ? km_launch_fast<5, 4096, true, true>(P, ctas_per_sm, stream) : km_launch_fast<5, 4096, false, true>(P, ctas_per_sm, stream);
     else if (fast && !peers) rc = d_stats ? km_launch_fast<8, 8192, true, false>(P, ctas_per_sm, stream) : km_launch_fast<8, 8192, false, false>(P, ctas_per_sm, stream);
     else if (fast) rc = d_stats ? km_launch_fast<8, 8192, true, true>(P, ctas_per_sm, stream) : km_launch_fast<8, 8192, false, true>(P, ctas_per_sm, stream);
-    else km_encode_probe_kernel<<<grid, KM_PROBE_WARPS * 32, 0, stream>>>(P);
+    else {
+        // mixed / long batches: reads of 257 .. 12000 bases get a CTA each (shared-memory dedup set), the any-length kernel
+        // takes the rest
+        const bool use_long = !d_kmers && !d_flags && !d_xq && max_len >= KM_LONG_MIN && db->geom.kmer_bits + KM_LONG_POS_BITS <= 64 && db->kmer_len <= 32 && !getenv("KMAT_NO_LONG_PROBE");
+        if (use_long) {
+            static bool attr_set = false;
+            if (!attr_set) { KM_CUDA(cudaFuncSetAttribute(km_encode_probe_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KM_LONG_SLOTS * 8)); attr_set = true; }
+            P.skip_mid = 1;
+            km_encode_probe_long_kernel<<<(int)std::max<uint32_t>(1, std::min<uint32_t>(n_reads, 148u)), KM_LONG_THREADS, KM_LONG_SLOTS * 8, stream>>>(P);
+            g_km_launches++;
+            KM_CUDA(cudaGetLastError());
+        }
+        km_encode_probe_kernel<<<grid, KM_PROBE_WARPS * 32, 0, stream>>>(P);
+    }
     if (rc != KMAT_OK) return rc;
     g_km_launches++;
     KM_CUDA(cudaGetLastError());

@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(KB_WARPS * 32, NCH == 5 ? 4 : 1) km_cand_kerne
                 const int i = lane + 32 * s;
                 if (i < C) P.cands[co + (i < C1 ? c_ord[s] : (uint32_t)i)] = kmat_pair{K.nid[s], __uint_as_float(c_hits[s])};
             }
-        } else { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_OVERFLOW; }       // candidate buffer too small: the host re-runs with the size asked for
+        } else { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_OVERFLOW; st_err++; }       // candidate buffer too small: the host re-runs with the size asked for
         if (lane == 0) { P.out[r] = res; if (P.pend_q) P.pend_q[qi] = r; }
         st_fast++;
     }
@@ -1141,12 +1141,13 @@ struct kmat_ctx {
     unsigned long long *d_pass = nullptr;            // per-pass packed cursor (KmScoreParams::pass_cursor)
     uint32_t *d_pendq = nullptr; uint64_t cap_pendq = 0;
     uint32_t *d_bigq = nullptr; unsigned int *d_bigcnt = nullptr;
-    unsigned char *d_big3 = nullptr, *d_big4 = nullptr; uint64_t cap_big3 = 0; uint32_t big_np_cap = 0, big_threads3 = 0;
+    unsigned char *d_big3 = nullptr, *d_big4 = nullptr; uint64_t cap_big3 = 0; uint32_t big_np_cap = 0, big_threads3 = 0, big_threads4 = 0;
     KmPeer *d_peers = nullptr; uint32_t n_peers = 0; std::vector<void *> ipc_mapped;
     uint32_t *d_pool2_all = nullptr;                                  // every shard's resolved pool, concatenated (list hits stay local)
     uint32_t *d_peer_recs = nullptr; uint64_t cap_peer_recs = 0;      // list records of the pass copied from their owners (km_peer_fetch_kernel)
     unsigned long long *d_peer_cur = nullptr;                         // [0] words used (per pass), [1] list hits dropped for lack of room (monotonic)
     unsigned long long peer_dropped_seen = 0; int peer_grow = 1;
+    int cand_grow = 1;                                                // candidate buffer: factor on the per-read estimate
     char *d_null_bases = nullptr; uint64_t *d_null_offs = nullptr; uint64_t cap_null_bases = 0, cap_null_offs = 0;
     unsigned long long *d_long_masks = nullptr; uint32_t long_mask_cap = 0;
     unsigned long long *d_long_sets = nullptr; uint32_t long_slots = 0; int long_warps = 0;
@@ -1386,12 +1387,19 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
     P.stats = c->collect_stats ? c->d_stats : nullptr;
     P.long_masks = nullptr; P.long_cap = 0;
     // slow path buffers (first use / longer reads than before)
-    const uint32_t KBIG_THREADS = 2048;            // threads (global scratch slots) of the big scoring kernel
+    // threads (= global scratch slots of 42 KB) of the big scoring kernel: few for short reads, where it is a rare path,
+    // a GB worth of them for long reads, where nearly every read takes it
+    const uint32_t KBIG_THREADS = L.max_len > 1024 ? 24576u : 2048u;
     const uint32_t np_need = (uint32_t)std::max<int>(1, (int)L.max_len - c->db->kmer_len + 1);
     if (!c->d_bigq) {
         KM_CUDA(cudaMalloc((void **)&c->d_bigq, (size_t)2 * KB_BIGQ * 4));
         KM_CUDA(cudaMalloc((void **)&c->d_bigcnt, 8));
+    }
+    if (KBIG_THREADS > c->big_threads4) {
+        KM_CUDA(cudaStreamSynchronize(s2));
+        cudaFree(c->d_big4); c->d_big4 = nullptr;
         KM_CUDA(cudaMalloc((void **)&c->d_big4, (size_t)KBIG_THREADS * sizeof(KsLocalBig)));
+        c->big_threads4 = KBIG_THREADS;
     }
     if (np_need > c->big_np_cap) {
         const size_t per = ((size_t)np_need + KB_CBIG) * KB_BIGW * 8;                       // one warp's position sets + lineage sets
@@ -1404,7 +1412,7 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
         c->big_np_cap = np_need; c->big_threads3 = threads;
     }
     P.big_qa = c->d_bigq; P.big_qb = c->d_bigq + KB_BIGQ; P.big_cnt = c->d_bigcnt;
-    P.big_scratch3 = c->d_big3; P.big_scratch4 = c->d_big4; P.big_np_cap = c->big_np_cap; P.big_threads3 = c->big_threads3; P.big_threads4 = KBIG_THREADS;
+    P.big_scratch3 = c->d_big3; P.big_scratch4 = c->d_big4; P.big_np_cap = c->big_np_cap; P.big_threads3 = c->big_threads3; P.big_threads4 = c->big_threads4;
     KM_CUDA(cudaMemsetAsync(c->d_bigcnt, 0, 8, s2));
     const int want_grid = (int)((n + KB_WARPS - 1) / KB_WARPS);
     const int g0 = cand_ctas_per_sm > 0 ? std::min(c->cand_grid[0], cand_ctas_per_sm * c->sms) : c->cand_grid[0];
@@ -1438,7 +1446,7 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
     km_score_kernel<<<(n + KS_THREADS - 1) / KS_THREADS, KS_THREADS, score_smem, s2>>>(P);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
-    km_score_big_kernel<<<KBIG_THREADS / 32, 32, 0, s2>>>(P);
+    km_score_big_kernel<<<c->big_threads4 / 32, 32, 0, s2>>>(P);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     km_cursor_roll_kernel<<<1, 1, 0, s2>>>(c->d_cursors, c->d_pass);
@@ -1508,10 +1516,15 @@ static int km_run_device(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
 }
 
 static int km_grow_cands(kmat_ctx *c, uint64_t want) { return km_grow(&c->d_cands, &c->cap_cands, want); }
-static int km_reserve_cands(kmat_ctx *c, uint64_t n_reads) {
+// Candidate / lineage pair buffers for a pass of n_reads reads of at most max_len bases.  A 150 bp read of the synthetic
+// workloads carries ~10 candidates; long reads collect chance hits all over the taxonomy (a 10 kbp read ~100-200), hence
+// the length term.  cand_grow doubles after a pass overflowed (kmat_ctx_sync / kmat_label_batch report that).
+static int km_reserve_cands(kmat_ctx *c, uint64_t n_reads, uint32_t max_len = 0) {
     int rc;
-    if (!c->d_cands || c->cap_cands < n_reads * 12 + 4096) { if ((rc = km_grow_cands(c, n_reads * 24 + 4096)) != KMAT_OK) return rc; }
-    if (c->opt.want_lineage && (!c->d_lin || c->cap_lin < n_reads * 12 + 4096)) { if ((rc = km_grow(&c->d_lin, &c->cap_lin, n_reads * 24 + 4096)) != KMAT_OK) return rc; }
+    const uint64_t per = std::min<uint64_t>(KB_CBIG, (uint64_t)(24 + max_len / 32) * (uint64_t)c->cand_grow);
+    const uint64_t want = n_reads * per + 4096;
+    if (!c->d_cands || c->cap_cands < want / 2) { if ((rc = km_grow_cands(c, want)) != KMAT_OK) return rc; }
+    if (c->opt.want_lineage && (!c->d_lin || c->cap_lin < want / 2)) { if ((rc = km_grow(&c->d_lin, &c->cap_lin, want)) != KMAT_OK) return rc; }
     return KMAT_OK;
 }
 
@@ -1530,7 +1543,7 @@ extern "C" int kmat_label_batch_device(kmat_ctx *c, const char *d_bases, const u
         c->cap_out_dev = (uint32_t)cap;
         d_out = c->d_out_dev;
     }
-    if ((rc = km_reserve_cands(c, n_reads)) != KMAT_OK) return rc;
+    if ((rc = km_reserve_cands(c, n_reads, max_read_len)) != KMAT_OK) return rc;
     KmPass L{d_bases, d_offs, n_reads, 0, total_bases, max_read_len, d_out, true};
     return km_run_device(c, L, st);
 }
@@ -1574,6 +1587,15 @@ extern "C" int kmat_ctx_sync(kmat_ctx *c) {
     if (!c) return KMAT_ERR_ARG;
     KM_CUDA(cudaSetDevice(c->device));
     KM_CUDA(cudaStreamSynchronize(c->stream));
+    // a device-resident pass whose candidate buffer was too small left reads in KMAT_ST_ERROR / KMAT_ERR_OVERFLOW: say so
+    unsigned long long cur[2] = {0, 0};
+    KM_CUDA(cudaMemcpy(cur, c->d_cursors, 16, cudaMemcpyDeviceToHost));
+    if (cur[0] > c->cap_cands || (c->opt.want_lineage && cur[1] > c->cap_lin)) {
+        c->cand_grow *= 2;
+        kmat_set_error("the candidate buffer (%llu pairs) was too small for the last pass (%llu needed): some reads are in KMAT_ST_ERROR; it grows now, run the batch again",
+                       (unsigned long long)c->cap_cands, cur[0]);
+        return KMAT_ERR_OVERFLOW;
+    }
     return km_peer_check(c);
 }
 

@@ -166,7 +166,7 @@ extern "C" int kmat_shard_encode(kmat_ctx *c, const char *d_bases, const uint64_
     *d_queries = nullptr;
     s->open = false; s->n_q = 0; s->n_shards = n_shards;
     if (!n_reads) { s->pass = KmPass{d_bases, d_offs, 0, 0, 0, max_read_len, nullptr, true}; s->open = true; return KMAT_OK; }
-    if ((rc = km_reserve_cands(c, n_reads)) != KMAT_OK) return rc;
+    if ((rc = km_reserve_cands(c, n_reads, max_read_len)) != KMAT_OK) return rc;
     s->pass = KmPass{d_bases, d_offs, n_reads, 0, total_bases, max_read_len, nullptr, true};
     if ((rc = km_prepare_pass(c, s->pass, st, &s->hit, &s->variant)) != KMAT_OK) return rc;
     if ((rc = km_grow(&s->d_xq, &s->cap_xq, total_bases + 1)) != KMAT_OK) return rc;

@@ -262,3 +262,44 @@ def test_pipelined_pass_matches_serial(golden_lists, dbs):
         r2, c2, l2 = ctx.label(seqs)
         assert ctx.tails(r2, c2, l2, prn_all=True) == serial, sub
         assert np.array_equal(r2["status"], res["status"]) and np.array_equal(r2["n_cand"], res["n_cand"])
+
+
+@pytest.mark.parametrize("long_kernel", [True, False])
+def test_long_reads_with_internal_repeats_match_oracle(golden_lists, dbs, long_kernel, monkeypatch):
+    """10 kbp-class reads full of internal repeats, N runs and case changes: the CTA-per-read probe kernel (dedup set in
+    shared memory, lowest position wins) and the any-length kernel (global set, chunks in order) must both reproduce the
+    oracle's first-occurrence semantics."""
+    if not long_kernel:
+        monkeypatch.setenv("KMAT_NO_LONG_PROBE", "1")
+    g = golden_lists
+    inp = S.build_inputs("lists", g.workdir + "/rep")
+    rng = np.random.default_rng(31)
+    gstr = [fx.codes_to_str(x) for x in inp["genomes"].values()]
+    seqs = []
+    for L in [257, 300, 1000, 2999, 5000, 9999, 10000, 11999, 12000, 12001, 20000]:
+        for rep in range(4):
+            gs = gstr[int(rng.integers(0, 6))]
+            parts = []
+            while sum(map(len, parts)) < L:
+                a = int(rng.integers(0, len(gs) - 400))
+                piece = gs[a:a + int(rng.integers(25, 400))]
+                parts.append(piece)
+                if rng.random() < 0.5:
+                    parts.append(parts[int(rng.integers(0, len(parts)))])          # an earlier piece again
+            s = "".join(parts)[:L]
+            if rep == 1:
+                s = s[:100] + "N" * 3 + s[103:L // 2] + "n" + s[L // 2 + 1:]
+            if rep == 2:
+                s = s.lower()
+            if rep == 3:
+                s = s[:L // 2] + s[:L - L // 2]                                     # the first half twice
+            seqs.append(s)
+    ctx = make_ctx(g, dbs[g.name], "run_rl")
+    orc = oracle_for(g, "run_rl")
+    res, cands, lin = ctx.label(seqs)
+    ores, _, _ = orc.label(seqs)
+    assert (res["status"] != 6).all()
+    for f in ("valid_kmers", "cand_kmer_cnt", "bin_sel", "n_cand"):
+        sel = ores["status"] >= 2
+        assert np.array_equal(res[f][sel], ores[f][sel]), (f, np.nonzero(res[f][sel] != ores[f][sel])[0][:5])
+    assert ctx.tails(res, cands, lin, prn_all=True) == orc.tails(ores)
