@@ -82,27 +82,56 @@ __global__ void __launch_bounds__(256) km_shard_count_kernel(const uint32_t *__r
     __syncthreads();
     if (threadIdx.x < n_shards && hist[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
 }
+#define KM_SCATTER_TILE 4096
 __global__ void __launch_bounds__(256) km_shard_scatter_kernel(const uint32_t *__restrict__ hit, const uint64_t *__restrict__ xq, uint64_t n_pos,
                                                                uint32_t n_shards, KmShardSeg base, unsigned long long *cursors,
                                                                uint64_t *q, uint32_t *origin) {
+    // A CTA takes tiles of 4096 positions: it counts the tile's queries per owner in shared memory, reserves their places
+    // with ONE global atomic per owner and tile (a warp-level atomic per 32 positions on 16 hot addresses cost 4 ms per
+    // 2^20 reads), then walks the tile again and hands out the places from shared-memory counters.
+    __shared__ unsigned int s_cnt[KM_MAX_SHARDS];
+    __shared__ unsigned long long s_base[KM_MAX_SHARDS];
     const int lane = threadIdx.x & 31;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t first = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31);           // warp-uniform loop bounds
-    for (uint64_t i0 = first; i0 < n_pos; i0 += stride) {
-        const uint64_t i = i0 + lane;
-        const bool m = i < n_pos && hit[i] == KM_HIT_MISS;
-        const uint64_t x = m ? xq[i] : 0;
-        const uint32_t owner = m ? km_owner_of_x(x, n_shards) : 0xFFFFFFFFu;
-        const uint32_t act = __ballot_sync(KM_FULL, m);
-        if (m) {
-            const uint32_t grp = __match_any_sync(act, owner);                                   // one atomic per owner and warp
-            const int leader = __ffs(grp) - 1;
-            unsigned long long b = 0;
-            if (lane == leader) b = atomicAdd(&cursors[owner], (unsigned long long)__popc(grp));
-            b = ((unsigned long long)__shfl_sync(grp, (uint32_t)(b >> 32), leader) << 32) | __shfl_sync(grp, (uint32_t)b, leader);
-            const unsigned long long dst = base.start[owner] + b + __popc(grp & ((1u << lane) - 1));
-            q[dst] = x; origin[dst] = (uint32_t)i;
+    const uint64_t n_tiles = (n_pos + KM_SCATTER_TILE - 1) / KM_SCATTER_TILE;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t t0 = tile * KM_SCATTER_TILE;
+        if (threadIdx.x < KM_MAX_SHARDS) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        unsigned int mine = 0;
+        for (int j = 0; j < KM_SCATTER_TILE / 256; j++) {
+            const uint64_t i = t0 + (uint64_t)j * 256 + threadIdx.x;
+            const bool m = i < n_pos && hit[i] == KM_HIT_MISS;
+            const uint32_t owner = m ? km_owner_of_x(xq[i], n_shards) : 0xFFFFFFFFu;
+            for (uint32_t o = 0; o < n_shards; o++) {
+                const uint32_t bal = __ballot_sync(KM_FULL, owner == o);
+                if ((uint32_t)lane == o) mine += __popc(bal);
+            }
         }
+        if ((uint32_t)lane < n_shards && mine) atomicAdd(&s_cnt[lane], mine);
+        __syncthreads();
+        if (threadIdx.x < n_shards) {
+            const unsigned int cn = s_cnt[threadIdx.x];
+            s_base[threadIdx.x] = base.start[threadIdx.x] + (cn ? atomicAdd(&cursors[threadIdx.x], (unsigned long long)cn) : 0ull);
+            s_cnt[threadIdx.x] = 0;
+        }
+        __syncthreads();
+        for (int j = 0; j < KM_SCATTER_TILE / 256; j++) {
+            const uint64_t i = t0 + (uint64_t)j * 256 + threadIdx.x;
+            const bool m = i < n_pos && hit[i] == KM_HIT_MISS;
+            const uint64_t x = m ? xq[i] : 0;
+            const uint32_t owner = m ? km_owner_of_x(x, n_shards) : 0xFFFFFFFFu;
+            const uint32_t act = __ballot_sync(KM_FULL, m);
+            if (m) {
+                const uint32_t grp = __match_any_sync(act, owner);
+                const int leader = __ffs(grp) - 1;
+                unsigned int off = 0;
+                if (lane == leader) off = atomicAdd(&s_cnt[owner], (unsigned int)__popc(grp));
+                off = __shfl_sync(grp, off, leader);
+                const unsigned long long dst = s_base[owner] + off + __popc(grp & ((1u << lane) - 1));
+                q[dst] = x; origin[dst] = (uint32_t)i;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -188,7 +217,7 @@ extern "C" int kmat_shard_encode(kmat_ctx *c, const char *d_bases, const uint64_
     s->n_q = tot;
     if ((rc = km_grow(&s->d_q, &s->cap_q, tot + 1)) != KMAT_OK) return rc;
     if ((rc = km_grow(&s->d_origin, &s->cap_origin, tot + 1)) != KMAT_OK) return rc;
-    km_shard_scatter_kernel<<<grid, 256, 0, st>>>(c->d_hit, s->d_xq, total_bases, (uint32_t)n_shards, base, s->d_counts + KM_MAX_SHARDS, s->d_q, s->d_origin);
+    km_shard_scatter_kernel<<<(int)std::min<uint64_t>((total_bases + KM_SCATTER_TILE - 1) / KM_SCATTER_TILE, 148ull * 8), 256, 0, st>>>(c->d_hit, s->d_xq, total_bases, (uint32_t)n_shards, base, s->d_counts + KM_MAX_SHARDS, s->d_q, s->d_origin);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     *d_queries = s->d_q;
