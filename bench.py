@@ -52,6 +52,8 @@ def parse_args():
                     help="replicated: every GPU holds the whole table (configs[1]); sharded: table partitioned by k-mer hash over "
                          "the ranks, query k-mers exchanged with an NCCL all-to-all (configs[3] layout on the configs[1] table)")
     ap.add_argument("--round-reads", type=int, default=1 << 20, help="reads per exchange round in sharded mode")
+    ap.add_argument("--exchange-slots", type=int, default=2, choices=[1, 2],
+                    help="sharded mode: 2 = two contexts per rank, the encode of round i+1 and the finish of round i overlap the exchanges")
     ap.add_argument("--pipeline", type=int, default=1, help="sub-batches per pass (kmat_ctx_set_pipeline); -1 automatic, 1 serial")
     return ap.parse_args()
 
@@ -189,7 +191,7 @@ def run_cpu_sample(sample, workdir, threads):
     return n / dt, dt
 
 
-def sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, setup_s, launches0, tstream):
+def sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, setup_s, launches0, tstream, ctx2=None):
     """DB-sharded arm: every rank holds 1/world of the table and its own reads; per round of --round-reads reads the
     first-occurrence k-mers go to their owner ranks (all-to-all), hit words and list records come back (all-to-all)."""
     import numpy as np
@@ -199,7 +201,11 @@ def sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, 
     n, L = reads.shape
     stream = tstream.cuda_stream
     ex = sharded.DistExchange(dev) if world > 1 else sharded.LocalExchange(sharded.LocalGroup(1), 0, sync=torch.cuda.synchronize)
-    lab = sharded.ShardedLabeler(sharded.CudaPhases(ctx, dev, world, stream), ex, round_reads=a.round_reads)
+    if ctx2 is None:
+        lab = sharded.ShardedLabeler(sharded.CudaPhases(ctx, dev, world, stream), ex, round_reads=a.round_reads)
+    else:
+        lab = sharded.ShardedLabeler(sharded.CudaPhases(ctx, dev, world, torch_stream=torch.cuda.Stream()), ex, round_reads=a.round_reads,
+                                     phases2=sharded.CudaPhases(ctx2, dev, world, torch_stream=torch.cuda.Stream()))
     rr = min(a.round_reads, n)
     offs_full = (torch.arange(rr + 1, device=dev, dtype=torch.int64) * L).contiguous()       # chunk-local offsets, every round
     d_out = torch.empty(n * api.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
@@ -217,6 +223,8 @@ def sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, 
         torch.cuda.synchronize()
 
     ctx.set_stats(False)
+    if ctx2 is not None:
+        ctx2.set_stats(False)
     for _ in range(a.warmup):
         step()
     barrier()
@@ -235,7 +243,10 @@ def sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, 
     # one more, untimed step with a CUDA event after every phase: where a round's time goes
     lab.timing = {}
     keep = (lab.lookups, lab.served, lab.payload_words, lab.rounds)
+    ph2_keep, lab.ph2 = lab.ph2, None              # the phase split is taken on the serial schedule
     step()
+    lab.ph2 = ph2_keep
+    torch.cuda.synchronize()
     phase_ms = {k: round(v, 2) for k, v in lab.timing.items()}
     lab.timing = None
     lab.lookups, lab.served, lab.payload_words, lab.rounds = keep
@@ -268,7 +279,7 @@ def sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, 
                                       f"(8 B), all-to-all of hit words (4 B) + list records back ({'NCCL, torch.distributed' if world > 1 else 'single rank'})"},
             "kmer_lookups_per_s": lookups_step / (ms_step * 1e-3), "lookups_per_read": lookups_step / (world * n),
             "exchange_bytes_per_step": int(lookups_step * 12 + int(tot[1].item()) / a.steps * 4), "reads_error": int(tot[2].item()),
-            "reads_labeled": int(tot[3].item()), "phase_ms_rank0": phase_ms, "labels_checksum_rank0": labels_checksum,
+            "reads_labeled": int(tot[3].item()), "phase_ms_rank0": phase_ms, "exchange_slots": 2 if ctx2 is not None else 1, "labels_checksum_rank0": labels_checksum,
             "roofline": {"bound": "hbm", "kernel": "km_shard_probe_kernel", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
                          "peak_source": peak_src, "note": "per-kernel split not measured in sharded mode; see the replicated line"},
             "e2e": None, "gpu_launches": int(api.lib().kmat_launch_count() - launches0), "clocks": clocks, "setup_s": setup_s,
@@ -385,7 +396,8 @@ def main():
             ctx.label_device(reads.data_ptr(), d_offs.data_ptr(), n, total, L, None, stream)
 
         if sharded_mode:
-            sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, setup_s, launches0, tstream)
+            ctx2 = api.Ctx(db, inputs, api.default_opts(min_kmer=30, hbias=0.0, sdiff=1.0, min_score=0.0, want_lineage=0)) if a.exchange_slots == 2 else None
+            sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, setup_s, launches0, tstream, ctx2)
             return
 
         def barrier():

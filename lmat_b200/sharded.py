@@ -52,6 +52,12 @@ class DistExchange:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
         return bool(t.item())
 
+    def max_int(self, v):
+        import torch
+        t = torch.tensor([int(v)], dtype=torch.int64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return int(t.item())
+
 
 class LocalGroup:
     """Shared state of `world` ranks running as threads of one process."""
@@ -98,6 +104,13 @@ class LocalExchange:
         self.g.barrier.wait()
         return r
 
+    def max_int(self, v):
+        self.g.slots[self.rank] = int(v)
+        self.g.barrier.wait()
+        r = max(self.g.slots)
+        self.g.barrier.wait()
+        return r
+
 
 # ------------------------------------------------------------------------------------------------
 # device phases over the C ABI
@@ -120,8 +133,18 @@ def _wrap(ptr, count, dtype, device):
 class CudaPhases:
     """The three libkmat phases of a round for one rank (api.Ctx over this rank's table shard)."""
 
-    def __init__(self, ctx, device, n_shards, stream=None):
+    def __init__(self, ctx, device, n_shards, stream=None, torch_stream=None):
+        """stream: raw cudaStream_t handle the library launches on (None = the ctx's own).  torch_stream: a torch.cuda.Stream
+        instead -- the phases AND this slot's exchanges then run on it (ShardedLabeler's two-slot pipeline)."""
         self.ctx, self.device, self.n_shards, self.stream = ctx, device, n_shards, stream
+        self.tstream = torch_stream
+        if torch_stream is not None:
+            self.stream = torch_stream.cuda_stream
+
+    def on_stream(self):
+        import contextlib
+        import torch
+        return torch.cuda.stream(self.tstream) if self.tstream is not None else contextlib.nullcontext()
 
     def empty_round(self):
         """Arguments of a round without reads (this rank still serves the others' queries)."""
@@ -152,8 +175,11 @@ class ShardedLabeler:
     """Runs the rounds of one rank.  Every rank of the group must call run() the same number of times; inside, ranks
     keep exchanging (with empty contributions once their own reads are done) until every rank has finished."""
 
-    def __init__(self, phases, exchange, round_reads=1 << 20, round_bases=(1 << 32) - (1 << 20)):
-        self.ph, self.ex = phases, exchange
+    def __init__(self, phases, exchange, round_reads=1 << 20, round_bases=(1 << 32) - (1 << 20), phases2=None):
+        """phases2: a second set of phases over a second context of the same shard.  Rounds then alternate between the two
+        slots and the encode phase of round i+1 is queued (on the other slot's stream) before round i's query exchange is
+        waited for, its finish phase overlaps the next round's exchange: see _run_pipelined."""
+        self.ph, self.ex, self.ph2 = phases, exchange, phases2
         self.round_reads, self.round_bases = int(round_reads), int(round_bases)
         self.lookups = 0            # first-occurrence k-mers this rank sent out (its unique lookups)
         self.served = 0             # queries this rank answered
@@ -179,6 +205,8 @@ class ShardedLabeler:
         """rounds: list of (r0, r1); round_args(r0, r1) -> (*encode_args, out): what the phases' encode() takes (CudaPhases:
         bases_ptr, offs_ptr, n_reads, total_bases, max_len with offsets local to the chunk) followed by what finish()
         gets as its output argument.  on_round(r0, r1) is called after each finished round of this rank."""
+        if self.ph2 is not None:
+            return self._run_pipelined(rounds, round_args, on_round)
         i = 0
         while True:
             mine = i < len(rounds)
@@ -196,6 +224,54 @@ class ShardedLabeler:
             i += 1
             self.rounds += 1
         self._collect_timing()
+
+    def _run_pipelined(self, rounds, round_args, on_round):
+        """Two slots (contexts + streams), rounds alternate.  All ranks issue the same sequence of collectives: per round
+        counts, queries | counts, hit words, list records -- the encode of the next round carries none."""
+        import contextlib
+        ph = [self.ph, self.ph2]
+        n_rounds = self.ex.max_int(len(rounds))              # one collective instead of one per round
+        cur = None
+        if getattr(ph[0], "tstream", None) is not None:
+            import torch
+            cur = torch.cuda.current_stream()
+            for p in ph:
+                p.tstream.wait_stream(cur)
+
+        def ctx(p):
+            return p.on_stream() if hasattr(p, "on_stream") else contextlib.nullcontext()
+
+        def encode(i):
+            p = ph[i % 2]
+            a = round_args(*rounds[i]) if i < len(rounds) else p.empty_round()
+            with ctx(p):
+                q, counts = p.encode(*a[:-1])
+            return a, q, counts
+
+        nxt = encode(0) if n_rounds else None
+        for i in range(n_rounds):
+            p = ph[i % 2]
+            args, send_q, send_counts = nxt
+            self.lookups += int(np.sum(send_counts))
+            with ctx(p):
+                recv_counts = self.ex.counts(send_counts)
+                recv_q = self.ex.all_to_all(send_q, send_counts, recv_counts)
+            if i + 1 < n_rounds:
+                nxt = encode(i + 1)                          # on the other slot's stream: runs while the queries travel
+            with ctx(p):
+                reply, payload, pay_counts = p.serve(recv_q, recv_counts)
+                self.served += int(np.sum(recv_counts))
+                self.payload_words += int(np.sum(pay_counts))
+                my_pay_counts = self.ex.counts(pay_counts)
+                my_reply = self.ex.all_to_all(reply, recv_counts, send_counts)
+                my_payload = self.ex.all_to_all(payload, pay_counts, my_pay_counts)
+                p.finish(my_reply, my_payload, my_pay_counts, args[-1])      # asynchronous: overlaps the next round's exchange
+            if i < len(rounds) and on_round:
+                on_round(*rounds[i], i % 2)
+            self.rounds += 1
+        if cur is not None:
+            for p in ph:
+                cur.wait_stream(p.tstream)
 
     def _mark(self, name):
         """Phase timing (opt-in: self.timing = {} before run()): a CUDA event on the current stream after each phase."""
@@ -219,6 +295,11 @@ class ShardedLabeler:
         self._marks = []
 
     def _round(self, args):
+        import contextlib
+        with (self.ph.on_stream() if hasattr(self.ph, "on_stream") else contextlib.nullcontext()):     # phases AND exchanges on the phases' stream
+            self._round_on_stream(args)
+
+    def _round_on_stream(self, args):
         out_ptr = args[-1]
         self._mark("start")
         send_q, send_counts = self.ph.encode(*args[:-1])
@@ -239,7 +320,7 @@ class ShardedLabeler:
         self._mark("finish")
 
 
-def label_sequences(ctx, exchange, device, seqs, n_shards, round_reads=1 << 20):
+def label_sequences(ctx, exchange, device, seqs, n_shards, round_reads=1 << 20, ctx2=None):
     """Convenience (tests, small inputs): label a list of reads through the sharded rounds of this rank and return
     (results, candidates) like api.Ctx.label -- numpy arrays, cand_off indexing the returned candidate array."""
     import torch
@@ -248,7 +329,12 @@ def label_sequences(ctx, exchange, device, seqs, n_shards, round_reads=1 << 20):
     offs_host = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
     flat = b"".join(x if isinstance(x, bytes) else x.encode("latin-1") for x in seqs)
     bases = torch.frombuffer(bytearray(flat if flat else b"\0"), dtype=torch.uint8).to(device)
-    lab = ShardedLabeler(CudaPhases(ctx, device, n_shards), exchange, round_reads=round_reads)
+    if ctx2 is None:
+        lab = ShardedLabeler(CudaPhases(ctx, device, n_shards), exchange, round_reads=round_reads)
+    else:                                   # two-slot pipeline: each slot its own context and torch stream
+        lab = ShardedLabeler(CudaPhases(ctx, device, n_shards, torch_stream=torch.cuda.Stream(device)), exchange, round_reads=round_reads,
+                             phases2=CudaPhases(ctx2, device, n_shards, torch_stream=torch.cuda.Stream(device)))
+    ctxs = [ctx, ctx2]
     res_parts, cand_parts, keep = [], [], []
     state = {"cands": 0}
 
@@ -258,9 +344,9 @@ def label_sequences(ctx, exchange, device, seqs, n_shards, round_reads=1 << 20):
         return (bases.data_ptr() + int(offs_host[r0]), o.data_ptr(), r1 - r0, int(offs_host[r1] - offs_host[r0]),
                 int(lens[r0:r1].max()) if r1 > r0 else 0, None)
 
-    def on_round(r0, r1):
+    def on_round(r0, r1, slot=0):
         torch.cuda.synchronize(device)
-        optr, cptr, n_c = ctx.device_results()
+        optr, cptr, n_c = ctxs[slot].device_results()
         res = _wrap(optr, (r1 - r0) * api.RESULT_DTYPE.itemsize, torch.uint8, device).cpu().numpy().view(api.RESULT_DTYPE).copy()
         cands = _wrap(cptr, n_c * api.PAIR_DTYPE.itemsize, torch.uint8, device).cpu().numpy().view(api.PAIR_DTYPE).copy()
         res["cand_off"] += np.uint64(state["cands"])

@@ -36,8 +36,8 @@ def run_ranks(world, fn):
     return out
 
 
-@pytest.mark.parametrize("world,opts", [(2, "run_rl"), (2, "permissive"), (2, "prune3"), (3, "run_rl"), (3, "permissive"), (3, "prune3"), (8, "run_rl")])
-def test_sharded_labels_equal_replicated(golden_lists, world, opts):
+@pytest.mark.parametrize("world,opts,slots", [(2, "run_rl", 1), (2, "permissive", 1), (2, "prune3", 2), (3, "run_rl", 2), (3, "permissive", 2), (3, "prune3", 1), (8, "run_rl", 2)])
+def test_sharded_labels_equal_replicated(golden_lists, world, opts, slots):
     import torch
     g = golden_lists
     t = api.Table.from_arrays(g.kmers, g.offs, g.ids, g.kmer_len, g.tid_bytes)
@@ -57,12 +57,13 @@ def test_sharded_labels_equal_replicated(golden_lists, world, opts):
     # uneven split: rank 0 gets half of the reads, so the others keep serving after their own reads are done
     cut = [0, len(seqs) // 2] + [len(seqs) // 2 + (len(seqs) - len(seqs) // 2) * (i + 1) // (world - 1) for i in range(world - 1)]
     ctxs = [make_ctx(g, shards[r], opts) for r in range(world)]
+    ctxs2 = [make_ctx(g, shards[r], opts) for r in range(world)] if slots == 2 else None      # two-slot pipeline of the driver
     grp = sharded.LocalGroup(world)
 
     def rank(r):
         ex = sharded.LocalExchange(grp, r, sync=lambda: torch.cuda.synchronize())
         mine = seqs[cut[r]:cut[r + 1]]
-        rr, cc, lab = sharded.label_sequences(ctxs[r], ex, "cuda:0", mine, world, round_reads=97)
+        rr, cc, lab = sharded.label_sequences(ctxs[r], ex, "cuda:0", mine, world, round_reads=97, ctx2=ctxs2[r] if ctxs2 else None)
         return ctxs[r].tails(rr, cc, np.zeros(0, dtype=api.PAIR_DTYPE), prn_all=True), lab
 
     outs = run_ranks(world, rank)

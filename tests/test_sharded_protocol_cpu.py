@@ -71,7 +71,7 @@ class NumpyPhases:
                 out[self.origin[i]] = [int(t) for t in payload[at + 1:at + 1 + n]]
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, pipelined=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
@@ -92,18 +92,23 @@ def _worker(rank, world, port, q):
             return "".join(parts) + "N" + "".join("ACGT"[x] for x in rng.integers(0, 4, 30))
         reads = [read() for _ in range(5 * (3 + 2 * rank))]
         ph = NumpyPhases(rank, world, kmers, offs, ids, k)
-        lab = sharded.ShardedLabeler(ph, sharded.DistExchange("cpu"), round_reads=5)
+        ph2 = NumpyPhases(rank, world, kmers, offs, ids, k) if pipelined else None
+        lab = sharded.ShardedLabeler(ph, sharded.DistExchange("cpu"), round_reads=5, phases2=ph2)
         got = {}
-        out_round = {}
+        out_rounds = [{}, {}]
+        turn = [0]
         lens = np.array([len(r) for r in reads])
         rounds = lab.plan(np.concatenate([[0], np.cumsum(lens)]))
 
         def round_args(r0, r1):
-            out_round.clear()
-            return (reads[r0:r1], out_round)
+            o = out_rounds[turn[0] % 2]                # the pipelined driver asks for round i+1 before round i has finished
+            turn[0] += 1
+            o.clear()
+            return (reads[r0:r1], o)
 
-        def on_round(r0, r1):
-            for (ri, p), lst in out_round.items():
+        def on_round(r0, r1, slot=None):
+            o = out_rounds[slot] if slot is not None else out_rounds[(turn[0] - 1) % 2]
+            for (ri, p), lst in o.items():
                 got[(r0 + ri, p)] = lst
         lab.run(rounds, round_args, on_round)
         full = {int(km): [int(x) for x in ids[int(offs[i]):int(offs[i + 1])]] for i, km in enumerate(kmers)}
@@ -118,13 +123,13 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_rounds_over_gloo(world):
+@pytest.mark.parametrize("world,pipelined", [(2, False), (3, False), (2, True), (3, True)])
+def test_sharded_rounds_over_gloo(world, pipelined):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + world
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    port = 29500 + (os.getpid() % 2000) + world + (10 if pipelined else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, pipelined)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in range(world)]
