@@ -37,6 +37,41 @@ def test_compute_call_without_gpu_fails_loudly():
     assert e.value.code == -2          # KMAT_ERR_NO_DEVICE: there is no CPU fallback
 
 
+def test_every_device_entry_point_fails_loudly_without_gpu(tmp_path):
+    """The entry points added for gene_label, null models, content_summ, the peer gather probe: argument errors are
+    reported as such, and a valid call without a device is KMAT_ERR_NO_DEVICE -- never a silent CPU result."""
+    import ctypes as C
+    L = api.lib()
+    with pytest.raises(api.KmatError) as e:
+        api.KmerCov([8, 21])                       # k > 20 does not fit the 40-bit k-mer field
+    assert e.value.code == -7
+    with pytest.raises(api.KmatError) as e:
+        api.KmerCov(list(range(1, 10)))            # more than 8 k values
+    assert e.value.code == -1
+    if api.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.KmatError) as e:
+        api.KmerCov([8, 20])
+    assert e.value.code == -2
+    with pytest.raises(api.KmatError) as e:
+        api.null_draw_reads(1, 0, 4, 50)
+    assert e.value.code == -2
+    with pytest.raises(api.KmatError) as e:
+        api.gather_bench_peer(0, 1, 1 << 20, 32, 1 << 10, 1)
+    assert e.value.code == -2
+    free_b, total_b = C.c_uint64(), C.c_uint64()
+    assert L.kmat_device_memory(0, C.byref(free_b), C.byref(total_b)) == -2
+    # the host binaries refuse to run too
+    from lmat_b200 import build
+    build.build_all()
+    import subprocess
+    for exe, args in ((build.RRL_BIN, ["-d", "x", "-o", str(tmp_path / "o"), "-t", "1", "-i", "50", "-g", "10", "-f", "m"]),
+                      (build.GL_BIN, ["-d", "x", "-o", str(tmp_path / "o"), "-l", "lst"]),
+                      (build.CS_BIN, ["-f", "lst", "-l", "fs", "-c", "tree", "-o", str(tmp_path / "o")])):
+        p = subprocess.run([exe] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert p.returncode != 0, exe
+
+
 def test_table_from_sorteddb_layout_roundtrip(golden_small):
     """Walk the reference's SortedDb memory layout (rebuilt by oracle_py.SortedDbArrays from the golden
     dump) through kmat_table_from_sorteddb and get the dump back."""
