@@ -397,7 +397,9 @@ __global__ void __launch_bounds__(KB_WARPS * 32, NCH == 5 ? 4 : 1) km_cand_kerne
         bool done = false;
         if (len < k) { res.status = KMAT_ST_SHORT_LEN; res.n1 = len; res.n2 = k; res.valid_kmers = 0; done = true; }             // :1217-1218
         else if (hd.x < X.opt.min_kmer) { res.status = KMAT_ST_SHORT_VALID; res.n1 = hd.x; res.n2 = X.opt.min_kmer; done = true; }   // :1232-1233
-        else if (NCH ? np > NCH * 32 : (uint32_t)np > P.long_cap) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; done = true; st_err++; }
+        else if (NCH ? np > NCH * 32 : ((uint32_t)np > P.long_cap || np > 0xFFFF)) {      // first-appearance keys hold 16-bit positions: reads beyond 65 kbp are refused, not mis-ordered
+            res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; done = true; st_err++;
+        }
         if (done) { if (lane == 0) P.out[r] = res; continue; }
 
         KbCand K;
