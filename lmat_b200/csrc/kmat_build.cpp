@@ -17,10 +17,15 @@
 //   * optional 32->16-bit id map (-f): every stored id goes through it; a missing id is the reference's assert
 //     ("bad read/single/set", :455-458 etc.) and KMAT_ERR_BAD_TAXID here.
 // The physical layout (top tier, pages, the kmer % 4096 echo) is not reproduced: libkmat has its own.
+#include <algorithm>
+#include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <memory>
 #include <queue>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <unordered_set>
@@ -71,6 +76,7 @@ struct Builder {
     bool has_adaptor = false;
     KmerStream human;
     uint64_t last_human = ~0ull, last_kmer = 0;
+    uint64_t first_kmer = 0; bool any_kmer = false;      // first raw k-mer this builder saw (the parallel build checks the order across files)
     uint16_t HUMAN_16 = 0, ADAPTOR_16 = 0;
     kmat_table *t;
     std::string err;
@@ -129,6 +135,7 @@ struct Builder {
             if (fread(&kmer, 8, 1, in) != 1) return fail(KMAT_ERR_FORMAT, std::string(fn) + ": truncated record");
             if (last_kmer > 0 && kmer <= last_kmer)
                 return fail(KMAT_ERR_FORMAT, "Kmers arriving out of order.  New: " + std::to_string(kmer) + " last: " + std::to_string(last_kmer));
+            if (!any_kmer) { any_kmer = true; first_kmer = kmer; }
             while (last_human < kmer) {                                   // new human-only k-mers (:170-226)
                 const bool ad = has_adaptor && adaptor.count(last_human);
                 push_single(last_human, ad ? (ADAPTOR_16 ? ADAPTOR_16 : 32630u) : (HUMAN_16 ? HUMAN_16 : 9606u));
@@ -251,6 +258,63 @@ extern "C" int kmat_table_build(const char *const *files, int n_files, const kma
     if (opts->adaptor_kmers && opts->adaptor_kmers[0]) afp = fopen(opts->adaptor_kmers, "r");
     b.human.fp = hfp; b.human.k = opts->kmer_length;
     int rc = KMAT_OK;
+    // Without a human k-mer stream (the only state that runs across files besides the ascending-order check) every input
+    // file can be parsed on its own: one worker per file, partial tables appended in file order.  The reference's build is
+    // one thread; KMAT_BUILD_SERIAL=1 keeps ours serial too.
+    if (!hfp && n_files > 1 && !getenv("KMAT_BUILD_SERIAL")) {
+        if (afp) {
+            KmerStream as; as.fp = afp; as.k = opts->kmer_length;
+            for (uint64_t v = as.next(); v != ~0ull; v = as.next()) b.adaptor.insert(v);
+            b.has_adaptor = true;
+            if (as.bad) { fclose(afp); kmat_set_error("adaptor k-mer file: a line shorter than k"); delete t; return KMAT_ERR_FORMAT; }
+            fclose(afp);
+        }
+        struct Part { std::unique_ptr<kmat_table> tab; std::unique_ptr<Builder> bld; bool ok = true; };
+        std::vector<Part> parts((size_t)n_files);
+        std::atomic<int> next{0};
+        auto worker = [&] {
+            for (int i = next++; i < n_files; i = next++) {
+                Part &pt = parts[(size_t)i];
+                pt.tab.reset(new kmat_table());
+                pt.tab->kmer_len = opts->kmer_length;
+                pt.tab->own_offs.push_back(0);
+                pt.bld.reset(new Builder(*opts, pt.tab.get()));
+                Builder &bi = *pt.bld;
+                bi.br_map = b.br_map; bi.has_br = b.has_br; bi.species_map = b.species_map; bi.adaptor = b.adaptor; bi.has_adaptor = b.has_adaptor;
+                bi.HUMAN_16 = b.HUMAN_16; bi.ADAPTOR_16 = b.ADAPTOR_16;
+                pt.ok = bi.add_file(files[i]);
+            }
+        };
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const int n_thr = (int)std::min<unsigned>({(unsigned)n_files, hw, 32u});
+        std::vector<std::thread> th;
+        for (int i = 0; i < n_thr; i++) th.emplace_back(worker);
+        for (auto &x : th) x.join();
+        uint64_t last = 0;
+        for (int i = 0; i < n_files && rc == KMAT_OK; i++) {
+            Part &pt = parts[(size_t)i];
+            Builder &bi = *pt.bld;
+            // the order check of add_data across the file boundary (SortedDb.cpp:164-167); a failure inside an earlier file wins
+            if (bi.any_kmer && last > 0 && bi.first_kmer <= last) {
+                // the serial build meets this record before anything that fails later in file i
+                rc = KMAT_ERR_FORMAT; b.err = "Kmers arriving out of order.  New: " + std::to_string(bi.first_kmer) + " last: " + std::to_string(last);
+                break;
+            }
+            if (!pt.ok) { rc = bi.err_code; b.err = bi.err; break; }
+            const uint64_t base = t->own_ids.size();
+            t->own_kmers.insert(t->own_kmers.end(), pt.tab->own_kmers.begin(), pt.tab->own_kmers.end());
+            t->own_ids.insert(t->own_ids.end(), pt.tab->own_ids.begin(), pt.tab->own_ids.end());
+            for (size_t j = 1; j < pt.tab->own_offs.size(); j++) t->own_offs.push_back(pt.tab->own_offs[j] + base);
+            if (bi.any_kmer) last = bi.last_kmer;
+            pt.bld.reset(); pt.tab.reset();
+        }
+        if (rc != KMAT_OK) { kmat_set_error("%s", b.err.c_str()); delete t; return rc; }
+        t->tid_bytes = b.has_br ? 2 : 4;
+        t->n_kmers = t->own_kmers.size(); t->n_ids = t->own_ids.size();
+        t->kmers = t->own_kmers.data(); t->offs = t->own_offs.data(); t->ids = t->own_ids.data();
+        *out = t;
+        return KMAT_OK;
+    }
     for (int i = 0; i < n_files && rc == KMAT_OK; i++) {
         if (i == 0 && afp) {                                               // get_kmer_set on the first add_data call (:112-116)
             KmerStream as; as.fp = afp; as.k = opts->kmer_length;
