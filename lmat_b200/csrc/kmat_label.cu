@@ -20,7 +20,7 @@
 #define KB_LIN 128         // lineage entries in findReadLabelVer2
 #define KS_THREADS 128     // threads per CTA of the scoring kernel (one read per thread)
 #define KMAT_ST_PENDING 7  // internal: candidates built, scoring still to run
-#define KMAT_ST_PENDING_BIG 8   // internal: candidates built by the slow kernel (more than KB_CMAX of them), scored by the big scoring kernel
+#define KMAT_ST_PENDING_BIG 8   // internal: candidates built by km_cand_big_kernel (more than KB_CMAX of them), scored by km_score_big_kernel
 #define KMAT_ST_DEFERRED 9      // internal: queued for the slow candidate kernel
 #define KB_CBIG 512        // candidate taxids per read the slow path holds (reads beyond it: KMAT_ERR_UNSUPPORTED)
 #define KB_LBIG 1024       // lineage entries of the big scoring kernel
@@ -364,7 +364,7 @@ __device__ __forceinline__ unsigned long long kb_chunk(const KmScoreParams &P, K
     return mymask;
 }
 
-// A read K3's register-resident candidate set cannot hold: hand it to the slow kernel (all lanes call; lane 0 acts)
+// A read K3's register-resident candidate set cannot hold: hand it to km_cand_big_kernel (all lanes call; lane 0 acts)
 __device__ __forceinline__ void kb_defer_big(const KmScoreParams &P, uint32_t r, kmat_read_result &res, int lane) {
     if (lane != 0) return;
     res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED;

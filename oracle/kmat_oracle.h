@@ -5,9 +5,9 @@
  * It exists only so that tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg can CHECK
  * the CUDA path.  Nothing under lmat_b200/ links, imports or calls it.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py compares this restatement line-for-line
- * with the unmodified reference binary (oracle/_ref/read_label, built by oracle/Makefile) on
- * generated fixtures, and tests/golden/ holds reference outputs it must reproduce.
+ * Parity status: PINNED.  tests/golden/ holds the outputs of the unmodified reference binaries (oracle/_ref/*, built by
+ * oracle/Makefile; generating scripts tests/golden/make_*golden.py) which this restatement must reproduce byte for byte
+ * (tests/test_oracle_golden.py, test_gene_label.py, test_null_model.py).
  *
  * The DB is consumed in the reference's own in-memory layout (SortedDb.hpp:143-148,453-481), so the
  * lookup restated here is the reference's two-level search, not the product's hash table.

@@ -153,7 +153,7 @@ def test_long_and_ragged_reads_match_oracle(golden_lists, dbs, opts):
 @pytest.mark.parametrize("opts", ["run_rl", "permissive", "prune3", "defaults"])
 def test_reads_with_more_than_64_candidates_match_oracle(golden_lists, dbs, opts):
     """Chimeric reads stitched from many genomes carry more candidate taxids than the warp kernel's 64 register slots:
-    they take the slow path (km_cand_slow_kernel + km_score_big_kernel, up to 512 candidates) and must come out exactly
+    they take the big kernels (km_cand_big_kernel + km_score_big_kernel, up to 512 candidates) and must come out exactly
     like the oracle's -- short reads (the <= 160-position kernel), medium and long ones (global position masks)."""
     g = golden_lists
     inp = S.build_inputs("lists", g.workdir + "/big_" + opts)
