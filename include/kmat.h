@@ -340,8 +340,10 @@ typedef struct kmat_read_batch kmat_read_batch;   /* one batch of reads: owned b
 int kmat_reader_open(const char *path, int fastq, kmat_reader **out);
 /* Same with `threads` parser threads.  FASTA in a regular file is mapped and cut at header lines into ~8 MB segments
  * that are parsed in parallel and handed out in file order, one segment per kmat_reader_next call (max_reads /
- * max_bases then do not apply); the (header, read) sequence is identical to the sequential reader's.  FASTQ, stdin
- * and threads <= 1 fall back to the sequential reader. */
+ * max_bases then do not apply); the (header, read) sequence is identical to the sequential reader's.  FASTQ files are
+ * cut at '@' lines that verifiably start a record (followed by sequence lines, a '+' / '-' line, one quality line and
+ * another '@' line or the end of the file); the reference's pairing of a FASTQ read with the previous record's header
+ * is carried across the cuts.  stdin and threads <= 1 fall back to the sequential reader. */
 int kmat_reader_open_mt(const char *path, int fastq, int threads, kmat_reader **out);
 void kmat_reader_close(kmat_reader *);
 kmat_read_batch *kmat_read_batch_new(void);

@@ -28,9 +28,10 @@ struct kmat_read_batch {
     std::string bases, hdrs;
     std::vector<uint64_t> offs, hdr_offs;
     std::vector<uint32_t> unknown;      // reads whose header is "unknown_hdr:<ordinal>" (needs the global ordinal)
+    std::string tail_hdr;               // parallel FASTQ: the header line of the segment's last record (the next segment's first read carries it)
     uint64_t first_ordinal = 1;
     uint32_t n = 0;
-    void clear() { bases.clear(); hdrs.clear(); offs.assign(1, 0); hdr_offs.assign(1, 0); unknown.clear(); n = 0; }
+    void clear() { bases.clear(); hdrs.clear(); offs.assign(1, 0); hdr_offs.assign(1, 0); unknown.clear(); tail_hdr.clear(); n = 0; }
 };
 
 // The line state machine of read_label main() (:1651-1713), independent of where the lines come from.
@@ -61,6 +62,8 @@ struct kmat_reader {
     std::vector<std::thread> workers;
     bool stop = false;
     uint64_t ordinal = 0;
+    bool mt_fastq = false;
+    std::string carry_hdr;                   // parallel FASTQ: header of the last record handed out so far
 };
 
 static const size_t kChunk = 8u << 20;
@@ -130,6 +133,14 @@ static void parse_lines(KmParseState &st, NextLine &&next_line, uint32_t max_rea
 }
 
 // ---- parallel mode ----------------------------------------------------------------------------------------------
+// FASTQ (-q): the state machine emits a read at its '+' line, paired with the header that was current BEFORE this record's
+// '@' line (:1689-1692, the reference's quirk), then skips the quality line.  A file cut right before a record's '@' line
+// parses independently on both sides except for that pairing: the first read of the right part must carry the header of
+// the left part's last record -- the worker returns it (tail_hdr) and kmat_reader_next patches it in, in file order.
+// Telling a record's '@' line from a quality line that happens to start with '@' needs context: a cut is only made at an
+// '@' line that is followed by >= 1 plain lines, a '+' / '-' line, one more line (the quality) and then an '@' line or the
+// end of the file.  A quality line starting with '@' is followed by the next header, so it never qualifies.
+//
 // A FASTA file cut right before a header line parses independently on both sides: at a '>' line the reference
 // pushes the pending read with the header that preceded it, which is also what the end-of-input branch (:1663-1669)
 // does for the last read of the left part, and the right part starts from the same fresh state as the file does.
@@ -149,14 +160,37 @@ static void km_reader_worker(kmat_reader *r) {
         b->clear();
         b->bases.reserve(r->seg[s + 1] - r->seg[s]);
         KmParseState st;
+        st.fastq = r->mt_fastq;
         KmMemLines src{r->map + r->seg[s], r->map + r->seg[s + 1]};
         while (!st.in_finished) parse_lines(st, [&](const char **ln, size_t *n) { return src.next(ln, n); }, 0xFFFFFFFFu, ~0ull, b);
+        b->tail_hdr = st.hdr_buff;
         {
             std::lock_guard<std::mutex> l(r->m);
             r->done[s] = b;
         }
         r->cv_done.notify_all();
     }
+}
+
+// Is the line starting at `p` the '@' line of a FASTQ record (see above)?
+static bool km_fastq_record_start(const char *map, size_t len, size_t p) {
+    if (p >= len || map[p] != '@') return false;
+    auto next_line = [&](size_t at) -> size_t { const char *nl = (const char *)memchr(map + at, '\n', len - at); return nl ? (size_t)(nl - map) + 1 : len; };
+    size_t q = next_line(p);
+    int plain = 0;
+    for (;;) {
+        if (q >= len) return false;
+        const char c = map[q];
+        if (c == '@') return false;
+        if (c == '+' || c == '-') break;
+        plain++;
+        q = next_line(q);
+    }
+    if (!plain) return false;
+    q = next_line(q);                        // the quality line
+    if (q >= len) return false;              // no quality line: leave the tail to one segment
+    q = next_line(q);
+    return q >= len || map[q] == '@';
 }
 
 static bool km_reader_start_mt(kmat_reader *r, int threads) {
@@ -176,7 +210,7 @@ static bool km_reader_start_mt(kmat_reader *r, int threads) {
         while (p < r->map_len) {
             const char *nl = (const char *)memchr(r->map + p, '\n', r->map_len - p);
             if (!nl) break;
-            if ((size_t)(nl - r->map) + 1 < r->map_len && nl[1] == '>') { hit = nl + 1; break; }
+            if (r->mt_fastq ? km_fastq_record_start(r->map, r->map_len, (size_t)(nl - r->map) + 1) : ((size_t)(nl - r->map) + 1 < r->map_len && nl[1] == '>')) { hit = nl + 1; break; }
             p = (size_t)(nl - r->map) + 1;
         }
         if (!hit) break;
@@ -201,8 +235,9 @@ extern "C" int kmat_reader_open_mt(const char *path, int fastq, int threads, kma
         r->own_fd = true;
         if (r->fd < 0) { kmat_set_error("Did not open for reading: %s (%s)", path, strerror(errno)); delete r; return KMAT_ERR_IO; }
     }
-    // FASTQ records cannot be told apart without context ('@' also starts quality lines) and stdin cannot be mapped
-    if (!(threads > 1 && !fastq && r->own_fd && km_reader_start_mt(r, threads))) r->buf.resize(kChunk);
+    // stdin cannot be mapped
+    r->mt_fastq = fastq != 0;
+    if (!(threads > 1 && r->own_fd && km_reader_start_mt(r, threads))) r->buf.resize(kChunk);
     *out = r;
     return KMAT_OK;
 }
@@ -247,15 +282,20 @@ extern "C" int64_t kmat_reader_next(kmat_reader *r, uint32_t max_reads, uint64_t
                 size_t u = 0;
                 for (uint32_t i = 0; i < b->n; i++) {
                     if (u < b->unknown.size() && b->unknown[u] == i) {
-                        char tmp[48];
-                        snprintf(tmp, sizeof tmp, "unknown_hdr:%llu", (unsigned long long)(r->ordinal + i + 1));
-                        h.append(tmp); u++;
+                        u++;
+                        if (r->mt_fastq && i == 0 && !r->carry_hdr.empty() && r->carry_hdr[0] != '\0') h.append(r->carry_hdr);   // the previous segment's last header
+                        else {
+                            char tmp[48];
+                            snprintf(tmp, sizeof tmp, "unknown_hdr:%llu", (unsigned long long)(r->ordinal + i + 1));
+                            h.append(tmp);
+                        }
                     } else h.append(b->hdrs, b->hdr_offs[i], b->hdr_offs[i + 1] - b->hdr_offs[i]);
                     ho.push_back(h.size());
                 }
                 b->hdrs.swap(h); b->hdr_offs.swap(ho);
             }
             r->ordinal += b->n;
+            if (r->mt_fastq) r->carry_hdr = b->tail_hdr;
             if (b->n) return (int64_t)b->n;
         }
     }

@@ -75,3 +75,35 @@ def test_parallel_reader_equals_sequential(tmp_path, golden_small, seg_bytes, mo
             got = api.read_file(p, threads=th)
             assert got == want, (name, th)
         assert want == tuple(op.read_fasta_like_reference(p)) or list(want) == list(op.read_fasta_like_reference(p))
+
+
+@pytest.mark.parametrize("seg_bytes", [1, 9, 80, 4096])
+def test_parallel_fastq_reader_equals_sequential(tmp_path, golden_small, seg_bytes, monkeypatch):
+    """kmat_reader_open_mt on FASTQ: segments start at the '@' line of a record (an '@' line followed by sequence lines, a
+    '+' / '-' line, the quality line and then another '@' line or the end), each read keeps the reference's pairing with
+    the PREVIOUS record's header across segment boundaries, quality lines starting with '@' or '+' never start a segment."""
+    monkeypatch.setenv("KMAT_READER_SEG_BYTES", str(seg_bytes))
+    import numpy as np
+    rng = np.random.default_rng(4)
+    recs = []
+    for i in range(300):
+        L = int(rng.integers(1, 90))
+        seq = "".join("ACGTN"[x] for x in rng.integers(0, 5, L))
+        q0 = "@+-I#"[int(rng.integers(0, 5))]                       # quality lines that look like headers / separators
+        qual = q0 + "".join(chr(int(x)) for x in rng.integers(33, 74, L - 1))
+        hdr = "" if i % 37 == 5 else f"read{i} len={L}"
+        if i % 11 == 3 and L > 10:                                  # sequence wrapped over two lines
+            recs.append(f"@{hdr}\n{seq[:L // 2]}\n{seq[L // 2:]}\n+{hdr}\n{qual}\n")
+        else:
+            recs.append(f"@{hdr}\n{seq}\n{'+-'[i % 2]}\n{qual}\n")
+    files = {"synthetic": "".join(recs).encode(), "golden": open(golden_small.paths["reads_fq"], "rb").read(),
+             "no_final_newline": "".join(recs)[:-1].encode(), "one": b"@r\nACGT\n+\nIIII\n"}
+    for name, data in files.items():
+        p = os.path.join(tmp_path, f"{name}_{seg_bytes}.fq")
+        open(p, "wb").write(data)
+        want = api.read_file(p, fastq=True, threads=1)
+        assert list(want) == list(op.read_fasta_like_reference(p, fastq=True)), name
+        for th in (2, 6):
+            got = api.read_file(p, fastq=True, threads=th)
+            assert got == want, (name, th)
+    assert sum(h.startswith("unknown_hdr:") for h in api.read_file(os.path.join(tmp_path, f"synthetic_{seg_bytes}.fq"), fastq=True, threads=3)[0]) >= 8
