@@ -343,7 +343,9 @@ int kmat_reader_open(const char *path, int fastq, kmat_reader **out);
  * max_bases then do not apply); the (header, read) sequence is identical to the sequential reader's.  FASTQ files are
  * cut at '@' lines that verifiably start a record (followed by sequence lines, a '+' / '-' line, one quality line and
  * another '@' line or the end of the file); the reference's pairing of a FASTQ read with the previous record's header
- * is carried across the cuts.  stdin and threads <= 1 fall back to the sequential reader. */
+ * is carried across the cuts; a segment of a malformed file that does not end between two records is detected after
+ * the fact and the rest of the file is then parsed sequentially from that segment on, so the sequence is identical to
+ * the sequential reader's for any input.  stdin and threads <= 1 fall back to the sequential reader. */
 int kmat_reader_open_mt(const char *path, int fastq, int threads, kmat_reader **out);
 void kmat_reader_close(kmat_reader *);
 kmat_read_batch *kmat_read_batch_new(void);

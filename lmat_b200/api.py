@@ -63,7 +63,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build_lib()
+    path = os.environ.get("KMAT_LIB") or _build.build_lib()      # KMAT_LIB: an instrumented build (tools/asan_host.sh)
     L = C.CDLL(path)
     vp, u64p = C.c_void_p, C.c_void_p
     L.kmat_strerror.restype = C.c_char_p

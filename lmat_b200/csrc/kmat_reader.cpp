@@ -29,6 +29,7 @@ struct kmat_read_batch {
     std::vector<uint64_t> offs, hdr_offs;
     std::vector<uint32_t> unknown;      // reads whose header is "unknown_hdr:<ordinal>" (needs the global ordinal)
     std::string tail_hdr;               // parallel FASTQ: the header line of the segment's last record (the next segment's first read carries it)
+    bool open_end = false;              // parallel FASTQ: the segment did not end between two records (malformed input)
     uint64_t first_ordinal = 1;
     uint32_t n = 0;
     void clear() { bases.clear(); hdrs.clear(); offs.assign(1, 0); hdr_offs.assign(1, 0); unknown.clear(); tail_hdr.clear(); n = 0; }
@@ -40,6 +41,7 @@ struct KmParseState {
     bool in_finished = false;   // the reference's flag: a getline failed
     std::string hdr_buff, last_hdr_buff;      // the pending read itself accumulates at the tail of the batch's `bases`
     uint64_t n_emitted = 0;     // read_count_in == read_count_out ordinal
+    bool open_end = false;      // FASTQ: the lines ran out with a read pending or inside a quality-line skip (see km_reader_worker)
 };
 
 struct kmat_reader {
@@ -63,6 +65,8 @@ struct kmat_reader {
     bool stop = false;
     uint64_t ordinal = 0;
     bool mt_fastq = false;
+    bool fallback = false;                   // parallel FASTQ met a segment with an open end: sequential from fb on
+    const char *fb_p = nullptr;
     std::string carry_hdr;                   // parallel FASTQ: header of the last record handed out so far
 };
 
@@ -127,7 +131,8 @@ static void parse_lines(KmParseState &st, NextLine &&next_line, uint32_t max_rea
         if (st.fastq && c0 != '@' && c0 != '+' && c0 != '-') { b->bases.append(line, len); len = 0; c0 = '\0'; } // :1684-1687
         if (((c0 == '>' || st.in_finished) || (st.fastq && (c0 == '+' || c0 == '-'))) && b->bases.size() > b->offs.back()) {    // :1688-1707
             emit(st, b, st.in_finished ? st.hdr_buff : st.last_hdr_buff);
-            if (st.fastq) { const char *q; size_t ql; next_line(&q, &ql); }                   // the quality line is skipped
+            if (st.fastq && st.in_finished) st.open_end = true;
+            if (st.fastq) { const char *q; size_t ql; if (!next_line(&q, &ql)) st.open_end = true; }     // the quality line is skipped
         }
     }
 }
@@ -140,6 +145,10 @@ static void parse_lines(KmParseState &st, NextLine &&next_line, uint32_t max_rea
 // Telling a record's '@' line from a quality line that happens to start with '@' needs context: a cut is only made at an
 // '@' line that is followed by >= 1 plain lines, a '+' / '-' line, one more line (the quality) and then an '@' line or the
 // end of the file.  A quality line starting with '@' is followed by the next header, so it never qualifies.
+// That rule is enough for well-formed files.  For anything else the cut is checked after the fact: the state machine is in
+// its start state at a cut exactly when the left part ended neither with a read still pending (pushed by the end-of-input
+// branch) nor inside the skip of a quality line; a segment that ends otherwise is flagged (open_end) and kmat_reader_next
+// then parses the rest of the file sequentially from that segment's first byte, where the state is known.
 //
 // A FASTA file cut right before a header line parses independently on both sides: at a '>' line the reference
 // pushes the pending read with the header that preceded it, which is also what the end-of-input branch (:1663-1669)
@@ -164,6 +173,7 @@ static void km_reader_worker(kmat_reader *r) {
         KmMemLines src{r->map + r->seg[s], r->map + r->seg[s + 1]};
         while (!st.in_finished) parse_lines(st, [&](const char **ln, size_t *n) { return src.next(ln, n); }, 0xFFFFFFFFu, ~0ull, b);
         b->tail_hdr = st.hdr_buff;
+        b->open_end = st.open_end;
         {
             std::lock_guard<std::mutex> l(r->m);
             r->done[s] = b;
@@ -261,7 +271,7 @@ extern "C" int64_t kmat_reader_next(kmat_reader *r, uint32_t max_reads, uint64_t
     if (!r || !b) { kmat_set_error("kmat_reader_next: bad argument"); return KMAT_ERR_ARG; }
     if (max_reads == 0) max_reads = 1;
     b->clear();
-    if (r->mt) {
+    if (r->mt && !r->fallback) {
         // segments come out in file order, each as one batch (max_reads / max_bases do not apply); empty ones are skipped
         for (;;) {
             if (r->next_out + 1 >= r->seg.size()) return 0;
@@ -272,8 +282,19 @@ extern "C" int64_t kmat_reader_next(kmat_reader *r, uint32_t max_reads, uint64_t
                 d = r->done[r->next_out];
                 r->done.erase(r->next_out);
                 r->next_out++;
+                if (d->open_end && r->next_out + 1 < r->seg.size()) {     // not the last segment: its end is not the end of the input
+                    r->stop = true;
+                    r->fallback = true;
+                }
             }
             r->cv_space.notify_all();
+            if (r->fallback) {
+                delete d;
+                r->fb_p = r->map + r->seg[r->next_out - 1];
+                r->st = KmParseState();
+                r->st.fastq = true; r->st.hdr_buff = r->carry_hdr; r->st.n_emitted = r->ordinal;
+                break;
+            }
             std::swap(*b, *d);
             delete d;
             b->first_ordinal = r->ordinal + 1;
@@ -300,6 +321,12 @@ extern "C" int64_t kmat_reader_next(kmat_reader *r, uint32_t max_reads, uint64_t
         }
     }
     b->first_ordinal = r->st.n_emitted + 1;
+    if (r->fallback) {
+        KmMemLines src{r->fb_p, r->map + r->map_len};
+        parse_lines(r->st, [&](const char **ln, size_t *n) { return src.next(ln, n); }, max_reads, max_bases, b);
+        r->fb_p = src.p;
+        return (int64_t)b->n;
+    }
     parse_lines(r->st, [&](const char **ln, size_t *n) { return next_line_fd(r, ln, n); }, max_reads, max_bases, b);
     return (int64_t)b->n;
 }

@@ -107,3 +107,50 @@ def test_parallel_fastq_reader_equals_sequential(tmp_path, golden_small, seg_byt
             got = api.read_file(p, fastq=True, threads=th)
             assert got == want, (name, th)
     assert sum(h.startswith("unknown_hdr:") for h in api.read_file(os.path.join(tmp_path, f"synthetic_{seg_bytes}.fq"), fastq=True, threads=3)[0]) >= 8
+
+
+def _fuzz_inputs(seed, n_cases):
+    """Byte soup over the characters the state machine looks at, and FASTQ-shaped records with occasional damage
+    (missing '+' lines, missing quality lines, blank lines, quality lines starting with '@' or '+')."""
+    import random
+    rng = random.Random(seed)
+    alpha = [b">", b"@", b"+", b"-", b"\n", b"\n", b"\n", b"A", b"C", b"G", b"T", b"N", b"\r", b" ", b"\t", b"I", b"x"]
+    for i in range(n_cases):
+        if i % 2 == 0:
+            n = rng.choice([0, 1, 2, 5, 20, 80, 300])
+            yield b"".join(rng.choice(alpha) * rng.choice([1, 1, 1, 2, 7]) for _ in range(n))
+        else:
+            out = []
+            for r in range(rng.choice([1, 3, 10, 40])):
+                seq = "".join(rng.choice("ACGTN") for _ in range(rng.choice([1, 4, 30])))
+                qual = rng.choice(["I", "@", "+", "-", ">"]) + "I" * (len(seq) - 1)
+                lines = ["@r%d" % r if rng.random() < 0.9 else "@", seq, rng.choice(["+", "+", "-", "+r"]), qual]
+                dmg = rng.random()
+                if dmg < 0.05: del lines[2]
+                elif dmg < 0.10: del lines[3]
+                elif dmg < 0.15: lines.insert(rng.randrange(4), "")
+                elif dmg < 0.20: lines.insert(2, seq[:3])
+                elif dmg < 0.25: del lines[0]
+                out += lines
+            yield ("\n".join(out) + ("\n" if rng.random() < 0.7 else "")).encode()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_reader_fuzz_sequential_and_parallel_equal_oracle(tmp_path, seed, monkeypatch):
+    """Arbitrary input, FASTA and FASTQ mode: the sequential reader and the parallel one (any segment size) give the oracle
+    reader's (header, read) sequence.  Malformed FASTQ is where the parallel reader's cut rule is not enough and its
+    after-the-fact check (open_end -> sequential from that segment on) has to take over."""
+    p = os.path.join(tmp_path, "fz.txt")
+    cases = [b"N\n@\n\n+\nG"] + list(_fuzz_inputs(seed, 60))
+    for data in cases:
+        open(p, "wb").write(data)
+        for fastq in (False, True):
+            want = op.read_fasta_like_reference(p, fastq=fastq)
+            monkeypatch.delenv("KMAT_READER_SEG_BYTES", raising=False)
+            for mr in (1, 1000):
+                got = api.read_file(p, fastq=fastq, max_reads=mr)
+                assert got[0] == want[0] and got[1] == want[1], (data, fastq, mr)
+            for seg in ("1", "13", "200"):
+                monkeypatch.setenv("KMAT_READER_SEG_BYTES", seg)
+                got = api.read_file(p, fastq=fastq, threads=3)
+                assert got[0] == want[0] and got[1] == want[1], (data, fastq, seg)
