@@ -211,6 +211,7 @@ extern "C" int kmat_db_upload(const kmat_table *t, int device, int shard_index, 
     for (uint64_t i = 0; i < t->n_kmers; i++) {
         if (shard_count > 1 && (int)kmat_shard_of(t->kmers[i], t->kmer_len, shard_count) != shard_index) continue;
         const uint64_t a = t->offs[i], c = t->offs[i + 1] - a;
+        if (t->offs[i + 1] < a || t->offs[i + 1] > t->n_ids) { kmat_set_error("table: list offsets of k-mer %llu are not ascending / exceed the id array", (unsigned long long)i); return KMAT_ERR_FORMAT; }
         if (c == 0) continue;                         // cannot occur in a SortedDb (every record has >= 1 tid)
         if (c >= 32768) { kmat_set_error("taxid list of %llu entries: counts >= 32768 turn label_vec[pos].first negative in the reference (int16_t, read_label.cpp:49); unsupported", (unsigned long long)c); return KMAT_ERR_UNSUPPORTED; }
         kmers.push_back(t->kmers[i]);

@@ -161,8 +161,14 @@ extern "C" int kmat_table_open(const char *path, int tid_bytes, kmat_table **out
     int rc;
     if (memcmp(b, kFlatMagic, 8) == 0) {
         KmatFileHeader h; memcpy(&h, b, sizeof h);
-        uint64_t need = sizeof h + 8 * h.n_kmers + 8 * (h.n_kmers + 1) + 4 * h.n_ids;
-        if (h.version != 1 || need > (uint64_t)sb.st_size) { munmap(m, sb.st_size); kmat_set_error("%s: truncated .kmat image", path); return KMAT_ERR_FORMAT; }
+        // counts are checked against the file size one by one (a damaged header must not wrap the sum around)
+        const uint64_t fsz = (uint64_t)sb.st_size;
+        const bool counts_ok = h.n_kmers <= fsz / 16 && h.n_ids <= fsz / 4 && sizeof h + 8 * h.n_kmers + 8 * (h.n_kmers + 1) + 4 * h.n_ids <= fsz;
+        if (h.version != 1 || !counts_ok) { munmap(m, sb.st_size); kmat_set_error("%s: truncated .kmat image", path); return KMAT_ERR_FORMAT; }
+        const uint64_t *offs = (const uint64_t *)(b + sizeof h) + h.n_kmers;
+        if (h.kmer_len < 1 || h.kmer_len > 32 || (h.tid_bytes != 2 && h.tid_bytes != 4) || offs[0] != 0 || offs[h.n_kmers] != h.n_ids) {
+            munmap(m, sb.st_size); kmat_set_error("%s: inconsistent .kmat header", path); return KMAT_ERR_FORMAT;
+        }
         kmat_table *t = new kmat_table();
         t->kmer_len = h.kmer_len; t->tid_bytes = h.tid_bytes; t->n_kmers = h.n_kmers; t->n_ids = h.n_ids;
         t->kmers = (const uint64_t *)(b + sizeof h);
@@ -185,7 +191,7 @@ extern "C" int kmat_table_open(const char *path, int tid_bytes, kmat_table **out
         if (klen == 20) bits2 = 13; else if (klen == 18) bits2 = 9;
         else { munmap(m, sb.st_size); kmat_set_error("K size %d not supported by this application version!", (int)klen); return KMAT_ERR_UNSUPPORTED; }   // SortedDb.hpp:195-197
         if (p_tt < base || p_table < base || p_storage < base || p_tt - base + tt_count * 8 > (uint64_t)sb.st_size ||
-            p_table - base + n_rec * 8 > (uint64_t)sb.st_size || p_storage - base > (uint64_t)sb.st_size) {
+            n_rec > (uint64_t)sb.st_size / 8 || p_table - base + n_rec * 8 > (uint64_t)sb.st_size || p_storage - base > (uint64_t)sb.st_size) {
             munmap(m, sb.st_size); kmat_set_error("%s: SortedDb pointers outside the image", path); return KMAT_ERR_FORMAT;
         }
         rc = kmat_table_from_sorteddb((const uint64_t *)(b + (p_tt - base)), tt_count, bits2, b + (p_table - base), n_rec,

@@ -159,3 +159,24 @@ def test_format_tail_numbers_match_printf_g():
         want = "%g %g 131\t" % (float(blk[0]), float(blk[1])) + "".join(" %d %g" % (int(t), float(s)) for t, s in zip(cands["tid"][::-1], cands["score"][::-1]))
         want += "\t9606 %g DirectMatch\n" % float(abs(blk[2]))
         assert n >= 0 and buf.raw[:n].decode() == want
+
+
+def test_flat_image_damaged_header_is_rejected(golden_small, tmp_path):
+    """A .kmat image whose header counts are damaged (including values that would wrap the size computation around)
+    or whose offsets do not end at n_ids is KMAT_ERR_FORMAT, not a crash."""
+    import struct
+    g = golden_small
+    p = str(tmp_path / "t.kmat")
+    api.Table.from_arrays(g.kmers, g.offs, g.ids, g.kmer_len, g.tid_bytes).save(p)
+    good = open(p, "rb").read()
+    for field_off, val in ((24, 1 << 62), (24, (1 << 64) - 1), (32, (1 << 64) - 1), (32, 1 << 62), (32, len(g.ids) - 1), (24, len(g.kmers) - 1),
+                           (12, 0), (12, 200), (16, 3)):
+        d = bytearray(good)
+        d[field_off:field_off + (8 if field_off >= 24 else 4)] = struct.pack("<Q" if field_off >= 24 else "<I", val)
+        open(p, "wb").write(bytes(d))
+        with pytest.raises(api.KmatError) as e:
+            api.Table.open(p)
+        assert e.value.code == -6, (field_off, val)
+    open(p, "wb").write(good[:len(good) // 2])
+    with pytest.raises(api.KmatError):
+        api.Table.open(p)
