@@ -939,11 +939,22 @@ template <int MODE>
 __global__ void km_gather_kernel(const uint8_t *__restrict__ base, uint64_t n_units, uint64_t n_gathers, uint64_t seed, unsigned long long *sink) {
     unsigned long long acc = 0;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_gathers; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t x = (i + seed) * 0x9E3779B97F4A7C15ull;
+        // 2xx modes: G consecutive lanes share one random 128-byte line (what a table ordered by minimizer would look like
+        // to the probe kernel: neighbouring k-mers of a read in one line); n_gathers still counts lanes
+        const int G = MODE == 204 ? 8 : (MODE == 201 || MODE == 202 || MODE == 205) ? 4 : 1;
+        uint64_t x = ((MODE >= 200 ? i / G : i) + seed) * 0x9E3779B97F4A7C15ull;
         x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32;
-        const uint64_t u = (uint64_t)(((unsigned __int128)x * n_units) >> 64);
-        const uint8_t *p = base + u * 32;                     // one access per 32-byte sector
+        const uint64_t u = MODE >= 200 ? (uint64_t)(((unsigned __int128)x * (n_units / 4)) >> 64) * 4 : (uint64_t)(((unsigned __int128)x * n_units) >> 64);
+        const uint8_t *p = base + u * 32;                     // one access per 32-byte sector (2xx: the line's first sector)
         unsigned long long v = 0;
+        if (MODE == 201) { uint64_t a, b, c, d; km_load_bucket((const uint64_t *)(p + (i & 3) * 32), a, b, c, d); v = a ^ b ^ c ^ d; }     // 4 lanes, one sector each
+        else if (MODE == 202) { uint64_t a, b, c, d; km_load_bucket((const uint64_t *)p, a, b, c, d); v = a ^ b ^ c ^ d; }                 // 4 lanes, the same sector
+        else if (MODE == 203 || MODE == 205) {                                                                                             // every lane reads the whole line
+#pragma unroll
+            for (int q = 0; q < 4; q++) { uint64_t a, b, c, d; asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p + q * 32)); v ^= a ^ b ^ c ^ d; }
+        }
+        else if (MODE == 204) { uint64_t a, b; asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p + (i & 7) * 16)); v = a ^ b; }   // 8 lanes, 16 bytes each
+        else
         if (MODE == 8) v = *(const unsigned long long *)p;
         else if (MODE == 16) { const ulonglong2 w = *(const ulonglong2 *)p; v = w.x ^ w.y; }
         else if (MODE == 32) { uint64_t a, b, c, d; km_load_bucket((const uint64_t *)p, a, b, c, d); v = a ^ b ^ c ^ d; }
@@ -992,7 +1003,7 @@ static int km_gather_bench_impl(int device, int mem_device, uint64_t span_bytes,
                                 double *gathers_per_s, double *sector_gbps) {
     if (kmat_device_count() <= device || kmat_device_count() <= mem_device) { kmat_set_error("CUDA device %d / %d not available", device, mem_device); return KMAT_ERR_NO_DEVICE; }
     const int mode = access_bytes;
-    if (mode != 8 && mode != 16 && mode != 32 && !(mode >= 101 && mode <= 110)) return KMAT_ERR_ARG;
+    if (mode != 8 && mode != 16 && mode != 32 && !(mode >= 101 && mode <= 110) && !(mode >= 201 && mode <= 205)) return KMAT_ERR_ARG;
     uint8_t *buf; unsigned long long *sink;
     KM_CUDA(cudaSetDevice(mem_device));
     KM_CUDA(cudaMalloc((void **)&buf, span_bytes));
@@ -1012,7 +1023,7 @@ static int km_gather_bench_impl(int device, int mem_device, uint64_t span_bytes,
         cudaEventRecord(e0);
         const int blocks = 148 * 16, threads = 256;
 #define KM_G(M) case M: km_gather_kernel<M><<<blocks, threads>>>(buf, n_units, n_gathers, 977 * it, sink); break;
-        switch (mode) { KM_G(8) KM_G(16) KM_G(32) KM_G(101) KM_G(102) KM_G(103) KM_G(104) KM_G(105) KM_G(106) KM_G(107) KM_G(108) KM_G(109) KM_G(110) }
+        switch (mode) { KM_G(8) KM_G(16) KM_G(32) KM_G(101) KM_G(102) KM_G(103) KM_G(104) KM_G(105) KM_G(106) KM_G(107) KM_G(108) KM_G(109) KM_G(110) KM_G(201) KM_G(202) KM_G(203) KM_G(204) KM_G(205) }
 #undef KM_G
         g_km_launches++;
         cudaEventRecord(e1); cudaEventSynchronize(e1);
