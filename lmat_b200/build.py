@@ -44,7 +44,9 @@ def build_lib(force=False, verbose=False):
     log = []
     for src in CUDA_SRCS:
         obj = os.path.join(HERE, "build", src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-I" + os.path.join(ROOT, "include"), "-c", os.path.join(CSRC, src), "-o", obj]
+        # KMAT_NVCC_DEFINES="-DKMAT_K4_PACKED_DEPTH=1 ...": compile-time experiments (see the #ifndef blocks in csrc/)
+        extra = os.environ.get("KMAT_NVCC_DEFINES", "").split()
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-I" + os.path.join(ROOT, "include"), "-c", os.path.join(CSRC, src), "-o", obj]
         p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         log.append(p.stdout)
         if p.returncode != 0:

@@ -626,10 +626,27 @@ struct KsLocalT {
 };
 typedef KsLocalT<KB_CMAX, KB_LIN, uint8_t> KsLocal;          // per-thread local arrays of the regular kernel
 typedef KsLocalT<KB_CBIG, KB_LBIG, uint16_t> KsLocalBig;     // global scratch slot of the big kernel
+// Experiment for the next GPU session (off by default, -DKMAT_K4_PACKED_DEPTH=1): the sorted element carries the depth in
+// the upper half of idx, so TCmp stops loading depth[a.idx] / depth[b.idx] from local memory twice per comparison (12.5 % of
+// the scoring kernel's stall samples sit on that line, profiles/r01r_hot_lines_k3_k4.txt).  Candidate indices are < 512.
+#ifndef KMAT_K4_PACKED_DEPTH
+#define KMAT_K4_PACKED_DEPTH 0
+#endif
+#if KMAT_K4_PACKED_DEPTH
+#define KS_RL_IDX(v) ((v) & 0xFFFFu)
+#define KS_RL_PACK(f, depth) ((uint32_t)(f) | ((uint32_t)(depth) << 16))
+#else
+#define KS_RL_IDX(v) (v)
+#define KS_RL_PACK(f, depth) ((uint32_t)(f))
+#endif
 struct KsTCmp {           // TCmp, read_label.cpp:475-485: |a-b| < 0.001 (double compare) -> shallower first, else by score
     const uint16_t *depth;
     __device__ bool operator()(const KmRl &a, const KmRl &b) const {
+#if KMAT_K4_PACKED_DEPTH
+        if ((double)fabsf(__fsub_rn(a.score, b.score)) < 0.001) return (int)(a.idx >> 16) < (int)(b.idx >> 16);
+#else
         if ((double)fabsf(__fsub_rn(a.score, b.score)) < 0.001) return (int)depth[a.idx] < (int)depth[b.idx];
+#endif
         return a.score < b.score;
     }
 };
@@ -719,7 +736,7 @@ __device__ __forceinline__ void ks_score_one(const KmScoreParams &P, const uint3
     for (int f = 0; f < C; f++) {
         float sc = T.score[f];
         if (hasHuman && (T.flags[f] & 1)) sc = __fadd_rn(sc, __fmul_rn(X.opt.hbias, stdev1));
-        T.rl[f].score = sc; T.rl[f].idx = (uint32_t)f;
+        T.rl[f].score = sc; T.rl[f].idx = KS_RL_PACK(f, T.depth[f]);
     }
     kmstd::sort(T.rl, C, KsTCmp{T.depth});
     const float diff_thresh = __fmul_rn(stdev1, X.opt.sdiff);                  // :895
@@ -730,7 +747,7 @@ __device__ __forceinline__ void ks_score_one(const KmScoreParams &P, const uint3
     int lowest = -1, highest = -1; float lowest_score = 0;
     int lidx = -1; bool linDone = false, lin_overflow = false;
     for (int i = C - 1; i >= 0; --i) {                                          // :295-325
-        const int ci = (int)T.rl[i].idx; const float sc = T.rl[i].score;
+        const int ci = (int)KS_RL_IDX(T.rl[i].idx); const float sc = T.rl[i].score;
         const unsigned cdepth = T.depth[ci];
         if (sc >= top_score && (T.flags[ci] & 4)) { plasmidTopHit = true; savePlasmid = ci; }
         bool added = false;
@@ -789,7 +806,7 @@ __device__ __forceinline__ void ks_score_one(const KmScoreParams &P, const uint3
     kmstd::sort(T.l_perm, nlin, KsLinDepthDesc<PermT>{T.l_depth});                     // cand_lin_vec sorted by depth desc :350-351
     bool any_nogood = false;
     for (int i = lidx; i >= 0; --i) {                                           // :355-362
-        const int ci = (int)T.rl[i].idx; const float sc = T.rl[i].score;
+        const int ci = (int)KS_RL_IDX(T.rl[i].idx); const float sc = T.rl[i].score;
         bool in_add = false;
         for (int q = add_lo; q < add_hi && !in_add; q++) in_add = T.l_tid[q] == T.tid[ci];
         if (in_add) continue;
@@ -832,7 +849,7 @@ __device__ __forceinline__ void ks_score_one(const KmScoreParams &P, const uint3
     if (match == KMAT_DIRECT || match == KMAT_MULTI || match == KMAT_PARTIAL) { res.tid = call_tid; res.score = call_score; }
     else { res.tid = 0; res.score = 0; }                                        // best_guess stays (0,0), :839
     // ---- outputs: sorted rank_label overwrites the (nid, hits) hand-over in place; lineage on request
-    if (P.cands && co + C <= P.cand_cap) for (int i = 0; i < C; i++) P.cands[co + i] = kmat_pair{T.tid[T.rl[i].idx], T.rl[i].score};
+    if (P.cands && co + C <= P.cand_cap) for (int i = 0; i < C; i++) P.cands[co + i] = kmat_pair{T.tid[KS_RL_IDX(T.rl[i].idx)], T.rl[i].score};
     if (X.opt.want_lineage) {
         res.n_lin = (uint32_t)nlin;
         const unsigned long long lo2 = atomicAdd(P.lin_cursor, (unsigned long long)nlin);
