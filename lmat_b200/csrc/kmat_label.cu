@@ -859,6 +859,53 @@ __device__ __forceinline__ void ks_score_one(const KmScoreParams &P, const uint3
     P.out[r] = res;
 }
 
+// Experiment for the next GPU session (off by default, -DKMAT_K4_BLOCK_SORT=1): a CTA takes KS_THREADS * KS_SORT_ROUNDS queue
+// entries, counting-sorts them by candidate count in shared memory and scores them in that order, so the 32 reads of a warp
+// have similar loop lengths (the insertion sort of rank_label and the ancestor scans run with 7-16 of 32 lanes active today,
+// profiles/r01r_hot_lines_k3_k4.txt).  Results do not depend on which thread scores a read.
+#ifndef KMAT_K4_BLOCK_SORT
+#define KMAT_K4_BLOCK_SORT 0
+#endif
+#define KS_SORT_ROUNDS 4
+#if KMAT_K4_BLOCK_SORT
+#define KS_READS_PER_CTA (KS_THREADS * KS_SORT_ROUNDS)
+__global__ void __launch_bounds__(KS_THREADS) km_score_kernel(KmScoreParams P) {
+    __shared__ uint32_t s_bin[KB_CMAX + 2];
+    __shared__ uint32_t s_r[KS_READS_PER_CTA];
+    const uint32_t n_q = P.pend_q ? (uint32_t)(*P.pass_cursor >> KB_PASS_SHIFT) : P.n_reads;
+    const uint32_t base = blockIdx.x * KS_READS_PER_CTA;
+    if (base >= n_q) return;                                   // the whole CTA leaves together
+    for (int i = threadIdx.x; i < KB_CMAX + 2; i += KS_THREADS) s_bin[i] = 0;
+    __syncthreads();
+    uint32_t rr[KS_SORT_ROUNDS], cc[KS_SORT_ROUNDS], pos[KS_SORT_ROUNDS];
+#pragma unroll
+    for (int k = 0; k < KS_SORT_ROUNDS; k++) {
+        const uint32_t q = base + k * KS_THREADS + threadIdx.x;
+        rr[k] = KMAT_NONE; cc[k] = 0; pos[k] = 0;
+        if (q < n_q) {
+            const uint32_t r = P.pend_q ? P.pend_q[q] : q;
+            if (P.out[r].status == KMAT_ST_PENDING) {
+                rr[k] = r; cc[k] = min(P.out[r].n_cand, (uint32_t)KB_CMAX);
+                pos[k] = atomicAdd(&s_bin[cc[k]], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                                    // exclusive scan, most candidates first
+        uint32_t run = 0;
+        for (int i = KB_CMAX; i >= 0; i--) { const uint32_t t = s_bin[i]; s_bin[i] = run; run += t; }
+        s_bin[KB_CMAX + 1] = run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < KS_SORT_ROUNDS; k++) if (rr[k] != KMAT_NONE) s_r[s_bin[cc[k]] + pos[k]] = rr[k];
+    __syncthreads();
+    const uint32_t total = s_bin[KB_CMAX + 1];
+    KsLocal T;
+    for (uint32_t i = threadIdx.x; i < total; i += KS_THREADS) ks_score_one<KB_LIN, uint8_t, false>(P, s_r[i], T);
+}
+#else
+#define KS_READS_PER_CTA KS_THREADS
 __global__ void __launch_bounds__(KS_THREADS) km_score_kernel(KmScoreParams P) {
     uint32_t r = blockIdx.x * KS_THREADS + threadIdx.x;
     if (P.pend_q) {                                 // dense queue of the reads K3 left PENDING: no lane idles on a read without candidates
@@ -868,6 +915,7 @@ __global__ void __launch_bounds__(KS_THREADS) km_score_kernel(KmScoreParams P) {
     KsLocal T;
     ks_score_one<KB_LIN, uint8_t, false>(P, r, T);
 }
+#endif
 // The reads of big_qb (more than KB_CMAX candidates, or a lineage the regular kernel could not hold): same code, working
 // arrays in a global scratch slot per thread.
 __global__ void __launch_bounds__(32) km_score_big_kernel(KmScoreParams P) {
@@ -1462,7 +1510,7 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
         const char *e = getenv("KMAT_SCORE_SMEM"); const int v = e ? atoi(e) : 0;
         if (v > 48 * 1024) cudaFuncSetAttribute(km_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
         return v > 0 ? v : 0; }();
-    km_score_kernel<<<(n + KS_THREADS - 1) / KS_THREADS, KS_THREADS, score_smem, s2>>>(P);
+    km_score_kernel<<<(n + KS_READS_PER_CTA - 1) / KS_READS_PER_CTA, KS_THREADS, score_smem, s2>>>(P);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     km_score_big_kernel<<<c->big_threads4 / 32, 32, 0, s2>>>(P);
