@@ -1,7 +1,7 @@
 #!/bin/bash
 # gpurun --timeout 2400 -- tools/gpu_k4_packed.sh : compile-time experiments on the scoring kernel (lmat_b200/csrc/kmat_label.cu)
 # against the default build: for each define set the library is rebuilt, the parity tests run, then the bench line
-# (kernel split in "kernel_ms").  The default library is restored at the end.
+# (kernel split in "kernels_ms").  The default library is restored at the end.
 #   -DKMAT_K4_PACKED_DEPTH=1  depth carried in the sorted rank_label element (no local-memory loads in TCmp)
 #   -DKMAT_K4_BLOCK_SORT=1    a CTA counting-sorts 512 queued reads by candidate count before scoring them
 mkdir -p gpurun_out
@@ -20,7 +20,7 @@ import json
 for n in ("default", "exp1", "exp2", "exp3"):
     try:
         j = json.loads(open(f"gpurun_out/k4_{n}.json").read().strip().splitlines()[-1])
-        print(n, j.get("value"), j.get("ms_per_step"), j.get("kernel_ms"))
+        print(n, j.get("value"), j.get("ms_per_step"), j.get("kernels_ms"))
     except Exception as e:
         print(n, "failed", e)
 PY
