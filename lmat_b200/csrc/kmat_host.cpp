@@ -563,12 +563,16 @@ static const char *match_str(int m) {
 // fraction); whenever the fraction is within 1e-6 of a rounding boundary, or the value is outside the fixed-notation
 // range, std::to_chars(general, 6) -- specified to equal printf("%.6g") -- decides.  tests/test_abi_cpu.py compares it
 // with printf over random bit patterns and the score-like ranges.
+static const char KM_DIGIT_PAIRS[201] =
+    "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566676869"
+    "707172737475767778798081828384858687888990919293949596979899";
 static inline char *km_fmt_u32(char *p, uint32_t v) {
-    char t[10];
-    int n = 0;
-    do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v);
-    while (n) *p++ = t[--n];
-    return p;
+    // digit count first, then two digits per step from the back (taxids are 1-8 digits: at most 4 steps)
+    const int n = v < 10 ? 1 : v < 100 ? 2 : v < 1000 ? 3 : v < 10000 ? 4 : v < 100000 ? 5 : v < 1000000 ? 6 : v < 10000000 ? 7 : v < 100000000 ? 8 : v < 1000000000 ? 9 : 10;
+    char *q = p + n;
+    while (v >= 100) { const uint32_t r = v % 100; v /= 100; q -= 2; memcpy(q, KM_DIGIT_PAIRS + 2 * r, 2); }
+    if (v >= 10) memcpy(q - 2, KM_DIGIT_PAIRS + 2 * v, 2); else q[-1] = (char)('0' + v);
+    return p + n;
 }
 static inline char *km_fmt_i32(char *p, int32_t v) {
     if (v < 0) { *p++ = '-'; return km_fmt_u32(p, (uint32_t)(-(int64_t)v)); }
@@ -593,23 +597,29 @@ static inline char *km_fmt_g(char *p, float f) {
     uint64_t n = (uint64_t)t;
     const double frac = t - (double)n;
     if (frac > 0.499999 && frac < 0.500001) return km_fmt_g_slow(p, x);
-    if (frac > 0.5) n++;
+    n += (uint64_t)(frac > 0.5);
     if (n >= 1000000) { n = 100000; e++; if (e > 5) return km_fmt_g_slow(p, x); }
     if (n < 100000) return km_fmt_g_slow(p, x);          // cannot happen for exact inputs; be safe
     if (x < 0) *p++ = '-';
-    char d[6];
-    for (int i = 5; i >= 0; i--) { d[i] = (char)('0' + n % 10); n /= 10; }
-    int last = 5;
-    while (last > 0 && d[last] == '0') last--;           // significant digits d[0..last]
+    // six significant digits, two per table lookup; d[6..15] pad the fixed-size copies below
+    char d[16] = {'0', '0', '0', '0', '0', '0', '0', '0', '0', '0', '0', '0', '0', '0', '0', '0'};
+    const uint32_t n32 = (uint32_t)n, g0 = n32 / 10000, lo = n32 % 10000, g1 = lo / 100, g2 = lo % 100;
+    memcpy(d, KM_DIGIT_PAIRS + 2 * g0, 2); memcpy(d + 2, KM_DIGIT_PAIRS + 2 * g1, 2); memcpy(d + 4, KM_DIGIT_PAIRS + 2 * g2, 2);
+    // index of the last non-zero digit (d[0] is never '0')
+    int last;
+    if (g2) last = (g2 % 10) ? 5 : 4;
+    else if (g1) last = (g1 % 10) ? 3 : 2;
+    else last = (g0 % 10) ? 1 : 0;
+    // no per-digit loops (their trip counts are what the branch predictor cannot learn): whole-group copies, then the
+    // returned pointer cuts the text to its length.  Callers leave >= 16 bytes of slack after every number.
     if (e >= 0) {
-        for (int i = 0; i <= e; i++) *p++ = d[i];        // integer part: e + 1 digits (zeros included)
-        if (last > e) { *p++ = '.'; for (int i = e + 1; i <= last; i++) *p++ = d[i]; }
-    } else {
-        *p++ = '0'; *p++ = '.';
-        for (int i = 0; i < -e - 1; i++) *p++ = '0';
-        for (int i = 0; i <= last; i++) *p++ = d[i];
+        memcpy(p, d, 8);                                 // integer part: digits 0 .. e (zeros included)
+        if (last > e) { p[e + 1] = '.'; memcpy(p + e + 2, d + e + 1, 8); return p + last + 2; }
+        return p + e + 1;
     }
-    return p;
+    memcpy(p, "0.000000", 8);                            // "0." and -e - 1 zeros
+    memcpy(p - e + 1, d, 8);
+    return p - e + 2 + last;
 }
 static inline char *km_fmt_str(char *p, const char *s) { while (*s) *p++ = *s++; return p; }
 // "<tid> <score>" with the text of the previous score reused when the value repeats (lineage ancestors share scores)

@@ -152,7 +152,7 @@ def test_format_tail_numbers_match_printf_g():
     for a in range(0, len(v) - 18, 18):
         blk = v[a:a + 18]
         res["log_avg"], res["stdev"], res["cand_kmer_cnt"], res["tid"], res["score"] = blk[0], blk[1], 131, 9606, abs(blk[2])
-        cands["tid"] = np.arange(16) + 7
+        cands["tid"] = rng.integers(0, 2 ** 32, 16, dtype=np.uint64) >> rng.integers(0, 32, 16, dtype=np.uint64)     # every digit count
         cands["score"] = np.abs(blk[2:18])
         cands["score"][5] = cands["score"][4]                       # repeated score: the memoised text
         n = api.lib().kmat_format_tail(res.ctypes.data, cands.ctypes.data, None, 1, buf, len(buf))
