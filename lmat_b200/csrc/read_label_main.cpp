@@ -24,6 +24,7 @@
 #include <fstream>
 #include <iostream>
 #include <map>
+#include <unordered_map>
 #include <mutex>
 #include <set>
 #include <sstream>
@@ -329,6 +330,8 @@ int main(int argc, char *argv[]) {
             FILE *ofs = fopen(ofname.c_str(), "w");
             if (!ofs) fail("could not open for writing " + ofname);
             std::vector<char> out;
+            std::unordered_map<uint32_t, std::pair<int, float>> tally;               // track_taxids / track_tscores of this "thread"
+            int nomatch[4] = {0, 0, 0, 0};                                            // track_nomatch
             for (;;) {
                 Batch *b = nullptr;
                 {
@@ -361,14 +364,15 @@ int main(int argc, char *argv[]) {
                         p += tn;
                         switch (kmat_tally_class(&r, min_score, opt.min_kmer)) {                 // :1217-1277
                             case 0: {
-                                auto it = w.track_tscore.find(r.tid);
-                                if (it == w.track_tscore.end()) { w.track_match[r.tid] = 1; w.track_tscore[r.tid] = r.score; }
-                                else { w.track_match[r.tid] += 1; it->second += r.score; }
+                                // per tid: count and the float sum of the scores in arrival order (hashed here, copied into
+                                // the ordered maps of the merge step when the writer ends: same per-tid additions, same order)
+                                auto ins = tally.try_emplace(r.tid, 1, r.score);
+                                if (!ins.second) { ins.first->second.first += 1; ins.first->second.second += r.score; }
                                 break;
                             }
-                            case 1: w.track_nomatch[1] += 1; break;
-                            case 2: w.track_nomatch[2] += 1; break;
-                            case 3: w.track_nomatch[3] += 1; break;
+                            case 1: nomatch[1] += 1; break;
+                            case 2: nomatch[2] += 1; break;
+                            case 3: nomatch[3] += 1; break;
                             default: break;
                         }
                     }
@@ -377,6 +381,8 @@ int main(int argc, char *argv[]) {
                 }
                 free_q.push(b);
             }
+            for (const auto &kv : tally) { w.track_match[kv.first] = kv.second.first; w.track_tscore[kv.first] = kv.second.second; }
+            for (int k = 1; k <= 3; k++) if (nomatch[k]) w.track_nomatch[k] = nomatch[k];
             if (ofs) fclose(ofs);
         });
 
