@@ -558,11 +558,10 @@ static const char *match_str(int m) {
 // ---- number formatting.  The reference prints floats with ostream << float, i.e. printf("%g") of the promoted
 // double (6 significant digits, trailing zeros stripped, exponent form outside [1e-4, 1e6)).  At tens of millions of
 // reads per second the host writes ~20 such numbers per read, so snprintf (~300 ns) is the bottleneck of the writers.
-// km_fmt_g is exact: scores in the common range are scaled to a 6-digit integer in double arithmetic (the float ->
-// double conversion and the power of ten are exact, so the product is off by at most half an ulp, ~1e-10 in the
-// fraction); whenever the fraction is within 1e-6 of a rounding boundary, or the value is outside the fixed-notation
-// range, std::to_chars(general, 6) -- specified to equal printf("%.6g") -- decides.  tests/test_abi_cpu.py compares it
-// with printf over random bit patterns and the score-like ranges.
+// km_fmt_g is exact by construction: a float in [1e-4, 999999) is scaled to its six significant digits in integer
+// arithmetic (see the function), rounded to nearest-even on the exact remainder; values outside that range take
+// std::to_chars(general, 6), specified to equal printf("%.6g").  tests/fmt_exhaustive.cpp compares it with printf on
+// every float of the range (279 M values), tests/test_abi_cpu.py on random bit patterns through kmat_format_tail.
 static const char KM_DIGIT_PAIRS[201] =
     "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566676869"
     "707172737475767778798081828384858687888990919293949596979899";
@@ -583,24 +582,35 @@ static char *km_fmt_g_slow(char *p, double x) {
     return r.ptr;
 }
 static inline char *km_fmt_g(char *p, float f) {
-    const double x = (double)f;
-    double v = x < 0 ? -x : x;
-    if (!(v >= 1e-4 && v < 999999.0)) {                  // zero, tiny, huge, inf, nan
-        if (v == 0) { if (std::signbit(x)) *p++ = '-'; *p++ = '0'; return p; }
-        return km_fmt_g_slow(p, x);
+    uint32_t bits; memcpy(&bits, &f, 4);
+    const uint32_t ab = bits & 0x7FFFFFFFu;
+    // fixed notation with a 6-digit significand covers [1e-4, 999999): 0x38D1B718 is the smallest float >= 1e-4,
+    // 0x497423F0 is 999999.0f; everything else (zero, tiny, huge, inf, nan) takes the library path
+    if (ab - 0x38D1B718u >= 0x497423F0u - 0x38D1B718u) {
+        if (ab == 0) { if (bits >> 31) *p++ = '-'; *p++ = '0'; return p; }
+        return km_fmt_g_slow(p, (double)f);
     }
-    static const double P10[] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10};
-    int e;                                               // floor(log10(v)), -4 .. 5
-    if (v >= 1.0) e = v < 10.0 ? 0 : v < 100.0 ? 1 : v < 1e3 ? 2 : v < 1e4 ? 3 : v < 1e5 ? 4 : 5;
-    else e = v >= 0.1 ? -1 : v >= 0.01 ? -2 : v >= 1e-3 ? -3 : -4;
-    const double t = v * P10[5 - e];                     // 1e5 <= t < 1e6 up to rounding
-    uint64_t n = (uint64_t)t;
-    const double frac = t - (double)n;
-    if (frac > 0.499999 && frac < 0.500001) return km_fmt_g_slow(p, x);
-    n += (uint64_t)(frac > 0.5);
-    if (n >= 1000000) { n = 100000; e++; if (e > 5) return km_fmt_g_slow(p, x); }
-    if (n < 100000) return km_fmt_g_slow(p, x);          // cannot happen for exact inputs; be safe
-    if (x < 0) *p++ = '-';
+    // The value is m * 2^(b2 - 23) exactly (m = 24-bit significand).  e = floor(log10(value)): a binade holds at most one
+    // power of ten, so e is the binade's lower bound E_LOW[b2] plus one when m reaches THR[b2], the smallest significand of
+    // that binade whose value is >= 10^(E_LOW + 1) (2^24 = none).  Tables generated with exact rational arithmetic for
+    // b2 = -14 .. 19.  The scaled significand m * 10^(5 - e) < 2^54 is then an exact integer, and shifting it right by
+    // 23 - b2 leaves the six digits and the exact remainder: round to nearest, ties to even -- what printf("%g") does with
+    // the exact binary value.  No floating-point operation, no fallback near ties.
+    static const int8_t E_LOW[34] = {-5, -4, -4, -4, -4, -3, -3, -3, -2, -2, -2, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 5, 5, 5};
+    static const uint32_t THR[34] = {13743896, 16777216, 16777216, 16777216, 8589935, 16777216, 16777216, 10737419, 16777216, 16777216, 13421773,
+                                     16777216, 16777216, 16777216, 16777216, 16777216, 16777216, 10485760, 16777216, 16777216, 13107200, 16777216,
+                                     16777216, 16384000, 16777216, 16777216, 16777216, 10240000, 16777216, 16777216, 12800000, 16777216, 16777216, 16000000};
+    static const uint64_t I10[11] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull, 1000000000ull, 10000000000ull};
+    const int b2 = (int)(ab >> 23) - 127;
+    const uint32_t m = (ab & 0x7FFFFFu) | 0x800000u;
+    int e = E_LOW[b2 + 14] + (m >= THR[b2 + 14]);        // -4 .. 5
+    const uint64_t scaled = (uint64_t)m * I10[5 - e];
+    const int sh = 23 - b2;                              // 4 .. 37
+    uint64_t n = scaled >> sh;
+    const uint64_t rem = scaled & ((1ull << sh) - 1), half = 1ull << (sh - 1);
+    n += (uint64_t)((rem > half) | ((rem == half) & (n & 1)));
+    if (n >= 1000000) { n = 100000; e++; if (e > 5) return km_fmt_g_slow(p, (double)f); }
+    if (bits >> 31) *p++ = '-';
     // six significant digits, two per table lookup; d[6..15] pad the fixed-size copies below
     char d[16] = {'0', '0', '0', '0', '0', '0', '0', '0', '0', '0', '0', '0', '0', '0', '0', '0'};
     const uint32_t n32 = (uint32_t)n, g0 = n32 / 10000, lo = n32 % 10000, g1 = lo / 100, g2 = lo % 100;

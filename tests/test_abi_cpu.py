@@ -180,3 +180,16 @@ def test_flat_image_damaged_header_is_rejected(golden_small, tmp_path):
     open(p, "wb").write(good[:len(good) // 2])
     with pytest.raises(api.KmatError):
         api.Table.open(p)
+
+
+def test_fast_float_formatter_equals_printf_over_its_whole_range(tmp_path):
+    """km_fmt_g is integer-exact by construction; this compares it with printf("%g") on every 7th float of its fast range
+    (40 M values; KMAT_EXHAUSTIVE=1: all 279 M, which is how the change was accepted)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "fmt_exhaustive")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "fmt_exhaustive.cpp"),
+                    "-o", exe, "-lz", "-lpthread"], check=True)
+    p = subprocess.run([exe, "1" if os.environ.get("KMAT_EXHAUSTIVE") else "7"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1200)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "mismatches 0" in p.stdout
