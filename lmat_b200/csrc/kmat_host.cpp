@@ -632,16 +632,24 @@ static inline char *km_fmt_g(char *p, float f) {
     return p - e + 2 + last;
 }
 static inline char *km_fmt_str(char *p, const char *s) { while (*s) *p++ = *s++; return p; }
-// "<tid> <score>" with the text of the previous score reused when the value repeats (lineage ancestors share scores)
-struct KmScoreMemo { float v; int n; char s[32]; bool ok = false; };
+// "<tid> <score>" with the text of the previous score reused when the value repeats (lineage ancestors share scores).
+// The memo points at the previous text inside the output buffer (text is only ever appended); the copy is a fixed 16
+// bytes (a %g text is at most 12), loaded before it is stored because source and destination may be closer than that.
+struct KmScoreMemo { uint32_t bits = 0; const char *s = nullptr; int n = 0; };
 static inline char *km_fmt_pair(char *p, uint32_t tid, float score, KmScoreMemo &m) {
     p = km_fmt_u32(p, tid);
     *p++ = ' ';
-    uint32_t a, b;
-    memcpy(&a, &score, 4); memcpy(&b, &m.v, 4);
-    if (!m.ok || a != b) { m.v = score; m.n = (int)(km_fmt_g(m.s, score) - m.s); m.ok = true; }
-    memcpy(p, m.s, (size_t)m.n);
-    return p + m.n;
+    uint32_t a;
+    memcpy(&a, &score, 4);
+    if (m.s && a == m.bits) {
+        uint64_t w0, w1;
+        memcpy(&w0, m.s, 8); memcpy(&w1, m.s + 8, 8);
+        memcpy(p, &w0, 8); memcpy(p + 8, &w1, 8);
+        return p + m.n;
+    }
+    char *q = km_fmt_g(p, score);
+    m.bits = a; m.s = p; m.n = (int)(q - p);
+    return q;
 }
 
 extern "C" int kmat_format_tail(const kmat_read_result *r, const kmat_pair *cands, const kmat_pair *lineage, int prn_all, char *buf, size_t cap) {
