@@ -18,7 +18,9 @@
 #define KB_CMAX 64         // candidate taxids per read: candidate i lives in lane i & 31, register slot i >> 5
 #define KB_LFAST 16        // list length resolved in registers (libstdc++ uses plain insertion sort up to 16)
 #define KB_LIN 128         // lineage entries in findReadLabelVer2
+#ifndef KS_THREADS
 #define KS_THREADS 128     // threads per CTA of the scoring kernel (one read per thread)
+#endif
 #define KMAT_ST_PENDING 7  // internal: candidates built, scoring still to run
 #define KMAT_ST_PENDING_BIG 8   // internal: candidates built by km_cand_big_kernel (more than KB_CMAX of them), scored by km_score_big_kernel
 #define KMAT_ST_DEFERRED 9      // internal: queued for the slow candidate kernel
@@ -866,7 +868,9 @@ __device__ __forceinline__ void ks_score_one(const KmScoreParams &P, const uint3
 #ifndef KMAT_K4_BLOCK_SORT
 #define KMAT_K4_BLOCK_SORT 0
 #endif
+#ifndef KS_SORT_ROUNDS
 #define KS_SORT_ROUNDS 4
+#endif
 #if KMAT_K4_BLOCK_SORT
 #define KS_READS_PER_CTA (KS_THREADS * KS_SORT_ROUNDS)
 __global__ void __launch_bounds__(KS_THREADS) km_score_kernel(KmScoreParams P) {

@@ -7,7 +7,7 @@
 mkdir -p gpurun_out
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/k4_default.json 2> gpurun_out/k4_default.err
 i=0
-for defs in "-DKMAT_K4_PACKED_DEPTH=1" "-DKMAT_K4_BLOCK_SORT=1" "-DKMAT_K4_PACKED_DEPTH=1 -DKMAT_K4_BLOCK_SORT=1"; do
+for defs in "-DKMAT_K4_PACKED_DEPTH=1" "-DKMAT_K4_BLOCK_SORT=1" "-DKMAT_K4_PACKED_DEPTH=1 -DKMAT_K4_BLOCK_SORT=1" "-DKMAT_K4_PACKED_DEPTH=1 -DKMAT_K4_BLOCK_SORT=1 -DKS_SORT_ROUNDS=8"; do
     i=$((i+1))
     KMAT_NVCC_DEFINES="$defs" python -c "from lmat_b200 import build; build.build_all(force=True)"
     python -m pytest tests -m gpu -x -q -k "parity or golden or cli" > gpurun_out/k4_exp${i}_tests.log 2>&1
@@ -17,7 +17,7 @@ done
 python -c "from lmat_b200 import build; build.build_all(force=True)"
 python - <<'PY'
 import json
-for n in ("default", "exp1", "exp2", "exp3"):
+for n in ("default", "exp1", "exp2", "exp3", "exp4"):
     try:
         j = json.loads(open(f"gpurun_out/k4_{n}.json").read().strip().splitlines()[-1])
         print(n, j.get("value"), j.get("ms_per_step"), j.get("kernels_ms"))
