@@ -6,7 +6,7 @@
 #   2. line-gather rates (tools/line_gather.py): does the request ceiling count lines or sectors?  Decides whether the
 #      minimizer-ordered table (lmat_b200/csrc/kmat_mzr.h) is worth its kernels.
 #   3. scoring kernel with the depth packed into the sorted element (-DKMAT_K4_PACKED_DEPTH=1): parity + bench.
-# Usage: gpurun --timeout 2400 -- tools/gpu_round3_first.sh
+# Usage: tools/build_variants.sh (here, ~1 min) then gpurun --timeout 2400 -- tools/gpu_round3_first.sh
 set -u
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02a_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02a_pytest_gpu.log
