@@ -36,6 +36,16 @@ extern "C" int kmat_device_memory(int device, uint64_t *free_bytes, uint64_t *to
 // geometry
 // ---------------------------------------------------------------------------------------------
 static int km_choose_bucket_bits(uint64_t n, int kmer_bits) {
+#if KMAT_LINE_TABLE
+    {   // <= 2 k-mers per 16-slot line on average; line bits within the geometry of kmat_mzr.h; 4 buckets per line
+        int bl = 4;
+        while (((uint64_t)2 << bl) < n) bl++;
+        if (getenv("KMAT_TEST_TIGHT_TABLE")) bl -= 2;
+        if (bl < kmer_bits + 4 - KM_REM_BITS) bl = kmer_bits + 4 - KM_REM_BITS;
+        if (bl > 2 * KM_LINE_M) bl = 2 * KM_LINE_M;
+        return bl + 2;
+    }
+#endif
     int b = 4;
     while (((uint64_t)1 << b) < n) b++;               // <= 1 key per 4-slot bucket on average: ~1.5 % of the home buckets are full
     if (getenv("KMAT_TEST_TIGHT_TABLE")) b = b > 6 ? b - 2 : 4;   // tests: a nearly full table exercises displacement, the stash and doubling
@@ -52,20 +62,33 @@ extern "C" uint32_t kmat_shard_of(uint64_t kmer, int kmer_length, int shard_coun
 // ---------------------------------------------------------------------------------------------
 // build
 // ---------------------------------------------------------------------------------------------
+#if KMAT_LINE_TABLE
+#define KM_STASH_CAP (1u << 25)       // heavy minimizers overflow their four lines: ~0.1-1 % of the k-mers at <= 2 per line
+#else
 #define KM_STASH_CAP 65536u
+#endif
 __global__ void km_insert_kernel(const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ payload, uint64_t n,
                                  unsigned long long *slots, uint64_t bucket_mask, int kmer_bits, int rem_bits,
                                  unsigned int *stash_n, uint64_t *stash_x, uint32_t *stash_hit,
                                  uint32_t shard_index, uint32_t shard_count, unsigned long long *n_kept) {
     unsigned long long kept = 0;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t x = km_mix(kmers[i], kmer_bits);
+        const uint64_t x = KM_KEY(kmers[i], kmer_bits, bucket_mask);
         if (shard_count > 1 && km_owner_of_x(x, shard_count) != shard_index) continue;     // another shard's k-mer
         kept++;
         const uint64_t home = x >> rem_bits, rem = x & ((1ull << rem_bits) - 1);
         const uint32_t pl = payload[i];
         const uint64_t base = (1ull << 63) | ((uint64_t)((pl >> 31) & 1) << 62) | (rem << 32) | (pl & 0x7FFFFFFFu);
         bool done = false;
+#if KMAT_LINE_TABLE
+        for (int t = 0; t < KM_LINE_STEPS && !done; t++) {           // home sector, rest of the line, then three more lines
+            unsigned long long *b = slots + km_line_bucket_at(home, t, bucket_mask) * KM_SLOTS_PER_BUCKET;
+            const unsigned long long v = base | ((uint64_t)(t >> 2) << 60);
+            for (int s = 0; s < KM_SLOTS_PER_BUCKET && !done; s++) {
+                if (b[s] == 0ull && atomicCAS(b + s, 0ull, v) == 0ull) done = true;
+            }
+        }
+#else
         for (int d = 0; d <= KM_MAX_DISP && !done; d++) {
             unsigned long long *b = slots + ((home + d) & bucket_mask) * KM_SLOTS_PER_BUCKET;
             const unsigned long long v = base | ((uint64_t)d << 60);
@@ -73,6 +96,7 @@ __global__ void km_insert_kernel(const uint64_t *__restrict__ kmers, const uint3
                 if (b[s] == 0ull && atomicCAS(b + s, 0ull, v) == 0ull) done = true;
             }
         }
+#endif
         if (!done) {                                   // KM_MAX_DISP + 1 full buckets: the key goes to the stash
             const unsigned int q = atomicAdd(stash_n, 1u);
             if (q < KM_STASH_CAP) { stash_x[q] = x; stash_hit[q] = pl; }
@@ -98,6 +122,10 @@ static int km_db_alloc_and_insert(kmat_db *db, const uint64_t *d_kmers, const ui
     for (int b = km_choose_bucket_bits(expect, kmer_bits);; b++) {
         if (b > kmer_bits) { kmat_set_error("hash table build failed: displacement limit at maximum size"); return KMAT_ERR_UNSUPPORTED; }
         db->geom.kmer_bits = kmer_bits; db->geom.bucket_bits = b; db->geom.rem_bits = kmer_bits - b;
+#if KMAT_LINE_TABLE
+        if (!km_line_ok(db->kmer_len, KM_LINE_M, b - 2) || shard_count > 1) { kmat_set_error("line-table experiment: k = %d with 2^%d lines (or a sharded table) is outside its geometry", db->kmer_len, b - 2); return KMAT_ERR_UNSUPPORTED; }
+        db->geom.rem_bits = KM_REM_BITS;
+#endif
         db->n_buckets = 1ull << b;
         const size_t bytes = db->n_buckets * KM_SLOTS_PER_BUCKET * sizeof(uint64_t);
         KM_CUDA(cudaMalloc((void **)&db->d_slots, bytes));
@@ -488,7 +516,7 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32) km_encode_probe_kernel(Km
             }
             if (p >= 0 && j < len) {
                 P.hit[off + p] = hw;
-                if (P.xq && first) P.xq[off + p] = km_mix(canon, kmer_bits);
+                if (P.xq && first) P.xq[off + p] = KM_KEY(canon, kmer_bits, P.db.bucket_mask);
                 if (P.out_kmers) { P.out_kmers[off + p] = ok ? canon : 0; P.out_flags[off + p] = ok ? (first ? 1 : 2) : 0; }
             }
             prev = cur; pinv = cinv; pgc = cgc;
@@ -627,7 +655,7 @@ __global__ void __launch_bounds__(KM_LONG_THREADS, 1) km_encode_probe_long_kerne
                     }
                     if (first[u]) {
                         cn[u] = canon;
-                        xk[u] = km_mix(canon, kmer_bits);
+                        xk[u] = KM_KEY(canon, kmer_bits, P.db.bucket_mask);
                         if (P.do_probe)
                             km_load_bucket(km_slots_of(P.db, xk[u], owner[u]) + ((xk[u] >> P.db.rem_bits) & P.db.bucket_mask) * KM_SLOTS_PER_BUCKET, bk[u][0], bk[u][1], bk[u][2], bk[u][3]);
                     }
@@ -735,7 +763,7 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
             if (ok) {
                 const uint64_t rc = km_revcomp(fwd, kmer_bits);
                 const uint64_t canon = fwd < rc ? fwd : rc;                    // read_label.cpp:1009
-                xk[c] = km_mix(canon, kmer_bits);
+                xk[c] = KM_KEY(canon, kmer_bits, P.db.bucket_mask);
                 if (STATS) canon_s[c] = canon;
                 okbits |= 1u << c;
             }
@@ -749,7 +777,7 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
             if ((okbits >> c) & 1) {
-                const uint32_t h = (uint32_t)(xk[c] >> 7) & (SETN - 1);
+                const uint32_t h = KM_SET_HASH(xk[c]) & (SETN - 1);
                 const uint32_t old = atomicOr(bitmap + (h >> 5), 1u << (h & 31));
                 if ((old >> (h & 31)) & 1) suspect |= 1u << c; else first |= 1u << c;
             }
@@ -777,7 +805,7 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
         }
         // the words this lane touched go back to zero for the next read (every set bit lies in such a word)
 #pragma unroll
-        for (int c = 0; c < NCH; c++) if ((okbits >> c) & 1) bitmap[((uint32_t)(xk[c] >> 7) & (SETN - 1)) >> 5] = 0;
+        for (int c = 0; c < NCH; c++) if ((okbits >> c) & 1) bitmap[(KM_SET_HASH(xk[c]) & (SETN - 1)) >> 5] = 0;
         // ---- probe the first occurrences: every home-bucket gather of the read is issued before the first one is
         //      looked at (NCH independent LDG.256 per lane in flight), then one hit word per k-mer start position
         uint64_t bk[NCH][4];

@@ -53,7 +53,12 @@ struct KmStatsDev {
 // L2 fill is limited to 64 bytes: by default a miss brings the whole 128-byte line in from DRAM (measured: 127 B of
 // DRAM traffic per random gather, 64 B with this hint, same request rate - profiles/r01_gather_modes.md).
 __device__ __forceinline__ void km_load_bucket(const uint64_t *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
+#if KMAT_LINE_TABLE
+    // the line table WANTS the whole 128-byte line in L2: the neighbouring k-mers of the read ask for its other sectors
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+#endif
 }
 
 // One bucket of the probe sequence against (rem, displacement d): 0 = found (hw set), 1 = absent for good (a free
@@ -92,6 +97,16 @@ __device__ __forceinline__ uint32_t km_probe_x(const KmDbDev &db, uint64_t x, ui
     extra = 0;
     uint32_t owner;
     const uint64_t *slots = km_slots_of(db, x, owner);
+#if KMAT_LINE_TABLE
+#pragma unroll 1
+    for (int t = d0; t < KM_LINE_STEPS; t++) {            // d0 = 1: the caller has already looked at the home sector (step 0)
+        uint64_t s0, s1, s2, s3;
+        km_load_bucket(slots + km_line_bucket_at(home, t, db.bucket_mask) * KM_SLOTS_PER_BUCKET, s0, s1, s2, s3);
+        uint32_t hw;
+        if (km_bucket_match(s0, s1, s2, s3, rem, t >> 2, hw) != 2) return km_tag_owner(db, hw, owner);
+        extra++;
+    }
+#else
 #pragma unroll 1
     for (int d = d0; d <= KM_MAX_DISP; d++) {
         uint64_t s0, s1, s2, s3;
@@ -100,6 +115,7 @@ __device__ __forceinline__ uint32_t km_probe_x(const KmDbDev &db, uint64_t x, ui
         if (km_bucket_match(s0, s1, s2, s3, rem, d, hw) != 2) return km_tag_owner(db, hw, owner);
         extra++;
     }
+#endif
     // every bucket of the probe window is full: the key, if present, sits in the stash
     const uint64_t *stash_x = db.stash_x; const uint32_t *stash_hit = db.stash_hit;
     uint32_t lo = 0, hi = db.n_stash;
@@ -113,7 +129,7 @@ __device__ __forceinline__ uint32_t km_probe_x(const KmDbDev &db, uint64_t x, ui
     return KM_HIT_MISS;
 }
 __device__ __forceinline__ uint32_t km_probe(const KmDbDev &db, uint64_t kmer, uint32_t &extra) {
-    return km_probe_x(db, km_mix(kmer, db.kmer_bits), extra);
+    return km_probe_x(db, KM_KEY(kmer, db.kmer_bits, db.bucket_mask), extra);
 }
 
 __device__ __forceinline__ int km_warp_sum(int v) { return __reduce_add_sync(KM_FULL, v); }

@@ -140,6 +140,35 @@ KM_HD uint64_t km_mzr_kmer_of(uint64_t line, uint32_t key, int k, int m, int b) 
 }
 KM_HD bool km_mzr_geometry_ok(int k, int m, int b) { return m >= 8 && 2 * m <= 32 && k - m + 1 <= (1 << KM_MZR_OFF_BITS) && k > m && b <= 2 * m && 2 * k - b + 4 <= KM_MZR_KEY_BITS; }
 
+// ---- the line table on today's slot format (-DKMAT_LINE_TABLE=1, kmat_internal.h; experiment, replicated table only) ----
+// The kernels address the table through a 64-bit key x: bucket = x >> rem_bits, remainder = the low rem_bits.  With
+//     x = [line : bl bits] [s0 : 2 bits] [key : 28 bits],  rem_bits = 28,  4 x 2^bl buckets of 4 slots
+// the home bucket is sector s0 = (a hash of the key) of the minimizer's 128-byte line, so the probe kernel's one LDG.256
+// per k-mer stays as it is.  What changes is where a k-mer goes when that sector is full -- the rest of its line first,
+// then the next three lines: step t = 0 .. 15 visits sector (s0 + t) & 3 of line home + (t >> 2), and the slot's two
+// displacement bits hold t >> 2.  Insert and probe walk the same order and an insert takes the first free slot, so a free
+// slot on the way proves absence.  (The key-function-only shortcut of profiles/r01_minimizer_study.md fails because it
+// keeps a minimizer's k-mers in ONE 4-slot bucket; here they have the 16 slots of their line and 48 more behind it.)
+KM_HD bool km_line_ok(int k, int m, int bl) { return km_mzr_geometry_ok(k, m, bl); }
+KM_HD uint64_t km_line_x(uint64_t canon, int k, int m, int bl) {
+    const uint64_t rck = km_mzr_revcomp(canon, k);         // window j of rck = reverse complement of window k-m-j of canon
+    KmMzr z; z.hmin = 0xFFFFFFFFu; z.off = 0; z.flip = 0;
+    for (int j = 0; j + m <= k; j++) {
+        const uint32_t f = km_mzr_window(canon, k, m, j), r = km_mzr_window(rck, k, m, k - m - j);
+        const uint32_t h = km_mzr_mix(f < r ? f : r, m);
+        if (h < z.hmin || j == 0) { z.hmin = h; z.off = (uint32_t)j; z.flip = f > r; }    // strict <: the smallest j wins a tie
+    }
+    const uint32_t key = km_mzr_key(canon, z, k, m, bl);
+    const uint32_t s0 = (key * 0x9E3779B1u) >> 30;
+    return (km_mzr_line(z, m, bl) << 30) | ((uint64_t)s0 << 28) | key;
+}
+KM_HD uint64_t km_line_kmer_of(uint64_t x, int k, int m, int bl) { return km_mzr_kmer_of(x >> 30, (uint32_t)(x & 0x0FFFFFFFu), k, m, bl); }
+// bucket visited at step t of the probe order (home_bucket = x >> 28)
+KM_HD uint64_t km_line_bucket_at(uint64_t home_bucket, int t, uint64_t bucket_mask) {
+    return ((((home_bucket >> 2) + (uint64_t)(t >> 2)) << 2) | ((home_bucket + (uint64_t)t) & 3)) & bucket_mask;
+}
+#define KM_LINE_STEPS 16
+
 // ---- one line: 16 slots of [63] occupied [62] is_list [61:60] displacement [59:32] key [31:0] payload (kmat_internal.h) ----
 // 0 = found (payload and list flag in hw), 1 = absent for good (a free slot: keys are only displaced out of FULL lines),
 // 2 = the line is full, look at the next one

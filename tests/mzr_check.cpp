@@ -152,6 +152,67 @@ int main(int argc, char **argv) {
         CHECK(hw == 0xFFFFFFFEu, "absent k-mer %llx answered %u", (unsigned long long)f, hw);
         absent++;
     }
+    // 3b. the line table on 4-slot buckets (-DKMAT_LINE_TABLE): key round trip, and the step order shared by insert and probe
+    {
+        const int k2 = 20, m2 = 15;
+        for (int bl : {16, 20, 29, 30}) {
+            CHECK(km_line_ok(k2, m2, bl), "line geometry %d", bl);
+            for (int style = 0; style < 3; style++)
+                for (int rep = 0; rep < 20; rep++) {
+                    const std::string s = random_seq(300, style);
+                    for (size_t p = 0; p + k2 <= s.size(); p++) {
+                        const uint64_t f = kmer_at(s, p, k2), r = km_mzr_revcomp(f, k2), c = f < r ? f : r;
+                        const uint64_t x = km_line_x(c, k2, m2, bl);
+                        CHECK((x >> 30) < (1ull << bl), "line range");
+                        CHECK(km_line_kmer_of(x, k2, m2, bl) == c, "line key round trip bl=%d kmer=%llx", bl, (unsigned long long)c);
+                        const KmMzr z = km_mzr_of(c, k2, m2);
+                        CHECK((x >> 30) == km_mzr_line(z, m2, bl) && (uint32_t)(x & 0x0FFFFFFFu) == km_mzr_key(c, z, k2, m2, bl), "line key fields");
+                    }
+                }
+        }
+        const int bl = 16;
+        const uint64_t bmask = (4ull << bl) - 1;
+        std::vector<uint64_t> slots((size_t)16 << bl, 0);
+        std::unordered_map<uint64_t, uint32_t> stash2;
+        uint64_t at_step[KM_LINE_STEPS + 1] = {0};
+        auto match = [&](const uint64_t *bk, uint64_t rem, int d, uint32_t &hw) {      // km_bucket_match of kmat_device.cuh
+            const uint64_t want = (1ull << 63) | ((uint64_t)d << 60) | (rem << 32), keymask = ~((1ull << 62) | 0xFFFFFFFFull);
+            bool full = true;
+            for (int q = 0; q < 4; q++) { if ((bk[q] & keymask) == want) { hw = (uint32_t)bk[q]; return 0; } if (!bk[q]) full = false; }
+            hw = 0xFFFFFFFEu; return full ? 2 : 1;
+        };
+        for (auto &kv : truth) {
+            const uint64_t x = km_line_x(kv.first, k2, m2, bl), home = x >> 28, rem = x & 0x0FFFFFFFull;
+            int t = 0; bool done = false;
+            for (; t < KM_LINE_STEPS && !done; t++) {
+                uint64_t *bk = &slots[km_line_bucket_at(home, t, bmask) * 4];
+                for (int q = 0; q < 4 && !done; q++) if (!bk[q]) { bk[q] = (1ull << 63) | ((uint64_t)(t >> 2) << 60) | (rem << 32) | kv.second; done = true; }
+                if (done) break;
+            }
+            if (!done) { stash2[x] = kv.second; at_step[KM_LINE_STEPS]++; } else at_step[t]++;
+        }
+        auto find2 = [&](uint64_t canon, uint32_t &hw) {
+            const uint64_t x = km_line_x(canon, k2, m2, bl), home = x >> 28, rem = x & 0x0FFFFFFFull;
+            for (int t = 0; t < KM_LINE_STEPS; t++) {
+                const int r = match(&slots[km_line_bucket_at(home, t, bmask) * 4], rem, t >> 2, hw);
+                if (r != 2) return t + 1;
+            }
+            auto it = stash2.find(x); hw = it == stash2.end() ? 0xFFFFFFFEu : it->second;
+            return KM_LINE_STEPS + 1;
+        };
+        uint64_t steps = 0;
+        for (auto &kv : truth) { uint32_t hw; steps += find2(kv.first, hw); CHECK(hw == kv.second, "line table k-mer %llx", (unsigned long long)kv.first); }
+        for (int i = 0; i < 200000; i++) {
+            const uint64_t f = rnd() & ((1ull << (2 * k2)) - 1), r = km_mzr_revcomp(f, k2), c = f < r ? f : r;
+            if (truth.count(c)) continue;
+            uint32_t hw; find2(c, hw);
+            CHECK(hw == 0xFFFFFFFEu, "line table: absent k-mer %llx answered", (unsigned long long)c);
+        }
+        fprintf(stderr, "line table (m=15, %.2f k-mers per line): home sector %.1f%%, rest of line %.1f%%, later lines %.1f%%, stash %.2f%%, %.2f sectors per stored lookup\n",
+                (double)truth.size() / (1ull << bl), 100.0 * at_step[0] / truth.size(), 100.0 * (at_step[1] + at_step[2] + at_step[3]) / truth.size(),
+                100.0 * (truth.size() - at_step[0] - at_step[1] - at_step[2] - at_step[3] - at_step[KM_LINE_STEPS]) / truth.size(),
+                100.0 * at_step[KM_LINE_STEPS] / truth.size(), (double)steps / truth.size());
+    }
     // 4. what the layout is for: distinct lines touched by the k-mers of a 150 bp read with a few substitutions
     uint64_t reads = 0, kmers = 0, lines = 0;
     for (int i = 0; i < 2000; i++) {

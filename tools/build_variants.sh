@@ -11,7 +11,8 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 build_one() {   # name, defines
     local name=$1; shift
     $NVCC $FLAGS "$@" -c $ROOT/lmat_b200/csrc/kmat_label.cu -o $V/obj/kmat_label_$name.o
-    $NVCC -shared -gencode arch=compute_100a,code=sm_100a -o $V/libkmat_$name.so $V/obj/kmat_label_$name.o $ROOT/lmat_b200/build/kmat_db.cu.o \
+    $NVCC $FLAGS "$@" -c $ROOT/lmat_b200/csrc/kmat_db.cu -o $V/obj/kmat_db_$name.o
+    $NVCC -shared -gencode arch=compute_100a,code=sm_100a -o $V/libkmat_$name.so $V/obj/kmat_label_$name.o $V/obj/kmat_db_$name.o \
         $ROOT/lmat_b200/build/kmat_host.cpp.o $ROOT/lmat_b200/build/kmat_reader.cpp.o $ROOT/lmat_b200/build/kmat_build.cpp.o -lz -Xcompiler -fPIC
     echo "built $V/libkmat_$name.so ($*)"
 }
@@ -19,3 +20,4 @@ build_one exp1 -DKMAT_K4_PACKED_DEPTH=1
 build_one exp2 -DKMAT_K4_BLOCK_SORT=1
 build_one exp3 -DKMAT_K4_PACKED_DEPTH=1 -DKMAT_K4_BLOCK_SORT=1
 build_one exp4 -DKMAT_K4_PACKED_DEPTH=1 -DKMAT_K4_BLOCK_SORT=1 -DKS_SORT_ROUNDS=8
+build_one exp5 -DKMAT_LINE_TABLE=1

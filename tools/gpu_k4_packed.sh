@@ -6,15 +6,18 @@
 #   exp1 -DKMAT_K4_PACKED_DEPTH=1     depth carried in the sorted rank_label element (no local-memory loads in TCmp)
 #   exp2 -DKMAT_K4_BLOCK_SORT=1       a CTA counting-sorts 512 queued reads by candidate count before scoring them
 #   exp3 both                          exp4 both, 1024 reads per CTA
+#   exp5 -DKMAT_LINE_TABLE=1           the minimizer-ordered line table (kmat_mzr.h) on today's slot format: replicated table
+#                                      only (the sharded tests are skipped for it); 69 GB table for the bench workload
 mkdir -p gpurun_out
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/k4_default.json 2> gpurun_out/k4_default.err
-DEFS=("" "-DKMAT_K4_PACKED_DEPTH=1" "-DKMAT_K4_BLOCK_SORT=1" "-DKMAT_K4_PACKED_DEPTH=1 -DKMAT_K4_BLOCK_SORT=1" "-DKMAT_K4_PACKED_DEPTH=1 -DKMAT_K4_BLOCK_SORT=1 -DKS_SORT_ROUNDS=8")
+DEFS=("" "-DKMAT_K4_PACKED_DEPTH=1" "-DKMAT_K4_BLOCK_SORT=1" "-DKMAT_K4_PACKED_DEPTH=1 -DKMAT_K4_BLOCK_SORT=1" "-DKMAT_K4_PACKED_DEPTH=1 -DKMAT_K4_BLOCK_SORT=1 -DKS_SORT_ROUNDS=8" "-DKMAT_LINE_TABLE=1")
 rebuilt=0
-for i in 1 2 3 4; do
+for i in 5 1 2 3 4; do
     lib=$PWD/lmat_b200/variants/libkmat_exp$i.so
     if [ -f "$lib" ]; then export KMAT_LIB=$lib
     else unset KMAT_LIB; rebuilt=1; KMAT_NVCC_DEFINES="${DEFS[$i]}" python -c "from lmat_b200 import build; build.build_all(force=True)"; fi
-    python -m pytest tests/test_gpu_parity.py tests/test_gpu_sharded.py -m gpu -x -q > gpurun_out/k4_exp${i}_tests.log 2>&1
+    T="tests/test_gpu_parity.py tests/test_gpu_sharded.py"; [ $i = 5 ] && T="tests/test_gpu_parity.py"
+    python -m pytest $T -m gpu -q > gpurun_out/k4_exp${i}_tests.log 2>&1
     echo "exp$i ${DEFS[$i]}: $(tail -1 gpurun_out/k4_exp${i}_tests.log)"
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/k4_exp${i}.json 2> gpurun_out/k4_exp${i}.err
 done
@@ -22,10 +25,10 @@ unset KMAT_LIB
 [ $rebuilt = 1 ] && python -c "from lmat_b200 import build; build.build_all(force=True)"
 python - <<'PY'
 import json
-for n in ("default", "exp1", "exp2", "exp3", "exp4"):
+for n in ("default", "exp5", "exp1", "exp2", "exp3", "exp4"):
     try:
         j = json.loads(open(f"gpurun_out/k4_{n}.json").read().strip().splitlines()[-1])
-        print(n, j.get("value"), j.get("ms_per_step"), j.get("kernels_ms"))
+        print(n, j.get("value"), j.get("ms_per_step"), j.get("kernels_ms"), (j.get("roofline") or {}).get("traffic"))
     except Exception as e:
         print(n, "failed", e)
 PY
