@@ -5,11 +5,12 @@
 #      table checks at upload, gather modes 201-205 -- the per-read kernels are unchanged)
 #   2. line-gather rates (tools/line_gather.py): does the request ceiling count lines or sectors?  Decides whether the
 #      minimizer-ordered table (lmat_b200/csrc/kmat_mzr.h) is worth its kernels.
-#   3. scoring kernel with the depth packed into the sorted element (-DKMAT_K4_PACKED_DEPTH=1): parity + bench.
-# Usage: tools/build_variants.sh (here, ~1 min) then gpurun --timeout 2400 -- tools/gpu_round3_first.sh
+#   3. the compile-time variants (tools/gpu_k4_packed.sh): exp5 = the line table (-DKMAT_LINE_TABLE=1) first, then the
+#      scoring-kernel switches (packed depth, per-CTA sort by candidate count): parity tests + bench line each.
+# Usage: tools/build_variants.sh (here, ~1 min) then gpurun --timeout 3600 -- tools/gpu_round3_first.sh
 set -u
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02a_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02a_pytest_gpu.log
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/r02a_smoke.log 2>&1; echo "smoke rc=$?"
 timeout 900 tools/gpu_line_gather.sh
-timeout 1500 tools/gpu_k4_packed.sh
+timeout 2400 tools/gpu_k4_packed.sh
