@@ -704,6 +704,17 @@ __global__ void __launch_bounds__(KM_LONG_THREADS, 1) km_encode_probe_long_kerne
 #ifndef KM_FAST_CTAS
 #define KM_FAST_CTAS 2
 #endif
+#ifndef KMAT_LINE_SHFL
+#define KMAT_LINE_SHFL 0
+#endif
+#if KMAT_LINE_TABLE && KMAT_LINE_SHFL
+// value of the lane `sh` bases to the left: this chunk's lanes, or the tail of the previous chunk (kmat_mzr.h, sliding minimum)
+__device__ __forceinline__ uint64_t km_fetch_left(uint64_t cur, uint64_t prv, int lane, int sh) {
+    const int src = (lane - sh) & 31;
+    const uint64_t a = kb_shfl_u64(cur, src), b = kb_shfl_u64(prv, src);
+    return lane >= sh ? a : b;
+}
+#endif
 template <int NCH, int SETN, bool STATS, bool PEERS>
 __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS : 1) km_encode_probe_fast_kernel(KmProbeParams P) {
     if (!PEERS) P.db.n_peers = 0;                 // the replicated table's instantiation carries no owner logic at all
@@ -743,6 +754,11 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
         uint32_t okbits = 0;
         uint64_t prev = 0; uint32_t pinv = 0xFFFFFFFFu, pgc = 0;
         int valid = 0, vgc = 0, vtot = 0;
+#if KMAT_LINE_TABLE && KMAT_LINE_SHFL
+        uint64_t sp_r[3] = {KM_SLIDE_NONE, KM_SLIDE_NONE, KM_SLIDE_NONE}, sp_l[3] = {KM_SLIDE_NONE, KM_SLIDE_NONE, KM_SLIDE_NONE};
+        const int sl_w = k - KM_LINE_M + 1;                  // windows per k-mer; the sliding form needs 5 .. 8 (uniform)
+        const int sl_bl = KM_BITS_OF_MASK(P.db.bucket_mask) - 2;
+#endif
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
             const uint32_t cinv = __ballot_sync(KM_FULL, code[c] < 0);
@@ -760,9 +776,25 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
             const bool ok_prev = wsh > 0 && ((inv64 >> (wsh - 1)) & wmask) == 0;
             xk[c] = 0;
             if (STATS) canon_s[c] = 0;
+#if KMAT_LINE_TABLE && KMAT_LINE_SHFL
+            uint64_t sl_kr = 0, sl_kl = 0;
+            if (sl_w >= 5 && sl_w <= 8) {                        // every lane takes part: one hash per base, three doubling steps
+                const uint32_t hh = km_slide_hash(fwd, KM_LINE_M);
+                const uint64_t r0 = km_slide_r0(hh), l0 = km_slide_l0(hh);
+                const uint64_t r1 = km_slide_r(r0, km_fetch_left(r0, sp_r[0], lane, 1), 1), l1 = km_slide_l(l0, km_fetch_left(l0, sp_l[0], lane, 1), 1);
+                const uint64_t r2 = km_slide_r(r1, km_fetch_left(r1, sp_r[1], lane, 2), 2), l2 = km_slide_l(l1, km_fetch_left(l1, sp_l[1], lane, 2), 2);
+                sl_kr = km_slide_r(r2, km_fetch_left(r2, sp_r[2], lane, sl_w - 4), sl_w - 4);
+                sl_kl = km_slide_l(l2, km_fetch_left(l2, sp_l[2], lane, sl_w - 4), sl_w - 4);
+                sp_r[0] = r0; sp_r[1] = r1; sp_r[2] = r2; sp_l[0] = l0; sp_l[1] = l1; sp_l[2] = l2;
+            }
+#endif
             if (ok) {
                 const uint64_t rc = km_revcomp(fwd, kmer_bits);
                 const uint64_t canon = fwd < rc ? fwd : rc;                    // read_label.cpp:1009
+#if KMAT_LINE_TABLE && KMAT_LINE_SHFL
+                if (sl_w >= 5 && sl_w <= 8) xk[c] = km_line_x_of(canon, km_slide_finish(sl_kr, sl_kl, fwd, fwd < rc, k, KM_LINE_M), k, KM_LINE_M, sl_bl);
+                else
+#endif
                 xk[c] = KM_KEY(canon, kmer_bits, P.db.bucket_mask);
                 if (STATS) canon_s[c] = canon;
                 okbits |= 1u << c;

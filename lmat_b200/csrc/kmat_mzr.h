@@ -169,6 +169,46 @@ KM_HD uint64_t km_line_bucket_at(uint64_t home_bucket, int t, uint64_t bucket_ma
 }
 #define KM_LINE_STEPS 16
 
+// ---- the minimizer of every k-mer of a read from ONE hash per base (-DKMAT_LINE_SHFL=1 on top of KMAT_LINE_TABLE) ---------
+// Lane j hashes the m-mer that ENDS at its base; the k-mer ending at base j owns the w = k - m + 1 m-mers ending at bases
+// j - w + 1 .. j, so its minimizer is a sliding minimum over the lanes to its left (and the tail of the previous 32-base
+// chunk).  Keys carry the distance to the owning lane so that the argmin survives: R = h << 3 | dist (ties: nearest =
+// rightmost window of the forward strand), L = h << 3 | (7 - dist) (ties: farthest = leftmost).  Three doubling steps
+// cover 1 -> 2 -> 4 -> w windows (5 <= w <= 8).  The canonical k-mer's rule (smallest offset in the CANONICAL k-mer) is the
+// leftmost window when the read's strand is the canonical one and the rightmost otherwise.
+#define KM_SLIDE_NONE 0x7FFFFFFFFFFFFF00ull     // "no m-mer here" (before the read): loses every minimum, survives + shift
+KM_HD uint64_t km_slide_r0(uint32_t h) { return (uint64_t)h << 3; }
+KM_HD uint64_t km_slide_l0(uint32_t h) { return ((uint64_t)h << 3) | 7u; }
+KM_HD uint64_t km_slide_r(uint64_t mine, uint64_t from_left, int shift) { const uint64_t c = from_left + (uint64_t)shift; return c < mine ? c : mine; }
+KM_HD uint64_t km_slide_l(uint64_t mine, uint64_t from_left, int shift) { const uint64_t c = from_left - (uint64_t)shift; return c < mine ? c : mine; }
+KM_HD uint32_t km_mzr_revcomp_m(uint32_t f, int m) {      // 32-bit twin of km_mzr_revcomp for m-mers (2m <= 32)
+    uint32_t x = ~f;
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+    x = (x >> 16) | (x << 16);
+    return m >= 16 ? x : x >> (32 - 2 * m);
+}
+KM_HD uint32_t km_slide_hash(uint64_t fwd_kmer_ending_here, int m) {
+    const uint32_t f = (uint32_t)(fwd_kmer_ending_here & (m >= 16 ? 0xFFFFFFFFull : ((1ull << (2 * m)) - 1))), r = km_mzr_revcomp_m(f, m);
+    return km_mzr_mix(f < r ? f : r, m);
+}
+// after the last step: the minimizer record of the k-mer `fwd` that ends at this lane
+KM_HD KmMzr km_slide_finish(uint64_t kr, uint64_t kl, uint64_t fwd, bool fwd_is_canon, int k, int m) {
+    KmMzr z;
+    z.hmin = (uint32_t)(kr >> 3);
+    const int w = k - m + 1, dist = fwd_is_canon ? 7 - (int)(kl & 7) : (int)(kr & 7);
+    const int i = (w - 1) - dist;                             // window index in the forward k-mer
+    const uint32_t f = km_mzr_window(fwd, k, m, i), r = km_mzr_revcomp_m(f, m);
+    if (fwd_is_canon) { z.off = (uint32_t)i; z.flip = f > r; }
+    else { z.off = (uint32_t)(k - m - i); z.flip = r > f; }
+    return z;
+}
+KM_HD uint64_t km_line_x_of(uint64_t canon, const KmMzr &z, int k, int m, int bl) {
+    const uint32_t key = km_mzr_key(canon, z, k, m, bl);
+    return (km_mzr_line(z, m, bl) << 30) | ((uint64_t)((key * 0x9E3779B1u) >> 30) << 28) | key;
+}
+
 // ---- one line: 16 slots of [63] occupied [62] is_list [61:60] displacement [59:32] key [31:0] payload (kmat_internal.h) ----
 // 0 = found (payload and list flag in hw), 1 = absent for good (a free slot: keys are only displaced out of FULL lines),
 // 2 = the line is full, look at the next one

@@ -213,6 +213,50 @@ int main(int argc, char **argv) {
                 100.0 * (truth.size() - at_step[0] - at_step[1] - at_step[2] - at_step[3] - at_step[KM_LINE_STEPS]) / truth.size(),
                 100.0 * at_step[KM_LINE_STEPS] / truth.size(), (double)steps / truth.size());
     }
+    // 3c. the sliding-minimum form of the minimizer (one hash per base, distance-carrying keys), emulated for a warp:
+    //     arrays stand for the 32 lanes, index arithmetic for the shuffles; chunks of 32 bases as in the probe kernel
+    {
+        uint64_t n_checked = 0;
+        for (int m2 : {14, 15}) {
+            const int k2 = 20, w = k2 - m2 + 1, last_shift = w - 4;
+            for (int style = 0; style < 3; style++)
+                for (int rep = 0; rep < 60; rep++) {
+                    const std::string s = random_seq(150 + rnd() % 100, style);
+                    const int len = (int)s.size(), nch = (len + 31) / 32;
+                    uint64_t pr[3][32], pl[3][32];                        // the previous chunk's keys at the three levels
+                    for (auto &a : pr) for (auto &v : a) v = KM_SLIDE_NONE;
+                    for (auto &a : pl) for (auto &v : a) v = KM_SLIDE_NONE;
+                    for (int c = 0; c < nch; c++) {
+                        uint64_t fwd[32], r0[32], l0[32], r1[32], l1[32], r2[32], l2[32], r3[32], l3[32];
+                        for (int lane = 0; lane < 32; lane++) {
+                            const int j = 32 * c + lane;
+                            uint64_t v = 0;                               // the k2 bases ending at j (zeros before the read, as in the kernel)
+                            for (int q = j - k2 + 1; q <= j; q++) v = (v << 2) | (uint64_t)((q >= 0 && q < len) ? s[q] : 0);
+                            fwd[lane] = v;
+                            const uint32_t h = km_slide_hash(v, m2);
+                            r0[lane] = km_slide_r0(h); l0[lane] = km_slide_l0(h);
+                        }
+                        auto fetch = [&](const uint64_t *cur, const uint64_t *prv, int lane, int sh) { return lane >= sh ? cur[lane - sh] : prv[lane - sh + 32]; };
+                        for (int lane = 0; lane < 32; lane++) { r1[lane] = km_slide_r(r0[lane], fetch(r0, pr[0], lane, 1), 1); l1[lane] = km_slide_l(l0[lane], fetch(l0, pl[0], lane, 1), 1); }
+                        for (int lane = 0; lane < 32; lane++) { r2[lane] = km_slide_r(r1[lane], fetch(r1, pr[1], lane, 2), 2); l2[lane] = km_slide_l(l1[lane], fetch(l1, pl[1], lane, 2), 2); }
+                        for (int lane = 0; lane < 32; lane++) { r3[lane] = km_slide_r(r2[lane], fetch(r2, pr[2], lane, last_shift), last_shift); l3[lane] = km_slide_l(l2[lane], fetch(l2, pl[2], lane, last_shift), last_shift); }
+                        for (int lane = 0; lane < 32; lane++) {
+                            const int j = 32 * c + lane;
+                            if (j < k2 - 1 || j >= len) continue;         // no k-mer ends here
+                            const uint64_t rc = km_mzr_revcomp(fwd[lane], k2);
+                            const bool fc = fwd[lane] < rc;
+                            const uint64_t canon = fc ? fwd[lane] : rc;
+                            const KmMzr a = km_mzr_of(canon, k2, m2), z = km_slide_finish(r3[lane], l3[lane], fwd[lane], fc, k2, m2);
+                            CHECK(a.hmin == z.hmin && a.off == z.off && a.flip == z.flip, "sliding minimum m=%d base %d: %u/%u/%u vs %u/%u/%u", m2, j, a.hmin, a.off, a.flip, z.hmin, z.off, z.flip);
+                            CHECK(km_line_x_of(canon, z, k2, m2, 20) == km_line_x(canon, k2, m2, 20), "line key from the sliding form");
+                            n_checked++;
+                        }
+                        for (int lane = 0; lane < 32; lane++) { pr[0][lane] = r0[lane]; pr[1][lane] = r1[lane]; pr[2][lane] = r2[lane]; pl[0][lane] = l0[lane]; pl[1][lane] = l1[lane]; pl[2][lane] = l2[lane]; }
+                    }
+                }
+        }
+        CHECK(n_checked > 50000, "sliding-minimum emulation checked too little");
+    }
     // 4. what the layout is for: distinct lines touched by the k-mers of a 150 bp read with a few substitutions
     uint64_t reads = 0, kmers = 0, lines = 0;
     for (int i = 0; i < 2000; i++) {

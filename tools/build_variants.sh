@@ -21,3 +21,4 @@ build_one exp2 -DKMAT_K4_BLOCK_SORT=1
 build_one exp3 -DKMAT_K4_PACKED_DEPTH=1 -DKMAT_K4_BLOCK_SORT=1
 build_one exp4 -DKMAT_K4_PACKED_DEPTH=1 -DKMAT_K4_BLOCK_SORT=1 -DKS_SORT_ROUNDS=8
 build_one exp5 -DKMAT_LINE_TABLE=1
+build_one exp6 -DKMAT_LINE_TABLE=1 -DKMAT_LINE_SHFL=1
