@@ -193,3 +193,33 @@ def test_fast_float_formatter_equals_printf_over_its_whole_range(tmp_path):
     p = subprocess.run([exe, "1" if os.environ.get("KMAT_EXHAUSTIVE") else "7"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1200)
     assert p.returncode == 0, p.stderr[-2000:]
     assert "mismatches 0" in p.stdout
+
+
+def test_format_tail_never_writes_past_its_capacity():
+    """Random results (any status, any float bit pattern, up to 300 candidates) into buffers of awkward sizes: the call
+    either fits (n <= cap) or reports KMAT_ERR_OVERFLOW / an error, and the bytes behind `cap` stay untouched (the
+    formatter places digits with fixed-size copies that need slack, which the capacity check has to account for)."""
+    L = api.lib()
+    rng = np.random.default_rng(5)
+    for it in range(4000):
+        nc = int(rng.choice([0, 1, 2, 5, 17, 64, 300]))
+        nl = int(rng.choice([0, 1, 3, 40]))
+        res = np.zeros(1, dtype=api.RESULT_DTYPE)
+        res["status"], res["match"] = rng.integers(0, 8), rng.integers(0, 6)
+        for f in ("n1", "n2", "valid_kmers", "cand_kmer_cnt", "bin_sel"):
+            res[f] = rng.integers(-2 ** 31, 2 ** 31)
+        res["tid"], res["n_cand"], res["n_lin"] = rng.integers(0, 2 ** 32), nc, nl
+        res["score"], res["log_avg"], res["stdev"] = rng.integers(0, 2 ** 32, 3, dtype=np.uint64).astype(np.uint32).view(np.float32)
+        cands, lin = np.zeros(max(nc, 1), dtype=api.PAIR_DTYPE), np.zeros(max(nl, 1), dtype=api.PAIR_DTYPE)
+        cands["tid"], lin["tid"] = rng.integers(0, 2 ** 32, len(cands)), rng.integers(0, 2 ** 32, len(lin))
+        mode = it % 3
+        for arr in (cands, lin):
+            n = len(arr)
+            arr["score"] = (rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32).view(np.float32) if mode == 0
+                            else (rng.random(n) * 10).astype(np.float32) if mode == 1 else np.repeat(np.float32(rng.random()), n))
+        full = 160 + 40 * max(nc, nl)
+        cap = int(rng.choice([0, 1, 50, 159, 160, 161, 200, full, full - 1, 100000]))
+        buf = np.full(cap + 64, 0xA5, dtype=np.uint8)
+        n = L.kmat_format_tail(res.ctypes.data, cands.ctypes.data, lin.ctypes.data, int(rng.integers(0, 2)), C.cast(buf.ctypes.data, C.c_char_p), cap)
+        assert n <= cap
+        assert np.all(buf[cap:] == 0xA5), (it, cap, n)
