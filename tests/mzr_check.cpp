@@ -217,7 +217,7 @@ int main(int argc, char **argv) {
     //     arrays stand for the 32 lanes, index arithmetic for the shuffles; chunks of 32 bases as in the probe kernel
     {
         uint64_t n_checked = 0;
-        for (int m2 : {14, 15}) {
+        for (int m2 : {13, 14, 15, 16}) {                                     // w = 8, 7, 6, 5
             const int k2 = 20, w = k2 - m2 + 1, last_shift = w - 4;
             for (int style = 0; style < 3; style++)
                 for (int rep = 0; rep < 60; rep++) {
