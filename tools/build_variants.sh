@@ -2,6 +2,7 @@
 # Builds the compile-time experiment variants of libkmat HERE (nvcc cross-compiles without a GPU) into
 # lmat_b200/variants/libkmat_<name>.so, so that the GPU box spends no time compiling: tools/gpu_k4_packed.sh picks them up
 # through KMAT_LIB (lmat_b200/api.py).  *.so is git-ignored but travels with gpurun.  Usage: tools/build_variants.sh
+# Remove lmat_b200/variants/ again once the experiments are read (30 MB per variant in every gpurun snapshot).
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 V=$ROOT/lmat_b200/variants; mkdir -p $V/obj
