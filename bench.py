@@ -44,7 +44,9 @@ def parse_args():
     ap.add_argument("--genome-len", type=int, default=500000)
     ap.add_argument("--reads", type=int, default=10_000_000)
     ap.add_argument("--read-len", type=int, default=150)
-    ap.add_argument("--cpu-genomes", type=int, default=24, help="genomes in the CPU-baseline sub-table")
+    ap.add_argument("--cpu-genomes", type=int, default=256,
+                    help="genomes in the CPU-baseline sub-table (256 -> 1.2e8 k-mers, a 2 GB reference DB: far outside the host's L3)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed bench-scale parity leg (GPU binary vs the unmodified reference)")
     ap.add_argument("--cpu-reads", type=int, default=200_000, help="reads in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -118,18 +120,36 @@ def measured_peaks():
 # -------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the unmodified reference read_label on a bounded sample
 # -------------------------------------------------------------------------------------------------
+def _sample_cache_dir(a):
+    """The CPU sample (reference DB, reads, taxonomy files) is built once per box and shared by the two arms the driver
+    runs back to back (`--impl reference`, then the kmat arm): /dev/shm/kmat_cpu_sample_<key>."""
+    key = f"g{a.genomes}_l{a.genome_len}_cg{a.cpu_genomes}_cr{a.cpu_reads}_rl{a.read_len}"
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    return os.path.join(base, "kmat_cpu_sample_" + key)
+
+
 def build_cpu_sample(a, workdir, device):
     """Sub-table of the first `cpu_genomes` genomes written as a tax_histo file and built into a reference DB by
-    oracle/_ref/make_db_table; reads drawn from those genomes with the workload's read model."""
+    oracle/_ref/make_db_table; reads drawn from those genomes with the workload's read model.  Cached (see above)."""
     import numpy as np
     import torch
     from lmat_b200 import fixtures as fx
     from lmat_b200 import synth
     from oracle import refchain as rc
+    cdir = _sample_cache_dir(a)
+    meta_p = os.path.join(cdir, "meta.json")
+    if os.path.exists(meta_p):
+        meta = json.load(open(meta_p))
+        if all(os.path.exists(p) for p in [meta["db"] or meta_p, meta["fasta"]] + list(meta["paths"].values())):
+            meta["cached"] = True
+            return meta
+    shutil.rmtree(cdir, ignore_errors=True)
+    os.makedirs(cdir, exist_ok=True)
+    t0 = time.time()
     G = min(a.cpu_genomes, a.genomes)
     tax, m16, anc_tid, anc_sid = synth.make_taxonomy_c2(20240, a.genomes)
-    paths = fx.write_taxonomy_files(tax, workdir)
-    null_lst = synth.write_null_models_for(tax, workdir)
+    paths = fx.write_taxonomy_files(tax, cdir)
+    null_lst = synth.write_null_models_for(tax, cdir)
     dev = device
     codes = synth.make_genomes_gpu(20240, tax, a.genomes, a.genome_len, dev)[:G].contiguous() if dev != "cpu" else \
         synth.make_genomes_gpu(20240, tax, G, a.genome_len, dev)
@@ -137,24 +157,32 @@ def build_cpu_sample(a, workdir, device):
     sid2tid = np.zeros(65536, dtype=np.uint32)
     for t, s in m16.items():
         sid2tid[s] = t
-    kmers, offs, tids, _ = synth.table_to_host(tbl, sid2tid)
-    th = os.path.join(workdir, "cpu_sample.th.bin")
-    synth.write_tax_histo_fast(th, 20, kmers, offs, tids)
-    size_gib = int(2 + (len(kmers) * 8 + len(tids) * 8) / (1 << 30) * 1.3) + 1
+    kmers, offs, tids = synth.table_logical(tbl, sid2tid)
+    n_kmers, n_tids = int(kmers.numel()), int(tids.numel())
+    th = os.path.join(cdir, "cpu_sample.th.bin")
+    synth.write_tax_histo_torch(th, 20, kmers, offs, tids)
+    del kmers, offs, tids, tbl
+    size_gib = int(2 + (n_kmers * 8 + n_tids * 8) / (1 << 30) * 1.3) + 1
     db = None
     kind = "port"
     if rc.have_ref("make_db_table") and rc.have_ref("read_label"):
-        db = rc.make_db_table([th], os.path.join(workdir, "cpu_sample.db"), 20, size_gib, workdir, map16=paths["map16"])
+        db = rc.make_db_table([th], os.path.join(cdir, "cpu_sample.db"), 20, size_gib, cdir, map16=paths["map16"])
         kind = "reference"
+        os.unlink(th)
     reads = synth.make_reads_gpu(20241, codes, a.cpu_reads, a.read_len).cpu().numpy()
-    fa = os.path.join(workdir, "cpu_sample.fa")
+    fa = os.path.join(cdir, "cpu_sample.fa")
+    hdr = np.char.add(np.char.add(">r", np.arange(reads.shape[0]).astype(str)), "\n").astype("S")
     with open(fa, "wb") as f:
         for i in range(reads.shape[0]):
-            f.write(b">r%d\n" % i)
+            f.write(hdr[i])
             f.write(reads[i].tobytes())
             f.write(b"\n")
-    return dict(db=db, kind=kind, paths=paths, null_lst=null_lst, fasta=fa, n_reads=int(reads.shape[0]), n_kmers=int(len(kmers)),
-                table=(kmers, offs, tids), reads=reads, genomes=G)
+    meta = dict(db=db, kind=kind, paths=paths, null_lst=null_lst, fasta=fa, n_reads=int(reads.shape[0]), n_kmers=n_kmers, genomes=G,
+                th=None if db else th, dir=cdir, build_s=round(time.time() - t0, 1), cached=False)
+    with open(meta_p + ".tmp", "w") as f:
+        json.dump(meta, f)
+    os.replace(meta_p + ".tmp", meta_p)
+    return meta
 
 
 def run_cpu_sample(sample, workdir, threads):
@@ -164,31 +192,87 @@ def run_cpu_sample(sample, workdir, threads):
         P = sample["paths"]
         t0 = time.time()
         out, qt = rc.read_label(sample["db"], sample["fasta"], os.path.join(workdir, "cpu_rl_"), P["depth"], P["tree"], threads=threads,
-                                map16=P["map16"], rank=P["rank"], names=P["names"], null_lst=sample["null_lst"], lmat_dir=workdir,
+                                map16=P["map16"], rank=P["rank"], names=P["names"], null_lst=sample["null_lst"], lmat_dir=sample["dir"],
                                 min_kmer=30, hbias=0, sdiff=1.0, prn_all=True)
         wall = time.time() - t0
         return sample["n_reads"] / qt, wall
-    # port: the plain-C oracle restatement, single thread
+    # port (only where the reference binaries are missing): the plain-C oracle restatement, single thread
     import numpy as np
+    from lmat_b200 import api
     from oracle import oracle_py as op
-    kmers, offs, tids = sample["table"]
-    from lmat_b200 import fixtures as fx
-    m16 = {}
-    for ln in open(sample["paths"]["map16"]):
-        t, s = ln.split()
-        m16[int(t)] = int(s)
-    ids = np.array([m16[int(t)] for t in tids], dtype=np.uint32)
+    t = api.Table.build([sample["th"]], kmer_len=20, map16=sample["paths"]["map16"])
+    kmers, offs, ids = t.arrays()
     sd = op.SortedDbArrays(kmers, offs, ids)
     orc = op.Oracle(cdb=sd.cdb(), keep=sd)
     P = sample["paths"]
     orc.set_opts(min_kmer=30, hbias=0.0, sdiff=1.0, prn_all=1)
-    orc.load_files(tree=P["tree"], depth=P["depth"], rank=P["rank"], map16=P["map16"], null_lst=sample["null_lst"], lmat_dir=workdir)
-    n = min(sample["n_reads"], 20000)
-    seqs = [sample["reads"][i].tobytes() for i in range(n)]
+    orc.load_files(tree=P["tree"], depth=P["depth"], rank=P["rank"], map16=P["map16"], null_lst=sample["null_lst"], lmat_dir=sample["dir"])
+    hdrs, seqs = op.read_fasta_like_reference(sample["fasta"])
+    seqs = seqs[:20000]
     t0 = time.time()
     orc.label(seqs)
     dt = time.time() - t0
-    return n / dt, dt
+    return len(seqs) / dt, dt
+
+
+_REC_SPLIT = None
+
+
+def out_records(ofbase, n_files):
+    """The per-read records of <ofbase><t>.out as a sorted list.  A silent NoMatch prints `hdr\tread\t` with no newline
+    (read_label.cpp:727-733, 1248-1253), so the next record of the same thread runs on in the same line: which records run
+    together depends on the thread partition, not on the labels -- lines are cut in front of every `r<N>\t<bases>\t`."""
+    import re
+    global _REC_SPLIT
+    if _REC_SPLIT is None:
+        _REC_SPLIT = re.compile(r"(?<=\t)(?=r[0-9]+\t[A-Za-z]+\t)")
+    recs = []
+    for t in range(n_files):
+        p = f"{ofbase}{t}.out"
+        if os.path.exists(p):
+            for ln in open(p, encoding="latin-1").read().split("\n"):
+                if ln:
+                    recs.extend(x for x in _REC_SPLIT.split(ln) if x)
+    recs.sort()
+    return recs
+
+
+def parity_at_scale(sample, workdir, threads):
+    """GPU labels vs the UNMODIFIED reference at bench scale: the drop-in binary (lmat_b200/bin/read_label -> libkmat) and the
+    reference read_label run on the same DB file, the same reads file and the same flags (bin/run_rl.sh:243); their per-read
+    records are compared as sorted multisets (the reference's own -t 1 vs -t N runs agree only in that sense)."""
+    from lmat_b200 import build
+    if sample["kind"] != "reference":
+        return {"reads": 0, "lines_equal": None, "note": "reference binaries not available"}
+    exe = build.BIN
+    P = sample["paths"]
+    ref_base = os.path.join(workdir, "cpu_rl_")
+    if not os.path.exists(ref_base + "0.out"):
+        run_cpu_sample(sample, workdir, threads)
+    ofb = os.path.join(workdir, "gpu_rl_")
+    n_out = 4
+    cmd = [exe, "-f", P["map16"], "-u", P["names"], "-w", P["rank"], "-x", "0", "-j", "30", "-l", "0", "-b", "1.0", "-n", sample["null_lst"],
+           "-e", P["depth"], "-p", "-t", str(n_out), "-i", sample["fasta"], "-d", sample["db"], "-c", P["tree"], "-o", ofb]
+    env = dict(os.environ)
+    env["LMAT_DIR"] = sample["dir"]
+    env.setdefault("KMAT_DEVICES", os.environ.get("LOCAL_RANK", "0"))
+    t0 = time.time()
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+    if p.returncode != 0:
+        return {"reads": sample["n_reads"], "lines_equal": False, "note": ("read_label (kmat) rc=%d: " % p.returncode + p.stderr[-300:])}
+    ref = out_records(ref_base, threads)
+    got = out_records(ofb, n_out)
+    n_diff = 0
+    first = None
+    if ref != got:
+        import collections
+        cr, cg = collections.Counter(ref), collections.Counter(got)
+        d = (cr - cg) + (cg - cr)
+        n_diff = sum(d.values())
+        first = next(iter(d))[:200]
+    return {"reads": sample["n_reads"], "records_ref": len(ref), "records_kmat": len(got), "lines_equal": ref == got, "n_diff": n_diff,
+            "first_diff": first, "db_kmers": sample["n_kmers"], "wall_s": round(time.time() - t0, 1),
+            "how": "lmat_b200/bin/read_label vs oracle/_ref/read_label: same DB file, reads file and flags; .out records as sorted multisets"}
 
 
 def sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, setup_s, launches0, tstream, ctx2=None):
@@ -512,7 +596,7 @@ def main():
                                            f"GPU's memory (CUDA IPC peer mapping, NVLink reads); reads stay home, no exchange rounds, no collective")
                            if direct_mode else f"read-sharded x{world}, table replicated, no data-path collective"},
                 "kmer_lookups_per_s": value * lookups_per_read, "lookups_per_read": lookups_per_read,
-                "hit_rate": st.hits / max(1, st.lookups), "reads_error": int(errs), "labels_checksum_rank0": labels_checksum,
+                "hit_rate": st.hits / max(1, st.lookups), "extra_buckets_per_lookup": st.probe_extra_buckets / max(1, st.lookups), "reads_error": int(errs), "labels_checksum_rank0": labels_checksum,
                 "kernels_ms": {"encode_probe": pm, "candidates": cm_, "score": sm_, "how": "CUDA events around each kernel of one serial pass"},
                 "pipeline_sub_batches": a.pipeline,
                 "roofline": {"bound": "hbm", "kernel": "km_encode_probe_fast_kernel<5>" if L <= 160 else ("km_encode_probe_fast_kernel<8>" if L <= 256 else "km_encode_probe_kernel"), "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
@@ -531,8 +615,12 @@ def main():
                     line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": sample["kind"],
                                             "sample": f"{sample['n_reads']} reads vs a {sample['n_kmers']}-k-mer sub-table (first {sample['genomes']} genomes); "
                                                       f"read_label -t {cores} 'Total query time'; wall {w:.1f} s"}
+                    if not a.no_parity:
+                        line["parity_at_scale"] = parity_at_scale(sample, workdir, threads)
                 except Exception as ex:          # the baseline must never take the GPU number down with it
-                    line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)[:200]}
+                    line.setdefault("cpu_baseline", {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)[:200]})
+                    if not a.no_parity:
+                        line.setdefault("parity_at_scale", {"reads": 0, "lines_equal": None, "note": repr(ex)[:200]})
             print(json.dumps(line), flush=True)
         if world > 1:
             dist.barrier()          # direct mode: peers read this rank's table until they are done

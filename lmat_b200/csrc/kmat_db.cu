@@ -900,14 +900,21 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
 template <int NCH, int SETN, bool STATS, bool PEERS>
 static int km_launch_fast(const KmProbeParams &P, int ctas_per_sm, cudaStream_t stream) {
     const int smem = KM_PROBE_WARPS * (SETN / 8);
-    static int resident = 0, sms = 148;    // per instantiation: CTAs that fit the device at once (persistent grid)
+    // per instantiation AND per device (function attributes belong to a device's context; a process may drive several
+    // GPUs, one thread each): CTAs that fit the device at once (persistent grid)
+    static std::atomic<int> resident_of[KM_MAX_DEVICES], sms_of[KM_MAX_DEVICES];
+    int dev = 0;
+    KM_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= KM_MAX_DEVICES) { kmat_set_error("device index %d out of range", dev); return KMAT_ERR_ARG; }
+    int resident = resident_of[dev].load(), sms = sms_of[dev].load();
     if (!resident) {
         KM_CUDA(cudaFuncSetAttribute(km_encode_probe_fast_kernel<NCH, SETN, STATS, PEERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int per_sm = 0, dev = 0;
+        int per_sm = 0;
         KM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_encode_probe_fast_kernel<NCH, SETN, STATS, PEERS>, KM_PROBE_WARPS * 32, smem));
-        cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        KM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         if (const char *e = getenv("KMAT_PROBE_CTAS")) { const int v = atoi(e); if (v > 0 && v < per_sm) per_sm = v; }
         resident = std::max(1, per_sm) * sms;
+        sms_of[dev].store(sms); resident_of[dev].store(resident);       // racing threads compute the same values
     }
     const uint32_t want = (P.n_reads + KM_PROBE_WARPS - 1) / KM_PROBE_WARPS;
     const uint32_t cap = ctas_per_sm > 0 ? std::min<uint32_t>((uint32_t)resident, (uint32_t)(ctas_per_sm * sms)) : (uint32_t)resident;
@@ -936,8 +943,8 @@ int km_launch_encode_probe(const kmat_db *db, const char *d_bases, const uint64_
         // takes the rest
         const bool use_long = !d_kmers && !d_flags && !d_xq && max_len >= KM_LONG_MIN && db->geom.kmer_bits + KM_LONG_POS_BITS <= 64 && db->kmer_len <= 32 && !getenv("KMAT_NO_LONG_PROBE");
         if (use_long) {
-            static bool attr_set = false;
-            if (!attr_set) { KM_CUDA(cudaFuncSetAttribute(km_encode_probe_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KM_LONG_SLOTS * 8)); attr_set = true; }
+            // per launch: the attribute belongs to the current device's context (several GPUs per process), and setting it is cheap
+            KM_CUDA(cudaFuncSetAttribute(km_encode_probe_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KM_LONG_SLOTS * 8));
             P.skip_mid = 1;
             km_encode_probe_long_kernel<<<(int)std::max<uint32_t>(1, std::min<uint32_t>(n_reads, 148u)), KM_LONG_THREADS, KM_LONG_SLOTS * 8, stream>>>(P);
             g_km_launches++;

@@ -198,8 +198,7 @@ extern "C" int kmat_gene_batch(const kmat_db *db, const char *bases, const uint6
     if (cudaMalloc((void **)&d_bigq, (size_t)bigq_cap * 4) != cudaSuccess || cudaMalloc((void **)&d_bigcnt, 4) != cudaSuccess) {
         cudaFree(d_bigq); cudaGetLastError(); kmat_set_error("kmat_gene_batch: out of device memory"); return KMAT_ERR_NOMEM;
     }
-    static bool big_attr = false;
-    if (!big_attr) { KM_CUDA(cudaFuncSetAttribute(km_gene_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * sizeof(KgBigW)))); big_attr = true; }
+    KM_CUDA(cudaFuncSetAttribute(km_gene_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * sizeof(KgBigW))));   // per call: the attribute is per device
     auto cleanup = [&] { cudaFree(d_b); cudaFree(d_o); cudaFree(d_hit); cudaFree(d_hdr); cudaFree(d_out); cudaFree(d_long); cudaFree(d_bigq); cudaFree(d_bigcnt); };
     for (uint32_t r0 = 0; r0 < n_reads && rc == KMAT_OK;) {
         uint32_t r1 = (uint32_t)std::min<uint64_t>(n_reads, (uint64_t)r0 + chunk_reads);

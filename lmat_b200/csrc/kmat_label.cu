@@ -628,27 +628,14 @@ struct KsLocalT {
 };
 typedef KsLocalT<KB_CMAX, KB_LIN, uint8_t> KsLocal;          // per-thread local arrays of the regular kernel
 typedef KsLocalT<KB_CBIG, KB_LBIG, uint16_t> KsLocalBig;     // global scratch slot of the big kernel
-// Experiment for the next GPU session (off by default, -DKMAT_K4_PACKED_DEPTH=1): the sorted element carries the depth in
-// the upper half of idx, so TCmp stops loading depth[a.idx] / depth[b.idx] from local memory twice per comparison (12.5 % of
-// the scoring kernel's stall samples sit on that line, profiles/r01r_hot_lines_k3_k4.txt).  Candidate indices are < 512.
-#ifndef KMAT_K4_PACKED_DEPTH
-#define KMAT_K4_PACKED_DEPTH 0
-#endif
-#if KMAT_K4_PACKED_DEPTH
+// The sorted rank_label element carries the candidate's depth in the upper half of idx, so TCmp does not load depth[a.idx] /
+// depth[b.idx] from local memory twice per comparison (12.5 % of the scoring kernel's stall samples sat on that line,
+// profiles/r01r_hot_lines_k3_k4.txt).  Candidate indices are < 512, depths fit 16 bits.
 #define KS_RL_IDX(v) ((v) & 0xFFFFu)
 #define KS_RL_PACK(f, depth) ((uint32_t)(f) | ((uint32_t)(depth) << 16))
-#else
-#define KS_RL_IDX(v) (v)
-#define KS_RL_PACK(f, depth) ((uint32_t)(f))
-#endif
 struct KsTCmp {           // TCmp, read_label.cpp:475-485: |a-b| < 0.001 (double compare) -> shallower first, else by score
-    const uint16_t *depth;
     __device__ bool operator()(const KmRl &a, const KmRl &b) const {
-#if KMAT_K4_PACKED_DEPTH
         if ((double)fabsf(__fsub_rn(a.score, b.score)) < 0.001) return (int)(a.idx >> 16) < (int)(b.idx >> 16);
-#else
-        if ((double)fabsf(__fsub_rn(a.score, b.score)) < 0.001) return (int)depth[a.idx] < (int)depth[b.idx];
-#endif
         return a.score < b.score;
     }
 };
@@ -740,7 +727,7 @@ __device__ __forceinline__ void ks_score_one(const KmScoreParams &P, const uint3
         if (hasHuman && (T.flags[f] & 1)) sc = __fadd_rn(sc, __fmul_rn(X.opt.hbias, stdev1));
         T.rl[f].score = sc; T.rl[f].idx = KS_RL_PACK(f, T.depth[f]);
     }
-    kmstd::sort(T.rl, C, KsTCmp{T.depth});
+    kmstd::sort(T.rl, C, KsTCmp());
     const float diff_thresh = __fmul_rn(stdev1, X.opt.sdiff);                  // :895
     // ---- findReadLabelVer2 (:284-419)
     int nlin = 0;
@@ -861,17 +848,13 @@ __device__ __forceinline__ void ks_score_one(const KmScoreParams &P, const uint3
     P.out[r] = res;
 }
 
-// Experiment for the next GPU session (off by default, -DKMAT_K4_BLOCK_SORT=1): a CTA takes KS_THREADS * KS_SORT_ROUNDS queue
-// entries, counting-sorts them by candidate count in shared memory and scores them in that order, so the 32 reads of a warp
-// have similar loop lengths (the insertion sort of rank_label and the ancestor scans run with 7-16 of 32 lanes active today,
-// profiles/r01r_hot_lines_k3_k4.txt).  Results do not depend on which thread scores a read.
-#ifndef KMAT_K4_BLOCK_SORT
-#define KMAT_K4_BLOCK_SORT 0
-#endif
+// A CTA takes KS_THREADS * KS_SORT_ROUNDS entries of the pending queue, counting-sorts them by candidate count in shared memory
+// and scores them in that order, so the 32 reads of a warp have similar loop lengths (the insertion sort of rank_label and
+// the ancestor scans ran with 7-16 of 32 lanes active before: 13.9 -> 9.4 ms per 10 M reads, profiles/r02a_variants.txt).
+// Results do not depend on which thread scores a read.
 #ifndef KS_SORT_ROUNDS
 #define KS_SORT_ROUNDS 4
 #endif
-#if KMAT_K4_BLOCK_SORT
 #define KS_READS_PER_CTA (KS_THREADS * KS_SORT_ROUNDS)
 __global__ void __launch_bounds__(KS_THREADS) km_score_kernel(KmScoreParams P) {
     __shared__ uint32_t s_bin[KB_CMAX + 2];
@@ -908,18 +891,6 @@ __global__ void __launch_bounds__(KS_THREADS) km_score_kernel(KmScoreParams P) {
     KsLocal T;
     for (uint32_t i = threadIdx.x; i < total; i += KS_THREADS) ks_score_one<KB_LIN, uint8_t, false>(P, s_r[i], T);
 }
-#else
-#define KS_READS_PER_CTA KS_THREADS
-__global__ void __launch_bounds__(KS_THREADS) km_score_kernel(KmScoreParams P) {
-    uint32_t r = blockIdx.x * KS_THREADS + threadIdx.x;
-    if (P.pend_q) {                                 // dense queue of the reads K3 left PENDING: no lane idles on a read without candidates
-        if (r >= (uint32_t)(*P.pass_cursor >> KB_PASS_SHIFT)) return;
-        r = P.pend_q[r];
-    } else if (r >= P.n_reads) return;
-    KsLocal T;
-    ks_score_one<KB_LIN, uint8_t, false>(P, r, T);
-}
-#endif
 // The reads of big_qb (more than KB_CMAX candidates, or a lineage the regular kernel could not hold): same code, working
 // arrays in a global scratch slot per thread.
 __global__ void __launch_bounds__(32) km_score_big_kernel(KmScoreParams P) {
@@ -1475,8 +1446,8 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
     if (np_need > c->big_np_cap) {
         const size_t per = ((size_t)np_need + KB_CBIG) * KB_BIGW * 8;                       // one warp's position sets + lineage sets
         uint32_t threads = (uint32_t)std::min<size_t>((size_t)c->sms * KBG_WARPS * 2, std::max<size_t>(1, ((size_t)1 << 30) / per));
-        static bool attr_set = false;
-        if (!attr_set) { KM_CUDA(cudaFuncSetAttribute(km_cand_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KBG_WARPS * sizeof(KbBigW)))); attr_set = true; }
+        // per launch: function attributes belong to the current device's context (read_label drives every visible GPU from one process)
+        KM_CUDA(cudaFuncSetAttribute(km_cand_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KBG_WARPS * sizeof(KbBigW))));
         KM_CUDA(cudaStreamSynchronize(s2));
         int rc3 = km_grow(&c->d_big3, &c->cap_big3, (uint64_t)per * threads);
         if (rc3 != KMAT_OK) return rc3;
@@ -1508,13 +1479,7 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
         KM_CUDA(cudaGetLastError());
         return KMAT_OK;
     }
-    // KMAT_SCORE_SMEM (experiment knob): dummy dynamic shared memory per CTA, to cap the resident CTAs of the scoring
-    // kernel -- its per-thread local arrays then fit the L1 instead of spilling through L2 to DRAM
-    static const int score_smem = [] {
-        const char *e = getenv("KMAT_SCORE_SMEM"); const int v = e ? atoi(e) : 0;
-        if (v > 48 * 1024) cudaFuncSetAttribute(km_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
-        return v > 0 ? v : 0; }();
-    km_score_kernel<<<(n + KS_READS_PER_CTA - 1) / KS_READS_PER_CTA, KS_THREADS, score_smem, s2>>>(P);
+    km_score_kernel<<<(n + KS_READS_PER_CTA - 1) / KS_READS_PER_CTA, KS_THREADS, 0, s2>>>(P);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     km_score_big_kernel<<<c->big_threads4 / 32, 32, 0, s2>>>(P);

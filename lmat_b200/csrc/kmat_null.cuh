@@ -64,8 +64,7 @@ __global__ void __launch_bounds__(KN_GEN_THREADS) km_randgen_kernel(uint64_t see
 static int km_launch_randgen(uint64_t seed, uint64_t first_index, uint32_t n_reads, uint32_t read_len, char *d_bases, uint64_t *d_offs, cudaStream_t st) {
     if (read_len == 0 || read_len > KN_GEN_SMEM) { kmat_set_error("kmat_null: read_len %u out of range (1..%d)", read_len, KN_GEN_SMEM); return KMAT_ERR_ARG; }
     const uint32_t rpb = std::max(1u, std::min<uint32_t>(KN_GEN_THREADS, KN_GEN_SMEM / read_len));
-    static bool attr_set = false;
-    if (!attr_set) { KM_CUDA(cudaFuncSetAttribute(km_randgen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KN_GEN_SMEM)); attr_set = true; }
+    KM_CUDA(cudaFuncSetAttribute(km_randgen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KN_GEN_SMEM));   // per launch: the attribute is per device
     km_randgen_kernel<<<(n_reads + rpb - 1) / rpb, KN_GEN_THREADS, (size_t)rpb * read_len, st>>>(seed, first_index, n_reads, read_len, rpb, d_bases, d_offs);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());

@@ -20,6 +20,7 @@
     } while (0)
 
 extern std::atomic<unsigned long long> g_km_launches;
+#define KM_MAX_DEVICES 64     // per-device caches of launch geometry (function attributes are per device)
 
 struct kmat_db {
     int device = 0, kmer_len = 0, tid_bytes = 2;

@@ -209,6 +209,64 @@ def table_to_host(tbl, sid_to_tid):
     return kmers, offs.cpu().numpy().astype(np.uint64), sid2tid[ids.cpu().numpy()], ids.cpu().numpy().astype(np.uint32)
 
 
+def table_logical(tbl, sid_to_tid):
+    """The logical table as torch tensors on the table's device: (kmers int64 ascending, offs int64 [n + 1], tids int64 in
+    list order, taxids not stored ids).  Same content as table_to_host without the host copies."""
+    dev = tbl.kmers.device
+    n = tbl.n
+    lens = torch.ones(n, dtype=torch.int64, device=dev)
+    if tbl.lists is not None:
+        lens[tbl.lists["multi_idx"]] = tbl.lists["ln"]
+    offs = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    offs[1:] = torch.cumsum(lens, 0)
+    ids = torch.zeros(int(offs[-1].item()), dtype=torch.int64, device=dev)
+    ids[offs[:-1][tbl.single]] = tbl.payload_i64[tbl.single]
+    if tbl.lists is not None:
+        li = tbl.lists
+        seg_of = torch.repeat_interleave(torch.arange(li["ln"].numel(), device=dev), li["ln"])
+        rank = torch.arange(li["lsid"].numel(), device=dev) - li["lstart"][seg_of]
+        ids[offs[:-1][li["multi_idx"]][seg_of] + rank] = li["lsid"]
+    s2t = torch.as_tensor(np.asarray(sid_to_tid, dtype=np.int64), device=dev)
+    return tbl.kmers, offs, s2t[ids]
+
+
+def write_tax_histo_torch(path, k, kmers, offs, tids, chunk=1 << 23):
+    """tax_histo binary (the format fixtures.write_tax_histo documents) from torch tensors on any device, assembled in
+    chunks of `chunk` records on that device: [kmer u64][count u16][count x tid u32], eight 0xFF bytes after every 1500th
+    record (the reader's sanity marker)."""
+    import struct
+    dev = kmers.device
+    n = int(kmers.numel())
+    ar8 = torch.arange(8, device=dev)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<IQQIcI", 29, n, 0xFFFFFFFFFFFFFFFF, 999, b"N", k))
+        for a in range(0, n, chunk):
+            b = min(n, a + chunk)
+            m = b - a
+            o = offs[a:b + 1] - offs[a]
+            lens = o[1:] - o[:-1]
+            idx = torch.arange(a, b, device=dev)
+            sanity = ((idx + 1) % 1500 == 0).to(torch.int64) * 8
+            sizes = 10 + 4 * lens + sanity
+            pos = torch.cumsum(sizes, 0) - sizes
+            buf = torch.zeros(int(sizes.sum().item()), dtype=torch.uint8, device=dev)
+            kb = kmers[a:b].contiguous().view(torch.uint8).reshape(m, 8)                   # little endian host and device
+            buf[(pos[:, None] + ar8[None, :]).reshape(-1)] = kb.reshape(-1)
+            cb = lens.to(torch.int16).contiguous().view(torch.uint8).reshape(m, 2)
+            buf[(pos[:, None] + 8 + ar8[None, :2]).reshape(-1)] = cb.reshape(-1)
+            t = tids[int(offs[a].item()):int(offs[b].item())]
+            rec = torch.repeat_interleave(torch.arange(m, device=dev), lens)
+            rank = torch.arange(t.numel(), device=dev) - o[:-1][rec]
+            tb = t.to(torch.int32).contiguous().view(torch.uint8).reshape(-1, 4)
+            buf[((pos[rec] + 10 + 4 * rank)[:, None] + ar8[None, :4]).reshape(-1)] = tb.reshape(-1)
+            sp = torch.nonzero(sanity).squeeze(1)
+            if sp.numel():
+                spos = pos[sp] + 10 + 4 * lens[sp]
+                buf[(spos[:, None] + ar8[None, :]).reshape(-1)] = 0xFF
+            f.write(buf.cpu().numpy().tobytes())
+            del buf
+
+
 def make_reads_gpu(seed, codes, n_reads, read_len=150, novel_frac=0.10, err_lo=0.001, err_hi=0.02, n_rate=0.0005,
                    chunk=1 << 20, genomes=None):
     """ASCII reads [n_reads, read_len] uint8 on the device (SURVEY.md 8(d) read model: 90 % from genomes, 10 %
