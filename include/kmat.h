@@ -104,6 +104,7 @@ int kmat_db_build_device(int device, int kmer_length, int tid_bytes, uint64_t n_
 uint32_t kmat_shard_of(uint64_t kmer, int kmer_length, int shard_count);
 uint64_t kmat_db_size(const kmat_db *);
 uint64_t kmat_db_bytes(const kmat_db *);             /* device bytes held */
+uint64_t kmat_db_overflow(const kmat_db *);          /* k-mers of a two-level table that live in its second level */
 int kmat_db_kmer_length(const kmat_db *);
 int kmat_db_device(const kmat_db *);
 void kmat_db_free(kmat_db *);

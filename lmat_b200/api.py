@@ -45,7 +45,7 @@ EXPORTS = [
     "kmat_strerror", "kmat_last_error", "kmat_abi_version", "kmat_device_count", "kmat_device_memory", "kmat_table_from_sorteddb",
     "kmat_table_from_arrays", "kmat_table_open", "kmat_table_save", "kmat_table_size", "kmat_table_kmer_length",
     "kmat_table_tid_bytes", "kmat_table_build", "kmat_build_opts_default", "kmat_table_view", "kmat_table_free", "kmat_db_upload", "kmat_db_build_device",
-    "kmat_shard_of", "kmat_db_size", "kmat_db_bytes", "kmat_db_kmer_length", "kmat_db_device", "kmat_db_free",
+    "kmat_shard_of", "kmat_db_size", "kmat_db_bytes", "kmat_db_overflow", "kmat_db_kmer_length", "kmat_db_device", "kmat_db_free",
     "kmat_lookup_batch", "kmat_encode_batch", "kmat_inputs_load", "kmat_inputs_free", "kmat_opts_default",
     "kmat_ctx_create", "kmat_ctx_set_opts", "kmat_ctx_destroy", "kmat_label_batch", "kmat_label_batch_device",
     "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_set_pipeline", "kmat_gene_batch", "kmat_shard_encode", "kmat_shard_serve", "kmat_shard_finish", "kmat_ctx_device_results", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench", "kmat_gather_bench_peer",
@@ -88,6 +88,8 @@ def lib():
     L.kmat_db_size.argtypes = [vp]
     L.kmat_db_bytes.restype = C.c_uint64
     L.kmat_db_bytes.argtypes = [vp]
+    L.kmat_db_overflow.restype = C.c_uint64
+    L.kmat_db_overflow.argtypes = [vp]
     L.kmat_db_kmer_length.argtypes = [vp]
     L.kmat_db_device.argtypes = [vp]
     L.kmat_db_free.argtypes = [vp]
@@ -265,6 +267,11 @@ class Db:
     @property
     def bytes(self):
         return lib().kmat_db_bytes(self.h)
+
+    @property
+    def overflow(self):
+        """k-mers of a two-level table that live in its second level (their first-level sector was full)"""
+        return lib().kmat_db_overflow(self.h)
 
     @property
     def kmer_length(self):

@@ -36,16 +36,6 @@ extern "C" int kmat_device_memory(int device, uint64_t *free_bytes, uint64_t *to
 // geometry
 // ---------------------------------------------------------------------------------------------
 static int km_choose_bucket_bits(uint64_t n, int kmer_bits) {
-#if KMAT_LINE_TABLE
-    {   // <= 2 k-mers per 16-slot line on average; line bits within the geometry of kmat_mzr.h; 4 buckets per line
-        int bl = 4;
-        while (((uint64_t)2 << bl) < n) bl++;
-        if (getenv("KMAT_TEST_TIGHT_TABLE")) bl -= 2;
-        if (bl < kmer_bits + 4 - KM_REM_BITS) bl = kmer_bits + 4 - KM_REM_BITS;
-        if (bl > 2 * KM_LINE_M) bl = 2 * KM_LINE_M;
-        return bl + 2;
-    }
-#endif
     int b = 4;
     while (((uint64_t)1 << b) < n) b++;               // <= 1 key per 4-slot bucket on average: ~1.5 % of the home buckets are full
     if (getenv("KMAT_TEST_TIGHT_TABLE")) b = b > 6 ? b - 2 : 4;   // tests: a nearly full table exercises displacement, the stash and doubling
@@ -53,42 +43,46 @@ static int km_choose_bucket_bits(uint64_t n, int kmer_bits) {
     if (b > kmer_bits) b = kmer_bits;
     return b;
 }
+// First level: 2^b 128-byte lines for n k-mers (the GLOBAL count: every shard of a table uses the same b).  Default
+// density: at most 2 k-mers per 16-slot line on average (profiles/r02_line_table.md: ~4 % of the k-mers then overflow into
+// the second level); KMAT_LINE_DENSITY=<k-mers per line> trades memory against second-level probes.
+static int km_choose_line_bits(uint64_t n, int k, int m) {
+    if (!m || getenv("KMAT_NO_LINE_LEVEL")) return 0;
+    double dens = 2.0;
+    if (const char *e = getenv("KMAT_LINE_DENSITY")) { const double v = atof(e); if (v >= 0.25 && v <= 16.0) dens = v; }
+    int b = km_line_min_bits(k);
+    while (b < 2 * m && (double)((uint64_t)1 << b) * dens < (double)n) b++;
+    if (getenv("KMAT_TEST_TIGHT_TABLE")) b = std::max(km_line_min_bits(k), b - 3);       // tests: many overflowing sectors
+    return km_line_geometry_ok(k, m, b) ? b : 0;
+}
 
 extern "C" uint32_t kmat_shard_of(uint64_t kmer, int kmer_length, int shard_count) {
     if (shard_count <= 1) return 0;
+    const int m = getenv("KMAT_NO_LINE_LEVEL") ? 0 : km_line_m(kmer_length);
+    if (m) return km_line_owner_of_g(km_mzr_mix2(km_mzr_of(kmer, kmer_length, m).c, m), m, (uint32_t)shard_count);
     return km_owner_of_x(km_mix(kmer, 2 * kmer_length), (uint32_t)shard_count);
 }
 
 // ---------------------------------------------------------------------------------------------
 // build
 // ---------------------------------------------------------------------------------------------
-#if KMAT_LINE_TABLE
-#define KM_STASH_CAP (1u << 25)       // heavy minimizers overflow their four lines: ~0.1-1 % of the k-mers at <= 2 per line
-#else
 #define KM_STASH_CAP 65536u
-#endif
-__global__ void km_insert_kernel(const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ payload, uint64_t n,
+// second level (or the whole table when there is no first level).  `sel` (optional): indices into kmers / payload of the
+// k-mers to insert (those that overflowed their first-level sector), n = their number.
+__global__ void km_insert_kernel(const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ payload, const uint32_t *__restrict__ sel, uint64_t n,
                                  unsigned long long *slots, uint64_t bucket_mask, int kmer_bits, int rem_bits,
                                  unsigned int *stash_n, uint64_t *stash_x, uint32_t *stash_hit,
                                  uint32_t shard_index, uint32_t shard_count, unsigned long long *n_kept) {
     unsigned long long kept = 0;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t x = KM_KEY(kmers[i], kmer_bits, bucket_mask);
-        if (shard_count > 1 && km_owner_of_x(x, shard_count) != shard_index) continue;     // another shard's k-mer
+    for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i0 < n; i0 += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = sel ? sel[i0] : i0;
+        const uint64_t x = km_mix(kmers[i], kmer_bits);
+        if (!sel && shard_count > 1 && km_owner_of_x(x, shard_count) != shard_index) continue;     // another shard's k-mer
         kept++;
         const uint64_t home = x >> rem_bits, rem = x & ((1ull << rem_bits) - 1);
         const uint32_t pl = payload[i];
         const uint64_t base = (1ull << 63) | ((uint64_t)((pl >> 31) & 1) << 62) | (rem << 32) | (pl & 0x7FFFFFFFu);
         bool done = false;
-#if KMAT_LINE_TABLE
-        for (int t = 0; t < KM_LINE_STEPS && !done; t++) {           // home sector, rest of the line, then three more lines
-            unsigned long long *b = slots + km_line_bucket_at(home, t, bucket_mask) * KM_SLOTS_PER_BUCKET;
-            const unsigned long long v = base | ((uint64_t)(t >> 2) << 60);
-            for (int s = 0; s < KM_SLOTS_PER_BUCKET && !done; s++) {
-                if (b[s] == 0ull && atomicCAS(b + s, 0ull, v) == 0ull) done = true;
-            }
-        }
-#else
         for (int d = 0; d <= KM_MAX_DISP && !done; d++) {
             unsigned long long *b = slots + ((home + d) & bucket_mask) * KM_SLOTS_PER_BUCKET;
             const unsigned long long v = base | ((uint64_t)d << 60);
@@ -96,7 +90,6 @@ __global__ void km_insert_kernel(const uint64_t *__restrict__ kmers, const uint3
                 if (b[s] == 0ull && atomicCAS(b + s, 0ull, v) == 0ull) done = true;
             }
         }
-#endif
         if (!done) {                                   // KM_MAX_DISP + 1 full buckets: the key goes to the stash
             const unsigned int q = atomicAdd(stash_n, 1u);
             if (q < KM_STASH_CAP) { stash_x[q] = x; stash_hit[q] = pl; }
@@ -105,6 +98,40 @@ __global__ void km_insert_kernel(const uint64_t *__restrict__ kmers, const uint3
     kept = __reduce_add_sync(0xffffffffu, (unsigned)kept);      // < 2^32 per warp pass: grid-stride, 32 lanes
     if ((threadIdx.x & 31) == 0 && kept) atomicAdd(n_kept, kept);
 }
+// first level: every k-mer of this shard goes to its sector (kmat_mzr.h) if one of the four slots is free; the others are
+// listed in `ovf` for the second level
+__global__ void km_line_insert_kernel(const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ payload, uint64_t n,
+                                      unsigned long long *lines, uint64_t line_first, int k, int m, int line_bits,
+                                      uint32_t shard_index, uint32_t shard_count, unsigned long long *n_kept,
+                                      uint32_t *ovf, unsigned long long *n_ovf, uint64_t ovf_cap) {
+    unsigned long long kept = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t x = km_line_x(kmers[i], k, m, line_bits);
+        if (shard_count > 1 && km_line_owner_of_g(km_line_g_of_x(x, k, m, line_bits), m, shard_count) != shard_index) continue;
+        kept++;
+        const uint32_t pl = payload[i];
+        const unsigned long long v = (1ull << 63) | ((uint64_t)((pl >> 31) & 1) << 62) | ((x & ((1ull << KM_MZR_KEY_BITS) - 1)) << 32) | (pl & 0x7FFFFFFFu);
+        unsigned long long *b = lines + (((x >> KM_LINE_XSHIFT) - line_first) * 4 + ((x >> KM_MZR_KEY_BITS) & 3u)) * KM_SLOTS_PER_BUCKET;
+        bool done = false;
+        for (int s = 0; s < KM_SLOTS_PER_BUCKET && !done; s++)
+            if (b[s] == 0ull && atomicCAS(b + s, 0ull, v) == 0ull) done = true;
+        if (!done) {
+            const unsigned long long q = atomicAdd(n_ovf, 1ull);
+            if (q < ovf_cap) ovf[q] = (uint32_t)i;
+        }
+    }
+    kept = __reduce_add_sync(0xffffffffu, (unsigned)kept);
+    if ((threadIdx.x & 31) == 0 && kept) atomicAdd(n_kept, kept);
+}
+// after the insertion has finished: the sectors of the overflowed k-mers get their flag (slot 0 of a full sector is occupied)
+__global__ void km_line_flag_kernel(const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ ovf, uint64_t n_ovf,
+                                    unsigned long long *lines, uint64_t line_first, int k, int m, int line_bits) {
+    for (uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; q < n_ovf; q += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t x = km_line_x(kmers[ovf[q]], k, m, line_bits);
+        unsigned long long *b = lines + (((x >> KM_LINE_XSHIFT) - line_first) * 4 + ((x >> KM_MZR_KEY_BITS) & 3u)) * KM_SLOTS_PER_BUCKET;
+        if (!(b[0] & KM_LINE_OVF)) atomicOr(b, KM_LINE_OVF);
+    }
+}
 __global__ void km_prefix_bits_kernel(const uint64_t *__restrict__ kmers, uint64_t n, uint32_t *bits, int shift) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t p = kmers[i] >> shift;
@@ -112,46 +139,49 @@ __global__ void km_prefix_bits_kernel(const uint64_t *__restrict__ kmers, uint64
     }
 }
 
-static int km_db_alloc_and_insert(kmat_db *db, const uint64_t *d_kmers, const uint32_t *d_payload, uint64_t n, int shard_index, int shard_count) {
+// device temporaries of a table build: freed on every path out
+struct KmBuildTmp {
+    unsigned long long *d_cnt = nullptr;      // [0] k-mers kept, [1] first-level overflows
+    uint32_t *d_ovf = nullptr;
+    unsigned int *d_sn = nullptr; uint64_t *d_sx = nullptr; uint32_t *d_sh = nullptr;
+    ~KmBuildTmp() { cudaFree(d_cnt); cudaFree(d_ovf); cudaFree(d_sn); cudaFree(d_sx); cudaFree(d_sh); }
+};
+
+// second level over the k-mers `sel` (or all n when sel == NULL, filtered by shard): sized for `expect` keys, doubled while
+// the stash overflows
+static int km_build_buckets(kmat_db *db, const uint64_t *d_kmers, const uint32_t *d_payload, const uint32_t *d_sel, uint64_t n, uint64_t expect,
+                            int shard_index, int shard_count, KmBuildTmp &T, unsigned long long *kept_out) {
     const int kmer_bits = 2 * db->kmer_len;
-    unsigned long long *d_kept;
-    KM_CUDA(cudaMalloc((void **)&d_kept, 8));
-    unsigned long long kept = 0;
-    // a shard keeps ~n / shard_count of the k-mers (the owner hash is uniform); the table is sized for that plus 5 %
-    const uint64_t expect = shard_count > 1 ? n / shard_count + n / (20 * (uint64_t)shard_count) + 1024 : n;
+    if (!T.d_sn) {
+        KM_CUDA(cudaMalloc((void **)&T.d_sn, sizeof(unsigned int)));
+        KM_CUDA(cudaMalloc((void **)&T.d_sx, (size_t)KM_STASH_CAP * 8)); KM_CUDA(cudaMalloc((void **)&T.d_sh, (size_t)KM_STASH_CAP * 4));
+    }
     for (int b = km_choose_bucket_bits(expect, kmer_bits);; b++) {
         if (b > kmer_bits) { kmat_set_error("hash table build failed: displacement limit at maximum size"); return KMAT_ERR_UNSUPPORTED; }
-        db->geom.kmer_bits = kmer_bits; db->geom.bucket_bits = b; db->geom.rem_bits = kmer_bits - b;
-#if KMAT_LINE_TABLE
-        if (!km_line_ok(db->kmer_len, KM_LINE_M, b - 2) || shard_count > 1) { kmat_set_error("line-table experiment: k = %d with 2^%d lines (or a sharded table) is outside its geometry", db->kmer_len, b - 2); return KMAT_ERR_UNSUPPORTED; }
-        db->geom.rem_bits = KM_REM_BITS;
-#endif
+        db->geom.bucket_bits = b; db->geom.rem_bits = kmer_bits - b;
         db->n_buckets = 1ull << b;
         const size_t bytes = db->n_buckets * KM_SLOTS_PER_BUCKET * sizeof(uint64_t);
         KM_CUDA(cudaMalloc((void **)&db->d_slots, bytes));
         KM_CUDA(cudaMemset(db->d_slots, 0, bytes));
-        unsigned int *d_sn; uint64_t *d_sx; uint32_t *d_sh;
-        KM_CUDA(cudaMalloc((void **)&d_sn, sizeof(unsigned int)));
-        KM_CUDA(cudaMalloc((void **)&d_sx, (size_t)KM_STASH_CAP * 8)); KM_CUDA(cudaMalloc((void **)&d_sh, (size_t)KM_STASH_CAP * 4));
-        KM_CUDA(cudaMemset(d_sn, 0, sizeof(unsigned int)));
-        KM_CUDA(cudaMemset(d_kept, 0, 8));
+        KM_CUDA(cudaMemset(T.d_sn, 0, sizeof(unsigned int)));
+        KM_CUDA(cudaMemset(T.d_cnt, 0, 8));
         if (n) {
             const int threads = 256;
             const int blocks = (int)std::min<uint64_t>((n + threads - 1) / threads, 148ull * 16);
-            km_insert_kernel<<<blocks, threads>>>(d_kmers, d_payload, n, (unsigned long long *)db->d_slots, db->n_buckets - 1,
-                                                  kmer_bits, db->geom.rem_bits, d_sn, d_sx, d_sh, (uint32_t)shard_index, (uint32_t)shard_count, d_kept);
+            km_insert_kernel<<<blocks, threads>>>(d_kmers, d_payload, d_sel, n, (unsigned long long *)db->d_slots, db->n_buckets - 1,
+                                                  kmer_bits, db->geom.rem_bits, T.d_sn, T.d_sx, T.d_sh, (uint32_t)shard_index, (uint32_t)shard_count, T.d_cnt);
             g_km_launches++;
             KM_CUDA(cudaGetLastError());
         }
         unsigned int sn = 0;
-        KM_CUDA(cudaMemcpy(&sn, d_sn, sizeof sn, cudaMemcpyDeviceToHost));
-        KM_CUDA(cudaMemcpy(&kept, d_kept, 8, cudaMemcpyDeviceToHost));
+        KM_CUDA(cudaMemcpy(&sn, T.d_sn, sizeof sn, cudaMemcpyDeviceToHost));
+        KM_CUDA(cudaMemcpy(kept_out, T.d_cnt, 8, cudaMemcpyDeviceToHost));
         if (sn <= KM_STASH_CAP) {
-            // the stash: sorted by mixed key on the host (a few hundred entries at most), searched by km_probe_x
+            // the stash: sorted by mixed key on the host (a few hundred entries at most), searched by km_probe_buckets
             if (sn) {
                 std::vector<uint64_t> sx(sn); std::vector<uint32_t> sh(sn), ord(sn);
-                KM_CUDA(cudaMemcpy(sx.data(), d_sx, (size_t)sn * 8, cudaMemcpyDeviceToHost));
-                KM_CUDA(cudaMemcpy(sh.data(), d_sh, (size_t)sn * 4, cudaMemcpyDeviceToHost));
+                KM_CUDA(cudaMemcpy(sx.data(), T.d_sx, (size_t)sn * 8, cudaMemcpyDeviceToHost));
+                KM_CUDA(cudaMemcpy(sh.data(), T.d_sh, (size_t)sn * 4, cudaMemcpyDeviceToHost));
                 for (unsigned int i = 0; i < sn; i++) ord[i] = i;
                 std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b2) { return sx[a] < sx[b2]; });
                 std::vector<uint64_t> sx2(sn); std::vector<uint32_t> sh2(sn);
@@ -161,10 +191,63 @@ static int km_db_alloc_and_insert(kmat_db *db, const uint64_t *d_kmers, const ui
                 KM_CUDA(cudaMemcpy(db->d_stash_hit, sh2.data(), (size_t)sn * 4, cudaMemcpyHostToDevice));
             }
             db->n_stash = sn;
+            return KMAT_OK;
         }
-        cudaFree(d_sn); cudaFree(d_sx); cudaFree(d_sh);
-        if (sn <= KM_STASH_CAP) break;
         cudaFree(db->d_slots); db->d_slots = nullptr;       // too many displaced keys for the stash: double the table
+    }
+}
+
+// n k-mers in the arrays; n_global = size of the whole table (decides the first level's geometry, which every shard must
+// share); prefiltered: the arrays hold this shard's k-mers only (the host upload path), else the kernels filter by owner.
+static int km_db_alloc_and_insert(kmat_db *db, const uint64_t *d_kmers, const uint32_t *d_payload, uint64_t n, uint64_t n_global, bool prefiltered,
+                                  int shard_index, int shard_count) {
+    const int kmer_bits = 2 * db->kmer_len;
+    KmBuildTmp T;
+    KM_CUDA(cudaMalloc((void **)&T.d_cnt, 16));
+    KM_CUDA(cudaMemset(T.d_cnt, 0, 16));
+    unsigned long long kept = 0;
+    db->geom.kmer_bits = kmer_bits;
+    db->geom.line_m = km_line_m(db->kmer_len);
+    db->geom.line_bits = km_choose_line_bits(n_global, db->kmer_len, db->geom.line_m);
+    if (!db->geom.line_bits || n >= (1ull << 32)) { db->geom.line_m = 0; db->geom.line_bits = 0; }      // the overflow list holds 32-bit indices
+    if (db->geom.line_m) {
+        const int m = db->geom.line_m, lb = db->geom.line_bits;
+        db->line_first = km_line_shard_first((uint32_t)shard_index, (uint32_t)shard_count, m, lb);
+        db->n_lines = km_line_shard_count((uint32_t)shard_index, (uint32_t)shard_count, m, lb);
+        const size_t bytes = db->n_lines * 128;
+        KM_CUDA(cudaMalloc((void **)&db->d_lines, bytes));
+        KM_CUDA(cudaMemset(db->d_lines, 0, bytes));
+        // a shard keeps ~n / shard_count of the k-mers; the overflow list is sized for all of them
+        const uint64_t ovf_cap = prefiltered ? n + 16 : n / shard_count + n / (4 * (uint64_t)shard_count) + 4096;
+        KM_CUDA(cudaMalloc((void **)&T.d_ovf, ovf_cap * 4));
+        unsigned long long n_ovf = 0;
+        if (n) {
+            const int blocks = (int)std::min<uint64_t>((n + 255) / 256, 148ull * 16);
+            km_line_insert_kernel<<<blocks, 256>>>(d_kmers, d_payload, n, (unsigned long long *)db->d_lines, db->line_first, db->kmer_len, m, lb,
+                                                   (uint32_t)shard_index, (uint32_t)shard_count, T.d_cnt, T.d_ovf, T.d_cnt + 1, ovf_cap);
+            g_km_launches++;
+            KM_CUDA(cudaGetLastError());
+            unsigned long long h[2];
+            KM_CUDA(cudaMemcpy(h, T.d_cnt, 16, cudaMemcpyDeviceToHost));
+            kept = h[0]; n_ovf = h[1];
+            if (n_ovf > ovf_cap) { kmat_set_error("table build: %llu first-level overflows exceed the list of %llu (uneven shards?)", n_ovf, (unsigned long long)ovf_cap); return KMAT_ERR_UNSUPPORTED; }
+            if (n_ovf) {
+                km_line_flag_kernel<<<(int)std::min<uint64_t>((n_ovf + 255) / 256, 148ull * 16), 256>>>(d_kmers, T.d_ovf, n_ovf, (unsigned long long *)db->d_lines, db->line_first, db->kmer_len, m, lb);
+                g_km_launches++;
+                KM_CUDA(cudaGetLastError());
+            }
+        }
+        db->n_overflow = n_ovf;
+        if (n_ovf) {
+            unsigned long long k2 = 0;
+            int rc = km_build_buckets(db, d_kmers, d_payload, T.d_ovf, n_ovf, n_ovf, 0, 1, T, &k2);
+            if (rc != KMAT_OK) return rc;
+        }
+    } else {
+        // a shard keeps ~n / shard_count of the k-mers (the owner hash is uniform); the table is sized for that plus 5 %
+        const uint64_t expect = (shard_count > 1 && !prefiltered) ? n / shard_count + n / (20 * (uint64_t)shard_count) + 1024 : n;
+        int rc = km_build_buckets(db, d_kmers, d_payload, nullptr, n, expect, shard_index, prefiltered ? 1 : shard_count, T, &kept);
+        if (rc != KMAT_OK) return rc;
     }
     // bitmap of the reference's non-empty top-tier prefixes: only used to count "prefix miss" lookups exactly
     // for the algorithmic-bytes statistic; 2^27 bits = 16 MiB
@@ -182,7 +265,6 @@ static int km_db_alloc_and_insert(kmat_db *db, const uint64_t *d_kmers, const ui
         db->prefix_bytes = words * 4;
     }
     KM_CUDA(cudaDeviceSynchronize());
-    cudaFree(d_kept);
     db->n_kmers = kept;
     db->shard_index = shard_index; db->shard_count = shard_count;
     return KMAT_OK;
@@ -191,11 +273,31 @@ static int km_db_alloc_and_insert(kmat_db *db, const uint64_t *d_kmers, const ui
 KmDbDev km_db_dev(const kmat_db *db) {
     KmDbDev d;
     d.peers = nullptr; d.n_peers = 0;
+    d.lines = db->d_lines; d.line_first = db->line_first; d.n_lines = db->n_lines; d.line_m = db->geom.line_m; d.line_bits = db->geom.line_bits;
     d.slots = db->d_slots; d.bucket_mask = db->n_buckets - 1; d.kmer_bits = db->geom.kmer_bits; d.rem_bits = db->geom.rem_bits;
     d.kmer_len = db->kmer_len; d.tid_bytes = db->tid_bytes; d.pool = db->d_pool; d.prefix_bits = db->d_prefix_bits;
     d.prefix_shift = db->prefix_shift;
     d.stash_x = db->d_stash_x; d.stash_hit = db->d_stash_hit; d.n_stash = db->n_stash;
     return d;
+}
+
+static int km_db_build(int device, int kmer_len, int tid_bytes, uint64_t n, uint64_t n_global, bool prefiltered, const uint64_t *d_kmers,
+                       const uint32_t *d_payload, const uint32_t *d_pool, uint64_t pool_words, uint32_t n_stored_ids,
+                       int shard_index, int shard_count, kmat_db **out) {
+    kmat_db *db = new kmat_db();
+    db->device = device; db->kmer_len = kmer_len; db->tid_bytes = tid_bytes; db->n_sid = tid_bytes == 2 ? 65536u : n_stored_ids;
+    db->pool_words = pool_words;
+    auto body = [&]() -> int {
+        if (pool_words) {
+            KM_CUDA(cudaMalloc((void **)&db->d_pool, pool_words * 4));
+            KM_CUDA(cudaMemcpy(db->d_pool, d_pool, pool_words * 4, cudaMemcpyDeviceToDevice));
+        }
+        return km_db_alloc_and_insert(db, d_kmers, d_payload, n, n_global, prefiltered, shard_index, shard_count);
+    };
+    const int rc = body();
+    if (rc != KMAT_OK) { kmat_db_free(db); return rc; }      // every device buffer of a failed build goes back
+    *out = db;
+    return KMAT_OK;
 }
 
 extern "C" int kmat_db_build_device(int device, int kmer_len, int tid_bytes, uint64_t n, const uint64_t *d_kmers,
@@ -205,18 +307,14 @@ extern "C" int kmat_db_build_device(int device, int kmer_len, int tid_bytes, uin
     if (kmat_device_count() <= device) { kmat_set_error("CUDA device %d not available", device); return KMAT_ERR_NO_DEVICE; }
     if (pool_words >= (1ull << 31)) { kmat_set_error("list pool of %llu words exceeds the 31-bit offset range", (unsigned long long)pool_words); return KMAT_ERR_UNSUPPORTED; }
     KM_CUDA(cudaSetDevice(device));
-    kmat_db *db = new kmat_db();
-    db->device = device; db->kmer_len = kmer_len; db->tid_bytes = tid_bytes; db->n_sid = tid_bytes == 2 ? 65536u : n_stored_ids;
-    db->pool_words = pool_words;
-    if (pool_words) {
-        KM_CUDA(cudaMalloc((void **)&db->d_pool, pool_words * 4));
-        KM_CUDA(cudaMemcpy(db->d_pool, d_pool, pool_words * 4, cudaMemcpyDeviceToDevice));
-    }
-    int rc = km_db_alloc_and_insert(db, d_kmers, d_payload, n, shard_index, shard_count);
-    if (rc != KMAT_OK) { kmat_db_free(db); return rc; }
-    *out = db;
-    return KMAT_OK;
+    return km_db_build(device, kmer_len, tid_bytes, n, n, false, d_kmers, d_payload, d_pool, pool_words, n_stored_ids, shard_index, shard_count, out);
 }
+
+// device copies of the host arrays of an upload: freed on every path out
+struct KmUploadTmp {
+    uint64_t *d_k = nullptr; uint32_t *d_p = nullptr, *d_pool = nullptr;
+    ~KmUploadTmp() { cudaFree(d_k); cudaFree(d_p); cudaFree(d_pool); }
+};
 
 // Host table -> device.  List pool record: 16-bit ids: [u16 count][u16 id]*count ; 32-bit ids: [u32 count][u32 id]*count,
 // padded to 4 bytes; a record of <= 32 bytes never straddles a 32-byte sector, so a list fetch is one sector.
@@ -237,6 +335,7 @@ extern "C" int kmat_db_upload(const kmat_table *t, int device, int shard_index, 
     };
     kmers.reserve(t->n_kmers / shard_count + 16); payload.reserve(t->n_kmers / shard_count + 16);
     for (uint64_t i = 0; i < t->n_kmers; i++) {
+        if (i && t->kmers[i] <= t->kmers[i - 1]) { kmat_set_error("table: k-mers are not strictly ascending at index %llu", (unsigned long long)i); return KMAT_ERR_FORMAT; }
         if (shard_count > 1 && (int)kmat_shard_of(t->kmers[i], t->kmer_len, shard_count) != shard_index) continue;
         const uint64_t a = t->offs[i], c = t->offs[i + 1] - a;
         if (t->offs[i + 1] < a || t->offs[i + 1] > t->n_ids) { kmat_set_error("table: list offsets of k-mer %llu are not ascending / exceed the id array", (unsigned long long)i); return KMAT_ERR_FORMAT; }
@@ -260,37 +359,39 @@ extern "C" int kmat_db_upload(const kmat_table *t, int device, int shard_index, 
         payload.push_back(0x80000000u | (uint32_t)at);
     }
     KM_CUDA(cudaSetDevice(device));
-    uint64_t *d_k = nullptr; uint32_t *d_p = nullptr, *d_pool = nullptr;
+    KmUploadTmp U;
     const uint64_t n = kmers.size();
     if (n) {
-        KM_CUDA(cudaMalloc((void **)&d_k, n * 8)); KM_CUDA(cudaMalloc((void **)&d_p, n * 4));
-        KM_CUDA(cudaMemcpy(d_k, kmers.data(), n * 8, cudaMemcpyHostToDevice));
-        KM_CUDA(cudaMemcpy(d_p, payload.data(), n * 4, cudaMemcpyHostToDevice));
+        KM_CUDA(cudaMalloc((void **)&U.d_k, n * 8)); KM_CUDA(cudaMalloc((void **)&U.d_p, n * 4));
+        KM_CUDA(cudaMemcpy(U.d_k, kmers.data(), n * 8, cudaMemcpyHostToDevice));
+        KM_CUDA(cudaMemcpy(U.d_p, payload.data(), n * 4, cudaMemcpyHostToDevice));
     }
     if (!pool.empty()) {
-        KM_CUDA(cudaMalloc((void **)&d_pool, pool.size() * 4));
-        KM_CUDA(cudaMemcpy(d_pool, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice));
+        KM_CUDA(cudaMalloc((void **)&U.d_pool, pool.size() * 4));
+        KM_CUDA(cudaMemcpy(U.d_pool, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice));
     }
-    // the host loop above already kept this shard's k-mers only (and only their lists), so no device-side filter
-    int rc = kmat_db_build_device(device, t->kmer_len, t->tid_bytes, n, d_k, d_p, d_pool, pool.size(), (uint32_t)stored.size(), 0, 1, out);
-    if (rc == KMAT_OK) { (*out)->shard_index = shard_index; (*out)->shard_count = shard_count; }
+    // the host loop above already kept this shard's k-mers only (and only their lists); the first level's geometry follows
+    // the size of the WHOLE table so that every shard computes the same keys
+    int rc = km_db_build(device, t->kmer_len, t->tid_bytes, n, t->n_kmers, true, U.d_k, U.d_p, U.d_pool, pool.size(), (uint32_t)stored.size(), shard_index, shard_count, out);
     if (rc == KMAT_OK && !stored.empty()) {
-        KM_CUDA(cudaMalloc((void **)&(*out)->d_stored_tids, stored.size() * 4));
-        KM_CUDA(cudaMemcpy((*out)->d_stored_tids, stored.data(), stored.size() * 4, cudaMemcpyHostToDevice));
+        if (cudaMalloc((void **)&(*out)->d_stored_tids, stored.size() * 4) != cudaSuccess ||
+            cudaMemcpy((*out)->d_stored_tids, stored.data(), stored.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaGetLastError(); kmat_db_free(*out); *out = nullptr; kmat_set_error("kmat_db_upload: out of device memory"); return KMAT_ERR_NOMEM;
+        }
     }
-    cudaFree(d_k); cudaFree(d_p); cudaFree(d_pool);
     if (rc == KMAT_OK) (*out)->stored_tids = stored;
     return rc;
 }
 
 extern "C" uint64_t kmat_db_size(const kmat_db *db) { return db ? db->n_kmers : 0; }
-extern "C" uint64_t kmat_db_bytes(const kmat_db *db) { return db ? db->n_buckets * 32 + db->pool_words * 4 + db->prefix_bytes + (uint64_t)db->n_stash * 12 : 0; }
+extern "C" uint64_t kmat_db_bytes(const kmat_db *db) { return db ? db->n_lines * 128 + (db->d_slots ? db->n_buckets * 32 : 0) + db->pool_words * 4 + db->prefix_bytes + (uint64_t)db->n_stash * 12 : 0; }
+extern "C" uint64_t kmat_db_overflow(const kmat_db *db) { return db ? db->n_overflow : 0; }      /* k-mers in the second level of a two-level table */
 extern "C" int kmat_db_kmer_length(const kmat_db *db) { return db ? db->kmer_len : 0; }
 extern "C" int kmat_db_device(const kmat_db *db) { return db ? db->device : -1; }
 extern "C" void kmat_db_free(kmat_db *db) {
     if (!db) return;
     cudaSetDevice(db->device);
-    cudaFree(db->d_slots); cudaFree(db->d_pool); cudaFree(db->d_prefix_bits); cudaFree(db->d_stash_x); cudaFree(db->d_stash_hit); cudaFree(db->d_stored_tids);
+    cudaFree(db->d_lines); cudaFree(db->d_slots); cudaFree(db->d_pool); cudaFree(db->d_prefix_bits); cudaFree(db->d_stash_x); cudaFree(db->d_stash_hit); cudaFree(db->d_stored_tids);
     delete db;
 }
 
@@ -516,7 +617,7 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32) km_encode_probe_kernel(Km
             }
             if (p >= 0 && j < len) {
                 P.hit[off + p] = hw;
-                if (P.xq && first) P.xq[off + p] = KM_KEY(canon, kmer_bits, P.db.bucket_mask);
+                if (P.xq && first) P.xq[off + p] = km_key(P.db, canon);
                 if (P.out_kmers) { P.out_kmers[off + p] = ok ? canon : 0; P.out_flags[off + p] = ok ? (first ? 1 : 2) : 0; }
             }
             prev = cur; pinv = cinv; pgc = cgc;
@@ -655,9 +756,8 @@ __global__ void __launch_bounds__(KM_LONG_THREADS, 1) km_encode_probe_long_kerne
                     }
                     if (first[u]) {
                         cn[u] = canon;
-                        xk[u] = KM_KEY(canon, kmer_bits, P.db.bucket_mask);
-                        if (P.do_probe)
-                            km_load_bucket(km_slots_of(P.db, xk[u], owner[u]) + ((xk[u] >> P.db.rem_bits) & P.db.bucket_mask) * KM_SLOTS_PER_BUCKET, bk[u][0], bk[u][1], bk[u][2], bk[u][3]);
+                        xk[u] = km_key(P.db, canon);
+                        if (P.do_probe) km_first_load(P.db, xk[u], owner[u], bk[u][0], bk[u][1], bk[u][2], bk[u][3]);
                     }
                 }
             }
@@ -671,8 +771,7 @@ __global__ void __launch_bounds__(KM_LONG_THREADS, 1) km_encode_probe_long_kerne
                     hw = KM_HIT_MISS;
                     if (P.do_probe) {
                         uint32_t extra = 0;
-                        if (km_bucket_match(bk[u][0], bk[u][1], bk[u][2], bk[u][3], xk[u] & ((1ull << P.db.rem_bits) - 1), 0, hw) == 2) { hw = km_probe_x(P.db, xk[u], extra, 1); extra++; }
-                        else hw = km_tag_owner(P.db, hw, owner[u]);
+                        hw = km_first_finish(P.db, xk[u], owner[u], bk[u][0], bk[u][1], bk[u][2], bk[u][3], extra);
                         if (P.stats) {
                             st_lookups++; st_extra += extra;
                             if (hw != KM_HIT_MISS) { st_hits++; if (hw & KM_HIT_LIST) st_lists++; }
@@ -704,18 +803,16 @@ __global__ void __launch_bounds__(KM_LONG_THREADS, 1) km_encode_probe_long_kerne
 #ifndef KM_FAST_CTAS
 #define KM_FAST_CTAS 2
 #endif
-#ifndef KMAT_LINE_SHFL
-#define KMAT_LINE_SHFL 0
-#endif
-#if KMAT_LINE_TABLE && KMAT_LINE_SHFL
-// value of the lane `sh` bases to the left: this chunk's lanes, or the tail of the previous chunk (kmat_mzr.h, sliding minimum)
-__device__ __forceinline__ uint64_t km_fetch_left(uint64_t cur, uint64_t prv, int lane, int sh) {
-    const int src = (lane - sh) & 31;
-    const uint64_t a = kb_shfl_u64(cur, src), b = kb_shfl_u64(prv, src);
-    return lane >= sh ? a : b;
+// value of the lane `sh` bases to the left: this chunk's lanes, or the tail of the previous chunk (kmat_mzr.h, sliding minimum).
+// Which of the two a SOURCE lane hands out depends on its own index only (the last sh lanes serve the next chunk's first
+// lanes), so one shuffle does it.
+__device__ __forceinline__ uint32_t km_fetch_left(uint32_t cur, uint32_t prv, int lane, int sh) {
+    return __shfl_sync(KM_FULL, lane < 32 - sh ? cur : prv, (lane - sh) & 31);
 }
-#endif
-template <int NCH, int SETN, bool STATS, bool PEERS>
+// LINE: the table has a minimizer-ordered first level (kmat_mzr.h).  Every lane hashes the m-mer that ends at its base, a
+// sliding minimum over the lanes gives each k-mer its minimizer, and the lanes that hold the k-mers of one super-k-mer then
+// read different sectors of ONE 128-byte line in the same instruction: ~48 requests per 150 bp read instead of 131.
+template <int NCH, int SETN, bool STATS, bool PEERS, bool LINE>
 __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS : 1) km_encode_probe_fast_kernel(KmProbeParams P) {
     if (!PEERS) P.db.n_peers = 0;                 // the replicated table's instantiation carries no owner logic at all
     extern __shared__ __align__(16) unsigned char km_smem[];
@@ -724,6 +821,9 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
     const uint64_t warp_global = blockIdx.x * KM_PROBE_WARPS + wib, n_warps = gridDim.x * KM_PROBE_WARPS;
     const int k = P.db.kmer_len, kmer_bits = P.db.kmer_bits;
     const uint64_t kmask = (1ull << kmer_bits) - 1;
+    const int lm = P.db.line_m, lb = P.db.line_bits;
+    int sl1 = 0, sl2 = 0, sl3 = 0;
+    if (LINE) km_slide_shifts(k - lm + 1, sl1, sl2, sl3);
     for (int i = lane; i < SETN / 32; i += 32) bitmap[i] = 0;
     unsigned long long st_lookups = 0, st_hits = 0, st_lists = 0, st_extra = 0, st_pmiss = 0;
     __syncwarp();
@@ -749,16 +849,12 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
         { const uint64_t r2 = r + 2 * n_warps; lenB = 0; if (r2 < n) { offB = P.offs[r2]; lenB = (int)(P.offs[r2 + 1] - offB); } }
 
         // ---- encode every chunk (read_label.cpp:943-950, 978-1009, GC bookkeeping :994-1008); start the bucket gathers
-        uint64_t xk[NCH];                  // mixed canonical k-mer ending at base j = 32 c + lane
+        uint64_t xk[NCH];                  // table key of the canonical k-mer ending at base j = 32 c + lane
         uint64_t canon_s[STATS ? NCH : 1];
         uint32_t okbits = 0;
         uint64_t prev = 0; uint32_t pinv = 0xFFFFFFFFu, pgc = 0;
         int valid = 0, vgc = 0, vtot = 0;
-#if KMAT_LINE_TABLE && KMAT_LINE_SHFL
-        uint64_t sp_r[3] = {KM_SLIDE_NONE, KM_SLIDE_NONE, KM_SLIDE_NONE}, sp_l[3] = {KM_SLIDE_NONE, KM_SLIDE_NONE, KM_SLIDE_NONE};
-        const int sl_w = k - KM_LINE_M + 1;                  // windows per k-mer; the sliding form needs 5 .. 8 (uniform)
-        const int sl_bl = KM_BITS_OF_MASK(P.db.bucket_mask) - 2;
-#endif
+        uint32_t sp_r[3] = {KM_SLIDE_NONE, KM_SLIDE_NONE, KM_SLIDE_NONE}, sp_l[3] = {KM_SLIDE_NONE, KM_SLIDE_NONE, KM_SLIDE_NONE};
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
             const uint32_t cinv = __ballot_sync(KM_FULL, code[c] < 0);
@@ -776,26 +872,21 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
             const bool ok_prev = wsh > 0 && ((inv64 >> (wsh - 1)) & wmask) == 0;
             xk[c] = 0;
             if (STATS) canon_s[c] = 0;
-#if KMAT_LINE_TABLE && KMAT_LINE_SHFL
-            uint64_t sl_kr = 0, sl_kl = 0;
-            if (sl_w >= 5 && sl_w <= 8) {                        // every lane takes part: one hash per base, three doubling steps
-                const uint32_t hh = km_slide_hash(fwd, KM_LINE_M);
-                const uint64_t r0 = km_slide_r0(hh), l0 = km_slide_l0(hh);
-                const uint64_t r1 = km_slide_r(r0, km_fetch_left(r0, sp_r[0], lane, 1), 1), l1 = km_slide_l(l0, km_fetch_left(l0, sp_l[0], lane, 1), 1);
-                const uint64_t r2 = km_slide_r(r1, km_fetch_left(r1, sp_r[1], lane, 2), 2), l2 = km_slide_l(l1, km_fetch_left(l1, sp_l[1], lane, 2), 2);
-                sl_kr = km_slide_r(r2, km_fetch_left(r2, sp_r[2], lane, sl_w - 4), sl_w - 4);
-                sl_kl = km_slide_l(l2, km_fetch_left(l2, sp_l[2], lane, sl_w - 4), sl_w - 4);
+            uint32_t sl_kr = 0, sl_kl = 0;
+            if (LINE) {                                          // every lane takes part: one hash per base, three doubling steps
+                const uint32_t hh = km_slide_hash(fwd, lm);
+                const uint32_t r0 = km_slide_r0(hh), l0 = km_slide_l0(hh);
+                const uint32_t r1 = km_slide_r(r0, km_fetch_left(r0, sp_r[0], lane, sl1), sl1), l1 = km_slide_l(l0, km_fetch_left(l0, sp_l[0], lane, sl1), sl1);
+                const uint32_t r2 = km_slide_r(r1, km_fetch_left(r1, sp_r[1], lane, sl2), sl2), l2 = km_slide_l(l1, km_fetch_left(l1, sp_l[1], lane, sl2), sl2);
+                sl_kr = km_slide_r(r2, km_fetch_left(r2, sp_r[2], lane, sl3), sl3);
+                sl_kl = km_slide_l(l2, km_fetch_left(l2, sp_l[2], lane, sl3), sl3);
                 sp_r[0] = r0; sp_r[1] = r1; sp_r[2] = r2; sp_l[0] = l0; sp_l[1] = l1; sp_l[2] = l2;
             }
-#endif
             if (ok) {
                 const uint64_t rc = km_revcomp(fwd, kmer_bits);
                 const uint64_t canon = fwd < rc ? fwd : rc;                    // read_label.cpp:1009
-#if KMAT_LINE_TABLE && KMAT_LINE_SHFL
-                if (sl_w >= 5 && sl_w <= 8) xk[c] = km_line_x_of(canon, km_slide_finish(sl_kr, sl_kl, fwd, fwd < rc, k, KM_LINE_M), k, KM_LINE_M, sl_bl);
-                else
-#endif
-                xk[c] = KM_KEY(canon, kmer_bits, P.db.bucket_mask);
+                if (LINE) xk[c] = km_line_x_of(canon, km_slide_finish(sl_kr, sl_kl, fwd, fwd < rc, k, lm), k, lm, lb);
+                else xk[c] = km_mix(canon, kmer_bits);
                 if (STATS) canon_s[c] = canon;
                 okbits |= 1u << c;
             }
@@ -838,16 +929,19 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
         // the words this lane touched go back to zero for the next read (every set bit lies in such a word)
 #pragma unroll
         for (int c = 0; c < NCH; c++) if ((okbits >> c) & 1) bitmap[(KM_SET_HASH(xk[c]) & (SETN - 1)) >> 5] = 0;
-        // ---- probe the first occurrences: every home-bucket gather of the read is issued before the first one is
+        // ---- probe the first occurrences: the first request of every lookup of the read is issued before the first one is
         //      looked at (NCH independent LDG.256 per lane in flight), then one hit word per k-mer start position
         uint64_t bk[NCH][4];
+        uint32_t owner[PEERS ? NCH : 1];
         if (P.do_probe) {
 #pragma unroll
             for (int c = 0; c < NCH; c++) {
                 bk[c][0] = bk[c][1] = bk[c][2] = bk[c][3] = 0;
+                if (PEERS) owner[c] = 0;
                 if ((first >> c) & 1) {
-                    uint32_t owner;                                   // direct sharded mode: the gather goes to the owner's memory
-                    km_load_bucket(km_slots_of(P.db, xk[c], owner) + ((xk[c] >> P.db.rem_bits) & P.db.bucket_mask) * KM_SLOTS_PER_BUCKET, bk[c][0], bk[c][1], bk[c][2], bk[c][3]);
+                    if (PEERS) km_first_load(P.db, xk[c], owner[c], bk[c][0], bk[c][1], bk[c][2], bk[c][3]);      // direct sharded mode: the gather goes to the owner's memory
+                    else if (LINE) km_load_sector(P.db.lines + (((xk[c] >> KM_LINE_XSHIFT) - P.db.line_first) * 4 + ((xk[c] >> KM_MZR_KEY_BITS) & 3u)) * KM_SLOTS_PER_BUCKET, bk[c][0], bk[c][1], bk[c][2], bk[c][3]);
+                    else km_load_bucket(P.db.slots + ((xk[c] >> P.db.rem_bits) & P.db.bucket_mask) * KM_SLOTS_PER_BUCKET, bk[c][0], bk[c][1], bk[c][2], bk[c][3]);
                 }
             }
         }
@@ -859,10 +953,13 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
                 hw = KM_HIT_MISS;
                 if (P.do_probe) {
                     uint32_t extra = 0;
-                    if (km_bucket_match(bk[c][0], bk[c][1], bk[c][2], bk[c][3], xk[c] & ((1ull << P.db.rem_bits) - 1), 0, hw) == 2) {
+                    if (PEERS) hw = km_first_finish(P.db, xk[c], owner[c], bk[c][0], bk[c][1], bk[c][2], bk[c][3], extra);
+                    else if (LINE) {
+                        if (km_sector_match(bk[c][0], bk[c][1], bk[c][2], bk[c][3], xk[c] & ((1ull << KM_MZR_KEY_BITS) - 1), hw) == 2) hw = km_probe_x(P.db, xk[c], extra, 1);
+                    } else if (km_bucket_match(bk[c][0], bk[c][1], bk[c][2], bk[c][3], xk[c] & ((1ull << P.db.rem_bits) - 1), 0, hw) == 2) {
                         hw = km_probe_x(P.db, xk[c], extra, 1);
                         extra++;
-                    } else if (P.db.n_peers) hw = km_tag_owner(P.db, hw, km_owner_of_x(xk[c], P.db.n_peers));
+                    }
                     if (STATS) {
                         st_lookups++; st_extra += extra;
                         if (hw != KM_HIT_MISS) { st_hits++; if (hw & KM_HIT_LIST) st_lists++; }
@@ -897,7 +994,7 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
     }
 }
 
-template <int NCH, int SETN, bool STATS, bool PEERS>
+template <int NCH, int SETN, bool STATS, bool PEERS, bool LINE>
 static int km_launch_fast(const KmProbeParams &P, int ctas_per_sm, cudaStream_t stream) {
     const int smem = KM_PROBE_WARPS * (SETN / 8);
     // per instantiation AND per device (function attributes belong to a device's context; a process may drive several
@@ -908,9 +1005,9 @@ static int km_launch_fast(const KmProbeParams &P, int ctas_per_sm, cudaStream_t 
     if (dev < 0 || dev >= KM_MAX_DEVICES) { kmat_set_error("device index %d out of range", dev); return KMAT_ERR_ARG; }
     int resident = resident_of[dev].load(), sms = sms_of[dev].load();
     if (!resident) {
-        KM_CUDA(cudaFuncSetAttribute(km_encode_probe_fast_kernel<NCH, SETN, STATS, PEERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        KM_CUDA(cudaFuncSetAttribute(km_encode_probe_fast_kernel<NCH, SETN, STATS, PEERS, LINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int per_sm = 0;
-        KM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_encode_probe_fast_kernel<NCH, SETN, STATS, PEERS>, KM_PROBE_WARPS * 32, smem));
+        KM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, km_encode_probe_fast_kernel<NCH, SETN, STATS, PEERS, LINE>, KM_PROBE_WARPS * 32, smem));
         KM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         if (const char *e = getenv("KMAT_PROBE_CTAS")) { const int v = atoi(e); if (v > 0 && v < per_sm) per_sm = v; }
         resident = std::max(1, per_sm) * sms;
@@ -919,8 +1016,17 @@ static int km_launch_fast(const KmProbeParams &P, int ctas_per_sm, cudaStream_t 
     const uint32_t want = (P.n_reads + KM_PROBE_WARPS - 1) / KM_PROBE_WARPS;
     const uint32_t cap = ctas_per_sm > 0 ? std::min<uint32_t>((uint32_t)resident, (uint32_t)(ctas_per_sm * sms)) : (uint32_t)resident;
     const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>(want, cap));
-    km_encode_probe_fast_kernel<NCH, SETN, STATS, PEERS><<<grid, KM_PROBE_WARPS * 32, smem, stream>>>(P);
+    km_encode_probe_fast_kernel<NCH, SETN, STATS, PEERS, LINE><<<grid, KM_PROBE_WARPS * 32, smem, stream>>>(P);
     return KMAT_OK;
+}
+template <int NCH, int SETN>
+static int km_launch_fast_pick(const KmProbeParams &P, bool stats, bool peers, bool line, int ctas_per_sm, cudaStream_t stream) {
+    if (line) {
+        if (peers) return stats ? km_launch_fast<NCH, SETN, true, true, true>(P, ctas_per_sm, stream) : km_launch_fast<NCH, SETN, false, true, true>(P, ctas_per_sm, stream);
+        return stats ? km_launch_fast<NCH, SETN, true, false, true>(P, ctas_per_sm, stream) : km_launch_fast<NCH, SETN, false, false, true>(P, ctas_per_sm, stream);
+    }
+    if (peers) return stats ? km_launch_fast<NCH, SETN, true, true, false>(P, ctas_per_sm, stream) : km_launch_fast<NCH, SETN, false, true, false>(P, ctas_per_sm, stream);
+    return stats ? km_launch_fast<NCH, SETN, true, false, false>(P, ctas_per_sm, stream) : km_launch_fast<NCH, SETN, false, false, false>(P, ctas_per_sm, stream);
 }
 
 int km_launch_encode_probe(const kmat_db *db, const char *d_bases, const uint64_t *d_offs, uint32_t n_reads, uint32_t max_len,
@@ -933,11 +1039,9 @@ int km_launch_encode_probe(const kmat_db *db, const char *d_bases, const uint64_
     P.do_probe = do_probe; P.xq = d_xq; P.skip_mid = 0;
     const bool fast = !d_kmers && !d_flags && max_len <= 256 && db->kmer_len <= 24 && !getenv("KMAT_NO_FAST_PROBE");
     int rc = KMAT_OK;
-    const bool peers = P.db.n_peers != 0;
-    if (fast && max_len <= 160 && !peers) rc = d_stats ? km_launch_fast<5, 4096, true, false>(P, ctas_per_sm, stream) : km_launch_fast<5, 4096, false, false>(P, ctas_per_sm, stream);
-    else if (fast && max_len <= 160) rc = d_stats ? km_launch_fast<5, 4096, true, true>(P, ctas_per_sm, stream) : km_launch_fast<5, 4096, false, true>(P, ctas_per_sm, stream);
-    else if (fast && !peers) rc = d_stats ? km_launch_fast<8, 8192, true, false>(P, ctas_per_sm, stream) : km_launch_fast<8, 8192, false, false>(P, ctas_per_sm, stream);
-    else if (fast) rc = d_stats ? km_launch_fast<8, 8192, true, true>(P, ctas_per_sm, stream) : km_launch_fast<8, 8192, false, true>(P, ctas_per_sm, stream);
+    const bool peers = P.db.n_peers != 0, line = P.db.line_m != 0;
+    if (fast && max_len <= 160) rc = km_launch_fast_pick<5, 4096>(P, d_stats != nullptr, peers, line, ctas_per_sm, stream);
+    else if (fast) rc = km_launch_fast_pick<8, 8192>(P, d_stats != nullptr, peers, line, ctas_per_sm, stream);
     else {
         // mixed / long batches: reads of 257 .. 12000 bases get a CTA each (shared-memory dedup set), the any-length kernel
         // takes the rest

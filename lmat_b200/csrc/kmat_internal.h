@@ -103,8 +103,10 @@ int kmat_build_host_ctx(const kmat_inputs &in, int tid_bytes, const std::vector<
 #define KM_MAX_DISP 3
 struct KmTableGeom {
     int kmer_bits;      // 2k
-    int bucket_bits;    // b: number of buckets = 2^b
-    int rem_bits;       // 2k - b  (<= KM_REM_BITS)
+    int bucket_bits;    // number of buckets of the second level = 2^bucket_bits
+    int rem_bits;       // 2k - bucket_bits  (<= KM_REM_BITS)
+    int line_m;         // minimizer length of the first level (0: no first level)
+    int line_bits;      // GLOBAL number of lines = 2^line_bits (a shard holds the lines of its owner range)
 };
 
 #if defined(__CUDACC__)
@@ -124,29 +126,11 @@ KM_HD uint64_t km_mix(uint64_t x, int kmer_bits) {
     x ^= x >> s;
     return x;
 }
-// The table key of a canonical k-mer.  Default: the bijective mix above.  -DKMAT_LINE_TABLE=1 (experiment for the next GPU
-// session; replicated table only, k - KM_LINE_M + 1 <= 8): the minimizer-ordered line table of kmat_mzr.h on the same slot
-// format -- the key depends on the number of buckets, rem_bits is 28, and a full home sector continues in the rest of its
-// 128-byte line (km_line_bucket_at).  KM_SET_HASH: the key bits that index the probe kernel's per-read bitmap.
-#ifndef KMAT_LINE_TABLE
-#define KMAT_LINE_TABLE 0
-#endif
-#if KMAT_LINE_TABLE
+// The first level of the table is ordered by minimizer (kmat_mzr.h): the key of a canonical k-mer is then km_line_x(),
+// [line][sector][28-bit key]; tables whose k has no line geometry (km_line_m(k) == 0) use the mixed k-mer above for
+// everything.  KM_SET_HASH: the key bits that index the probe kernel's per-read dedup bitmap.
 #include "kmat_mzr.h"
-#ifndef KM_LINE_M
-#define KM_LINE_M 15
-#endif
-#if defined(__CUDA_ARCH__)
-#define KM_BITS_OF_MASK(m) __popcll((unsigned long long)(m))
-#else
-#define KM_BITS_OF_MASK(m) __builtin_popcountll((unsigned long long)(m))
-#endif
-#define KM_KEY(canon, kmer_bits, bucket_mask) km_line_x((canon), (kmer_bits) / 2, KM_LINE_M, KM_BITS_OF_MASK(bucket_mask) - 2)
-#define KM_SET_HASH(x) ((uint32_t)(((x) * 0x9E3779B97F4A7C15ull) >> 40))
-#else
-#define KM_KEY(canon, kmer_bits, bucket_mask) km_mix((canon), (kmer_bits))
-#define KM_SET_HASH(x) ((uint32_t)((x) >> 7))
-#endif
+#define KM_SET_HASH(x) ((((uint32_t)(x) ^ (uint32_t)((x) >> 30)) * 0x9E3779B1u) >> 16)
 // Owner shard of a mixed key x = km_mix(kmer) in DB-sharded mode (SURVEY.md 8(e) mode B: hash prefix of the canonical
 // k-mer; a raw k-mer prefix would be skewed).  A second multiply/xor-shift round so that owner and bucket index (the top
 // bits of x) are independent; multiply-shift range reduction instead of a modulo.

@@ -203,7 +203,7 @@ __device__ void kr_resolve_list(const KmCtxDev &C, uint32_t lo, uint2 *scratch, 
 struct KmResolveParams {
     KmCtxDev C;
     uint32_t *pool2;
-    unsigned long long n_slots, n_table_slots;   // n_slots = table slots + stash entries
+    unsigned long long n_slots, n_table_slots, n_line_slots;   // n_slots = first-level slots + second-level slots + stash entries
     uint32_t *big_queue; uint32_t big_cap;       // pool offsets of the lists left to the big pass
     unsigned int *counters;                      // [0] lists queued, [1] longest list (entries), [2] lists seen
     uint2 *scratch; uint32_t scratch_entries;    // big pass: per-thread scratch
@@ -214,12 +214,12 @@ __global__ void __launch_bounds__(256) km_resolve_kernel(KmResolveParams R) {
     uint2 local[2 * KB_LFAST];
     for (unsigned long long s = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; s < R.n_slots; s += (unsigned long long)gridDim.x * blockDim.x) {
         uint32_t lo;
-        if (s < R.n_table_slots) {
-            const uint64_t v = C.db.slots[s];
+        if (s < R.n_line_slots + R.n_table_slots) {       // both levels use bit 63 = occupied, bit 62 = list, payload below
+            const uint64_t v = s < R.n_line_slots ? C.db.lines[s] : C.db.slots[s - R.n_line_slots];
             if (!(v >> 63) || !((v >> 62) & 1)) continue;
             lo = (uint32_t)v & 0x7FFFFFFFu;
         } else {                                          // the overflow stash holds hit words
-            const uint32_t hw = C.db.stash_hit[s - R.n_table_slots];
+            const uint32_t hw = C.db.stash_hit[s - R.n_line_slots - R.n_table_slots];
             if (!(hw & KM_HIT_LIST)) continue;
             lo = hw & 0x7FFFFFFFu;
         }
@@ -1227,8 +1227,9 @@ static int km_resolve_lists(kmat_ctx *c) {
     KmResolveParams R;
     R.C = km_ctx_dev(c);
     R.pool2 = c->d_pool2;
-    R.n_table_slots = db->n_buckets * KM_SLOTS_PER_BUCKET;
-    R.n_slots = R.n_table_slots + db->n_stash;
+    R.n_table_slots = db->d_slots ? db->n_buckets * KM_SLOTS_PER_BUCKET : 0;
+    R.n_line_slots = db->n_lines * 16;
+    R.n_slots = R.n_line_slots + R.n_table_slots + db->n_stash;
     R.big_cap = (uint32_t)(db->pool_words / 9 + 16);         // a list of > KB_LFAST 16-bit ids occupies >= 9 pool words
     R.scratch = nullptr; R.scratch_entries = 0;
     KM_CUDA(cudaMalloc((void **)&R.big_queue, (size_t)R.big_cap * 4));

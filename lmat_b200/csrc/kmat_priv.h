@@ -26,7 +26,8 @@ struct kmat_db {
     int device = 0, kmer_len = 0, tid_bytes = 2;
     KmTableGeom geom{};
     uint64_t n_buckets = 0, n_kmers = 0, pool_words = 0, prefix_bytes = 0;
-    uint64_t *d_slots = nullptr;
+    uint64_t *d_lines = nullptr; uint64_t n_lines = 0, line_first = 0, n_overflow = 0;    // first level (kmat_mzr.h), this shard's line range
+    uint64_t *d_slots = nullptr;                                                           // second level
     uint32_t *d_pool = nullptr;
     uint32_t *d_prefix_bits = nullptr;
     uint64_t *d_stash_x = nullptr; uint32_t *d_stash_hit = nullptr; uint32_t n_stash = 0;   // overflow stash (see km_probe_x)

@@ -60,7 +60,7 @@ __device__ __forceinline__ int km_seg_of(const KmShardSeg &g, int n, unsigned lo
 }
 
 // ---- home: count and scatter the first-occurrence k-mers by owner -------------------------------------------------
-__global__ void __launch_bounds__(256) km_shard_count_kernel(const uint32_t *__restrict__ hit, const uint64_t *__restrict__ xq, uint64_t n_pos,
+__global__ void __launch_bounds__(256) km_shard_count_kernel(KmDbDev db, const uint32_t *__restrict__ hit, const uint64_t *__restrict__ xq, uint64_t n_pos,
                                                              uint32_t n_shards, unsigned long long *counts) {
     // per-lane private counter of owner `lane` (n_shards <= 16 < 32), fed by one ballot per owner: no contended atomics
     __shared__ unsigned int hist[KM_MAX_SHARDS];
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) km_shard_count_kernel(const uint32_t *__r
     for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31); i0 < n_pos; i0 += stride) {       // warp-uniform bounds
         const uint64_t i = i0 + lane;
         const bool m = i < n_pos && hit[i] == KM_HIT_MISS;
-        const uint32_t owner = m ? km_owner_of_x(xq[i], n_shards) : 0xFFFFFFFFu;
+        const uint32_t owner = m ? km_owner_of_key(db, xq[i], n_shards) : 0xFFFFFFFFu;
         for (uint32_t o = 0; o < n_shards; o++) {
             const uint32_t b = __ballot_sync(KM_FULL, owner == o);
             if ((uint32_t)lane == o) mine += __popc(b);
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) km_shard_count_kernel(const uint32_t *__r
     if (threadIdx.x < n_shards && hist[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
 }
 #define KM_SCATTER_TILE 4096
-__global__ void __launch_bounds__(256) km_shard_scatter_kernel(const uint32_t *__restrict__ hit, const uint64_t *__restrict__ xq, uint64_t n_pos,
+__global__ void __launch_bounds__(256) km_shard_scatter_kernel(KmDbDev db, const uint32_t *__restrict__ hit, const uint64_t *__restrict__ xq, uint64_t n_pos,
                                                                uint32_t n_shards, KmShardSeg base, unsigned long long *cursors,
                                                                uint64_t *q, uint32_t *origin) {
     // A CTA takes tiles of 4096 positions: it counts the tile's queries per owner in shared memory, reserves their places
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) km_shard_scatter_kernel(const uint32_t *_
         for (int j = 0; j < KM_SCATTER_TILE / 256; j++) {
             const uint64_t i = t0 + (uint64_t)j * 256 + threadIdx.x;
             const bool m = i < n_pos && hit[i] == KM_HIT_MISS;
-            const uint32_t owner = m ? km_owner_of_x(xq[i], n_shards) : 0xFFFFFFFFu;
+            const uint32_t owner = m ? km_owner_of_key(db, xq[i], n_shards) : 0xFFFFFFFFu;
             for (uint32_t o = 0; o < n_shards; o++) {
                 const uint32_t bal = __ballot_sync(KM_FULL, owner == o);
                 if ((uint32_t)lane == o) mine += __popc(bal);
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) km_shard_scatter_kernel(const uint32_t *_
             const uint64_t i = t0 + (uint64_t)j * 256 + threadIdx.x;
             const bool m = i < n_pos && hit[i] == KM_HIT_MISS;
             const uint64_t x = m ? xq[i] : 0;
-            const uint32_t owner = m ? km_owner_of_x(x, n_shards) : 0xFFFFFFFFu;
+            const uint32_t owner = m ? km_owner_of_key(db, x, n_shards) : 0xFFFFFFFFu;
             const uint32_t act = __ballot_sync(KM_FULL, m);
             if (m) {
                 const uint32_t grp = __match_any_sync(act, owner);
@@ -206,7 +206,7 @@ extern "C" int kmat_shard_encode(kmat_ctx *c, const char *d_bases, const uint64_
     if (rc != KMAT_OK) return rc;
     KM_CUDA(cudaMemsetAsync(s->d_counts, 0, 2 * KM_MAX_SHARDS * sizeof(unsigned long long), st));
     const int grid = (int)std::min<uint64_t>((total_bases + 255) / 256, 148ull * 8);
-    km_shard_count_kernel<<<grid, 256, 0, st>>>(c->d_hit, s->d_xq, total_bases, (uint32_t)n_shards, s->d_counts);
+    km_shard_count_kernel<<<grid, 256, 0, st>>>(km_db_dev(c->db), c->d_hit, s->d_xq, total_bases, (uint32_t)n_shards, s->d_counts);
     g_km_launches++;
     unsigned long long h_counts[KM_MAX_SHARDS];
     KM_CUDA(cudaMemcpyAsync(h_counts, s->d_counts, sizeof h_counts, cudaMemcpyDeviceToHost, st));
@@ -217,7 +217,7 @@ extern "C" int kmat_shard_encode(kmat_ctx *c, const char *d_bases, const uint64_
     s->n_q = tot;
     if ((rc = km_grow(&s->d_q, &s->cap_q, tot + 1)) != KMAT_OK) return rc;
     if ((rc = km_grow(&s->d_origin, &s->cap_origin, tot + 1)) != KMAT_OK) return rc;
-    km_shard_scatter_kernel<<<(int)std::min<uint64_t>((total_bases + KM_SCATTER_TILE - 1) / KM_SCATTER_TILE, 148ull * 8), 256, 0, st>>>(c->d_hit, s->d_xq, total_bases, (uint32_t)n_shards, base, s->d_counts + KM_MAX_SHARDS, s->d_q, s->d_origin);
+    km_shard_scatter_kernel<<<(int)std::min<uint64_t>((total_bases + KM_SCATTER_TILE - 1) / KM_SCATTER_TILE, 148ull * 8), 256, 0, st>>>(km_db_dev(c->db), c->d_hit, s->d_xq, total_bases, (uint32_t)n_shards, base, s->d_counts + KM_MAX_SHARDS, s->d_q, s->d_origin);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     *d_queries = s->d_q;
@@ -337,9 +337,10 @@ extern "C" int kmat_ctx_device_results(kmat_ctx *c, const kmat_read_result **d_o
 struct KmPeerBlob {
     uint32_t magic; int32_t pid, device, shard_index, shard_count;
     int32_t bucket_bits, rem_bits, kmer_bits, tid_bytes, pool2_mul, rkmer, permissive, max_count;
-    uint32_t n_stash; uint64_t pool_words;
-    uint64_t p_slots, p_stash_x, p_stash_hit, p_pool2;                 // raw device pointers (valid inside the exporting process)
-    cudaIpcMemHandle_t h_slots, h_stash_x, h_stash_hit, h_pool2;       // the same allocations for other processes
+    int32_t line_m, line_bits;
+    uint32_t n_stash; uint64_t pool_words, line_first;
+    uint64_t p_lines, p_slots, p_stash_x, p_stash_hit, p_pool2;                 // raw device pointers (valid inside the exporting process)
+    cudaIpcMemHandle_t h_lines, h_slots, h_stash_x, h_stash_hit, h_pool2;       // the same allocations for other processes
 };
 static_assert(sizeof(KmPeerBlob) <= sizeof(kmat_peer_info), "kmat_peer_info too small");
 #define KM_PEER_MAGIC 0x4B4D5045u
@@ -356,8 +357,10 @@ extern "C" int kmat_ctx_peer_export(kmat_ctx *c, kmat_peer_info *out) {
     b.bucket_bits = db->geom.bucket_bits; b.rem_bits = db->geom.rem_bits; b.kmer_bits = db->geom.kmer_bits; b.tid_bytes = db->tid_bytes;
     b.pool2_mul = c->pool2_mul; b.rkmer = c->opt.rkmer_mode != 0; b.permissive = c->opt.permissive != 0; b.max_count = c->opt.max_count;
     b.n_stash = db->n_stash; b.pool_words = db->pool_words;
+    b.line_m = db->geom.line_m; b.line_bits = db->geom.line_bits; b.line_first = db->line_first; b.p_lines = (uint64_t)db->d_lines;
+    if (db->d_lines) KM_CUDA(cudaIpcGetMemHandle(&b.h_lines, db->d_lines));
     b.p_slots = (uint64_t)db->d_slots; b.p_stash_x = (uint64_t)db->d_stash_x; b.p_stash_hit = (uint64_t)db->d_stash_hit; b.p_pool2 = (uint64_t)c->d_pool2;
-    KM_CUDA(cudaIpcGetMemHandle(&b.h_slots, db->d_slots));
+    if (db->d_slots) KM_CUDA(cudaIpcGetMemHandle(&b.h_slots, db->d_slots));
     if (db->n_stash) { KM_CUDA(cudaIpcGetMemHandle(&b.h_stash_x, db->d_stash_x)); KM_CUDA(cudaIpcGetMemHandle(&b.h_stash_hit, db->d_stash_hit)); }
     if (c->d_pool2) KM_CUDA(cudaIpcGetMemHandle(&b.h_pool2, c->d_pool2));
     memcpy(out, &b, sizeof b);
@@ -376,15 +379,16 @@ extern "C" int kmat_ctx_peer_attach(kmat_ctx *c, int n_shards, const kmat_peer_i
         KmPeerBlob b;
         memcpy(&b, &all[s], sizeof b);
         if (b.magic != KM_PEER_MAGIC || b.shard_index != s || b.shard_count != n_shards) { kmat_set_error("kmat_ctx_peer_attach: entry %d is not the export of shard %d of %d", s, s, n_shards); return KMAT_ERR_ARG; }
-        if (b.bucket_bits != db->geom.bucket_bits || b.rem_bits != db->geom.rem_bits || b.kmer_bits != db->geom.kmer_bits || b.tid_bytes != db->tid_bytes) {
-            kmat_set_error("kmat_ctx_peer_attach: shard %d has a different table geometry (2^%d buckets, here 2^%d)", s, b.bucket_bits, db->geom.bucket_bits); return KMAT_ERR_UNSUPPORTED; }
+        if (b.line_m != db->geom.line_m || b.line_bits != db->geom.line_bits || b.kmer_bits != db->geom.kmer_bits || b.tid_bytes != db->tid_bytes) {
+            kmat_set_error("kmat_ctx_peer_attach: shard %d has a different table geometry (2^%d lines, here 2^%d)", s, b.line_bits, db->geom.line_bits); return KMAT_ERR_UNSUPPORTED; }
         if (b.pool2_mul != c->pool2_mul || b.rkmer != (c->opt.rkmer_mode != 0) || b.permissive != (c->opt.permissive != 0) || b.max_count != c->opt.max_count) {
             kmat_set_error("kmat_ctx_peer_attach: shard %d's context was created with different options (-g / -s / rkmer)", s); return KMAT_ERR_ARG; }
         if (b.pool_words > (1ull << KM_PEER_SHIFT)) { kmat_set_error("kmat_ctx_peer_attach: shard %d's list pool (%llu words) exceeds the 2^%d-word offset range of direct mode", s, (unsigned long long)b.pool_words, KM_PEER_SHIFT); return KMAT_ERR_UNSUPPORTED; }
         KmPeer &p = peers[(size_t)s];
         p.n_stash = b.n_stash; p.pool_base = KM_PEER_NO_BASE;
+        p.line_first = b.line_first; p.lines = nullptr; p.slots = nullptr; p.rem_bits = b.rem_bits; p.bucket_mask = (1ull << b.bucket_bits) - 1;
         if (s == db->shard_index) {
-            p.slots = db->d_slots; p.stash_x = db->d_stash_x; p.stash_hit = db->d_stash_hit; p.pool2 = c->d_pool2;
+            p.lines = db->d_lines; p.slots = db->d_slots; p.stash_x = db->d_stash_x; p.stash_hit = db->d_stash_hit; p.pool2 = c->d_pool2;
         } else if (b.pid == me) {
             // same process: the exporter's pointers are ours too; another device needs peer access switched on
             if (b.device != c->device) {
@@ -395,7 +399,7 @@ extern "C" int kmat_ctx_peer_attach(kmat_ctx *c, int n_shards, const kmat_peer_i
                 if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { kmat_set_error("cudaDeviceEnablePeerAccess(%d): %s", b.device, cudaGetErrorString(e)); cudaGetLastError(); return KMAT_ERR_CUDA; }
                 cudaGetLastError();
             }
-            p.slots = (const uint64_t *)b.p_slots; p.stash_x = (const uint64_t *)b.p_stash_x; p.stash_hit = (const uint32_t *)b.p_stash_hit; p.pool2 = (const uint32_t *)b.p_pool2;
+            p.lines = (const uint64_t *)b.p_lines; p.slots = (const uint64_t *)b.p_slots; p.stash_x = (const uint64_t *)b.p_stash_x; p.stash_hit = (const uint32_t *)b.p_stash_hit; p.pool2 = (const uint32_t *)b.p_pool2;
         } else {
             auto open = [&](const cudaIpcMemHandle_t &h, const void **dst) -> int {
                 void *q = nullptr;
@@ -405,7 +409,8 @@ extern "C" int kmat_ctx_peer_attach(kmat_ctx *c, int n_shards, const kmat_peer_i
                 return KMAT_OK;
             };
             int rc;
-            if ((rc = open(b.h_slots, (const void **)&p.slots)) != KMAT_OK) return rc;
+            if (b.p_lines && (rc = open(b.h_lines, (const void **)&p.lines)) != KMAT_OK) return rc;
+            if (b.p_slots && (rc = open(b.h_slots, (const void **)&p.slots)) != KMAT_OK) return rc;
             p.stash_x = nullptr; p.stash_hit = nullptr; p.pool2 = nullptr;
             if (b.n_stash) { if ((rc = open(b.h_stash_x, (const void **)&p.stash_x)) != KMAT_OK) return rc; if ((rc = open(b.h_stash_hit, (const void **)&p.stash_hit)) != KMAT_OK) return rc; }
             if (b.p_pool2) { if ((rc = open(b.h_pool2, (const void **)&p.pool2)) != KMAT_OK) return rc; }

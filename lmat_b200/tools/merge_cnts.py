@@ -10,8 +10,9 @@ Python 2 arithmetic where the result depends on it:
 Deviations, on purpose: taxids are processed in ascending order (the reference iterates a Python 2 dict, i.e. in hash order;
 the consumer, loadRandHits, read_label.cpp:512-678, keys every line by taxid), and `merge_hack` / the E. coli defaults are
 empty instead of a NameError when taxids 561 / 562 are absent from the data.
-PARITY: unpinned -- no Python 2 interpreter and no fixture of this script exist offline; tests check the structural
-contract (every taxid of the count table gets a line loadRandHits accepts) and the arithmetic above on hand-made cases.
+PARITY: pinned against the reference script itself -- no Python 2 interpreter exists offline, so oracle/py2run.py executes
+/root/reference/bin/merge_cnts.py unmodified with Python 2 division, mixed-type ordering and dict iteration order emulated
+in the AST (tests/golden/make_golden_rollup.py -> tests/golden/rollup/); tests/test_null_rollup_cpu.py compares the lines.
 
 usage: merge_cnts.py <x.rand_lst> <taxonomy> <rank table> <min_obs> <tax_histo counts | missing> <output> <num_bins>
 """

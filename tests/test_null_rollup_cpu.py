@@ -1,7 +1,8 @@
 """CPU: the null-model roll-up (lmat_b200/tools/merge_cnts.py, a Python 3 restatement of the reference's Python 2
-bin/merge_cnts.py -- parity unpinned, see its header) and the gen_rand_mod driver.  Checked here: the Python 2 comparison
-semantics the script depends on, the structural contract of the output (what loadRandHits, read_label.cpp:512-678, needs),
-and that both loaders of this repository -- the oracle's and libkmat's -- accept the generated models."""
+bin/merge_cnts.py) and the gen_rand_mod driver.  Pinned against tests/golden/rollup/: the outputs of the reference script
+itself, executed unmodified under oracle/py2run.py (Python 2 semantics emulated; tests/golden/make_golden_rollup.py).  Also
+checked: the Python 2 comparison semantics the script depends on, the structural contract of the output (what loadRandHits,
+read_label.cpp:512-678, needs), and that both loaders of this repository -- the oracle's and libkmat's -- accept the models."""
 import gzip
 import os
 import stat
@@ -16,6 +17,39 @@ from lmat_b200.tools import gen_rand_mod, merge_cnts
 from oracle import oracle_py as op
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("case,min_obs,thc,inp", [("counts_min2", 2, "counts.txt", "in.rand_lst"), ("counts_min5", 5, "counts.txt", "in.rand_lst"),
+                                                  ("nocounts_min2", 2, "missing.txt", "in.nocounts.rand_lst")])
+def test_rollup_equals_the_reference_script(case, min_obs, thc, inp, tmp_path):
+    """Same lines as /root/reference/bin/merge_cnts.py on the hand-made NCBI-like inputs (E. coli / Shigella defaults,
+    eukaryote genus default, human, "other sequences", plasmid-range ids, bins below min_obs, missing count table).  The
+    reference emits them in Python 2 dict order, this tool in ascending taxid order (documented deviation; the consumer keys
+    every line by taxid), so the bodies are compared as sorted lists."""
+    G = os.path.join(GOLDEN, "rollup")
+    out = str(tmp_path / "out.txt")
+    n = merge_cnts.roll_up(os.path.join(G, inp), os.path.join(G, "tax.dat"), os.path.join(G, "rank.txt"), min_obs, os.path.join(G, thc), out, 10)
+    mine = open(out).read().split("\n")
+    want = open(os.path.join(G, f"out.{case}.txt")).read().split("\n")
+    assert mine[0] == want[0] == "10" and n == len(want) - 2
+    assert sorted(mine[1:]) == sorted(want[1:])
+    if case != "nocounts_min2":
+        assert any(" genus-561 " in ln for ln in want) and any(ln.startswith("32630 ") for ln in want)
+
+
+def test_py2_harness_semantics():
+    """oracle/py2run.py: the three Python 2 behaviours the reference script depends on."""
+    from oracle import py2run
+    assert py2run.py2_div(7, 2) == 3 and py2run.py2_div(-7, 2) == -4 and py2run.py2_div(7.0, 2) == 3.5
+    assert py2run.py2_cmp("Gt", "0.1", 5) and not py2run.py2_cmp("GtE", 0.9, "0.1") and py2run.py2_cmp("Lt", 3, 4) and py2run.py2_cmp("Gt", "b", "a")
+    d = py2run.Py2Dict()
+    for k in range(20, 0, -1):
+        d[k] = k
+    assert d.keys() == list(range(1, 21))                       # small ints land in their own slots of the 32-slot table
+    d = py2run.Py2Dict()
+    for k in (8, 16, 0):
+        d[k] = 1
+    assert d.keys() == [8, 16, 0]                               # all hash to slot 0 of 8: 8 stays, 16 -> slot 1 (i*5+1+perturb), 0 -> later probe
 
 
 def test_python2_mixed_comparisons():
