@@ -848,18 +848,27 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
         for (int c = 0; c < NCH; c++) { const int j = (c << 5) + lane; raw[c] = j < lenA ? (unsigned char)P.bases[offA + j] : (unsigned char)0; }
         { const uint64_t r2 = r + 2 * n_warps; lenB = 0; if (r2 < n) { offB = P.offs[r2]; lenB = (int)(P.offs[r2 + 1] - offB); } }
 
-        // ---- encode every chunk (read_label.cpp:943-950, 978-1009, GC bookkeeping :994-1008); start the bucket gathers
+        // ---- encode every chunk (read_label.cpp:943-950, 978-1009, GC bookkeeping :994-1008).  ONE copy of the chunk body in
+        //      the instruction stream (it is the bulk of the kernel's code and the fully unrolled form stalled on instruction
+        //      fetch, profiles/r02e): the chunk's code is selected into a scalar and its key selected back, so code[] / xk[]
+        //      stay in registers
         uint64_t xk[NCH];                  // table key of the canonical k-mer ending at base j = 32 c + lane
         uint64_t canon_s[STATS ? NCH : 1];
+#pragma unroll
+        for (int c = 0; c < NCH; c++) { xk[c] = 0; if (STATS) canon_s[c] = 0; }
         uint32_t okbits = 0;
         uint64_t prev = 0; uint32_t pinv = 0xFFFFFFFFu, pgc = 0;
         int valid = 0, vgc = 0, vtot = 0;
         uint32_t sp_r[3] = {KM_SLIDE_NONE, KM_SLIDE_NONE, KM_SLIDE_NONE}, sp_l[3] = {KM_SLIDE_NONE, KM_SLIDE_NONE, KM_SLIDE_NONE};
+        const int nch = (len + 31) >> 5;
+#pragma unroll 1
+        for (int c = 0; c < nch; c++) {
+            int code1 = code[0];
 #pragma unroll
-        for (int c = 0; c < NCH; c++) {
-            const uint32_t cinv = __ballot_sync(KM_FULL, code[c] < 0);
-            const uint32_t cgc = __ballot_sync(KM_FULL, code[c] == 1 || code[c] == 2);
-            const uint32_t cc = code[c] < 0 ? 0u : (uint32_t)code[c];
+            for (int q = 1; q < NCH; q++) if (c == q) code1 = code[q];
+            const uint32_t cinv = __ballot_sync(KM_FULL, code1 < 0);
+            const uint32_t cgc = __ballot_sync(KM_FULL, code1 == 1 || code1 == 2);
+            const uint32_t cc = code1 < 0 ? 0u : (uint32_t)code1;
             const uint32_t hi = __reduce_or_sync(KM_FULL, lane < 16 ? cc << (30 - 2 * lane) : 0u);
             const uint32_t lo = __reduce_or_sync(KM_FULL, lane >= 16 ? cc << (62 - 2 * lane) : 0u);
             const uint64_t cur = ((uint64_t)hi << 32) | lo;
@@ -870,8 +879,6 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
             const int wsh = 32 + lane - k + 1;
             const bool ok = ((inv64 >> wsh) & wmask) == 0;
             const bool ok_prev = wsh > 0 && ((inv64 >> (wsh - 1)) & wmask) == 0;
-            xk[c] = 0;
-            if (STATS) canon_s[c] = 0;
             uint32_t sl_kr = 0, sl_kl = 0;
             if (LINE) {                                          // every lane takes part: one hash per base, three doubling steps
                 const uint32_t hh = km_slide_hash(fwd, lm);
@@ -882,14 +889,16 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
                 sl_kl = km_slide_l(l2, km_fetch_left(l2, sp_l[2], lane, sl3), sl3);
                 sp_r[0] = r0; sp_r[1] = r1; sp_r[2] = r2; sp_l[0] = l0; sp_l[1] = l1; sp_l[2] = l2;
             }
+            uint64_t x1 = 0, canon1 = 0;
             if (ok) {
                 const uint64_t rc = km_revcomp(fwd, kmer_bits);
-                const uint64_t canon = fwd < rc ? fwd : rc;                    // read_label.cpp:1009
-                if (LINE) xk[c] = km_line_x_of(canon, km_slide_finish(sl_kr, sl_kl, fwd, fwd < rc, k, lm), k, lm, lb);
-                else xk[c] = km_mix(canon, kmer_bits);
-                if (STATS) canon_s[c] = canon;
+                canon1 = fwd < rc ? fwd : rc;                                  // read_label.cpp:1009
+                if (LINE) x1 = km_line_x_of(canon1, km_slide_finish(sl_kr, sl_kl, fwd, fwd < rc, k, lm), k, lm, lb);
+                else x1 = km_mix(canon1, kmer_bits);
                 okbits |= 1u << c;
             }
+#pragma unroll
+            for (int q = 0; q < NCH; q++) if (c == q) { xk[q] = x1; if (STATS) canon_s[q] = canon1; }
             const int add_tot = ok ? (ok_prev ? 1 : k) : 0;
             const int add_gc = ok ? (ok_prev ? (int)((cgc >> lane) & 1) : __popcll((gc64 >> wsh) & wmask)) : 0;
             valid += ok; vtot += add_tot; vgc += add_gc;
@@ -905,25 +914,31 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
                 if ((old >> (h & 31)) & 1) suspect |= 1u << c; else first |= 1u << c;
             }
         }
+        if (__any_sync(KM_FULL, suspect != 0)) {
+#pragma unroll 1
+            for (int c = 0; c < nch; c++) {
+                uint32_t pend = __ballot_sync(KM_FULL, (suspect >> c) & 1);
+                if (!pend) continue;
+                uint64_t xc = xk[0];
 #pragma unroll
-        for (int c = 0; c < NCH; c++) {
-            uint32_t pend = __ballot_sync(KM_FULL, (suspect >> c) & 1);
-            while (pend) {                                        // rare: ~ (k-mers per read)^2 / (2 SETN) suspects per read
-                const int src = __ffs(pend) - 1;
-                pend &= pend - 1;
-                const uint64_t key = kb_shfl_u64(xk[c], src);
-                const int ps = (c << 5) + src;                    // the suspect's position index (base index of its last base)
-                bool lower = false;
+                for (int q = 1; q < NCH; q++) if (c == q) xc = xk[q];
+                while (pend) {                                        // rare: ~ (k-mers per read)^2 / (2 SETN) suspects per read
+                    const int src = __ffs(pend) - 1;
+                    pend &= pend - 1;
+                    const uint64_t key = kb_shfl_u64(xc, src);
+                    const int ps = (c << 5) + src;                    // the suspect's position index (base index of its last base)
+                    bool lower = false;
 #pragma unroll
-                for (int c2 = 0; c2 < NCH; c2++) {
-                    if (((okbits >> c2) & 1) && xk[c2] == key) {
-                        const int pq = (c2 << 5) + lane;
-                        if (pq < ps) lower = true;
-                        else if (pq > ps) first &= ~(1u << c2);    // a later copy of the suspect's k-mer is never the first
+                    for (int c2 = 0; c2 < NCH; c2++) {
+                        if (((okbits >> c2) & 1) && xk[c2] == key) {
+                            const int pq = (c2 << 5) + lane;
+                            if (pq < ps) lower = true;
+                            else if (pq > ps) first &= ~(1u << c2);    // a later copy of the suspect's k-mer is never the first
+                        }
                     }
+                    const bool dup = __any_sync(KM_FULL, lower);
+                    if (lane == src && !dup) first |= 1u << c;
                 }
-                const bool dup = __any_sync(KM_FULL, lower);
-                if (lane == src && !dup) first |= 1u << c;
             }
         }
         // the words this lane touched go back to zero for the next read (every set bit lies in such a word)
@@ -933,6 +948,9 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
         //      looked at (NCH independent LDG.256 per lane in flight), then one hit word per k-mer start position
         uint64_t bk[NCH][4];
         uint32_t owner[PEERS ? NCH : 1];
+        uint32_t hwv[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; c++) hwv[c] = ((first >> c) & 1) ? KM_HIT_MISS : KM_HIT_INVALID;
         if (P.do_probe) {
 #pragma unroll
             for (int c = 0; c < NCH; c++) {
@@ -944,34 +962,61 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
                     else km_load_bucket(P.db.slots + ((xk[c] >> P.db.rem_bits) & P.db.bucket_mask) * KM_SLOTS_PER_BUCKET, bk[c][0], bk[c][1], bk[c][2], bk[c][3]);
                 }
             }
-        }
+            uint32_t more = 0;                 // lookups that have to go on: a flagged sector (second level) / a full home bucket
+            uint32_t st_x = 0;
 #pragma unroll
-        for (int c = 0; c < NCH; c++) {
-            const int j = (c << 5) + lane, p = j - k + 1;
-            uint32_t hw = KM_HIT_INVALID;
-            if ((first >> c) & 1) {
-                hw = KM_HIT_MISS;
-                if (P.do_probe) {
-                    uint32_t extra = 0;
+            for (int c = 0; c < NCH; c++) {
+                if ((first >> c) & 1) {
+                    uint32_t hw = KM_HIT_MISS, extra = 0;
                     if (PEERS) hw = km_first_finish(P.db, xk[c], owner[c], bk[c][0], bk[c][1], bk[c][2], bk[c][3], extra);
-                    else if (LINE) {
-                        if (km_sector_match(bk[c][0], bk[c][1], bk[c][2], bk[c][3], xk[c] & ((1ull << KM_MZR_KEY_BITS) - 1), hw) == 2) hw = km_probe_x(P.db, xk[c], extra, 1);
-                    } else if (km_bucket_match(bk[c][0], bk[c][1], bk[c][2], bk[c][3], xk[c] & ((1ull << P.db.rem_bits) - 1), 0, hw) == 2) {
-                        hw = km_probe_x(P.db, xk[c], extra, 1);
-                        extra++;
+                    else if (LINE) { if (km_sector_match(bk[c][0], bk[c][1], bk[c][2], bk[c][3], xk[c] & ((1ull << KM_MZR_KEY_BITS) - 1), hw) == 2) more |= 1u << c; }
+                    else if (km_bucket_match(bk[c][0], bk[c][1], bk[c][2], bk[c][3], xk[c] & ((1ull << P.db.rem_bits) - 1), 0, hw) == 2) more |= 1u << c;
+                    hwv[c] = hw; st_x += extra;
+                }
+            }
+            // the rare continuations of the whole read together: their loads are issued back to back by the lanes that need
+            // them instead of one dependent chain per chunk with one or two lanes active (9 % of the stall samples before)
+            if (!PEERS && __any_sync(KM_FULL, more != 0)) {
+                if (LINE) {
+#pragma unroll
+                    for (int c = 0; c < NCH; c++) {
+                        if ((more >> c) & 1) {
+                            xk[c] = km_mix(km_line_kmer_of(xk[c], k, lm, lb), kmer_bits);         // the second level is addressed by the mixed k-mer
+                            if (P.db.slots) km_load_bucket(P.db.slots + ((xk[c] >> P.db.rem_bits) & P.db.bucket_mask) * KM_SLOTS_PER_BUCKET, bk[c][0], bk[c][1], bk[c][2], bk[c][3]);
+                            else bk[c][0] = bk[c][1] = bk[c][2] = bk[c][3] = 0;
+                        }
                     }
-                    if (STATS) {
-                        st_lookups++; st_extra += extra;
-                        if (hw != KM_HIT_MISS) { st_hits++; if (hw & KM_HIT_LIST) st_lists++; }
+                }
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {
+                    if ((more >> c) & 1) {
+                        uint32_t hw = KM_HIT_MISS, extra = 1;
+                        if (LINE) { if (km_bucket_match(bk[c][0], bk[c][1], bk[c][2], bk[c][3], xk[c] & ((1ull << P.db.rem_bits) - 1), 0, hw) == 2) { uint32_t e2 = 0; hw = km_probe_buckets(P.db, xk[c], 0u, e2, 1); extra += 1 + e2; } }
+                        else { uint32_t e2 = 0; hw = km_probe_buckets(P.db, xk[c], 0u, e2, 1); extra += e2; }
+                        hwv[c] = hw; st_x += extra;
+                    }
+                }
+            }
+            if (STATS) {
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {
+                    if ((first >> c) & 1) {
+                        st_lookups++;
+                        if (hwv[c] != KM_HIT_MISS) { st_hits++; if (hwv[c] & KM_HIT_LIST) st_lists++; }
                         else if (P.db.prefix_bits) {
                             const uint64_t pf = canon_s[c] >> P.db.prefix_shift;
                             if (!((P.db.prefix_bits[pf >> 5] >> (pf & 31)) & 1)) st_pmiss++;
                         }
                     }
                 }
+                st_extra += st_x;
             }
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const int j = (c << 5) + lane, p = j - k + 1;
             if (p >= 0 && j < len) {
-                P.hit[off + p] = hw;
+                P.hit[off + p] = hwv[c];
                 if (P.xq && ((first >> c) & 1)) P.xq[off + p] = xk[c];
             }
         }

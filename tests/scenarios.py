@@ -191,3 +191,48 @@ def content_summ_args(run: dict, P: dict, files: dict, ofbase: str) -> list:
     if run["threshold"] is not None:
         a += ["-v", str(run["threshold"])]
     return a + ["-o", ofbase]
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs[0] ("c1"): the reference's bundled data.  DB: the five adenovirus genomes of
+# src/kmerdb/examples/tests/data/test.fa under a small hand-made taxonomy (the tarball ships no DB); reads: the 1000 real
+# reads of example/example.tgz (simple_list.1000.fna: headers with spaces, 80-column wrapped lines, 60-250 bases) and 400
+# reads simulated from the genomes.  The table dump and both read files are committed under tests/golden/ (made by
+# tests/golden/make_golden_c1.py from the reference tree); this function only writes the seeded text inputs.
+# ------------------------------------------------------------------------------------------------
+C1_GENOME_TIDS = (1001, 1002, 1003, 1004, 1005)
+
+
+def c1_taxonomy():
+    tax = fx.Taxonomy()
+    tax.add(1, 1, "no rank", "root")
+    tax.add(10, 1, "superkingdom", "Viruses")
+    tax.add(100, 10, "family", "Adenoviridae")
+    tax.add(101, 100, "genus", "Mastadenovirus")
+    tax.add(102, 100, "genus", "Atadenovirus")
+    tax.add(201, 101, "species", "Human mastadenovirus C")
+    tax.add(1001, 101, "species", "Human adenovirus 52")
+    tax.add(1002, 101, "species", "Simian adenovirus 7")
+    tax.add(1003, 201, "strain", "Human adenovirus C serotype 5")
+    tax.add(1004, 101, "species", "Porcine adenovirus 3")
+    tax.add(1005, 102, "species", "Snake adenovirus")
+    tax.leaves = list(C1_GENOME_TIDS)
+    return tax
+
+
+def build_c1_inputs(workdir: str) -> dict:
+    import gzip
+    import shutil
+    os.makedirs(workdir, exist_ok=True)
+    tax = c1_taxonomy()
+    paths = fx.write_taxonomy_files(tax, workdir)
+    paths["null_lst"] = fx.write_null_models(1007, tax, workdir)
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for key, name in (("reads_example", "c1.reads_example.fna"), ("reads_sim", "c1.reads_sim.fa")):
+        paths[key] = os.path.join(workdir, name)
+        src = os.path.join(golden, name + ".gz")
+        if os.path.exists(src):
+            with gzip.open(src, "rb") as f, open(paths[key], "wb") as o:
+                shutil.copyfileobj(f, o)
+    paths["workdir"] = workdir
+    return dict(paths=paths, tax=tax)
