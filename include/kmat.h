@@ -189,6 +189,32 @@ int kmat_label_batch(kmat_ctx *, const char *bases, const uint64_t *offs, uint32
                      kmat_pair *cands, uint64_t cands_cap, uint64_t *n_cands,
                      kmat_pair *lineage, uint64_t lineage_cap, uint64_t *n_lineage);
 
+/* ---- compact interface: 2-bit packed reads in, 32-byte results out ------------------------------------------------
+ * Same labels as kmat_label_batch with a third of the bytes on the PCIe / host-memory path (46 B instead of 158 B in and
+ * 32 B + one pair list instead of 64 B + lists out per 150-base read): what the parallel reader hands to a GPU worker and
+ * what bench.py's end-to-end leg measures.
+ *   codes    : 2 bits per base (a/A 0, c/C 1, g/G 2, t/T 3: the ENCODE macro, read_label.cpp:943-950) indexed by the
+ *              base's GLOBAL offset in the batch: word w holds bases 16 w .. 16 w + 15, base i in bits 2 (i % 16)..+1
+ *   inv_pos  : ascending offsets of the bases that are none of those eight characters (they reset the k-mer run)
+ *   offs     : as for kmat_label_batch (n_reads + 1 base offsets)
+ * kmat_pack_reads produces codes / inv_pos from ASCII on `threads` host threads (codes: kmat_pack_words(total) words;
+ * KMAT_ERR_OVERFLOW with *n_inv = the count needed when inv_cap is too small). */
+typedef struct {
+    uint32_t tid; float score, log_avg, stdev;
+    uint32_t list_off;       /* first pair of this read's list in `list`                                             */
+    uint16_t n_list;         /* rank_label (ctx with want_lineage == 0: the -p line) or valid_cand (want_lineage == 1)  */
+    uint16_t valid_kmers, cand_kmer_cnt;
+    uint16_t flags;          /* status | match << 3 | bin_sel << 6 | (-err) << 10                                     */
+    uint32_t n_cand;
+} kmat_read_result32;
+uint64_t kmat_pack_words(uint64_t total_bases);
+int kmat_pack_reads(const char *bases, uint64_t total_bases, int threads, uint32_t *codes, uint64_t *inv_pos, uint64_t inv_cap, uint64_t *n_inv);
+int kmat_label_batch_packed(kmat_ctx *, const uint32_t *codes, const uint64_t *inv_pos, uint64_t n_inv, const uint64_t *offs, uint32_t n_reads,
+                            kmat_read_result32 *out, kmat_pair *list, uint64_t list_cap, uint64_t *n_list);
+/* 32-byte record -> the 64-byte one kmat_format_tail / kmat_tally_class take (the two integers of the ReadTooShort /
+ * NoDbHits lines are the read's length, k and -j: read_label.cpp:1217-1218, 1232-1233, 1270-1271) */
+void kmat_result_expand(const kmat_read_result32 *in, uint32_t read_len, int kmer_length, int min_kmer, int want_lineage, kmat_read_result *out);
+
 /* ---- DB-sharded mode (SURVEY.md 8(e) mode B: table partitioned by kmat_shard_of over n_shards ranks) ---------------
  * One pass over a batch = three device phases around two exchange steps that the CALLER performs (NCCL all-to-all
  * between one-process-per-GPU ranks -- lmat_b200/sharded.py over torch.distributed -- or peer copies in one process).

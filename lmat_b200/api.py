@@ -21,6 +21,8 @@ RESULT_DTYPE = np.dtype([("status", "<i4"), ("n1", "<i4"), ("n2", "<i4"), ("vali
                          ("log_avg", "<f4"), ("stdev", "<f4"), ("n_cand", "<u4"), ("n_lin", "<u4"),
                          ("cand_off", "<u8"), ("lin_off", "<u8"), ("bin_sel", "<i4"), ("err", "<i4")])
 PAIR_DTYPE = np.dtype([("tid", "<u4"), ("score", "<f4")])
+RESULT32_DTYPE = np.dtype([("tid", "<u4"), ("score", "<f4"), ("log_avg", "<f4"), ("stdev", "<f4"), ("list_off", "<u4"), ("n_list", "<u2"),
+                           ("valid_kmers", "<u2"), ("cand_kmer_cnt", "<u2"), ("flags", "<u2"), ("n_cand", "<u4")])
 GENE_DTYPE = np.dtype([("status", "<i4"), ("valid_kmers", "<u4"), ("n_genes", "<u4"), ("gene", "<u4"), ("count", "<u4"), ("score", "<f4")])
 
 
@@ -48,6 +50,7 @@ EXPORTS = [
     "kmat_shard_of", "kmat_db_size", "kmat_db_bytes", "kmat_db_overflow", "kmat_db_kmer_length", "kmat_db_device", "kmat_db_free",
     "kmat_lookup_batch", "kmat_encode_batch", "kmat_inputs_load", "kmat_inputs_free", "kmat_opts_default",
     "kmat_ctx_create", "kmat_ctx_set_opts", "kmat_ctx_destroy", "kmat_label_batch", "kmat_label_batch_device",
+    "kmat_pack_words", "kmat_pack_reads", "kmat_label_batch_packed", "kmat_result_expand",
     "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_set_pipeline", "kmat_gene_batch", "kmat_shard_encode", "kmat_shard_serve", "kmat_shard_finish", "kmat_ctx_device_results", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench", "kmat_gather_bench_peer",
     "kmat_set_l2_fetch_granularity", "kmat_reader_open", "kmat_reader_open_mt", "kmat_reader_close", "kmat_read_batch_new", "kmat_read_batch_free",
     "kmat_reader_next", "kmat_read_batch_view", "kmat_tally_class", "kmat_host_alloc", "kmat_host_free",
@@ -103,6 +106,12 @@ def lib():
     L.kmat_ctx_destroy.argtypes = [vp]
     L.kmat_label_batch.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, C.POINTER(C.c_uint64), vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.kmat_label_batch_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, vp, vp]
+    L.kmat_pack_words.restype = C.c_uint64
+    L.kmat_pack_words.argtypes = [C.c_uint64]
+    L.kmat_pack_reads.argtypes = [vp, C.c_uint64, C.c_int, vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.kmat_label_batch_packed.argtypes = [vp, vp, vp, C.c_uint64, vp, C.c_uint32, vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.kmat_result_expand.restype = None
+    L.kmat_result_expand.argtypes = [vp, C.c_uint32, C.c_int, C.c_int, C.c_int, vp]
     L.kmat_ctx_sync.argtypes = [vp]
     L.kmat_ctx_last_stats.argtypes = [vp, C.POINTER(BatchStats)]
     L.kmat_ctx_set_stats.argtypes = [vp, C.c_int]
@@ -374,6 +383,42 @@ class Ctx:
                 continue
             _check(rc)
             return res, cands[:n_c.value], lin[:n_l.value]
+
+    def label_packed(self, seqs=None, blob=None, offs=None, threads=4):
+        """The compact interface: kmat_pack_reads on the host, kmat_label_batch_packed, 32-byte results expanded back to the
+        64-byte records (so that tails() applies).  Returns (results, candidates, lineage) like label()."""
+        if seqs is not None:
+            blob, offs = pack_reads(seqs)
+        n = len(offs) - 1
+        total = int(offs[n])
+        ptr = blob if isinstance(blob, (bytes, bytearray)) else blob.ctypes.data
+        codes = np.zeros(max(1, lib().kmat_pack_words(total)), dtype=np.uint32)
+        n_inv = C.c_uint64()
+        inv = np.zeros(1024, dtype=np.uint64)
+        rc = lib().kmat_pack_reads(ptr, total, threads, codes.ctypes.data, inv.ctypes.data, len(inv), C.byref(n_inv))
+        if rc == -10:
+            inv = np.zeros(n_inv.value, dtype=np.uint64)
+            rc = lib().kmat_pack_reads(ptr, total, threads, codes.ctypes.data, inv.ctypes.data, len(inv), C.byref(n_inv))
+        _check(rc)
+        res32 = np.zeros(n, dtype=RESULT32_DTYPE)
+        cap = max(4096, 32 * n)
+        n_l = C.c_uint64()
+        while True:
+            lst = np.zeros(cap, dtype=PAIR_DTYPE)
+            rc = lib().kmat_label_batch_packed(self.h, codes.ctypes.data, inv.ctypes.data, n_inv.value, offs.ctypes.data, n, res32.ctypes.data,
+                                               lst.ctypes.data, len(lst), C.byref(n_l))
+            if rc == -10:
+                cap = int(n_l.value) + 16
+                continue
+            _check(rc)
+            break
+        res = np.zeros(n, dtype=RESULT_DTYPE)
+        k = self.db.kmer_length
+        for i in range(n):
+            lib().kmat_result_expand(res32[i:i + 1].ctypes.data, int(offs[i + 1] - offs[i]), k, self.opts.min_kmer, self.opts.want_lineage, res[i:i + 1].ctypes.data)
+        lst = lst[:n_l.value]
+        empty = np.zeros(0, dtype=PAIR_DTYPE)
+        return (res, empty, lst) if self.opts.want_lineage else (res, lst, empty)
 
     def tails(self, res, cands, lin, prn_all=True):
         out = []

@@ -16,6 +16,7 @@
 #include <fstream>
 #include <map>
 #include <sstream>
+#include <thread>
 #include <unordered_map>
 
 #include "kmat_internal.h"
@@ -739,5 +740,48 @@ extern "C" int kmat_null_write(const char *path, int n_sets, const uint32_t *con
         if (fwrite(buf, 1, (size_t)(p - buf), f) != (size_t)(p - buf)) { fclose(f); kmat_set_error("write to %s failed", path); return KMAT_ERR_IO; }
     }
     if (fclose(f) != 0) { kmat_set_error("write to %s failed", path); return KMAT_ERR_IO; }
+    return KMAT_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// compact interface, host side: ASCII -> 2-bit code words + positions of the invalid bases (include/kmat.h)
+// ---------------------------------------------------------------------------------------------
+extern "C" uint64_t kmat_pack_words(uint64_t total_bases) { return (total_bases + 15) / 16; }
+extern "C" int kmat_pack_reads(const char *bases, uint64_t total_bases, int threads, uint32_t *codes, uint64_t *inv_pos, uint64_t inv_cap, uint64_t *n_inv) {
+    if ((total_bases && (!bases || !codes)) || !n_inv) { kmat_set_error("kmat_pack_reads: bad argument"); return KMAT_ERR_ARG; }
+    static const std::vector<uint8_t> lut = [] {                       // ENCODE (read_label.cpp:943-950): everything else is 4 = invalid
+        std::vector<uint8_t> t(256, 4);
+        t['a'] = t['A'] = 0; t['c'] = t['C'] = 1; t['g'] = t['G'] = 2; t['t'] = t['T'] = 3;
+        return t; }();
+    const uint64_t n_words = kmat_pack_words(total_bases);
+    if (threads < 1) threads = 1;
+    threads = (int)std::min<uint64_t>((uint64_t)threads, std::max<uint64_t>(1, n_words / 4096));
+    std::vector<std::vector<uint64_t>> inv((size_t)threads);
+    auto work = [&](int t) {
+        const uint64_t w0 = n_words * (uint64_t)t / (uint64_t)threads, w1 = n_words * (uint64_t)(t + 1) / (uint64_t)threads;
+        const uint8_t *L = lut.data();
+        for (uint64_t w = w0; w < w1; w++) {
+            const uint64_t b0 = w * 16, nb = std::min<uint64_t>(16, total_bases - b0);
+            uint32_t v = 0;
+            for (uint64_t i = 0; i < nb; i++) {
+                const uint8_t c = L[(uint8_t)bases[b0 + i]];
+                if (c > 3) inv[(size_t)t].push_back(b0 + i); else v |= (uint32_t)c << (2 * i);
+            }
+            codes[w] = v;
+        }
+    };
+    if (threads == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < threads; t++) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+    }
+    uint64_t total = 0;
+    for (auto &v : inv) total += v.size();
+    *n_inv = total;
+    if (total > inv_cap || (total && !inv_pos)) { kmat_set_error("kmat_pack_reads: %llu invalid bases, room for %llu", (unsigned long long)total, (unsigned long long)inv_cap); return KMAT_ERR_OVERFLOW; }
+    uint64_t at = 0;
+    for (auto &v : inv) { if (!v.empty()) memcpy(inv_pos + at, v.data(), v.size() * 8); at += v.size(); }
     return KMAT_OK;
 }

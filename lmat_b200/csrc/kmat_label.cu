@@ -1158,6 +1158,9 @@ struct kmat_ctx {
     struct Slot {
         char *d_bases = nullptr; uint64_t cap_bases = 0;
         uint64_t *d_offs = nullptr; kmat_read_result *d_out = nullptr; uint32_t cap_reads = 0;
+        uint32_t *d_codes = nullptr; uint64_t cap_codes = 0;      // compact interface: the chunk's 2-bit code words ...
+        uint64_t *d_inv = nullptr; uint64_t cap_inv = 0;          // ... and the positions of its non-ACGT bases
+        kmat_read_result32 *d_out32 = nullptr;                    // ... and its 32-byte results (cap_reads entries)
         unsigned long long *h_cur = nullptr;       // pinned: cursors after this slot's chunk
         cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
     } slot[2];
@@ -1318,7 +1321,7 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
     cudaFree(c->d_nodeA); cudaFree(c->d_nodeB); cudaFree(c->d_paths); cudaFree(c->d_prune); cudaFree(c->d_sid2nid);
     cudaFree(c->d_model_of_cand); cudaFree(c->d_mrow); cudaFree(c->d_cut); cudaFree(c->d_cls);
     for (auto &sl : c->slot) {
-        cudaFree(sl.d_bases); cudaFree(sl.d_offs); cudaFree(sl.d_out); cudaFreeHost(sl.h_cur);
+        cudaFree(sl.d_bases); cudaFree(sl.d_offs); cudaFree(sl.d_out); cudaFree(sl.d_codes); cudaFree(sl.d_inv); cudaFree(sl.d_out32); cudaFreeHost(sl.h_cur);
         if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
         if (sl.ev_comp) cudaEventDestroy(sl.ev_comp);
         if (sl.ev_d2h) cudaEventDestroy(sl.ev_d2h);
@@ -1505,7 +1508,12 @@ static int km_run_device(kmat_ctx *c, const KmPass &L, cudaStream_t st) {
     int S = c->pipeline;
     if (S < 0) S = (variant == 0 && L.n_reads >= (1u << 19)) ? 8 : 1;
     if (variant != 0 || S < 1 || c->d_peers) S = 1;
-    if (c->d_peers && !c->d_pool2_all && (rc = km_peer_prepare(c, L, st)) != KMAT_OK) return rc;
+    if (c->d_peers && !c->d_pool2_all) {
+        if ((rc = km_peer_prepare(c, L, st)) != KMAT_OK) return rc;
+        // km_peer_fetch_kernel walks EVERY hit word of the pass; the last k - 1 positions of a read are never written by the
+        // probe kernel and would otherwise hold stale words of an earlier pass (with owner tags of another shard count)
+        KM_CUDA(cudaMemsetAsync(hit, 0xFF, (size_t)L.total_bases * 4, st));
+    }
     if (S > 16) S = 16;
     const bool piped = S > 1;
     KM_CUDA(cudaEventRecord(c->ev[0], st));
@@ -1657,14 +1665,74 @@ extern "C" int kmat_ctx_last_stats(kmat_ctx *c, kmat_batch_stats *out) {
     return KMAT_OK;
 }
 
+// ---- compact interface: 2-bit packed reads in, 32-byte results out (kmat_label_batch_packed) --------------------------
+// One thread per code word: 16 bases -> 16 ASCII bytes, stored as one 16-byte vector.  The chunk's byte buffer starts at a
+// multiple of 16 bases, so word w of the chunk is bytes [16 w, 16 w + 16).
+__global__ void __launch_bounds__(256) km_unpack_kernel(const uint32_t *__restrict__ codes, uint64_t n_words, uint4 *out) {
+    const uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    const uint32_t c = codes[w];
+    uint32_t q[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) v |= ((0x54474341u >> (8 * ((c >> (2 * (4 * i + j))) & 3u))) & 0xFFu) << (8 * j);     // "ACGT"[code]
+        q[i] = v;
+    }
+    out[w] = make_uint4(q[0], q[1], q[2], q[3]);
+}
+__global__ void __launch_bounds__(256) km_unpack_inv_kernel(const uint64_t *__restrict__ inv, uint64_t n_inv, uint64_t base0, char *out) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n_inv) out[inv[i] - base0] = 'N';                      // any byte outside ACGTacgt resets the k-mer run (read_label.cpp:943-950)
+}
+// 64-byte internal results -> the 32-byte records of the compact interface
+__global__ void __launch_bounds__(256) km_compact_kernel(const kmat_read_result *__restrict__ in, uint32_t n, int want_lineage, kmat_read_result32 *out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const kmat_read_result r = in[i];
+    kmat_read_result32 o;
+    o.tid = r.tid; o.score = r.score; o.log_avg = r.log_avg; o.stdev = r.stdev;
+    o.list_off = (uint32_t)(want_lineage ? r.lin_off : r.cand_off);
+    o.n_list = (uint16_t)min(want_lineage ? r.n_lin : r.n_cand, 0xFFFFu);
+    o.valid_kmers = (uint16_t)min(max(r.valid_kmers, 0), 0xFFFF);
+    o.cand_kmer_cnt = (uint16_t)r.cand_kmer_cnt;
+    o.flags = (uint16_t)((r.status & 7) | ((r.match & 7) << 3) | ((r.bin_sel & 15) << 6) | (((-r.err) & 63) << 10));
+    o.n_cand = r.n_cand;
+    out[i] = o;
+}
+extern "C" void kmat_result_expand(const kmat_read_result32 *in, uint32_t read_len, int kmer_length, int min_kmer, int want_lineage, kmat_read_result *out) {
+    memset(out, 0, sizeof *out);
+    out->status = in->flags & 7; out->match = (in->flags >> 3) & 7; out->bin_sel = (in->flags >> 6) & 15; out->err = -(int32_t)((in->flags >> 10) & 63);
+    out->tid = in->tid; out->score = in->score; out->log_avg = in->log_avg; out->stdev = in->stdev;
+    out->valid_kmers = in->valid_kmers; out->cand_kmer_cnt = in->cand_kmer_cnt; out->n_cand = in->n_cand;
+    if (want_lineage) { out->n_lin = in->n_list; out->lin_off = in->list_off; } else { out->n_cand = in->n_list; out->cand_off = in->list_off; }
+    // the two integers of the ReadTooShort / NoDbHits lines (read_label.cpp:1217-1218, 1232-1233, 1270-1271)
+    if (out->status == KMAT_ST_SHORT_LEN) { out->n1 = (int32_t)read_len; out->n2 = kmer_length; out->valid_kmers = 0; }
+    else if (out->status == KMAT_ST_SHORT_VALID) { out->n1 = out->valid_kmers; out->n2 = min_kmer; }
+    else if (out->status == KMAT_ST_NODBHITS) { out->n1 = (int32_t)read_len; out->n2 = kmer_length; }
+}
+
 // Host buffers in, host buffers out.  The batch is cut into chunks; chunk i's kernels (one stream, in order, so the
 // candidate records of a chunk are contiguous behind one running cursor) overlap the H2D copy of chunk i+1 and the
 // D2H copy of chunk i-1 on two copy streams.  Pinned caller buffers (kmat_host_alloc) make those copies truly
 // asynchronous; pageable ones are staged by the driver and still overlap the kernels.
-extern "C" int kmat_label_batch(kmat_ctx *c, const char *bases, const uint64_t *offs, uint32_t n_reads, kmat_read_result *out,
-                                kmat_pair *cands, uint64_t cands_cap, uint64_t *n_cands, kmat_pair *lineage, uint64_t lineage_cap,
-                                uint64_t *n_lineage) {
-    if (!c || !offs || !out || (n_reads && !bases)) { kmat_set_error("kmat_label_batch: bad argument"); return KMAT_ERR_ARG; }
+// Two front ends share it: ASCII reads + 64-byte results (kmat_label_batch), and the compact interface -- 2-bit packed reads
+// (unpacked on the device: the kernels read the same byte buffer either way) + 32-byte results carrying ONE pair list.
+struct KmHostIO {
+    const char *bases = nullptr;                                        // ASCII front end
+    const uint32_t *codes = nullptr; const uint64_t *inv = nullptr; uint64_t n_inv = 0;      // compact front end
+    kmat_read_result *out = nullptr; kmat_read_result32 *out32 = nullptr;
+    kmat_pair *cands = nullptr; uint64_t cands_cap = 0; uint64_t *n_cands = nullptr;
+    kmat_pair *lineage = nullptr; uint64_t lineage_cap = 0; uint64_t *n_lineage = nullptr;
+};
+static int km_label_host(kmat_ctx *c, const KmHostIO &io, const uint64_t *offs, uint32_t n_reads) {
+    const char *bases = io.bases;
+    kmat_read_result *out = io.out;
+    kmat_pair *cands = io.cands, *lineage = io.lineage;
+    const uint64_t cands_cap = io.cands_cap, lineage_cap = io.lineage_cap;
+    uint64_t *n_cands = io.n_cands, *n_lineage = io.n_lineage;
+    const bool compact = io.codes != nullptr;
     if (c->opt.rkmer_mode) { kmat_set_error("kmat_label_batch: the ctx was created with rkmer_mode (kmat_null_* only)"); return KMAT_ERR_ARG; }
     if (c->db->shard_count > 1 && !c->d_peers) { kmat_set_error("kmat_label_batch: the table is shard %d of %d; attach the peers (kmat_ctx_peer_attach) or use the kmat_shard_* rounds", c->db->shard_index, c->db->shard_count); return KMAT_ERR_ARG; }
     if (n_cands) *n_cands = 0;
@@ -1682,7 +1750,8 @@ extern "C" int kmat_label_batch(kmat_ctx *c, const char *bases, const uint64_t *
             kmat_ctx::Slot &sl = c->slot[ch.slot];
             KM_CUDA(cudaEventSynchronize(sl.ev_comp));
             const unsigned long long cur_c = std::min<unsigned long long>(sl.h_cur[0], c->cap_cands), cur_l = std::min<unsigned long long>(sl.h_cur[1], c->cap_lin);
-            KM_CUDA(cudaMemcpyAsync(out + ch.r0, sl.d_out, (size_t)(ch.r1 - ch.r0) * sizeof(kmat_read_result), cudaMemcpyDeviceToHost, c->st_d2h));
+            if (compact) KM_CUDA(cudaMemcpyAsync(io.out32 + ch.r0, sl.d_out32, (size_t)(ch.r1 - ch.r0) * sizeof(kmat_read_result32), cudaMemcpyDeviceToHost, c->st_d2h));
+            else KM_CUDA(cudaMemcpyAsync(out + ch.r0, sl.d_out, (size_t)(ch.r1 - ch.r0) * sizeof(kmat_read_result), cudaMemcpyDeviceToHost, c->st_d2h));
             if (cands && cur_c > done_c && done_c < cands_cap) {
                 const unsigned long long hi = std::min<unsigned long long>(cur_c, cands_cap);
                 KM_CUDA(cudaMemcpyAsync(cands + done_c, c->d_cands + done_c, (size_t)(hi - done_c) * sizeof(kmat_pair), cudaMemcpyDeviceToHost, c->st_d2h));
@@ -1708,31 +1777,59 @@ extern "C" int kmat_label_batch(kmat_ctx *c, const char *bases, const uint64_t *
             }
             const uint32_t n = r1 - r0;
             const uint64_t nb = offs[r1] - offs[r0];
+            // compact front end: the chunk's byte buffer covers whole code words, i.e. starts at base 16 * w0
+            const uint64_t w0 = offs[r0] / 16, w1 = (offs[r1] + 15) / 16, base0 = compact ? w0 * 16 : offs[r0];
+            const uint64_t need_b = compact ? (w1 - w0) * 16 : nb;
             uint32_t max_len = 0;
             for (uint32_t r = r0; r < r1; r++) max_len = std::max<uint32_t>(max_len, (uint32_t)(offs[r + 1] - offs[r]));
             kmat_ctx::Slot &sl = c->slot[ci & 1];
-            if (nb + 1 > sl.cap_bases || n + 1 > sl.cap_reads) {
+            if (need_b + 1 > sl.cap_bases || n + 1 > sl.cap_reads || (compact && ((w1 - w0) > sl.cap_codes || !sl.d_out32))) {
                 // growing a slot: everything queued on it must have finished
                 KM_CUDA(cudaStreamSynchronize(c->st_h2d)); KM_CUDA(cudaStreamSynchronize(c->stream)); KM_CUDA(cudaStreamSynchronize(c->st_d2h));
-                if (nb + 1 > sl.cap_bases) { if ((rc = km_grow(&sl.d_bases, &sl.cap_bases, nb + 1)) != KMAT_OK) return rc; }
-                if (n + 1 > sl.cap_reads) {
-                    cudaFree(sl.d_offs); cudaFree(sl.d_out); sl.d_offs = nullptr; sl.d_out = nullptr;
-                    const size_t cap = (size_t)n + n / 4 + 64;
+                if (need_b + 1 > sl.cap_bases) { if ((rc = km_grow(&sl.d_bases, &sl.cap_bases, need_b + 1)) != KMAT_OK) return rc; }
+                if (compact && (w1 - w0) > sl.cap_codes) { if ((rc = km_grow(&sl.d_codes, &sl.cap_codes, w1 - w0)) != KMAT_OK) return rc; }
+                if (n + 1 > sl.cap_reads || (compact && !sl.d_out32)) {
+                    cudaFree(sl.d_offs); cudaFree(sl.d_out); cudaFree(sl.d_out32); sl.d_offs = nullptr; sl.d_out = nullptr; sl.d_out32 = nullptr;
+                    const size_t cap = std::max<size_t>((size_t)n + n / 4 + 64, sl.cap_reads);
                     KM_CUDA(cudaMalloc((void **)&sl.d_offs, (cap + 1) * 8));
                     KM_CUDA(cudaMalloc((void **)&sl.d_out, cap * sizeof(kmat_read_result)));
+                    if (compact) KM_CUDA(cudaMalloc((void **)&sl.d_out32, cap * sizeof(kmat_read_result32)));
                     sl.cap_reads = (uint32_t)cap;
+                }
+            }
+            uint64_t i_lo = 0, i_hi = 0;
+            if (compact && io.n_inv) {
+                i_lo = (uint64_t)(std::lower_bound(io.inv, io.inv + io.n_inv, offs[r0]) - io.inv);
+                i_hi = (uint64_t)(std::lower_bound(io.inv, io.inv + io.n_inv, offs[r1]) - io.inv);
+                if (i_hi - i_lo > sl.cap_inv) {
+                    KM_CUDA(cudaStreamSynchronize(c->st_h2d)); KM_CUDA(cudaStreamSynchronize(c->stream));
+                    if ((rc = km_grow(&sl.d_inv, &sl.cap_inv, i_hi - i_lo)) != KMAT_OK) return rc;
                 }
             }
             // H2D once the kernels that last read this slot's inputs are done
             if (ci >= 2) KM_CUDA(cudaStreamWaitEvent(c->st_h2d, sl.ev_comp, 0));
-            KM_CUDA(cudaMemcpyAsync(sl.d_bases, bases + offs[r0], nb, cudaMemcpyHostToDevice, c->st_h2d));
+            if (compact) {
+                KM_CUDA(cudaMemcpyAsync(sl.d_codes, io.codes + w0, (size_t)(w1 - w0) * 4, cudaMemcpyHostToDevice, c->st_h2d));
+                if (i_hi > i_lo) KM_CUDA(cudaMemcpyAsync(sl.d_inv, io.inv + i_lo, (size_t)(i_hi - i_lo) * 8, cudaMemcpyHostToDevice, c->st_h2d));
+            } else KM_CUDA(cudaMemcpyAsync(sl.d_bases, bases + offs[r0], nb, cudaMemcpyHostToDevice, c->st_h2d));
             KM_CUDA(cudaMemcpyAsync(sl.d_offs, offs + r0, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->st_h2d));
             KM_CUDA(cudaEventRecord(sl.ev_h2d, c->st_h2d));
             // kernels once the inputs are in and the previous results of this slot have been copied out
             KM_CUDA(cudaStreamWaitEvent(c->stream, sl.ev_h2d, 0));
             if (ci >= 2) KM_CUDA(cudaStreamWaitEvent(c->stream, sl.ev_d2h, 0));
-            KmPass L{sl.d_bases - offs[r0], sl.d_offs, n, offs[r0], nb, max_len, sl.d_out, ci == 0};
+            if (compact) {
+                km_unpack_kernel<<<(unsigned)((w1 - w0 + 255) / 256), 256, 0, c->stream>>>(sl.d_codes, w1 - w0, (uint4 *)sl.d_bases);
+                g_km_launches++;
+                if (i_hi > i_lo) { km_unpack_inv_kernel<<<(unsigned)((i_hi - i_lo + 255) / 256), 256, 0, c->stream>>>(sl.d_inv, i_hi - i_lo, base0, sl.d_bases); g_km_launches++; }
+                KM_CUDA(cudaGetLastError());
+            }
+            KmPass L{sl.d_bases - base0, sl.d_offs, n, offs[r0], nb, max_len, sl.d_out, ci == 0};
             if ((rc = km_run_device(c, L, c->stream)) != KMAT_OK) return rc;
+            if (compact) {
+                km_compact_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(sl.d_out, n, c->opt.want_lineage, sl.d_out32);
+                g_km_launches++;
+                KM_CUDA(cudaGetLastError());
+            }
             KM_CUDA(cudaMemcpyAsync(sl.h_cur, c->d_cursors, 16, cudaMemcpyDeviceToHost, c->stream));
             KM_CUDA(cudaEventRecord(sl.ev_comp, c->stream));
             if (prev.valid && (rc = drain(prev)) != KMAT_OK) return rc;
@@ -1754,6 +1851,7 @@ extern "C" int kmat_label_batch(kmat_ctx *c, const char *bases, const uint64_t *
         if (n_cands) *n_cands = total_c;
         if (n_lineage) *n_lineage = c->opt.want_lineage ? total_l : 0;
         if ((rc = km_fetch_stats(c, c->stream)) != KMAT_OK) return rc;
+        if (compact && std::max(total_c, total_l) >= (1ull << 32)) { kmat_set_error("compact interface: more than 2^32 pairs in one call; split the batch"); return KMAT_ERR_UNSUPPORTED; }
         if ((cands && total_c > cands_cap) || (lineage && c->opt.want_lineage && total_l > lineage_cap)) {
             kmat_set_error("candidate buffer too small: need %llu candidate and %llu lineage pairs", total_c, total_l);
             return KMAT_ERR_OVERFLOW;
@@ -1762,6 +1860,27 @@ extern "C" int kmat_label_batch(kmat_ctx *c, const char *bases, const uint64_t *
     }
     kmat_set_error("candidate buffer kept overflowing");
     return KMAT_ERR_CUDA;
+}
+extern "C" int kmat_label_batch(kmat_ctx *c, const char *bases, const uint64_t *offs, uint32_t n_reads, kmat_read_result *out,
+                                kmat_pair *cands, uint64_t cands_cap, uint64_t *n_cands, kmat_pair *lineage, uint64_t lineage_cap,
+                                uint64_t *n_lineage) {
+    if (!c || !offs || !out || (n_reads && !bases)) { kmat_set_error("kmat_label_batch: bad argument"); return KMAT_ERR_ARG; }
+    KmHostIO io;
+    io.bases = bases; io.out = out; io.cands = cands; io.cands_cap = cands_cap; io.n_cands = n_cands;
+    io.lineage = lineage; io.lineage_cap = lineage_cap; io.n_lineage = n_lineage;
+    return km_label_host(c, io, offs, n_reads);
+}
+// The compact interface: reads as 2-bit code words indexed by GLOBAL base offset (word w = bases 16 w .. 16 w + 15, base i in
+// bits 2 (i % 16) .. of its word) + the ascending offsets of the non-ACGT bases (kmat_pack_reads writes both); results as
+// 32-byte records with ONE pair list each -- rank_label when the ctx has want_lineage == 0 (the -p line), else valid_cand.
+extern "C" int kmat_label_batch_packed(kmat_ctx *c, const uint32_t *codes, const uint64_t *inv_pos, uint64_t n_inv, const uint64_t *offs, uint32_t n_reads,
+                                       kmat_read_result32 *out, kmat_pair *list, uint64_t list_cap, uint64_t *n_list) {
+    if (!c || !offs || !out || (n_reads && !codes) || (n_inv && !inv_pos)) { kmat_set_error("kmat_label_batch_packed: bad argument"); return KMAT_ERR_ARG; }
+    KmHostIO io;
+    io.codes = codes; io.inv = inv_pos; io.n_inv = n_inv; io.out32 = out;
+    if (c->opt.want_lineage) { io.lineage = list; io.lineage_cap = list_cap; io.n_lineage = n_list; }
+    else { io.cands = list; io.cands_cap = list_cap; io.n_cands = n_list; }
+    return km_label_host(c, io, offs, n_reads);
 }
 
 // Page-locked host memory for the buffers handed to kmat_label_batch (optional: pageable buffers work, pinned

@@ -169,11 +169,13 @@ KM_HD uint64_t km_line_x_of(uint64_t canon, const KmMzr &z, int k, int m, int b)
     const int s = 2 * m - b;
     const uint64_t line = s >= 32 ? 0ull : (uint64_t)(g >> s);
     const uint32_t grem = s >= 32 ? g : (g & (uint32_t)((1ull << s) - 1));
-    const int j = (int)z.off, right_bases = k - m - j;
-    const uint64_t left = j ? canon >> (2 * (k - j)) : 0ull;
-    const uint64_t right = canon & ((1ull << (2 * right_bases)) - 1);
-    const uint64_t flanks = (left << (2 * right_bases)) | right;                        // 2 (k - m) bits
-    const uint64_t key = ((((uint64_t)grem << (KM_MZR_OFF_BITS + 1)) | ((uint64_t)z.off << 1) | z.flip) << (2 * (k - m))) | flanks;
+    // the k - m bases outside the window: zero the window's 2m bits; what is left of the left flank sits at the top of the
+    // 2k-bit value, the right flank at the bottom -- fold the top down (k - m <= 7 bases: the two parts cannot collide)
+    const int right_bits = 2 * (k - m - (int)z.off), fb = 2 * (k - m);
+    const uint64_t wmask = (m >= 16 ? 0xFFFFFFFFull : ((1ull << (2 * m)) - 1)) << right_bits;
+    const uint64_t v = canon & ~wmask;
+    const uint64_t flanks = ((v >> (2 * m)) | v) & ((1ull << fb) - 1);
+    const uint64_t key = ((((uint64_t)grem << (KM_MZR_OFF_BITS + 1)) | ((uint64_t)z.off << 1) | z.flip) << fb) | flanks;
     return (line << KM_LINE_XSHIFT) | ((uint64_t)(z.off & 3u) << KM_MZR_KEY_BITS) | key;
 }
 KM_HD uint64_t km_line_x(uint64_t canon, int k, int m, int b) { return km_line_x_of(canon, km_mzr_of(canon, k, m), k, m, b); }
@@ -193,9 +195,9 @@ KM_HD uint64_t km_line_kmer_of(uint64_t x, int k, int m, int b) {
     const uint32_t flip = head & 1, j = (head >> 1) & ((1u << KM_MZR_OFF_BITS) - 1);
     const uint32_t c = km_mzr_unmix2(km_line_g_of_x(x, k, m, b), m);
     const uint64_t win = flip ? (uint64_t)km_mzr_revcomp_m(c, m) : (uint64_t)c;
-    const int right_bases = k - m - (int)j;
-    const uint64_t left = flanks >> (2 * right_bases), right = flanks & ((1ull << (2 * right_bases)) - 1);
-    return (j ? left << (2 * (k - (int)j)) : 0ull) | (win << (2 * right_bases)) | right;
+    const int right_bits = 2 * (k - m - (int)j);
+    const uint64_t right = flanks & ((1ull << right_bits) - 1), left = flanks >> right_bits;       // left flank: the top j bases
+    return (left << (2 * m + right_bits)) | (win << right_bits) | right;
 }
 // owner shard of a table key: the top of g, so a line belongs to one owner (multiply-shift: any shard count)
 KM_HD uint32_t km_line_owner_of_g(uint32_t g, int m, uint32_t n_shards) { return (uint32_t)(((uint64_t)g * n_shards) >> (2 * m)); }

@@ -48,6 +48,7 @@ struct kmat_reader {
     int fd = -1;
     bool own_fd = false;
     bool file_eof = false;      // read(2) returned 0
+    int io_error = 0;           // errno of a failed read(2): reported by kmat_reader_next instead of a silent truncation
     std::vector<char> buf;
     size_t pos = 0, end = 0;
     KmParseState st;
@@ -68,6 +69,8 @@ struct kmat_reader {
     bool fallback = false;                   // parallel FASTQ met a segment with an open end: sequential from fb on
     const char *fb_p = nullptr;
     std::string carry_hdr;                   // parallel FASTQ: header of the last record handed out so far
+    kmat_read_batch *cur = nullptr;          // parallel mode: the parsed segment being handed out in max_reads / max_bases slices
+    uint32_t cur_i = 0;
 };
 
 static const size_t kChunk = 8u << 20;
@@ -87,6 +90,7 @@ static bool next_line_fd(kmat_reader *r, const char **line, size_t *len) {
         if (r->end == r->buf.size()) r->buf.resize(r->buf.size() * 2);
         ssize_t got;
         do { got = read(r->fd, r->buf.data() + r->end, r->buf.size() - r->end); } while (got < 0 && errno == EINTR);
+        if (got < 0) r->io_error = errno;
         if (got <= 0) r->file_eof = true; else r->end += (size_t)got;
     }
 }
@@ -259,6 +263,7 @@ extern "C" void kmat_reader_close(kmat_reader *r) {
         r->cv_space.notify_all();
         for (auto &t : r->workers) t.join();
         for (auto &kv : r->done) delete kv.second;
+        delete r->cur;
         munmap((void *)r->map, r->map_len);
     }
     if (r->own_fd && r->fd >= 0) close(r->fd);
@@ -271,8 +276,28 @@ extern "C" int64_t kmat_reader_next(kmat_reader *r, uint32_t max_reads, uint64_t
     if (!r || !b) { kmat_set_error("kmat_reader_next: bad argument"); return KMAT_ERR_ARG; }
     if (max_reads == 0) max_reads = 1;
     b->clear();
+    // reads [cur_i, ...) of the current parsed segment, cut to max_reads / max_bases (at least one read)
+    auto slice = [&]() -> int64_t {
+        kmat_read_batch *d = r->cur;
+        const uint32_t i0 = r->cur_i;
+        uint32_t i1 = i0;
+        while (i1 < d->n && i1 - i0 < max_reads && (i1 == i0 || d->offs[i1 + 1] - d->offs[i0] <= max_bases)) i1++;
+        const bool last = i1 >= d->n;
+        if (i0 == 0 && last) std::swap(*b, *d);                  // the whole segment fits: no copy
+        else {
+            b->bases.assign(d->bases, d->offs[i0], d->offs[i1] - d->offs[i0]);
+            b->hdrs.assign(d->hdrs, d->hdr_offs[i0], d->hdr_offs[i1] - d->hdr_offs[i0]);
+            for (uint32_t i = i0; i < i1; i++) { b->offs.push_back(d->offs[i + 1] - d->offs[i0]); b->hdr_offs.push_back(d->hdr_offs[i + 1] - d->hdr_offs[i0]); }
+            b->n = i1 - i0;
+            b->first_ordinal = d->first_ordinal + i0;
+        }
+        r->cur_i = i1;
+        if (last) { delete r->cur; r->cur = nullptr; r->cur_i = 0; }
+        return (int64_t)b->n;
+    };
+    if (r->mt && r->cur) return slice();
     if (r->mt && !r->fallback) {
-        // segments come out in file order, each as one batch (max_reads / max_bases do not apply); empty ones are skipped
+        // segments come out in file order; empty ones are skipped
         for (;;) {
             if (r->next_out + 1 >= r->seg.size()) return 0;
             kmat_read_batch *d = nullptr;
@@ -295,14 +320,12 @@ extern "C" int64_t kmat_reader_next(kmat_reader *r, uint32_t max_reads, uint64_t
                 r->st.fastq = true; r->st.hdr_buff = r->carry_hdr; r->st.n_emitted = r->ordinal;
                 break;
             }
-            std::swap(*b, *d);
-            delete d;
-            b->first_ordinal = r->ordinal + 1;
-            if (!b->unknown.empty()) {                         // rebuild the headers with the global ordinals
+            d->first_ordinal = r->ordinal + 1;
+            if (!d->unknown.empty()) {                         // rebuild the headers with the global ordinals
                 std::string h; std::vector<uint64_t> ho(1, 0);
                 size_t u = 0;
-                for (uint32_t i = 0; i < b->n; i++) {
-                    if (u < b->unknown.size() && b->unknown[u] == i) {
+                for (uint32_t i = 0; i < d->n; i++) {
+                    if (u < d->unknown.size() && d->unknown[u] == i) {
                         u++;
                         if (r->mt_fastq && i == 0 && !r->carry_hdr.empty() && r->carry_hdr[0] != '\0') h.append(r->carry_hdr);   // the previous segment's last header
                         else {
@@ -310,14 +333,16 @@ extern "C" int64_t kmat_reader_next(kmat_reader *r, uint32_t max_reads, uint64_t
                             snprintf(tmp, sizeof tmp, "unknown_hdr:%llu", (unsigned long long)(r->ordinal + i + 1));
                             h.append(tmp);
                         }
-                    } else h.append(b->hdrs, b->hdr_offs[i], b->hdr_offs[i + 1] - b->hdr_offs[i]);
+                    } else h.append(d->hdrs, d->hdr_offs[i], d->hdr_offs[i + 1] - d->hdr_offs[i]);
                     ho.push_back(h.size());
                 }
-                b->hdrs.swap(h); b->hdr_offs.swap(ho);
+                d->hdrs.swap(h); d->hdr_offs.swap(ho);
             }
-            r->ordinal += b->n;
-            if (r->mt_fastq) r->carry_hdr = b->tail_hdr;
-            if (b->n) return (int64_t)b->n;
+            r->ordinal += d->n;
+            if (r->mt_fastq) r->carry_hdr = d->tail_hdr;
+            if (!d->n) { delete d; continue; }
+            r->cur = d; r->cur_i = 0;
+            return slice();
         }
     }
     b->first_ordinal = r->st.n_emitted + 1;
@@ -328,6 +353,7 @@ extern "C" int64_t kmat_reader_next(kmat_reader *r, uint32_t max_reads, uint64_t
         return (int64_t)b->n;
     }
     parse_lines(r->st, [&](const char **ln, size_t *n) { return next_line_fd(r, ln, n); }, max_reads, max_bases, b);
+    if (r->io_error) { kmat_set_error("read error on the input: %s", strerror(r->io_error)); return KMAT_ERR_IO; }
     return (int64_t)b->n;
 }
 

@@ -154,3 +154,37 @@ def test_reader_fuzz_sequential_and_parallel_equal_oracle(tmp_path, seed, monkey
                 monkeypatch.setenv("KMAT_READER_SEG_BYTES", seg)
                 got = api.read_file(p, fastq=fastq, threads=3)
                 assert got[0] == want[0] and got[1] == want[1], (data, fastq, seg)
+
+
+def test_parallel_reader_respects_batch_limits(tmp_path):
+    """Parallel mode parses 8 MB segments; kmat_reader_next still hands out at most max_reads reads / max_bases bases per
+    batch (a batch always holds at least one read), in file order, with the same records as the sequential reader."""
+    import ctypes as C
+    rng = np.random.default_rng(11)
+    hdrs = [f"r{i} x" for i in range(3000)]
+    seqs = ["".join("ACGT"[c] for c in rng.integers(0, 4, int(rng.integers(30, 300)))) for _ in hdrs]
+    p = str(tmp_path / "r.fa")
+    fx.write_fasta(p, hdrs, seqs)
+    L = api.lib()
+    for max_reads, max_bases in ((17, 1 << 30), (1 << 20, 2000), (1, 1)):
+        r = C.c_void_p()
+        assert L.kmat_reader_open_mt(p.encode(), 0, 4, C.byref(r)) == 0
+        b = C.c_void_p(L.kmat_read_batch_new())
+        got, sizes = [], []
+        while True:
+            n = L.kmat_reader_next(r, max_reads, max_bases, b)
+            assert n >= 0
+            if n == 0:
+                break
+            bp, op_, hp, hop = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+            nn, first = C.c_uint32(), C.c_uint64()
+            assert L.kmat_read_batch_view(b, C.byref(bp), C.byref(op_), C.byref(hp), C.byref(hop), C.byref(nn), C.byref(first)) == 0
+            offs = np.ctypeslib.as_array(C.cast(op_, C.POINTER(C.c_uint64)), shape=(n + 1,))
+            assert first.value == len(got) + 1 and nn.value == n
+            assert n <= max_reads and (n == 1 or int(offs[n]) <= max_bases)
+            bases = C.string_at(bp, int(offs[n]))
+            got += [bases[int(offs[i]):int(offs[i + 1])].decode() for i in range(n)]
+            sizes.append(n)
+        L.kmat_read_batch_free(b)
+        L.kmat_reader_close(r)
+        assert got == seqs and len(sizes) > 1
