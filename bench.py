@@ -40,7 +40,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kmat", choices=["kmat", "reference"])
-    ap.add_argument("--genomes", type=int, default=2000)
+    ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4"],
+                    help="BASELINE.json configs[1] (default: 2000 genomes, ~0.96 G k-mers, table replicated), configs[2] (C3: marker-scale, 3550 genomes = "
+                         "1.7 G k-mers, run-time pruning -g 10, denser first level so that one GPU holds it) or configs[3] (C4: 5200 genomes = 2.5 G k-mers, a "
+                         "~185 GB table at the default density: sharded over the ranks, query k-mers exchanged over NCCL)")
+    ap.add_argument("--genomes", type=int, default=None)
     ap.add_argument("--genome-len", type=int, default=500000)
     ap.add_argument("--reads", type=int, default=10_000_000)
     ap.add_argument("--read-len", type=int, default=150)
@@ -56,11 +60,25 @@ def parse_args():
     ap.add_argument("--round-reads", type=int, default=1 << 20, help="reads per exchange round in sharded mode")
     ap.add_argument("--exchange-slots", type=int, default=2, choices=[1, 2],
                     help="sharded mode: 2 = two contexts per rank, the encode of round i+1 and the finish of round i overlap the exchanges")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "torch"],
+                    help="sharded mode: nccl = the exchange inside libkmat (kmat_shard_label_device: ncclSend/ncclRecv groups driven from C++); "
+                         "torch = the Python driver over torch.distributed all_to_all_single (two-slot pipeline)")
     ap.add_argument("--pipeline", type=int, default=1, help="sub-batches per pass (kmat_ctx_set_pipeline); -1 automatic, 1 serial")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.genomes is None:
+        a.genomes = {"C2": 2000, "C3": 3550, "C4": 5200}[a.workload]
+    a.prune = 10 if a.workload == "C3" else 0
+    if a.workload == "C3":
+        os.environ.setdefault("KMAT_LINE_DENSITY", "4")          # 2^29 lines = 69 GB instead of 137 GB: the replicated table + its build temporaries fit one GPU
+    if a.workload == "C4" and a.table_mode == "replicated":
+        a.table_mode = "sharded"
+    return a
 
 
 def workload_name(a):
+    if a.workload != "C2":
+        return (f"{a.workload}: {a.genomes} random genomes x {a.genome_len} bp (10% sibling-shared, 2% mutated), k=20, 16-bit ids"
+                f"{', lists pruned at run time to <= 10 taxids (-g 10 -m)' if a.prune else ''}; {a.reads} x {a.read_len} bp reads/GPU (90% genomic, 10% novel, 0.1%-2% subst, 0.05% N)")
     return (f"C2-replicated: {a.genomes} random genomes x {a.genome_len} bp (10% sibling-shared, 2% mutated), k=20, "
             f"16-bit ids; {a.reads} x {a.read_len} bp reads/GPU (90% genomic, 10% novel, 0.1%-2% subst, 0.05% N)")
 
@@ -290,6 +308,17 @@ def sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, 
     else:
         lab = sharded.ShardedLabeler(sharded.CudaPhases(ctx, dev, world, torch_stream=torch.cuda.Stream()), ex, round_reads=a.round_reads,
                                      phases2=sharded.CudaPhases(ctx2, dev, world, torch_stream=torch.cuda.Stream()))
+    comm = None
+    if a.exchange == "nccl":
+        # the exchange lives in libkmat: one NCCL communicator per rank; the 128-byte unique id travels over torch.distributed once
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(api.Comm.unique_id()), dtype=torch.uint8))
+        if world > 1:
+            dist.broadcast(uid, 0)
+        comm = api.Comm(local, rank, world, uid.cpu().numpy().tobytes())
+        h_offs_all = (np.arange(n + 1, dtype=np.uint64) * np.uint64(L))
+        d_offs_all = torch.as_tensor(h_offs_all.astype(np.int64), device=dev)
     rr = min(a.round_reads, n)
     offs_full = (torch.arange(rr + 1, device=dev, dtype=torch.int64) * L).contiguous()       # chunk-local offsets, every round
     d_out = torch.empty(n * api.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
@@ -298,8 +327,15 @@ def sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, 
     def round_args(r0, r1):
         return (reads.data_ptr() + r0 * L, offs_full.data_ptr(), r1 - r0, (r1 - r0) * L, L, d_out.data_ptr() + r0 * api.RESULT_DTYPE.itemsize)
 
+    comm_stats = [0, 0, 0, 0]
+
     def step():
-        lab.run(rounds, round_args)
+        if comm is not None:
+            st_ = comm.label_device(ctx, reads.data_ptr(), h_offs_all, d_offs_all.data_ptr(), n, d_out.data_ptr(), a.round_reads, stream)
+            for i_ in range(4):
+                comm_stats[i_] += st_[i_]
+        else:
+            lab.run(rounds, round_args)
 
     def barrier():
         if world > 1:
@@ -315,25 +351,30 @@ def sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, 
     sampler = ClockSampler(local)
     sampler.start()
     lab.lookups = lab.served = lab.payload_words = lab.rounds = 0
+    comm_stats[:] = [0, 0, 0, 0]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    e0.record()
+    e0.record(tstream)
     for _ in range(a.steps):
         step()
-    e1.record()
+    e1.record(tstream)
     barrier()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop()
-    # one more, untimed step with a CUDA event after every phase: where a round's time goes
-    lab.timing = {}
-    keep = (lab.lookups, lab.served, lab.payload_words, lab.rounds)
-    ph2_keep, lab.ph2 = lab.ph2, None              # the phase split is taken on the serial schedule
-    step()
-    lab.ph2 = ph2_keep
-    torch.cuda.synchronize()
-    phase_ms = {k: round(v, 2) for k, v in lab.timing.items()}
-    lab.timing = None
-    lab.lookups, lab.served, lab.payload_words, lab.rounds = keep
+    phase_ms = {}
+    if comm is not None:
+        lab.lookups, lab.served, lab.payload_words, lab.rounds = comm_stats
+    else:
+        # one more, untimed step with a CUDA event after every phase: where a round's time goes
+        lab.timing = {}
+        keep = (lab.lookups, lab.served, lab.payload_words, lab.rounds)
+        ph2_keep, lab.ph2 = lab.ph2, None              # the phase split is taken on the serial schedule
+        step()
+        lab.ph2 = ph2_keep
+        torch.cuda.synchronize()
+        phase_ms = {k: round(v, 2) for k, v in lab.timing.items()}
+        lab.timing = None
+        lab.lookups, lab.served, lab.payload_words, lab.rounds = keep
     res = d_out.cpu().numpy().view(api.RESULT_DTYPE)
     labels_checksum = int(((res["status"].astype(np.int64) * 1000003 + res["tid"].astype(np.int64) * 7919 + res["score"].view(np.int32).astype(np.int64)) & 0xFFFFFFFF).sum())
     errs = int((res["status"] == 6).sum())
@@ -360,10 +401,10 @@ def sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, 
                        "options": "run_rl.sh:243 (-j 30 -l 0 -b 1 -p, null models on)", "round_reads": a.round_reads,
                        "l2_policy": "inputs larger than L2; no flush needed",
                        "parallelism": f"table sharded x{world} by kmat_shard_of (k-mer hash), reads stay home; per round: all-to-all of query k-mers "
-                                      f"(8 B), all-to-all of hit words (4 B) + list records back ({'NCCL, torch.distributed' if world > 1 else 'single rank'})"},
+                                      f"(8 B), all-to-all of hit words (4 B) + list records back ({'ncclSend/ncclRecv groups inside libkmat (kmat_shard_label_device)' if comm is not None else 'NCCL, torch.distributed all_to_all_single'})"},
             "kmer_lookups_per_s": lookups_step / (ms_step * 1e-3), "lookups_per_read": lookups_step / (world * n),
             "exchange_bytes_per_step": int(lookups_step * 12 + int(tot[1].item()) / a.steps * 4), "reads_error": int(tot[2].item()),
-            "reads_labeled": int(tot[3].item()), "phase_ms_rank0": phase_ms, "exchange_slots": 2 if ctx2 is not None else 1, "labels_checksum_rank0": labels_checksum,
+            "reads_labeled": int(tot[3].item()), "phase_ms_rank0": phase_ms, "exchange": a.exchange, "exchange_slots": (2 if ctx2 is not None else 1) if comm is None else 1, "labels_checksum_rank0": labels_checksum,
             "roofline": {"bound": "hbm", "kernel": "km_shard_probe_kernel", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
                          "peak_source": peak_src, "note": "per-kernel split not measured in sharded mode; see the replicated line"},
             "e2e": None, "gpu_launches": int(api.lib().kmat_launch_count() - launches0), "clocks": clocks, "setup_s": setup_s,
@@ -455,9 +496,13 @@ def main():
         db = synth.upload_table(tbl, local, shard_index=rank if split else 0, shard_count=world if split else 1)
         del tbl
         torch.cuda.empty_cache()
-        inputs = api.Inputs(tree=paths["tree"], depth=paths["depth"], rank=paths["rank"], map16=paths["map16"], null_lst=null_lst, lmat_dir=workdir)
-        # options of bin/run_rl.sh:243: -j 30 -l 0 -b 1.0 -x 0 -p, null models on
-        ctx = api.Ctx(db, inputs, api.default_opts(min_kmer=30, hbias=0.0, sdiff=1.0, min_score=0.0, want_lineage=0))
+        inputs = api.Inputs(tree=paths["tree"], depth=paths["depth"], rank=paths["rank"], map16=paths["map16"], null_lst=null_lst, lmat_dir=workdir,
+                            numrank=paths["numrank"] if a.prune else None)
+        # options of bin/run_rl.sh:243: -j 30 -l 0 -b 1.0 -x 0 -p, null models on (C3 adds -g 10 -m numeric_ranks)
+        kw_opts = dict(min_kmer=30, hbias=0.0, sdiff=1.0, min_score=0.0, want_lineage=0)
+        if a.prune:
+            kw_opts["max_count"] = a.prune
+        ctx = api.Ctx(db, inputs, api.default_opts(**kw_opts))
         if direct_mode and world > 1:
             from lmat_b200 import sharded
             sharded.attach_peers(ctx, device=dev)
@@ -480,7 +525,7 @@ def main():
             ctx.label_device(reads.data_ptr(), d_offs.data_ptr(), n, total, L, None, stream)
 
         if sharded_mode:
-            ctx2 = api.Ctx(db, inputs, api.default_opts(min_kmer=30, hbias=0.0, sdiff=1.0, min_score=0.0, want_lineage=0)) if a.exchange_slots == 2 else None
+            ctx2 = api.Ctx(db, inputs, api.default_opts(**kw_opts)) if (a.exchange_slots == 2 and a.exchange == "torch") else None
             sharded_bench(a, ctx, db, reads, world, rank, local, dev, n_kmers, n_lists, setup_s, launches0, tstream, ctx2)
             return
 

@@ -102,6 +102,9 @@ int kmat_db_build_device(int device, int kmer_length, int tid_bytes, uint64_t n_
                          int shard_index, int shard_count /* keep kmat_shard_of() == shard_index only; 0, 1 = all */,
                          kmat_db **out);
 uint32_t kmat_shard_of(uint64_t kmer, int kmer_length, int shard_count);
+/* HBM (bytes) one device needs to build and hold one of `shard_count` shards of the table, batch buffers included: lets a
+ * host decide between a replicated and a sharded table before it uploads anything. */
+uint64_t kmat_table_device_bytes(const kmat_table *, int shard_count);
 uint64_t kmat_db_size(const kmat_db *);
 uint64_t kmat_db_bytes(const kmat_db *);             /* device bytes held */
 uint64_t kmat_db_overflow(const kmat_db *);          /* k-mers of a two-level table that live in its second level */
@@ -242,6 +245,26 @@ int kmat_shard_finish(kmat_ctx *, const uint32_t *d_reply, const uint32_t *d_pay
 /* Device-resident results of the last pass that was given d_out == NULL, and the device candidate pairs that
  * cand_off / n_cand index (rank_label after sort(TCmp), ascending).  Synchronises. */
 int kmat_ctx_device_results(kmat_ctx *, const kmat_read_result **d_out, const kmat_pair **d_cands, uint64_t *n_cands);
+
+/* The exchange itself, inside the library: NCCL send/recv groups (libnccl.so.2 is loaded on first use; KMAT_ERR_UNSUPPORTED
+ * when it is absent).  One kmat_comm per rank; rank r's ctx must sit on shard r of `world`.  The 128-byte unique id is made
+ * by one rank and handed to the others by the caller (a broadcast of the launcher in use, or shared memory between the
+ * threads of one process); kmat_comm_init is collective. */
+typedef struct kmat_comm kmat_comm;
+int kmat_comm_unique_id(unsigned char *id128);
+int kmat_comm_init(int device, int rank, int world, const unsigned char *id128, kmat_comm **out);
+void kmat_comm_free(kmat_comm *);
+/* COLLECTIVE pass over this rank's device-resident reads (possibly none): rounds of `round_reads` reads (0 = 2^20) through
+ * kmat_shard_encode -> send/recv -> kmat_shard_serve -> send/recv -> kmat_shard_finish until every rank has finished.
+ * h_offs / d_offs = the n_reads + 1 absolute base offsets on the host and on the device; results to d_out[0 .. n_reads).
+ * stats (optional, host, 4 entries): unique lookups sent, queries served, list-record words received, rounds. */
+int kmat_shard_label_device(kmat_ctx *, kmat_comm *, const char *d_bases, const uint64_t *h_offs, const uint64_t *d_offs, uint32_t n_reads,
+                            uint32_t round_reads, kmat_read_result *d_out, uint64_t *stats, void *stream);
+/* The same with host buffers in and out: kmat_label_batch for a sharded table.  COLLECTIVE (a rank without reads passes
+ * n_reads = 0).  KMAT_ERR_OVERFLOW: the pass has run to its end (the ranks stay in step); *n_cands / *n_lineage hold the
+ * capacities needed. */
+int kmat_shard_label_batch(kmat_ctx *, kmat_comm *, const char *bases, const uint64_t *offs, uint32_t n_reads, kmat_read_result *out,
+                           kmat_pair *cands, uint64_t cands_cap, uint64_t *n_cands, kmat_pair *lineage, uint64_t lineage_cap, uint64_t *n_lineage);
 
 /* ---- gene_label -------------------------------------------------------------------------------
  * Replaces retrieve_kmer_labels + the top-gene pick of proc_line in src/gene_label.cpp (:217-301) for a batch of reads

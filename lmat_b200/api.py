@@ -47,14 +47,14 @@ EXPORTS = [
     "kmat_strerror", "kmat_last_error", "kmat_abi_version", "kmat_device_count", "kmat_device_memory", "kmat_table_from_sorteddb",
     "kmat_table_from_arrays", "kmat_table_open", "kmat_table_save", "kmat_table_size", "kmat_table_kmer_length",
     "kmat_table_tid_bytes", "kmat_table_build", "kmat_build_opts_default", "kmat_table_view", "kmat_table_free", "kmat_db_upload", "kmat_db_build_device",
-    "kmat_shard_of", "kmat_db_size", "kmat_db_bytes", "kmat_db_overflow", "kmat_db_kmer_length", "kmat_db_device", "kmat_db_free",
+    "kmat_shard_of", "kmat_table_device_bytes", "kmat_db_size", "kmat_db_bytes", "kmat_db_overflow", "kmat_db_kmer_length", "kmat_db_device", "kmat_db_free",
     "kmat_lookup_batch", "kmat_encode_batch", "kmat_inputs_load", "kmat_inputs_free", "kmat_opts_default",
     "kmat_ctx_create", "kmat_ctx_set_opts", "kmat_ctx_destroy", "kmat_label_batch", "kmat_label_batch_device",
     "kmat_pack_words", "kmat_pack_reads", "kmat_label_batch_packed", "kmat_result_expand",
     "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_set_pipeline", "kmat_gene_batch", "kmat_shard_encode", "kmat_shard_serve", "kmat_shard_finish", "kmat_ctx_device_results", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench", "kmat_gather_bench_peer",
     "kmat_set_l2_fetch_granularity", "kmat_reader_open", "kmat_reader_open_mt", "kmat_reader_close", "kmat_read_batch_new", "kmat_read_batch_free",
     "kmat_reader_next", "kmat_read_batch_view", "kmat_tally_class", "kmat_host_alloc", "kmat_host_free",
-    "kmat_ctx_peer_export", "kmat_ctx_peer_attach",
+    "kmat_ctx_peer_export", "kmat_ctx_peer_attach", "kmat_comm_unique_id", "kmat_comm_init", "kmat_comm_free", "kmat_shard_label_device", "kmat_shard_label_batch",
     "kmat_kcov_create", "kmat_kcov_add", "kmat_kcov_finish", "kmat_kcov_query", "kmat_kcov_free",
     "kmat_null_reset", "kmat_null_batch", "kmat_null_random", "kmat_null_draw_reads", "kmat_null_fetch", "kmat_null_write",
 ]
@@ -89,6 +89,8 @@ def lib():
     L.kmat_shard_of.argtypes = [C.c_uint64, C.c_int, C.c_int]
     L.kmat_db_size.restype = C.c_uint64
     L.kmat_db_size.argtypes = [vp]
+    L.kmat_table_device_bytes.restype = C.c_uint64
+    L.kmat_table_device_bytes.argtypes = [vp, C.c_int]
     L.kmat_db_bytes.restype = C.c_uint64
     L.kmat_db_bytes.argtypes = [vp]
     L.kmat_db_overflow.restype = C.c_uint64
@@ -106,6 +108,12 @@ def lib():
     L.kmat_ctx_destroy.argtypes = [vp]
     L.kmat_label_batch.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, C.POINTER(C.c_uint64), vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.kmat_label_batch_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, vp, vp]
+    L.kmat_comm_unique_id.argtypes = [vp]
+    L.kmat_comm_init.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp)]
+    L.kmat_comm_free.argtypes = [vp]
+    L.kmat_comm_free.restype = None
+    L.kmat_shard_label_device.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp]
+    L.kmat_shard_label_batch.argtypes = [vp, vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, C.POINTER(C.c_uint64), vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.kmat_pack_words.restype = C.c_uint64
     L.kmat_pack_words.argtypes = [C.c_uint64]
     L.kmat_pack_reads.argtypes = [vp, C.c_uint64, C.c_int, vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
@@ -520,6 +528,62 @@ class Ctx:
     def __del__(self):
         try:
             lib().kmat_ctx_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Comm:
+    """NCCL communicator of the DB-sharded mode, owned by libkmat (kmat_comm_*).  rank r's Ctx must sit on shard r."""
+
+    @staticmethod
+    def _preload():
+        # In a Python process torch's own NCCL (same soname, newer) must be the one in the address space before libkmat
+        # dlopen()s "libnccl.so.2": a system copy loaded first would shadow it for torch's later import.
+        try:
+            import torch  # noqa: F401
+        except Exception:
+            pass
+
+    def __init__(self, device, rank, world, unique_id):
+        Comm._preload()
+        self.h = C.c_void_p()
+        self.rank, self.world = rank, world
+        uid = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        assert uid.size == 128
+        _check(lib().kmat_comm_init(device, rank, world, uid.ctypes.data, C.byref(self.h)))
+
+    @staticmethod
+    def unique_id():
+        Comm._preload()
+        uid = np.zeros(128, dtype=np.uint8)
+        _check(lib().kmat_comm_unique_id(uid.ctypes.data))
+        return uid.tobytes()
+
+    def label_device(self, ctx, d_bases_ptr, h_offs, d_offs_ptr, n_reads, d_out_ptr, round_reads=0, stream=None):
+        """COLLECTIVE: kmat_shard_label_device.  h_offs: numpy uint64 [n_reads + 1].  Returns (lookups, served, payload_words, rounds)."""
+        st = np.zeros(4, dtype=np.uint64)
+        ho = np.ascontiguousarray(h_offs, dtype=np.uint64)
+        _check(lib().kmat_shard_label_device(ctx.h, self.h, d_bases_ptr, ho.ctypes.data, d_offs_ptr, n_reads, round_reads, d_out_ptr, st.ctypes.data, stream))
+        return tuple(int(x) for x in st)
+
+    def label(self, ctx, seqs):
+        """COLLECTIVE: kmat_shard_label_batch (host buffers).  Returns (results, candidates, lineage) like Ctx.label."""
+        blob, offs = pack_reads(seqs)
+        n = len(offs) - 1
+        res = np.zeros(max(1, n), dtype=RESULT_DTYPE)
+        cap = max(4096, 32 * n)
+        n_c, n_l = C.c_uint64(), C.c_uint64()
+        cands = np.zeros(cap, dtype=PAIR_DTYPE)
+        lin = np.zeros(cap if ctx.opts.want_lineage else 1, dtype=PAIR_DTYPE)
+        _check(lib().kmat_shard_label_batch(ctx.h, self.h, blob, offs.ctypes.data, n, res.ctypes.data, cands.ctypes.data, len(cands), C.byref(n_c),
+                                            lin.ctypes.data if ctx.opts.want_lineage else None, len(lin), C.byref(n_l)))
+        return res[:n], cands[:n_c.value], lin[:n_l.value]
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().kmat_comm_free(self.h)
+                self.h = None
         except Exception:
             pass
 

@@ -383,6 +383,26 @@ extern "C" int kmat_db_upload(const kmat_table *t, int device, int shard_index, 
     return rc;
 }
 
+// HBM one device needs to hold (one shard of) this table and to build it: both levels from the real geometry, the list pools
+// (stored + resolved), the upload temporaries that are live next to them, and room for the per-batch buffers.
+extern "C" uint64_t kmat_table_device_bytes(const kmat_table *t, int shard_count) {
+    if (!t || shard_count < 1) return 0;
+    const uint64_t n = t->n_kmers, n_s = n / (uint64_t)shard_count + 1;
+    const int m = km_line_m(t->kmer_len), lb = (n < (1ull << 32)) ? km_choose_line_bits(n, t->kmer_len, m) : 0;
+    uint64_t bytes = 0;
+    if (lb) {
+        bytes += (((uint64_t)1 << lb) / (uint64_t)shard_count + 2) * 128;                         // first level
+        bytes += ((uint64_t)1 << km_choose_bucket_bits(n_s / 12 + 16, 2 * t->kmer_len)) * 32;      // second level: ~5 % of the k-mers, doubled once
+        bytes += n_s * 4;                                                                           // overflow list during the build
+    } else bytes += ((uint64_t)1 << km_choose_bucket_bits(n_s + n_s / 20, 2 * t->kmer_len)) * 32;
+    const uint64_t list_ids = t->n_ids > n ? t->n_ids - n : 0;                                      // ids beyond one per k-mer sit in lists
+    const uint64_t pool = (list_ids * 2 * (uint64_t)t->tid_bytes + list_ids) / (uint64_t)shard_count;  // records incl. counts and padding (upper bound)
+    bytes += pool * (t->tid_bytes == 2 ? 4 : 3);                                                    // stored pool + its upload copy + the resolved pool
+    bytes += n_s * 12 + (16ull << 20);                                                              // k-mers + payloads of the upload, prefix bitmap
+    bytes += 3ull << 30;                                                                            // batch buffers of a 131072-read batch pipeline, candidates, scratch
+    return bytes;
+}
+
 extern "C" uint64_t kmat_db_size(const kmat_db *db) { return db ? db->n_kmers : 0; }
 extern "C" uint64_t kmat_db_bytes(const kmat_db *db) { return db ? db->n_lines * 128 + (db->d_slots ? db->n_buckets * 32 : 0) + db->pool_words * 4 + db->prefix_bytes + (uint64_t)db->n_stash * 12 : 0; }
 extern "C" uint64_t kmat_db_overflow(const kmat_db *db) { return db ? db->n_overflow : 0; }      /* k-mers in the second level of a two-level table */

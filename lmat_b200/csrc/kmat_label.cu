@@ -1893,5 +1893,6 @@ extern "C" void *kmat_host_alloc(size_t bytes) {
 extern "C" void kmat_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 #include "kmat_shard.cuh"
+#include "kmat_comm.cuh"
 #include "kmat_gene.cuh"
 #include "kmat_null.cuh"

@@ -9,6 +9,8 @@
 //                    each writer keeps the reference's per-thread tallies (float sums in file order), merged in
 //                    thread order like :1760-1800.
 // Environment: KMAT_DEVICES="0,2,.." (default: every visible GPU), KMAT_BATCH_READS (default 131072),
+// KMAT_TABLE_MODE=sharded | exchange (table split over the GPUs: probes read the owner's memory over NVLink | query k-mers
+// travel over NCCL, kmat_shard_label_batch; default: replicated, or sharded when one GPU cannot hold the table),
 // KMAT_READER_THREADS (FASTA files are parsed in parallel segments; default hw threads / 4, 2..8),
 // KMAT_TID_BYTES (2|4: sizeof(DBTID_T) of the DB, default 2), LMAT_DIR as in the reference (:555-560).
 #include <getopt.h>
@@ -212,6 +214,8 @@ int main(int argc, char *argv[]) {
     const auto t_start = std::chrono::steady_clock::now();                       // StopWatch clock (:1604-1605)
     std::vector<kmat_db *> dbs(devs.size(), nullptr);
     std::vector<kmat_ctx *> ctxs(devs.size(), nullptr);
+    std::vector<kmat_comm *> comms(devs.size(), nullptr);
+    bool exchange = false;
     {
         std::vector<std::thread> up;
         std::vector<int> urc(devs.size(), 0);
@@ -220,11 +224,12 @@ int main(int argc, char *argv[]) {
         // and every GPU maps the others' shards (peer access over NVLink); the probe kernel then reads each bucket from
         // its owner.  Default: the whole table on every GPU.
         const char *tm = getenv("KMAT_TABLE_MODE");
-        bool split = tm && strcmp(tm, "sharded") == 0;
+        exchange = tm && strcmp(tm, "exchange") == 0;            // sharded table, query k-mers exchanged over NCCL (kmat_shard_label_batch)
+        bool split = tm && (strcmp(tm, "sharded") == 0 || exchange);
         if (!tm && devs.size() > 1) {
             uint64_t free_b = 0, total_b = 0;
             if (kmat_device_memory(devs[0], &free_b, &total_b) == KMAT_OK) {
-                const double need = 36.0 * (double)kmat_table_size(table) * 1.2;          // ~32 B of bucket + list pool share per k-mer, + batches
+                const double need = (double)kmat_table_device_bytes(table, 1);            // both table levels from the real geometry, list pools, upload temporaries, batch buffers
                 if (need > (double)free_b) { split = true; std::cout << "Table does not fit one GPU (" << need / 1e9 << " GB needed): sharding it over " << devs.size() << " GPUs" << std::endl; }
             }
         }
@@ -239,7 +244,20 @@ int main(int argc, char *argv[]) {
         for (auto &t : up) t.join();
         for (size_t d = 0; d < devs.size(); d++)
             if (urc[d] != KMAT_OK) { std::cerr << "ERROR! device " << devs[d] << ": " << uerr[d] << std::endl; return -1; }
-        if (split && n_sh > 1) {
+        if (split && exchange) {
+            // one NCCL communicator per GPU thread; the unique id is shared through this process's memory
+            unsigned char uid[128];
+            if (kmat_comm_unique_id(uid) != KMAT_OK) { std::cerr << "ERROR! " << kmat_last_error() << std::endl; return -1; }
+            std::vector<std::thread> ci;
+            std::vector<int> crc(devs.size(), 0);
+            std::vector<std::string> cerr_(devs.size());
+            for (size_t d = 0; d < devs.size(); d++)
+                ci.emplace_back([&, d] { crc[d] = kmat_comm_init(devs[d], (int)d, n_sh, uid, &comms[d]); if (crc[d] != KMAT_OK) cerr_[d] = kmat_last_error(); });
+            for (auto &t : ci) t.join();
+            for (size_t d = 0; d < devs.size(); d++)
+                if (crc[d] != KMAT_OK) { std::cerr << "ERROR! device " << devs[d] << ": " << cerr_[d] << std::endl; return -1; }
+            std::cout << "Table sharded over " << n_sh << " GPUs (query k-mers exchanged over NCCL)" << std::endl;
+        } else if (split && n_sh > 1) {
             std::vector<kmat_peer_info> blobs(devs.size());
             for (size_t d = 0; d < devs.size(); d++)
                 if (kmat_ctx_peer_export(ctxs[d], &blobs[d]) != KMAT_OK) { std::cerr << "ERROR! device " << devs[d] << ": " << kmat_last_error() << std::endl; return -1; }
@@ -299,26 +317,59 @@ int main(int argc, char *argv[]) {
         w.ready[b->seq] = b;
         w.cv.notify_one();
     };
+    // exchange mode: the GPU workers move in lockstep -- every super-step each takes one batch (or none) and all of them
+    // enter the collective pass; they stop together when no worker got a batch
+    struct Lockstep {
+        std::mutex m; std::condition_variable cv; int waiting = 0, got = 0; uint64_t gen = 0; bool last_any = false;
+        bool any(bool mine, int n) {             // barrier + OR
+            std::unique_lock<std::mutex> l(m);
+            const uint64_t g = gen;
+            got += mine ? 1 : 0;
+            if (++waiting == n) { last_any = got > 0; waiting = 0; got = 0; gen++; cv.notify_all(); return last_any; }
+            cv.wait(l, [&] { return gen != g; });
+            return last_any;
+        }
+    } lockstep;
     std::vector<std::thread> dev_thr;
     for (size_t d = 0; d < devs.size(); d++)
         dev_thr.emplace_back([&, d] {
             Batch *b;
-            while (work_q.pop(b)) {
-                const char *bases; const uint64_t *offs; uint32_t n;
-                kmat_read_batch_view(b->rb, &bases, &offs, nullptr, nullptr, &n, nullptr);
-                b->res.resize(n);
-                if (b->cands.size() < (size_t)n * 20 + 1024) b->cands.resize((size_t)n * 20 + 1024);
-                if (opt.want_lineage && b->lin.size() < (size_t)n * 20 + 1024) b->lin.resize((size_t)n * 20 + 1024);
-                uint64_t nc = 0, nl = 0;
-                for (int attempt = 0; attempt < 3; attempt++) {
-                    b->rc = kmat_label_batch(ctxs[d], bases, offs, n, b->res.data(), b->cands.data(), b->cands.size(), &nc,
-                                             opt.want_lineage ? b->lin.data() : nullptr, b->lin.size(), &nl);
-                    if (b->rc != KMAT_ERR_OVERFLOW) break;
-                    if (nc > b->cands.size()) b->cands.resize(nc + nc / 8);
-                    if (nl > b->lin.size()) b->lin.resize(nl + nl / 8);
+            for (;;) {
+                bool have = work_q.pop(b);
+                if (exchange) { if (!lockstep.any(have, (int)devs.size())) break; }
+                else if (!have) break;
+                const char *bases = nullptr; const uint64_t *offs = nullptr; uint32_t n = 0;
+                static const uint64_t zero_off[1] = {0};
+                if (have) {
+                    kmat_read_batch_view(b->rb, &bases, &offs, nullptr, nullptr, &n, nullptr);
+                    b->res.resize(n);
+                    if (b->cands.size() < (size_t)n * 20 + 1024) b->cands.resize((size_t)n * 20 + 1024);
+                    if (opt.want_lineage && b->lin.size() < (size_t)n * 20 + 1024) b->lin.resize((size_t)n * 20 + 1024);
                 }
-                if (b->rc != KMAT_OK) { b->err = kmat_last_error(); fail("device " + std::to_string(devs[d]) + ": " + b->err); }
-                deliver(b);
+                uint64_t nc = 0, nl = 0;
+                int rc = KMAT_OK;
+                for (int attempt = 0; attempt < 3; attempt++) {
+                    if (exchange) {
+                        rc = kmat_shard_label_batch(ctxs[d], comms[d], have ? bases : "", have ? offs : zero_off, n, have ? b->res.data() : nullptr,
+                                                    have ? b->cands.data() : nullptr, have ? b->cands.size() : 0, &nc,
+                                                    have && opt.want_lineage ? b->lin.data() : nullptr, have ? b->lin.size() : 0, &nl);
+                        // a retry is collective too: every worker learns whether any of them overflowed
+                        const bool again = lockstep.any(rc == KMAT_ERR_OVERFLOW, (int)devs.size());
+                        if (have && rc == KMAT_ERR_OVERFLOW) { if (nc > b->cands.size()) b->cands.resize(nc + nc / 8); if (nl > b->lin.size()) b->lin.resize(nl + nl / 8); }
+                        if (!again) break;
+                    } else {
+                        rc = kmat_label_batch(ctxs[d], bases, offs, n, b->res.data(), b->cands.data(), b->cands.size(), &nc,
+                                              opt.want_lineage ? b->lin.data() : nullptr, b->lin.size(), &nl);
+                        if (rc != KMAT_ERR_OVERFLOW) break;
+                        if (nc > b->cands.size()) b->cands.resize(nc + nc / 8);
+                        if (nl > b->lin.size()) b->lin.resize(nl + nl / 8);
+                    }
+                }
+                if (have) {
+                    b->rc = rc;
+                    if (b->rc != KMAT_OK) { b->err = kmat_last_error(); fail("device " + std::to_string(devs[d]) + ": " + b->err); }
+                    deliver(b);
+                } else if (rc != KMAT_OK && rc != KMAT_ERR_OVERFLOW) fail("device " + std::to_string(devs[d]) + ": " + kmat_last_error());
             }
         });
 
@@ -445,7 +496,7 @@ int main(int argc, char *argv[]) {
         static const char *names[] = {"Error", "ReadTooShort", "NoDbHits", "LowScore"};
         for (auto &kv : nomatch_merge_count) nom_ofs << names[kv.first] << "\t" << kv.second << std::endl;
     }
-    for (size_t d = 0; d < devs.size(); d++) { kmat_ctx_destroy(ctxs[d]); kmat_db_free(dbs[d]); }
+    for (size_t d = 0; d < devs.size(); d++) { kmat_comm_free(comms[d]); kmat_ctx_destroy(ctxs[d]); kmat_db_free(dbs[d]); }
     kmat_inputs_free(inputs);
     const auto t_end = std::chrono::steady_clock::now();
     const double q = std::chrono::duration<double>(t_end - t_query).count(), up = std::chrono::duration<double>(t_query - t_start).count();

@@ -164,3 +164,25 @@ def test_cli_sharded_table_mode(golden_lists, cli, flat_dbs, tmp_path):
     assert "Table sharded over 3 GPUs" in p.stdout
     assert open(ofb + "0.out", encoding="latin-1").read() == g.golden_out("run_rl")      # -t 1: one writer, input order
     assert open(ofb + ".0.30.fastsummary").read() == g.golden_file("run_rl.fastsummary")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["replicated", "sharded", "exchange"])
+def test_cli_two_distinct_devices(mode, golden_lists, cli, flat_dbs, tmp_path):
+    """Two different GPUs driven by one process (one worker thread and one CUDA context per device): replicated table, direct
+    peer reads, and the NCCL exchange (KMAT_TABLE_MODE=exchange: kmat_shard_label_batch, the workers in lockstep).  -t 1 and
+    input order, so the outputs are byte-identical to the reference's."""
+    if api.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    g = golden_lists
+    ofb = str(tmp_path / "rl_")
+    args = ref_args(g, S.OPTION_SETS["run_rl"], flat_dbs[g.name], g.paths["reads"], ofb, 1)
+    env = {"LMAT_DIR": g.workdir, "KMAT_DEVICES": "0,1", "KMAT_BATCH_READS": "50"}
+    if mode != "replicated":
+        env["KMAT_TABLE_MODE"] = mode
+    p = run_cli(cli, args, env=env)
+    assert p.returncode == 0, p.stderr
+    if mode == "exchange":
+        assert "exchanged over NCCL" in p.stdout
+    assert open(ofb + "0.out", encoding="latin-1").read() == g.golden_out("run_rl")
+    assert open(ofb + ".0.30.fastsummary").read() == g.golden_file("run_rl.fastsummary")

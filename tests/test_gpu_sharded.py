@@ -147,3 +147,68 @@ def test_direct_sharded_record_buffer_overflow_is_reported_and_recovers(golden_l
     assert b"list-record buffer" in api.lib().kmat_last_error()
     rr, cc, ll = ctxs[0].label(seqs)                       # the Python wrapper retries on KMAT_ERR_OVERFLOW; the buffer doubles each time
     assert ctxs[0].tails(rr, cc, ll, prn_all=True) == want
+
+
+def _label_through_comm(ctx, comm, device, seqs, round_reads):
+    """One rank's reads through kmat_shard_label_device; returns the result records (numpy) of this rank."""
+    import torch
+    lens = np.array([len(x) for x in seqs], dtype=np.int64)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    flat = b"".join(x.encode("latin-1") for x in seqs) or b"\0"
+    with torch.cuda.device(device):
+        bases = torch.frombuffer(bytearray(flat), dtype=torch.uint8).to(device)
+        d_offs = torch.as_tensor(offs.astype(np.int64), device=device)
+        d_out = torch.zeros(max(1, len(seqs)) * api.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=device)
+        torch.cuda.synchronize(device)
+        st = comm.label_device(ctx, bases.data_ptr(), offs, d_offs.data_ptr(), len(seqs), d_out.data_ptr(), round_reads=round_reads)
+        ctx.sync()
+        torch.cuda.synchronize(device)
+        res = d_out.cpu().numpy().view(api.RESULT_DTYPE)[:len(seqs)].copy()
+    return res, st
+
+
+def test_nccl_exchange_single_rank(golden_lists):
+    """kmat_comm_* / kmat_shard_label_device with a world of one: NCCL send/recv to self; labels of the replicated path."""
+    g = golden_lists
+    db = api.Db.upload(api.Table.from_arrays(g.kmers, g.offs, g.ids, g.kmer_len, g.tid_bytes))
+    ctx = make_ctx(g, db, "run_rl")
+    hdrs, seqs = op.read_fasta_like_reference(g.paths["reads"])
+    seqs = seqs + ["", "ACGT", "N" * 40]
+    want, _, _ = ctx.label(seqs)
+    comm = api.Comm(0, 0, 1, api.Comm.unique_id())
+    res, st = _label_through_comm(ctx, comm, "cuda:0", seqs, round_reads=97)
+    for f in ("status", "tid", "match", "valid_kmers", "cand_kmer_cnt", "n_cand"):
+        assert np.array_equal(res[f], want[f]), f
+    assert np.array_equal(res["score"].view(np.uint32), want["score"].view(np.uint32))
+    assert st[0] == st[1] > 0 and st[3] == (len(seqs) + 96) // 97
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_nccl_exchange_between_gpus(golden_lists, world):
+    """One thread per GPU (what the read_label binary does): shard r on device r, NCCL send/recv between the devices."""
+    import torch
+    if api.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    g = golden_lists
+    t = api.Table.from_arrays(g.kmers, g.offs, g.ids, g.kmer_len, g.tid_bytes)
+    full = api.Db.upload(t)
+    hdrs, seqs = op.read_fasta_like_reference(g.paths["reads"])
+    ref_ctx = make_ctx(g, full, "run_rl")
+    want, _, _ = ref_ctx.label(seqs)
+    cut = [len(seqs) * i // world for i in range(world + 1)]
+    cut[1] = len(seqs) // 2 if world > 2 else cut[1]           # uneven: the others keep serving
+    cut = sorted(cut)
+    uid = api.Comm.unique_id()
+    shards = [api.Db.upload(t, r, r, world) for r in range(world)]
+    ctxs = [make_ctx(g, shards[r], "run_rl") for r in range(world)]
+
+    def rank(r):
+        comm = api.Comm(r, r, world, uid)
+        return _label_through_comm(ctxs[r], comm, f"cuda:{r}", seqs[cut[r]:cut[r + 1]], round_reads=101)
+
+    outs = run_ranks(world, rank)
+    res = np.concatenate([o[0] for o in outs])
+    for f in ("status", "tid", "match", "valid_kmers", "cand_kmer_cnt", "n_cand"):
+        assert np.array_equal(res[f], want[f]), f
+    assert np.array_equal(res["score"].view(np.uint32), want["score"].view(np.uint32))
+    assert sum(o[1][0] for o in outs) == sum(o[1][1] for o in outs) > 0
