@@ -160,6 +160,8 @@ def test_parallel_reader_respects_batch_limits(tmp_path):
     """Parallel mode parses 8 MB segments; kmat_reader_next still hands out at most max_reads reads / max_bases bases per
     batch (a batch always holds at least one read), in file order, with the same records as the sequential reader."""
     import ctypes as C
+    import numpy as np
+    from lmat_b200 import fixtures as fx
     rng = np.random.default_rng(11)
     hdrs = [f"r{i} x" for i in range(3000)]
     seqs = ["".join("ACGT"[c] for c in rng.integers(0, 4, int(rng.integers(30, 300)))) for _ in hdrs]
