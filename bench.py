@@ -489,11 +489,14 @@ def main():
         null_lst = synth.write_null_models_for(tax, workdir)
         codes = synth.make_genomes_gpu(20240, tax, a.genomes, a.genome_len, dev)
         tbl = synth.build_table_gpu(codes, anc_sid)
-        n_kmers, n_lists = tbl.n, int((~tbl.single).sum().item())
+        n_kmers = tbl.n
         sharded_mode = a.table_mode == "sharded"
         direct_mode = a.table_mode == "direct"        # table sharded, probes go to the owner GPU's memory over NVLink (no rounds)
         split = sharded_mode or direct_mode
+        del codes
+        torch.cuda.empty_cache()
         db = synth.upload_table(tbl, local, shard_index=rank if split else 0, shard_count=world if split else 1)
+        n_lists = tbl.n_lists
         del tbl
         torch.cuda.empty_cache()
         inputs = api.Inputs(tree=paths["tree"], depth=paths["depth"], rank=paths["rank"], map16=paths["map16"], null_lst=null_lst, lmat_dir=workdir,
@@ -506,6 +509,7 @@ def main():
         if direct_mode and world > 1:
             from lmat_b200 import sharded
             sharded.attach_peers(ctx, device=dev)
+        codes = synth.make_genomes_gpu(20240, tax, a.genomes, a.genome_len, dev)          # again: they were freed to make room for the table build
         reads = synth.make_reads_gpu(20241 + rank, codes, a.reads, a.read_len)           # weak scaling: every rank its own R reads
         del codes
         torch.cuda.empty_cache()

@@ -307,7 +307,9 @@ extern "C" int kmat_db_build_device(int device, int kmer_len, int tid_bytes, uin
     if (kmat_device_count() <= device) { kmat_set_error("CUDA device %d not available", device); return KMAT_ERR_NO_DEVICE; }
     if (pool_words >= (1ull << 31)) { kmat_set_error("list pool of %llu words exceeds the 31-bit offset range", (unsigned long long)pool_words); return KMAT_ERR_UNSUPPORTED; }
     KM_CUDA(cudaSetDevice(device));
-    return km_db_build(device, kmer_len, tid_bytes, n, n, false, d_kmers, d_payload, d_pool, pool_words, n_stored_ids, shard_index, shard_count, out);
+    const int rc = km_db_build(device, kmer_len, tid_bytes, n, n, false, d_kmers, d_payload, d_pool, pool_words, n_stored_ids, shard_index, shard_count, out);
+    if (rc == KMAT_OK && shard_count > 1) (*out)->pool_shared = true;        // the payloads of every shard index this one pool
+    return rc;
 }
 
 // device copies of the host arrays of an upload: freed on every path out

@@ -1189,6 +1189,7 @@ struct kmat_ctx {
     unsigned char *d_big3 = nullptr, *d_big4 = nullptr; uint64_t cap_big3 = 0; uint32_t big_np_cap = 0, big_threads3 = 0, big_threads4 = 0;
     KmPeer *d_peers = nullptr; uint32_t n_peers = 0; std::vector<void *> ipc_mapped;
     uint32_t *d_pool2_all = nullptr;                                  // every shard's resolved pool, concatenated (list hits stay local)
+    bool pool2_all_alias = false;                                     //   ... or simply d_pool2 when every shard holds the same pool
     uint32_t *d_peer_recs = nullptr; uint64_t cap_peer_recs = 0;      // list records of the pass copied from their owners (km_peer_fetch_kernel)
     unsigned long long *d_peer_cur = nullptr;                         // [0] words used (per pass), [1] list hits dropped for lack of room (monotonic)
     unsigned long long peer_dropped_seen = 0; int peer_grow = 1;
@@ -1226,6 +1227,7 @@ static int km_resolve_lists(kmat_ctx *c) {
         cudaFree(c->d_pool2); c->d_pool2 = nullptr;
         KM_CUDA(cudaMalloc((void **)&c->d_pool2, ((size_t)db->pool_words * mul + 32) * 4));      // + padding: the direct-mode fetch reads two whole sectors from a record's start
         c->pool2_mul = mul;
+        if (c->pool2_all_alias) c->d_pool2_all = c->d_pool2;
     }
     KmResolveParams R;
     R.C = km_ctx_dev(c);
@@ -1328,7 +1330,7 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
     }
     km_shard_free(c->shard);
     for (void *p : c->ipc_mapped) cudaIpcCloseMemHandle(p);
-    cudaFree(c->d_peers); cudaFree(c->d_peer_recs); cudaFree(c->d_peer_cur); cudaFree(c->d_pool2_all);
+    cudaFree(c->d_peers); cudaFree(c->d_peer_recs); cudaFree(c->d_peer_cur); if (!c->pool2_all_alias) cudaFree(c->d_pool2_all);
     cudaFree(c->d_bigq); cudaFree(c->d_bigcnt); cudaFree(c->d_big3); cudaFree(c->d_big4); cudaFree(c->d_pass); cudaFree(c->d_pendq);
     cudaFree(c->d_null_max); cudaFree(c->d_null_cnt); cudaFree(c->d_null_err); cudaFree(c->d_null_bases); cudaFree(c->d_null_offs);
     cudaFree(c->d_hit); cudaFree(c->d_hdr); cudaFree(c->d_out_dev);

@@ -33,6 +33,7 @@ struct kmat_db {
     uint64_t *d_stash_x = nullptr; uint32_t *d_stash_hit = nullptr; uint32_t n_stash = 0;   // overflow stash (see km_probe_x)
     int prefix_shift = 13;
     uint32_t n_sid = 65536;
+    bool pool_shared = false;              // a shard built from the whole table's arrays (kmat_db_build_device): every shard holds the SAME list pool
     int shard_index = 0, shard_count = 1;  // DB-sharded mode: this table holds the k-mers with kmat_shard_of() == shard_index
     std::vector<uint32_t> stored_tids;     // 32-bit tables: dense stored id -> tid
     uint32_t *d_stored_tids = nullptr;     //   the same on the device (gene_label path)

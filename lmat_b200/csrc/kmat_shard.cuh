@@ -337,7 +337,7 @@ extern "C" int kmat_ctx_device_results(kmat_ctx *c, const kmat_read_result **d_o
 struct KmPeerBlob {
     uint32_t magic; int32_t pid, device, shard_index, shard_count;
     int32_t bucket_bits, rem_bits, kmer_bits, tid_bytes, pool2_mul, rkmer, permissive, max_count;
-    int32_t line_m, line_bits;
+    int32_t line_m, line_bits, pool_shared;
     uint32_t n_stash; uint64_t pool_words, line_first;
     uint64_t p_lines, p_slots, p_stash_x, p_stash_hit, p_pool2;                 // raw device pointers (valid inside the exporting process)
     cudaIpcMemHandle_t h_lines, h_slots, h_stash_x, h_stash_hit, h_pool2;       // the same allocations for other processes
@@ -357,6 +357,7 @@ extern "C" int kmat_ctx_peer_export(kmat_ctx *c, kmat_peer_info *out) {
     b.bucket_bits = db->geom.bucket_bits; b.rem_bits = db->geom.rem_bits; b.kmer_bits = db->geom.kmer_bits; b.tid_bytes = db->tid_bytes;
     b.pool2_mul = c->pool2_mul; b.rkmer = c->opt.rkmer_mode != 0; b.permissive = c->opt.permissive != 0; b.max_count = c->opt.max_count;
     b.n_stash = db->n_stash; b.pool_words = db->pool_words;
+    b.pool_shared = db->pool_shared ? 1 : 0;
     b.line_m = db->geom.line_m; b.line_bits = db->geom.line_bits; b.line_first = db->line_first; b.p_lines = (uint64_t)db->d_lines;
     if (db->d_lines) KM_CUDA(cudaIpcGetMemHandle(&b.h_lines, db->d_lines));
     b.p_slots = (uint64_t)db->d_slots; b.p_stash_x = (uint64_t)db->d_stash_x; b.p_stash_hit = (uint64_t)db->d_stash_hit; b.p_pool2 = (uint64_t)c->d_pool2;
@@ -383,7 +384,7 @@ extern "C" int kmat_ctx_peer_attach(kmat_ctx *c, int n_shards, const kmat_peer_i
             kmat_set_error("kmat_ctx_peer_attach: shard %d has a different table geometry (2^%d lines, here 2^%d)", s, b.line_bits, db->geom.line_bits); return KMAT_ERR_UNSUPPORTED; }
         if (b.pool2_mul != c->pool2_mul || b.rkmer != (c->opt.rkmer_mode != 0) || b.permissive != (c->opt.permissive != 0) || b.max_count != c->opt.max_count) {
             kmat_set_error("kmat_ctx_peer_attach: shard %d's context was created with different options (-g / -s / rkmer)", s); return KMAT_ERR_ARG; }
-        if (b.pool_words > (1ull << KM_PEER_SHIFT)) { kmat_set_error("kmat_ctx_peer_attach: shard %d's list pool (%llu words) exceeds the 2^%d-word offset range of direct mode", s, (unsigned long long)b.pool_words, KM_PEER_SHIFT); return KMAT_ERR_UNSUPPORTED; }
+        if (!b.pool_shared && b.pool_words > (1ull << KM_PEER_SHIFT)) { kmat_set_error("kmat_ctx_peer_attach: shard %d's list pool (%llu words) exceeds the 2^%d-word offset range of direct mode", s, (unsigned long long)b.pool_words, KM_PEER_SHIFT); return KMAT_ERR_UNSUPPORTED; }
         KmPeer &p = peers[(size_t)s];
         p.n_stash = b.n_stash; p.pool_base = KM_PEER_NO_BASE;
         p.line_first = b.line_first; p.lines = nullptr; p.slots = nullptr; p.rem_bits = b.rem_bits; p.bucket_mask = (1ull << b.bucket_bits) - 1;
@@ -420,7 +421,14 @@ extern "C" int kmat_ctx_peer_attach(kmat_ctx *c, int n_shards, const kmat_peer_i
     // hits then never leave the GPU again; the hit words carry offsets into the concatenation.  When the pools together
     // are too large for that (KMAT_PEER_LISTS=fetch forces it), list hits are tagged with their owner instead and the
     // records of every pass are fetched from the owners (km_peer_fetch_kernel).
-    {
+    bool all_shared = db->pool_shared;
+    for (int s = 0; s < n_shards; s++) { KmPeerBlob b; memcpy(&b, &all[s], sizeof b); all_shared = all_shared && b.pool_shared && b.pool_words == db->pool_words; }
+    if (all_shared) {
+        // every shard was built from the whole table's arrays and holds the same list pool: this rank's own resolved pool answers
+        // every list hit, nothing to copy or fetch
+        for (int s = 0; s < n_shards; s++) peers[(size_t)s].pool_base = 0;
+        c->d_pool2_all = c->d_pool2; c->pool2_all_alias = true;
+    } else {
         uint64_t total_raw = 0;
         std::vector<uint64_t> raw(n_shards);
         for (int s = 0; s < n_shards; s++) { KmPeerBlob b; memcpy(&b, &all[s], sizeof b); raw[s] = b.pool_words; total_raw += b.pool_words; }

@@ -102,6 +102,39 @@ def build_table_gpu(codes, anc_sid, k=20, chunk_genomes=None):
         del km
     key = torch.cat(keys)
     del keys
+    anc = torch.as_tensor(anc_sid, device=dev)
+    LIMIT = (1 << 31) - 1024                        # torch.sort / unique_consecutive take at most INT_MAX elements
+    if key.numel() <= LIMIT:
+        return _table_from_keys(key, anc, D, gbits, dev)
+    # larger tables (C4: 2.6 G (k-mer, genome) pairs): split by k-mer range -- canonical k-mers of random genomes are close to
+    # uniform below 2^(2k-1) -- build every part on its own and concatenate (k-mers stay ascending; list offsets are rebased)
+    n_parts = int(key.numel() // (LIMIT // 2)) + 1
+    top = 1 << (2 * k + gbits)
+    parts, pool_base = [], 0
+    for pi in range(n_parts):
+        lo, hi = top * pi // (2 * n_parts), (top * (pi + 1) // (2 * n_parts) if pi + 1 < n_parts else top)
+        sub = key[(key >= lo) & (key < hi)]
+        w = _table_from_keys(sub, anc, D, gbits, dev)
+        is_list = w.payload_i64 >= (1 << 31)
+        w.payload_i64 = torch.where(is_list, w.payload_i64 + pool_base, w.payload_i64)
+        pool_base += w.pool_words
+        parts.append(w)
+    del key
+    out = Workload()
+    out.kmers = torch.cat([w.kmers for w in parts])
+    out.payload_i64 = torch.cat([w.payload_i64 for w in parts])
+    out.pool16 = torch.cat([w.pool16[:2 * w.pool_words] for w in parts] + [torch.zeros(2, dtype=torch.int16, device=dev)])
+    out.pool_words = pool_base
+    assert pool_base < (1 << 31)
+    out.n = int(out.kmers.numel())
+    out.counts = None
+    out.single = torch.cat([w.single for w in parts])
+    out.lists = None                               # table_logical / table_to_host are for the small CPU samples only
+    return out
+
+
+def _table_from_keys(key, anc, D, gbits, dev):
+    """The table content of a set of (k-mer << gbits | genome) keys (see build_table_gpu)."""
     key = torch.sort(key).values
     key = torch.unique_consecutive(key)
     kmer_all = key >> gbits
@@ -110,7 +143,6 @@ def build_table_gpu(codes, anc_sid, k=20, chunk_genomes=None):
     kmers, counts = torch.unique_consecutive(kmer_all, return_counts=True)
     n = kmers.numel()
     starts = torch.cumsum(counts, 0) - counts
-    anc = torch.as_tensor(anc_sid, device=dev)
     payload = torch.zeros(n, dtype=torch.int64, device=dev)
     single = counts == 1
     payload[single] = anc[gid_all[starts[single]], D]
@@ -182,7 +214,17 @@ def upload_table(tbl, device_index=0, k=20, shard_index=0, shard_count=1):
     pay32 = torch.empty(tbl.n, dtype=torch.int32, device=tbl.kmers.device)
     pay32.copy_(torch.where(pay >= (1 << 31), pay - (1 << 32), pay).to(torch.int32))
     kmers = tbl.kmers.contiguous()
+    # everything the library does not read goes back to the driver before the table is allocated (a 1.7 G k-mer table takes
+    # 69-137 GB; torch's caching allocator would otherwise sit on the generator's temporaries)
+    n_lists = int((~tbl.single).sum().item())
+    tbl.n_lists = n_lists
+    tbl.payload_i64 = None
+    tbl.counts = None
+    tbl.single = None
+    tbl.lists = None
+    del pay
     torch.cuda.synchronize()
+    torch.cuda.empty_cache()
     db = api.Db.build_device(device_index, k, 2, tbl.n, kmers.data_ptr(), pay32.data_ptr(), tbl.pool16.data_ptr(), tbl.pool_words,
                              shard_index=shard_index, shard_count=shard_count)
     torch.cuda.synchronize()

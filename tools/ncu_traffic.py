@@ -15,12 +15,13 @@ per = {}
 for r in rows[1:]:
     if "km_encode_probe" not in r[ik]:
         continue
-    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[r[iu]]
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(r[iu], 1)
     per.setdefault((r[0], r[ik]), {})[r[im]] = float(r[iv].replace(",", "")) * mult
-launches = [v for v in per.values() if len(v) == 2]
+launches = [v for v in per.values() if "dram__bytes_read.sum" in v and "dram__bytes_write.sum" in v]
 tot = sorted(v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"] for v in launches)
 res = {"kernel": list(per)[0][1], "launches_seen": len(launches), "dram_bytes_per_launch": tot[len(tot) // 2],
        "dram_read_bytes": sorted(v["dram__bytes_read.sum"] for v in launches)[len(launches) // 2],
+       "l2_read_requests": sorted(v.get("lts__t_requests_srcunit_tex_op_read.sum", 0) for v in launches)[len(launches) // 2],
        "reads": reads, "genomes": genomes, "read_len": read_len, "genome_len": genome_len,
        "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, median over the captured launches"}
 json.dump(res, open(out, "w"), indent=1)
