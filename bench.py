@@ -70,8 +70,8 @@ def parse_args():
     a.prune = 10 if a.workload == "C3" else 0
     if a.workload == "C3":
         os.environ.setdefault("KMAT_LINE_DENSITY", "4")          # 2^29 lines = 69 GB instead of 137 GB: the replicated table + its build temporaries fit one GPU
-    if a.workload == "C4" and a.table_mode == "replicated":
-        a.table_mode = "sharded"
+    if a.workload == "C4" and a.table_mode == "replicated" and not os.environ.get("KMAT_LINE_DENSITY"):
+        a.table_mode = "sharded"                                  # with an explicit density (8: a 69 GB first level) one GPU can hold C4 as well
     return a
 
 

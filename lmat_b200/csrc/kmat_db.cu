@@ -684,7 +684,8 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32) km_encode_probe_kernel(Km
 //     distinct k-mer survives" (read_label.cpp:1010-1017) whatever order the atomics were served in.  Keys are the
 //     mixed k-mers (km_mix is a bijection), which the probe needs anyway;
 //   * the home bucket answers ~98.5 % of the lookups; a full home bucket continues with km_probe_x(d = 1).
-// Dynamic shared memory per warp: SETN / 8 B dedup bitmap.
+// Dynamic shared memory per warp: SETN / 8 B dedup bitmap (16 Ki bits for 150 bp reads: ~0.5 suspects per read; the warp-wide
+// settlement of a suspect costs ~50 instructions, 2 per read at 4 Ki bits were 5 % of the kernel).
 // ---------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------
 // K1 + K2 for long reads (257 .. 12000 bases, k <= 20): one CTA per read.  The any-length kernel above keeps the dedup set
@@ -1034,12 +1035,20 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32, NCH <= 5 ? KM_FAST_CTAS :
                 st_extra += st_x;
             }
         }
+        {
+            uint32_t *hp = P.hit + off + lane - (k - 1);                    // hit word of the k-mer that ENDS at this lane's base of chunk 0
 #pragma unroll
-        for (int c = 0; c < NCH; c++) {
-            const int j = (c << 5) + lane, p = j - k + 1;
-            if (p >= 0 && j < len) {
-                P.hit[off + p] = hwv[c];
-                if (P.xq && ((first >> c) & 1)) P.xq[off + p] = xk[c];
+            for (int c = 0; c < NCH; c++) {
+                const int j = (c << 5) + lane;
+                if (j >= k - 1 && j < len) hp[c << 5] = hwv[c];
+            }
+            if (P.xq) {                                                     // DB-sharded encode only: the table keys travel to their owners
+                uint64_t *xp = P.xq + off + lane - (k - 1);
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {
+                    const int j = (c << 5) + lane;
+                    if (j >= k - 1 && j < len && ((first >> c) & 1)) xp[c << 5] = xk[c];
+                }
             }
         }
         valid = km_warp_sum(valid); vgc = km_warp_sum(vgc); vtot = km_warp_sum(vtot);
@@ -1107,8 +1116,8 @@ int km_launch_encode_probe(const kmat_db *db, const char *d_bases, const uint64_
     const bool fast = !d_kmers && !d_flags && max_len <= 256 && db->kmer_len <= 24 && !getenv("KMAT_NO_FAST_PROBE");
     int rc = KMAT_OK;
     const bool peers = P.db.n_peers != 0, line = P.db.line_m != 0;
-    if (fast && max_len <= 160) rc = km_launch_fast_pick<5, 4096>(P, d_stats != nullptr, peers, line, ctas_per_sm, stream);
-    else if (fast) rc = km_launch_fast_pick<8, 8192>(P, d_stats != nullptr, peers, line, ctas_per_sm, stream);
+    if (fast && max_len <= 160) rc = km_launch_fast_pick<5, 16384>(P, d_stats != nullptr, peers, line, ctas_per_sm, stream);
+    else if (fast) rc = km_launch_fast_pick<8, 32768>(P, d_stats != nullptr, peers, line, ctas_per_sm, stream);
     else {
         // mixed / long batches: reads of 257 .. 12000 bases get a CTA each (shared-memory dedup set), the any-length kernel
         // takes the rest

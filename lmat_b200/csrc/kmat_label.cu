@@ -1221,14 +1221,22 @@ static int km_resolve_lists(kmat_ctx *c) {
     if (!db->pool_words) return KMAT_OK;
     if (c->d_pool2 && c->resolved_max_count == c->opt.max_count && c->resolved_permissive == (c->opt.permissive != 0) &&
         c->resolved_rkmer == (c->opt.rkmer_mode != 0)) return KMAT_OK;
+    if (c->pool2_all_alias) {
+        // direct mode over a shared pool: the records of the other shards' lists were merged in at attach time and cannot be
+        // rebuilt by this rank alone
+        kmat_set_error("kmat_ctx_set_opts: -g / -s cannot change after kmat_ctx_peer_attach on a shared list pool; create the contexts with the new options and attach again");
+        return KMAT_ERR_UNSUPPORTED;
+    }
     KM_CUDA(cudaStreamSynchronize(c->stream));
     const int mul = (db->tid_bytes == 2 ? 2 : 1) * (c->opt.permissive ? 2 : 1);
     if (!c->d_pool2 || mul != c->pool2_mul) {
         cudaFree(c->d_pool2); c->d_pool2 = nullptr;
         KM_CUDA(cudaMalloc((void **)&c->d_pool2, ((size_t)db->pool_words * mul + 32) * 4));      // + padding: the direct-mode fetch reads two whole sectors from a record's start
         c->pool2_mul = mul;
-        if (c->pool2_all_alias) c->d_pool2_all = c->d_pool2;
     }
+    // A shard built from the whole table's arrays resolves only the lists ITS k-mers point at (the kernel below walks this
+    // shard's slots); the rest of the pool stays zero so that kmat_ctx_peer_attach can merge the shards' pools word by word
+    if (db->pool_shared) KM_CUDA(cudaMemsetAsync(c->d_pool2, 0, ((size_t)db->pool_words * mul + 32) * 4, c->stream));
     KmResolveParams R;
     R.C = km_ctx_dev(c);
     R.pool2 = c->d_pool2;
@@ -1311,10 +1319,13 @@ extern "C" int kmat_ctx_create(const kmat_db *db, const kmat_inputs *in, const k
 }
 extern "C" int kmat_ctx_set_opts(kmat_ctx *c, const kmat_opts *o) {
     if (!c || !o) return KMAT_ERR_ARG;
+    const kmat_opts before = c->opt;
     c->opt = *o;
     if (c->opt.rkmer_mode) { c->opt.min_kmer = 0; c->opt.min_fnd_kmer = 0; c->opt.permissive = 0; c->opt.want_lineage = 0; }
     KM_CUDA(cudaSetDevice(c->device));
-    return km_resolve_lists(c);          // the resolved lists depend on -g and -s
+    const int rc = km_resolve_lists(c);  // the resolved lists depend on -g and -s
+    if (rc != KMAT_OK) c->opt = before;  // refused: the context keeps the options its lists were resolved for
+    return rc;
 }
 extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
     if (!c) return;

@@ -368,6 +368,15 @@ extern "C" int kmat_ctx_peer_export(kmat_ctx *c, kmat_peer_info *out) {
     return KMAT_OK;
 }
 
+// dst |= src over a resolved list pool (shared-pool shards: every word is non-zero in at most one shard's pool)
+__global__ void __launch_bounds__(256) km_pool_merge_kernel(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, uint64_t words) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < words; i += stride) {
+        const uint32_t v = src[i];
+        if (v) dst[i] = v;
+    }
+}
+
 extern "C" int kmat_ctx_peer_attach(kmat_ctx *c, int n_shards, const kmat_peer_info *all) {
     if (!c || !all || n_shards < 1 || n_shards > KM_MAX_SHARDS) { kmat_set_error("kmat_ctx_peer_attach: bad argument"); return KMAT_ERR_ARG; }
     if (c->d_peers) { kmat_set_error("kmat_ctx_peer_attach: peers already attached"); return KMAT_ERR_ARG; }
@@ -423,11 +432,23 @@ extern "C" int kmat_ctx_peer_attach(kmat_ctx *c, int n_shards, const kmat_peer_i
     // records of every pass are fetched from the owners (km_peer_fetch_kernel).
     bool all_shared = db->pool_shared;
     for (int s = 0; s < n_shards; s++) { KmPeerBlob b; memcpy(&b, &all[s], sizeof b); all_shared = all_shared && b.pool_shared && b.pool_words == db->pool_words; }
-    if (all_shared) {
-        // every shard was built from the whole table's arrays and holds the same list pool: this rank's own resolved pool answers
-        // every list hit, nothing to copy or fetch
-        for (int s = 0; s < n_shards; s++) peers[(size_t)s].pool_base = 0;
+    if (all_shared && db->pool_words) {
+        // every shard was built from the whole table's arrays and indexes the same list pool, but has resolved only the lists of
+        // its own k-mers (km_resolve_lists leaves the rest zero): OR the peers' resolved pools into this rank's -- one bulk
+        // read of every peer's pool over NVLink, once -- and every list hit is answered locally with its offset unchanged.
+        // A peer that merges at the same time only ever turns a zero word into its final value, so the order does not matter.
+        const uint64_t words = db->pool_words * (uint64_t)c->pool2_mul;
+        for (int s = 0; s < n_shards; s++) {
+            peers[(size_t)s].pool_base = 0;
+            if (s == db->shard_index) continue;
+            if (!peers[(size_t)s].pool2) { kmat_set_error("kmat_ctx_peer_attach: shard %d exports no resolved list pool", s); return KMAT_ERR_ARG; }
+            km_pool_merge_kernel<<<148 * 8, 256, 0, c->stream>>>(c->d_pool2, peers[(size_t)s].pool2, words);
+            g_km_launches++;
+        }
+        KM_CUDA(cudaStreamSynchronize(c->stream));
         c->d_pool2_all = c->d_pool2; c->pool2_all_alias = true;
+    } else if (all_shared) {
+        for (int s = 0; s < n_shards; s++) peers[(size_t)s].pool_base = 0;
     } else {
         uint64_t total_raw = 0;
         std::vector<uint64_t> raw(n_shards);

@@ -212,3 +212,61 @@ def test_nccl_exchange_between_gpus(golden_lists, world):
         assert np.array_equal(res[f], want[f]), f
     assert np.array_equal(res["score"].view(np.uint32), want["score"].view(np.uint32))
     assert sum(o[1][0] for o in outs) == sum(o[1][1] for o in outs) > 0
+
+
+def _device_arrays(g, dev="cuda:0"):
+    """The golden table as the device arrays kmat_db_build_device takes: k-mers, payloads (stored id, or LIST | pool word offset)
+    and ONE list pool of [u16 count][u16 id]* records -- the form the bench's generator hands to every shard."""
+    import torch
+    assert g.tid_bytes == 2
+    offs = g.offs.astype(np.int64)
+    cnt = np.diff(offs)
+    n = len(g.kmers)
+    payload = np.zeros(n, dtype=np.int64)
+    single = cnt == 1
+    payload[single] = g.ids[offs[:-1][single]]
+    pool, at = [], 0
+    for i in np.nonzero(~single)[0]:
+        c = int(cnt[i])
+        rec = np.zeros(((1 + c) + 1) // 2 * 2, dtype=np.uint16)
+        rec[0] = c
+        rec[1:1 + c] = g.ids[offs[i]:offs[i] + c]
+        payload[i] = (1 << 31) | at
+        pool.append(rec)
+        at += len(rec) // 2
+    pool16 = np.concatenate(pool + [np.zeros(2, dtype=np.uint16)])
+    pay32 = np.where(payload >= (1 << 31), payload - (1 << 32), payload).astype(np.int32)
+    return (torch.as_tensor(g.kmers.astype(np.int64), device=dev), torch.as_tensor(pay32, device=dev),
+            torch.as_tensor(pool16.view(np.int16), device=dev), at)
+
+
+@pytest.mark.parametrize("world,opts", [(2, "run_rl"), (3, "permissive"), (3, "prune3"), (8, "run_rl")])
+def test_direct_sharded_shared_pool_labels_equal_replicated(golden_lists, world, opts):
+    """Shards built with kmat_db_build_device from the WHOLE table's device arrays (bench.py, C4) share one list pool and each
+    resolves only the lists of its own k-mers; kmat_ctx_peer_attach merges the resolved pools.  (An earlier version aliased
+    the local pool without the merge: list hits owned by another shard then read unresolved records.)"""
+    import torch
+    g = golden_lists
+    kmers, pay32, pool16, pool_words = _device_arrays(g)
+    assert pool_words > 0
+    torch.cuda.synchronize()
+    build = lambda r, w: api.Db.build_device(0, g.kmer_len, 2, len(g.kmers), kmers.data_ptr(), pay32.data_ptr(), pool16.data_ptr(), pool_words,
+                                             shard_index=r, shard_count=w)
+    full = build(0, 1)
+    shards = [build(r, world) for r in range(world)]
+    hdrs, seqs = op.read_fasta_like_reference(g.paths["reads"])
+    ref_ctx = make_ctx(g, full, opts)
+    res, cands, lin = ref_ctx.label(seqs)
+    want = ref_ctx.tails(res, cands, lin, prn_all=True)
+    # the device-built table answers like the uploaded one, which test_gpu_parity.py pins to the reference
+    up_ctx = make_ctx(g, api.Db.upload(api.Table.from_arrays(g.kmers, g.offs, g.ids, g.kmer_len, g.tid_bytes)), opts)
+    r2, c2, l2 = up_ctx.label(seqs)
+    assert up_ctx.tails(r2, c2, l2, prn_all=True) == want
+    ctxs = [make_ctx(g, shards[r], opts) for r in range(world)]
+    sharded.attach_peers_local(ctxs)
+    for r in range(world):
+        mine = seqs[r::world]
+        rr, cc, ll = ctxs[r].label(mine)
+        assert ctxs[r].tails(rr, cc, ll, prn_all=True) == want[r::world], r
+    with pytest.raises(api.KmatError):                    # the merged pool cannot be rebuilt by one rank alone
+        ctxs[0].set_opts(max_count=2)
