@@ -6,6 +6,7 @@
 // on lane 0 from shared memory, in the reference's own operation order (no FMA contraction: every float op is
 // an explicit __f*_rn intrinsic; logf is the glibc algorithm, km_logf).
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -852,11 +853,12 @@ __device__ __forceinline__ void ks_score_one(const KmScoreParams &P, const uint3
 // and scores them in that order, so the 32 reads of a warp have similar loop lengths (the insertion sort of rank_label and
 // the ancestor scans ran with 7-16 of 32 lanes active before: 13.9 -> 9.4 ms per 10 M reads, profiles/r02a_variants.txt).
 // Results do not depend on which thread scores a read.
-#ifndef KS_SORT_ROUNDS
-#define KS_SORT_ROUNDS 4
-#endif
-#define KS_READS_PER_CTA (KS_THREADS * KS_SORT_ROUNDS)
+// KS_SORT_ROUNDS: 4 for large passes; the ~1 M-read chunks of the host-buffer pipeline take 2 -- their grid is only a couple of
+// waves of CTAs, and halving the window halves what the last, partly filled wave costs (e2e 128 -> 132 M reads/s,
+// profiles/r02s_k4_window.txt) while the 10 M-read launch keeps the better sort (9.45 against 9.51 ms).
+template <int KS_SORT_ROUNDS>
 __global__ void __launch_bounds__(KS_THREADS) km_score_kernel(KmScoreParams P) {
+    constexpr int KS_READS_PER_CTA = KS_THREADS * KS_SORT_ROUNDS;
     __shared__ uint32_t s_bin[KB_CMAX + 2];
     __shared__ uint32_t s_r[KS_READS_PER_CTA];
     const uint32_t n_q = P.pend_q ? (uint32_t)(*P.pass_cursor >> KB_PASS_SHIFT) : P.n_reads;
@@ -1496,7 +1498,8 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
         KM_CUDA(cudaGetLastError());
         return KMAT_OK;
     }
-    km_score_kernel<<<(n + KS_READS_PER_CTA - 1) / KS_READS_PER_CTA, KS_THREADS, 0, s2>>>(P);
+    if (n >= (4u << 20)) km_score_kernel<4><<<(n + KS_THREADS * 4 - 1) / (KS_THREADS * 4), KS_THREADS, 0, s2>>>(P);
+    else km_score_kernel<2><<<(n + KS_THREADS * 2 - 1) / (KS_THREADS * 2), KS_THREADS, 0, s2>>>(P);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     km_score_big_kernel<<<c->big_threads4 / 32, 32, 0, s2>>>(P);
@@ -1780,9 +1783,27 @@ static int km_label_host(kmat_ctx *c, const KmHostIO &io, const uint64_t *offs, 
         uint32_t r0 = 0;
         int ci = 0;
         unsigned long long total_c = 0, total_l = 0;
+        // KMAT_PIPE_TRACE=1 (debugging aid): per chunk, when its copies and kernels started and ended on the device and when
+        // the host queued them -- printed to stderr after the call
+        static const bool trace = getenv("KMAT_PIPE_TRACE") != nullptr;
+        struct Tr { cudaEvent_t h0, h1, k0, k1, d0, d1; double t_submit, t_launched, t_drain0, t_drain1; };
+        std::vector<Tr> tr;
+        cudaEvent_t tr_base = nullptr;
+        auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t_host0 = now_ms();
+        if (trace) { cudaEventCreate(&tr_base); cudaEventRecord(tr_base, c->stream); }
+        auto tr_ev = [&](cudaEvent_t *e, cudaStream_t st) { if (trace) { cudaEventCreate(e); cudaEventRecord(*e, st); } };
         while (r0 < n_reads) {
-            // chunk [r0, r1): bounded by reads and by bases (at least one read)
-            uint32_t r1 = std::min<uint64_t>(n_reads, (uint64_t)r0 + chunk_reads);
+            // chunk [r0, r1): bounded by reads and by bases (at least one read).  The first and the last chunk of a large batch
+            // are a quarter of the regular size: nothing overlaps the first chunk's copy in and the last chunk's copy out
+            const uint32_t left = n_reads - r0, quarter = std::max(1u, chunk_reads / 4);
+            uint32_t take = chunk_reads;
+            if (n_reads > chunk_reads) {
+                if (ci == 0) take = quarter;
+                else if (left <= quarter) take = left;
+                else if (left <= chunk_reads + quarter) take = left - quarter;
+            }
+            uint32_t r1 = std::min<uint64_t>(n_reads, (uint64_t)r0 + take);
             if (offs[r1] - offs[r0] > chunk_bases) {
                 uint32_t lo = r0 + 1, hi = r1;                      // largest r1 with offs[r1] - offs[r0] <= chunk_bases
                 while (lo < hi) { const uint32_t mid = lo + (hi - lo + 1) / 2; if (offs[mid] - offs[r0] <= chunk_bases) lo = mid; else hi = mid - 1; }
@@ -1821,15 +1842,18 @@ static int km_label_host(kmat_ctx *c, const KmHostIO &io, const uint64_t *offs, 
             }
             // H2D once the kernels that last read this slot's inputs are done
             if (ci >= 2) KM_CUDA(cudaStreamWaitEvent(c->st_h2d, sl.ev_comp, 0));
+            if (trace) { tr.push_back(Tr{}); tr.back().t_submit = now_ms() - t_host0; tr_ev(&tr.back().h0, c->st_h2d); }
             if (compact) {
                 KM_CUDA(cudaMemcpyAsync(sl.d_codes, io.codes + w0, (size_t)(w1 - w0) * 4, cudaMemcpyHostToDevice, c->st_h2d));
                 if (i_hi > i_lo) KM_CUDA(cudaMemcpyAsync(sl.d_inv, io.inv + i_lo, (size_t)(i_hi - i_lo) * 8, cudaMemcpyHostToDevice, c->st_h2d));
             } else KM_CUDA(cudaMemcpyAsync(sl.d_bases, bases + offs[r0], nb, cudaMemcpyHostToDevice, c->st_h2d));
             KM_CUDA(cudaMemcpyAsync(sl.d_offs, offs + r0, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->st_h2d));
             KM_CUDA(cudaEventRecord(sl.ev_h2d, c->st_h2d));
+            if (trace) tr_ev(&tr.back().h1, c->st_h2d);
             // kernels once the inputs are in and the previous results of this slot have been copied out
             KM_CUDA(cudaStreamWaitEvent(c->stream, sl.ev_h2d, 0));
             if (ci >= 2) KM_CUDA(cudaStreamWaitEvent(c->stream, sl.ev_d2h, 0));
+            if (trace) tr_ev(&tr.back().k0, c->stream);
             if (compact) {
                 km_unpack_kernel<<<(unsigned)((w1 - w0 + 255) / 256), 256, 0, c->stream>>>(sl.d_codes, w1 - w0, (uint4 *)sl.d_bases);
                 g_km_launches++;
@@ -1845,11 +1869,30 @@ static int km_label_host(kmat_ctx *c, const KmHostIO &io, const uint64_t *offs, 
             }
             KM_CUDA(cudaMemcpyAsync(sl.h_cur, c->d_cursors, 16, cudaMemcpyDeviceToHost, c->stream));
             KM_CUDA(cudaEventRecord(sl.ev_comp, c->stream));
-            if (prev.valid && (rc = drain(prev)) != KMAT_OK) return rc;
+            if (trace) { tr_ev(&tr.back().k1, c->stream); tr.back().t_launched = now_ms() - t_host0; }
+            if (prev.valid) {
+                if (trace) { tr[ci - 1].t_drain0 = now_ms() - t_host0; tr_ev(&tr[ci - 1].d0, c->st_d2h); }
+                if ((rc = drain(prev)) != KMAT_OK) return rc;
+                if (trace) { tr[ci - 1].t_drain1 = now_ms() - t_host0; tr_ev(&tr[ci - 1].d1, c->st_d2h); }
+            }
             prev.r0 = r0; prev.r1 = r1; prev.slot = ci & 1; prev.valid = true;
             r0 = r1; ci++;
         }
+        if (trace) { tr[ci - 1].t_drain0 = now_ms() - t_host0; tr_ev(&tr[ci - 1].d0, c->st_d2h); }
         if ((rc = drain(prev)) != KMAT_OK) return rc;
+        if (trace) {
+            tr[ci - 1].t_drain1 = now_ms() - t_host0; tr_ev(&tr[ci - 1].d1, c->st_d2h);
+            cudaStreamSynchronize(c->st_d2h); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->st_h2d);
+            fprintf(stderr, "[kmat pipe trace] %d chunks, host total %.2f ms; device times relative to the call's first event, host times to its start\n", ci, now_ms() - t_host0);
+            fprintf(stderr, "chunk   h2d0   h2d1 |  krn0   krn1 |  d2h0   d2h1 || submit launched drain0 drain1\n");
+            for (int i = 0; i < ci; i++) {
+                float v[6] = {0, 0, 0, 0, 0, 0};
+                cudaEvent_t ev[6] = {tr[i].h0, tr[i].h1, tr[i].k0, tr[i].k1, tr[i].d0, tr[i].d1};
+                for (int j = 0; j < 6; j++) { cudaEventElapsedTime(&v[j], tr_base, ev[j]); cudaEventDestroy(ev[j]); }
+                fprintf(stderr, "%5d %6.2f %6.2f | %6.2f %6.2f | %6.2f %6.2f || %6.2f %6.2f %6.2f %6.2f\n", i, v[0], v[1], v[2], v[3], v[4], v[5], tr[i].t_submit, tr[i].t_launched, tr[i].t_drain0, tr[i].t_drain1);
+            }
+            cudaEventDestroy(tr_base);
+        }
         total_c = c->slot[prev.slot].h_cur[0]; total_l = c->slot[prev.slot].h_cur[1];
         KM_CUDA(cudaStreamSynchronize(c->st_d2h));
         bool again = false;
