@@ -28,6 +28,13 @@
 #define KB_CBIG 512        // candidate taxids per read the slow path holds (reads beyond it: KMAT_ERR_UNSUPPORTED)
 #define KB_LBIG 1024       // lineage entries of the big scoring kernel
 #define KB_BIGQ (1u << 20)  // reads per pass the slow path takes
+#define KMAT_ST_PENDING_HUGE 10 // internal: candidates built by km_cand_huge_kernel (more than KB_CBIG of them), scored by km_score_huge_kernel
+#define KB_CHUGE 16384     // candidate taxids per read of the last-resort path (all working arrays in global memory, linear in the count)
+#define KB_HHASH_BITS 15   // its taxid -> index hash: 2 * KB_CHUGE slots
+#define KB_HLIN (1u << 20) // lineage entries (candidate indices) one read's qualifying members may add up to
+#define KB_HUGEQ (1u << 16) // reads per pass the last-resort path takes
+#define KBH_WARPS 32       // warps (reads in flight) of km_cand_huge_kernel; KBH_THREADS reads in flight in km_score_huge_kernel
+#define KBH_THREADS 64
 #define KB_PASS_SHIFT 40   // per-pass cursor: pairs in the low 40 bits, reads queued for K4 above
 #define KB_PASS_MASK ((1ull << KB_PASS_SHIFT) - 1)
 #define KB_PASS_ONE_READ (1ull << KB_PASS_SHIFT)
@@ -71,6 +78,9 @@ struct KmScoreParams {
     // in big_qa for km_cand_big_kernel, which (like K4 on a lineage overflow) queues them in big_qb for the big scoring kernel
     uint32_t *big_qa, *big_qb; unsigned int *big_cnt;     // big_cnt[0] / [1]: entries of big_qa / big_qb (may exceed KB_BIGQ: the excess is dropped)
     unsigned char *big_scratch3, *big_scratch4; uint32_t big_np_cap, big_threads3, big_threads4;
+    // last resort for reads with more than KB_CBIG candidates: km_cand_big_kernel queues them in huge_qa for km_cand_huge_kernel,
+    // which queues them in huge_qb for km_score_huge_kernel (big_cnt[2] / [3] count the entries)
+    uint32_t *huge_qa, *huge_qb; unsigned char *huge_scratch3, *huge_scratch4;
 };
 
 struct KmRl { float score; uint32_t idx; };          // rank_label element: candidate index + (bias-adjusted) score
@@ -647,10 +657,10 @@ struct KsLinDepthDesc {   // CmpDepth over lineage entries (:159-167), sorting a
 };
 
 // One read.  T: the thread's working arrays (local memory in the regular kernel, a global scratch slot in the big one).
-template <int LIN, typename PermT, bool BIG, typename TT>
+template <int LIN, typename PermT, int BIG /* 0: regular kernel, 1: big, 2: huge */, typename TT>
 __device__ __forceinline__ void ks_score_one(const KmScoreParams &P, const uint32_t r, TT &T) {
     kmat_read_result res = P.out[r];
-    if (res.status != KMAT_ST_PENDING && !(BIG && res.status == KMAT_ST_PENDING_BIG)) return;
+    if (res.status != KMAT_ST_PENDING && !(BIG == 1 && res.status == KMAT_ST_PENDING_BIG) && !(BIG == 2 && res.status == KMAT_ST_PENDING_HUGE)) return;
     const KmCtxDev &X = P.C;
     const int C = (int)res.n_cand;
     const unsigned long long co = res.cand_off;
@@ -891,7 +901,7 @@ __global__ void __launch_bounds__(KS_THREADS) km_score_kernel(KmScoreParams P) {
     __syncthreads();
     const uint32_t total = s_bin[KB_CMAX + 1];
     KsLocal T;
-    for (uint32_t i = threadIdx.x; i < total; i += KS_THREADS) ks_score_one<KB_LIN, uint8_t, false>(P, s_r[i], T);
+    for (uint32_t i = threadIdx.x; i < total; i += KS_THREADS) ks_score_one<KB_LIN, uint8_t, 0>(P, s_r[i], T);
 }
 // The reads of big_qb (more than KB_CMAX candidates, or a lineage the regular kernel could not hold): same code, working
 // arrays in a global scratch slot per thread.
@@ -900,7 +910,7 @@ __global__ void __launch_bounds__(32) km_score_big_kernel(KmScoreParams P) {
     if (slot >= P.big_threads4) return;
     KsLocalBig &T = *(KsLocalBig *)(P.big_scratch4 + (size_t)slot * sizeof(KsLocalBig));
     const uint32_t n = min(P.big_cnt[1], (unsigned int)KB_BIGQ);
-    for (uint32_t q = slot; q < n; q += min(n_threads, P.big_threads4)) ks_score_one<KB_LBIG, uint16_t, true>(P, P.big_qb[q], T);
+    for (uint32_t q = slot; q < n; q += min(n_threads, P.big_threads4)) ks_score_one<KB_LBIG, uint16_t, 1>(P, P.big_qb[q], T);
 }
 
 __global__ void km_cursor_roll_kernel(unsigned long long *cand_cursor, unsigned long long *pass_cursor) {
@@ -932,6 +942,16 @@ __device__ __forceinline__ int kbg_find_or_add(KbBigW &W, int &C, uint32_t v, in
     if (lane < KB_BIGW) W.anc[(size_t)idx * KB_BIGW + lane] = 0ull;
     __syncwarp();
     return idx;
+}
+// more than KB_CBIG candidates: on to km_cand_huge_kernel (all lanes call; lane 0 acts)
+__device__ __forceinline__ void kbg_defer_huge(const KmScoreParams &P, uint32_t r, kmat_read_result &res, int lane) {
+    if (lane != 0) return;
+    res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED;
+    if (P.huge_qa) {
+        const unsigned int q = atomicAdd(P.big_cnt + 2, 1u);
+        if (q < KB_HUGEQ) { P.huge_qa[q] = r; res.status = KMAT_ST_DEFERRED; res.err = 0; }
+    }
+    P.out[r] = res;
 }
 __global__ void __launch_bounds__(KBG_WARPS * 32) km_cand_big_kernel(KmScoreParams P) {
     extern __shared__ __align__(16) unsigned char kbg_smem[];
@@ -1022,7 +1042,7 @@ __global__ void __launch_bounds__(KBG_WARPS * 32) km_cand_big_kernel(KmScorePara
         err = __reduce_max_sync(KM_FULL, err < 0 ? -err : 0);
         overflow = __any_sync(KM_FULL, overflow);
         if (err) { res.status = KMAT_ST_ERROR; res.err = -err; if (lane == 0) P.out[r] = res; continue; }
-        if (overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; if (lane == 0) P.out[r] = res; continue; }
+        if (overflow) { kbg_defer_huge(P, r, res, lane); continue; }
         const int C1 = C;
         if (C1 == 0) { res.status = KMAT_ST_NODBHITS; res.n1 = len; res.n2 = k; if (lane == 0) P.out[r] = res; continue; }
         const uint16_t cand16 = (uint16_t)cand_cnt;
@@ -1076,7 +1096,7 @@ __global__ void __launch_bounds__(KBG_WARPS * 32) km_cand_big_kernel(KmScorePara
                 __syncwarp();
                 if (overflow) break;
             }
-            if (overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; if (lane == 0) P.out[r] = res; continue; }
+            if (overflow) { kbg_defer_huge(P, r, res, lane); continue; }
         }
         for (int i = lane; i < C; i += 32) W.hits[i] = 0;
         __syncwarp();
@@ -1141,6 +1161,286 @@ __global__ void __launch_bounds__(KBG_WARPS * 32) km_cand_big_kernel(KmScorePara
 }
 
 // ---------------------------------------------------------------------------------------------
+// Last resort: reads with more than KB_CBIG candidate taxids (the reference has no bound: std::set / std::map per read,
+// read_label.cpp:698-726).  One warp per read, every working array in a global scratch slot, memory LINEAR in the candidate
+// count: a taxid -> index hash instead of a scan, the lineage of a qualifying member as a list of candidate indices instead of
+// a bit set, and the per-candidate position counts by walking the positions once more with a "last position that counted me"
+// stamp per candidate instead of per-position bit sets.  Same steps and the same results as km_cand_kernel.
+// ---------------------------------------------------------------------------------------------
+struct KbHugeW {
+    uint32_t *nid, *leaf, *key, *hits, *tid, *spec, *stamp, *lin_off, *hash;
+    uint16_t *lin_len, *lin;
+};
+#define KBH_SLOT3_BYTES ((size_t)KB_CHUGE * (8 * 4 + 2) + ((size_t)4 << KB_HHASH_BITS) + (size_t)KB_HLIN * 2)
+__device__ __forceinline__ KbHugeW kbh_carve(unsigned char *base) {
+    KbHugeW W;
+    uint32_t *u = (uint32_t *)base;
+    W.nid = u; W.leaf = u + KB_CHUGE; W.key = u + 2 * KB_CHUGE; W.hits = u + 3 * KB_CHUGE; W.tid = u + 4 * KB_CHUGE; W.spec = u + 5 * KB_CHUGE;
+    W.stamp = u + 6 * KB_CHUGE; W.lin_off = u + 7 * KB_CHUGE; W.hash = u + 8 * KB_CHUGE;
+    W.lin_len = (uint16_t *)(W.hash + ((size_t)1 << KB_HHASH_BITS));
+    W.lin = W.lin_len + KB_CHUGE;
+    return W;
+}
+__device__ __forceinline__ uint32_t kbh_hash(uint32_t v) { return (v * 0x9E3779B1u) >> (32 - KB_HHASH_BITS); }
+// index of `v` among the candidates or -1 (any lane, on its own)
+__device__ __forceinline__ int kbh_find(const KbHugeW &W, uint32_t v) {
+    uint32_t h = kbh_hash(v);
+    for (;;) {
+        const uint32_t s = W.hash[h];
+        if (!s) return -1;
+        if (W.nid[s - 1] == v) return (int)s - 1;
+        h = (h + 1) & ((1u << KB_HHASH_BITS) - 1);
+    }
+}
+// find-or-append `v` (warp-uniform; all lanes call, lane 0 works); -1 when KB_CHUGE is exceeded
+__device__ __forceinline__ int kbh_find_or_add(const KbHugeW &W, int &C, uint32_t v, int lane) {
+    int idx = -1;
+    if (lane == 0) {
+        uint32_t h = kbh_hash(v);
+        for (;;) {
+            const uint32_t s = W.hash[h];
+            if (!s) break;
+            if (W.nid[s - 1] == v) { idx = (int)s - 1; break; }
+            h = (h + 1) & ((1u << KB_HHASH_BITS) - 1);
+        }
+        if (idx < 0 && C < KB_CHUGE) {
+            idx = C; W.hash[h] = (uint32_t)C + 1u;
+            W.nid[C] = v; W.leaf[C] = 0; W.key[C] = 0xFFFFFFFFu; W.hits[C] = 0; W.stamp[C] = 0; W.lin_len[C] = 0; W.lin_off[C] = 0;
+        }
+    }
+    idx = __shfl_sync(KM_FULL, idx, 0);
+    if (idx == C) C++;
+    __syncwarp();
+    return idx;
+}
+// position `stamp` - 1 contains candidate idx: count it once
+__device__ __forceinline__ void kbh_mark(const KbHugeW &W, int idx, uint32_t stamp) {
+    if (atomicExch(W.stamp + idx, stamp) != stamp) atomicAdd(W.hits + idx, 1u);
+}
+__global__ void __launch_bounds__(128) km_cand_huge_kernel(KmScoreParams P) {
+    const KmCtxDev &X = P.C;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t nq = min(P.big_cnt[2], (unsigned int)KB_HUGEQ);
+    if (warp_global >= nq) return;
+    const KbHugeW W = kbh_carve(P.huge_scratch3 + (size_t)warp_global * KBH_SLOT3_BYTES);
+    const int k = X.db.kmer_len;
+    const bool permissive = X.opt.permissive != 0;
+    const unsigned long long cand_base = *P.cand_cursor;
+    for (uint32_t q = warp_global; q < nq; q += n_warps) {
+        const uint32_t r = P.huge_qa[q];
+        const uint64_t off = P.offs[r];
+        const int len = (int)(P.offs[r + 1] - off);
+        const int np = len - k + 1;
+        const int2 hd = P.hdr[r];
+        kmat_read_result res;
+        memset(&res, 0, sizeof res);
+        res.valid_kmers = hd.x; res.bin_sel = hd.y; res.match = KMAT_NOMATCH;
+        if (np <= 0 || np > 0xFFFF) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; if (lane == 0) P.out[r] = res; continue; }
+        for (uint32_t i = lane; i < (1u << KB_HHASH_BITS); i += 32) W.hash[i] = 0;
+        __syncwarp();
+        int C = 0, cand_cnt = 0, fnd_cnt = 0, err = 0;
+        bool overflow = false;
+        // ---- per position: members in insertion order (as kb_chunk; the position sets are not kept)
+        const int nch = (np + 31) >> 5;
+        for (int c = 0; c < nch && !overflow; c++) {
+            const int p = (c << 5) + lane;
+            const uint32_t hw = p < np ? __ldg(P.hit + off + p) : KM_HIT_INVALID;
+            uint32_t a = 0, b = 0, v0 = KMAT_NONE;
+            const uint32_t *rec = nullptr;
+            if (hw != KM_HIT_INVALID) {
+                cand_cnt++;
+                if (hw != KM_HIT_MISS) {
+                    if (!(hw & KM_HIT_LIST)) {
+                        const uint32_t e = hw < X.n_sid ? __ldg(X.sid2nid + hw) : KMAT_NONE;
+                        if (e == KMAT_NONE) err = KMAT_ERR_BAD_TAXID;
+                        else if (!(e & KB_SID_DROP)) {
+                            v0 = ((e & KB_SID_HUMAN) && !X.opt.rkmer_mode) ? X.nid_human : (e & KB_SID_NIDMASK); a = 1;
+                            if (permissive) b = (kb_nodeA(X, v0).meta & KM_META_DEPTH_MASK) ? 1 : 0;
+                        }
+                    } else {
+                        rec = kb_rec_of(X, hw);
+                        const uint32_t h = __ldg(rec);
+                        if (h == KR_ERR_BAD) { err = KMAT_ERR_BAD_TAXID; rec = nullptr; }
+                        else { a = h & 0xFFFFu; if (permissive) { b = rec[1]; rec += 2; } else rec += 1; }
+                    }
+                }
+            }
+            if (a) fnd_cnt++;
+            uint32_t seqno = 0, bi = 0, pq = 0, poff = 0, plen = 0;
+            for (;;) {
+                uint32_t val = KMAT_NONE;
+                if (seqno < a) val = rec ? rec[seqno] : v0;
+                else if (permissive) {
+                    while (bi < b && pq >= plen) {
+                        const KmNodeB nb = kb_nodeB(X, rec ? rec[a + bi] : v0);
+                        poff = nb.path_off; plen = nb.path_len; pq = 0; bi++;
+                    }
+                    if (pq < plen) val = X.paths[poff + pq++];
+                }
+                uint32_t pending = __ballot_sync(KM_FULL, val != KMAT_NONE);
+                if (!pending) break;
+                while (pending) {
+                    const int leader = __ffs(pending) - 1;
+                    const uint32_t v = __shfl_sync(KM_FULL, val, leader);
+                    const uint32_t grp = __ballot_sync(KM_FULL, val == v);
+                    const int idx = kbh_find_or_add(W, C, v, lane);
+                    if (idx < 0) { overflow = true; break; }
+                    if (lane == 0) {
+                        const uint32_t key = ((uint32_t)((c << 5) + leader) << 16) | min(seqno, 0xFFFFu);
+                        W.key[idx] = min(W.key[idx], key); W.leaf[idx] += __popc(grp);
+                    }
+                    pending &= ~grp;
+                }
+                if (overflow) break;
+                seqno++;
+            }
+            __syncwarp();
+        }
+        cand_cnt = km_warp_sum(cand_cnt); fnd_cnt = km_warp_sum(fnd_cnt);
+        err = __reduce_max_sync(KM_FULL, err < 0 ? -err : 0);
+        overflow = __any_sync(KM_FULL, overflow);
+        if (err) { res.status = KMAT_ST_ERROR; res.err = -err; if (lane == 0) P.out[r] = res; continue; }
+        if (overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; if (lane == 0) P.out[r] = res; continue; }
+        const int C1 = C;
+        if (C1 == 0) { res.status = KMAT_ST_NODBHITS; res.n1 = len; res.n2 = k; if (lane == 0) P.out[r] = res; continue; }
+        const uint16_t cand16 = (uint16_t)cand_cnt;
+        res.cand_kmer_cnt = cand16;
+        if (fnd_cnt < X.opt.min_fnd_kmer || (int)cand16 < X.opt.min_kmer) {
+            res.status = KMAT_ST_SILENT; res.match = KMAT_NOMATCH; res.tid = 0; res.score = -1.0f;
+            if (lane == 0) P.out[r] = res;
+            continue;
+        }
+        if (!permissive) {
+            // ---- node data of the members; representative strain per species -> which members bring their lineage
+            for (int i = lane; i < C1; i += 32) {
+                const KmNodeA na = kb_nodeA(X, W.nid[i]);
+                W.tid[i] = na.tid; W.spec[i] = na.species_anc; W.leaf[i] = (W.leaf[i] & 0x3FFFFFFFu) | (((na.meta >> KM_META_RANK_SHIFT) & 3u) << 30);
+            }
+            __syncwarp();
+            for (int i = lane; i < C1; i += 32) {
+                const bool strain = (W.leaf[i] >> 30) == 1;
+                bool qual = !strain;
+                if (strain && W.spec[i] != KMAT_NONE) {
+                    bool beaten = false;
+                    for (int j = 0; j < C1 && !beaten; j++)
+                        beaten = (W.leaf[j] >> 30) == 1 && W.spec[j] == W.spec[i] && (W.leaf[j] > W.leaf[i] || (W.leaf[j] == W.leaf[i] && W.tid[j] < W.tid[i]));
+                    qual = !beaten;
+                }
+                W.hits[i] = qual ? 1u : 0u;                 // "still to expand" marker until the counts are taken
+            }
+            __syncwarp();
+            // ---- lineage expansion in (first position, taxid) order: the appended ancestors take the next indices; the
+            //      lineage of a member is kept as the list of its ancestors' candidate indices
+            uint32_t lin_used = 0;
+            for (;;) {
+                unsigned long long mine = ~0ull;
+                for (int i = lane; i < C1; i += 32)
+                    if (W.hits[i]) { const unsigned long long kk = ((unsigned long long)(W.key[i] >> 16) << 32) | W.tid[i]; if (kk < mine) mine = kk; }
+                const unsigned long long best = kb_warp_min64(mine);
+                if (best == ~0ull) break;
+                int s2 = -1;
+                for (int i = lane; i < C1; i += 32)
+                    if (W.hits[i] && ((((unsigned long long)(W.key[i] >> 16) << 32) | W.tid[i]) == best)) s2 = i;
+                s2 = __reduce_max_sync(KM_FULL, s2);
+                const KmNodeB nb = kb_nodeB(X, W.nid[s2]);
+                if (lin_used + nb.path_len > KB_HLIN || nb.path_len > 0xFFFFu) { overflow = true; break; }
+                if (lane == 0) { W.hits[s2] = 0; W.lin_off[s2] = lin_used; W.lin_len[s2] = (uint16_t)nb.path_len; }
+                for (uint32_t c0 = 0; c0 < nb.path_len && !overflow; c0 += 32) {
+                    const uint32_t av = c0 + lane < nb.path_len ? X.paths[nb.path_off + c0 + lane] : KMAT_NONE;
+                    const int cnt = min(32u, nb.path_len - c0);
+                    for (int z = 0; z < cnt; z++) {
+                        const int idx = kbh_find_or_add(W, C, __shfl_sync(KM_FULL, av, z), lane);
+                        if (idx < 0) { overflow = true; break; }
+                        if (lane == 0) W.lin[lin_used + c0 + z] = (uint16_t)idx;
+                    }
+                }
+                lin_used += nb.path_len;
+                __syncwarp();
+                if (overflow) break;
+            }
+            if (overflow) { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; if (lane == 0) P.out[r] = res; continue; }
+        }
+        for (int i = lane; i < C; i += 32) { W.hits[i] = 0; W.stamp[i] = 0; }
+        __syncwarp();
+        // ---- hits per candidate = positions whose expanded set holds it: one position after the other, the lanes over its
+        //      members (and their lineages); stamp[idx] = last position that counted idx
+        for (int p = 0; p < np; p++) {
+            const uint32_t hw = __ldg(P.hit + off + p), stamp = (uint32_t)p + 1u;
+            if (hw == KM_HIT_INVALID || hw == KM_HIT_MISS) continue;                       // warp-uniform
+            uint32_t a = 0, b = 0, v0 = KMAT_NONE;
+            const uint32_t *rec = nullptr;
+            if (!(hw & KM_HIT_LIST)) {
+                const uint32_t e = __ldg(X.sid2nid + hw);                                  // checked in the first walk
+                if (e & KB_SID_DROP) continue;
+                v0 = ((e & KB_SID_HUMAN) && !X.opt.rkmer_mode) ? X.nid_human : (e & KB_SID_NIDMASK); a = 1;
+                if (permissive) b = (kb_nodeA(X, v0).meta & KM_META_DEPTH_MASK) ? 1 : 0;
+            } else {
+                rec = kb_rec_of(X, hw);
+                a = __ldg(rec) & 0xFFFFu;
+                if (permissive) { b = rec[1]; rec += 2; } else rec += 1;
+            }
+            for (uint32_t m = lane; m < a; m += 32) {
+                const int idx = kbh_find(W, rec ? rec[m] : v0);
+                if (idx < 0) continue;                                                     // cannot happen: the first walk added every member
+                kbh_mark(W, idx, stamp);
+                if (!permissive && idx < C1) {
+                    const uint32_t lo = W.lin_off[idx], ll = W.lin_len[idx];
+                    for (uint32_t z = 0; z < ll; z++) kbh_mark(W, (int)W.lin[lo + z], stamp);
+                }
+            }
+            for (uint32_t bi = 0; bi < b; bi++) {                                          // permissive: the root paths of the b owners
+                const KmNodeB nb = kb_nodeB(X, rec ? rec[a + bi] : v0);
+                for (uint32_t z = lane; z < nb.path_len; z += 32) { const int idx = kbh_find(W, X.paths[nb.path_off + z]); if (idx >= 0) kbh_mark(W, idx, stamp); }
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+        // ---- hand over in taxid_lst order: members by first appearance (rank of the key), then the appended ancestors
+        unsigned long long co = 0;
+        if (lane == 0) co = atomicAdd(P.pass_cursor, (unsigned long long)C);
+        co = cand_base + (kb_shfl64(co, 0) & KB_PASS_MASK);
+        res.status = KMAT_ST_PENDING_HUGE; res.n_cand = (uint32_t)C; res.cand_off = co;
+        if (P.cands && co + C <= P.cand_cap) {
+            for (int i = lane; i < C; i += 32) {
+                uint32_t ord = (uint32_t)i;
+                if (i < C1) { ord = 0; const uint32_t ki = W.key[i]; for (int j = 0; j < C1; j++) ord += W.key[j] < ki; }
+                P.cands[co + ord] = kmat_pair{W.nid[i], __uint_as_float(W.hits[i])};
+            }
+        } else { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_OVERFLOW; }
+        if (lane == 0) {
+            if (res.status == KMAT_ST_PENDING_HUGE) {
+                const unsigned int q2 = atomicAdd(P.big_cnt + 3, 1u);
+                if (q2 < KB_HUGEQ) P.huge_qb[q2] = r; else { res.status = KMAT_ST_ERROR; res.err = KMAT_ERR_UNSUPPORTED; }
+            }
+            P.out[r] = res;
+        }
+        __syncwarp();
+    }
+}
+// The working arrays of ks_score_one for a read of up to KB_CHUGE candidates: views into a global scratch slot
+struct KsHuge {
+    uint32_t *nid, *tid, *tin, *tout; float *score; uint16_t *depth; uint8_t *flags, *cls; KmRl *rl;
+    uint32_t *l_tid, *l_tin, *l_tout; float *l_score; uint16_t *l_depth; uint8_t *l_nogood; uint16_t *l_perm;
+    float *track_val; uint8_t *track_has;
+};
+#define KBH_SLOT4_BYTES ((size_t)KB_CHUGE * (4 * 5 + 8 + 2 + 1 + 1) + (size_t)KB_LBIG * (4 * 4 + 2 + 2 + 2) + 64 * 4 + 64)
+__global__ void __launch_bounds__(32) km_score_huge_kernel(KmScoreParams P) {
+    const uint32_t slot = blockIdx.x * 32 + threadIdx.x, n_threads = gridDim.x * 32;
+    const uint32_t n = min(P.big_cnt[3], (unsigned int)KB_HUGEQ);
+    if (slot >= n) return;
+    unsigned char *b = P.huge_scratch4 + (size_t)slot * KBH_SLOT4_BYTES;
+    KsHuge T;
+    T.nid = (uint32_t *)b; T.tid = T.nid + KB_CHUGE; T.tin = T.tid + KB_CHUGE; T.tout = T.tin + KB_CHUGE; T.score = (float *)(T.tout + KB_CHUGE);
+    T.rl = (KmRl *)(T.score + KB_CHUGE);
+    T.l_tid = (uint32_t *)(T.rl + KB_CHUGE); T.l_tin = T.l_tid + KB_LBIG; T.l_tout = T.l_tin + KB_LBIG; T.l_score = (float *)(T.l_tout + KB_LBIG);
+    T.track_val = T.l_score + KB_LBIG;
+    T.depth = (uint16_t *)(T.track_val + 64); T.l_depth = T.depth + KB_CHUGE; T.l_perm = T.l_depth + KB_LBIG;
+    T.flags = (uint8_t *)(T.l_perm + KB_LBIG); T.cls = T.flags + KB_CHUGE; T.l_nogood = T.cls + KB_CHUGE; T.track_has = T.l_nogood + KB_LBIG;
+    for (uint32_t q = slot; q < n; q += n_threads) ks_score_one<KB_LBIG, uint16_t, 2>(P, P.huge_qb[q], T);
+}
+
+// ---------------------------------------------------------------------------------------------
 // kmat_ctx
 // ---------------------------------------------------------------------------------------------
 struct KmShardState;
@@ -1188,6 +1488,7 @@ struct kmat_ctx {
     unsigned long long *d_pass = nullptr;            // per-pass packed cursor (KmScoreParams::pass_cursor)
     uint32_t *d_pendq = nullptr; uint64_t cap_pendq = 0;
     uint32_t *d_bigq = nullptr; unsigned int *d_bigcnt = nullptr;
+    unsigned char *d_huge3 = nullptr, *d_huge4 = nullptr;             // scratch slots of km_cand_huge_kernel / km_score_huge_kernel
     unsigned char *d_big3 = nullptr, *d_big4 = nullptr; uint64_t cap_big3 = 0; uint32_t big_np_cap = 0, big_threads3 = 0, big_threads4 = 0;
     KmPeer *d_peers = nullptr; uint32_t n_peers = 0; std::vector<void *> ipc_mapped;
     uint32_t *d_pool2_all = nullptr;                                  // every shard's resolved pool, concatenated (list hits stay local)
@@ -1344,7 +1645,7 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
     km_shard_free(c->shard);
     for (void *p : c->ipc_mapped) cudaIpcCloseMemHandle(p);
     cudaFree(c->d_peers); cudaFree(c->d_peer_recs); cudaFree(c->d_peer_cur); if (!c->pool2_all_alias) cudaFree(c->d_pool2_all);
-    cudaFree(c->d_bigq); cudaFree(c->d_bigcnt); cudaFree(c->d_big3); cudaFree(c->d_big4); cudaFree(c->d_pass); cudaFree(c->d_pendq);
+    cudaFree(c->d_bigq); cudaFree(c->d_bigcnt); cudaFree(c->d_big3); cudaFree(c->d_big4); cudaFree(c->d_huge3); cudaFree(c->d_huge4); cudaFree(c->d_pass); cudaFree(c->d_pendq);
     cudaFree(c->d_null_max); cudaFree(c->d_null_cnt); cudaFree(c->d_null_err); cudaFree(c->d_null_bases); cudaFree(c->d_null_offs);
     cudaFree(c->d_hit); cudaFree(c->d_hdr); cudaFree(c->d_out_dev);
     if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
@@ -1453,8 +1754,11 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
     const uint32_t KBIG_THREADS = L.max_len > 1024 ? 24576u : 2048u;
     const uint32_t np_need = (uint32_t)std::max<int>(1, (int)L.max_len - c->db->kmer_len + 1);
     if (!c->d_bigq) {
-        KM_CUDA(cudaMalloc((void **)&c->d_bigq, (size_t)2 * KB_BIGQ * 4));
-        KM_CUDA(cudaMalloc((void **)&c->d_bigcnt, 8));
+        KM_CUDA(cudaMalloc((void **)&c->d_bigq, ((size_t)2 * KB_BIGQ + 2 * KB_HUGEQ) * 4));
+        KM_CUDA(cudaMalloc((void **)&c->d_bigcnt, 16));
+        // the last-resort path (more than KB_CBIG candidates): KBH_WARPS + KBH_THREADS scratch slots, ~120 MB
+        KM_CUDA(cudaMalloc((void **)&c->d_huge3, (size_t)KBH_WARPS * KBH_SLOT3_BYTES));
+        KM_CUDA(cudaMalloc((void **)&c->d_huge4, (size_t)KBH_THREADS * KBH_SLOT4_BYTES));
     }
     if (KBIG_THREADS > c->big_threads4) {
         KM_CUDA(cudaStreamSynchronize(s2));
@@ -1474,7 +1778,8 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
     }
     P.big_qa = c->d_bigq; P.big_qb = c->d_bigq + KB_BIGQ; P.big_cnt = c->d_bigcnt;
     P.big_scratch3 = c->d_big3; P.big_scratch4 = c->d_big4; P.big_np_cap = c->big_np_cap; P.big_threads3 = c->big_threads3; P.big_threads4 = c->big_threads4;
-    KM_CUDA(cudaMemsetAsync(c->d_bigcnt, 0, 8, s2));
+    P.huge_qa = c->d_bigq + 2 * KB_BIGQ; P.huge_qb = P.huge_qa + KB_HUGEQ; P.huge_scratch3 = c->d_huge3; P.huge_scratch4 = c->d_huge4;
+    KM_CUDA(cudaMemsetAsync(c->d_bigcnt, 0, 16, s2));
     const int want_grid = (int)((n + KB_WARPS - 1) / KB_WARPS);
     const int g0 = cand_ctas_per_sm > 0 ? std::min(c->cand_grid[0], cand_ctas_per_sm * c->sms) : c->cand_grid[0];
     if (variant == 0) km_cand_kernel<5><<<std::max(1, std::min(g0, want_grid)), KB_WARPS * 32, 0, s2>>>(P);
@@ -1487,6 +1792,9 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
     KM_CUDA(cudaGetLastError());
     // the (rare) reads K3 could not hold in registers; an empty queue costs two tiny launches
     km_cand_big_kernel<<<(c->big_threads3 + KBG_WARPS - 1) / KBG_WARPS, KBG_WARPS * 32, KBG_WARPS * sizeof(KbBigW), s2>>>(P);
+    g_km_launches++;
+    KM_CUDA(cudaGetLastError());
+    km_cand_huge_kernel<<<KBH_WARPS / 4, 128, 0, s2>>>(P);        // the reads even that one could not hold (an empty queue: every warp leaves at once)
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     if (ev_mid) KM_CUDA(cudaEventRecord(ev_mid, s2));
@@ -1503,6 +1811,9 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     km_score_big_kernel<<<c->big_threads4 / 32, 32, 0, s2>>>(P);
+    g_km_launches++;
+    KM_CUDA(cudaGetLastError());
+    km_score_huge_kernel<<<KBH_THREADS / 32, 32, 0, s2>>>(P);
     g_km_launches++;
     KM_CUDA(cudaGetLastError());
     km_cursor_roll_kernel<<<1, 1, 0, s2>>>(c->d_cursors, c->d_pass);

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) km_nullacc_kernel(KmNullParams N) {
     const kmat_read_result *o = N.out + r;
     const int status = o->status;
     if (status == KMAT_ST_ERROR) { atomicAdd(N.n_err, 1ull); return; }
-    if (status != KMAT_ST_PENDING && status != KMAT_ST_PENDING_BIG) return;                   // shorter than k, no valid k-mer, or no taxid at all: nothing to count
+    if (status != KMAT_ST_PENDING && status != KMAT_ST_PENDING_BIG && status != KMAT_ST_PENDING_HUGE) return;                   // shorter than k, no valid k-mer, or no taxid at all: nothing to count
     const uint32_t bucket = (uint32_t)((N.first_index + r) % KMAT_NULL_BUCKETS);
     const float valid = (float)o->valid_kmers;
     const kmat_pair *cp = N.cands + o->cand_off;
