@@ -399,6 +399,9 @@ int kmat_reader_open(const char *path, int fastq, kmat_reader **out);
 int kmat_reader_open_mt(const char *path, int fastq, int threads, kmat_reader **out);
 void kmat_reader_close(kmat_reader *);
 kmat_read_batch *kmat_read_batch_new(void);
+/* The same, with the bases handed out from page-locked memory (kmat_host_alloc): kmat_label_batch then copies them to the
+ * device by DMA instead of through the driver's staging buffer.  Falls back to pageable memory when pinning fails. */
+kmat_read_batch *kmat_read_batch_new_pinned(void);
 void kmat_read_batch_free(kmat_read_batch *);
 /* Fill `b` with up to max_reads reads / about max_bases bases (at least one read).  Returns the number of
  * reads (0 = end of input) or a negative KMAT_ERR_*. */

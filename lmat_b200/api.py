@@ -52,7 +52,7 @@ EXPORTS = [
     "kmat_ctx_create", "kmat_ctx_set_opts", "kmat_ctx_destroy", "kmat_label_batch", "kmat_label_batch_device",
     "kmat_pack_words", "kmat_pack_reads", "kmat_label_batch_packed", "kmat_result_expand",
     "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_set_pipeline", "kmat_gene_batch", "kmat_shard_encode", "kmat_shard_serve", "kmat_shard_finish", "kmat_ctx_device_results", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench", "kmat_gather_bench_peer",
-    "kmat_set_l2_fetch_granularity", "kmat_reader_open", "kmat_reader_open_mt", "kmat_reader_close", "kmat_read_batch_new", "kmat_read_batch_free",
+    "kmat_set_l2_fetch_granularity", "kmat_reader_open", "kmat_reader_open_mt", "kmat_reader_close", "kmat_read_batch_new", "kmat_read_batch_new_pinned", "kmat_read_batch_free",
     "kmat_reader_next", "kmat_read_batch_view", "kmat_tally_class", "kmat_host_alloc", "kmat_host_free",
     "kmat_ctx_peer_export", "kmat_ctx_peer_attach", "kmat_comm_unique_id", "kmat_comm_init", "kmat_comm_free", "kmat_shard_label_device", "kmat_shard_label_batch",
     "kmat_kcov_create", "kmat_kcov_add", "kmat_kcov_finish", "kmat_kcov_query", "kmat_kcov_free",
@@ -139,6 +139,7 @@ def lib():
     L.kmat_reader_open_mt.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
     L.kmat_reader_close.argtypes = [vp]
     L.kmat_read_batch_new.restype = vp
+    L.kmat_read_batch_new_pinned.restype = vp
     L.kmat_read_batch_free.argtypes = [vp]
     L.kmat_reader_next.restype = C.c_int64
     L.kmat_reader_next.argtypes = [vp, C.c_uint32, C.c_uint64, vp]
@@ -600,12 +601,13 @@ def gather_bench_peer(device, mem_device, span_bytes=1 << 30, access_bytes=32, n
     return g.value, s.value
 
 
-def read_file(path, fastq=False, max_reads=1 << 20, max_bases=1 << 28, threads=1):
-    """(headers, reads) through kmat_reader_* -- the host parser that replaces read_label.cpp:1651-1732."""
+def read_file(path, fastq=False, max_reads=1 << 20, max_bases=1 << 28, threads=1, pinned=False):
+    """(headers, reads) through kmat_reader_* -- the host parser that replaces read_label.cpp:1651-1732.
+    pinned: the batch hands its bases out from page-locked memory (what the read_label binary does)."""
     L = lib()
     r, hdrs, seqs = C.c_void_p(), [], []
     _check(L.kmat_reader_open_mt(_b(path), int(fastq), int(threads), C.byref(r)))
-    b = C.c_void_p(L.kmat_read_batch_new())
+    b = C.c_void_p(L.kmat_read_batch_new_pinned() if pinned else L.kmat_read_batch_new())
     try:
         while True:
             n = L.kmat_reader_next(r, max_reads, max_bases, b)

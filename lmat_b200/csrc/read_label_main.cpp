@@ -42,11 +42,34 @@
 
 namespace {
 
+// Result buffers of a batch in page-locked memory (kmat_host_alloc; plain memory when pinning fails): the copies back from the
+// device are then DMA transfers that overlap the kernels instead of staged pageable copies (~6 GB/s, the device worker's time).
+template <typename T>
+struct PinBuf {
+    T *p = nullptr; size_t cap = 0; bool pinned = false;
+    PinBuf() = default;
+    PinBuf(const PinBuf &) = delete;
+    PinBuf &operator=(const PinBuf &) = delete;
+    ~PinBuf() { release(); }
+    void release() { if (p) { if (pinned) kmat_host_free(p); else free(p); } p = nullptr; cap = 0; }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    size_t size() const { return cap; }
+    T &operator[](size_t i) { return p[i]; }
+    void reserve(size_t n) {               // contents are not kept
+        if (n <= cap) return;
+        release();
+        n += n / 8;
+        p = (T *)kmat_host_alloc(n * sizeof(T)); pinned = p != nullptr;
+        if (!p) p = (T *)malloc(n * sizeof(T));
+        cap = p ? n : 0;
+    }
+};
 struct Batch {
     uint64_t seq = 0;
     kmat_read_batch *rb = nullptr;
-    std::vector<kmat_read_result> res;
-    std::vector<kmat_pair> cands, lin;
+    PinBuf<kmat_read_result> res;
+    PinBuf<kmat_pair> cands, lin;
     int rc = 0;
     std::string err;
 };
@@ -215,6 +238,9 @@ int main(int argc, char *argv[]) {
     std::vector<kmat_db *> dbs(devs.size(), nullptr);
     std::vector<kmat_ctx *> ctxs(devs.size(), nullptr);
     std::vector<kmat_comm *> comms(devs.size(), nullptr);
+    // replicated table: a second context per GPU (its own streams and batch buffers over the same table) driven by a second worker
+    // thread, so that one batch's copies overlap the other's kernels (KMAT_WORKERS_PER_GPU=1 switches it off)
+    std::vector<kmat_ctx *> ctxs2(devs.size(), nullptr);
     bool exchange = false;
     {
         std::vector<std::thread> up;
@@ -239,6 +265,8 @@ int main(int argc, char *argv[]) {
             up.emplace_back([&, d] {
                 urc[d] = kmat_db_upload(table, devs[d], split ? (int)d : 0, n_sh, &dbs[d]);
                 if (urc[d] == KMAT_OK) urc[d] = kmat_ctx_create(dbs[d], inputs, &opt, &ctxs[d]);
+                const char *wpg = getenv("KMAT_WORKERS_PER_GPU");
+                if (urc[d] == KMAT_OK && !split && !(wpg && atoi(wpg) == 1)) urc[d] = kmat_ctx_create(dbs[d], inputs, &opt, &ctxs2[d]);
                 if (urc[d] != KMAT_OK) uerr[d] = kmat_last_error();
             });
         for (auto &t : up) t.join();
@@ -283,13 +311,18 @@ int main(int argc, char *argv[]) {
     const uint64_t batch_bases = (uint64_t)batch_reads * 400;
     // batches in flight: one being read, two per GPU (one queued), one per writer + one waiting for it; the buffers are
     // reused, so a small pool also keeps the working set (and its first-touch page faults) small
-    const size_t n_inflight = 2 * devs.size() + (size_t)n_threads + 3;
+    const size_t n_inflight = 4 * devs.size() + (size_t)n_threads + 3;
     Channel<Batch *> free_q(n_inflight + 1), work_q(n_inflight + 1);
     std::vector<Batch> pool(n_inflight);
-    for (auto &b : pool) { b.rb = kmat_read_batch_new(); free_q.push(&b); }
+    for (auto &b : pool) { b.rb = getenv("KMAT_NO_PINNED") ? kmat_read_batch_new() : kmat_read_batch_new_pinned(); free_q.push(&b); }
     std::vector<Writer> writers(n_threads);
     for (int w = 0; w < n_threads; w++) writers[w].next_seq = (uint64_t)w;
     std::atomic<uint64_t> reads_loaded{0};
+    // KMAT_CLI_TRACE=1: busy seconds of every stage (reader: parsing; device workers: inside kmat_label_batch; writers:
+    // formatting + fwrite), printed to stderr at the end -- which stage bounds the file-to-file rate
+    const bool cli_trace = getenv("KMAT_CLI_TRACE") != nullptr;
+    std::atomic<uint64_t> ns_reader{0}, ns_device{0}, ns_format{0}, ns_write{0};
+    auto now_ns = [] { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     std::atomic<int> failed{0};
     std::string fail_msg;
     std::mutex fail_m;
@@ -300,7 +333,9 @@ int main(int argc, char *argv[]) {
         for (;;) {
             Batch *b;
             if (!free_q.pop(b)) break;
+            const uint64_t t0 = cli_trace ? now_ns() : 0;
             const int64_t n = kmat_reader_next(reader, batch_reads, batch_bases, b->rb);
+            if (cli_trace) ns_reader += now_ns() - t0;
             if (n < 0) { fail(kmat_last_error()); break; }
             if (n == 0) break;
             reads_loaded += (uint64_t)n;
@@ -331,8 +366,12 @@ int main(int argc, char *argv[]) {
         }
     } lockstep;
     std::vector<std::thread> dev_thr;
-    for (size_t d = 0; d < devs.size(); d++)
-        dev_thr.emplace_back([&, d] {
+    const size_t n_dev_workers = devs.size() * 2;
+    for (size_t dw = 0; dw < n_dev_workers; dw++) {
+        const size_t d = dw / 2;
+        kmat_ctx *const my_ctx = (dw & 1) ? ctxs2[d] : ctxs[d];
+        if (!my_ctx) continue;
+        dev_thr.emplace_back([&, d, my_ctx] {
             Batch *b;
             for (;;) {
                 bool have = work_q.pop(b);
@@ -342,29 +381,32 @@ int main(int argc, char *argv[]) {
                 static const uint64_t zero_off[1] = {0};
                 if (have) {
                     kmat_read_batch_view(b->rb, &bases, &offs, nullptr, nullptr, &n, nullptr);
-                    b->res.resize(n);
-                    if (b->cands.size() < (size_t)n * 20 + 1024) b->cands.resize((size_t)n * 20 + 1024);
-                    if (opt.want_lineage && b->lin.size() < (size_t)n * 20 + 1024) b->lin.resize((size_t)n * 20 + 1024);
+                    b->res.reserve(n);
+                    b->cands.reserve((size_t)n * 20 + 1024);
+                    if (opt.want_lineage) b->lin.reserve((size_t)n * 20 + 1024);
+                    if (!b->res.data() || !b->cands.data() || (opt.want_lineage && !b->lin.data())) { std::cerr << "ERROR! out of host memory" << std::endl; _exit(1); }
                 }
                 uint64_t nc = 0, nl = 0;
                 int rc = KMAT_OK;
+                const uint64_t t_dev0 = cli_trace ? now_ns() : 0;
                 for (int attempt = 0; attempt < 3; attempt++) {
                     if (exchange) {
-                        rc = kmat_shard_label_batch(ctxs[d], comms[d], have ? bases : "", have ? offs : zero_off, n, have ? b->res.data() : nullptr,
+                        rc = kmat_shard_label_batch(my_ctx, comms[d], have ? bases : "", have ? offs : zero_off, n, have ? b->res.data() : nullptr,
                                                     have ? b->cands.data() : nullptr, have ? b->cands.size() : 0, &nc,
                                                     have && opt.want_lineage ? b->lin.data() : nullptr, have ? b->lin.size() : 0, &nl);
                         // a retry is collective too: every worker learns whether any of them overflowed
                         const bool again = lockstep.any(rc == KMAT_ERR_OVERFLOW, (int)devs.size());
-                        if (have && rc == KMAT_ERR_OVERFLOW) { if (nc > b->cands.size()) b->cands.resize(nc + nc / 8); if (nl > b->lin.size()) b->lin.resize(nl + nl / 8); }
+                        if (have && rc == KMAT_ERR_OVERFLOW) { b->cands.reserve(nc); b->lin.reserve(nl); }
                         if (!again) break;
                     } else {
-                        rc = kmat_label_batch(ctxs[d], bases, offs, n, b->res.data(), b->cands.data(), b->cands.size(), &nc,
+                        rc = kmat_label_batch(my_ctx, bases, offs, n, b->res.data(), b->cands.data(), b->cands.size(), &nc,
                                               opt.want_lineage ? b->lin.data() : nullptr, b->lin.size(), &nl);
                         if (rc != KMAT_ERR_OVERFLOW) break;
-                        if (nc > b->cands.size()) b->cands.resize(nc + nc / 8);
-                        if (nl > b->lin.size()) b->lin.resize(nl + nl / 8);
+                        b->cands.reserve(nc);
+                        b->lin.reserve(nl);
                     }
                 }
+                if (cli_trace) ns_device += now_ns() - t_dev0;
                 if (have) {
                     b->rc = rc;
                     if (b->rc != KMAT_OK) { b->err = kmat_last_error(); fail("device " + std::to_string(devs[d]) + ": " + b->err); }
@@ -372,6 +414,7 @@ int main(int argc, char *argv[]) {
                 } else if (rc != KMAT_OK && rc != KMAT_ERR_OVERFLOW) fail("device " + std::to_string(devs[d]) + ": " + kmat_last_error());
             }
         });
+    }
 
     std::vector<std::thread> wr_thr;
     for (int wi = 0; wi < n_threads; wi++)
@@ -402,6 +445,7 @@ int main(int argc, char *argv[]) {
                     for (uint32_t i = 0; i < n; i++) bound += (size_t)(prn_all ? b->res[i].n_cand : b->res[i].n_lin) * 40;
                     if (out.size() < bound) out.resize(bound + bound / 8);
                     char *p = out.data();
+                    const uint64_t t_f0 = cli_trace ? now_ns() : 0;
                     for (uint32_t i = 0; i < n; i++) {
                         const kmat_read_result &r = b->res[i];
                         const size_t hl = (size_t)(hoffs[i + 1] - hoffs[i]), rl = (size_t)(offs[i + 1] - offs[i]);
@@ -428,7 +472,9 @@ int main(int argc, char *argv[]) {
                         }
                     }
                     const size_t out_n = (size_t)(p - out.data());
+                    const uint64_t t_w0 = cli_trace ? now_ns() : 0;
                     if (fwrite(out.data(), 1, out_n, ofs) != out_n) fail("write failed: " + ofname);
+                    if (cli_trace) { ns_format += t_w0 - t_f0; ns_write += now_ns() - t_w0; }
                 }
                 free_q.push(b);
             }
@@ -445,6 +491,9 @@ int main(int argc, char *argv[]) {
     kmat_reader_close(reader);
     for (auto &b : pool) kmat_read_batch_free(b.rb);
     if (failed.load()) { std::cerr << "ERROR! " << fail_msg << std::endl; return -1; }
+    if (cli_trace)
+        fprintf(stderr, "[kmat cli trace] busy seconds: reader %.3f (%d parser threads), device workers %.3f (%zu), writers: format %.3f + write %.3f (%d threads)\n",
+                ns_reader.load() * 1e-9, reader_threads, ns_device.load() * 1e-9, dev_thr.size(), ns_format.load() * 1e-9, ns_write.load() * 1e-9, n_threads);
 
     std::cout << "Finished classifing reads, doing final steps sequentially..." << std::endl;
     // merge the per-thread tallies in thread order (:1760-1800)
@@ -496,7 +545,7 @@ int main(int argc, char *argv[]) {
         static const char *names[] = {"Error", "ReadTooShort", "NoDbHits", "LowScore"};
         for (auto &kv : nomatch_merge_count) nom_ofs << names[kv.first] << "\t" << kv.second << std::endl;
     }
-    for (size_t d = 0; d < devs.size(); d++) { kmat_comm_free(comms[d]); kmat_ctx_destroy(ctxs[d]); kmat_db_free(dbs[d]); }
+    for (size_t d = 0; d < devs.size(); d++) { kmat_comm_free(comms[d]); kmat_ctx_destroy(ctxs[d]); kmat_ctx_destroy(ctxs2[d]); kmat_db_free(dbs[d]); }
     kmat_inputs_free(inputs);
     const auto t_end = std::chrono::steady_clock::now();
     const double q = std::chrono::duration<double>(t_end - t_query).count(), up = std::chrono::duration<double>(t_query - t_start).count();

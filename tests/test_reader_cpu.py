@@ -190,3 +190,26 @@ def test_parallel_reader_respects_batch_limits(tmp_path):
         L.kmat_read_batch_free(b)
         L.kmat_reader_close(r)
         assert got == seqs and len(sizes) > 1
+
+
+@pytest.mark.parametrize("threads,max_reads", [(1, 1 << 20), (1, 7), (4, 1 << 20), (4, 50)])
+def test_pinned_batches_hand_out_the_same_reads(golden_small, threads, max_reads, monkeypatch):
+    """kmat_read_batch_new_pinned (what the read_label binary uses): same reads whether the page-locked buffer exists (GPU box)
+    or pinning fails and the batch silently stays pageable (here)."""
+    monkeypatch.setenv("KMAT_READER_SEG_BYTES", "4096")
+    for key, fastq in (("reads", False), ("reads_wrapped", False), ("reads_fq", True)):
+        path = golden_small.paths[key]
+        want = op.read_fasta_like_reference(path, fastq=fastq)
+        got = api.read_file(path, fastq=fastq, max_reads=max_reads, threads=threads, pinned=True)
+        assert got[0] == want[0] and got[1] == want[1], (key, threads, max_reads)
+
+
+@pytest.mark.gpu
+def test_pinned_batches_on_the_gpu_box(golden_small, monkeypatch):
+    monkeypatch.setenv("KMAT_READER_SEG_BYTES", "4096")
+    for threads, max_reads in ((1, 7), (4, 50), (4, 1 << 20)):
+        for key, fastq in (("reads", False), ("reads_fq", True)):
+            path = golden_small.paths[key]
+            want = op.read_fasta_like_reference(path, fastq=fastq)
+            got = api.read_file(path, fastq=fastq, max_reads=max_reads, threads=threads, pinned=True)
+            assert got[0] == want[0] and got[1] == want[1], (key, threads, max_reads)

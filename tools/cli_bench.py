@@ -83,6 +83,9 @@ def main():
             if p.returncode != 0:
                 print(p.stdout[-2000:], p.stderr[-2000:], file=sys.stderr)
                 raise SystemExit(f"read_label failed rc={p.returncode}")
+            for ln in p.stderr.splitlines():
+                if ln.startswith("[kmat"):
+                    print(ln, file=sys.stderr)
             q = float(re.search(r"Total query time: ([0-9.eE+-]+) sec", p.stdout).group(1))
             up = float(re.search(r"Table upload time: ([0-9.eE+-]+) sec", p.stdout).group(1))
             out_bytes = sum(os.path.getsize(os.path.join(wd, f)) for f in os.listdir(wd) if re.match(r"out\d+\.out$", f))
