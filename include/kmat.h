@@ -379,6 +379,19 @@ uint64_t kmat_launch_count(void);
 int kmat_format_tail(const kmat_read_result *, const kmat_pair *cands, const kmat_pair *lineage, int prn_all,
                      char *buf, size_t cap);
 
+/* kmat_label_batch with those tails formatted ON THE DEVICE (K5): replaces the per-read output formatting of
+ * proc_line / construct_labels (read_label.cpp:894-937, 1218, 1233, 1271, 844-848) for a batch; the caller pastes
+ * "hdr\tread\t" and the tail together.  text_ref[i] = offset << KMAT_TEXT_LEN_BITS | length of read i's tail inside `text`
+ * (the same bytes kmat_format_tail writes), or KMAT_TEXT_ON_HOST for a read the device formatter leaves to
+ * kmat_format_tail: a number that prints in exponent notation, a tail longer than 768 bytes, no room left in `text`, a read
+ * in KMAT_ST_ERROR.  *n_text = bytes of `text` in use.  text_cap may be anything (0: every read is left to the host). */
+#define KMAT_TEXT_LEN_BITS 24
+#define KMAT_TEXT_ON_HOST (~0ull)
+int kmat_label_batch_text(kmat_ctx *, const char *bases, const uint64_t *offs, uint32_t n_reads, kmat_read_result *out,
+                          kmat_pair *cands, uint64_t cands_cap, uint64_t *n_cands,
+                          kmat_pair *lineage, uint64_t lineage_cap, uint64_t *n_lineage,
+                          int prn_all, char *text, uint64_t text_cap, uint64_t *n_text, uint64_t *text_ref);
+
 /* ---- read ingest (host) -------------------------------------------------------------------------
  * Replaces the single-producer FASTA/FASTQ parser of read_label main() (read_label.cpp:1651-1713) and the
  * header substitution of :1728-1732, quirks included: FASTA lines of length <= 1 are ignored and wrapped lines
@@ -415,6 +428,10 @@ int kmat_read_batch_view(const kmat_read_batch *, const char **bases, const uint
  * Returns 0 = counted for (tid, score) [track_taxids / track_tscores], 1 = ReadTooShort, 2 = NoDbHits,
  * 3 = LowScore, -1 = nothing (NaN score). */
 int kmat_tally_class(const kmat_read_result *, float min_score, int32_t min_kmer);
+
+/* Test hook for the device formatter (K5): printf("%g") text of n floats as the device writes it, 16 bytes each (NUL padded;
+ * first byte 0xFF = a value the device leaves to the host formatter). */
+int kmat_test_format_floats(int device, const float *vals, uint32_t n, char *out16);
 
 /* Random-access HBM roofline probe: uniform random `access_bytes`-wide loads
  * (8, 16 or 32) over a `span_bytes` device allocation; returns achieved gathers/s. */

@@ -52,7 +52,7 @@ EXPORTS = [
     "kmat_ctx_create", "kmat_ctx_set_opts", "kmat_ctx_destroy", "kmat_label_batch", "kmat_label_batch_device",
     "kmat_pack_words", "kmat_pack_reads", "kmat_label_batch_packed", "kmat_result_expand",
     "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_set_pipeline", "kmat_gene_batch", "kmat_shard_encode", "kmat_shard_serve", "kmat_shard_finish", "kmat_ctx_device_results", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench", "kmat_gather_bench_peer",
-    "kmat_set_l2_fetch_granularity", "kmat_reader_open", "kmat_reader_open_mt", "kmat_reader_close", "kmat_read_batch_new", "kmat_read_batch_new_pinned", "kmat_read_batch_free",
+    "kmat_set_l2_fetch_granularity", "kmat_reader_open", "kmat_reader_open_mt", "kmat_reader_close", "kmat_read_batch_new", "kmat_read_batch_new_pinned", "kmat_label_batch_text", "kmat_test_format_floats", "kmat_read_batch_free",
     "kmat_reader_next", "kmat_read_batch_view", "kmat_tally_class", "kmat_host_alloc", "kmat_host_free",
     "kmat_ctx_peer_export", "kmat_ctx_peer_attach", "kmat_comm_unique_id", "kmat_comm_init", "kmat_comm_free", "kmat_shard_label_device", "kmat_shard_label_batch",
     "kmat_kcov_create", "kmat_kcov_add", "kmat_kcov_finish", "kmat_kcov_query", "kmat_kcov_free",
@@ -107,6 +107,9 @@ def lib():
     L.kmat_ctx_set_opts.argtypes = [vp, C.POINTER(Opts)]
     L.kmat_ctx_destroy.argtypes = [vp]
     L.kmat_label_batch.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, C.POINTER(C.c_uint64), vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.kmat_test_format_floats.argtypes = [C.c_int, vp, C.c_uint32, vp]
+    L.kmat_label_batch_text.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, C.POINTER(C.c_uint64), vp, C.c_uint64, C.POINTER(C.c_uint64),
+                                        C.c_int, vp, C.c_uint64, C.POINTER(C.c_uint64), vp]
     L.kmat_label_batch_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, vp, vp]
     L.kmat_comm_unique_id.argtypes = [vp]
     L.kmat_comm_init.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp)]
@@ -392,6 +395,42 @@ class Ctx:
                 continue
             _check(rc)
             return res, cands[:n_c.value], lin[:n_l.value]
+
+    def label_text(self, seqs=None, blob=None, offs=None, prn_all=True, text_cap=None):
+        """kmat_label_batch_text: label() plus the output-line tails formatted on the device (K5).  Returns (results, candidates,
+        lineage, tails, n_on_host): tails[i] is the device text, or None where the device left read i to kmat_format_tail."""
+        if seqs is not None:
+            blob, offs = pack_reads(seqs)
+        n = len(offs) - 1
+        res = np.zeros(n, dtype=RESULT_DTYPE)
+        cap = max(4096, 32 * n)
+        n_c, n_l, n_t = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        text = np.zeros(max(1, 256 * n + 4096 if text_cap is None else text_cap), dtype=np.uint8)
+        ref = np.zeros(max(1, n), dtype=np.uint64)
+        while True:
+            cands = np.zeros(cap, dtype=PAIR_DTYPE)
+            lin = np.zeros(cap if self.opts.want_lineage else 1, dtype=PAIR_DTYPE)
+            ptr = blob if isinstance(blob, (bytes, bytearray)) else blob.ctypes.data
+            rc = lib().kmat_label_batch_text(self.h, ptr, offs.ctypes.data, n, res.ctypes.data, cands.ctypes.data, len(cands), C.byref(n_c),
+                                             lin.ctypes.data if self.opts.want_lineage else None, len(lin), C.byref(n_l), int(prn_all),
+                                             text.ctypes.data, 0 if text_cap == 0 else len(text), C.byref(n_t), ref.ctypes.data)
+            if rc == -10:
+                cap = int(max(n_c.value, n_l.value)) + 16
+                continue
+            _check(rc)
+            break
+        raw = text.tobytes()
+        tails, on_host = [], 0
+        for i in range(n):
+            r = int(ref[i])
+            if r == 0xFFFFFFFFFFFFFFFF:
+                tails.append(None)
+                on_host += 1
+            else:
+                o, ln = r >> 24, r & 0xFFFFFF
+                assert o + ln <= n_t.value
+                tails.append(raw[o:o + ln].decode())
+        return res, cands[:n_c.value], lin[:n_l.value], tails, on_host
 
     def label_packed(self, seqs=None, blob=None, offs=None, threads=4):
         """The compact interface: kmat_pack_reads on the host, kmat_label_batch_packed, 32-byte results expanded back to the

@@ -1463,6 +1463,7 @@ struct kmat_ctx {
         uint32_t *d_codes = nullptr; uint64_t cap_codes = 0;      // compact interface: the chunk's 2-bit code words ...
         uint64_t *d_inv = nullptr; uint64_t cap_inv = 0;          // ... and the positions of its non-ACGT bases
         kmat_read_result32 *d_out32 = nullptr;                    // ... and its 32-byte results (cap_reads entries)
+        unsigned long long *d_ref = nullptr; uint64_t cap_ref = 0; // K5: where each read's tail went (kmat_label_batch_text)
         unsigned long long *h_cur = nullptr;       // pinned: cursors after this slot's chunk
         cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
     } slot[2];
@@ -1477,7 +1478,8 @@ struct kmat_ctx {
     int2 *d_hdr = nullptr; uint32_t cap_hdr = 0;
     kmat_read_result *d_out_dev = nullptr; uint32_t cap_out_dev = 0;   // kmat_label_batch_device with d_out == NULL
     kmat_pair *d_cands = nullptr, *d_lin = nullptr; uint64_t cap_cands = 0, cap_lin = 0;
-    unsigned long long *d_cursors = nullptr;     // [0] cands, [1] lineage
+    unsigned long long *d_cursors = nullptr;     // [0] cands, [1] lineage, [2] text bytes (K5, kmat_format.cuh)
+    char *d_text = nullptr; uint64_t cap_text = 0;    // the tails of a host-buffer call formatted on the device
     uint32_t *d_pool2 = nullptr; int pool2_mul = 1;            // resolved lists (km_resolve_kernel)
     int resolved_max_count = -1, resolved_permissive = -1, resolved_rkmer = -1;
     // rand_read_label accumulators (kmat_null.cuh): [n_nodes * KMAT_NULL_BUCKETS] max fraction (float bits) / read counts
@@ -1602,9 +1604,9 @@ extern "C" int kmat_ctx_create(const kmat_db *db, const kmat_inputs *in, const k
         KM_CUDA(cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
         KM_CUDA(cudaEventCreateWithFlags(&sl.ev_comp, cudaEventDisableTiming));
         KM_CUDA(cudaEventCreateWithFlags(&sl.ev_d2h, cudaEventDisableTiming));
-        KM_CUDA(cudaMallocHost((void **)&sl.h_cur, 16));
+        KM_CUDA(cudaMallocHost((void **)&sl.h_cur, 24));
     }
-    KM_CUDA(cudaMalloc((void **)&c->d_cursors, 16));
+    KM_CUDA(cudaMalloc((void **)&c->d_cursors, 24));
     KM_CUDA(cudaMalloc((void **)&c->d_pass, 8));
     KM_CUDA(cudaMemset(c->d_pass, 0, 8));
     KM_CUDA(cudaMalloc((void **)&c->d_stats, sizeof(KmStatsDev)));
@@ -1637,7 +1639,7 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
     cudaFree(c->d_nodeA); cudaFree(c->d_nodeB); cudaFree(c->d_paths); cudaFree(c->d_prune); cudaFree(c->d_sid2nid);
     cudaFree(c->d_model_of_cand); cudaFree(c->d_mrow); cudaFree(c->d_cut); cudaFree(c->d_cls);
     for (auto &sl : c->slot) {
-        cudaFree(sl.d_bases); cudaFree(sl.d_offs); cudaFree(sl.d_out); cudaFree(sl.d_codes); cudaFree(sl.d_inv); cudaFree(sl.d_out32); cudaFreeHost(sl.h_cur);
+        cudaFree(sl.d_bases); cudaFree(sl.d_offs); cudaFree(sl.d_out); cudaFree(sl.d_codes); cudaFree(sl.d_inv); cudaFree(sl.d_out32); cudaFree(sl.d_ref); cudaFreeHost(sl.h_cur);
         if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
         if (sl.ev_comp) cudaEventDestroy(sl.ev_comp);
         if (sl.ev_d2h) cudaEventDestroy(sl.ev_d2h);
@@ -1654,7 +1656,7 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (auto &e : c->ev_sub) if (e) cudaEventDestroy(e);
-    cudaFree(c->d_cands); cudaFree(c->d_lin); cudaFree(c->d_cursors); cudaFree(c->d_pool2); cudaFree(c->d_long_masks); cudaFree(c->d_long_sets); cudaFree(c->d_stats);
+    cudaFree(c->d_cands); cudaFree(c->d_lin); cudaFree(c->d_text); cudaFree(c->d_cursors); cudaFree(c->d_pool2); cudaFree(c->d_long_masks); cudaFree(c->d_long_sets); cudaFree(c->d_stats);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
@@ -1710,7 +1712,7 @@ static int km_prepare_pass(kmat_ctx *c, const KmPass &L, cudaStream_t st, uint32
         }
     }
     if (L.reset) {
-        KM_CUDA(cudaMemsetAsync(c->d_cursors, 0, 16, st));
+        KM_CUDA(cudaMemsetAsync(c->d_cursors, 0, 24, st));
         if (c->collect_stats) KM_CUDA(cudaMemsetAsync(c->d_stats, 0, sizeof(KmStatsDev), st));
     }
     *hit = c->d_hit - L.first_off;
@@ -2040,6 +2042,8 @@ extern "C" void kmat_result_expand(const kmat_read_result32 *in, uint32_t read_l
     else if (out->status == KMAT_ST_NODBHITS) { out->n1 = (int32_t)read_len; out->n2 = kmer_length; }
 }
 
+#include "kmat_format.cuh"
+
 // Host buffers in, host buffers out.  The batch is cut into chunks; chunk i's kernels (one stream, in order, so the
 // candidate records of a chunk are contiguous behind one running cursor) overlap the H2D copy of chunk i+1 and the
 // D2H copy of chunk i-1 on two copy streams.  Pinned caller buffers (kmat_host_alloc) make those copies truly
@@ -2052,6 +2056,8 @@ struct KmHostIO {
     kmat_read_result *out = nullptr; kmat_read_result32 *out32 = nullptr;
     kmat_pair *cands = nullptr; uint64_t cands_cap = 0; uint64_t *n_cands = nullptr;
     kmat_pair *lineage = nullptr; uint64_t lineage_cap = 0; uint64_t *n_lineage = nullptr;
+    // K5 (kmat_label_batch_text): the tails of the output lines, formatted on the device
+    char *text = nullptr; uint64_t text_cap = 0; uint64_t *n_text = nullptr; uint64_t *text_ref = nullptr; int prn_all = 0;
 };
 static int km_label_host(kmat_ctx *c, const KmHostIO &io, const uint64_t *offs, uint32_t n_reads) {
     const char *bases = io.bases;
@@ -2066,12 +2072,20 @@ static int km_label_host(kmat_ctx *c, const KmHostIO &io, const uint64_t *offs, 
     if (n_lineage) *n_lineage = 0;
     if (!n_reads) return KMAT_OK;
     KM_CUDA(cudaSetDevice(c->device));
-    static const uint32_t chunk_reads = [] { const char *e = getenv("KMAT_CHUNK_READS"); const long v = e ? atol(e) : 0; return (uint32_t)(v > 0 ? v : (1 << 20)); }();
+    const uint32_t chunk_reads = [] { const char *e = getenv("KMAT_CHUNK_READS"); const long v = e ? atol(e) : 0; return (uint32_t)(v > 0 ? v : (1 << 20)); }();
     const uint64_t chunk_bases = (uint64_t)256 << 20;
     int rc;
+    if (io.n_text) *io.n_text = 0;
+    if (io.text_ref) {
+        // room for the device-formatted tails: what the caller can take, at most ~256 bytes per read (a tail without room is
+        // left to the host formatter, never an error)
+        const uint64_t want = std::min<uint64_t>(io.text_cap, (uint64_t)n_reads * 256 + 4096);
+        if (want > c->cap_text) { KM_CUDA(cudaStreamSynchronize(c->stream)); KM_CUDA(cudaStreamSynchronize(c->st_d2h)); if ((rc = km_grow(&c->d_text, &c->cap_text, want)) != KMAT_OK) return rc; }
+    }
+    const uint64_t text_room = io.text_ref ? std::min<uint64_t>(io.text_cap, c->cap_text) : 0;
     for (int attempt = 0; attempt < 3; attempt++) {
         if ((rc = km_reserve_cands(c, n_reads)) != KMAT_OK) return rc;
-        unsigned long long done_c = 0, done_l = 0;      // candidate / lineage pairs already copied out
+        unsigned long long done_c = 0, done_l = 0, done_t = 0;      // candidate / lineage pairs and text bytes already copied out
         struct Chunk { uint32_t r0 = 0, r1 = 0; int slot = 0; bool valid = false; } prev;
         auto drain = [&](const Chunk &ch) -> int {      // results of a finished chunk -> caller buffers
             kmat_ctx::Slot &sl = c->slot[ch.slot];
@@ -2088,6 +2102,12 @@ static int km_label_host(kmat_ctx *c, const KmHostIO &io, const uint64_t *offs, 
                 KM_CUDA(cudaMemcpyAsync(lineage + done_l, c->d_lin + done_l, (size_t)(hi - done_l) * sizeof(kmat_pair), cudaMemcpyDeviceToHost, c->st_d2h));
             }
             done_c = std::max(done_c, cur_c); done_l = std::max(done_l, cur_l);
+            if (io.text_ref) {
+                const unsigned long long cur_t = std::min<unsigned long long>(sl.h_cur[2], text_room);
+                if (cur_t > done_t) KM_CUDA(cudaMemcpyAsync(io.text + done_t, c->d_text + done_t, (size_t)(cur_t - done_t), cudaMemcpyDeviceToHost, c->st_d2h));
+                KM_CUDA(cudaMemcpyAsync(io.text_ref + ch.r0, sl.d_ref, (size_t)(ch.r1 - ch.r0) * 8, cudaMemcpyDeviceToHost, c->st_d2h));
+                done_t = std::max(done_t, cur_t);
+            }
             KM_CUDA(cudaEventRecord(sl.ev_d2h, c->st_d2h));
             return KMAT_OK;
         };
@@ -2142,6 +2162,10 @@ static int km_label_host(kmat_ctx *c, const KmHostIO &io, const uint64_t *offs, 
                     sl.cap_reads = (uint32_t)cap;
                 }
             }
+            if (io.text_ref && (uint64_t)n > sl.cap_ref) {
+                KM_CUDA(cudaStreamSynchronize(c->st_h2d)); KM_CUDA(cudaStreamSynchronize(c->stream)); KM_CUDA(cudaStreamSynchronize(c->st_d2h));
+                if ((rc = km_grow(&sl.d_ref, &sl.cap_ref, (uint64_t)n + n / 4 + 64)) != KMAT_OK) return rc;
+            }
             uint64_t i_lo = 0, i_hi = 0;
             if (compact && io.n_inv) {
                 i_lo = (uint64_t)(std::lower_bound(io.inv, io.inv + io.n_inv, offs[r0]) - io.inv);
@@ -2173,12 +2197,16 @@ static int km_label_host(kmat_ctx *c, const KmHostIO &io, const uint64_t *offs, 
             }
             KmPass L{sl.d_bases - base0, sl.d_offs, n, offs[r0], nb, max_len, sl.d_out, ci == 0};
             if ((rc = km_run_device(c, L, c->stream)) != KMAT_OK) return rc;
+            if (io.text_ref) {
+                // K5 sees the chunk's final results; its text lands behind the previous chunks' in c->d_text
+                if ((rc = km_launch_format(c, sl.d_out, n, io.prn_all, text_room, sl.d_ref, c->stream)) != KMAT_OK) return rc;
+            }
             if (compact) {
                 km_compact_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(sl.d_out, n, c->opt.want_lineage, sl.d_out32);
                 g_km_launches++;
                 KM_CUDA(cudaGetLastError());
             }
-            KM_CUDA(cudaMemcpyAsync(sl.h_cur, c->d_cursors, 16, cudaMemcpyDeviceToHost, c->stream));
+            KM_CUDA(cudaMemcpyAsync(sl.h_cur, c->d_cursors, 24, cudaMemcpyDeviceToHost, c->stream));
             KM_CUDA(cudaEventRecord(sl.ev_comp, c->stream));
             if (trace) { tr_ev(&tr.back().k1, c->stream); tr.back().t_launched = now_ms() - t_host0; }
             if (prev.valid) {
@@ -2217,6 +2245,7 @@ static int km_label_host(kmat_ctx *c, const KmHostIO &io, const uint64_t *offs, 
         if (again) continue;                     // candidate buffer was too small: re-run with the exact size
         if (n_cands) *n_cands = total_c;
         if (n_lineage) *n_lineage = c->opt.want_lineage ? total_l : 0;
+        if (io.n_text) *io.n_text = done_t;
         if ((rc = km_fetch_stats(c, c->stream)) != KMAT_OK) return rc;
         if (compact && std::max(total_c, total_l) >= (1ull << 32)) { kmat_set_error("compact interface: more than 2^32 pairs in one call; split the batch"); return KMAT_ERR_UNSUPPORTED; }
         if ((cands && total_c > cands_cap) || (lineage && c->opt.want_lineage && total_l > lineage_cap)) {
@@ -2235,6 +2264,20 @@ extern "C" int kmat_label_batch(kmat_ctx *c, const char *bases, const uint64_t *
     KmHostIO io;
     io.bases = bases; io.out = out; io.cands = cands; io.cands_cap = cands_cap; io.n_cands = n_cands;
     io.lineage = lineage; io.lineage_cap = lineage_cap; io.n_lineage = n_lineage;
+    return km_label_host(c, io, offs, n_reads);
+}
+// kmat_label_batch + K5: the tail of every read's output line (what kmat_format_tail writes, byte for byte) formatted on the
+// device.  text_ref[i] = offset << KMAT_TEXT_LEN_BITS | length into `text`, or KMAT_TEXT_ON_HOST for the reads the device
+// formatter leaves to kmat_format_tail (a number in exponent notation, a very long tail, no room left in `text`, an error).
+extern "C" int kmat_label_batch_text(kmat_ctx *c, const char *bases, const uint64_t *offs, uint32_t n_reads, kmat_read_result *out,
+                                     kmat_pair *cands, uint64_t cands_cap, uint64_t *n_cands, kmat_pair *lineage, uint64_t lineage_cap,
+                                     uint64_t *n_lineage, int prn_all, char *text, uint64_t text_cap, uint64_t *n_text, uint64_t *text_ref) {
+    if (!c || !offs || !out || (n_reads && !bases) || (n_reads && (!text_ref || (!text && text_cap)))) { kmat_set_error("kmat_label_batch_text: bad argument"); return KMAT_ERR_ARG; }
+    if (prn_all && !cands) { kmat_set_error("kmat_label_batch_text: prn_all needs the candidate buffer"); return KMAT_ERR_ARG; }
+    KmHostIO io;
+    io.bases = bases; io.out = out; io.cands = cands; io.cands_cap = cands_cap; io.n_cands = n_cands;
+    io.lineage = lineage; io.lineage_cap = lineage_cap; io.n_lineage = n_lineage;
+    io.text = text; io.text_cap = text_cap; io.n_text = n_text; io.text_ref = text_ref; io.prn_all = prn_all;
     return km_label_host(c, io, offs, n_reads);
 }
 // The compact interface: reads as 2-bit code words indexed by GLOBAL base offset (word w = bases 16 w .. 16 w + 15, base i in

@@ -5,7 +5,9 @@
 // refills its queue in rounds of 2*n_threads reads; a round always ends right after a read was pushed, and the
 // header variables it resets per round are always reassigned before the next push, so one continuous state
 // machine yields the same (header, read) sequence.
+#include <algorithm>
 #include <atomic>
+#include <new>
 #include <cerrno>
 #include <condition_variable>
 #include <map>
@@ -24,33 +26,86 @@
 
 #include "kmat_internal.h"
 
+// Page-locked blocks for the bases of batches that asked for them (kmat_read_batch_new_pinned): allocated once, then handed
+// from batch to batch -- cudaMallocHost costs milliseconds per block, and a parser thread takes one per 8 MB segment.  The pool
+// lives for the whole process (never destroyed: the CUDA runtime may be gone by the time static destructors run).
+struct KmPinPool {
+    std::mutex m;
+    std::vector<std::pair<char *, size_t>> free_;
+    bool failed = false;                         // pinning does not work here (no GPU): plain memory from now on
+    char *get(size_t want, size_t *cap) {
+        {
+            std::lock_guard<std::mutex> l(m);
+            if (failed) return nullptr;
+            size_t best = free_.size();
+            for (size_t i = 0; i < free_.size(); i++)
+                if (free_[i].second >= want && (best == free_.size() || free_[i].second < free_[best].second)) best = i;
+            if (best < free_.size()) { char *p = free_[best].first; *cap = free_[best].second; free_.erase(free_.begin() + (long)best); return p; }
+        }
+        const size_t sz = (want + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        char *p = (char *)kmat_host_alloc(sz);
+        if (!p) { std::lock_guard<std::mutex> l(m); failed = true; return nullptr; }
+        *cap = sz;
+        return p;
+    }
+    void put(char *p, size_t cap) {
+        {
+            std::lock_guard<std::mutex> l(m);
+            if (free_.size() < 96) { free_.emplace_back(p, cap); return; }
+        }
+        kmat_host_free(p);
+    }
+};
+static KmPinPool &km_pin_pool() { static KmPinPool *pool = new KmPinPool(); return *pool; }
+
+// The bases of a batch: a growable byte buffer (the std::string subset the parser uses) whose storage is a pool block when
+// the batch wants page-locked memory
+class KmBytes {
+    char *p_ = nullptr; size_t n_ = 0, cap_ = 0; bool from_pool_ = false;
+    void release() { if (p_) { if (from_pool_) km_pin_pool().put(p_, cap_); else free(p_); } p_ = nullptr; cap_ = 0; from_pool_ = false; }
+  public:
+    bool pinned_mode = false;
+    KmBytes() = default;
+    KmBytes(const KmBytes &) = delete;
+    KmBytes &operator=(const KmBytes &) = delete;
+    ~KmBytes() { release(); }
+    size_t size() const { return n_; }
+    const char *data() const { return p_ ? p_ : ""; }
+    bool is_pinned() const { return from_pool_; }
+    void clear() { n_ = 0; }
+    void reserve(size_t want) {
+        if (want <= cap_) return;
+        char *q = nullptr; size_t qc = 0; bool qp = false;
+        if (pinned_mode) { q = km_pin_pool().get(want, &qc); qp = q != nullptr; }
+        if (!q) { qc = want; q = (char *)malloc(qc ? qc : 1); if (!q) throw std::bad_alloc(); }
+        if (n_) memcpy(q, p_, n_);
+        const size_t keep = n_;
+        release();
+        p_ = q; cap_ = qc; from_pool_ = qp; n_ = keep;
+    }
+    void append(const char *s, size_t len) {
+        if (!len) return;
+        if (n_ + len > cap_) reserve(std::max(n_ + len, cap_ + cap_ / 2 + 4096));
+        memcpy(p_ + n_, s, len);
+        n_ += len;
+    }
+    void assign(const KmBytes &src, size_t pos, size_t len) { n_ = 0; if (len > cap_) reserve(len); if (len) memcpy(p_, src.p_ + pos, len); n_ = len; }
+    void swap(KmBytes &o) { std::swap(p_, o.p_); std::swap(n_, o.n_); std::swap(cap_, o.cap_); std::swap(from_pool_, o.from_pool_); }
+};
+
 struct kmat_read_batch {
-    std::string bases, hdrs;
+    KmBytes bases;
+    std::string hdrs;
     std::vector<uint64_t> offs, hdr_offs;
     std::vector<uint32_t> unknown;      // reads whose header is "unknown_hdr:<ordinal>" (needs the global ordinal)
     std::string tail_hdr;               // parallel FASTQ: the header line of the segment's last record (the next segment's first read carries it)
     bool open_end = false;              // parallel FASTQ: the segment did not end between two records (malformed input)
     uint64_t first_ordinal = 1;
     uint32_t n = 0;
-    // kmat_read_batch_new_pinned: the bases are handed out (kmat_read_batch_view) from a page-locked buffer, so that the copy to
-    // the device is a DMA straight from it (pageable memory goes through the driver's staging buffer at ~6 GB/s)
-    bool want_pin = false, pin_valid = false;
-    char *pin = nullptr; size_t pin_cap = 0;
     kmat_read_batch() = default;
     kmat_read_batch(const kmat_read_batch &) = delete;
     kmat_read_batch &operator=(const kmat_read_batch &) = delete;
-    ~kmat_read_batch() { if (pin) kmat_host_free(pin); }
-    void clear() { bases.clear(); hdrs.clear(); offs.assign(1, 0); hdr_offs.assign(1, 0); unknown.clear(); tail_hdr.clear(); n = 0; pin_valid = false; }
-    // room for `len` bases in the page-locked buffer; false (and pinning given up for good) when the allocation fails
-    bool pin_reserve(size_t len) {
-        if (!want_pin) return false;
-        if (len <= pin_cap) return true;
-        if (pin) kmat_host_free(pin);
-        pin_cap = std::max<size_t>(len + len / 4, (size_t)1 << 20);
-        pin = (char *)kmat_host_alloc(pin_cap);
-        if (!pin) { pin_cap = 0; want_pin = false; return false; }
-        return true;
-    }
+    void clear() { bases.clear(); hdrs.clear(); offs.assign(1, 0); hdr_offs.assign(1, 0); unknown.clear(); tail_hdr.clear(); n = 0; }
 };
 
 // The line state machine of read_label main() (:1651-1713), independent of where the lines come from.
@@ -87,6 +142,7 @@ struct kmat_reader {
     bool fallback = false;                   // parallel FASTQ met a segment with an open end: sequential from fb on
     const char *fb_p = nullptr;
     std::string carry_hdr;                   // parallel FASTQ: header of the last record handed out so far
+    std::atomic<bool> pin_segments{false};   // a caller batch wants page-locked bases: the parser threads fill pool blocks (no copy on hand-over)
     kmat_read_batch *cur = nullptr;          // parallel mode: the parsed segment being handed out in max_reads / max_bases slices
     uint32_t cur_i = 0;
 };
@@ -189,6 +245,7 @@ static void km_reader_worker(kmat_reader *r) {
         if (s + 1 >= r->seg.size()) return;
         kmat_read_batch *b = new kmat_read_batch();
         b->clear();
+        b->bases.pinned_mode = r->pin_segments.load();
         b->bases.reserve(r->seg[s + 1] - r->seg[s]);
         KmParseState st;
         st.fastq = r->mt_fastq;
@@ -288,13 +345,14 @@ extern "C" void kmat_reader_close(kmat_reader *r) {
     delete r;
 }
 extern "C" kmat_read_batch *kmat_read_batch_new(void) { return new kmat_read_batch(); }
-extern "C" kmat_read_batch *kmat_read_batch_new_pinned(void) { kmat_read_batch *b = new kmat_read_batch(); b->want_pin = true; return b; }
+extern "C" kmat_read_batch *kmat_read_batch_new_pinned(void) { kmat_read_batch *b = new kmat_read_batch(); b->bases.pinned_mode = true; return b; }
 extern "C" void kmat_read_batch_free(kmat_read_batch *b) { delete b; }
 
 extern "C" int64_t kmat_reader_next(kmat_reader *r, uint32_t max_reads, uint64_t max_bases, kmat_read_batch *b) {
     if (!r || !b) { kmat_set_error("kmat_reader_next: bad argument"); return KMAT_ERR_ARG; }
     if (max_reads == 0) max_reads = 1;
     b->clear();
+    if (b->bases.pinned_mode) r->pin_segments.store(true);
     // reads [cur_i, ...) of the current parsed segment, cut to max_reads / max_bases (at least one read)
     auto slice = [&]() -> int64_t {
         kmat_read_batch *d = r->cur;
@@ -302,14 +360,12 @@ extern "C" int64_t kmat_reader_next(kmat_reader *r, uint32_t max_reads, uint64_t
         uint32_t i1 = i0;
         while (i1 < d->n && i1 - i0 < max_reads && (i1 == i0 || d->offs[i1 + 1] - d->offs[i0] <= max_bases)) i1++;
         const bool last = i1 >= d->n;
-        if (i0 == 0 && last && !b->want_pin) {                   // the whole segment fits: no copy
-            std::swap(b->bases, d->bases); std::swap(b->hdrs, d->hdrs); std::swap(b->offs, d->offs); std::swap(b->hdr_offs, d->hdr_offs);
+        if (i0 == 0 && last) {                                   // the whole segment fits: no copy
+            b->bases.swap(d->bases); std::swap(b->hdrs, d->hdrs); std::swap(b->offs, d->offs); std::swap(b->hdr_offs, d->hdr_offs);
             std::swap(b->unknown, d->unknown); std::swap(b->tail_hdr, d->tail_hdr);
             b->open_end = d->open_end; b->first_ordinal = d->first_ordinal; b->n = d->n;
         } else {
-            const size_t len = (size_t)(d->offs[i1] - d->offs[i0]);
-            if (b->pin_reserve(len)) { memcpy(b->pin, d->bases.data() + d->offs[i0], len); b->pin_valid = true; }   // the one copy goes into the page-locked buffer
-            else b->bases.assign(d->bases, d->offs[i0], len);
+            b->bases.assign(d->bases, d->offs[i0], (size_t)(d->offs[i1] - d->offs[i0]));
             b->hdrs.assign(d->hdrs, d->hdr_offs[i0], d->hdr_offs[i1] - d->hdr_offs[i0]);
             for (uint32_t i = i0; i < i1; i++) { b->offs.push_back(d->offs[i + 1] - d->offs[i0]); b->hdr_offs.push_back(d->hdr_offs[i + 1] - d->hdr_offs[i0]); }
             b->n = i1 - i0;
@@ -378,14 +434,13 @@ extern "C" int64_t kmat_reader_next(kmat_reader *r, uint32_t max_reads, uint64_t
     }
     parse_lines(r->st, [&](const char **ln, size_t *n) { return next_line_fd(r, ln, n); }, max_reads, max_bases, b);
     if (r->io_error) { kmat_set_error("read error on the input: %s", strerror(r->io_error)); return KMAT_ERR_IO; }
-    if (b->n && !b->pin_valid && b->pin_reserve(b->bases.size())) { memcpy(b->pin, b->bases.data(), b->bases.size()); b->pin_valid = true; }   // sequential parser
     return (int64_t)b->n;
 }
 
 extern "C" int kmat_read_batch_view(const kmat_read_batch *b, const char **bases, const uint64_t **offs, const char **hdrs,
                                     const uint64_t **hdr_offs, uint32_t *n_reads, uint64_t *first_ordinal) {
     if (!b) return KMAT_ERR_ARG;
-    if (bases) *bases = b->pin_valid ? b->pin : b->bases.data();
+    if (bases) *bases = b->bases.data();
     if (offs) *offs = b->offs.data();
     if (hdrs) *hdrs = b->hdrs.data();
     if (hdr_offs) *hdr_offs = b->hdr_offs.data();

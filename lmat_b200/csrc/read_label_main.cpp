@@ -8,7 +8,10 @@
 //                    reference's single-thread output byte for byte and any -t gives the same multiset of lines;
 //                    each writer keeps the reference's per-thread tallies (float sums in file order), merged in
 //                    thread order like :1760-1800.
+//   (two device workers per GPU, each with its own context; batches live in page-locked memory; the tail of every line comes
+//   formatted from the device -- kmat_label_batch_text -- and the writers paste header, read and tail together)
 // Environment: KMAT_DEVICES="0,2,.." (default: every visible GPU), KMAT_BATCH_READS (default 131072),
+// KMAT_WORKERS_PER_GPU=1 / KMAT_NO_PINNED=1 / KMAT_HOST_FORMAT=1 (switch the three off), KMAT_CLI_TRACE=1 (busy time per stage),
 // KMAT_TABLE_MODE=sharded | exchange (table split over the GPUs: probes read the owner's memory over NVLink | query k-mers
 // travel over NCCL, kmat_shard_label_batch; default: replicated, or sharded when one GPU cannot hold the table),
 // KMAT_READER_THREADS (FASTA files are parsed in parallel segments; default hw threads / 4, 2..8),
@@ -70,6 +73,7 @@ struct Batch {
     kmat_read_batch *rb = nullptr;
     PinBuf<kmat_read_result> res;
     PinBuf<kmat_pair> cands, lin;
+    PinBuf<char> text; PinBuf<uint64_t> tref; bool has_text = false;    // K5: the tails formatted on the device (kmat_label_batch_text)
     int rc = 0;
     std::string err;
 };
@@ -366,6 +370,8 @@ int main(int argc, char *argv[]) {
         }
     } lockstep;
     std::vector<std::thread> dev_thr;
+    // K5: the tails of the output lines come formatted from the device (KMAT_HOST_FORMAT=1: the host formatter for every read)
+    const bool device_text = !exchange && !getenv("KMAT_HOST_FORMAT");
     const size_t n_dev_workers = devs.size() * 2;
     for (size_t dw = 0; dw < n_dev_workers; dw++) {
         const size_t d = dw / 2;
@@ -384,6 +390,8 @@ int main(int argc, char *argv[]) {
                     b->res.reserve(n);
                     b->cands.reserve((size_t)n * 20 + 1024);
                     if (opt.want_lineage) b->lin.reserve((size_t)n * 20 + 1024);
+                    b->has_text = false;
+                    if (device_text) { b->text.reserve((size_t)n * 256 + 4096); b->tref.reserve((size_t)n + 1); if (!b->text.data() || !b->tref.data()) { std::cerr << "ERROR! out of host memory" << std::endl; _exit(1); } }
                     if (!b->res.data() || !b->cands.data() || (opt.want_lineage && !b->lin.data())) { std::cerr << "ERROR! out of host memory" << std::endl; _exit(1); }
                 }
                 uint64_t nc = 0, nl = 0;
@@ -399,6 +407,13 @@ int main(int argc, char *argv[]) {
                         if (have && rc == KMAT_ERR_OVERFLOW) { b->cands.reserve(nc); b->lin.reserve(nl); }
                         if (!again) break;
                     } else {
+                        if (device_text) {
+                            uint64_t nt = 0;
+                            rc = kmat_label_batch_text(my_ctx, bases, offs, n, b->res.data(), b->cands.data(), b->cands.size(), &nc,
+                                                       opt.want_lineage ? b->lin.data() : nullptr, b->lin.size(), &nl,
+                                                       prn_all ? 1 : 0, b->text.data(), b->text.size(), &nt, b->tref.data());
+                            b->has_text = true;
+                        } else
                         rc = kmat_label_batch(my_ctx, bases, offs, n, b->res.data(), b->cands.data(), b->cands.size(), &nc,
                                               opt.want_lineage ? b->lin.data() : nullptr, b->lin.size(), &nl);
                         if (rc != KMAT_ERR_OVERFLOW) break;
@@ -425,6 +440,9 @@ int main(int argc, char *argv[]) {
             if (!ofs) fail("could not open for writing " + ofname);
             std::vector<char> out;
             std::unordered_map<uint32_t, std::pair<int, float>> tally;               // track_taxids / track_tscores of this "thread"
+            // the map's nodes never move: a small direct-mapped cache of tid -> node saves the hash lookup for the tids that keep coming
+            struct TallySlot { uint32_t tid = 0; std::pair<int, float> *v = nullptr; };
+            std::vector<TallySlot> tcache(4096);
             int nomatch[4] = {0, 0, 0, 0};                                            // track_nomatch
             for (;;) {
                 Batch *b = nullptr;
@@ -454,15 +472,25 @@ int main(int argc, char *argv[]) {
                         if (prn_read) { memcpy(p, bases + offs[i], rl); p += rl; } else *p++ = 'X';
                         *p++ = '\t';
                         if (r.status == KMAT_ST_ERROR) { fail("read " + std::string(hdrs + hoffs[i], hdrs + hoffs[i + 1]) + ": " + kmat_strerror(r.err)); continue; }
-                        const int tn = kmat_format_tail(&r, b->cands.data(), b->lin.data(), prn_all ? 1 : 0, p, (size_t)(out.data() + out.size() - p));
-                        if (tn < 0) { fail("formatting failed"); continue; }
-                        p += tn;
+                        const uint64_t tr = b->has_text ? b->tref[i] : KMAT_TEXT_ON_HOST;
+                        if (tr != KMAT_TEXT_ON_HOST) {                           // formatted on the device: paste it in
+                            const size_t tl = (size_t)(tr & ((1ull << KMAT_TEXT_LEN_BITS) - 1));
+                            memcpy(p, b->text.data() + (tr >> KMAT_TEXT_LEN_BITS), tl);
+                            p += tl;
+                        } else {
+                            const int tn = kmat_format_tail(&r, b->cands.data(), b->lin.data(), prn_all ? 1 : 0, p, (size_t)(out.data() + out.size() - p));
+                            if (tn < 0) { fail("formatting failed"); continue; }
+                            p += tn;
+                        }
                         switch (kmat_tally_class(&r, min_score, opt.min_kmer)) {                 // :1217-1277
                             case 0: {
                                 // per tid: count and the float sum of the scores in arrival order (hashed here, copied into
                                 // the ordered maps of the merge step when the writer ends: same per-tid additions, same order)
+                                TallySlot &ts = tcache[(r.tid * 0x9E3779B1u) >> 20];
+                                if (ts.v && ts.tid == r.tid) { ts.v->first += 1; ts.v->second += r.score; break; }
                                 auto ins = tally.try_emplace(r.tid, 1, r.score);
                                 if (!ins.second) { ins.first->second.first += 1; ins.first->second.second += r.score; }
+                                ts.tid = r.tid; ts.v = &ins.first->second;
                                 break;
                             }
                             case 1: nomatch[1] += 1; break;
