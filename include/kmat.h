@@ -374,7 +374,8 @@ int kmat_ctx_last_kernel_ms(kmat_ctx *, float *probe_ms, float *cand_ms, float *
 uint64_t kmat_launch_count(void);
 
 /* Text after "hdr\tread\t" exactly as the reference writes it (read_label.cpp:1218,1233,1271,
- * 844-848,894-937; floats via ostream<<float == "%g").  prn_all = -p.  Returns bytes written
+ * 844-848,894-937; floats via ostream<<float == "%g").  prn_all = -p (2: -p together with -y, which also prints the
+ * candidates with a negative score, :901).  Returns bytes written
  * (0 for KMAT_ST_SILENT: the reference writes nothing, not even '\n') or <0 if cap is too small. */
 int kmat_format_tail(const kmat_read_result *, const kmat_pair *cands, const kmat_pair *lineage, int prn_all,
                      char *buf, size_t cap);

@@ -133,7 +133,7 @@ __device__ __forceinline__ void kf_tail(KfOut &o, const kmat_read_result &r, con
                 bool prn = false;
                 for (int i = (int)r.n_cand - 1; i >= 0 && !o.bad; --i) {
                     const kmat_pair c = cands[r.cand_off + (uint64_t)i];
-                    if (c.score >= 0) { o.put(' '); kf_pair(o, c.tid, c.score); prn = true; }
+                    if (c.score >= 0 || prn_all > 1) { o.put(' '); kf_pair(o, c.tid, c.score); prn = true; }
                 }
                 if (!prn) o.str("-1 -1");
                 o.put('\t');

@@ -684,7 +684,7 @@ extern "C" int kmat_format_tail(const kmat_read_result *r, const kmat_pair *cand
                 bool prn = false;
                 for (int i = (int)r->n_cand - 1; i >= 0; --i) {
                     const kmat_pair &c = cands[r->cand_off + (uint64_t)i];
-                    if (c.score >= 0) { *p++ = ' '; p = km_fmt_pair(p, c.tid, c.score, memo); prn = true; }
+                    if (c.score >= 0 || prn_all > 1) { *p++ = ' '; p = km_fmt_pair(p, c.tid, c.score, memo); prn = true; }   // prn_all = 2: -p under -y (:901)
                 }
                 if (!prn) p = km_fmt_str(p, "-1 -1");
                 *p++ = '\t';

@@ -201,7 +201,8 @@ int main(int argc, char *argv[]) {
     }
     opt.min_score = min_score;
     opt.want_lineage = prn_all ? 0 : 1;
-    if (verbose) std::cerr << "WARNING! -y (per-k-mer debug traces) is not produced by the GPU path; ignored." << std::endl;
+    if (verbose) std::cerr << "WARNING! -y: the per-k-mer debug traces on stdout are not produced by the GPU path; its effect on the -p list (candidates with a negative score are printed too, read_label.cpp:901) is." << std::endl;
+    const int prn_mode = prn_all ? (verbose ? 2 : 1) : 0;
 
     std::cout << "=== LMAT === read_label === ver. " << KMAT_LMAT_VERSION << " === kmat/B200 ===" << std::endl;
     std::cout << "Start kmer DB load..." << std::endl;
@@ -411,7 +412,7 @@ int main(int argc, char *argv[]) {
                             uint64_t nt = 0;
                             rc = kmat_label_batch_text(my_ctx, bases, offs, n, b->res.data(), b->cands.data(), b->cands.size(), &nc,
                                                        opt.want_lineage ? b->lin.data() : nullptr, b->lin.size(), &nl,
-                                                       prn_all ? 1 : 0, b->text.data(), b->text.size(), &nt, b->tref.data());
+                                                       prn_mode, b->text.data(), b->text.size(), &nt, b->tref.data());
                             b->has_text = true;
                         } else
                         rc = kmat_label_batch(my_ctx, bases, offs, n, b->res.data(), b->cands.data(), b->cands.size(), &nc,
@@ -478,7 +479,7 @@ int main(int argc, char *argv[]) {
                             memcpy(p, b->text.data() + (tr >> KMAT_TEXT_LEN_BITS), tl);
                             p += tl;
                         } else {
-                            const int tn = kmat_format_tail(&r, b->cands.data(), b->lin.data(), prn_all ? 1 : 0, p, (size_t)(out.data() + out.size() - p));
+                            const int tn = kmat_format_tail(&r, b->cands.data(), b->lin.data(), prn_mode, p, (size_t)(out.data() + out.size() - p));
                             if (tn < 0) { fail("formatting failed"); continue; }
                             p += tn;
                         }

@@ -1332,7 +1332,7 @@ int kmo_format_tail(const kmo_ctx *c, const kmo_result *r, char *buf, size_t cap
                 int prn = 0;
                 for (int i = (int)r->n_cand - 1; i >= 0; --i) {
                     const kmo_pair *p = &c->cands.v[r->cand_off + (uint64_t)i];
-                    if (p->score >= 0) { EMIT(" %u %g", p->tid, (double)p->score); prn = 1; }
+                    if (p->score >= 0 || c->opt.prn_all > 1) { EMIT(" %u %g", p->tid, (double)p->score); prn = 1; }   /* prn_all = 2: -p with -y (read_label.cpp:901) */
                 }
                 if (!prn) EMIT("-1 -1");
                 EMIT("\t");

@@ -161,6 +161,27 @@ def test_format_tail_numbers_match_printf_g():
         assert n >= 0 and buf.raw[:n].decode() == want
 
 
+def test_format_tail_negative_scores_and_verbose_mode():
+    """-p prints a candidate only when its score is >= 0; together with -y (prn_all = 2) all of them (read_label.cpp:901); a list
+    without a printable candidate prints "-1 -1"."""
+    res = np.zeros(1, dtype=api.RESULT_DTYPE)
+    res["status"], res["match"], res["n_cand"], res["cand_off"] = 5, 0, 4, 0
+    res["log_avg"], res["stdev"], res["cand_kmer_cnt"], res["tid"], res["score"] = 1.5, 0.25, 100, 562, 2.0
+    cands = np.zeros(4, dtype=api.PAIR_DTYPE)
+    cands["tid"] = [10, 20, 30, 40]
+    cands["score"] = [-0.5, 0.0, -3.25, 2.0]
+    buf = C.create_string_buffer(4096)
+    def fmt(mode):
+        n = api.lib().kmat_format_tail(res.ctypes.data, cands.ctypes.data, None, mode, buf, len(buf))
+        assert n >= 0
+        return buf.raw[:n].decode()
+    assert fmt(1) == "1.5 0.25 100\t 40 2 20 0\t562 2 DirectMatch\n"
+    assert fmt(2) == "1.5 0.25 100\t 40 2 30 -3.25 20 0 10 -0.5\t562 2 DirectMatch\n"
+    assert fmt(0) == "1.5 0.25 100\t562 2 DirectMatch\n"
+    cands["score"] = [-0.5, -1.0, -3.25, -2.0]
+    assert fmt(1) == "1.5 0.25 100\t-1 -1\t562 2 DirectMatch\n"
+
+
 def test_flat_image_damaged_header_is_rejected(golden_small, tmp_path):
     """A .kmat image whose header counts are damaged (including values that would wrap the size computation around)
     or whose offsets do not end at n_ids is KMAT_ERR_FORMAT, not a crash."""

@@ -108,6 +108,25 @@ def test_cli_reproduces_reference_run(scen, request, cli, flat_dbs, tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("scen", ["golden_small", "golden_lists"])
+@pytest.mark.parametrize("host_format", [False, True])
+def test_cli_verbose_prints_negative_candidates(scen, host_format, request, cli, flat_dbs, tmp_path):
+    """-y: the debug traces on stdout are not produced, but its effect on the .out file is -- under -p the candidates with a
+    negative score are printed too (read_label.cpp:901).  Golden: the unmodified reference run with -p -y
+    (tests/golden/make_golden_verbose.py); 10 / 39 lines differ from the plain -p output.  Both formatters (device, host)."""
+    g = request.getfixturevalue(scen)
+    ofb = str(tmp_path / "rl_")
+    env = {"LMAT_DIR": g.workdir}
+    if host_format:
+        env["KMAT_HOST_FORMAT"] = "1"
+    p = run_cli(cli, ref_args(g, S.OPTION_SETS["run_rl"], flat_dbs[g.name], g.paths["reads"], ofb, 1) + ["-y"], env=env)
+    assert p.returncode == 0, p.stderr
+    got = open(ofb + "0.out", encoding="latin-1").read()
+    assert got == g.golden_out("run_rl_verbose")
+    assert got != g.golden_out("run_rl")
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("opts", ["defaults", "tight", "prune3", "nophix_hide", "quirk", "plasmid", "nonull"])
 def test_cli_option_sets(opts, golden_lists, cli, flat_dbs, tmp_path):
     g = golden_lists

@@ -35,6 +35,12 @@ def test_device_tails_equal_host_tails(request, scen, opts):
     if opts in ("run_rl",):
         full = [t if t is not None else want[i] for i, t in enumerate(tails)]
         assert op.assemble_lines(hdrs, seqs, full) == g.golden_out(opts)
+        # -p together with -y (prn_all = 2): candidates with a negative score are printed too (read_label.cpp:901)
+        res3, cands3, lin3, tails3, _ = ctx.label_text(seqs, prn_all=2)
+        want3 = ctx.tails(res3, cands3, lin3, prn_all=2)
+        full3 = [t if t is not None else want3[i] for i, t in enumerate(tails3)]
+        assert all(t is None or t == want3[i] for i, t in enumerate(tails3))
+        assert op.assemble_lines(hdrs, seqs, full3) == g.golden_out("run_rl_verbose")
 
 
 def test_device_tails_many_reads_and_small_buffers(golden_lists, monkeypatch):

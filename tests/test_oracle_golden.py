@@ -21,6 +21,19 @@ def test_oracle_reproduces_reference_out(scen, opts, request):
     assert mine == g.golden_out(opts)
 
 
+@pytest.mark.parametrize("scen", ["golden_small", "golden_lists"])
+def test_oracle_reproduces_reference_out_under_verbose(scen, request):
+    """-p -y: the candidates with a negative score are printed too (read_label.cpp:901; golden from the unmodified reference,
+    tests/golden/make_golden_verbose.py)."""
+    g = request.getfixturevalue(scen)
+    orc = oracle_for(g, "run_rl")
+    orc.set_opts(prn_all=2)
+    hdrs, seqs = op.read_fasta_like_reference(g.paths["reads"])
+    res, _, _ = orc.label(seqs)
+    mine = op.assemble_lines(hdrs, seqs, orc.tails(res))
+    assert mine == g.golden_out("run_rl_verbose") and mine != g.golden_out("run_rl")
+
+
 @pytest.mark.parametrize("tag,key,fastq", [("wrapped", "reads_wrapped", False), ("fastq", "reads_fq", True)])
 def test_reader_restatement_matches_reference(golden_small, tag, key, fastq):
     g = golden_small
