@@ -631,19 +631,31 @@ def main():
             t_res32 = torch.empty(n * api.RESULT32_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
             t_list = torch.empty(max(1, 24 * n) * api.PAIR_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
             list_cap = t_list.numel() // api.PAIR_DTYPE.itemsize
+            n_w = C.c_uint64()
+
+            def packed_rl_step():
+                # the pair lists in run-length form (a taxid word, its score once per run of equal scores): fewer bytes on the way out
+                rc = L_.kmat_label_batch_packed_rl(ctx.h, t_codes.data_ptr(), t_inv.data_ptr(), n_inv.value, h_offs.ctypes.data, n, t_res32.data_ptr(),
+                                                   t_list.data_ptr(), 2 * list_cap, C.byref(n_w))
+                if rc < 0:
+                    raise api.KmatError(rc, L_.kmat_last_error().decode())
 
             def packed_step():
                 rc = L_.kmat_label_batch_packed(ctx.h, t_codes.data_ptr(), t_inv.data_ptr(), n_inv.value, h_offs.ctypes.data, n, t_res32.data_ptr(),
                                                 t_list.data_ptr(), list_cap, C.byref(n_c))
                 if rc < 0:
                     raise api.KmatError(rc, L_.kmat_last_error().decode())
-            dt = timed(packed_step)
+            dt = timed(packed_rl_step)
             e2e = {"value": world * n / dt, "unit": UNIT, "h2d_bytes_per_step": int(4 * n_words + 8 * n_inv.value + 8 * (n + 1)),
-                   "d2h_bytes_per_step": int(n * api.RESULT32_DTYPE.itemsize + n_c.value * 8),
-                   "api": "kmat_label_batch_packed: 2-bit packed reads + invalid-base positions + offsets in (packed by kmat_pack_reads before the timed region), "
-                          "32-byte results + rank_label pairs out; pinned host buffers"}
+                   "d2h_bytes_per_step": int(n * api.RESULT32_DTYPE.itemsize + n_w.value * 4),
+                   "api": "kmat_label_batch_packed_rl: 2-bit packed reads + invalid-base positions + offsets in (packed by kmat_pack_reads before the timed region), "
+                          "32-byte results + the rank_label pairs in run-length form out (kmat_list_decode rebuilds them); pinned host buffers"}
             r32 = t_res32.numpy().view(api.RESULT32_DTYPE)
             e2e_checksum = int((((r32["flags"] & 7).astype(np.int64) * 1000003 + r32["tid"].astype(np.int64) * 7919 + r32["score"].view(np.int32).astype(np.int64)) & 0xFFFFFFFF).sum())
+            # the plain compact interface (8-byte pairs) next to it; tests/test_compact_io.py checks that the words decode to the same pairs
+            dt_plain = timed(packed_step)
+            e2e["plain_pairs"] = {"value": world * n / dt_plain, "d2h_bytes_per_step": int(n * api.RESULT32_DTYPE.itemsize + n_c.value * 8),
+                                  "api": "kmat_label_batch_packed (8-byte pairs out)"}
             del t_codes, t_inv, t_res32, t_list
             # ASCII interface
             t_res = torch.empty(n * api.RESULT_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)

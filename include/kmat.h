@@ -214,6 +214,14 @@ uint64_t kmat_pack_words(uint64_t total_bases);
 int kmat_pack_reads(const char *bases, uint64_t total_bases, int threads, uint32_t *codes, uint64_t *inv_pos, uint64_t inv_cap, uint64_t *n_inv);
 int kmat_label_batch_packed(kmat_ctx *, const uint32_t *codes, const uint64_t *inv_pos, uint64_t n_inv, const uint64_t *offs, uint32_t n_reads,
                             kmat_read_result32 *out, kmat_pair *list, uint64_t list_cap, uint64_t *n_list);
+/* The same with the pair list in RUN-LENGTH form: equal scores are adjacent in rank_label / valid_cand, so a taxid word with bit 31
+ * set is followed by the score (float bits) that holds for it and for the unflagged taxid words after it -- ~5 instead of 8 bytes
+ * per pair on the way out, which is what bounds several GPUs behind one host.  list_off of a record is the offset of the read's
+ * words in `words`, n_list its number of pairs; kmat_list_decode rebuilds them (returns the words consumed).  Taxonomies with a
+ * taxid >= 2^31: KMAT_ERR_UNSUPPORTED.  KMAT_ERR_OVERFLOW: *n_words = the capacity needed. */
+int kmat_label_batch_packed_rl(kmat_ctx *, const uint32_t *codes, const uint64_t *inv_pos, uint64_t n_inv, const uint64_t *offs, uint32_t n_reads,
+                               kmat_read_result32 *out, uint32_t *words, uint64_t words_cap, uint64_t *n_words);
+uint32_t kmat_list_decode(const uint32_t *words, uint32_t n_list, kmat_pair *out);
 /* 32-byte record -> the 64-byte one kmat_format_tail / kmat_tally_class take (the two integers of the ReadTooShort /
  * NoDbHits lines are the read's length, k and -j: read_label.cpp:1217-1218, 1232-1233, 1270-1271) */
 void kmat_result_expand(const kmat_read_result32 *in, uint32_t read_len, int kmer_length, int min_kmer, int want_lineage, kmat_read_result *out);

@@ -52,7 +52,7 @@ EXPORTS = [
     "kmat_ctx_create", "kmat_ctx_set_opts", "kmat_ctx_destroy", "kmat_label_batch", "kmat_label_batch_device",
     "kmat_pack_words", "kmat_pack_reads", "kmat_label_batch_packed", "kmat_result_expand",
     "kmat_ctx_sync", "kmat_ctx_last_stats", "kmat_ctx_set_stats", "kmat_ctx_set_pipeline", "kmat_gene_batch", "kmat_shard_encode", "kmat_shard_serve", "kmat_shard_finish", "kmat_ctx_device_results", "kmat_ctx_last_kernel_ms", "kmat_launch_count", "kmat_format_tail", "kmat_gather_bench", "kmat_gather_bench_peer",
-    "kmat_set_l2_fetch_granularity", "kmat_reader_open", "kmat_reader_open_mt", "kmat_reader_close", "kmat_read_batch_new", "kmat_read_batch_new_pinned", "kmat_label_batch_text", "kmat_test_format_floats", "kmat_read_batch_free",
+    "kmat_set_l2_fetch_granularity", "kmat_reader_open", "kmat_reader_open_mt", "kmat_reader_close", "kmat_read_batch_new", "kmat_read_batch_new_pinned", "kmat_label_batch_text", "kmat_test_format_floats", "kmat_label_batch_packed_rl", "kmat_list_decode", "kmat_read_batch_free",
     "kmat_reader_next", "kmat_read_batch_view", "kmat_tally_class", "kmat_host_alloc", "kmat_host_free",
     "kmat_ctx_peer_export", "kmat_ctx_peer_attach", "kmat_comm_unique_id", "kmat_comm_init", "kmat_comm_free", "kmat_shard_label_device", "kmat_shard_label_batch",
     "kmat_kcov_create", "kmat_kcov_add", "kmat_kcov_finish", "kmat_kcov_query", "kmat_kcov_free",
@@ -107,6 +107,9 @@ def lib():
     L.kmat_ctx_set_opts.argtypes = [vp, C.POINTER(Opts)]
     L.kmat_ctx_destroy.argtypes = [vp]
     L.kmat_label_batch.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, C.POINTER(C.c_uint64), vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.kmat_label_batch_packed_rl.argtypes = [vp, vp, vp, C.c_uint64, vp, C.c_uint32, vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.kmat_list_decode.argtypes = [vp, C.c_uint32, vp]
+    L.kmat_list_decode.restype = C.c_uint32
     L.kmat_test_format_floats.argtypes = [C.c_int, vp, C.c_uint32, vp]
     L.kmat_label_batch_text.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, C.POINTER(C.c_uint64), vp, C.c_uint64, C.POINTER(C.c_uint64),
                                         C.c_int, vp, C.c_uint64, C.POINTER(C.c_uint64), vp]
@@ -467,6 +470,50 @@ class Ctx:
         lst = lst[:n_l.value]
         empty = np.zeros(0, dtype=PAIR_DTYPE)
         return (res, empty, lst) if self.opts.want_lineage else (res, lst, empty)
+
+    def label_packed_rl(self, seqs=None, blob=None, offs=None, threads=4):
+        """kmat_label_batch_packed_rl: the compact interface with run-length lists, decoded back (kmat_list_decode) into the
+        pair arrays label_packed() returns.  Returns (results, candidates, lineage, words used)."""
+        if seqs is not None:
+            blob, offs = pack_reads(seqs)
+        n = len(offs) - 1
+        total = int(offs[n])
+        ptr = blob if isinstance(blob, (bytes, bytearray)) else blob.ctypes.data
+        codes = np.zeros(max(1, lib().kmat_pack_words(total)), dtype=np.uint32)
+        n_inv = C.c_uint64()
+        inv = np.zeros(1024, dtype=np.uint64)
+        rc = lib().kmat_pack_reads(ptr, total, threads, codes.ctypes.data, inv.ctypes.data, len(inv), C.byref(n_inv))
+        if rc == -10:
+            inv = np.zeros(n_inv.value, dtype=np.uint64)
+            rc = lib().kmat_pack_reads(ptr, total, threads, codes.ctypes.data, inv.ctypes.data, len(inv), C.byref(n_inv))
+        _check(rc)
+        res32 = np.zeros(n, dtype=RESULT32_DTYPE)
+        cap = max(4096, 16 * n)
+        n_w = C.c_uint64()
+        while True:
+            words = np.zeros(cap, dtype=np.uint32)
+            rc = lib().kmat_label_batch_packed_rl(self.h, codes.ctypes.data, inv.ctypes.data, n_inv.value, offs.ctypes.data, n, res32.ctypes.data,
+                                                  words.ctypes.data, len(words), C.byref(n_w))
+            if rc == -10:
+                cap = int(n_w.value) + 16
+                continue
+            _check(rc)
+            break
+        res = np.zeros(n, dtype=RESULT_DTYPE)
+        k = self.db.kmer_length
+        lst = np.zeros(max(1, int(res32["n_list"].astype(np.int64).sum())), dtype=PAIR_DTYPE)
+        at = 0
+        for i in range(n):
+            nl = int(res32["n_list"][i])
+            used = lib().kmat_list_decode(words[int(res32["list_off"][i]):].ctypes.data, nl, lst[at:].ctypes.data) if nl else 0
+            assert int(res32["list_off"][i]) + used <= n_w.value
+            r32 = res32[i:i + 1].copy()
+            r32["list_off"] = at
+            lib().kmat_result_expand(r32.ctypes.data, int(offs[i + 1] - offs[i]), k, self.opts.min_kmer, self.opts.want_lineage, res[i:i + 1].ctypes.data)
+            at += nl
+        lst = lst[:at]
+        empty = np.zeros(0, dtype=PAIR_DTYPE)
+        return ((res, empty, lst) if self.opts.want_lineage else (res, lst, empty)) + (int(n_w.value),)
 
     def tails(self, res, cands, lin, prn_all=True):
         out = []

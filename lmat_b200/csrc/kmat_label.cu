@@ -33,8 +33,8 @@
 #define KB_HHASH_BITS 15   // its taxid -> index hash: 2 * KB_CHUGE slots
 #define KB_HLIN (1u << 20) // lineage entries (candidate indices) one read's qualifying members may add up to
 #define KB_HUGEQ (1u << 16) // reads per pass the last-resort path takes
-#define KBH_WARPS 32       // warps (reads in flight) of km_cand_huge_kernel; KBH_THREADS reads in flight in km_score_huge_kernel
-#define KBH_THREADS 64
+#define KBH_WARPS 128      // warps (reads in flight) of km_cand_huge_kernel (2.8 MB of scratch each); KBH_THREADS reads in flight in
+#define KBH_THREADS 256    // km_score_huge_kernel (0.55 MB each): ~0.5 GB per context, so that a sample rich in such reads does not crawl
 #define KB_PASS_SHIFT 40   // per-pass cursor: pairs in the low 40 bits, reads queued for K4 above
 #define KB_PASS_MASK ((1ull << KB_PASS_SHIFT) - 1)
 #define KB_PASS_ONE_READ (1ull << KB_PASS_SHIFT)
@@ -1478,7 +1478,9 @@ struct kmat_ctx {
     int2 *d_hdr = nullptr; uint32_t cap_hdr = 0;
     kmat_read_result *d_out_dev = nullptr; uint32_t cap_out_dev = 0;   // kmat_label_batch_device with d_out == NULL
     kmat_pair *d_cands = nullptr, *d_lin = nullptr; uint64_t cap_cands = 0, cap_lin = 0;
-    unsigned long long *d_cursors = nullptr;     // [0] cands, [1] lineage, [2] text bytes (K5, kmat_format.cuh)
+    unsigned long long *d_cursors = nullptr;     // [0] cands, [1] lineage, [2] text bytes (K5, kmat_format.cuh), [3] run-length list words
+    uint32_t *d_plist = nullptr; uint64_t cap_plist = 0;     // the pair lists of a host-buffer call in run-length form (kmat_label_batch_packed_rl)
+    uint32_t max_tid = 0;                                    // largest taxid of the node universe (the run-length form needs bit 31 of a taxid)
     char *d_text = nullptr; uint64_t cap_text = 0;    // the tails of a host-buffer call formatted on the device
     uint32_t *d_pool2 = nullptr; int pool2_mul = 1;            // resolved lists (km_resolve_kernel)
     int resolved_max_count = -1, resolved_permissive = -1, resolved_rkmer = -1;
@@ -1604,9 +1606,9 @@ extern "C" int kmat_ctx_create(const kmat_db *db, const kmat_inputs *in, const k
         KM_CUDA(cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
         KM_CUDA(cudaEventCreateWithFlags(&sl.ev_comp, cudaEventDisableTiming));
         KM_CUDA(cudaEventCreateWithFlags(&sl.ev_d2h, cudaEventDisableTiming));
-        KM_CUDA(cudaMallocHost((void **)&sl.h_cur, 24));
+        KM_CUDA(cudaMallocHost((void **)&sl.h_cur, 32));
     }
-    KM_CUDA(cudaMalloc((void **)&c->d_cursors, 24));
+    KM_CUDA(cudaMalloc((void **)&c->d_cursors, 32));
     KM_CUDA(cudaMalloc((void **)&c->d_pass, 8));
     KM_CUDA(cudaMemset(c->d_pass, 0, 8));
     KM_CUDA(cudaMalloc((void **)&c->d_stats, sizeof(KmStatsDev)));
@@ -1619,6 +1621,7 @@ extern "C" int kmat_ctx_create(const kmat_db *db, const kmat_inputs *in, const k
     for (int i = 0; i < 3; i++) c->cand_grid[i] = std::max(1, per_sm[i]) * sms;
     rc = km_resolve_lists(c);
     if (rc != KMAT_OK) { kmat_ctx_destroy(c); return rc; }
+    for (const KmNodeA &na : c->h.nodeA) c->max_tid = std::max(c->max_tid, na.tid);
     *out = c;
     return KMAT_OK;
 }
@@ -1656,7 +1659,7 @@ extern "C" void kmat_ctx_destroy(kmat_ctx *c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (auto &e : c->ev_sub) if (e) cudaEventDestroy(e);
-    cudaFree(c->d_cands); cudaFree(c->d_lin); cudaFree(c->d_text); cudaFree(c->d_cursors); cudaFree(c->d_pool2); cudaFree(c->d_long_masks); cudaFree(c->d_long_sets); cudaFree(c->d_stats);
+    cudaFree(c->d_cands); cudaFree(c->d_lin); cudaFree(c->d_text); cudaFree(c->d_plist); cudaFree(c->d_cursors); cudaFree(c->d_pool2); cudaFree(c->d_long_masks); cudaFree(c->d_long_sets); cudaFree(c->d_stats);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
@@ -1712,7 +1715,7 @@ static int km_prepare_pass(kmat_ctx *c, const KmPass &L, cudaStream_t st, uint32
         }
     }
     if (L.reset) {
-        KM_CUDA(cudaMemsetAsync(c->d_cursors, 0, 24, st));
+        KM_CUDA(cudaMemsetAsync(c->d_cursors, 0, 32, st));
         if (c->collect_stats) KM_CUDA(cudaMemsetAsync(c->d_stats, 0, sizeof(KmStatsDev), st));
     }
     *hit = c->d_hit - L.first_off;
@@ -1758,7 +1761,7 @@ static int km_launch_cand_score(kmat_ctx *c, const KmPass &L, uint32_t r0, uint3
     if (!c->d_bigq) {
         KM_CUDA(cudaMalloc((void **)&c->d_bigq, ((size_t)2 * KB_BIGQ + 2 * KB_HUGEQ) * 4));
         KM_CUDA(cudaMalloc((void **)&c->d_bigcnt, 16));
-        // the last-resort path (more than KB_CBIG candidates): KBH_WARPS + KBH_THREADS scratch slots, ~120 MB
+        // the last-resort path (more than KB_CBIG candidates): KBH_WARPS + KBH_THREADS scratch slots, ~0.5 GB
         KM_CUDA(cudaMalloc((void **)&c->d_huge3, (size_t)KBH_WARPS * KBH_SLOT3_BYTES));
         KM_CUDA(cudaMalloc((void **)&c->d_huge4, (size_t)KBH_THREADS * KBH_SLOT4_BYTES));
     }
@@ -2042,6 +2045,48 @@ extern "C" void kmat_result_expand(const kmat_read_result32 *in, uint32_t read_l
     else if (out->status == KMAT_ST_NODBHITS) { out->n1 = (int32_t)read_len; out->n2 = kmer_length; }
 }
 
+// The pair list of a read in run-length form: equal scores are adjacent in rank_label (sorted by score) and in valid_cand
+// (a lineage chain), and a 150-base read's ~9 pairs carry ~2.5 distinct scores.  Word stream: a taxid with bit 31 set is followed
+// by the score (float bits) that holds for it and for the unflagged taxids after it.  8 B per pair -> ~5 B; the copy out is what
+// bounds eight GPUs behind one host (profiles/r03g_pipe_trace_n8.txt).  One thread per read; a warp takes one piece of the
+// pass's word buffer.  list_off of the 32-byte record becomes the read's word offset.
+__global__ void __launch_bounds__(256) km_pack_lists_kernel(kmat_read_result32 *out, uint32_t n, const kmat_pair *__restrict__ pairs,
+                                                            uint32_t *words, unsigned long long cap, unsigned long long *cursor) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint32_t nl = 0; const kmat_pair *src = nullptr;
+    if (i < n) { nl = out[i].n_list; src = pairs + out[i].list_off; }
+    uint32_t len = 0, prev = 0;
+    for (uint32_t j = 0; j < nl; j++) { const uint32_t b = __float_as_uint(src[j].score); len += (j == 0 || b != prev) ? 2u : 1u; prev = b; }
+    uint32_t incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(KM_FULL, incl, d); if (lane >= d) incl += v; }
+    const uint32_t total = __shfl_sync(KM_FULL, incl, 31);
+    unsigned long long at = 0;
+    if (lane == 0 && total) at = atomicAdd(cursor, (unsigned long long)total);
+    at = kb_shfl64(at, 0) + (incl - len);
+    if (i >= n) return;
+    out[i].list_off = (uint32_t)at;
+    if (at + len > cap) return;                                  // reported through the cursor
+    uint32_t *w = words + at;
+    for (uint32_t j = 0; j < nl; j++) {
+        const kmat_pair p = src[j];
+        const uint32_t b = __float_as_uint(p.score);
+        if (j == 0 || b != prev) { *w++ = p.tid | 0x80000000u; *w++ = b; } else *w++ = p.tid;
+        prev = b;
+    }
+}
+extern "C" uint32_t kmat_list_decode(const uint32_t *words, uint32_t n_list, kmat_pair *out) {
+    const uint32_t *w = words;
+    float sc = 0.0f;
+    for (uint32_t j = 0; j < n_list; j++) {
+        const uint32_t t = *w++;
+        if (t & 0x80000000u) { memcpy(&sc, w, 4); w++; }
+        out[j].tid = t & 0x7FFFFFFFu; out[j].score = sc;
+    }
+    return (uint32_t)(w - words);
+}
+
 #include "kmat_format.cuh"
 
 // Host buffers in, host buffers out.  The batch is cut into chunks; chunk i's kernels (one stream, in order, so the
@@ -2058,6 +2103,8 @@ struct KmHostIO {
     kmat_pair *lineage = nullptr; uint64_t lineage_cap = 0; uint64_t *n_lineage = nullptr;
     // K5 (kmat_label_batch_text): the tails of the output lines, formatted on the device
     char *text = nullptr; uint64_t text_cap = 0; uint64_t *n_text = nullptr; uint64_t *text_ref = nullptr; int prn_all = 0;
+    // compact front end, run-length lists (kmat_label_batch_packed_rl): the one pair list goes out as words instead of pairs
+    uint32_t *plist = nullptr; uint64_t plist_cap = 0; uint64_t *n_plist = nullptr;
 };
 static int km_label_host(kmat_ctx *c, const KmHostIO &io, const uint64_t *offs, uint32_t n_reads) {
     const char *bases = io.bases;
@@ -2085,7 +2132,11 @@ static int km_label_host(kmat_ctx *c, const KmHostIO &io, const uint64_t *offs, 
     const uint64_t text_room = io.text_ref ? std::min<uint64_t>(io.text_cap, c->cap_text) : 0;
     for (int attempt = 0; attempt < 3; attempt++) {
         if ((rc = km_reserve_cands(c, n_reads)) != KMAT_OK) return rc;
-        unsigned long long done_c = 0, done_l = 0, done_t = 0;      // candidate / lineage pairs and text bytes already copied out
+        if (io.plist) {                                   // at worst two words per pair
+            const uint64_t want = 2 * (c->opt.want_lineage ? c->cap_lin : c->cap_cands) + 64;
+            if (want > c->cap_plist) { KM_CUDA(cudaStreamSynchronize(c->stream)); KM_CUDA(cudaStreamSynchronize(c->st_d2h)); if ((rc = km_grow(&c->d_plist, &c->cap_plist, want)) != KMAT_OK) return rc; }
+        }
+        unsigned long long done_c = 0, done_l = 0, done_t = 0, done_p = 0;      // candidate / lineage pairs, text bytes and list words already copied out
         struct Chunk { uint32_t r0 = 0, r1 = 0; int slot = 0; bool valid = false; } prev;
         auto drain = [&](const Chunk &ch) -> int {      // results of a finished chunk -> caller buffers
             kmat_ctx::Slot &sl = c->slot[ch.slot];
@@ -2102,6 +2153,11 @@ static int km_label_host(kmat_ctx *c, const KmHostIO &io, const uint64_t *offs, 
                 KM_CUDA(cudaMemcpyAsync(lineage + done_l, c->d_lin + done_l, (size_t)(hi - done_l) * sizeof(kmat_pair), cudaMemcpyDeviceToHost, c->st_d2h));
             }
             done_c = std::max(done_c, cur_c); done_l = std::max(done_l, cur_l);
+            if (io.plist) {
+                const unsigned long long cur_p = std::min<unsigned long long>(std::min<unsigned long long>(sl.h_cur[3], c->cap_plist), io.plist_cap);
+                if (cur_p > done_p) KM_CUDA(cudaMemcpyAsync(io.plist + done_p, c->d_plist + done_p, (size_t)(cur_p - done_p) * 4, cudaMemcpyDeviceToHost, c->st_d2h));
+                done_p = std::max(done_p, cur_p);
+            }
             if (io.text_ref) {
                 const unsigned long long cur_t = std::min<unsigned long long>(sl.h_cur[2], text_room);
                 if (cur_t > done_t) KM_CUDA(cudaMemcpyAsync(io.text + done_t, c->d_text + done_t, (size_t)(cur_t - done_t), cudaMemcpyDeviceToHost, c->st_d2h));
@@ -2205,8 +2261,13 @@ static int km_label_host(kmat_ctx *c, const KmHostIO &io, const uint64_t *offs, 
                 km_compact_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(sl.d_out, n, c->opt.want_lineage, sl.d_out32);
                 g_km_launches++;
                 KM_CUDA(cudaGetLastError());
+                if (io.plist) {
+                    km_pack_lists_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(sl.d_out32, n, c->opt.want_lineage ? c->d_lin : c->d_cands, c->d_plist, c->cap_plist, c->d_cursors + 3);
+                    g_km_launches++;
+                    KM_CUDA(cudaGetLastError());
+                }
             }
-            KM_CUDA(cudaMemcpyAsync(sl.h_cur, c->d_cursors, 24, cudaMemcpyDeviceToHost, c->stream));
+            KM_CUDA(cudaMemcpyAsync(sl.h_cur, c->d_cursors, 32, cudaMemcpyDeviceToHost, c->stream));
             KM_CUDA(cudaEventRecord(sl.ev_comp, c->stream));
             if (trace) { tr_ev(&tr.back().k1, c->stream); tr.back().t_launched = now_ms() - t_host0; }
             if (prev.valid) {
@@ -2246,6 +2307,12 @@ static int km_label_host(kmat_ctx *c, const KmHostIO &io, const uint64_t *offs, 
         if (n_cands) *n_cands = total_c;
         if (n_lineage) *n_lineage = c->opt.want_lineage ? total_l : 0;
         if (io.n_text) *io.n_text = done_t;
+        if (io.plist) {
+            const unsigned long long total_p = c->slot[prev.slot].h_cur[3];
+            if (io.n_plist) *io.n_plist = total_p;
+            if (total_p >= (1ull << 32)) { kmat_set_error("compact interface: more than 2^32 list words in one call; split the batch"); return KMAT_ERR_UNSUPPORTED; }
+            if (total_p > io.plist_cap) { kmat_set_error("list buffer too small: need %llu words", total_p); return KMAT_ERR_OVERFLOW; }
+        }
         if ((rc = km_fetch_stats(c, c->stream)) != KMAT_OK) return rc;
         if (compact && std::max(total_c, total_l) >= (1ull << 32)) { kmat_set_error("compact interface: more than 2^32 pairs in one call; split the batch"); return KMAT_ERR_UNSUPPORTED; }
         if ((cands && total_c > cands_cap) || (lineage && c->opt.want_lineage && total_l > lineage_cap)) {
@@ -2290,6 +2357,18 @@ extern "C" int kmat_label_batch_packed(kmat_ctx *c, const uint32_t *codes, const
     io.codes = codes; io.inv = inv_pos; io.n_inv = n_inv; io.out32 = out;
     if (c->opt.want_lineage) { io.lineage = list; io.lineage_cap = list_cap; io.n_lineage = n_list; }
     else { io.cands = list; io.cands_cap = list_cap; io.n_cands = n_list; }
+    return km_label_host(c, io, offs, n_reads);
+}
+
+// kmat_label_batch_packed with the pair list in run-length form (km_pack_lists_kernel): list_off of a record is the offset of the
+// read's words in `words`, n_list the number of pairs kmat_list_decode rebuilds from them.
+extern "C" int kmat_label_batch_packed_rl(kmat_ctx *c, const uint32_t *codes, const uint64_t *inv_pos, uint64_t n_inv, const uint64_t *offs, uint32_t n_reads,
+                                          kmat_read_result32 *out, uint32_t *words, uint64_t words_cap, uint64_t *n_words) {
+    if (!c || !offs || !out || (n_reads && !codes) || (n_inv && !inv_pos) || (n_reads && !words)) { kmat_set_error("kmat_label_batch_packed_rl: bad argument"); return KMAT_ERR_ARG; }
+    if (c->max_tid & 0x80000000u) { kmat_set_error("kmat_label_batch_packed_rl: the taxonomy holds a taxid of 2^31 or more (the run-length form uses bit 31); use kmat_label_batch_packed"); return KMAT_ERR_UNSUPPORTED; }
+    KmHostIO io;
+    io.codes = codes; io.inv = inv_pos; io.n_inv = n_inv; io.out32 = out;
+    io.plist = words; io.plist_cap = words_cap; io.n_plist = n_words;
     return km_label_host(c, io, offs, n_reads);
 }
 

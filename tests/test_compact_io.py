@@ -81,3 +81,20 @@ def test_packed_labels_equal_ascii_labels(scen, opts, request):
     assert np.array_equal(res["valid_kmers"], r2["valid_kmers"]) and np.array_equal(res["status"], r2["status"])
     if scen == "golden_small" and opts in ("run_rl",):
         assert op.assemble_lines(hdrs[:-6], seqs[:-6], got[:-6]) == g.golden_out(opts)
+    # the run-length form of the lists (kmat_label_batch_packed_rl + kmat_list_decode): the same lines from fewer words
+    r3, c3, l3, n_words = ctx.label_packed_rl(seqs)
+    assert ctx.tails(r3, c3, l3, prn_all=prn_all) == want
+    n_pairs = len(c3) + len(l3)                         # the pairs the records refer to (the plain interface also ships the orphaned
+    ref2 = int((r2["n_lin"] if S.OPTION_SETS[opts]["prn_all"] is False else r2["n_cand"]).astype(np.int64).sum())   # pairs of PhiX / silent reads)
+    assert n_pairs == ref2 <= len(c2) + len(l2) and (n_pairs == 0 or n_pairs < n_words < 2 * n_pairs)
+
+
+def test_list_decode():
+    """kmat_list_decode: a taxid word with bit 31 set is followed by the score of it and of the unflagged taxids after it."""
+    f = lambda x: int(np.array([x], dtype=np.float32).view(np.uint32)[0])
+    words = np.array([0x80000000 | 562, f(1.5), 561, 543, 0x80000000 | 1224, f(-0.25), 0x80000000 | 2, f(1.5), 1], dtype=np.uint32)
+    out = np.zeros(6, dtype=api.PAIR_DTYPE)
+    used = api.lib().kmat_list_decode(words.ctypes.data, 6, out.ctypes.data)
+    assert used == 9
+    assert out["tid"].tolist() == [562, 561, 543, 1224, 2, 1] and out["score"].tolist() == [1.5, 1.5, 1.5, -0.25, 1.5, 1.5]
+    assert api.lib().kmat_list_decode(words.ctypes.data, 0, out.ctypes.data) == 0
