@@ -629,7 +629,8 @@ def main():
             if rc < 0:
                 raise api.KmatError(rc, L_.kmat_last_error().decode())
             t_res32 = torch.empty(n * api.RESULT32_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
-            t_list = torch.empty(max(1, 24 * n) * api.PAIR_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+            pairs_per_read = 24 + L // 40                      # ~10 candidates per 150-base read, ~100 per 10 kbp read
+            t_list = torch.empty(max(1, pairs_per_read * n) * api.PAIR_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
             list_cap = t_list.numel() // api.PAIR_DTYPE.itemsize
             n_w = C.c_uint64()
 
@@ -659,7 +660,7 @@ def main():
             del t_codes, t_inv, t_res32, t_list
             # ASCII interface
             t_res = torch.empty(n * api.RESULT_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
-            t_cands = torch.empty(max(1, 24 * n) * api.PAIR_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+            t_cands = torch.empty(max(1, pairs_per_read * n) * api.PAIR_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
             res = t_res.numpy().view(api.RESULT_DTYPE)
             cands = t_cands.numpy().view(api.PAIR_DTYPE)
 
