@@ -695,8 +695,13 @@ __global__ void __launch_bounds__(KM_PROBE_WARPS * 32) km_encode_probe_kernel(Km
 // packed word), phase 2 re-encodes, asks the set whether a window is the first occurrence and gathers the buckets of the
 // first occurrences, four chunks in flight per warp.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t km_fetch_left(uint32_t cur, uint32_t prv, int lane, int sh);     // below, with the short-read kernel
+// KEY: also the table key of the lane's k-mer when the table has a first level (the stateless sliding minimum: this chunk's
+// level-0 keys and those of the previous chunk's tail, w - 1 linear steps; host model in tests/mzr_check.cpp, 3d) -- the k-mer
+// need not be valid, every lane takes part in the shuffles
+template <bool KEY>
 __device__ __forceinline__ void kl_encode_chunk(const KmProbeParams &P, uint64_t off, int len, int c, int lane, int k, uint64_t kmask, int kmer_bits,
-                                                uint64_t &canon, bool &ok, bool &ok_prev, uint32_t &cgc_bit, int &gc_win) {
+                                                uint64_t &canon, bool &ok, bool &ok_prev, uint32_t &cgc_bit, int &gc_win, uint64_t *key = nullptr) {
     // the 32 bases of chunk c and of the chunk before it (re-read: they are in L1/L2), packed as in the any-length kernel
     const int j = (c << 5) + lane;
     const int code = j < len ? km_code((unsigned char)P.bases[off + j]) : -1;
@@ -715,9 +720,21 @@ __device__ __forceinline__ void kl_encode_chunk(const KmProbeParams &P, uint64_t
     ok = ((inv64 >> wsh) & wmask) == 0;
     ok_prev = wsh > 0 && ((inv64 >> (wsh - 1)) & wmask) == 0;
     canon = 0;
-    if (ok) { const uint64_t rc = km_revcomp(fwd, kmer_bits); canon = fwd < rc ? fwd : rc; }
+    bool fwd_is_canon = true;
+    if (ok) { const uint64_t rc = km_revcomp(fwd, kmer_bits); fwd_is_canon = fwd < rc; canon = fwd_is_canon ? fwd : rc; }
     cgc_bit = (cgc >> lane) & 1;
     gc_win = __popcll((gc64 >> wsh) & wmask);
+    if (KEY) {
+        const int lm = P.db.line_m;
+        if (lm) {
+            const int w = k - lm + 1;
+            const uint32_t hh = km_slide_hash(fwd, lm), hp = km_slide_hash(prev >> s, lm);       // the m-mer ending at this lane's base, here and one chunk back
+            const uint32_t r0 = km_slide_r0(hh), l0 = km_slide_l0(hh), r0p = km_slide_r0(hp), l0p = km_slide_l0(hp);
+            uint32_t kr = r0, kl = l0;
+            for (int d = 1; d < w; d++) { kr = km_slide_r(kr, km_fetch_left(r0, r0p, lane, d), d); kl = km_slide_l(kl, km_fetch_left(l0, l0p, lane, d), d); }
+            *key = ok ? km_line_x_of(canon, km_slide_finish(kr, kl, fwd, fwd_is_canon, k, lm), k, lm, P.db.line_bits) : 0ull;
+        } else *key = ok ? km_mix(canon, kmer_bits) : 0ull;
+    }
 }
 __device__ __forceinline__ uint32_t kl_slot(uint64_t canon) { return (uint32_t)((canon * 0x9E3779B97F4A7C15ull) >> 40) & (KM_LONG_SLOTS - 1); }
 
@@ -741,7 +758,7 @@ __global__ void __launch_bounds__(KM_LONG_THREADS, 1) km_encode_probe_long_kerne
         int valid = 0, vgc = 0, vtot = 0;
         for (int c = wid; c < nchunks; c += NW) {
             uint64_t canon; bool ok, ok_prev; uint32_t gcb; int gcw;
-            kl_encode_chunk(P, off, len, c, lane, k, kmask, kmer_bits, canon, ok, ok_prev, gcb, gcw);
+            kl_encode_chunk<false>(P, off, len, c, lane, k, kmask, kmer_bits, canon, ok, ok_prev, gcb, gcw);
             valid += ok; vtot += ok ? (ok_prev ? 1 : k) : 0; vgc += ok ? (ok_prev ? (int)gcb : gcw) : 0;
             if (ok) {
                 const int p = (c << 5) + lane - k + 1;
@@ -767,8 +784,8 @@ __global__ void __launch_bounds__(KM_LONG_THREADS, 1) km_encode_probe_long_kerne
                 bk[u][0] = bk[u][1] = bk[u][2] = bk[u][3] = 0;
                 const int c = c0 + u;
                 if (c >= nchunks) continue;                                   // warp-uniform
-                uint64_t canon; bool ok, ok_prev; uint32_t gcb; int gcw;
-                kl_encode_chunk(P, off, len, c, lane, k, kmask, kmer_bits, canon, ok, ok_prev, gcb, gcw);
+                uint64_t canon, key; bool ok, ok_prev; uint32_t gcb; int gcw;
+                kl_encode_chunk<true>(P, off, len, c, lane, k, kmask, kmer_bits, canon, ok, ok_prev, gcb, gcw, &key);
                 if (ok) {
                     const int p = (c << 5) + lane - k + 1;
                     uint32_t h = kl_slot(canon);
@@ -779,7 +796,7 @@ __global__ void __launch_bounds__(KM_LONG_THREADS, 1) km_encode_probe_long_kerne
                     }
                     if (first[u]) {
                         cn[u] = canon;
-                        xk[u] = km_key(P.db, canon);
+                        xk[u] = key;                                          // = km_key(P.db, canon), from the sliding minimum instead of the definition
                         if (P.do_probe) km_first_load(P.db, xk[u], owner[u], bk[u][0], bk[u][1], bk[u][2], bk[u][3]);
                     }
                 }

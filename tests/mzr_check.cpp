@@ -214,6 +214,56 @@ int main(int argc, char **argv) {
         }
         CHECK(n_checked > 100000, "sliding-minimum emulation checked too little");
     }
+    // 3d. the stateless form the LONG-read probe kernel uses: a warp sees one 32-base chunk and the packed bases of the chunk
+    //     before it, nothing else.  Level-0 keys of this chunk's lanes and of the previous chunk's lanes (its last w - 1 are
+    //     needed; their m-mers lie inside the previous chunk's 64-bit word for m <= 16 and lanes >= m - 1), then w - 1 linear
+    //     steps: min over d = 0 .. w - 1 of key(j - d) shifted by d.  Same minimizer records as the definition.
+    {
+        uint64_t n_checked = 0;
+        const int km[][2] = {{20, 13}, {20, 14}, {20, 15}, {20, 16}, {17, 16}, {18, 16}, {19, 16}, {21, 16}, {22, 16}, {23, 16}};
+        for (auto &g2 : km) {
+            const int k2 = g2[0], m2 = g2[1], w = k2 - m2 + 1;
+            const uint64_t kmask = (1ull << (2 * k2)) - 1;
+            for (int style = 0; style < 3; style++)
+                for (int rep = 0; rep < 40; rep++) {
+                    const std::string s = random_seq(257 + rnd() % 300, style);
+                    const int len = (int)s.size(), nch = (len + 31) / 32;
+                    for (int c = 0; c < nch; c++) {
+                        uint64_t cur = 0, prev = 0;                       // bases of chunk c / c - 1, base of lane 0 in the top two bits
+                        for (int lane = 0; lane < 32; lane++) {
+                            const int j = 32 * c + lane, jp = j - 32;
+                            cur |= (uint64_t)((j < len) ? s[j] : 0) << (62 - 2 * lane);
+                            prev |= (uint64_t)((jp >= 0) ? s[jp] : 0) << (62 - 2 * lane);
+                        }
+                        uint64_t fwd[32]; uint32_t r0[32], l0[32], r0p[32], l0p[32], kr[32], kl[32];
+                        for (int lane = 0; lane < 32; lane++) {
+                            const int sh = 62 - 2 * lane;
+                            fwd[lane] = ((cur >> sh) | (sh ? (prev << (64 - sh)) : 0ull)) & kmask;
+                            const uint32_t h = km_slide_hash(fwd[lane], m2), hp = km_slide_hash(prev >> sh, m2);
+                            r0[lane] = km_slide_r0(h); l0[lane] = km_slide_l0(h); r0p[lane] = km_slide_r0(hp); l0p[lane] = km_slide_l0(hp);
+                        }
+                        auto fetch = [&](const uint32_t *cu, const uint32_t *pv, int lane, int sh) { return lane >= sh ? cu[lane - sh] : pv[lane - sh + 32]; };
+                        for (int lane = 0; lane < 32; lane++) {
+                            uint32_t a = r0[lane], b = l0[lane];
+                            for (int d = 1; d < w; d++) { a = km_slide_r(a, fetch(r0, r0p, lane, d), d); b = km_slide_l(b, fetch(l0, l0p, lane, d), d); }
+                            kr[lane] = a; kl[lane] = b;
+                        }
+                        for (int lane = 0; lane < 32; lane++) {
+                            const int j = 32 * c + lane;
+                            if (j < k2 - 1 || j >= len) continue;
+                            const uint64_t rc = km_mzr_revcomp(fwd[lane], k2);
+                            const bool fc = fwd[lane] < rc;
+                            const uint64_t canon = fc ? fwd[lane] : rc;
+                            const KmMzr a = km_mzr_of(canon, k2, m2), z = km_slide_finish(kr[lane], kl[lane], fwd[lane], fc, k2, m2);
+                            CHECK(a.c == z.c && a.off == z.off && a.flip == z.flip, "stateless sliding minimum k=%d m=%d base %d: %u/%u/%u vs %u/%u/%u", k2, m2, j, a.c, a.off, a.flip, z.c, z.off, z.flip);
+                            CHECK(km_line_x_of(canon, z, k2, m2, 26) == km_line_x(canon, k2, m2, 26), "line key from the stateless sliding form");
+                            n_checked++;
+                        }
+                    }
+                }
+        }
+        CHECK(n_checked > 200000, "stateless sliding-minimum emulation checked too little");
+    }
     // 4. what the layout is for: requests made by the k-mers of a 150 bp read with a few substitutions -- one per distinct
     //    line of each 32-lane chunk (the lanes of a chunk issue their sector loads in one instruction) + second-level probes
     uint64_t reads = 0, kmers = 0, lines = 0, second = 0;
